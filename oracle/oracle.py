@@ -1,0 +1,219 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/liboracle.so) and of the
+reference-math library (oracle/_ref/libxsref.so, built from the reference's own headers).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this
+module.  The product package exastamp_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+class GridDesc(C.Structure):
+    """orc_grid_t (same field order as xsb_grid_desc's leading part)."""
+    _fields_ = [("dims", C.c_int32 * 3), ("ghost_layers", C.c_int32), ("cell_size", C.c_double),
+                ("origin", C.c_double * 3), ("xform", C.c_double * 9), ("xform_is_identity", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
+def build(force=False):
+    """make liboracle.so (+ _ref/libxsref.so when /root/reference exists)."""
+    need = force or not os.path.exists(os.path.join(HERE, "liboracle.so"))
+    if not need:
+        so_t = os.path.getmtime(os.path.join(HERE, "liboracle.so"))
+        for f in ("xs_oracle.cpp", "snap_oracle.cpp", "orc_math.h"):
+            p = os.path.join(HERE, f)
+            if os.path.exists(p) and os.path.getmtime(p) > so_t:
+                need = True
+    if need:
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/src/potential") and (force or not os.path.exists(os.path.join(HERE, "_ref", "libxsref.so"))):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(os.path.join(HERE, "liboracle.so"))
+        gp = C.POINTER(GridDesc)
+        L.orc_nbh_build.restype = C.c_void_p
+        L.orc_nbh_build.argtypes = [gp, _u64p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int]
+        L.orc_nbh_free.argtypes = [C.c_void_p]
+        L.orc_nbh_total_size.restype = C.c_uint64
+        L.orc_nbh_total_size.argtypes = [C.c_void_p]
+        L.orc_nbh_export.argtypes = [C.c_void_p, _u64p, C.c_void_p]
+        L.orc_nbh_import.restype = C.c_void_p
+        L.orc_nbh_import.argtypes = [C.c_uint64, _u64p, _u16p, C.c_int, C.c_int]
+        L.orc_nbh_decode.restype = C.c_uint64
+        L.orc_nbh_decode.argtypes = [gp, _u64p, C.c_void_p, _u32p, _u64p, C.c_void_p]
+        L.orc_nbh_bruteforce_counts.argtypes = [gp, C.c_uint64, _dp, _dp, _dp, C.c_double, _u32p]
+        vp = C.c_void_p
+        L.orc_pair_force.argtypes = [gp, _u64p, _dp, _dp, _dp, vp, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp, vp, vp]
+        L.orc_pair_multi_force.argtypes = [gp, _u64p, _dp, _dp, _dp, _u8p, vp, C.c_int, C.c_int, _dp, C.c_double, C.c_int,
+                                           _dp, _dp, _dp, vp, vp]
+        L.orc_eam_johnson.argtypes = [gp, _u64p, _dp, _dp, _dp, vp, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
+        L.orc_eam_alloy_load.restype = vp
+        L.orc_eam_alloy_load.argtypes = [C.c_char_p]
+        L.orc_eam_alloy_free.argtypes = [vp]
+        ip, dpp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        L.orc_eam_alloy_info.argtypes = [vp, ip, ip, ip, dpp, dpp, dpp, dpp]
+        L.orc_eam_alloy_table.restype = C.POINTER(C.c_double)
+        L.orc_eam_alloy_table.argtypes = [vp, C.c_int]
+        L.orc_eam_alloy_eval.restype = C.c_double
+        L.orc_eam_alloy_eval.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dpp]
+        L.orc_eam_alloy.argtypes = [gp, _u64p, _dp, _dp, _dp, _u8p, vp, vp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
+        L.orc_num_threads.restype = C.c_int
+        L.orc_ev_internal.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def ref():
+    """reference-math library; None when it was never built (no /root/reference and no prebuilt .so)."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(HERE, "_ref", "libxsref.so")
+        if not os.path.exists(p):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        dpp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+        R.xsref_lj.argtypes = [C.c_double, C.c_double, C.c_double, dpp, dpp]
+        R.xsref_johnson.argtypes = [_dp, C.c_int, C.c_double, dpp, dpp]
+        R.xsref_eam_alloy_load.restype = vp
+        R.xsref_eam_alloy_load.argtypes = [C.c_char_p, C.c_int]
+        R.xsref_eam_alloy_free.argtypes = [vp]
+        R.xsref_eam_alloy_info.argtypes = [vp, ip, ip, ip, dpp, dpp, dpp, dpp]
+        R.xsref_eam_alloy_table.restype = C.POINTER(C.c_double)
+        R.xsref_eam_alloy_table.argtypes = [vp, C.c_int]
+        R.xsref_eam_alloy_eval.restype = C.c_double
+        R.xsref_eam_alloy_eval.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dpp]
+        R.xsref_ev_internal.restype = C.c_double
+        _ref = R
+    return _ref
+
+
+def make_grid(dims, ghost_layers, cell_size, origin, xform=None):
+    g = GridDesc()
+    g.dims[:] = [int(d) for d in dims]
+    g.ghost_layers = int(ghost_layers)
+    g.cell_size = float(cell_size)
+    g.origin[:] = [float(o) for o in origin]
+    X = np.eye(3) if xform is None else np.asarray(xform, dtype=np.float64).reshape(3, 3)
+    g.xform[:] = [float(v) for v in X.ravel()]
+    g.xform_is_identity = int(np.array_equal(X, np.eye(3)))
+    return g
+
+
+class Neighbors:
+    """chunk_neighbors list held by the oracle (reference uint16 stream per cell)."""
+
+    def __init__(self, handle, grid, cell_off, chunk_size, has_offsets):
+        self.h, self.grid, self.cell_off = handle, grid, cell_off
+        self.chunk_size, self.has_offsets = chunk_size, has_offsets
+
+    @classmethod
+    def build(cls, grid, cell_off, rx, ry, rz, nbh_dist_lab, chunk_size=1, build_particle_offset=True):
+        h = lib().orc_nbh_build(C.byref(grid), cell_off, rx, ry, rz, float(nbh_dist_lab), int(chunk_size), int(build_particle_offset))
+        return cls(h, grid, cell_off, chunk_size, build_particle_offset)
+
+    @classmethod
+    def from_streams(cls, grid, cell_off, stream_off, data, chunk_size=1, has_offsets=True):
+        h = lib().orc_nbh_import(len(stream_off) - 1, np.ascontiguousarray(stream_off, dtype=np.uint64),
+                                 np.ascontiguousarray(data, dtype=np.uint16), int(chunk_size), int(has_offsets))
+        return cls(h, grid, cell_off, chunk_size, has_offsets)
+
+    def export(self):
+        ncells = len(self.cell_off) - 1
+        off = np.zeros(ncells + 1, dtype=np.uint64)
+        lib().orc_nbh_export(self.h, off, None)
+        data = np.zeros(int(off[-1]), dtype=np.uint16)
+        lib().orc_nbh_export(self.h, off, data.ctypes.data_as(C.c_void_p))
+        return off, data
+
+    def decode(self):
+        """(counts[N], idx_off[N+1], idx[total]) flat CSR in stream-traversal order."""
+        n = int(self.cell_off[-1])
+        counts = np.zeros(n, dtype=np.uint32)
+        idx_off = np.zeros(n + 1, dtype=np.uint64)
+        tot = lib().orc_nbh_decode(C.byref(self.grid), self.cell_off, self.h, counts, idx_off, None)
+        idx = np.zeros(int(tot), dtype=np.uint32)
+        lib().orc_nbh_decode(C.byref(self.grid), self.cell_off, self.h, counts, idx_off, idx.ctypes.data_as(C.c_void_p))
+        return counts, idx_off, idx
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_nbh_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pair_force(grid, cell_off, rx, ry, rz, nbh, params, rcut, ghost, fx, fy, fz, ep=None, vir=None, pot=0):
+    lib().orc_pair_force(C.byref(grid), cell_off, rx, ry, rz, nbh.h, pot, np.ascontiguousarray(params, dtype=np.float64),
+                         float(rcut), int(ghost), fx, fy, fz, _opt(ep), _opt(vir))
+
+
+def pair_multi_force(grid, cell_off, rx, ry, rz, typ, nbh, pair_params, rcut_max, ghost, fx, fy, fz, ep=None, vir=None, pot=0):
+    pp = np.ascontiguousarray(pair_params, dtype=np.float64)
+    lib().orc_pair_multi_force(C.byref(grid), cell_off, rx, ry, rz, typ, nbh.h, pot, pp.shape[0], pp, float(rcut_max), int(ghost),
+                               fx, fy, fz, _opt(ep), _opt(vir))
+
+
+def eam_johnson(grid, cell_off, rx, ry, rz, nbh, params19, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb):
+    lib().orc_eam_johnson(C.byref(grid), cell_off, rx, ry, rz, nbh.h, np.ascontiguousarray(params19, dtype=np.float64), float(rcut),
+                          int(flags), fx, fy, fz, ep, _opt(vir), rho_dEmb)
+
+
+class EamAlloy:
+    def __init__(self, path, use_ref=False):
+        self.use_ref = use_ref
+        self.L = ref() if use_ref else lib()
+        self.pre = "xsref_" if use_ref else "orc_"
+        load = getattr(self.L, self.pre + "eam_alloy_load")
+        self.h = load(path.encode(), 0) if use_ref else load(path.encode())
+        if not self.h:
+            raise IOError("cannot read setfl file %s" % path)
+        ne, nr, nrho = C.c_int(), C.c_int(), C.c_int()
+        rdr, rdrho, rc, rhomax = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        getattr(self.L, self.pre + "eam_alloy_info")(self.h, ne, nr, nrho, rdr, rdrho, rc, rhomax)
+        self.nelements, self.nr, self.nrho = ne.value, nr.value, nrho.value
+        self.rdr, self.rdrho, self.rc, self.rhomax = rdr.value, rdrho.value, rc.value, rhomax.value
+
+    def table(self, which):
+        n = {0: self.nelements * (self.nrho + 1), 1: self.nelements * (self.nr + 1),
+             2: self.nelements * (self.nelements + 1) // 2 * (self.nr + 1)}[which]
+        p = getattr(self.L, self.pre + "eam_alloy_table")(self.h, which)
+        return np.ctypeslib.as_array(p, shape=(n, 8)).copy()
+
+    def eval(self, what, x, ti=0, tj=0, fpi=0.0, fpj=0.0):
+        o2 = C.c_double()
+        v = getattr(self.L, self.pre + "eam_alloy_eval")(self.h, what, float(x), ti, tj, float(fpi), float(fpj), o2)
+        return v, o2.value
+
+
+def eam_alloy(grid, cell_off, rx, ry, rz, typ, nbh, eam, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb):
+    assert not eam.use_ref
+    lib().orc_eam_alloy(C.byref(grid), cell_off, rx, ry, rz, typ, nbh.h, eam.h, float(rcut), int(flags), fx, fy, fz, ep, _opt(vir), rho_dEmb)

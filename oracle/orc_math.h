@@ -1,0 +1,260 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle, never linked into or called by the product path.
+//
+// orc_math.h : plain C++ restatement of the per-pair / per-atom arithmetic of the exaStamp
+// short-range force operators.  Every function cites the reference file:line it follows
+// (paths relative to /root/reference).  The restatement is pinned by tests/test_oracle_math.py
+// against oracle/_ref/libxsref.so, which compiles the reference's own unmodified headers.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace orc
+{
+
+// ---------------------------------------------------------------------------------------------
+// internal unit system: angstrom, Dalton, picosecond, e, K (include/exaStamp/unit_system.h:28-36)
+// => energy unit Da.ang^2/ps^2.  onika's constant table is external (not vendored); CODATA-2018
+// values are used here and in the product library (one place each), so both sides agree.
+// ---------------------------------------------------------------------------------------------
+static constexpr double ELEMENTARY_CHARGE_C = 1.602176634e-19;
+static constexpr double ATOMIC_MASS_KG      = 1.66053906660e-27;
+static constexpr double EV_INTERNAL         = ELEMENTARY_CHARGE_C / ( ATOMIC_MASS_KG * 1.0e4 ); // 1 eV
+static constexpr double EV_ANG_INTERNAL     = EV_INTERNAL;                                       // 1 eV.ang
+
+// src/potential/pair_potentials/lennard_jones/include/.../lennard_jones.h:40-50
+struct LJParams { double epsilon, sigma; };
+static inline void lj_compute_energy(const LJParams& p, double r, double& e, double& de)
+{
+  const double ratio   = p.sigma / r;
+  const double ratio2  = ratio * ratio;
+  const double ratio6  = ratio2 * ratio2 * ratio2;
+  const double ratio12 = ratio6 * ratio6;
+  e  = 4. * p.epsilon * (ratio12 - ratio6);
+  de = ( -24. * p.epsilon * (2. * ratio12 - ratio6) ) / r;
+}
+
+// src/potential/pair_potential_template/pair_potential_impl.hxx:488-498 (energy_cutoff)
+static inline double lj_energy_cutoff(const LJParams& p, double rcut)
+{
+  double e = 0.0, de = 0.0;
+  if( rcut > 0.0 ) lj_compute_energy(p, rcut, e, de);
+  return e;
+}
+
+// src/potential/eam_potentials/johnson/johnson.h:29-50 (19 scalars, same order)
+struct JohnsonParams
+{
+  double re, fe, rhoe, alpha, beta, A, B, kappa, lambda, Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, Fo, eta;
+};
+
+// johnson.h:56-91
+static inline void johnson_phi(const JohnsonParams& p, double r, double& phi, double& dphi)
+{
+  const int n = 20, m = 20;
+  const double x = r / p.re, ire = 1. / p.re;
+  double c1 = p.A * std::exp(-p.alpha * (x - 1.));
+  double c2 = x - p.kappa;
+  double c3 = std::pow(c2, m);
+  double num = c1, den = 1. + c3;
+  double dnum = -p.alpha * c1, dden = m * c3 / c2;
+  phi  = num / den;
+  dphi = ire * (dnum * den - num * dden) / (den * den);
+  c1 = -p.B * std::exp(-p.beta * (x - 1.));
+  c2 = x - p.lambda;
+  c3 = std::pow(c2, n);
+  num = c1; den = 1. + c3;
+  dnum = -p.beta * c1; dden = n * c3 / c2;
+  phi  += num / den;
+  dphi += ire * (dnum * den - num * dden) / (den * den);
+}
+
+// johnson.h:97-114
+static inline void johnson_rho(const JohnsonParams& p, double r, double& rho, double& drho)
+{
+  const int n = 20;
+  const double x = r / p.re, ire = 1. / p.re;
+  const double c1 = p.fe * std::exp(-p.beta * (x - 1.));
+  const double c2 = x - p.lambda;
+  const double c3 = std::pow(c2, n);
+  const double num = c1, den = 1. + c3;
+  const double dnum = -p.beta * c1, dden = n * c3 / c2;
+  rho  = num / den;
+  drho = ire * (dnum * den - num * dden) / (den * den);
+}
+
+// johnson.h:120-166
+static inline void johnson_fEmbed(const JohnsonParams& p, double rho, double& f, double& df)
+{
+  const double rhon = 0.85 * p.rhoe, rho0 = 1.15 * p.rhoe;
+  const double irhon = 1. / rhon, irhoe = 1. / p.rhoe;
+  if( rho < rhon )
+  {
+    const double q1 = rho / rhon - 1., q2 = q1 * q1, q3 = q1 * q2;
+    f  = p.Fn0 + p.Fn1 * q1 + p.Fn2 * q2 + p.Fn3 * q3;
+    df = p.Fn1 + 2. * p.Fn2 * q1 + 3. * p.Fn3 * q2;
+    df *= irhon;
+  }
+  else if( rho < rho0 )
+  {
+    const double q1 = rho * irhoe - 1., q2 = q1 * q1, q3 = q1 * q2;
+    f  = p.F0 + p.F1 * q1 + p.F2 * q2 + p.F3 * q3;
+    df = p.F1 + 2. * p.F2 * q1 + 3. * p.F3 * q2;
+    df *= irhoe;
+  }
+  else
+  {
+    const double raprho = rho * irhoe;
+    const double rpe = std::pow(raprho, p.eta);
+    const double lrpe = std::log(rpe);
+    f  = p.Fo * (1. - lrpe) * rpe;
+    df = -p.eta * rpe + (1. - lrpe) * p.eta * rpe;
+    df *= p.Fo * irhoe / raprho;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eam/alloy (setfl) tables, LAMMPS pair_eam 7-coefficient splines.
+// reader: src/potential/eam_potentials/eam_alloy/eam_alloy.cpp:66-278 ; interpolate :29-58 ;
+// evaluation eam_alloy.h:185-313 ; type tables eam_alloy.h:70-133.
+// Rows are stored 8 doubles wide like SplineCoeffs (eam_alloy.h:37-42); row 0 is unused.
+// ---------------------------------------------------------------------------------------------
+struct EamAlloy
+{
+  int nelements = 0, nr = 0, nrho = 0;
+  double rdr = 0, rdrho = 0, rc = 0, rhomax = 0, dr = 0, drho = 0;
+  std::vector<std::string> names;
+  std::vector<double> mass;
+  std::vector<double> frho;  // [nelements][nrho+1][8]
+  std::vector<double> rhor;  // [nelements][nr+1][8]
+  std::vector<double> z2r;   // [nelements(nelements+1)/2][nr+1][8]
+  double conv_z2r = EV_ANG_INTERNAL, conv_frho = EV_INTERNAL;
+
+  // type maps of eam_alloy.h:70-133 collapse (map[i]=i-1) to: rhor(i,j) -> table i ;
+  // z2r(i,j) -> hi*(hi+1)/2+lo ; frho(i) -> table i  (0-based types)
+  static inline int z2r_index(int a, int b) { int hi = a > b ? a : b, lo = a > b ? b : a; return hi * (hi + 1) / 2 + lo; }
+};
+
+static inline void eam_interpolate(int n, double delta, const double* f /*[n+1], 1-based*/, double* s /*[n+1][8]*/)
+{
+  auto S = [&](int m, int k) -> double& { return s[size_t(m) * 8 + k]; };
+  for(int m = 1; m <= n; m++) S(m,6) = f[m];
+  S(1,5)   = S(2,6) - S(1,6);
+  S(2,5)   = 0.5 * (S(3,6) - S(1,6));
+  S(n-1,5) = 0.5 * (S(n,6) - S(n-2,6));
+  S(n,5)   = S(n,6) - S(n-1,6);
+  for(int m = 3; m <= n - 2; m++) S(m,5) = ((S(m-2,6) - S(m+2,6)) + 8.0 * (S(m+1,6) - S(m-1,6))) / 12.0;
+  for(int m = 1; m <= n - 1; m++)
+  {
+    S(m,4) = 3.0 * (S(m+1,6) - S(m,6)) - 2.0 * S(m,5) - S(m+1,5);
+    S(m,3) = S(m,5) + S(m+1,5) - 2.0 * (S(m+1,6) - S(m,6));
+  }
+  S(n,4) = 0.0; S(n,3) = 0.0;
+  for(int m = 1; m <= n; m++)
+  {
+    S(m,2) = S(m,5) / delta;
+    S(m,1) = 2.0 * S(m,4) / delta;
+    S(m,0) = 3.0 * S(m,3) / delta;
+  }
+}
+
+static inline bool eam_alloy_read(const char* path, EamAlloy& v)
+{
+  std::ifstream file(path);
+  if( !file ) return false;
+  for(int i = 0; i < 3; i++) file.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
+  size_t nel = 0; file >> nel;
+  v.names.resize(nel); v.mass.resize(nel);
+  for(size_t i = 0; i < nel; i++) file >> v.names[i];
+  size_t nrho = 0, nr = 0; double drho = 0, dr = 0, rcut = 0;
+  file >> nrho >> drho >> nr >> dr >> rcut;
+  if( !file || nel == 0 || nr < 5 || nrho < 5 ) return false;
+  v.nelements = int(nel); v.nr = int(nr); v.nrho = int(nrho);
+  v.dr = dr; v.drho = drho; v.rdr = 1.0 / dr; v.rdrho = 1.0 / drho; v.rc = rcut; v.rhomax = (nrho - 1) * drho;
+  const size_t nz2r = nel * (nel + 1) / 2;
+  std::vector<std::vector<double>> frho(nel), rhor(nel), z2r(nz2r);
+  for(size_t i = 0; i < nel; i++)
+  {
+    int z; double mass, a0; std::string st;
+    file >> z >> mass >> a0 >> st;
+    v.mass[i] = mass;
+    frho[i].assign(nrho + 1, 0.0); rhor[i].assign(nr + 1, 0.0);
+    for(size_t k = 0; k < nrho; k++) file >> frho[i][k + 1];
+    for(size_t k = 0; k < nr; k++) file >> rhor[i][k + 1];
+  }
+  for(size_t i = 0; i < nz2r; i++)
+  {
+    z2r[i].assign(nr + 1, 0.0);
+    for(size_t k = 0; k < nr; k++) file >> z2r[i][k + 1];
+  }
+  if( !file ) return false;
+  v.frho.assign(nel * (nrho + 1) * 8, 0.0);
+  v.rhor.assign(nel * (nr + 1) * 8, 0.0);
+  v.z2r.assign(nz2r * (nr + 1) * 8, 0.0);
+  for(size_t i = 0; i < nel; i++)  eam_interpolate(int(nrho), drho, frho[i].data(), v.frho.data() + i * (nrho + 1) * 8);
+  for(size_t i = 0; i < nel; i++)  eam_interpolate(int(nr), dr, rhor[i].data(), v.rhor.data() + i * (nr + 1) * 8);
+  for(size_t i = 0; i < nz2r; i++) eam_interpolate(int(nr), dr, z2r[i].data(), v.z2r.data() + i * (nr + 1) * 8);
+  return true;
+}
+
+// eam_alloy.h:185-207 : rho contribution, table of element `itype`
+static inline double eam_alloy_rho_noderiv(const EamAlloy& eam, double r, int itype, int /*jtype*/)
+{
+  double p = r * eam.rdr + 1.0;
+  int m = static_cast<int>(p);
+  m = std::min(m, eam.nr - 1);
+  p -= m;
+  p = std::min(p, 1.0);
+  const double* c = eam.rhor.data() + (size_t(itype) * (eam.nr + 1) + m) * 8;
+  return ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+}
+
+// eam_alloy.h:211-265 : returns fpair (reference multiplies dr in place) and phi
+static inline double eam_alloy_mm_force(const EamAlloy& eam, double& phi, double r, double fpi, double fpj, int itype, int jtype)
+{
+  double p = r * eam.rdr + 1.0;
+  int m = static_cast<int>(p);
+  m = std::min(m, eam.nr - 1);
+  p -= m;
+  p = std::min(p, 1.0);
+  const double* ci = eam.rhor.data() + (size_t(itype) * (eam.nr + 1) + m) * 8;
+  const double rhoip = (ci[0] * p + ci[1]) * p + ci[2];
+  const double* cj = eam.rhor.data() + (size_t(jtype) * (eam.nr + 1) + m) * 8;
+  const double rhojp = (cj[0] * p + cj[1]) * p + cj[2];
+  const double* c = eam.z2r.data() + (size_t(EamAlloy::z2r_index(itype, jtype)) * (eam.nr + 1) + m) * 8;
+  const double z2p = (c[0] * p + c[1]) * p + c[2];
+  const double z2  = ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+  const double recip = 1.0 / r;
+  phi = z2 * recip;
+  const double phip = (z2p * recip - phi * recip) * eam.conv_z2r;
+  phi *= eam.conv_z2r;
+  const double psip = fpi * rhojp + fpj * rhoip + phip;
+  return psip * recip;
+}
+
+// eam_alloy.h:289-313
+static inline void eam_alloy_fEmbed(const EamAlloy& eam, double rho, double& phi, double& fp, int itype)
+{
+  double p = rho * eam.rdrho + 1.0;
+  int m = static_cast<int>(p);
+  m = std::max(1, std::min(m, eam.nrho - 1));
+  p -= m;
+  p = std::min(p, 1.0);
+  const double* c = eam.frho.data() + (size_t(itype) * (eam.nrho + 1) + m) * 8;
+  fp  = (c[0] * p + c[1]) * p + c[2];
+  phi = ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+  if( rho > eam.rhomax ) phi += fp * (rho - eam.rhomax);
+  phi *= eam.conv_frho;
+  fp  *= eam.conv_frho;
+}
+
+// ext exanb unique_pair_id (symmetric triangular index; used at
+// pair_potential_force_op_multiparam.h:94 and eam_force_op_multimat.h:148)
+static inline unsigned unique_pair_id(unsigned a, unsigned b) { if( a > b ) { unsigned t = a; a = b; b = t; } return b * (b + 1) / 2 + a; }
+
+} // namespace orc

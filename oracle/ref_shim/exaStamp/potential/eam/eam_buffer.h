@@ -1,0 +1,3 @@
+#pragma once
+#include "../../../xsref_common.h"
+namespace exanb {}

@@ -1,0 +1,82 @@
+"""Test/bench helpers: synthetic lattices and a numpy statement of the cell grid with materialised periodic
+ghost particles (what exaNBody's grid + ghost_update_* give the force operators)."""
+import numpy as np
+
+
+def lattice(structure, ncells, a, noise_sigma=0.0, seed=1, types=None):
+    """perfect lattice + Gaussian noise (decks: lattice + gaussian_noise_r).  Returns pos[N,3] in [0,L), type[N], box[3]."""
+    basis = {"FCC": [[0.25, 0.25, 0.25], [0.25, 0.75, 0.75], [0.75, 0.25, 0.75], [0.75, 0.75, 0.25]],
+             "BCC": [[0.25, 0.25, 0.25], [0.75, 0.75, 0.75]],
+             "SC": [[0.5, 0.5, 0.5]]}[structure.upper()]
+    nc = np.array([ncells] * 3 if np.isscalar(ncells) else ncells, dtype=np.int64)
+    i, j, k = np.meshgrid(np.arange(nc[0]), np.arange(nc[1]), np.arange(nc[2]), indexing="ij")
+    cells = np.stack([i.ravel(), j.ravel(), k.ravel()], axis=1).astype(np.float64)
+    pos = (cells[:, None, :] + np.asarray(basis)[None, :, :]).reshape(-1, 3) * a
+    nb = len(basis)
+    if types is None:
+        typ = np.zeros(len(pos), dtype=np.uint8)
+    else:
+        typ = np.tile(np.asarray(types, dtype=np.uint8), len(pos) // nb)
+    box = nc.astype(np.float64) * a
+    if noise_sigma > 0:
+        rng = np.random.default_rng(seed)
+        pos = pos + rng.normal(0.0, noise_sigma, pos.shape)
+        pos = np.mod(pos, box)
+        pos = np.where(pos >= box, 0.0, pos)
+    return np.ascontiguousarray(pos), typ, box
+
+
+class GridSystem:
+    """flat SoA sorted by cell (IJK, i fastest) including ghost cells filled with periodic images."""
+
+    def __init__(self, pos, typ, box, cell_size, ghost_layers, xform=None):
+        pos = np.asarray(pos, dtype=np.float64)
+        box = np.asarray(box, dtype=np.float64)
+        n_own = np.maximum(1, np.floor(box / cell_size + 1e-9).astype(np.int64))
+        self.cell_size = float(cell_size)
+        # cells must tile the box exactly for periodic wrap; callers pick cell_size = box / integer
+        assert np.allclose(n_own * cell_size, box), "cell_size must divide the box"
+        gl = int(ghost_layers)
+        self.gl, self.n_own, self.box = gl, n_own, box
+        self.dims = n_own + 2 * gl
+        self.origin = -gl * self.cell_size * np.ones(3)
+        self.xform = np.eye(3) if xform is None else np.asarray(xform, dtype=np.float64)
+        nx, ny, nz = [int(d) for d in self.dims]
+        ncells = nx * ny * nz
+        ijk = np.clip(np.floor(pos / cell_size).astype(np.int64), 0, n_own - 1) + gl
+        cid = ijk[:, 0] + nx * (ijk[:, 1] + ny * ijk[:, 2])
+        order = np.argsort(cid, kind="stable")
+        own_count = np.bincount(cid, minlength=ncells)
+        own_start = np.concatenate([[0], np.cumsum(own_count)])
+        # every cell (own or ghost) mirrors an own cell: wrap per axis
+        ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+        # flat order must be i fastest
+        ci, cj, ck = [np.transpose(a, (2, 1, 0)).ravel() for a in (ci, cj, ck)]
+        cc = np.stack([ci, cj, ck], axis=1)
+        wrapn = np.floor_divide(cc - gl, n_own)
+        src = (cc - gl) - wrapn * n_own + gl
+        src_cid = src[:, 0] + nx * (src[:, 1] + ny * src[:, 2])
+        counts = own_count[src_cid]
+        self.cell_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        ntot = int(self.cell_off[-1])
+        # for each output particle: index into the sorted-own array
+        cell_of = np.repeat(np.arange(ncells), counts)
+        within = np.arange(ntot) - np.repeat(self.cell_off[:-1].astype(np.int64), counts)
+        src_sorted = own_start[src_cid[cell_of]] + within
+        self.src_index = order[src_sorted]              # index into the caller's original arrays
+        shift = (wrapn[cell_of] * box[None, :]).astype(np.float64)
+        p = pos[self.src_index] + shift
+        self.rx = np.ascontiguousarray(p[:, 0]); self.ry = np.ascontiguousarray(p[:, 1]); self.rz = np.ascontiguousarray(p[:, 2])
+        self.type = np.ascontiguousarray(np.asarray(typ, dtype=np.uint8)[self.src_index])
+        self.is_ghost = np.any(wrapn[cell_of] != 0, axis=1)
+        self.ghost_cell = np.any(wrapn != 0, axis=1)
+        self.n = ntot
+        self.n_owned = int((~self.is_ghost).sum())
+        self.ncells = ncells
+
+    def oracle_grid(self):
+        from oracle import oracle as O
+        return O.make_grid(self.dims, self.gl, self.cell_size, self.origin, self.xform)
+
+    def zeros(self):
+        return np.zeros(self.n, dtype=np.float64)
