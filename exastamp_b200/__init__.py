@@ -1,0 +1,263 @@
+"""exastamp_b200 -- thin ctypes binding of libxsb200.so (the C ABI declared in include/xsb200.h).
+
+The package holds no numerics of its own: every operator call goes through the C ABI into hand-written
+sm_100a CUDA kernels.  There is no CPU fallback -- importing works without a GPU (so the build check and the
+symbol tests can run), but creating a Context or calling any operator without the library / a B200 raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxsb200.so")
+
+# xsb_field
+F_RX, F_RY, F_RZ, F_FX, F_FY, F_FZ, F_EP, F_VX, F_VY, F_VZ, F_VIRIAL, F_RHO_DEMB, F_TYPE, F_ID = range(14)
+FLAG_GHOST, FLAG_ENERGY, FLAG_VIRIAL, FLAG_MIXED = 1, 2, 4, 8
+EAM_RHO, EAM_RHO2EMB, EAM_GHOST, EAM_FORCE, EAM_EFLAG = 1, 2, 4, 8, 16
+POT_LJ = 0
+_FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
+
+# every symbol include/xsb200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "xsb_create", "xsb_destroy", "xsb_last_error", "xsb_sync", "xsb_version", "xsb_kernel_launch_count",
+    "xsb_grid_set", "xsb_particles_set_cells", "xsb_num_particles", "xsb_num_cells", "xsb_field_upload",
+    "xsb_field_download", "xsb_field_device_ptr", "xsb_zero_force_energy",
+    "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
+    "xsb_chunk_neighbors_export", "xsb_chunk_neighbors_download_flat",
+    "xsb_pair_force", "xsb_pair_multi_force", "xsb_eam_johnson_force",
+    "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
+    "xsb_comm_unique_id", "xsb_comm_init", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
+]
+
+
+class XsbError(RuntimeError):
+    pass
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("dims", C.c_int32 * 3), ("ghost_layers", C.c_int32), ("cell_size", C.c_double),
+                ("origin", C.c_double * 3), ("xform", C.c_double * 9), ("xform_is_identity", C.c_int32),
+                ("pad_", C.c_int32)]
+
+
+class ChunkNeighborsConfig(C.Structure):
+    _fields_ = [("chunk_size", C.c_int32), ("build_particle_offset", C.c_int32), ("subcell_compaction", C.c_int32),
+                ("free_scratch_memory", C.c_int32), ("stream_prealloc_factor", C.c_double)]
+
+
+class EamAlloyTables(C.Structure):
+    _fields_ = [("nelements", C.c_int32), ("nr", C.c_int32), ("nrho", C.c_int32), ("pad_", C.c_int32),
+                ("rdr", C.c_double), ("rdrho", C.c_double), ("rc", C.c_double), ("rhomax", C.c_double),
+                ("conversion_z2r", C.c_double), ("conversion_frho", C.c_double),
+                ("frho", C.POINTER(C.c_double)), ("rhor", C.POINTER(C.c_double)), ("z2r", C.POINTER(C.c_double))]
+
+
+class DomainDesc(C.Structure):
+    _fields_ = [("global_cells", C.c_int32 * 3), ("periodic", C.c_int32 * 3), ("rank_dims", C.c_int32 * 3),
+                ("rank_coord", C.c_int32 * 3), ("box", C.c_double * 3)]
+
+
+_lib = None
+
+
+def build():
+    from . import buildlib as _b
+    return _b.build()
+
+
+def load_library():
+    """dlopen libxsb200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XsbError("libxsb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                       "exastamp_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64, dbl = C.c_void_p, C.c_int, C.c_uint64, C.c_double
+    L.xsb_create.argtypes = [i32, C.POINTER(vp)]
+    L.xsb_destroy.argtypes = [vp]
+    L.xsb_last_error.restype = C.c_char_p
+    L.xsb_last_error.argtypes = [vp]
+    L.xsb_version.restype = C.c_char_p
+    L.xsb_sync.argtypes = [vp]
+    L.xsb_kernel_launch_count.restype = u64
+    L.xsb_kernel_launch_count.argtypes = [vp]
+    L.xsb_grid_set.argtypes = [vp, C.POINTER(GridDesc)]
+    L.xsb_particles_set_cells.argtypes = [vp, vp]
+    L.xsb_num_particles.restype = u64
+    L.xsb_num_particles.argtypes = [vp]
+    L.xsb_num_cells.restype = u64
+    L.xsb_num_cells.argtypes = [vp]
+    L.xsb_field_upload.argtypes = [vp, i32, vp]
+    L.xsb_field_download.argtypes = [vp, i32, vp]
+    L.xsb_field_device_ptr.restype = vp
+    L.xsb_field_device_ptr.argtypes = [vp, i32]
+    L.xsb_zero_force_energy.argtypes = [vp, i32]
+    L.xsb_chunk_neighbors_build.argtypes = [vp, dbl, C.POINTER(ChunkNeighborsConfig)]
+    L.xsb_chunk_neighbors_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_uint32)]
+    L.xsb_chunk_neighbors_export_size.argtypes = [vp, C.POINTER(u64)]
+    L.xsb_chunk_neighbors_export.argtypes = [vp, vp, vp]
+    L.xsb_chunk_neighbors_download_flat.argtypes = [vp, vp, vp, vp]
+    L.xsb_pair_force.argtypes = [vp, i32, vp, i32, dbl, i32]
+    L.xsb_pair_multi_force.argtypes = [vp, i32, i32, vp, i32, dbl, i32]
+    L.xsb_eam_johnson_force.argtypes = [vp, vp, dbl, i32, i32]
+    L.xsb_eam_alloy_read.argtypes = [C.c_char_p, C.POINTER(EamAlloyTables), C.c_char_p, C.c_size_t]
+    L.xsb_eam_alloy_free.argtypes = [C.POINTER(EamAlloyTables)]
+    L.xsb_eam_alloy_set.argtypes = [vp, C.POINTER(EamAlloyTables)]
+    L.xsb_eam_alloy_force.argtypes = [vp, dbl, i32, i32]
+    L.xsb_comm_unique_id.argtypes = [vp]
+    L.xsb_comm_init.argtypes = [vp, i32, i32, vp]
+    L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc), vp]
+    L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
+    L.xsb_ghost_reduce_add.argtypes = [vp, C.c_uint32]
+    _lib = L
+    return L
+
+
+def make_grid(dims, ghost_layers, cell_size, origin, xform=None):
+    g = GridDesc()
+    g.dims[:] = [int(d) for d in dims]
+    g.ghost_layers = int(ghost_layers)
+    g.cell_size = float(cell_size)
+    g.origin[:] = [float(o) for o in origin]
+    X = np.eye(3) if xform is None else np.asarray(xform, dtype=np.float64).reshape(3, 3)
+    g.xform[:] = [float(v) for v in X.ravel()]
+    g.xform_is_identity = int(np.array_equal(X, np.eye(3)))
+    return g
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """one xsb_ctx (one GPU).  Methods mirror the C ABI one to one; host numpy buffers in, host numpy buffers out."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.xsb_create(int(device), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.xsb_last_error(self.h).decode() if self.h else "xsb_create failed"
+            if self.h:
+                self.L.xsb_destroy(self.h)
+                self.h = None
+            raise XsbError("xsb_create(%d): %s" % (device, msg))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise XsbError("%s failed (%d): %s" % (what, rc, self.L.xsb_last_error(self.h).decode()))
+
+    # ---- a1
+    def grid_set(self, grid):
+        self.grid = grid
+        self._ck(self.L.xsb_grid_set(self.h, C.byref(grid)), "xsb_grid_set")
+
+    def particles_set_cells(self, cell_off):
+        off = np.ascontiguousarray(cell_off, dtype=np.uint64)
+        self._ck(self.L.xsb_particles_set_cells(self.h, _ptr(off)), "xsb_particles_set_cells")
+
+    @property
+    def n(self):
+        return int(self.L.xsb_num_particles(self.h))
+
+    def upload(self, field, arr):
+        dt = _FIELD_DTYPE.get(field, np.float64)
+        a = np.ascontiguousarray(arr, dtype=dt)
+        want = self.n * (9 if field == F_VIRIAL else 1)
+        if a.size != want:
+            raise XsbError("upload(field %d): %d elements given, %d expected" % (field, a.size, want))
+        self._ck(self.L.xsb_field_upload(self.h, field, _ptr(a)), "xsb_field_upload")
+        self._ck(self.L.xsb_sync(self.h), "xsb_sync")   # `a` may be a temporary
+
+    def download(self, field, out=None):
+        dt = _FIELD_DTYPE.get(field, np.float64)
+        shape = (self.n, 9) if field == F_VIRIAL else (self.n,)
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        self._ck(self.L.xsb_field_download(self.h, field, _ptr(out)), "xsb_field_download")
+        return out
+
+    def device_ptr(self, field):
+        return self.L.xsb_field_device_ptr(self.h, field)
+
+    def zero_force_energy(self, ghost=False):
+        self._ck(self.L.xsb_zero_force_energy(self.h, int(ghost)), "xsb_zero_force_energy")
+
+    def sync(self):
+        self._ck(self.L.xsb_sync(self.h), "xsb_sync")
+
+    @property
+    def launches(self):
+        return int(self.L.xsb_kernel_launch_count(self.h))
+
+    # ---- a2
+    def chunk_neighbors(self, nbh_dist_lab, chunk_size=1, build_particle_offset=True, stream_prealloc_factor=1.05):
+        cfg = ChunkNeighborsConfig(int(chunk_size), int(build_particle_offset), 1, 0, float(stream_prealloc_factor))
+        self._ck(self.L.xsb_chunk_neighbors_build(self.h, float(nbh_dist_lab), C.byref(cfg)), "xsb_chunk_neighbors_build")
+
+    def chunk_neighbors_stats(self):
+        t, m = C.c_uint64(), C.c_uint32()
+        self._ck(self.L.xsb_chunk_neighbors_stats(self.h, C.byref(t), C.byref(m)), "xsb_chunk_neighbors_stats")
+        return t.value, m.value
+
+    def chunk_neighbors_export(self):
+        tot = C.c_uint64()
+        self._ck(self.L.xsb_chunk_neighbors_export_size(self.h, C.byref(tot)), "xsb_chunk_neighbors_export_size")
+        off = np.zeros(int(self.L.xsb_num_cells(self.h)) + 1, dtype=np.uint64)
+        data = np.zeros(max(1, tot.value), dtype=np.uint16)
+        self._ck(self.L.xsb_chunk_neighbors_export(self.h, _ptr(off), _ptr(data)), "xsb_chunk_neighbors_export")
+        return off, data[:tot.value]
+
+    def chunk_neighbors_flat(self):
+        total, _ = self.chunk_neighbors_stats()
+        counts = np.zeros(self.n, dtype=np.uint32)
+        offs = np.zeros(self.n + 1, dtype=np.uint64)
+        idx = np.zeros(max(1, total), dtype=np.uint32)
+        self._ck(self.L.xsb_chunk_neighbors_download_flat(self.h, _ptr(counts), _ptr(offs), _ptr(idx)), "xsb_chunk_neighbors_download_flat")
+        return counts, offs, idx[:total]
+
+    # ---- a3-a6
+    def pair_force(self, params, rcut, flags=FLAG_ENERGY, pot=POT_LJ):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.xsb_pair_force(self.h, pot, _ptr(p), p.size, float(rcut), int(flags)), "xsb_pair_force")
+
+    def pair_multi_force(self, n_types, pair_params, rcut_max, flags=FLAG_ENERGY, pot=POT_LJ):
+        p = np.ascontiguousarray(pair_params, dtype=np.float64)
+        self._ck(self.L.xsb_pair_multi_force(self.h, pot, int(n_types), _ptr(p), p.shape[1] - 1, float(rcut_max), int(flags)), "xsb_pair_multi_force")
+
+    # ---- a7-a8
+    def eam_johnson_force(self, params19, rcut, phases=7, flags=0):
+        p = np.ascontiguousarray(params19, dtype=np.float64)
+        assert p.size == 19
+        self._ck(self.L.xsb_eam_johnson_force(self.h, _ptr(p), float(rcut), int(phases), int(flags)), "xsb_eam_johnson_force")
+
+    def eam_alloy_load(self, path):
+        t = EamAlloyTables()
+        names = C.create_string_buffer(256)
+        rc = self.L.xsb_eam_alloy_read(path.encode(), C.byref(t), names, 256)
+        if rc != 0:
+            raise XsbError("xsb_eam_alloy_read(%s) failed (%d)" % (path, rc))
+        try:
+            self._ck(self.L.xsb_eam_alloy_set(self.h, C.byref(t)), "xsb_eam_alloy_set")
+            info = dict(nelements=t.nelements, nr=t.nr, nrho=t.nrho, rc=t.rc, names=names.value.decode().split())
+        finally:
+            self.L.xsb_eam_alloy_free(C.byref(t))
+        return info
+
+    def eam_alloy_force(self, rcut, phases=EAM_RHO | EAM_RHO2EMB | EAM_GHOST | EAM_FORCE, flags=0):
+        self._ck(self.L.xsb_eam_alloy_force(self.h, float(rcut), int(phases), int(flags)), "xsb_eam_alloy_force")

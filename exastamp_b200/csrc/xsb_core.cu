@@ -1,0 +1,235 @@
+// xsb_core.cu -- context, grid + particle storage, zero_force_energy.
+#include "xsb_ctx.h"
+#include <cmath>
+#include <new>
+
+namespace xsb
+{
+
+static void inverse3(const double* m, double* inv)
+{
+  const double det = m[0]*(m[4]*m[8]-m[5]*m[7]) - m[1]*(m[3]*m[8]-m[5]*m[6]) + m[2]*(m[3]*m[7]-m[4]*m[6]);
+  const double id = 1.0 / det;
+  inv[0] =  (m[4]*m[8]-m[5]*m[7])*id; inv[1] = -(m[1]*m[8]-m[2]*m[7])*id; inv[2] =  (m[1]*m[5]-m[2]*m[4])*id;
+  inv[3] = -(m[3]*m[8]-m[5]*m[6])*id; inv[4] =  (m[0]*m[8]-m[2]*m[6])*id; inv[5] = -(m[0]*m[5]-m[2]*m[3])*id;
+  inv[6] =  (m[3]*m[7]-m[4]*m[6])*id; inv[7] = -(m[0]*m[7]-m[1]*m[6])*id; inv[8] =  (m[0]*m[4]-m[1]*m[3])*id;
+}
+
+void search_range(const xsb_grid_desc& g, double dist, int R[3])
+{
+  double inv[9] = {1,0,0,0,1,0,0,0,1};
+  if( !g.xform_is_identity ) inverse3(g.xform, inv);
+  for(int a = 0; a < 3; a++)
+  {
+    const double nrm = std::sqrt(inv[3*a]*inv[3*a] + inv[3*a+1]*inv[3*a+1] + inv[3*a+2]*inv[3*a+2]);
+    R[a] = int(std::ceil(dist * nrm / g.cell_size));
+    if( R[a] < 1 ) R[a] = 1;
+    if( R[a] > 15 ) R[a] = 15;   // range of the 5-bit relative cell index of the exported stream
+  }
+}
+
+__global__ void zero_fields_kernel(const unsigned* __restrict__ atoms, unsigned n_atoms, unsigned n_all, bool all,
+                                   double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                   double* __restrict__ ep, double* __restrict__ vir)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned n = all ? n_all : n_atoms;
+  for(unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+  {
+    const unsigned a = all ? t : atoms[t];
+    fx[a] = 0.0; fy[a] = 0.0; fz[a] = 0.0; ep[a] = 0.0;
+    if( vir ) { double* v = vir + 9ull * a; for(int k = 0; k < 9; k++) v[k] = 0.0; }
+  }
+}
+
+} // namespace xsb
+
+using namespace xsb;
+
+int xsb_internal_ensure_virial(xsb_ctx* ctx)
+{
+  if( ctx->virial_allocated && ctx->f64[XSB_F_VIRIAL].cap >= 9 * (ctx->n + 1) ) return XSB_OK;
+  XSB_CUDA(ctx, ctx->f64[XSB_F_VIRIAL].reserve(9 * (ctx->n + 1), 1.02));
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[XSB_F_VIRIAL].p, 0, 9 * (ctx->n + 1) * sizeof(double), ctx->stream));
+  ctx->virial_allocated = true;
+  return XSB_OK;
+}
+
+extern "C" {
+
+const char* xsb_version(void) { return "xsb200 0.1 (sm_100a)"; }
+
+int xsb_create(int device, xsb_ctx** out)
+{
+  if( !out ) return XSB_ERR_INVALID;
+  *out = nullptr;
+  xsb_ctx* ctx = new (std::nothrow) xsb_ctx;
+  if( !ctx ) return XSB_ERR_INVALID;
+  *out = ctx;   // returned even on failure so xsb_last_error() can be read; caller still must xsb_destroy it
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if( e != cudaSuccess || ndev == 0 )
+    return ctx->fail(XSB_ERR_CUDA, "no CUDA device available (%s); libxsb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if( device < 0 || device >= ndev ) return ctx->fail(XSB_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  cudaDeviceProp prop;
+  XSB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+  if( prop.major != 10 )
+    return ctx->fail(XSB_ERR_CUDA, "device %d is sm_%d%d; libxsb200 is built for sm_100a only", device, prop.major, prop.minor);
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  XSB_CUDA(ctx, cudaSetDevice(device));
+  XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  return XSB_OK;
+}
+
+void xsb_destroy(xsb_ctx* ctx)
+{
+  if( !ctx ) return;
+  if( ctx->stream )
+  {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  ctx->cell_start.release(); ctx->cell_of.release(); ctx->own_atoms.release();
+  for(auto& b : ctx->f64) b.release();
+  ctx->type.release(); ctx->id.release();
+  ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->scratch.release(); ctx->scratch64.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release();
+  xsb_ghost_release(ctx);
+  if( ctx->stream ) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* xsb_last_error(const xsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t xsb_kernel_launch_count(const xsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int xsb_sync(xsb_ctx* ctx)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, g != nullptr, XSB_ERR_INVALID, "null grid");
+  XSB_REQUIRE(ctx, g->dims[0] > 0 && g->dims[1] > 0 && g->dims[2] > 0, XSB_ERR_INVALID, "grid dims must be positive");
+  XSB_REQUIRE(ctx, g->ghost_layers >= 0 && 2 * g->ghost_layers < g->dims[0] && 2 * g->ghost_layers < g->dims[1] && 2 * g->ghost_layers < g->dims[2],
+              XSB_ERR_INVALID, "ghost_layers inconsistent with dims");
+  XSB_REQUIRE(ctx, g->cell_size > 0.0, XSB_ERR_INVALID, "cell_size must be > 0");
+  const uint64_t nc = uint64_t(g->dims[0]) * uint64_t(g->dims[1]) * uint64_t(g->dims[2]);
+  XSB_REQUIRE(ctx, nc < (1ull << 31), XSB_ERR_OVERFLOW, "too many cells");
+  ctx->grid = *g;
+  ctx->ncells = nc;
+  ctx->grid_set = true;
+  ctx->nbh_built = false;
+  ctx->n = 0;
+  return XSB_OK;
+}
+
+int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
+  XSB_REQUIRE(ctx, off != nullptr && off[0] == 0, XSB_ERR_INVALID, "cell_particle_offset[0] must be 0");
+  const uint64_t nc = ctx->ncells;
+  for(uint64_t c = 0; c < nc; c++) XSB_REQUIRE(ctx, off[c+1] >= off[c], XSB_ERR_INVALID, "cell_particle_offset must be non-decreasing");
+  const uint64_t n = off[nc];
+  XSB_REQUIRE(ctx, n < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->h_cell_off.assign(off, off + nc + 1);
+  std::vector<unsigned> start(nc + 1), cellof(n), own; own.reserve(n);
+  const GridView gv = ctx->view();
+  for(uint64_t c = 0; c <= nc; c++) start[c] = unsigned(off[c]);
+  for(uint64_t c = 0; c < nc; c++)
+  {
+    const bool ghost = gv.is_ghost_cell(unsigned(c));
+    for(uint64_t p = off[c]; p < off[c+1]; p++) { cellof[p] = unsigned(c); if( !ghost ) own.push_back(unsigned(p)); }
+  }
+  ctx->n = n; ctx->n_own = own.size();
+  XSB_CUDA(ctx, ctx->cell_start.reserve(nc + 1));
+  XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1));
+  XSB_CUDA(ctx, ctx->own_atoms.reserve(own.size() + 1));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, start.data(), (nc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  if( n ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_of.p, cellof.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  if( !own.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->own_atoms.p, own.data(), own.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  for(int f = 0; f < XSB_F_TYPE; f++)
+  {
+    if( f == XSB_F_VIRIAL ) continue;   // allocated on first use
+    XSB_CUDA(ctx, ctx->f64[f].reserve(n + 1, 1.02));
+    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, (n + 1) * sizeof(double), ctx->stream));
+  }
+  if( ctx->virial_allocated )
+  {
+    XSB_CUDA(ctx, ctx->f64[XSB_F_VIRIAL].reserve(9 * (n + 1), 1.02));
+    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[XSB_F_VIRIAL].p, 0, 9 * (n + 1) * sizeof(double), ctx->stream));
+  }
+  XSB_CUDA(ctx, ctx->type.reserve(n + 16, 1.02));
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, n + 16, ctx->stream));
+  XSB_CUDA(ctx, ctx->id.reserve(n + 1, 1.02));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
+  ctx->nbh_built = false;
+  return XSB_OK;
+}
+
+uint64_t xsb_num_particles(const xsb_ctx* ctx) { return ctx ? ctx->n : 0; }
+uint64_t xsb_num_cells(const xsb_ctx* ctx) { return ctx ? ctx->ncells : 0; }
+
+static int field_ptr(xsb_ctx* ctx, int field, void** p, size_t* bytes)
+{
+  XSB_REQUIRE(ctx, field >= 0 && field < XSB_F_COUNT_, XSB_ERR_INVALID, "unknown field");
+  XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "xsb_particles_set_cells must be called first");
+  if( field == XSB_F_TYPE ) { *p = ctx->type.p; *bytes = ctx->n; }
+  else if( field == XSB_F_ID ) { *p = ctx->id.p; *bytes = ctx->n * sizeof(uint64_t); }
+  else if( field == XSB_F_VIRIAL ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; *p = ctx->f64[field].p; *bytes = 9 * ctx->n * sizeof(double); }
+  else { *p = ctx->f64[field].p; *bytes = ctx->n * sizeof(double); }
+  return XSB_OK;
+}
+
+int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, src != nullptr, XSB_ERR_INVALID, "null source");
+  void* p = nullptr; size_t bytes = 0;
+  int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
+  if( bytes ) XSB_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_field_download(xsb_ctx* ctx, int field, void* dst)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, dst != nullptr, XSB_ERR_INVALID, "null destination");
+  void* p = nullptr; size_t bytes = 0;
+  int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
+  if( bytes ) XSB_CUDA(ctx, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XSB_OK;
+}
+
+void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
+{
+  if( !ctx || !ctx->stream ) return nullptr;
+  void* p = nullptr; size_t bytes = 0;
+  if( field_ptr(ctx, field, &p, &bytes) ) return nullptr;
+  return p;
+}
+
+int xsb_zero_force_energy(xsb_ctx* ctx, int ghost)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
+  if( ctx->n == 0 ) return XSB_OK;
+  const unsigned n = ghost ? unsigned(ctx->n) : unsigned(ctx->n_own);
+  if( n == 0 ) return XSB_OK;
+  const int block = 256;
+  const int grid = int(std::min<uint64_t>((n + block - 1) / block, uint64_t(ctx->sm_count) * 8));
+  zero_fields_kernel<<<grid, block, 0, ctx->stream>>>(ctx->own_atoms.p, unsigned(ctx->n_own), unsigned(ctx->n), ghost != 0,
+      ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, ctx->f64[XSB_F_EP].p,
+      ctx->virial_allocated ? ctx->f64[XSB_F_VIRIAL].p : nullptr);
+  XSB_LAUNCH_CHECK(ctx);
+  return XSB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,127 @@
+// xsb_ctx.h -- internal state of one libxsb200 context (one per GPU).  Not part of the C ABI.
+#pragma once
+#include "../../include/xsb200.h"
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct ncclComm;
+
+namespace xsb
+{
+
+// RAII-less device buffer: grows geometrically, never shrinks until the context dies (steady-state MD loops
+// must not touch cudaMalloc).
+template<class T> struct DevBuf
+{
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t n, double factor = 1.0)
+  {
+    if( n <= cap ) return cudaSuccess;
+    size_t want = size_t(double(n) * (factor < 1.0 ? 1.0 : factor));
+    if( want < n ) want = n;
+    if( p ) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if( e == cudaSuccess ) cap = want;
+    return e;
+  }
+  void release() { if( p ) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// device-side view of the grid handed to kernels by value
+struct GridView
+{
+  int nx, ny, nz, gl;
+  double cell_size;
+  double xf[9];
+  int xform_identity;
+  __host__ __device__ inline bool is_ghost_cell(unsigned c) const
+  {
+    const int i = int(c % unsigned(nx)), j = int((c / unsigned(nx)) % unsigned(ny)), k = int(c / (unsigned(nx) * unsigned(ny)));
+    return i < gl || i >= nx - gl || j < gl || j >= ny - gl || k < gl || k >= nz - gl;
+  }
+};
+
+struct EamAlloyDev
+{
+  int nelements = 0, nr = 0, nrho = 0;
+  double rdr = 0, rdrho = 0, rc = 0, rhomax = 0, conv_z2r = 0, conv_frho = 0;
+  DevBuf<double> frho;      // reference layout [nel][nrho+1][8]
+  DevBuf<double> rtab;      // fused r-tables, see xsb_eam.cu
+  bool set = false;
+};
+
+} // namespace xsb
+
+struct xsb_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  // a1 grid + particles
+  bool grid_set = false;
+  xsb_grid_desc grid{};
+  uint64_t ncells = 0, n = 0;         // all cells / all particles (ghosts included)
+  std::vector<uint64_t> h_cell_off;   // host copy
+  xsb::DevBuf<unsigned> cell_start;   // [ncells+1] flat start of each cell
+  xsb::DevBuf<unsigned> cell_of;      // [n] cell of each particle
+  xsb::DevBuf<unsigned> own_atoms;    // flat indices of particles in non-ghost cells
+  uint64_t n_own = 0;
+  xsb::DevBuf<double> f64[XSB_F_TYPE]; // RX..RHO_DEMB (virial: 9n)
+  xsb::DevBuf<uint8_t> type;
+  xsb::DevBuf<uint64_t> id;
+  bool virial_allocated = false;
+
+  // a2 neighbour list (flat CSR, canonical order)
+  bool nbh_built = false;
+  double nbh_dist = 0.0;
+  xsb_chunk_neighbors_config nbh_cfg{1, 1, 1, 0, 1.05};
+  xsb::DevBuf<unsigned> nbh_count;            // [n]
+  xsb::DevBuf<unsigned long long> nbh_off;    // [n+1]
+  xsb::DevBuf<unsigned> nbh_idx;              // [total]
+  uint64_t nbh_total = 0;
+  unsigned nbh_max = 0;
+  xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.
+  xsb::DevBuf<unsigned long long> scratch64;  // misc u64 scratch
+
+  // a8
+  xsb::EamAlloyDev eam;
+
+  // a10
+  ncclComm* comm = nullptr; int nranks = 1, rank = 0;
+
+  int fail(int code, const char* fmt, ...)
+  {
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    err = buf; return code;
+  }
+  xsb::GridView view() const
+  {
+    xsb::GridView v; v.nx = grid.dims[0]; v.ny = grid.dims[1]; v.nz = grid.dims[2]; v.gl = grid.ghost_layers;
+    v.cell_size = grid.cell_size; for(int i = 0; i < 9; i++) v.xf[i] = grid.xform[i]; v.xform_identity = grid.xform_is_identity;
+    return v;
+  }
+};
+
+#define XSB_CUDA(ctx, call) do { cudaError_t e__ = (call); if( e__ != cudaSuccess ) \
+  return (ctx)->fail(XSB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } while(0)
+#define XSB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if( e__ != cudaSuccess ) \
+  return (ctx)->fail(XSB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } while(0)
+#define XSB_REQUIRE(ctx, cond, code, msg) do { if( !(cond) ) return (ctx)->fail(code, "%s", msg); } while(0)
+
+// internal helpers shared across translation units (C++ linkage, not exported by the header)
+int  xsb_internal_ensure_virial(xsb_ctx* ctx);
+void xsb_ghost_release(xsb_ctx* ctx);
+
+namespace xsb
+{
+// search range (cell layers per axis) covering every grid-space displacement of physical length < dist
+void search_range(const xsb_grid_desc& g, double dist, int R[3]);
+}

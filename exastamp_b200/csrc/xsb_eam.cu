@@ -1,0 +1,489 @@
+// xsb_eam.cu -- EAM force operators.
+//  * johnson_force & co: single-species analytic EAM, two pair passes (rho -> F'(rho) ; force).
+//      operator src/potential/eam_potential_template/eam_potential.cu:69-176, functors
+//      eam_force_op_singlemat.h:39-171, math src/potential/eam_potentials/johnson/johnson.h:56-166.
+//  * eam_alloy_force: multi-species tabulated (setfl) EAM, phases rho / rho2emb / force.
+//      operator eam_potential_multimat.cu:65-259, functors eam_force_op_multimat.h:107-343,
+//      tables + evaluation src/potential/eam_potentials/eam_alloy/eam_alloy.h:37-313, reader eam_alloy.cpp:66-278.
+#include "xsb_traverse.cuh"
+#include <fstream>
+#include <limits>
+#include <string>
+
+namespace xsb
+{
+
+// ------------------------------------------------------------------------------------------------
+// Johnson analytic EAM
+// ------------------------------------------------------------------------------------------------
+struct JohnsonP
+{
+  double re, fe, rhoe, alpha, beta, A, B, kappa, lambda, Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, Fo, eta;
+};
+
+// c^20 and c^19 by squaring (johnson.h uses pow(c2,20) and 20*c3/c2)
+__device__ __forceinline__ void pow20_19(double c, double& c20, double& c19)
+{
+  const double c2 = c * c, c4 = c2 * c2, c8 = c4 * c4, c16 = c8 * c8;
+  c20 = c16 * c4; c19 = c16 * c2 * c;
+}
+
+// one term  s*exp(-k(x-1)) / (1+(x-l)^20)  and its derivative wrt r (ire = 1/re)
+__device__ __forceinline__ void johnson_term(double s, double k, double l, double x, double ire, double& f, double& df)
+{
+  const double num = s * exp(-k * (x - 1.0));
+  double c20, c19; pow20_19(x - l, c20, c19);
+  const double den = 1.0 + c20, iden = 1.0 / den;
+  f = num * iden;
+  df = ire * ((-k * num) * den - num * (20.0 * c19)) * iden * iden;
+}
+
+__device__ __forceinline__ void johnson_rho(const JohnsonP& p, double r, double& rho, double& drho)
+{
+  const double ire = 1.0 / p.re;
+  johnson_term(p.fe, p.beta, p.lambda, r * ire, ire, rho, drho);
+}
+
+__device__ __forceinline__ void johnson_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+{
+  const double ire = 1.0 / p.re, x = r * ire;
+  double f1, d1, f2, d2;
+  johnson_term(p.A, p.alpha, p.kappa, x, ire, f1, d1);
+  johnson_term(-p.B, p.beta, p.lambda, x, ire, f2, d2);
+  phi = f1 + f2; dphi = d1 + d2;
+}
+
+__device__ __forceinline__ void johnson_fEmbed(const JohnsonP& p, double rho, double& f, double& df)
+{
+  const double rhon = 0.85 * p.rhoe, rho0 = 1.15 * p.rhoe;
+  if( rho < rhon )
+  {
+    const double q1 = rho / rhon - 1., q2 = q1 * q1, q3 = q1 * q2;
+    f = p.Fn0 + p.Fn1 * q1 + p.Fn2 * q2 + p.Fn3 * q3;
+    df = (p.Fn1 + 2. * p.Fn2 * q1 + 3. * p.Fn3 * q2) / rhon;
+  }
+  else if( rho < rho0 )
+  {
+    const double q1 = rho / p.rhoe - 1., q2 = q1 * q1, q3 = q1 * q2;
+    f = p.F0 + p.F1 * q1 + p.F2 * q2 + p.F3 * q3;
+    df = (p.F1 + 2. * p.F2 * q1 + 3. * p.F3 * q2) / p.rhoe;
+  }
+  else
+  {
+    const double rap = rho / p.rhoe;
+    const double rpe = pow(rap, p.eta), l = log(rpe);
+    f = p.Fo * (1. - l) * rpe;
+    df = (-p.eta * rpe + (1. - l) * p.eta * rpe) * p.Fo / (p.rhoe * rap);
+  }
+}
+
+// pass 1 (EmbOp): rho_i = sum rho(r_ij) ; ep_i += F(rho_i) ; rho_dEmb_i = F'(rho_i)
+template<int TPA, bool XFORM>
+__global__ void __launch_bounds__(256) johnson_emb_kernel(ParticleView P, XForm X, JohnsonP p, double rcut2,
+                                                           double* __restrict__ ep, double* __restrict__ rho_dEmb)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = t / TPA, sub = t % TPA;
+  const bool valid = g < P.n_atoms;
+  unsigned a = 0; unsigned long long e0 = 0, e1 = 0; double xa = 0, ya = 0, za = 0;
+  if( valid ) { a = P.atoms ? P.atoms[g] : g; e0 = P.nbh_off[a]; e1 = P.nbh_off[a+1]; xa = P.rx[a]; ya = P.ry[a]; za = P.rz[a]; }
+  double srho = 0.0; unsigned cnt = 0;
+  for(unsigned long long e = e0 + sub; e < e1; e += TPA)
+  {
+    const unsigned b = P.nbh_idx[e];
+    double dx = P.rx[b] - xa, dy = P.ry[b] - ya, dz = P.rz[b] - za;
+    apply_xform<XFORM>(X, dx, dy, dz);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if( d2 <= rcut2 )
+    {
+      double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
+      srho += rho; ++cnt;
+    }
+  }
+  srho = group_sum<TPA>(srho);
+# pragma unroll
+  for(int o = TPA / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if( valid && sub == 0 && cnt > 0 )   // the functor only runs for non-empty pair buffers
+  {
+    double f, df; johnson_fEmbed(p, srho, f, df);
+    ep[a] += f; rho_dEmb[a] = df;
+  }
+}
+
+// pass 2 (ForceOp): de = (rho'(r)(F'_i+F'_j) + phi'(r))/r
+template<int TPA, bool XFORM, bool VIRIAL>
+__global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XForm X, JohnsonP p, double rcut2, const double* __restrict__ rho_dEmb,
+                                                             double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                                             double* __restrict__ ep, double* __restrict__ vir)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = t / TPA, sub = t % TPA;
+  const bool valid = g < P.n_atoms;
+  unsigned a = 0; unsigned long long e0 = 0, e1 = 0; double xa = 0, ya = 0, za = 0, fpi = 0;
+  if( valid ) { a = P.atoms ? P.atoms[g] : g; e0 = P.nbh_off[a]; e1 = P.nbh_off[a+1]; xa = P.rx[a]; ya = P.ry[a]; za = P.rz[a]; fpi = rho_dEmb[a]; }
+  double sfx = 0, sfy = 0, sfz = 0, sep = 0;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0, v7 = 0, v8 = 0;
+  for(unsigned long long e = e0 + sub; e < e1; e += TPA)
+  {
+    const unsigned b = P.nbh_idx[e];
+    double dx = P.rx[b] - xa, dy = P.ry[b] - ya, dz = P.rz[b] - za;
+    apply_xform<XFORM>(X, dx, dy, dz);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if( d2 <= rcut2 )
+    {
+      const double r = sqrt(d2);
+      double rho, drho, phi, dphi;
+      johnson_rho(p, r, rho, drho);
+      johnson_phi(p, r, phi, dphi);
+      const double de = (drho * (fpi + rho_dEmb[b]) + dphi) / r;
+      const double fex = de * dx, fey = de * dy, fez = de * dz;
+      sfx += fex; sfy += fey; sfz += fez; sep += 0.5 * phi;
+      if( VIRIAL )
+      {
+        v0 -= 0.5 * fex * dx; v1 -= 0.5 * fex * dy; v2 -= 0.5 * fex * dz;
+        v3 -= 0.5 * fey * dx; v4 -= 0.5 * fey * dy; v5 -= 0.5 * fey * dz;
+        v6 -= 0.5 * fez * dx; v7 -= 0.5 * fez * dy; v8 -= 0.5 * fez * dz;
+      }
+    }
+  }
+  sfx = group_sum<TPA>(sfx); sfy = group_sum<TPA>(sfy); sfz = group_sum<TPA>(sfz); sep = group_sum<TPA>(sep);
+  if( VIRIAL )
+  {
+    v0 = group_sum<TPA>(v0); v1 = group_sum<TPA>(v1); v2 = group_sum<TPA>(v2);
+    v3 = group_sum<TPA>(v3); v4 = group_sum<TPA>(v4); v5 = group_sum<TPA>(v5);
+    v6 = group_sum<TPA>(v6); v7 = group_sum<TPA>(v7); v8 = group_sum<TPA>(v8);
+  }
+  if( valid && sub == 0 )
+  {
+    fx[a] += sfx; fy[a] += sfy; fz[a] += sfz; ep[a] += sep;
+    if( VIRIAL )
+    {
+      double* v = vir + 9ull * a;
+      v[0] += v0; v[1] += v1; v[2] += v2; v[3] += v3; v[4] += v4; v[5] += v5; v[6] += v6; v[7] += v7; v[8] += v8;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// eam/alloy tabulated EAM
+// ------------------------------------------------------------------------------------------------
+struct EamAlloyView
+{
+  const double* __restrict__ frho; const double* __restrict__ rhor; const double* __restrict__ z2r;
+  int nr, nrho; double rdr, rdrho, rhomax, conv_z2r, conv_frho;
+};
+
+__device__ __forceinline__ int z2r_index(int a, int b) { return a > b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// spline row lookup for an r-indexed table (eam_alloy.h:196-200): no lower clamp on m
+__device__ __forceinline__ void r_lookup(const EamAlloyView& T, double r, int& m, double& p)
+{
+  p = r * T.rdr + 1.0;
+  m = static_cast<int>(p);
+  m = min(m, T.nr - 1);
+  p -= m;
+  p = fmin(p, 1.0);
+}
+
+template<int TPA, bool XFORM>
+__global__ void __launch_bounds__(256) eam_alloy_rho_kernel(ParticleView P, XForm X, EamAlloyView T, double rcut2, double* __restrict__ rho_dEmb)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = t / TPA, sub = t % TPA;
+  const bool valid = g < P.n_atoms;
+  unsigned a = 0; unsigned long long e0 = 0, e1 = 0; double xa = 0, ya = 0, za = 0;
+  if( valid ) { a = P.atoms ? P.atoms[g] : g; e0 = P.nbh_off[a]; e1 = P.nbh_off[a+1]; xa = P.rx[a]; ya = P.ry[a]; za = P.rz[a]; }
+  double srho = 0.0;
+  for(unsigned long long e = e0 + sub; e < e1; e += TPA)
+  {
+    const unsigned b = P.nbh_idx[e];
+    double dx = P.rx[b] - xa, dy = P.ry[b] - ya, dz = P.rz[b] - za;
+    apply_xform<XFORM>(X, dx, dy, dz);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if( d2 <= rcut2 )
+    {
+      int m; double p; r_lookup(T, sqrt(d2), m, p);
+      const double* c = T.rhor + (size_t(P.type[b]) * (T.nr + 1) + m) * 8;   // density of the NEIGHBOUR's element
+      srho += ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+    }
+  }
+  srho = group_sum<TPA>(srho);
+  if( valid && sub == 0 ) rho_dEmb[a] += srho;
+}
+
+__global__ void eam_alloy_rho2emb_kernel(const unsigned* __restrict__ atoms, unsigned n_atoms, EamAlloyView T, const unsigned char* __restrict__ type,
+                                         double* __restrict__ rho_dEmb, double* __restrict__ ep)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= n_atoms ) return;
+  const unsigned a = atoms ? atoms[t] : t;
+  const double rho = rho_dEmb[a];
+  double p = rho * T.rdrho + 1.0;
+  int m = static_cast<int>(p);
+  m = max(1, min(m, T.nrho - 1));
+  p -= m;
+  p = fmin(p, 1.0);
+  const double* c = T.frho + (size_t(type[a]) * (T.nrho + 1) + m) * 8;
+  double fp = (c[0] * p + c[1]) * p + c[2];
+  double phi = ((c[3] * p + c[4]) * p + c[5]) * p + c[6];
+  if( rho > T.rhomax ) phi += fp * (rho - T.rhomax);
+  rho_dEmb[a] = fp * T.conv_frho;
+  if( ep ) ep[a] += phi * T.conv_frho;
+}
+
+template<int TPA, bool XFORM, bool EFLAG, bool VIRIAL>
+__global__ void __launch_bounds__(256) eam_alloy_force_kernel(ParticleView P, XForm X, EamAlloyView T, double rcut2, const double* __restrict__ dEmb,
+                                                               double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                                               double* __restrict__ ep, double* __restrict__ vir)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = t / TPA, sub = t % TPA;
+  const bool valid = g < P.n_atoms;
+  unsigned a = 0; unsigned long long e0 = 0, e1 = 0; double xa = 0, ya = 0, za = 0, fpi = 0; int ta = 0;
+  if( valid ) { a = P.atoms ? P.atoms[g] : g; e0 = P.nbh_off[a]; e1 = P.nbh_off[a+1]; xa = P.rx[a]; ya = P.ry[a]; za = P.rz[a]; fpi = dEmb[a]; ta = P.type[a]; }
+  double sfx = 0, sfy = 0, sfz = 0, sep = 0;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0, v7 = 0, v8 = 0;
+  for(unsigned long long e = e0 + sub; e < e1; e += TPA)
+  {
+    const unsigned b = P.nbh_idx[e];
+    double dx = P.rx[b] - xa, dy = P.ry[b] - ya, dz = P.rz[b] - za;
+    apply_xform<XFORM>(X, dx, dy, dz);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if( d2 <= rcut2 )
+    {
+      const double r = sqrt(d2);
+      int m; double p; r_lookup(T, r, m, p);
+      const int tb = P.type[b];
+      const double* ci = T.rhor + (size_t(ta) * (T.nr + 1) + m) * 8;
+      const double* cj = T.rhor + (size_t(tb) * (T.nr + 1) + m) * 8;
+      const double* cz = T.z2r + (size_t(z2r_index(ta, tb)) * (T.nr + 1) + m) * 8;
+      const double rhoip = (ci[0] * p + ci[1]) * p + ci[2];
+      const double rhojp = (cj[0] * p + cj[1]) * p + cj[2];
+      const double z2p = (cz[0] * p + cz[1]) * p + cz[2];
+      const double z2 = ((cz[3] * p + cz[4]) * p + cz[5]) * p + cz[6];
+      const double recip = 1.0 / r;
+      double phi = z2 * recip;
+      const double phip = (z2p * recip - phi * recip) * T.conv_z2r;
+      phi *= T.conv_z2r;
+      const double fpair = (fpi * rhojp + dEmb[b] * rhoip + phip) * recip;
+      const double fex = dx * fpair, fey = dy * fpair, fez = dz * fpair;
+      sfx += fex; sfy += fey; sfz += fez;
+      if( EFLAG ) sep += 0.5 * phi;
+      if( VIRIAL )
+      {
+        v0 -= 0.5 * fex * dx; v1 -= 0.5 * fex * dy; v2 -= 0.5 * fex * dz;
+        v3 -= 0.5 * fey * dx; v4 -= 0.5 * fey * dy; v5 -= 0.5 * fey * dz;
+        v6 -= 0.5 * fez * dx; v7 -= 0.5 * fez * dy; v8 -= 0.5 * fez * dz;
+      }
+    }
+  }
+  sfx = group_sum<TPA>(sfx); sfy = group_sum<TPA>(sfy); sfz = group_sum<TPA>(sfz);
+  if( EFLAG ) sep = group_sum<TPA>(sep);
+  if( VIRIAL )
+  {
+    v0 = group_sum<TPA>(v0); v1 = group_sum<TPA>(v1); v2 = group_sum<TPA>(v2);
+    v3 = group_sum<TPA>(v3); v4 = group_sum<TPA>(v4); v5 = group_sum<TPA>(v5);
+    v6 = group_sum<TPA>(v6); v7 = group_sum<TPA>(v7); v8 = group_sum<TPA>(v8);
+  }
+  if( valid && sub == 0 )
+  {
+    fx[a] += sfx; fy[a] += sfy; fz[a] += sfz;
+    if( EFLAG ) ep[a] += sep;
+    if( VIRIAL )
+    {
+      double* v = vir + 9ull * a;
+      v[0] += v0; v[1] += v1; v[2] += v2; v[3] += v3; v[4] += v4; v[5] += v5; v[6] += v6; v[7] += v7; v[8] += v8;
+    }
+  }
+}
+
+// LAMMPS-style 7-coefficient spline rows (eam_alloy.cpp:29-58), rows padded to 8 doubles, row 0 unused
+static void interpolate(int n, double delta, const double* f, double* s)
+{
+  auto S = [&](int m, int k) -> double& { return s[size_t(m) * 8 + k]; };
+  for(int m = 1; m <= n; m++) S(m,6) = f[m];
+  S(1,5) = S(2,6) - S(1,6);
+  S(2,5) = 0.5 * (S(3,6) - S(1,6));
+  S(n-1,5) = 0.5 * (S(n,6) - S(n-2,6));
+  S(n,5) = S(n,6) - S(n-1,6);
+  for(int m = 3; m <= n - 2; m++) S(m,5) = ((S(m-2,6) - S(m+2,6)) + 8.0 * (S(m+1,6) - S(m-1,6))) / 12.0;
+  for(int m = 1; m <= n - 1; m++)
+  {
+    S(m,4) = 3.0 * (S(m+1,6) - S(m,6)) - 2.0 * S(m,5) - S(m+1,5);
+    S(m,3) = S(m,5) + S(m+1,5) - 2.0 * (S(m+1,6) - S(m,6));
+  }
+  S(n,4) = 0.0; S(n,3) = 0.0;
+  for(int m = 1; m <= n; m++) { S(m,2) = S(m,5) / delta; S(m,1) = 2.0 * S(m,4) / delta; S(m,0) = 3.0 * S(m,3) / delta; }
+}
+
+} // namespace xsb
+
+using namespace xsb;
+
+extern "C" {
+
+int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int phases, int flags)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, params19 != nullptr && rcut > 0.0, XSB_ERR_INVALID, "johnson: null parameters or rcut <= 0");
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
+  XSB_REQUIRE(ctx, rcut <= ctx->nbh_dist, XSB_ERR_INVALID, "rcut exceeds the neighbour-list distance nbh_dist_lab");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  JohnsonP p; std::memcpy(&p, params19, sizeof(p));
+  const bool virial = flags & XSB_FLAG_VIRIAL;
+  if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
+  const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;
+  constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
+  ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr, 0 };
+  double* emb = ctx->f64[XSB_F_RHO_DEMB].p;
+  if( (phases & 1) && ctx->n )
+  {
+    const bool ghost = phases & 2;
+    P.atoms = ghost ? nullptr : ctx->own_atoms.p; P.n_atoms = unsigned(ghost ? ctx->n : ctx->n_own);
+    XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
+    if( P.n_atoms )
+    {
+      const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
+      if( xf ) johnson_emb_kernel<TPA, true ><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, ctx->f64[XSB_F_EP].p, emb);
+      else     johnson_emb_kernel<TPA, false><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, ctx->f64[XSB_F_EP].p, emb);
+      XSB_LAUNCH_CHECK(ctx);
+    }
+  }
+  if( (phases & 4) && ctx->n_own )
+  {
+    P.atoms = ctx->own_atoms.p; P.n_atoms = unsigned(ctx->n_own);
+    const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
+    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+    if( xf ) { if( virial ) johnson_force_kernel<TPA, true, true><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, emb, fx, fy, fz, ep, vir);
+               else         johnson_force_kernel<TPA, true, false><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, emb, fx, fy, fz, ep, vir); }
+    else     { if( virial ) johnson_force_kernel<TPA, false, true><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, emb, fx, fy, fz, ep, vir);
+               else         johnson_force_kernel<TPA, false, false><<<grid, block, 0, ctx->stream>>>(P, X, p, rc2, emb, fx, fy, fz, ep, vir); }
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  return XSB_OK;
+}
+
+int xsb_eam_alloy_read(const char* path, xsb_eam_alloy_tables* out, char* names, size_t names_len)
+{
+  if( !path || !out ) return XSB_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  std::ifstream file(path);
+  if( !file ) return XSB_ERR_IO;
+  for(int i = 0; i < 3; i++) file.ignore(std::numeric_limits<std::streamsize>::max(), '\n');   // 3 comment lines
+  size_t nel = 0; file >> nel;
+  if( !file || nel == 0 || nel > 7 ) return XSB_ERR_IO;                                           // MAX_ELEMENTS = 7 (eam_alloy.h:137)
+  std::string all;
+  for(size_t i = 0; i < nel; i++) { std::string s; file >> s; all += (i ? " " : "") + s; }
+  size_t nrho = 0, nr = 0; double drho = 0, dr = 0, rc = 0;
+  file >> nrho >> drho >> nr >> dr >> rc;
+  if( !file || nrho < 5 || nr < 5 || drho <= 0 || dr <= 0 ) return XSB_ERR_IO;
+  const size_t nz = nel * (nel + 1) / 2;
+  std::vector<double> f(std::max(nrho, nr) + 1);
+  double* frho = new double[nel * (nrho + 1) * 8](); double* rhor = new double[nel * (nr + 1) * 8](); double* z2r = new double[nz * (nr + 1) * 8]();
+  bool ok = true;
+  for(size_t i = 0; i < nel && ok; i++)
+  {
+    int z; double mass, a0; std::string st;
+    file >> z >> mass >> a0 >> st;
+    f[0] = 0.0; for(size_t k = 0; k < nrho; k++) file >> f[k + 1];
+    if( !file ) { ok = false; break; }
+    interpolate(int(nrho), drho, f.data(), frho + i * (nrho + 1) * 8);
+    for(size_t k = 0; k < nr; k++) file >> f[k + 1];
+    if( !file ) { ok = false; break; }
+    interpolate(int(nr), dr, f.data(), rhor + i * (nr + 1) * 8);
+  }
+  for(size_t i = 0; i < nz && ok; i++)
+  {
+    for(size_t k = 0; k < nr; k++) file >> f[k + 1];
+    if( !file ) { ok = false; break; }
+    interpolate(int(nr), dr, f.data(), z2r + i * (nr + 1) * 8);
+  }
+  if( !ok ) { delete[] frho; delete[] rhor; delete[] z2r; return XSB_ERR_IO; }
+  out->nelements = int(nel); out->nr = int(nr); out->nrho = int(nrho);
+  out->rdr = 1.0 / dr; out->rdrho = 1.0 / drho; out->rc = rc; out->rhomax = (nrho - 1) * drho;
+  const double ev = 1.602176634e-19 / (1.66053906660e-27 * 1.0e4);   // 1 eV in (Da, ang, ps) units
+  out->conversion_z2r = ev; out->conversion_frho = ev;
+  out->frho = frho; out->rhor = rhor; out->z2r = z2r;
+  if( names && names_len ) { std::strncpy(names, all.c_str(), names_len - 1); names[names_len - 1] = 0; }
+  return XSB_OK;
+}
+
+void xsb_eam_alloy_free(xsb_eam_alloy_tables* t)
+{
+  if( !t ) return;
+  delete[] t->frho; delete[] t->rhor; delete[] t->z2r;
+  t->frho = t->rhor = t->z2r = nullptr;
+}
+
+int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, t && t->frho && t->rhor && t->z2r, XSB_ERR_INVALID, "null eam tables");
+  XSB_REQUIRE(ctx, t->nelements >= 1 && t->nelements <= 7 && t->nr >= 5 && t->nrho >= 5, XSB_ERR_INVALID, "bad eam table sizes");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  EamAlloyDev& E = ctx->eam;
+  const size_t nel = t->nelements, nz = nel * (nel + 1) / 2;
+  const size_t nf = nel * (t->nrho + 1) * 8, nrr = nel * (t->nr + 1) * 8, nzz = nz * (t->nr + 1) * 8;
+  XSB_CUDA(ctx, E.frho.reserve(nf));
+  XSB_CUDA(ctx, E.rtab.reserve(nrr + nzz));
+  XSB_CUDA(ctx, cudaMemcpyAsync(E.frho.p, t->frho, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(E.rtab.p, t->rhor, nrr * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(E.rtab.p + nrr, t->z2r, nzz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  E.nelements = t->nelements; E.nr = t->nr; E.nrho = t->nrho; E.rdr = t->rdr; E.rdrho = t->rdrho; E.rc = t->rc; E.rhomax = t->rhomax;
+  E.conv_z2r = t->conversion_z2r; E.conv_frho = t->conversion_frho; E.set = true;
+  return XSB_OK;
+}
+
+int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->eam.set, XSB_ERR_STATE, "xsb_eam_alloy_set must be called first");
+  XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
+  XSB_REQUIRE(ctx, rcut <= ctx->nbh_dist, XSB_ERR_INVALID, "rcut exceeds the neighbour-list distance nbh_dist_lab");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const EamAlloyDev& E = ctx->eam;
+  EamAlloyView T{ E.frho.p, E.rtab.p, E.rtab.p + size_t(E.nelements) * (E.nr + 1) * 8, E.nr, E.nrho, E.rdr, E.rdrho, E.rhomax, E.conv_z2r, E.conv_frho };
+  const bool eflag = phases & XSB_EAM_EFLAG, ghost = phases & XSB_EAM_GHOST;
+  const bool virial = eflag && (flags & XSB_FLAG_VIRIAL);
+  if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
+  const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;
+  constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
+  ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr, 0 };
+  double* emb = ctx->f64[XSB_F_RHO_DEMB].p;
+  const unsigned* sel = ghost ? nullptr : ctx->own_atoms.p; const unsigned nsel = unsigned(ghost ? ctx->n : ctx->n_own);
+  if( (phases & XSB_EAM_RHO) && ctx->n )
+  {
+    XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
+    P.atoms = sel; P.n_atoms = nsel;
+    if( nsel )
+    {
+      const unsigned grid = groups_grid<TPA>(nsel, block);
+      if( xf ) eam_alloy_rho_kernel<TPA, true ><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb);
+      else     eam_alloy_rho_kernel<TPA, false><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb);
+      XSB_LAUNCH_CHECK(ctx);
+    }
+  }
+  if( (phases & XSB_EAM_RHO2EMB) && nsel )
+  {
+    eam_alloy_rho2emb_kernel<<<(nsel + 255) / 256, 256, 0, ctx->stream>>>(sel, nsel, T, ctx->type.p, emb, eflag ? ctx->f64[XSB_F_EP].p : nullptr);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  if( (phases & XSB_EAM_FORCE) && ctx->n_own )
+  {
+    P.atoms = ctx->own_atoms.p; P.n_atoms = unsigned(ctx->n_own);
+    const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
+    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+#   define XSB_EAM_GO(XF, EF, VIR) eam_alloy_force_kernel<TPA, XF, EF, VIR><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb, fx, fy, fz, ep, vir)
+    if( xf ) { if( virial ) XSB_EAM_GO(true, true, true); else if( eflag ) XSB_EAM_GO(true, true, false); else XSB_EAM_GO(true, false, false); }
+    else     { if( virial ) XSB_EAM_GO(false, true, true); else if( eflag ) XSB_EAM_GO(false, true, false); else XSB_EAM_GO(false, false, false); }
+#   undef XSB_EAM_GO
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  return XSB_OK;
+}
+
+} // extern "C"

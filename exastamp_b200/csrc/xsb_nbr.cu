@@ -1,0 +1,316 @@
+// xsb_nbr.cu -- chunk_neighbors operator.
+//
+// Device representation: flat CSR list (count / offset / u32 flat neighbour index) in canonical order
+// (ascending neighbour cell, then ascending p_b) -- the order in which the reference stream is traversed.
+// The reference's own uint16 per-cell stream (decoder: src/rigidmol/compute_pair_rigidmol.h:154-234) is
+// produced on demand by xsb_chunk_neighbors_export() from the same list, honouring chunk_size and
+// build_particle_offset (data/config/config_move_particles.msp:54-61).
+//
+// Build = two warp-per-particle sweeps (count, then fill) over the (2Ry+1)(2Rz+1) x-rows of cells around the
+// particle's cell: cells of one row are contiguous in the flat SoA (i fastest), so each row is one coalesced
+// run of candidates; lanes test 32 candidates per step and ballot-compact the survivors.
+#include "xsb_ctx.h"
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
+
+namespace xsb
+{
+
+struct NbrParams
+{
+  GridView g;
+  int Rx, Ry, Rz;
+  double d2max;
+  unsigned n;
+};
+
+// physical-space squared distance with the CPU's operation order (no FMA contraction) so that the
+// membership test 0 < d2 < d2max is bit-identical to the host restatement.
+template<bool XFORM>
+__device__ __forceinline__ double nbh_d2(const GridView& g, double dx, double dy, double dz)
+{
+  if( XFORM )
+  {
+    const double* m = g.xf;
+    const double x = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dx), __dmul_rn(m[1], dy)), __dmul_rn(m[2], dz));
+    const double y = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dx), __dmul_rn(m[4], dy)), __dmul_rn(m[5], dz));
+    const double z = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dx), __dmul_rn(m[7], dy)), __dmul_rn(m[8], dz));
+    dx = x; dy = y; dz = z;
+  }
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// FILL=false: counts[a] ; FILL=true: idx[off[a] ...] in canonical order
+template<bool XFORM, bool FILL>
+__global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_of,
+                                                         const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                                         unsigned* __restrict__ counts, const unsigned long long* __restrict__ off, unsigned* __restrict__ idx)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if( a >= P.n ) return;
+  const unsigned ca = cell_of[a];
+  const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
+  const int ia = int(ca % unsigned(nx)), ja = int((ca / unsigned(nx)) % unsigned(ny)), ka = int(ca / (unsigned(nx) * unsigned(ny)));
+  const double xa = rx[a], ya = ry[a], za = rz[a];
+  const int ilo = max(0, ia - P.Rx), ihi = min(nx - 1, ia + P.Rx);
+  unsigned cnt = 0;
+  unsigned long long w = FILL ? off[a] : 0ull;
+  for(int rk = -P.Rz; rk <= P.Rz; rk++)
+  {
+    const int kb = ka + rk; if( kb < 0 || kb >= nz ) continue;
+    for(int rj = -P.Ry; rj <= P.Ry; rj++)
+    {
+      const int jb = ja + rj; if( jb < 0 || jb >= ny ) continue;
+      const unsigned row = unsigned(nx) * (unsigned(jb) + unsigned(ny) * unsigned(kb));
+      const unsigned b0 = cell_start[row + ilo], b1 = cell_start[row + ihi + 1];
+      for(unsigned base = b0; base < b1; base += 32u)
+      {
+        const unsigned b = base + lane;
+        bool keep = false;
+        if( b < b1 && b != a )
+        {
+          const double d2 = nbh_d2<XFORM>(P.g, rx[b] - xa, ry[b] - ya, rz[b] - za);
+          keep = d2 > 0.0 && d2 < P.d2max;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if( FILL )
+        {
+          if( keep ) idx[w + __popc(m & ((1u << lane) - 1u))] = b;
+          w += __popc(m);
+        }
+        else cnt += __popc(m);
+      }
+    }
+  }
+  if( !FILL && lane == 0 ) counts[a] = cnt;
+}
+
+// ---- export to the reference uint16 stream ---------------------------------------------------------
+__device__ __forceinline__ unsigned short encode_cell_index(int ri, int rj, int rk)
+{
+  return (unsigned short)((ri + 16) | ((rj + 16) << 5) | ((rk + 16) << 10));
+}
+
+// per-particle stream length: 1 + 2*groups + chunks
+__global__ void stream_len_kernel(unsigned n, const unsigned long long* __restrict__ off, const unsigned* __restrict__ idx,
+                                  const unsigned* __restrict__ cell_of, const unsigned* __restrict__ cell_start, int cs_log2,
+                                  unsigned long long* __restrict__ len)
+{
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if( a >= n ) return;
+  unsigned groups = 0, chunks = 0, pc = 0xffffffffu, pk = 0xffffffffu;
+  for(unsigned long long e = off[a]; e < off[a+1]; e++)
+  {
+    const unsigned b = idx[e], c = cell_of[b], k = (b - cell_start[c]) >> cs_log2;
+    if( c != pc ) { ++groups; ++chunks; pc = c; pk = k; }
+    else if( k != pk ) { ++chunks; pk = k; }
+  }
+  len[a] = 1ull + 2ull * groups + chunks;
+}
+
+__global__ void stream_off_kernel(unsigned ncells, const unsigned* __restrict__ cell_start, const unsigned long long* __restrict__ poff,
+                                  int has_offsets, unsigned long long* __restrict__ stream_off)
+{
+  const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+  if( c > ncells ) return;
+  const unsigned s = cell_start[c];
+  stream_off[c] = poff[s] + (has_offsets ? 2ull * s : 0ull);
+}
+
+__global__ void stream_fill_kernel(unsigned n, GridView g, const unsigned long long* __restrict__ off, const unsigned* __restrict__ idx,
+                                   const unsigned* __restrict__ cell_of, const unsigned* __restrict__ cell_start, int cs_log2, int has_offsets,
+                                   const unsigned long long* __restrict__ poff, const unsigned long long* __restrict__ stream_off,
+                                   unsigned short* __restrict__ data)
+{
+  const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+  if( a >= n ) return;
+  const unsigned ca = cell_of[a], s = cell_start[ca], na = cell_start[ca + 1] - s, p = a - s;
+  const unsigned long long rel = poff[a] - poff[s];
+  unsigned short* cell_stream = data + stream_off[ca];
+  if( has_offsets )
+  {
+    const unsigned o = 2u * na + unsigned(rel);
+    cell_stream[2*p] = (unsigned short)(o & 0xFFFFu); cell_stream[2*p+1] = (unsigned short)(o >> 16);
+    cell_stream += 2u * na;
+  }
+  unsigned short* w = cell_stream + rel;
+  unsigned short* groups_pos = w++; unsigned short* nchunks_pos = nullptr;
+  unsigned groups = 0, nchunks = 0, pc = 0xffffffffu, pk = 0xffffffffu;
+  const int nx = g.nx, ny = g.ny;
+  const int ia = int(ca % unsigned(nx)), ja = int((ca / unsigned(nx)) % unsigned(ny)), ka = int(ca / (unsigned(nx) * unsigned(ny)));
+  for(unsigned long long e = off[a]; e < off[a+1]; e++)
+  {
+    const unsigned b = idx[e], c = cell_of[b], k = (b - cell_start[c]) >> cs_log2;
+    if( c != pc )
+    {
+      if( nchunks_pos ) *nchunks_pos = (unsigned short)nchunks;
+      const int ib = int(c % unsigned(nx)), jb = int((c / unsigned(nx)) % unsigned(ny)), kb = int(c / (unsigned(nx) * unsigned(ny)));
+      *(w++) = encode_cell_index(ib - ia, jb - ja, kb - ka);
+      nchunks_pos = w++; nchunks = 0; ++groups; pc = c; pk = 0xffffffffu;
+    }
+    if( k != pk ) { *(w++) = (unsigned short)k; ++nchunks; pk = k; }
+  }
+  if( nchunks_pos ) *nchunks_pos = (unsigned short)nchunks;
+  *groups_pos = (unsigned short)groups;
+}
+
+__global__ void widen_kernel(unsigned n, const unsigned* __restrict__ in, unsigned long long* __restrict__ out)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i < n ) out[i] = in[i];
+}
+
+static int exclusive_scan_u64(xsb_ctx* ctx, const unsigned long long* in, unsigned long long* out, size_t n)
+{
+  size_t tmp = 0;
+  XSB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
+  XSB_CUDA(ctx, ctx->scratch.reserve(tmp + 16));
+  XSB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scratch.p, tmp, in, out, n, ctx->stream));
+  ctx->launches += 2;
+  return XSB_OK;
+}
+
+} // namespace xsb
+
+using namespace xsb;
+
+extern "C" {
+
+int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk_neighbors_config* cfg)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "grid/particles not set");
+  XSB_REQUIRE(ctx, nbh_dist_lab > 0.0, XSB_ERR_INVALID, "nbh_dist_lab must be > 0");
+  if( cfg )
+  {
+    int cs = cfg->chunk_size;
+    XSB_REQUIRE(ctx, cs >= 1 && cs <= 32 && (cs & (cs - 1)) == 0, XSB_ERR_INVALID, "chunk_size is not a power of two in 1..32");
+    ctx->nbh_cfg = *cfg;
+    if( ctx->nbh_cfg.stream_prealloc_factor < 1.0 ) ctx->nbh_cfg.stream_prealloc_factor = 1.0;
+  }
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned n = unsigned(ctx->n);
+  ctx->nbh_built = false; ctx->nbh_total = 0; ctx->nbh_max = 0; ctx->nbh_dist = nbh_dist_lab;
+  XSB_CUDA(ctx, ctx->nbh_count.reserve(n + 1, 1.02));
+  XSB_CUDA(ctx, ctx->nbh_off.reserve(n + 2, 1.02));
+  XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, 1.02));
+  if( n == 0 ) { ctx->nbh_built = true; return XSB_OK; }
+  NbrParams P; P.g = ctx->view(); P.n = n; P.d2max = nbh_dist_lab * nbh_dist_lab;
+  int R[3]; search_range(ctx->grid, nbh_dist_lab, R); P.Rx = R[0]; P.Ry = R[1]; P.Rz = R[2];
+  const int block = 256; const unsigned grid = unsigned((uint64_t(n) * 32 + block - 1) / block);
+  const double *rx = ctx->f64[XSB_F_RX].p, *ry = ctx->f64[XSB_F_RY].p, *rz = ctx->f64[XSB_F_RZ].p;
+  if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr);
+  else                     nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr);
+  XSB_LAUNCH_CHECK(ctx);
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->scratch64.p + n, 0, sizeof(unsigned long long), ctx->stream));
+  widen_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->nbh_count.p, ctx->scratch64.p);
+  XSB_LAUNCH_CHECK(ctx);
+  int rc = exclusive_scan_u64(ctx, ctx->scratch64.p, ctx->nbh_off.p, size_t(n) + 1); if( rc ) return rc;
+  unsigned long long total = 0;
+  {
+    size_t tmp = 0; unsigned* dmax = reinterpret_cast<unsigned*>(ctx->scratch64.p);   // scratch64 is free again after the scan
+    XSB_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tmp, ctx->nbh_count.p, dmax, int(n), ctx->stream));
+    XSB_CUDA(ctx, ctx->scratch.reserve(tmp + 16));
+    XSB_CUDA(ctx, cub::DeviceReduce::Max(ctx->scratch.p, tmp, ctx->nbh_count.p, dmax, int(n), ctx->stream));
+    ctx->launches += 1;
+    XSB_CUDA(ctx, cudaMemcpyAsync(&ctx->nbh_max, dmax, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  XSB_CUDA(ctx, cudaMemcpyAsync(&total, ctx->nbh_off.p + n, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nbh_total = total;
+  XSB_CUDA(ctx, ctx->nbh_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+  if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
+  else                     nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
+  XSB_LAUNCH_CHECK(ctx);
+  ctx->nbh_built = true;
+  return XSB_OK;
+}
+
+int xsb_chunk_neighbors_stats(xsb_ctx* ctx, uint64_t* total, uint32_t* maxn)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors not built");
+  if( total ) *total = ctx->nbh_total;
+  if( maxn ) *maxn = ctx->nbh_max;
+  return XSB_OK;
+}
+
+static int export_prepare(xsb_ctx* ctx, DevBuf<unsigned long long>& poff, DevBuf<unsigned long long>& soff, uint64_t* total_u16)
+{
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors not built");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned n = unsigned(ctx->n), nc = unsigned(ctx->ncells);
+  int cs_log2 = 0; while( (1 << cs_log2) < ctx->nbh_cfg.chunk_size ) ++cs_log2;
+  XSB_CUDA(ctx, poff.reserve(size_t(n) + 2));
+  XSB_CUDA(ctx, soff.reserve(size_t(nc) + 2));
+  XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(n) + 2));
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->scratch64.p, 0, (size_t(n) + 1) * sizeof(unsigned long long), ctx->stream));
+  if( n )
+  {
+    stream_len_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->cell_of.p, ctx->cell_start.p, cs_log2, ctx->scratch64.p);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  int rc = exclusive_scan_u64(ctx, ctx->scratch64.p, poff.p, size_t(n) + 1); if( rc ) return rc;
+  stream_off_kernel<<<(nc + 1 + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->cell_start.p, poff.p, ctx->nbh_cfg.build_particle_offset, soff.p);
+  XSB_LAUNCH_CHECK(ctx);
+  unsigned long long tot = 0;
+  XSB_CUDA(ctx, cudaMemcpyAsync(&tot, soff.p + nc, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *total_u16 = tot;
+  return XSB_OK;
+}
+
+int xsb_chunk_neighbors_export_size(xsb_ctx* ctx, uint64_t* total_u16)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, total_u16 != nullptr, XSB_ERR_INVALID, "null output");
+  DevBuf<unsigned long long> poff, soff;
+  int rc = export_prepare(ctx, poff, soff, total_u16);
+  poff.release(); soff.release();
+  return rc;
+}
+
+int xsb_chunk_neighbors_export(xsb_ctx* ctx, uint64_t* stream_off, uint16_t* data)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, stream_off != nullptr && data != nullptr, XSB_ERR_INVALID, "null output");
+  DevBuf<unsigned long long> poff, soff; DevBuf<unsigned short> dd;
+  uint64_t tot = 0;
+  int rc = export_prepare(ctx, poff, soff, &tot);
+  if( rc == XSB_OK )
+  {
+    const unsigned n = unsigned(ctx->n);
+    int cs_log2 = 0; while( (1 << cs_log2) < ctx->nbh_cfg.chunk_size ) ++cs_log2;
+    cudaError_t e = dd.reserve(tot + 16);
+    if( e != cudaSuccess ) rc = ctx->fail(XSB_ERR_CUDA, "export buffer: %s", cudaGetErrorString(e));
+    else
+    {
+      if( n )
+      {
+        stream_fill_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->view(), ctx->nbh_off.p, ctx->nbh_idx.p, ctx->cell_of.p, ctx->cell_start.p, cs_log2,
+                                                                      ctx->nbh_cfg.build_particle_offset, poff.p, soff.p, dd.p);
+        ctx->launches++;
+      }
+      e = cudaMemcpyAsync(stream_off, soff.p, (ctx->ncells + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if( e == cudaSuccess && tot ) e = cudaMemcpyAsync(data, dd.p, tot * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if( e == cudaSuccess ) e = cudaStreamSynchronize(ctx->stream);
+      if( e != cudaSuccess ) rc = ctx->fail(XSB_ERR_CUDA, "export: %s", cudaGetErrorString(e));
+    }
+  }
+  poff.release(); soff.release(); dd.release();
+  return rc;
+}
+
+int xsb_chunk_neighbors_download_flat(xsb_ctx* ctx, uint32_t* counts, uint64_t* offsets, uint32_t* idx)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors not built");
+  if( counts && ctx->n ) XSB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->nbh_count.p, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if( offsets ) XSB_CUDA(ctx, cudaMemcpyAsync(offsets, ctx->nbh_off.p, (ctx->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if( idx && ctx->nbh_total ) XSB_CUDA(ctx, cudaMemcpyAsync(idx, ctx->nbh_idx.p, ctx->nbh_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XSB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,164 @@
+// xsb_pair.cu -- <pot>_compute_force and <pot>_multi_force.
+// Reference functors: src/potential/pair_potential_template/pair_potential_force_op_singlemat.h:45-218 with body
+// force_op_impl2.hxx:22-78 (single species) and pair_potential_force_op_multiparam.h:76-223 (per type pair).
+// Potential math: src/potential/pair_potentials/lennard_jones/include/.../lennard_jones.h:40-50.
+#include "xsb_traverse.cuh"
+
+namespace xsb
+{
+
+struct LJPair { double eps4, eps24, sigma2, ecut, rcut2; };   // 4*eps, 24*eps, sigma^2, e(rcut), rcut^2
+
+struct LJMulti { LJPair pp[16]; };   // indexed by unique_pair_id (MAX_TYPE_PAIR_IDS = 16, multiparam.h:68)
+
+__host__ __device__ inline unsigned unique_pair_id(unsigned a, unsigned b) { return a > b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// LJ from d2 only (algebraically identical to lj_compute_energy followed by de/r):
+//   e = 4 eps (s^12 - s^6) - ecut ;  de/r = -24 eps (2 s^12 - s^6) / r^2
+template<class real>
+__device__ __forceinline__ void lj_eval(const LJPair& p, real d2, real& e, real& de_r)
+{
+  const real rinv2 = real(1) / d2;
+  const real s2 = real(p.sigma2) * rinv2;
+  const real s6 = s2 * s2 * s2;
+  const real s12 = s6 * s6;
+  e = real(p.eps4) * (s12 - s6) - real(p.ecut);
+  de_r = -real(p.eps24) * (real(2) * s12 - s6) * rinv2;
+}
+
+template<int TPA, bool XFORM, bool MULTI, bool VIRIAL, class real>
+__global__ void __launch_bounds__(256) pair_force_kernel(ParticleView P, XForm X, LJMulti prm, double rcut2_max,
+                                                          double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                                                          double* __restrict__ ep, double* __restrict__ vir)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = t / TPA, sub = t % TPA;
+  const bool valid = g < P.n_atoms;
+  unsigned a = 0; unsigned long long e0 = 0, e1 = 0;
+  double xa = 0, ya = 0, za = 0; unsigned ta = 0;
+  if( valid )
+  {
+    a = P.atoms ? P.atoms[g] : g;
+    e0 = P.nbh_off[a]; e1 = P.nbh_off[a + 1];
+    xa = P.rx[a]; ya = P.ry[a]; za = P.rz[a];
+    if( MULTI ) ta = P.type[a];
+  }
+  double sfx = 0, sfy = 0, sfz = 0, sep = 0;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0, v7 = 0, v8 = 0;
+  for(unsigned long long e = e0 + sub; e < e1; e += TPA)
+  {
+    const unsigned b = P.nbh_idx[e];
+    double dx = P.rx[b] - xa, dy = P.ry[b] - ya, dz = P.rz[b] - za;
+    apply_xform<XFORM>(X, dx, dy, dz);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if( d2 <= rcut2_max )
+    {
+      const LJPair& pp = MULTI ? prm.pp[unique_pair_id(ta, P.type[b])] : prm.pp[0];
+      if( !MULTI || d2 <= pp.rcut2 )
+      {
+        real e_, de_r;
+        lj_eval<real>(pp, real(d2), e_, de_r);
+        const double fex = double(de_r) * dx, fey = double(de_r) * dy, fez = double(de_r) * dz;
+        sfx += fex; sfy += fey; sfz += fez; sep += 0.5 * double(e_);
+        if( VIRIAL )
+        {
+          v0 -= 0.5 * fex * dx; v1 -= 0.5 * fex * dy; v2 -= 0.5 * fex * dz;
+          v3 -= 0.5 * fey * dx; v4 -= 0.5 * fey * dy; v5 -= 0.5 * fey * dz;
+          v6 -= 0.5 * fez * dx; v7 -= 0.5 * fez * dy; v8 -= 0.5 * fez * dz;
+        }
+      }
+    }
+  }
+  sfx = group_sum<TPA>(sfx); sfy = group_sum<TPA>(sfy); sfz = group_sum<TPA>(sfz); sep = group_sum<TPA>(sep);
+  if( VIRIAL )
+  {
+    v0 = group_sum<TPA>(v0); v1 = group_sum<TPA>(v1); v2 = group_sum<TPA>(v2);
+    v3 = group_sum<TPA>(v3); v4 = group_sum<TPA>(v4); v5 = group_sum<TPA>(v5);
+    v6 = group_sum<TPA>(v6); v7 = group_sum<TPA>(v7); v8 = group_sum<TPA>(v8);
+  }
+  if( valid && sub == 0 )
+  {
+    fx[a] += sfx; fy[a] += sfy; fz[a] += sfz;
+    if( ep ) ep[a] += sep;
+    if( VIRIAL )
+    {
+      double* v = vir + 9ull * a;
+      v[0] += v0; v[1] += v1; v[2] += v2; v[3] += v3; v[4] += v4; v[5] += v5; v[6] += v6; v[7] += v7; v[8] += v8;
+    }
+  }
+}
+
+static LJPair make_lj(double eps, double sigma, double rcut)
+{
+  LJPair p; p.eps4 = 4.0 * eps; p.eps24 = 24.0 * eps; p.sigma2 = sigma * sigma; p.rcut2 = rcut * rcut; p.ecut = 0.0;
+  if( rcut > 0.0 )   // energy_cutoff(): e(rcut) through the reference formula (pair_potential_impl.hxx:488-498)
+  {
+    const double ratio = sigma / rcut, r2 = ratio * ratio, r6 = r2 * r2 * r2, r12 = r6 * r6;
+    p.ecut = 4. * eps * (r12 - r6);
+  }
+  return p;
+}
+
+template<bool MULTI>
+static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int flags)
+{
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
+  XSB_REQUIRE(ctx, rcut_max <= ctx->nbh_dist, XSB_ERR_INVALID, "rcut exceeds the neighbour-list distance nbh_dist_lab");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool ghost = flags & XSB_FLAG_GHOST, virial = flags & XSB_FLAG_VIRIAL, mixed = flags & XSB_FLAG_MIXED;
+  if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
+  ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p,
+                  ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own) };
+  if( P.n_atoms == 0 ) return XSB_OK;
+  const XForm X = make_xform(ctx->grid);
+  constexpr int TPA = 8; const int block = 256;
+  const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
+  double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p;
+  double *ep = (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr, *vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+  const double rc2 = rcut_max * rcut_max;
+  const bool xf = !ctx->grid.xform_is_identity;
+# define XSB_PAIR_GO(XF, VIR, REAL) pair_force_kernel<TPA, XF, MULTI, VIR, REAL><<<grid, block, 0, ctx->stream>>>(P, X, prm, rc2, fx, fy, fz, ep, vir)
+  if( mixed ) { if( xf ) { if( virial ) XSB_PAIR_GO(true, true, float); else XSB_PAIR_GO(true, false, float); }
+                else     { if( virial ) XSB_PAIR_GO(false, true, float); else XSB_PAIR_GO(false, false, float); } }
+  else        { if( xf ) { if( virial ) XSB_PAIR_GO(true, true, double); else XSB_PAIR_GO(true, false, double); }
+                else     { if( virial ) XSB_PAIR_GO(false, true, double); else XSB_PAIR_GO(false, false, double); } }
+# undef XSB_PAIR_GO
+  XSB_LAUNCH_CHECK(ctx);
+  return XSB_OK;
+}
+
+} // namespace xsb
+
+using namespace xsb;
+
+extern "C" {
+
+int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, pot == XSB_POT_LJ, XSB_ERR_UNSUPPORTED, "pair potential not implemented (only lj)");
+  XSB_REQUIRE(ctx, params != nullptr && nparams == 2, XSB_ERR_INVALID, "lj expects 2 parameters: epsilon, sigma");
+  XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
+  LJMulti prm; prm.pp[0] = make_lj(params[0], params[1], rcut);
+  return launch_pair<false>(ctx, prm, rcut, flags);
+}
+
+int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, double rcut_max, int flags)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, pot == XSB_POT_LJ, XSB_ERR_UNSUPPORTED, "pair potential not implemented (only lj)");
+  XSB_REQUIRE(ctx, pair_params != nullptr && nparams == 2, XSB_ERR_INVALID, "lj expects rows of {epsilon, sigma, rcut}");
+  const int npairs = n_types * (n_types + 1) / 2;
+  XSB_REQUIRE(ctx, n_types >= 1 && npairs <= 16, XSB_ERR_INVALID, "too many type pairs (MAX_TYPE_PAIR_IDS = 16)");
+  LJMulti prm; double rmax = 0.0;
+  for(int i = 0; i < npairs; i++)
+  {
+    const double* row = pair_params + 3 * i;
+    prm.pp[i] = make_lj(row[0], row[1], row[2]);
+    if( row[2] > rmax ) rmax = row[2];
+  }
+  XSB_REQUIRE(ctx, rcut_max >= rmax, XSB_ERR_INVALID, "rcut_max is smaller than a pair rcut");
+  return launch_pair<true>(ctx, prm, rcut_max, flags);
+}
+
+} // extern "C"

@@ -1,0 +1,177 @@
+/*
+ * xsb200.h -- C ABI of libxsb200.so: the B200-native (sm_100a) implementation of exaStamp's short-range
+ * force hot path (chunk_neighbors + pair / EAM / SNAP force operators + ghost exchange).
+ *
+ * exaStamp exposes no C ABI: a force field is an onika::scg::OperatorNode subclass registered under a YAML
+ * name (src/potential/pair_potential_template/pair_potential_impl.hxx:510-513).  Each entry point below is
+ * what the `execute()` of one of those operators needs once its slots have been resolved; the reference
+ * interface it replaces is cited per function (paths relative to the exaStamp source tree).  INTEGRATION.md
+ * shows the ~30-line OperatorNode shim that forwards slots to these calls.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every call returns XSB_OK (0) or an xsb_status error code and never
+ *    aborts; xsb_last_error() gives the message.  One context per GPU, not thread-safe per context.
+ *  - all calls enqueue work on the context's CUDA stream and return; xsb_sync() waits.  Downloads sync.
+ *  - particle data: flat SoA sorted by cell (cells IJK row-major, i fastest, ghost layers included), flat
+ *    index = cell_particle_offset[cell] + p  -- the layout of exanb::Grid::cell_particle_offset_data().
+ *    Positions are in grid space; physical = xform * r (exanb::Domain::xform).  Quantities are in exaStamp
+ *    internal units (angstrom, Da, ps, e, K : include/exaStamp/unit_system.h:28-36).
+ *  - force operators ACCUMULATE (+=) into fx,fy,fz,ep,virial like the reference functors, so several can be
+ *    chained under `compute_force: [...]`; xsb_zero_force_energy() is the `zero_force_energy` operator.
+ *  - there is no CPU fallback: every compute entry point fails with XSB_ERR_CUDA when no sm_100 device is
+ *    usable.
+ */
+#ifndef XSB200_H
+#define XSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xsb_ctx xsb_ctx;
+
+typedef enum xsb_status {
+  XSB_OK = 0, XSB_ERR_INVALID = 1, XSB_ERR_CUDA = 2, XSB_ERR_STATE = 3, XSB_ERR_NCCL = 4, XSB_ERR_IO = 5,
+  XSB_ERR_UNSUPPORTED = 6, XSB_ERR_OVERFLOW = 7
+} xsb_status;
+
+/* exanb::Grid + exanb::Domain as seen by the force operators (accessors listed in SURVEY.md 8a row a1) */
+typedef struct xsb_grid_desc {
+  int32_t dims[3];            /* grid.dimension(): cells per axis INCLUDING ghost layers            */
+  int32_t ghost_layers;       /* grid.ghost_layers()                                                */
+  double  cell_size;          /* domain.cell_size(), grid space                                     */
+  double  origin[3];          /* grid-space corner of cell (0,0,0) (grid.origin() + offset*cell)    */
+  double  xform[9];           /* domain.xform(), row-major; physical = xform * grid-space           */
+  int32_t xform_is_identity;  /* domain.xform_is_identity()                                         */
+  int32_t pad_;
+} xsb_grid_desc;
+
+/* per-particle fields (include/exaStamp/fields.h:32-37,64-70 + exanb rx,ry,rz,fx..,vx..,id,type) */
+typedef enum xsb_field {
+  XSB_F_RX = 0, XSB_F_RY, XSB_F_RZ, XSB_F_FX, XSB_F_FY, XSB_F_FZ, XSB_F_EP,     /* double               */
+  XSB_F_VX, XSB_F_VY, XSB_F_VZ,                                                  /* double               */
+  XSB_F_VIRIAL,                                                                  /* 9 doubles/atom Mat3d */
+  XSB_F_RHO_DEMB,                                                                /* double (eam_buffer.h:37-49 field "rho_dEmb") */
+  XSB_F_TYPE,                                                                    /* uint8                */
+  XSB_F_ID,                                                                      /* uint64               */
+  XSB_F_COUNT_
+} xsb_field;
+
+/* operator flags (slots `ghost`, grid-has-virial, trigger_thermo_state, ...) */
+enum {
+  XSB_FLAG_GHOST   = 1,   /* slot `ghost`: also compute central atoms of ghost cells                    */
+  XSB_FLAG_ENERGY  = 2,   /* accumulate ep                                                              */
+  XSB_FLAG_VIRIAL  = 4,   /* accumulate per-atom virial (grid field set has field::virial)              */
+  XSB_FLAG_MIXED   = 8    /* FP32 pair math, FP64 accumulation (north_star "mixed mode", tol 1e-5)      */
+};
+
+/* eam_alloy_force phase slots (src/potential/eam_potential_template/eam_potential_multimat.cu:101-105) */
+enum {
+  XSB_EAM_RHO = 1, XSB_EAM_RHO2EMB = 2, XSB_EAM_GHOST = 4, XSB_EAM_FORCE = 8,
+  XSB_EAM_EFLAG = 16  /* trigger_thermo_state: ep (+ virial when XSB_FLAG_VIRIAL given in flags) */
+};
+
+/* pair potentials behind <pot>_compute_force / <pot>_multi_force (src/potential/pair_potentials/) */
+typedef enum xsb_pair_pot { XSB_POT_LJ = 0 /* params: epsilon, sigma */ } xsb_pair_pot;
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* context                                                                                              */
+int         xsb_create(int device, xsb_ctx** out);         /* onika init_cuda / ParallelExecutionContext  */
+void        xsb_destroy(xsb_ctx* ctx);
+const char* xsb_last_error(const xsb_ctx* ctx);
+int         xsb_sync(xsb_ctx* ctx);
+const char* xsb_version(void);
+uint64_t    xsb_kernel_launch_count(const xsb_ctx* ctx);   /* CUDA kernels launched by this context so far */
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a1  Grid / GridCellParticles                                                                         */
+int      xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* grid);
+/* cell_particle_offset: host array of ncells+1 entries (exanb::Grid::cell_particle_offset_data()).     */
+int      xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* cell_particle_offset);
+uint64_t xsb_num_particles(const xsb_ctx* ctx);
+uint64_t xsb_num_cells(const xsb_ctx* ctx);
+/* whole-array copies between host buffers and the context's device SoA (N or 9N elements)              */
+int      xsb_field_upload(xsb_ctx* ctx, int field, const void* host_src);
+int      xsb_field_download(xsb_ctx* ctx, int field, void* host_dst);
+/* device pointer of a field (zero-copy for callers that already live on the GPU, e.g. managed grids)   */
+void*    xsb_field_device_ptr(xsb_ctx* ctx, int field);
+/* zero_force_energy operator (src/compute/zero_force_energy.cu:98-135): fx,fy,fz,ep,(virial) = 0       */
+int      xsb_zero_force_energy(xsb_ctx* ctx, int ghost);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a2  chunk_neighbors operator (config: data/config/config_move_particles.msp:54-61; entry point        */
+/*     chunk_neighbors_execute, src/particle_species/type_pair_rcut_neighbors.cpp:136)                    */
+typedef struct xsb_chunk_neighbors_config {
+  int32_t chunk_size;              /* power of two, 1..32 (only affects the exported stream)            */
+  int32_t build_particle_offset;   /* emit the per-particle offset table in the exported stream         */
+  int32_t subcell_compaction;      /* accepted, no effect (host-side AMR detail of the reference)       */
+  int32_t free_scratch_memory;     /* release build scratch after each build                            */
+  double  stream_prealloc_factor;  /* growth factor of the device list allocation (>=1)                 */
+} xsb_chunk_neighbors_config;
+/* builds, for every particle of every cell (ghost cells included), the list of (cell_b,p_b) with        */
+/* 0 < |xform*(r_b-r_a)|^2 < nbh_dist_lab^2, in canonical order (ascending cell_b, then p_b).            */
+int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk_neighbors_config* cfg);
+int xsb_chunk_neighbors_stats(xsb_ctx* ctx, uint64_t* total_neighbors, uint32_t* max_neighbors);
+/* exanb::GridChunkNeighbors in the reference uint16 per-cell stream format (decoder:                    */
+/* src/rigidmol/compute_pair_rigidmol.h:154-234).  stream_off: ncells+1 offsets in uint16 units.         */
+int xsb_chunk_neighbors_export_size(xsb_ctx* ctx, uint64_t* total_u16);
+int xsb_chunk_neighbors_export(xsb_ctx* ctx, uint64_t* stream_off, uint16_t* data);
+/* flat CSR view of the same list (device resident): counts[N] (u32), offsets[N+1] (u64), idx (u32)     */
+int xsb_chunk_neighbors_download_flat(xsb_ctx* ctx, uint32_t* counts, uint64_t* offsets, uint32_t* idx);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a3-a6  <pot>_compute_force (pair_potential_impl.hxx:39-500) and <pot>_multi_force                     */
+/*        (pair_potential_force_op_multiparam.h:57-223).  ecut = e(rcut) is computed inside              */
+/*        (energy_cutoff, pair_potential_impl.hxx:488-498).                                              */
+int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags);
+/* pair_params: one row per unique_pair_id(type_a,type_b) = hi*(hi+1)/2+lo : {params..., rcut}           */
+int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams,
+                         double rcut_max, int flags);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a7  johnson_force / johnson_emb / johnson_force_reuse_emb (eam_potential.cu:69-176, johnson.h:56-166)  */
+/*     params19: re fe rhoe alpha beta A B kappa lambda Fn0..Fn3 F0..F3 Fo eta.                          */
+/*     phases: bit0 emb pass, bit1 emb pass covers ghost cells (ComputeGhostEmb), bit2 force pass.        */
+int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int phases, int flags);
+
+/* a8  eam_alloy_force (eam_potential_multimat.cu:65-259, eam_alloy.h:37-313).                           */
+typedef struct xsb_eam_alloy_tables {
+  int32_t nelements, nr, nrho, pad_;
+  double  rdr, rdrho, rc, rhomax;
+  double  conversion_z2r, conversion_frho;   /* 1 eV.ang and 1 eV in internal units (eam_alloy.h:154-155) */
+  const double* frho;   /* [nelements][nrho+1][8]  7-coefficient rows padded to 8 (eam_alloy.h:37-42)    */
+  const double* rhor;   /* [nelements][nr+1][8]                                                          */
+  const double* z2r;    /* [nelements(nelements+1)/2][nr+1][8]                                           */
+} xsb_eam_alloy_tables;
+/* reads a setfl file and builds the spline tables (eam_alloy.cpp:66-278); free with xsb_eam_alloy_free  */
+int  xsb_eam_alloy_read(const char* path, xsb_eam_alloy_tables* out, char* names, size_t names_len);
+void xsb_eam_alloy_free(xsb_eam_alloy_tables* t);
+int  xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t);   /* uploads tables (host pointers)  */
+int  xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* a10 ghost operators.  Single rank: ghosts are periodic images inside the same context.                */
+typedef struct xsb_domain_desc {
+  int32_t global_cells[3];   /* own (non-ghost) cells of the whole domain                               */
+  int32_t periodic[3];
+  int32_t rank_dims[3];      /* brick decomposition, product = number of ranks                          */
+  int32_t rank_coord[3];     /* this rank's brick                                                        */
+  double  box[3];            /* domain extent in grid space (global_cells * cell_size)                   */
+} xsb_domain_desc;
+/* NCCL communicator from a 128-byte ncclUniqueId created by rank 0 (xsb_comm_unique_id)                  */
+int xsb_comm_unique_id(void* id128);
+int xsb_comm_init(xsb_ctx* ctx, int nranks, int rank, const void* id128);
+/* ghost_comm_scheme + ghost_update_all_no_fv (config_move_particles.msp:82-87): given the own-cell       */
+/* particle counts, lays out ghost cells, exchanges counts and fills every ghost field.                   */
+int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom, const uint64_t* own_cell_count);
+/* ghost_update_r / ghost_update_opt: owner -> ghost copy of the fields in field_mask (bit = xsb_field)   */
+int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
+/* update_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29): ghost -> owner add                  */
+int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSB200_H */

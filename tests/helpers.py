@@ -80,3 +80,57 @@ class GridSystem:
 
     def zeros(self):
         return np.zeros(self.n, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic potential parameter sets / files
+# ---------------------------------------------------------------------------------------------------
+EV = 1.602176634e-19 / (1.66053906660e-27 * 1.0e4)   # 1 eV in internal units (ang, Da, ps)
+
+# Johnson-form EAM parameter set: the only one shipped by the reference is Ta
+# (data/regression_new/potentials/eam/eam_johnson/single_specy.msp:6-27); a Cu set of the same functional
+# form (Zhou/Johnson/Wadley 2004 Cu values, eV / ang) is used for the FCC Cu benchmark.  Energies in eV
+# are converted to internal units by the caller (johnson_params()).
+JOHNSON_CU = dict(re=2.556162, fe=1.554485, rhoe=21.175871, alpha=8.127620, beta=4.334731, A=0.396620, B=0.548085,
+                  kappa=0.308782, **{"lambda": 0.756515}, Fn0=-2.170269, Fn1=-0.263788, Fn2=1.088878, Fn3=-0.817603,
+                  F0=-2.19, F1=0.0, F2=0.561830, F3=-2.100595, Fo=-2.186568, eta=0.310490)
+_J_ORDER = ["re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lambda", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta"]
+_J_ENERGY = {"A", "B", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo"}
+
+
+def johnson_params(d=JOHNSON_CU):
+    """19 scalars in the reference's order (johnson.h:29-50), energies converted eV -> internal."""
+    return np.array([d[k] * (EV if k in _J_ENERGY else 1.0) for k in _J_ORDER], dtype=np.float64)
+
+
+def write_setfl(path, elements, nrho=2000, drho=0.1, nr=2000, rc=7.29, rmin=0.6):
+    """write a setfl (eam/alloy) file with Sutton-Chen-form tables, the same functional forms as the reference's
+    generator scripts/python/pytab-eam-alloy/pytab-eam-alloy-sutton-chen.py (F=-c*eps*sqrt(rho), rho=(a/r)^m,
+    r*phi = r*eps*(a/r)^n), evaluated with r clamped below at `rmin` so every knot is finite.
+    elements: list of dict(name, z, mass, a0, c, eps, a, n, m).  Cross pairs use arithmetic/geometric mixing."""
+    dr = rc / nr
+    r = np.maximum(np.arange(nr) * dr, rmin)
+    rho_x = np.arange(nrho) * drho
+    with open(path, "w") as f:
+        f.write("synthetic Sutton-Chen setfl generated by tests/helpers.py\nxsb200 test fixture\nXX\n")
+        f.write("%d %s\n" % (len(elements), " ".join(e["name"] for e in elements)))
+        f.write("%d %.12e %d %.12e %.12e\n" % (nrho, drho, nr, dr, rc))
+        for e in elements:
+            f.write("%d %.4f %.4f fcc\n" % (e["z"], e["mass"], e["a0"]))
+            F = -e["c"] * e["eps"] * np.sqrt(rho_x)
+            rho = (e["a"] / r) ** e["m"]
+            f.write("\n".join("%.16e" % v for v in F) + "\n")
+            f.write("\n".join("%.16e" % v for v in rho) + "\n")
+        for i in range(len(elements)):
+            for j in range(i + 1):
+                ei, ej = elements[i], elements[j]
+                eps = np.sqrt(ei["eps"] * ej["eps"]); a = 0.5 * (ei["a"] + ej["a"]); n = 0.5 * (ei["n"] + ej["n"])
+                rphi = r * eps * (a / r) ** n
+                f.write("\n".join("%.16e" % v for v in rphi) + "\n")
+    return path
+
+
+# Sutton-Chen Cu of the reference's generator script (c, eps[J]->eV, a, n, m : lines 91-96) and a second,
+# made-up element so that multi-species paths can be exercised where /root/reference is absent.
+SC_CU = dict(name="Cu", z=29, mass=63.546, a0=3.27, c=33.17, eps=3.605e-21 / 1.6021892e-19, a=3.27, n=9.050, m=5.005)
+SC_XX = dict(name="Xx", z=13, mass=26.982, a0=3.50, c=30.00, eps=0.0200, a=3.40, n=8.5, m=5.5)

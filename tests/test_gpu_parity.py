@@ -1,0 +1,282 @@
+"""GPU parity tests (run with -m gpu on a B200): every operator is called through the C ABI (ctypes ->
+libxsb200.so) and compared with the CPU oracle on the same seeded input.
+Bars: neighbour lists bit-exact (exported uint16 stream == oracle stream, byte for byte);
+forces / energies / virial within 1e-10 (FP64) or 1e-5 (mixed) relative to the largest magnitude of the field."""
+import os
+
+import numpy as np
+import pytest
+
+import exastamp_b200 as xsb
+from helpers import EV, GridSystem, SC_CU, SC_XX, johnson_params, lattice, write_setfl
+
+pytestmark = pytest.mark.gpu
+TOL64, TOLMIX = 1e-10, 1e-5
+
+
+def oracle():
+    from oracle import oracle as O
+    return O
+
+
+def rel_err(a, b):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def make_ctx(gs):
+    ctx = xsb.Context(0)
+    ctx.grid_set(xsb.make_grid(gs.dims, gs.gl, gs.cell_size, gs.origin, gs.xform))
+    ctx.particles_set_cells(gs.cell_off)
+    ctx.upload(xsb.F_RX, gs.rx); ctx.upload(xsb.F_RY, gs.ry); ctx.upload(xsb.F_RZ, gs.rz)
+    ctx.upload(xsb.F_TYPE, gs.type)
+    return ctx
+
+
+def system(structure="FCC", ncells=6, a=5.0, sigma=0.1, cell=None, gl=2, seed=1, types=None, xform=None):
+    pos, typ, box = lattice(structure, ncells, a, sigma, seed=seed, types=types)
+    return GridSystem(pos, typ, box, cell if cell else a, gl, xform=xform)
+
+
+# ------------------------------------------------------------------------------------------------ a2
+@pytest.mark.parametrize("chunk_size,offsets", [(1, True), (1, False), (4, True), (8, True)])
+def test_chunk_neighbors_stream_bit_exact(chunk_size, offsets):
+    O = oracle()
+    gs = system(ncells=6, a=5.0, gl=2)
+    nb = O.Neighbors.build(gs.oracle_grid(), gs.cell_off, gs.rx, gs.ry, gs.rz, 9.0, chunk_size, offsets)
+    ooff, odata = nb.export()
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0, chunk_size, offsets)
+    goff, gdata = ctx.chunk_neighbors_export()
+    assert np.array_equal(ooff, goff)
+    assert odata.tobytes() == gdata.tobytes()
+
+
+def test_chunk_neighbors_flat_list_and_stats():
+    O = oracle()
+    gs = system(ncells=5, a=5.0, gl=2, seed=3)
+    nb = O.Neighbors.build(gs.oracle_grid(), gs.cell_off, gs.rx, gs.ry, gs.rz, 9.0, 1, True)
+    cnt, off, idx = nb.decode()
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    gcnt, goff, gidx = ctx.chunk_neighbors_flat()
+    assert np.array_equal(cnt, gcnt) and np.array_equal(off, goff) and np.array_equal(idx, gidx)
+    total, mx = ctx.chunk_neighbors_stats()
+    assert total == int(cnt.sum()) and mx == int(cnt.max())
+
+
+def test_chunk_neighbors_triclinic_xform_bit_exact():
+    O = oracle()
+    X = np.array([[1.02, 0.03, 0.01], [0.0, 0.98, 0.02], [0.0, 0.0, 1.01]])
+    gs = system(ncells=6, a=5.0, gl=2, xform=X)
+    nb = O.Neighbors.build(gs.oracle_grid(), gs.cell_off, gs.rx, gs.ry, gs.rz, 9.0, 1, True)
+    ooff, odata = nb.export()
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    goff, gdata = ctx.chunk_neighbors_export()
+    assert np.array_equal(ooff, goff) and odata.tobytes() == gdata.tobytes()
+
+
+def test_chunk_neighbors_empty_and_ragged_cells():
+    O = oracle()
+    rng = np.random.default_rng(5)
+    box = np.array([30.0, 30.0, 30.0])
+    pos = rng.uniform(0, 30.0, (400, 3))
+    pos = pos[(pos[:, 0] < 12) | (pos[:, 0] > 22)]          # a slab of empty cells
+    gs = GridSystem(pos, np.zeros(len(pos), np.uint8), box, 5.0, 2)
+    nb = O.Neighbors.build(gs.oracle_grid(), gs.cell_off, gs.rx, gs.ry, gs.rz, 8.5, 4, True)
+    ooff, odata = nb.export()
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(8.5, 4, True)
+    goff, gdata = ctx.chunk_neighbors_export()
+    assert np.array_equal(ooff, goff) and odata.tobytes() == gdata.tobytes()
+
+
+def test_empty_grid():
+    ctx = xsb.Context(0)
+    ctx.grid_set(xsb.make_grid([4, 4, 4], 1, 5.0, [-5.0] * 3))
+    ctx.particles_set_cells(np.zeros(65, dtype=np.uint64))
+    ctx.chunk_neighbors(6.0)
+    assert ctx.chunk_neighbors_stats() == (0, 0)
+    ctx.zero_force_energy()
+    ctx.pair_force([1.0, 3.0], 5.0)
+    off, data = ctx.chunk_neighbors_export()
+    assert data.size == 0 and np.all(off == 0)
+
+
+# ------------------------------------------------------------------------------------------------ a4/a5
+def lj_reference(gs, rcut, ghost, want_vir, nbh_dist=9.0, params=(0.0104 * EV, 3.4)):
+    O = oracle()
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh_dist, 1, True)
+    fx, fy, fz, ep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if want_vir else None
+    O.pair_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, params, rcut, ghost, fx, fy, fz, ep, vir)
+    return fx, fy, fz, ep, vir
+
+
+@pytest.mark.parametrize("ghost,virial", [(False, False), (False, True), (True, True)])
+def test_lj_compute_force_parity(ghost, virial):
+    gs = system(ncells=6, a=5.0, gl=2)
+    fx, fy, fz, ep, vir = lj_reference(gs, 8.0, ghost, virial)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    ctx.zero_force_energy(ghost=True)
+    flags = xsb.FLAG_ENERGY | (xsb.FLAG_GHOST if ghost else 0) | (xsb.FLAG_VIRIAL if virial else 0)
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0, flags)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+    if not ghost:
+        assert np.all(ctx.download(xsb.F_FX)[gs.is_ghost] == 0.0)
+
+
+def test_lj_accumulates_and_zero_force_energy():
+    gs = system(ncells=5, a=5.0, gl=2)
+    fx, *_ = lj_reference(gs, 8.0, False, False)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    ctx.zero_force_energy()
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0)
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0)          # chained operators add up (compute_force: [a, b])
+    assert rel_err(ctx.download(xsb.F_FX), 2 * fx) < TOL64
+    ctx.zero_force_energy()
+    assert np.all(ctx.download(xsb.F_FX) == 0.0) and np.all(ctx.download(xsb.F_EP) == 0.0)
+
+
+def test_lj_mixed_precision_parity():
+    gs = system(ncells=6, a=5.0, gl=2)
+    fx, fy, fz, ep, _ = lj_reference(gs, 8.0, False, False)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    ctx.zero_force_energy()
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0, xsb.FLAG_ENERGY | xsb.FLAG_MIXED)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOLMIX
+
+
+def test_lj_triclinic_xform_parity():
+    X = np.array([[1.02, 0.03, 0.01], [0.0, 0.98, 0.02], [0.0, 0.0, 1.01]])
+    gs = system(ncells=6, a=5.0, gl=2, xform=X)
+    fx, fy, fz, ep, vir = lj_reference(gs, 8.0, False, True)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    ctx.zero_force_energy()
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0, xsb.FLAG_ENERGY | xsb.FLAG_VIRIAL)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep), (xsb.F_VIRIAL, vir)):
+        assert rel_err(ctx.download(f), ref) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ a6
+@pytest.mark.parametrize("virial", [False, True])
+def test_lj_multi_force_parity(virial):
+    O = oracle()
+    gs = system(ncells=6, a=5.0, gl=2, types=[0, 1, 0, 1])
+    # rows by unique_pair_id: (0,0), (0,1), (1,1) : eps, sigma, rcut   (values of potentials/pair/lj/multi_species_nosym.msp style)
+    rows = np.array([[0.0104 * EV, 3.4, 8.0], [0.0150 * EV, 3.2, 7.0], [0.0200 * EV, 3.0, 6.5]])
+    ecut = []
+    for e, s, rc in rows:
+        q = (s / rc) ** 2; q6 = q * q * q
+        ecut.append(4 * e * (q6 * q6 - q6))
+    pp = np.column_stack([rows, np.array(ecut)])
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 9.0, 1, True)
+    fx, fy, fz, ep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, pp, 8.0, 0, fx, fy, fz, ep, vir)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    ctx.zero_force_energy()
+    ctx.pair_multi_force(2, rows, 8.0, xsb.FLAG_ENERGY | (xsb.FLAG_VIRIAL if virial else 0))
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ a7
+@pytest.mark.parametrize("virial", [False, True])
+def test_johnson_force_parity(virial):
+    O = oracle()
+    gs = system(ncells=5, a=3.615, sigma=0.05, cell=3.615, gl=4)     # ghost thickness >= 2*rcut + skin
+    rcut, nbh = 5.5, 6.5
+    p = johnson_params()
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    fx, fy, fz, ep, emb = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    O.eam_johnson(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, p, rcut, 7, fx, fy, fz, ep, vir, emb)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_johnson_force(p, rcut, 7, xsb.FLAG_VIRIAL if virial else 0)
+    assert rel_err(ctx.download(xsb.F_RHO_DEMB), emb) < TOL64
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ a8
+def eam_alloy_case(tmp_path, elements, types, eflag, virial, two_step):
+    O = oracle()
+    path = str(tmp_path / "synthetic.eam.alloy")
+    write_setfl(path, elements, nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    gs = system(ncells=5, a=3.615, sigma=0.05, cell=3.615, gl=4, types=types)
+    rcut, nbh = 6.0, 7.0
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    eam = O.EamAlloy(path)
+    fx, fy, fz, ep, emb = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    flags = 1 | 2 | 4 | 8 | (16 if eflag else 0) | (32 if virial else 0)
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, rcut, flags, fx, fy, fz, ep, vir, emb)
+    ctx = make_ctx(gs)
+    info = ctx.eam_alloy_load(path)
+    assert info["nelements"] == len(elements) and info["nr"] == 2000
+    ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    ef = xsb.EAM_EFLAG if eflag else 0
+    fl = xsb.FLAG_VIRIAL if virial else 0
+    if two_step:
+        ctx.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | ef, fl)
+        ctx.eam_alloy_force(rcut, xsb.EAM_FORCE | ef, fl)
+    else:
+        ctx.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_FORCE | ef, fl)
+    assert rel_err(ctx.download(xsb.F_RHO_DEMB), emb) < TOL64
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64, "field %d" % f
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+
+
+@pytest.mark.parametrize("eflag,virial,two_step", [(False, False, False), (True, False, True), (True, True, False)])
+def test_eam_alloy_single_species_parity(tmp_path, eflag, virial, two_step):
+    eam_alloy_case(tmp_path, [SC_CU], None, eflag, virial, two_step)
+
+
+@pytest.mark.parametrize("eflag,virial", [(False, False), (True, True)])
+def test_eam_alloy_two_species_parity(tmp_path, eflag, virial):
+    eam_alloy_case(tmp_path, [SC_CU, SC_XX], [0, 1, 1, 0], eflag, virial, False)
+
+
+# ------------------------------------------------------------------------------------------------ properties at scale
+def test_c1_full_size_properties():
+    """BASELINE config C1 (131 072 atoms): momentum conservation and symmetry of the list at full size."""
+    pos, typ, box = lattice("FCC", 32, 5.0, 0.1, seed=1)
+    gs = GridSystem(pos, typ, box, 160.0 / 17, 1)                   # 17^3 cells of 9.41 ang >= rc + skin
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(9.0)
+    cnt, off, idx = ctx.chunk_neighbors_flat()
+    own = ~gs.is_ghost
+    assert 80 < cnt[own].mean() < 92
+    ctx.zero_force_energy()
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0)
+    fx, fy, fz = ctx.download(xsb.F_FX), ctx.download(xsb.F_FY), ctx.download(xsb.F_FZ)
+    fmax = np.abs(np.concatenate([fx, fy, fz])).max()
+    for f in (fx, fy, fz):
+        assert abs(f[own].sum()) < 1e-9 * fmax * np.sqrt(own.sum())   # Newton's third law holds globally
+    # every owned pair (a,b) in the list has its mirror image listed as well: pair count is even per distance
+    ep = ctx.download(xsb.F_EP)
+    assert -0.09 < ep[own].mean() / EV < -0.03
