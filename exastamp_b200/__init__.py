@@ -28,7 +28,8 @@ ABI_SYMBOLS = [
     "xsb_chunk_neighbors_export", "xsb_chunk_neighbors_download_flat",
     "xsb_pair_force", "xsb_pair_multi_force", "xsb_eam_johnson_force",
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
-    "xsb_comm_unique_id", "xsb_comm_init", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
+    "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
+    "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
 ]
 
 
@@ -108,9 +109,20 @@ def load_library():
     L.xsb_eam_alloy_free.argtypes = [C.POINTER(EamAlloyTables)]
     L.xsb_eam_alloy_set.argtypes = [vp, C.POINTER(EamAlloyTables)]
     L.xsb_eam_alloy_force.argtypes = [vp, dbl, i32, i32]
+    L.xsb_particles_assign.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.xsb_particles_rebin.argtypes = [vp, C.POINTER(DomainDesc)]
+    L.xsb_push_f_v_r.argtypes = [vp, dbl]
+    L.xsb_push_f_v.argtypes = [vp, dbl]
+    L.xsb_force_to_accel.argtypes = [vp, i32, vp]
+    L.xsb_backup_r.argtypes = [vp]
+    L.xsb_particle_displ_over.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(dbl)]
     L.xsb_comm_unique_id.argtypes = [vp]
     L.xsb_comm_init.argtypes = [vp, i32, i32, vp]
-    L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc), vp]
+    L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc)]
+    L.xsb_comm_allreduce_max.argtypes = [vp, C.POINTER(C.c_double)]
+    L.xsb_num_own_particles.restype = u64
+    L.xsb_num_own_particles.argtypes = [vp]
+    L.xsb_cell_offsets_download.argtypes = [vp, vp]
     L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
     L.xsb_ghost_reduce_add.argtypes = [vp, C.c_uint32]
     _lib = L
@@ -261,3 +273,73 @@ class Context:
 
     def eam_alloy_force(self, rcut, phases=EAM_RHO | EAM_RHO2EMB | EAM_GHOST | EAM_FORCE, flags=0):
         self._ck(self.L.xsb_eam_alloy_force(self.h, float(rcut), int(phases), int(flags)), "xsb_eam_alloy_force")
+
+    # ---- a10
+    def comm_init(self, nranks, rank, unique_id=None):
+        self._ck(self.L.xsb_comm_init(self.h, int(nranks), int(rank), unique_id), "xsb_comm_init")
+
+    def set_domain(self, global_cells, periodic=(1, 1, 1), rank_dims=(1, 1, 1), rank_coord=(0, 0, 0), box=None):
+        d = DomainDesc()
+        d.global_cells[:] = [int(v) for v in global_cells]
+        d.periodic[:] = [int(v) for v in periodic]
+        d.rank_dims[:] = [int(v) for v in rank_dims]
+        d.rank_coord[:] = [int(v) for v in rank_coord]
+        if box is None:
+            box = [g * self.grid.cell_size for g in global_cells]
+        d.box[:] = [float(v) for v in box]
+        self.domain = d
+        return d
+
+    def ghost_comm_scheme(self):
+        self._ck(self.L.xsb_ghost_comm_scheme(self.h, C.byref(self.domain)), "xsb_ghost_comm_scheme")
+
+    def particles_assign(self, rx, ry, rz, vx=None, vy=None, vz=None, typ=None, ids=None):
+        f = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+        arrs = [f(rx, np.float64), f(ry, np.float64), f(rz, np.float64), f(vx, np.float64), f(vy, np.float64), f(vz, np.float64),
+                f(typ, np.uint8), f(ids, np.uint64)]
+        ptrs = [None if a is None else _ptr(a) for a in arrs]
+        self._ck(self.L.xsb_particles_assign(self.h, len(arrs[0]), *ptrs), "xsb_particles_assign")
+
+    def particles_rebin(self):
+        self._ck(self.L.xsb_particles_rebin(self.h, C.byref(self.domain)), "xsb_particles_rebin")
+
+    def push_f_v_r(self, dt):
+        self._ck(self.L.xsb_push_f_v_r(self.h, float(dt)), "xsb_push_f_v_r")
+
+    def push_f_v(self, dt):
+        self._ck(self.L.xsb_push_f_v(self.h, float(dt)), "xsb_push_f_v")
+
+    def force_to_accel(self, masses):
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        self._ck(self.L.xsb_force_to_accel(self.h, m.size, _ptr(m)), "xsb_force_to_accel")
+
+    def backup_r(self):
+        self._ck(self.L.xsb_backup_r(self.h), "xsb_backup_r")
+
+    def particle_displ_over(self, threshold):
+        r, d = C.c_int(), C.c_double()
+        self._ck(self.L.xsb_particle_displ_over(self.h, float(threshold), C.byref(r), C.byref(d)), "xsb_particle_displ_over")
+        return bool(r.value), d.value
+
+    def ghost_update(self, fields):
+        self._ck(self.L.xsb_ghost_update(self.h, sum(1 << f for f in fields)), "xsb_ghost_update")
+
+    def ghost_reduce_add(self, fields):
+        self._ck(self.L.xsb_ghost_reduce_add(self.h, sum(1 << f for f in fields)), "xsb_ghost_reduce_add")
+
+    def cell_offsets(self):
+        off = np.zeros(int(self.L.xsb_num_cells(self.h)) + 1, dtype=np.uint64)
+        self._ck(self.L.xsb_cell_offsets_download(self.h, _ptr(off)), "xsb_cell_offsets_download")
+        return off
+
+    @property
+    def n_own(self):
+        return int(self.L.xsb_num_own_particles(self.h))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = load_library().xsb_comm_unique_id(buf)
+    if rc != 0:
+        raise XsbError("xsb_comm_unique_id failed (%d): NCCL not loadable" % rc)
+    return buf.raw

@@ -55,6 +55,94 @@ int xsb_internal_ensure_virial(xsb_ctx* ctx)
   return XSB_OK;
 }
 
+// host-side cell tables (flat start, cell of each particle, list of particles in non-ghost cells) -> device
+int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
+{
+  const uint64_t nc = ctx->ncells, n = off[nc];
+  ctx->h_cell_off.assign(off, off + nc + 1);
+  std::vector<unsigned> start(nc + 1), cellof(n), own; own.reserve(n);
+  const GridView gv = ctx->view();
+  for(uint64_t c = 0; c <= nc; c++) start[c] = unsigned(off[c]);
+  for(uint64_t c = 0; c < nc; c++)
+  {
+    const bool ghost = gv.is_ghost_cell(unsigned(c));
+    for(uint64_t p = off[c]; p < off[c+1]; p++) { cellof[p] = unsigned(c); if( !ghost ) own.push_back(unsigned(p)); }
+  }
+  ctx->n = n; ctx->n_own = own.size();
+  XSB_CUDA(ctx, ctx->cell_start.reserve(nc + 1));
+  XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, 1.02));
+  XSB_CUDA(ctx, ctx->own_atoms.reserve(own.size() + 1, 1.02));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, start.data(), (nc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  if( n ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_of.p, cellof.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  if( !own.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->own_atoms.p, own.data(), own.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
+  ctx->nbh_built = false;
+  return XSB_OK;
+}
+
+namespace xsb
+{
+template<class T>
+__global__ void relayout_kernel(unsigned n_new, GridView g, const unsigned* __restrict__ cell_of, const unsigned* __restrict__ new_start,
+                                const unsigned* __restrict__ old_start, const T* __restrict__ in, T* __restrict__ out)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= n_new ) return;
+  const unsigned c = cell_of[i];
+  out[i] = g.is_ghost_cell(c) ? T(0) : in[old_start[c] + (i - new_start[c])];
+}
+}
+
+// new cell offsets where every NON-ghost cell keeps its particle count: persistent fields (r, v, type, id) of own
+// cells move to their new flat position, ghost slots are zero-filled, accumulators (f, ep, virial, rho_dEmb) are zeroed.
+int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
+{
+  const uint64_t nc = ctx->ncells;
+  const GridView gv = ctx->view();
+  for(uint64_t c = 0; c < nc; c++)
+    if( !gv.is_ghost_cell(unsigned(c)) && new_off[c+1] - new_off[c] != ctx->h_cell_off[c+1] - ctx->h_cell_off[c] )
+      return ctx->fail(XSB_ERR_INVALID, "relayout: particle count of own cell %llu changed", (unsigned long long)c);
+  XSB_REQUIRE(ctx, new_off[nc] < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU");
+  XSB_CUDA(ctx, ctx->old_cell_start.reserve(nc + 1));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->old_cell_start.p, ctx->cell_start.p, (nc + 1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, ctx->stream));
+  int rc = xsb_internal_install_cells(ctx, new_off); if( rc ) return rc;
+  const unsigned n = unsigned(ctx->n);
+  const unsigned grid = (n + 255) / 256;
+  XSB_CUDA(ctx, ctx->tmp64.reserve(size_t(n) + 16, 1.02));
+  const int moved[6] = { XSB_F_RX, XSB_F_RY, XSB_F_RZ, XSB_F_VX, XSB_F_VY, XSB_F_VZ };
+  for(int k = 0; k < 6 && n; k++)
+  {
+    DevBuf<double>& b = ctx->f64[moved[k]];
+    relayout_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p, b.p, reinterpret_cast<double*>(ctx->tmp64.p));
+    XSB_LAUNCH_CHECK(ctx);
+    XSB_CUDA(ctx, b.reserve_keep(n + 1, 1.02, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(b.p, ctx->tmp64.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if( n )
+  {
+    relayout_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p,
+                                                                       reinterpret_cast<const unsigned long long*>(ctx->id.p), ctx->tmp64.p);
+    XSB_LAUNCH_CHECK(ctx);
+    XSB_CUDA(ctx, ctx->id.reserve_keep(n + 1, 1.02, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->id.p, ctx->tmp64.p, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    relayout_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p, ctx->type.p,
+                                                                  reinterpret_cast<unsigned char*>(ctx->tmp64.p));
+    XSB_LAUNCH_CHECK(ctx);
+    XSB_CUDA(ctx, ctx->type.reserve_keep(n + 16, 1.02, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->type.p, ctx->tmp64.p, size_t(n), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  const int zeroed[6] = { XSB_F_FX, XSB_F_FY, XSB_F_FZ, XSB_F_EP, XSB_F_RHO_DEMB, XSB_F_VIRIAL };
+  for(int k = 0; k < 6; k++)
+  {
+    const int f = zeroed[k];
+    if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;
+    const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 1), 1.02));
+    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (size_t(n) + 1) * sizeof(double), ctx->stream));
+  }
+  return XSB_OK;
+}
+
 extern "C" {
 
 const char* xsb_version(void) { return "xsb200 0.1 (sm_100a)"; }
@@ -135,43 +223,34 @@ int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
   XSB_REQUIRE(ctx, off != nullptr && off[0] == 0, XSB_ERR_INVALID, "cell_particle_offset[0] must be 0");
   const uint64_t nc = ctx->ncells;
   for(uint64_t c = 0; c < nc; c++) XSB_REQUIRE(ctx, off[c+1] >= off[c], XSB_ERR_INVALID, "cell_particle_offset must be non-decreasing");
-  const uint64_t n = off[nc];
-  XSB_REQUIRE(ctx, n < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU");
+  XSB_REQUIRE(ctx, off[nc] < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->h_cell_off.assign(off, off + nc + 1);
-  std::vector<unsigned> start(nc + 1), cellof(n), own; own.reserve(n);
-  const GridView gv = ctx->view();
-  for(uint64_t c = 0; c <= nc; c++) start[c] = unsigned(off[c]);
-  for(uint64_t c = 0; c < nc; c++)
-  {
-    const bool ghost = gv.is_ghost_cell(unsigned(c));
-    for(uint64_t p = off[c]; p < off[c+1]; p++) { cellof[p] = unsigned(c); if( !ghost ) own.push_back(unsigned(p)); }
-  }
-  ctx->n = n; ctx->n_own = own.size();
-  XSB_CUDA(ctx, ctx->cell_start.reserve(nc + 1));
-  XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1));
-  XSB_CUDA(ctx, ctx->own_atoms.reserve(own.size() + 1));
-  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, start.data(), (nc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  if( n ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_of.p, cellof.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  if( !own.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->own_atoms.p, own.data(), own.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = xsb_internal_install_cells(ctx, off); if( rc ) return rc;
+  const uint64_t n = ctx->n;
   for(int f = 0; f < XSB_F_TYPE; f++)
   {
-    if( f == XSB_F_VIRIAL ) continue;   // allocated on first use
-    XSB_CUDA(ctx, ctx->f64[f].reserve(n + 1, 1.02));
-    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, (n + 1) * sizeof(double), ctx->stream));
-  }
-  if( ctx->virial_allocated )
-  {
-    XSB_CUDA(ctx, ctx->f64[XSB_F_VIRIAL].reserve(9 * (n + 1), 1.02));
-    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[XSB_F_VIRIAL].p, 0, 9 * (n + 1) * sizeof(double), ctx->stream));
+    if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;   // allocated on first use
+    const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (n + 1), 1.02));
+    XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (n + 1) * sizeof(double), ctx->stream));
   }
   XSB_CUDA(ctx, ctx->type.reserve(n + 16, 1.02));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, n + 16, ctx->stream));
   XSB_CUDA(ctx, ctx->id.reserve(n + 1, 1.02));
-  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
-  ctx->nbh_built = false;
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->id.p, 0, (n + 1) * sizeof(uint64_t), ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return XSB_OK;
 }
+
+int xsb_cell_offsets_download(xsb_ctx* ctx, uint64_t* off)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, off != nullptr && ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
+  std::memcpy(off, ctx->h_cell_off.data(), (ctx->ncells + 1) * sizeof(uint64_t));
+  return XSB_OK;
+}
+
+uint64_t xsb_num_own_particles(const xsb_ctx* ctx) { return ctx ? ctx->n_own : 0; }
 
 uint64_t xsb_num_particles(const xsb_ctx* ctx) { return ctx ? ctx->n : 0; }
 uint64_t xsb_num_cells(const xsb_ctx* ctx) { return ctx ? ctx->ncells : 0; }

@@ -29,6 +29,18 @@ template<class T> struct DevBuf
     if( e == cudaSuccess ) cap = want;
     return e;
   }
+  // grow but keep the first `cap` elements (reserve() discards contents)
+  cudaError_t reserve_keep(size_t n, double factor, cudaStream_t st)
+  {
+    if( n <= cap ) return cudaSuccess;
+    size_t want = size_t(double(n) * (factor < 1.0 ? 1.0 : factor)); if( want < n ) want = n;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, want * sizeof(T));
+    if( e != cudaSuccess ) return e;
+    if( p ) { e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); cudaFree(p); }
+    p = q; cap = want;
+    return e;
+  }
   void release() { if( p ) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -45,6 +57,9 @@ struct GridView
     return i < gl || i >= nx - gl || j < gl || j >= ny - gl || k < gl || k >= nz - gl;
   }
 };
+
+struct GhostState;
+struct XFormInv { double m[9]; int identity; };
 
 struct EamAlloyDev
 {
@@ -96,6 +111,12 @@ struct xsb_ctx
 
   // a10
   ncclComm* comm = nullptr; int nranks = 1, rank = 0;
+  xsb::GhostState* ghost = nullptr;           // built by xsb_ghost_comm_scheme (xsb_ghost.cu)
+  xsb::DevBuf<unsigned> old_cell_start;       // relayout scratch
+  xsb::DevBuf<unsigned long long> tmp64;      // relayout / sort scratch (8-byte words)
+  xsb::DevBuf<unsigned> tmp32a, tmp32b, tmp32c, tmp32d;
+  xsb::DevBuf<unsigned> gseg_send, gseg_recv, goff_send, goff_recv;   // ghost segment tables (device)
+  xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
 
   int fail(int code, const char* fmt, ...)
   {
@@ -118,6 +139,8 @@ struct xsb_ctx
 
 // internal helpers shared across translation units (C++ linkage, not exported by the header)
 int  xsb_internal_ensure_virial(xsb_ctx* ctx);
+int  xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* cell_off);
+int  xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_cell_off);
 void xsb_ghost_release(xsb_ctx* ctx);
 
 namespace xsb

@@ -1,10 +1,439 @@
-// xsb_ghost.cu -- ghost operators -- placeholder, filled in below.
+// xsb_ghost.cu -- ghost operators: ghost_comm_scheme, ghost_update_r / ghost_update_opt /
+// ghost_update_all_no_fv (owner -> ghost copies) and update_force_energy_from_ghost (ghost -> owner add).
+// Reference names: src/mpi/update_ghosts.cu:30-47, src/mpi/update_from_ghosts.cu:29-48; graph
+// data/config/config_move_particles.msp:82-96,134-135.  The reference implementation is exaNBody's MPI
+// point-to-point code; here one process drives one GPU and the exchange is NCCL P2P (ncclSend/ncclRecv in one
+// group per call) over NVLink, with pack / unpack kernels at both ends.  Periodic images are materialised as
+// ghost particles exactly like the reference does, even on a single rank (self peer = one fused kernel).
+//
+// Decomposition: static 3-D bricks of the global cell grid, rank (px,py,pz) owns cells
+// [p*G/P, (p+1)*G/P) per axis.  Because the decomposition is a pure function of xsb_domain_desc, every rank
+// derives its send lists from its peers' receive lists locally: only particle counts travel at scheme time.
 #include "xsb_ctx.h"
-void xsb_ghost_release(xsb_ctx*) {}
-extern "C" {
-int xsb_comm_unique_id(void*) { return XSB_ERR_UNSUPPORTED; }
-int xsb_comm_init(xsb_ctx* ctx, int, int, const void*) { return ctx ? ctx->fail(XSB_ERR_UNSUPPORTED, "not implemented") : XSB_ERR_STATE; }
-int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc*, const uint64_t*) { return ctx ? ctx->fail(XSB_ERR_UNSUPPORTED, "not implemented") : XSB_ERR_STATE; }
-int xsb_ghost_update(xsb_ctx* ctx, uint32_t) { return ctx ? ctx->fail(XSB_ERR_UNSUPPORTED, "not implemented") : XSB_ERR_STATE; }
-int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t) { return ctx ? ctx->fail(XSB_ERR_UNSUPPORTED, "not implemented") : XSB_ERR_STATE; }
+#include <algorithm>
+#include <dlfcn.h>
+
+namespace xsb
+{
+
+// ---- NCCL, bound at run time so that the library loads without it and shares the copy torch already loaded ---
+typedef struct { char internal[128]; } NcclUniqueId;
+struct NcclApi
+{
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm**, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static const int NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static bool nccl_load(std::string& why)
+{
+  if( g_nccl.ok ) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if( !h ) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if( !h ) h = dlopen("libnccl.so", RTLD_NOW);
+  if( !h ) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+  g_nccl.lib = h;
+# define XSB_SYM(name) *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name); if( !g_nccl.name ) { why = "missing symbol nccl" #name; return false; }
+  XSB_SYM(GetUniqueId) XSB_SYM(CommInitRank) XSB_SYM(CommDestroy) XSB_SYM(GroupStart) XSB_SYM(GroupEnd) XSB_SYM(Send) XSB_SYM(Recv)
+  XSB_SYM(AllReduce) XSB_SYM(GetErrorString)
+# undef XSB_SYM
+  g_nccl.ok = true;
+  return true;
 }
+
+#define XSB_NCCL(ctx, call) do { int r__ = (call); if( r__ != 0 ) \
+  return (ctx)->fail(XSB_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); } while(0)
+
+// ---- scheme ------------------------------------------------------------------------------------------------
+struct GhostCell { int ghost_cell; int owner_rank; int owner_cell; int w[3]; };
+
+struct GhostState
+{
+  xsb_domain_desc dom{};
+  int nranks = 1;
+  // per peer (rank order) segment offsets into the concatenated particle lists, n = nranks+1
+  std::vector<unsigned> send_off, recv_off;
+  unsigned n_send = 0, n_recv = 0;
+  DevBuf<unsigned> send_idx;            // owner particle (flat)   [n_send]
+  DevBuf<unsigned char> send_code;      // shift code 0..26        [n_send]
+  DevBuf<unsigned> recv_idx;            // ghost particle (flat)   [n_recv]
+  DevBuf<unsigned long long> send_buf, recv_buf;   // 8-byte words, [nfields][segment] per peer
+  double shift[27][3];
+};
+
+static inline int block_start(int r, int G, int P) { return int((long long)r * G / P); }
+
+static inline int owner_of(int gc, int G, int P)
+{
+  int r = int(((long long)(gc + 1) * P - 1) / G);   // largest r with start(r) <= gc
+  while( r > 0 && block_start(r, G, P) > gc ) --r;
+  while( r + 1 < P && block_start(r + 1, G, P) <= gc ) ++r;
+  return r;
+}
+
+// receive list of `rank`: every ghost cell of its local grid that mirrors an existing domain cell
+static void ghost_list(const xsb_domain_desc& d, int gl, const int rc[3], std::vector<GhostCell>& out)
+{
+  int s[3], n[3], dims[3];
+  for(int a = 0; a < 3; a++) { s[a] = block_start(rc[a], d.global_cells[a], d.rank_dims[a]); n[a] = block_start(rc[a] + 1, d.global_cells[a], d.rank_dims[a]) - s[a]; dims[a] = n[a] + 2 * gl; }
+  out.clear();
+  for(int k = 0; k < dims[2]; k++) for(int j = 0; j < dims[1]; j++) for(int i = 0; i < dims[0]; i++)
+  {
+    const int l[3] = { i, j, k };
+    if( i >= gl && i < dims[0] - gl && j >= gl && j < dims[1] - gl && k >= gl && k < dims[2] - gl ) continue;
+    GhostCell g; g.ghost_cell = i + dims[0] * (j + dims[1] * k);
+    int orank[3], ocell[3]; bool exists = true;
+    for(int a = 0; a < 3; a++)
+    {
+      const int G = d.global_cells[a];
+      int gc = s[a] + l[a] - gl, w = 0;
+      if( gc < 0 || gc >= G )
+      {
+        if( !d.periodic[a] ) { exists = false; break; }
+        w = gc >= 0 ? gc / G : -((-gc + G - 1) / G);
+        gc -= w * G;
+      }
+      g.w[a] = w;
+      orank[a] = owner_of(gc, G, d.rank_dims[a]);
+      const int os = block_start(orank[a], G, d.rank_dims[a]);
+      ocell[a] = gc - os + gl;
+    }
+    if( !exists ) continue;
+    g.owner_rank = orank[0] + d.rank_dims[0] * (orank[1] + d.rank_dims[1] * orank[2]);
+    int odims[2];
+    for(int a = 0; a < 2; a++) odims[a] = block_start(orank[a] + 1, d.global_cells[a], d.rank_dims[a]) - block_start(orank[a], d.global_cells[a], d.rank_dims[a]) + 2 * gl;
+    g.owner_cell = ocell[0] + odims[0] * (ocell[1] + odims[1] * ocell[2]);
+    out.push_back(g);
+  }
+  std::stable_sort(out.begin(), out.end(), [](const GhostCell& a, const GhostCell& b) { return a.owner_rank < b.owner_rank; });
+}
+
+static inline int shift_code(const int w[3]) { auto c = [](int v) { return v < 0 ? 0 : (v > 0 ? 2 : 1); }; return c(w[0]) + 3 * c(w[1]) + 9 * c(w[2]); }
+
+// ---- kernels -----------------------------------------------------------------------------------------------
+struct FieldPtrs { const void* src[8]; void* dst[8]; int kind[8]; int nf; };   // kind: 0 double, 1..3 position axis (adds shift), 4 u64, 5 u8
+struct ShiftTab { double s[27][3]; };
+
+__device__ __forceinline__ unsigned long long load_word(const void* base, int kind, unsigned i)
+{
+  if( kind == 5 ) return (unsigned long long)static_cast<const unsigned char*>(base)[i];
+  return static_cast<const unsigned long long*>(base)[i];
+}
+__device__ __forceinline__ void store_word(void* base, int kind, unsigned i, unsigned long long v)
+{
+  if( kind == 5 ) static_cast<unsigned char*>(base)[i] = (unsigned char)v;
+  else static_cast<unsigned long long*>(base)[i] = v;
+}
+
+// owner -> wire : buf[peer segment][field][k] ; shift added to positions on the sender side
+__global__ void ghost_pack_kernel(unsigned n, FieldPtrs F, ShiftTab S, const unsigned* __restrict__ idx, const unsigned char* __restrict__ code,
+                                  const unsigned* __restrict__ seg_of, const unsigned* __restrict__ seg_off, unsigned long long* __restrict__ buf, bool from_ghost, unsigned me)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k >= n ) return;
+  if( seg_of[k] == me ) return;   // self segment is served by ghost_self_kernel
+  const unsigned q = seg_of[k], s0 = seg_off[q], len = seg_off[q + 1] - s0, src = idx[k];
+  unsigned long long* seg = buf + size_t(F.nf) * s0;
+  for(int f = 0; f < F.nf; f++)
+  {
+    unsigned long long w = load_word(F.src[f], F.kind[f], src);
+    if( !from_ghost && F.kind[f] >= 1 && F.kind[f] <= 3 ) w = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)w) + S.s[code[k]][F.kind[f] - 1]);
+    seg[size_t(f) * len + (k - s0)] = w;
+  }
+}
+
+// wire -> ghost (copy) or wire -> owner (add)
+__global__ void ghost_unpack_kernel(unsigned n, FieldPtrs F, const unsigned* __restrict__ idx, const unsigned* __restrict__ seg_of,
+                                    const unsigned* __restrict__ seg_off, const unsigned long long* __restrict__ buf, bool add, unsigned me)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k >= n ) return;
+  if( seg_of[k] == me ) return;
+  const unsigned q = seg_of[k], s0 = seg_off[q], len = seg_off[q + 1] - s0, dst = idx[k];
+  const unsigned long long* seg = buf + size_t(F.nf) * s0;
+  for(int f = 0; f < F.nf; f++)
+  {
+    const unsigned long long w = seg[size_t(f) * len + (k - s0)];
+    if( add ) atomicAdd(static_cast<double*>(F.dst[f]) + dst, __longlong_as_double((long long)w));
+    else store_word(F.dst[f], F.kind[f], dst, w);
+  }
+}
+
+// single-rank fast path: ghost[k] = owner[k] (+ shift), no staging buffer
+__global__ void ghost_self_kernel(unsigned n, FieldPtrs F, ShiftTab S, const unsigned* __restrict__ send_idx, const unsigned char* __restrict__ code,
+                                  const unsigned* __restrict__ recv_idx, bool reverse_add)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k >= n ) return;
+  const unsigned o = send_idx[k], g = recv_idx[k];
+  for(int f = 0; f < F.nf; f++)
+  {
+    if( reverse_add ) { atomicAdd(static_cast<double*>(F.dst[f]) + o, static_cast<const double*>(F.src[f])[g]); continue; }
+    unsigned long long w = load_word(F.src[f], F.kind[f], o);
+    if( F.kind[f] >= 1 && F.kind[f] <= 3 ) w = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)w) + S.s[code[k]][F.kind[f] - 1]);
+    store_word(F.dst[f], F.kind[f], g, w);
+  }
+}
+
+static int make_fields(xsb_ctx* ctx, uint32_t mask, bool reverse, FieldPtrs& F)
+{
+  F.nf = 0;
+  for(int f = 0; f < XSB_F_COUNT_; f++)
+  {
+    if( !(mask & (1u << f)) ) continue;
+    XSB_REQUIRE(ctx, F.nf < 8, XSB_ERR_INVALID, "at most 8 fields per ghost exchange");
+    XSB_REQUIRE(ctx, f != XSB_F_VIRIAL, XSB_ERR_UNSUPPORTED, "virial ghost exchange not supported");
+    void* p; int kind = 0;
+    if( f == XSB_F_TYPE ) { p = ctx->type.p; kind = 5; }
+    else if( f == XSB_F_ID ) { p = ctx->id.p; kind = 4; }
+    else { p = ctx->f64[f].p; kind = (f == XSB_F_RX) ? 1 : (f == XSB_F_RY) ? 2 : (f == XSB_F_RZ) ? 3 : 0; }
+    XSB_REQUIRE(ctx, !reverse || kind <= 3, XSB_ERR_INVALID, "only real-valued fields can be reduced from ghosts");
+    F.src[F.nf] = p; F.dst[F.nf] = p; F.kind[F.nf] = kind; ++F.nf;
+  }
+  XSB_REQUIRE(ctx, F.nf > 0, XSB_ERR_INVALID, "empty field mask");
+  return XSB_OK;
+}
+
+// exchange(): forward (owner->ghost copy) or reverse (ghost->owner add)
+static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
+{
+  GhostState* G = ctx->ghost;
+  XSB_REQUIRE(ctx, G != nullptr, XSB_ERR_STATE, "xsb_ghost_comm_scheme must be called first");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FieldPtrs F; int rc = make_fields(ctx, mask, reverse, F); if( rc ) return rc;
+  ShiftTab S; std::memcpy(S.s, G->shift, sizeof(S.s));
+  const int me = ctx->rank, P = G->nranks;
+  // self segment
+  const unsigned s0 = G->send_off[me], ns = G->send_off[me + 1] - s0, r0 = G->recv_off[me];
+  if( ns )
+  {
+    ghost_self_kernel<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ns, F, S, G->send_idx.p + s0, G->send_code.p + s0, G->recv_idx.p + r0, reverse);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  if( P == 1 ) return XSB_OK;
+  XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "multi-rank ghost exchange needs xsb_comm_init");
+  // remote peers: pack everything (self segment included, it is simply not sent), one grouped send/recv, unpack
+  const unsigned n_out = reverse ? G->n_recv : G->n_send, n_in = reverse ? G->n_send : G->n_recv;
+  const std::vector<unsigned>& out_off = reverse ? G->recv_off : G->send_off;
+  const std::vector<unsigned>& in_off = reverse ? G->send_off : G->recv_off;
+  XSB_CUDA(ctx, G->send_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, 1.1));
+  XSB_CUDA(ctx, G->recv_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, 1.1));
+  const unsigned* d_out_seg = reverse ? ctx->gseg_recv.p : ctx->gseg_send.p;   // seg_of arrays (built with the scheme)
+  const unsigned* d_in_seg = reverse ? ctx->gseg_send.p : ctx->gseg_recv.p;
+  const unsigned* d_out_off = reverse ? ctx->goff_recv.p : ctx->goff_send.p;
+  const unsigned* d_in_off = reverse ? ctx->goff_send.p : ctx->goff_recv.p;
+  if( n_out )
+  {
+    ghost_pack_kernel<<<(n_out + 255) / 256, 256, 0, ctx->stream>>>(n_out, F, S, reverse ? G->recv_idx.p : G->send_idx.p, G->send_code.p,
+                                                                     d_out_seg, d_out_off, G->send_buf.p, reverse, unsigned(me));
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  XSB_NCCL(ctx, g_nccl.GroupStart());
+  for(int q = 0; q < P; q++)
+  {
+    if( q == me ) continue;
+    const size_t so = size_t(F.nf) * out_off[q], sc = size_t(F.nf) * (out_off[q + 1] - out_off[q]);
+    const size_t ro = size_t(F.nf) * in_off[q], rcnt = size_t(F.nf) * (in_off[q + 1] - in_off[q]);
+    if( sc ) XSB_NCCL(ctx, g_nccl.Send(G->send_buf.p + so, sc, NCCL_UINT64, q, ctx->comm, ctx->stream));
+    if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(G->recv_buf.p + ro, rcnt, NCCL_UINT64, q, ctx->comm, ctx->stream));
+  }
+  XSB_NCCL(ctx, g_nccl.GroupEnd());
+  if( n_in )
+  {
+    ghost_unpack_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(n_in, F, reverse ? G->send_idx.p : G->recv_idx.p, d_in_seg, d_in_off, G->recv_buf.p, reverse, unsigned(me));
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  return XSB_OK;
+}
+
+} // namespace xsb
+
+using namespace xsb;
+
+void xsb_ghost_release(xsb_ctx* ctx)
+{
+  if( ctx->ghost )
+  {
+    ctx->ghost->send_idx.release(); ctx->ghost->send_code.release(); ctx->ghost->recv_idx.release();
+    ctx->ghost->send_buf.release(); ctx->ghost->recv_buf.release();
+    delete ctx->ghost; ctx->ghost = nullptr;
+  }
+  ctx->old_cell_start.release(); ctx->tmp64.release(); ctx->tmp32a.release(); ctx->tmp32b.release(); ctx->tmp32c.release(); ctx->tmp32d.release(); ctx->gseg_send.release(); ctx->gseg_recv.release(); ctx->goff_send.release(); ctx->goff_recv.release(); ctx->backup.release();
+  if( ctx->comm && g_nccl.ok ) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+}
+
+extern "C" {
+
+int xsb_comm_unique_id(void* id128)
+{
+  std::string why;
+  if( !id128 || !nccl_load(why) ) return XSB_ERR_NCCL;
+  NcclUniqueId id;
+  if( g_nccl.GetUniqueId(&id) != 0 ) return XSB_ERR_NCCL;
+  std::memcpy(id128, &id, 128);
+  return XSB_OK;
+}
+
+int xsb_comm_init(xsb_ctx* ctx, int nranks, int rank, const void* id128)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, XSB_ERR_INVALID, "bad rank / nranks");
+  ctx->nranks = nranks; ctx->rank = rank;
+  if( nranks == 1 ) return XSB_OK;
+  XSB_REQUIRE(ctx, id128 != nullptr, XSB_ERR_INVALID, "null ncclUniqueId");
+  std::string why;
+  if( !nccl_load(why) ) return ctx->fail(XSB_ERR_NCCL, "%s", why.c_str());
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclUniqueId id; std::memcpy(&id, id128, 128);
+  XSB_NCCL(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+  return XSB_OK;
+}
+
+int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  if( ctx->nranks == 1 ) return XSB_OK;
+  XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "xsb_comm_init must be called first");
+  XSB_CUDA(ctx, ctx->scratch64.reserve(16));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch64.p, inout_host, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_NCCL(ctx, g_nccl.AllReduce(ctx->scratch64.p, ctx->scratch64.p, 1, NCCL_FLOAT64, NCCL_MAX, ctx->comm, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(inout_host, ctx->scratch64.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, dom != nullptr, XSB_ERR_INVALID, "null domain");
+  XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "grid/particles not set");
+  const int P = dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2];
+  XSB_REQUIRE(ctx, P == ctx->nranks, XSB_ERR_INVALID, "rank_dims product differs from the communicator size");
+  const int me = dom->rank_coord[0] + dom->rank_dims[0] * (dom->rank_coord[1] + dom->rank_dims[1] * dom->rank_coord[2]);
+  XSB_REQUIRE(ctx, me == ctx->rank, XSB_ERR_INVALID, "rank_coord does not match this rank (x fastest)");
+  const int gl = ctx->grid.ghost_layers;
+  for(int a = 0; a < 3; a++)
+  {
+    const int own = block_start(dom->rank_coord[a] + 1, dom->global_cells[a], dom->rank_dims[a]) - block_start(dom->rank_coord[a], dom->global_cells[a], dom->rank_dims[a]);
+    XSB_REQUIRE(ctx, own + 2 * gl == ctx->grid.dims[a], XSB_ERR_INVALID, "local grid dims do not match the brick of this rank");
+    XSB_REQUIRE(ctx, dom->global_cells[a] >= dom->rank_dims[a], XSB_ERR_INVALID, "fewer cells than ranks along an axis");
+  }
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if( !ctx->ghost ) ctx->ghost = new GhostState;
+  GhostState* G = ctx->ghost;
+  G->dom = *dom; G->nranks = P;
+  for(int c = 0; c < 27; c++) { const int w[3] = { c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1 }; for(int a = 0; a < 3; a++) G->shift[c][a] = 0.0; (void)w; }
+
+  // receive list (mine) and send lists (entries of every peer's receive list that I own)
+  std::vector<GhostCell> mine; ghost_list(*dom, gl, dom->rank_coord, mine);
+  std::vector< std::vector<GhostCell> > to_peer(P);
+  for(int q = 0; q < P; q++)
+  {
+    const int qc[3] = { q % dom->rank_dims[0], (q / dom->rank_dims[0]) % dom->rank_dims[1], q / (dom->rank_dims[0] * dom->rank_dims[1]) };
+    std::vector<GhostCell> theirs; ghost_list(*dom, gl, qc, theirs);
+    for(const GhostCell& g : theirs) if( g.owner_rank == me ) to_peer[q].push_back(g);
+  }
+  const GridView gv = ctx->view();
+  const std::vector<uint64_t>& off = ctx->h_cell_off;
+  for(int q = 0; q < P; q++) for(const GhostCell& g : to_peer[q])
+    XSB_REQUIRE(ctx, g.owner_cell >= 0 && uint64_t(g.owner_cell) < ctx->ncells && !gv.is_ghost_cell(unsigned(g.owner_cell)), XSB_ERR_STATE, "ghost scheme: owner cell is not an own cell");
+
+  // particle counts: mine are known, peers' travel as u32 arrays (one per peer, cells in list order)
+  std::vector<unsigned> send_counts, recv_counts(mine.size(), 0), sc_off(P + 1, 0), rc_off(P + 1, 0);
+  for(int q = 0; q < P; q++) { for(const GhostCell& g : to_peer[q]) send_counts.push_back(unsigned(off[g.owner_cell + 1] - off[g.owner_cell])); sc_off[q + 1] = unsigned(send_counts.size()); }
+  { size_t i = 0; for(int q = 0; q < P; q++) { while( i < mine.size() && mine[i].owner_rank == q ) ++i; rc_off[q + 1] = unsigned(i); } }
+  for(unsigned i = rc_off[me]; i < rc_off[me + 1]; i++) recv_counts[i] = unsigned(off[mine[i].owner_cell + 1] - off[mine[i].owner_cell]);
+  if( P > 1 )
+  {
+    XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "multi-rank ghost scheme needs xsb_comm_init");
+    XSB_CUDA(ctx, ctx->tmp32a.reserve(send_counts.size() + 16)); XSB_CUDA(ctx, ctx->tmp32b.reserve(recv_counts.size() + 16));
+    if( !send_counts.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->tmp32a.p, send_counts.data(), send_counts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    XSB_NCCL(ctx, g_nccl.GroupStart());
+    for(int q = 0; q < P; q++)
+    {
+      if( q == me ) continue;
+      // counts are sent as bytes so that no particular integer NCCL type value is assumed
+      if( sc_off[q+1] > sc_off[q] ) XSB_NCCL(ctx, g_nccl.Send(ctx->tmp32a.p + sc_off[q], size_t(sc_off[q+1] - sc_off[q]) * 4, /*ncclUint8*/ 1, q, ctx->comm, ctx->stream));
+      if( rc_off[q+1] > rc_off[q] ) XSB_NCCL(ctx, g_nccl.Recv(ctx->tmp32b.p + rc_off[q], size_t(rc_off[q+1] - rc_off[q]) * 4, /*ncclUint8*/ 1, q, ctx->comm, ctx->stream));
+    }
+    XSB_NCCL(ctx, g_nccl.GroupEnd());
+    std::vector<unsigned> tmp(recv_counts.size());
+    if( !tmp.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->tmp32b.p, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int q = 0; q < P; q++) if( q != me ) for(unsigned i = rc_off[q]; i < rc_off[q+1]; i++) recv_counts[i] = tmp[i];
+  }
+
+  // new layout: own cells keep their counts, ghost cells take the received ones (others become empty)
+  std::vector<uint64_t> cnt(ctx->ncells, 0), new_off(ctx->ncells + 1, 0);
+  for(uint64_t c = 0; c < ctx->ncells; c++) if( !gv.is_ghost_cell(unsigned(c)) ) cnt[c] = off[c + 1] - off[c];
+  for(size_t i = 0; i < mine.size(); i++) cnt[mine[i].ghost_cell] = recv_counts[i];
+  for(uint64_t c = 0; c < ctx->ncells; c++) new_off[c + 1] = new_off[c] + cnt[c];
+  int rc = xsb_internal_relayout(ctx, new_off.data()); if( rc ) return rc;
+
+  // particle-level lists
+  const double box[3] = { dom->box[0], dom->box[1], dom->box[2] };
+  for(int c = 0; c < 27; c++) { G->shift[c][0] = (c % 3 - 1) * box[0]; G->shift[c][1] = ((c / 3) % 3 - 1) * box[1]; G->shift[c][2] = (c / 9 - 1) * box[2]; }
+  std::vector<unsigned> sidx, ridx, sseg, rseg; std::vector<unsigned char> scode;
+  G->send_off.assign(P + 1, 0); G->recv_off.assign(P + 1, 0);
+  for(int q = 0; q < P; q++)
+  {
+    for(const GhostCell& g : to_peer[q])
+    {
+      XSB_REQUIRE(ctx, std::abs(g.w[0]) <= 1 && std::abs(g.w[1]) <= 1 && std::abs(g.w[2]) <= 1, XSB_ERR_UNSUPPORTED, "ghost layers wider than the periodic domain");
+      const unsigned code = unsigned(shift_code(g.w));
+      for(uint64_t p = new_off[g.owner_cell]; p < new_off[g.owner_cell + 1]; p++) { sidx.push_back(unsigned(p)); scode.push_back((unsigned char)code); sseg.push_back(unsigned(q)); }
+    }
+    G->send_off[q + 1] = unsigned(sidx.size());
+  }
+  for(int q = 0; q < P; q++)
+  {
+    for(unsigned i = rc_off[q]; i < rc_off[q + 1]; i++)
+      for(uint64_t p = new_off[mine[i].ghost_cell]; p < new_off[mine[i].ghost_cell + 1]; p++) { ridx.push_back(unsigned(p)); rseg.push_back(unsigned(q)); }
+    G->recv_off[q + 1] = unsigned(ridx.size());
+  }
+  G->n_send = unsigned(sidx.size()); G->n_recv = unsigned(ridx.size());
+  XSB_REQUIRE(ctx, G->send_off[me + 1] - G->send_off[me] == G->recv_off[me + 1] - G->recv_off[me], XSB_ERR_STATE, "ghost scheme: self segment mismatch");
+  XSB_CUDA(ctx, G->send_idx.reserve(sidx.size() + 16, 1.05)); XSB_CUDA(ctx, G->send_code.reserve(scode.size() + 16, 1.05)); XSB_CUDA(ctx, G->recv_idx.reserve(ridx.size() + 16, 1.05));
+  XSB_CUDA(ctx, ctx->gseg_send.reserve(sseg.size() + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_send.reserve(P + 2));
+  XSB_CUDA(ctx, ctx->gseg_recv.reserve(rseg.size() + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_recv.reserve(P + 2));
+  if( !sidx.empty() )
+  {
+    XSB_CUDA(ctx, cudaMemcpyAsync(G->send_idx.p, sidx.data(), sidx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(G->send_code.p, scode.data(), scode.size(), cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->gseg_send.p, sseg.data(), sseg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if( !ridx.empty() )
+  {
+    XSB_CUDA(ctx, cudaMemcpyAsync(G->recv_idx.p, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->gseg_recv.p, rseg.data(), rseg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_send.p, G->send_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_recv.p, G->recv_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // ghost_update_all_no_fv: every persistent field travels once
+  return exchange(ctx, (1u << XSB_F_RX) | (1u << XSB_F_RY) | (1u << XSB_F_RZ) | (1u << XSB_F_VX) | (1u << XSB_F_VY) | (1u << XSB_F_VZ) | (1u << XSB_F_TYPE) | (1u << XSB_F_ID), false);
+}
+
+int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  return exchange(ctx, field_mask, false);
+}
+
+int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  return exchange(ctx, field_mask, true);
+}
+
+} // extern "C"

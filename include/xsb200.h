@@ -92,6 +92,13 @@ int      xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* grid);
 int      xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* cell_particle_offset);
 uint64_t xsb_num_particles(const xsb_ctx* ctx);
 uint64_t xsb_num_cells(const xsb_ctx* ctx);
+uint64_t xsb_num_own_particles(const xsb_ctx* ctx);       /* particles in non-ghost cells              */
+int      xsb_cell_offsets_download(xsb_ctx* ctx, uint64_t* cell_particle_offset);   /* ncells+1 entries */
+/* bins n unsorted particles (HOST arrays; v*, type, id may be NULL) into the own cells of the grid:    */
+/* stable sort by cell, ghost cells left empty (lattice / init_rcb_grid + particle insertion of the      */
+/* decks).  Follow with xsb_ghost_comm_scheme.                                                            */
+int      xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const double* ry, const double* rz,
+                              const double* vx, const double* vy, const double* vz, const uint8_t* type, const uint64_t* id);
 /* whole-array copies between host buffers and the context's device SoA (N or 9N elements)              */
 int      xsb_field_upload(xsb_ctx* ctx, int field, const void* host_src);
 int      xsb_field_download(xsb_ctx* ctx, int field, void* host_dst);
@@ -163,13 +170,33 @@ typedef struct xsb_domain_desc {
 /* NCCL communicator from a 128-byte ncclUniqueId created by rank 0 (xsb_comm_unique_id)                  */
 int xsb_comm_unique_id(void* id128);
 int xsb_comm_init(xsb_ctx* ctx, int nranks, int rank, const void* id128);
-/* ghost_comm_scheme + ghost_update_all_no_fv (config_move_particles.msp:82-87): given the own-cell       */
-/* particle counts, lays out ghost cells, exchanges counts and fills every ghost field.                   */
-int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom, const uint64_t* own_cell_count);
+int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host);   /* MPI_Allreduce(MAX) of particle_displ_over */
+/* ghost_comm_scheme + ghost_update_all_no_fv (config_move_particles.msp:82-87).  Precondition: the grid is   */
+/* this rank's brick + ghost layers and the OWN cells hold their particles (ghost cells are ignored).        */
+/* Effect: peers exchange per-cell counts, the SoA is re-laid out with every ghost cell sized for its        */
+/* images, and r (shifted by the periodic box), v, type, id are copied owner -> ghost.  The particle count    */
+/* and cell offsets change: re-read them with xsb_num_particles / xsb_cell_offsets_download.                  */
+int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom);
 /* ghost_update_r / ghost_update_opt: owner -> ghost copy of the fields in field_mask (bit = xsb_field)   */
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
 /* update_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29): ghost -> owner add                  */
 int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask);
+
+/* move_particles (config_move_particles.msp:121-125) for a single rank: wrap into the periodic box,     */
+/* re-bin own particles into cells; ghost cells are emptied (call xsb_ghost_comm_scheme next).           */
+int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom);
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* "next" rows: the per-particle operators either side of the force path               */
+/* push_f_v_r: r += v dt + a dt^2/2 (a in fx,fy,fz after force_to_accel; grid-space r, INV_XFORM);       */
+/* push_f_v: v += a dt  (config_numerical_schemes.msp:23-52 calls it with dt/2)                          */
+int xsb_push_f_v_r(xsb_ctx* ctx, double dt);
+int xsb_push_f_v(xsb_ctx* ctx, double dt);
+/* force_to_accel (src/compute/force_to_accel.cu:82-101): f /= mass[type]                               */
+int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass);
+/* backup_r + particle_displ_over (config_move_particles.msp:19-23): result = max |r - r_backup| > thr   */
+int xsb_backup_r(xsb_ctx* ctx);
+int xsb_particle_displ_over(xsb_ctx* ctx, double threshold, int* result, double* max_displ);
 
 #ifdef __cplusplus
 }

@@ -280,3 +280,101 @@ def test_c1_full_size_properties():
     # every owned pair (a,b) in the list has its mirror image listed as well: pair count is even per distance
     ep = ctx.download(xsb.F_EP)
     assert -0.09 < ep[own].mean() / EV < -0.03
+
+
+# ------------------------------------------------------------------------------------------------ a10 + grid assembly
+def assigned_ctx(pos, typ, box, cell, gl, vel=None):
+    n_own = np.round(box / cell).astype(int)
+    ctx = xsb.Context(0)
+    ctx.grid_set(xsb.make_grid(n_own + 2 * gl, gl, cell, [-gl * cell] * 3))
+    v = (None, None, None) if vel is None else (vel[:, 0], vel[:, 1], vel[:, 2])
+    ctx.particles_assign(pos[:, 0], pos[:, 1], pos[:, 2], *v, typ=typ)
+    ctx.set_domain(n_own)
+    ctx.ghost_comm_scheme()
+    return ctx
+
+
+@pytest.mark.parametrize("ncells,cell,gl", [(6, 5.0, 2), (4, 5.0, 3), (5, 2.5, 4)])
+def test_assign_and_ghost_scheme_equal_host_statement(ncells, cell, gl):
+    pos, typ, box = lattice("FCC", ncells, 5.0, 0.1, seed=7, types=[0, 1, 0, 1])
+    gs = GridSystem(pos, typ, box, cell, gl)
+    ctx = assigned_ctx(pos, typ, box, cell, gl)
+    assert ctx.n == gs.n and ctx.n_own == gs.n_owned
+    assert np.array_equal(ctx.cell_offsets(), gs.cell_off)
+    assert ctx.download(xsb.F_RX).tobytes() == gs.rx.tobytes()
+    assert ctx.download(xsb.F_RY).tobytes() == gs.ry.tobytes()
+    assert ctx.download(xsb.F_RZ).tobytes() == gs.rz.tobytes()
+    assert np.array_equal(ctx.download(xsb.F_TYPE), gs.type)
+    assert np.array_equal(ctx.download(xsb.F_ID), gs.src_index.astype(np.uint64))
+
+
+def test_ghost_update_and_reduce_add():
+    pos, typ, box = lattice("FCC", 5, 5.0, 0.1, seed=9)
+    gs = GridSystem(pos, typ, box, 5.0, 2)
+    ctx = assigned_ctx(pos, typ, box, 5.0, 2)
+    rng = np.random.default_rng(11)
+    # move owners, ghosts must follow with their periodic shift (ghost_update_r)
+    d = rng.normal(0, 0.05, (len(pos), 3))
+    newpos = pos + d
+    rx = gs.rx.copy(); own = ~gs.is_ghost
+    rx[own] = newpos[gs.src_index[own], 0]
+    ctx.upload(xsb.F_RX, rx)
+    ctx.ghost_update([xsb.F_RX])
+    expect = newpos[gs.src_index, 0] + (gs.rx - pos[gs.src_index, 0])       # same shift as before
+    got = ctx.download(xsb.F_RX)
+    assert np.max(np.abs(got - expect)) < 1e-12
+    # ghost_update_opt on an optional field
+    emb = rng.normal(0, 1, gs.n); emb[~own] = 0
+    ctx.upload(xsb.F_RHO_DEMB, emb)
+    ctx.ghost_update([xsb.F_RHO_DEMB])
+    per_atom = np.zeros(len(pos)); per_atom[gs.src_index[own]] = emb[own]
+    assert np.array_equal(ctx.download(xsb.F_RHO_DEMB), per_atom[gs.src_index])
+    # update_force_energy_from_ghost: owners receive the sum of their images
+    f = rng.normal(0, 1, gs.n)
+    ctx.upload(xsb.F_FX, f); ctx.upload(xsb.F_EP, f)
+    ctx.ghost_reduce_add([xsb.F_FX, xsb.F_EP])
+    tot = np.zeros(len(pos)); np.add.at(tot, gs.src_index, f)
+    got = ctx.download(xsb.F_FX)
+    assert np.max(np.abs(got[own] - tot[gs.src_index[own]])) < 1e-12
+    assert np.max(np.abs(ctx.download(xsb.F_EP)[own] - tot[gs.src_index[own]])) < 1e-12
+
+
+def test_nve_loop_pieces_and_rebin():
+    """push_f_v_r / push_f_v / force_to_accel / backup_r / particle_displ_over / rebin against numpy."""
+    pos, typ, box = lattice("FCC", 5, 5.0, 0.1, seed=13)
+    rng = np.random.default_rng(17)
+    vel = rng.normal(0, 2.0, pos.shape)
+    gs = GridSystem(pos, typ, box, 5.0, 2)
+    ctx = assigned_ctx(pos, typ, box, 5.0, 2, vel)
+    own = ~gs.is_ghost
+    f = rng.normal(0, 50.0, (gs.n, 3))
+    for k, fld in enumerate((xsb.F_FX, xsb.F_FY, xsb.F_FZ)):
+        ctx.upload(fld, f[:, k])
+    mass = 39.948
+    ctx.force_to_accel([mass])
+    ax = ctx.download(xsb.F_FX)
+    assert np.allclose(ax[own], f[own, 0] / mass, rtol=1e-15) and np.array_equal(ax[~own], f[~own, 0])
+    ctx.backup_r()
+    dt = 1e-3
+    ctx.push_f_v_r(dt)
+    x = ctx.download(xsb.F_RX)
+    v0 = vel[gs.src_index, 0]
+    assert np.allclose(x[own], gs.rx[own] + v0[own] * dt + 0.5 * ax[own] * dt * dt, rtol=1e-15, atol=1e-15)
+    ctx.push_f_v(0.5 * dt)
+    assert np.allclose(ctx.download(xsb.F_VX)[own], v0[own] + ax[own] * 0.5 * dt, rtol=1e-15)
+    over, dmax = ctx.particle_displ_over(0.5)
+    disp = np.sqrt(sum((ctx.download(fl)[own] - g[own]) ** 2 for fl, g in ((xsb.F_RX, gs.rx), (xsb.F_RY, gs.ry), (xsb.F_RZ, gs.rz))))
+    assert not over and abs(dmax - disp.max()) < 1e-12
+    over, _ = ctx.particle_displ_over(disp.max() * 0.5)
+    assert over
+    # big move, then move_particles: wrap + re-bin + ghosts equals binning the moved positions from scratch
+    ctx.push_f_v_r(1.0)
+    newp = np.stack([ctx.download(fl)[own] for fl in (xsb.F_RX, xsb.F_RY, xsb.F_RZ)], axis=1)
+    ids = ctx.download(xsb.F_ID)[own]
+    ctx.particles_rebin(); ctx.ghost_comm_scheme()
+    wrapped = newp - np.floor(newp / box) * box
+    wrapped = np.where(wrapped >= box, 0.0, wrapped)
+    gs2 = GridSystem(wrapped, typ, box, 5.0, 2)
+    assert np.array_equal(ctx.cell_offsets(), gs2.cell_off)
+    assert np.max(np.abs(ctx.download(xsb.F_RX) - gs2.rx)) < 1e-9
+    assert np.array_equal(ctx.download(xsb.F_ID), ids[gs2.src_index])
