@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- atom-timesteps/s of the short-range force hot path (neighbour + force) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the CPU restatement of the reference path on the host cores)
+
+Workload at N=1: BASELINE.json configs[1] "EAM Cu FCC 2M atoms NVE on 1xB200": FCC Cu a=3.6 ang, 79^3 unit cells =
+1 972 156 atoms, Gaussian position noise 0.1 ang (seed 1), 300 K Maxwell velocities, tabulated eam/alloy (setfl)
+potential with the header of the reference's Cu.eam.alloy (nrho 10000 x 0.02, nr 5000, rc 7.29 ang; Sutton-Chen form,
+generated at run time), rcut_inc (skin) 1.0 ang, dt 1 fs, eam_alloy_force driven in three phases
+(rho, rho2emb | ghost_update_opt rho_dEmb | force) exactly as data/regression_new/potentials/eam/eam_alloy decks do.
+One "step" = one full NVE Verlet step: push_f_v_r, push_f_v, particle_displ_over trigger, ghost_update_r (or, when the
+trigger fires / every --rebuild-every steps: move_particles + ghost_comm_scheme + chunk_neighbors), zero_force_energy,
+the EAM phases, force_to_accel, push_f_v.  N>1 is weak scaling: every rank owns a 79^3-unit-cell brick.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from helpers import EV, SC_CU, lattice, write_setfl  # noqa: E402
+
+A_CU, RCUT, SKIN, DT, MASS_CU = 3.6, 7.29, 1.0, 1.0e-3, 63.546
+KB_INTERNAL = 8.617333262e-5 * EV      # Boltzmann constant, internal energy units per K
+METRIC, UNIT = "atom-timesteps/s (neighbor+force)", "atom-timesteps/s"
+
+
+def rank_dims(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def make_setfl(tmpdir):
+    path = os.path.join(tmpdir, "Cu_sc.eam.alloy")
+    write_setfl(path, [SC_CU], nrho=10000, drho=0.02, nr=5000, rc=RCUT)
+    return path
+
+
+def brick_system(ucells, coord, seed):
+    """one rank's brick of the FCC lattice: positions in GLOBAL coordinates, velocities, types"""
+    pos, typ, box = lattice("FCC", ucells, A_CU, 0.1, seed=seed)
+    # noise may push atoms slightly out of the brick: they are clamped into the brick's border cells, which is
+    # harmless for a first list build (cell edge has > 0.1 ang of slack) and fixed by the first move_particles
+    pos = pos + np.asarray(coord, dtype=np.float64) * box
+    rng = np.random.default_rng(seed + 1000)
+    vel = rng.normal(0.0, np.sqrt(KB_INTERNAL * 300.0 / MASS_CU), pos.shape)
+    vel -= vel.mean(axis=0)
+    return pos, vel, typ, box
+
+
+def n_cells_for(box_len):
+    return int(np.floor(box_len / (RCUT + SKIN)))
+
+
+class Clocks:
+    """samples nvidia-smi clocks + throttle reasons while the timed region runs (recipe: B200_PROFILING.md)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hi = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample_ucells, steps, rebuild_every):
+    """times the CPU restatement (oracle/, OpenMP on all host cores) of chunk_neighbors + eam_alloy_force on a bounded
+    sample of the same workload; returns atom-timesteps/s and a description."""
+    from oracle import oracle as O
+    from helpers import GridSystem
+    tmp = tempfile.mkdtemp()
+    path = make_setfl(tmp)
+    pos, typ, box = lattice("FCC", sample_ucells, A_CU, 0.1, seed=1)
+    nc = n_cells_for(box[0])
+    gs = GridSystem(pos, typ, box, box[0] / nc, 1)
+    g = gs.oracle_grid()
+    eam = O.EamAlloy(path)
+    fx, fy, fz, ep, emb = [gs.zeros() for _ in range(5)]
+    t0 = time.perf_counter()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, RCUT + SKIN, 1, True)
+    t_nb = time.perf_counter() - t0
+    # eam_ghost=false + rho_dEmb ghost copy between the phases, like the GPU arm
+    own = ~gs.is_ghost
+    owner_of = np.zeros(len(pos), dtype=np.int64); owner_of[gs.src_index[own]] = np.nonzero(own)[0]
+    t_force = 0.0
+    for _ in range(steps):
+        fx[:] = 0; fy[:] = 0; fz[:] = 0; ep[:] = 0
+        t0 = time.perf_counter()
+        O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, RCUT, 1 | 2, fx, fy, fz, ep, None, emb)
+        emb[:] = emb[owner_of[gs.src_index]]
+        O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, RCUT, 8, fx, fy, fz, ep, None, emb)
+        t_force += time.perf_counter() - t0
+    per_step = t_force / steps + t_nb / rebuild_every
+    return gs.n_owned / per_step, {"atoms": int(gs.n_owned), "steps": steps, "nbh_build_s": t_nb, "force_s_per_step": t_force / steps,
+                                    "threads": O.lib().orc_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        v, info = cpu_reference_run(args.cpu_sample_cells, 1, args.rebuild_every)
+        vals.append(v)
+    vals = vals[args.warmup:]
+    value = float(np.mean(vals))
+    sample = "EAM Cu FCC %d^3 unit cells = %d atoms, same potential/cutoffs, 1 force step + 1/%d list build per step" % (
+        args.cpu_sample_cells, info["atoms"], args.rebuild_every)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * info["atoms"] / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0, "host_cores": cores}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": "EAM Cu FCC %d^3 unit cells x %d GPU = %d atoms, NVE Verlet, eam_alloy_force (setfl Sutton-Chen Cu, rc %.2f, skin %.1f)" % (
+                args.cells, n, 4 * args.cells ** 3 * n, RCUT, SKIN),
+            "baseline_config": "configs[1] EAM Cu FCC 2M atoms NVE on 1xB200",
+            "rebuild": "particle_displ_over(skin/2) trigger, forced at least every %d steps" % args.rebuild_every,
+            "l2": "inputs larger than L2 (positions + neighbour lists > 1 GB per GPU)",
+            "parallelism": "bricks %s" % "x".join(str(d) for d in rank_dims(n))}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_xsb(args):
+    import torch
+    import exastamp_b200 as xsb
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    xsb.build()
+    tmp = tempfile.mkdtemp()
+    setfl = make_setfl(tmp)
+    rd = rank_dims(world)
+    coord = (rank % rd[0], (rank // rd[0]) % rd[1], rank // (rd[0] * rd[1]))
+    pos, vel, typ, brick = brick_system(args.cells, coord, seed=1 + rank)
+    ncb = n_cells_for(brick[0])                        # cells per brick axis
+    cell = brick[0] / ncb
+    gcells = [ncb * d for d in rd]
+    origin = [(c * ncb - 1) * cell for c in coord]
+    ctx = xsb.Context(local)
+    if world > 1:
+        ids = [xsb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+    ctx.grid_set(xsb.make_grid([ncb + 2] * 3, 1, cell, origin))
+    ctx.particles_assign(pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2], typ)
+    ctx.set_domain(gcells, (1, 1, 1), rd, coord)
+    ctx.ghost_comm_scheme()
+    ctx.eam_alloy_load(setfl)
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    n_own = ctx.n_own
+    state = {"rebuilds": 0, "since": 0}
+
+    def rebuild(first=False):
+        if not first:
+            if world == 1:
+                ctx.particles_rebin()
+            ctx.ghost_comm_scheme()
+        ctx.chunk_neighbors(RCUT + SKIN)
+        ctx.backup_r()
+        state["rebuilds"] += 1; state["since"] = 0
+
+    def forces():
+        ctx.zero_force_energy()
+        ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB)
+        ctx.ghost_update([xsb.F_RHO_DEMB])
+        ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE)
+        ctx.force_to_accel([MASS_CU])
+
+    def step():
+        ctx.push_f_v_r(DT); ctx.push_f_v(0.5 * DT)
+        state["since"] += 1
+        over, _ = ctx.particle_displ_over(0.5 * SKIN)
+        if over or state["since"] >= args.rebuild_every:
+            rebuild()
+        else:
+            ctx.ghost_update(POS)
+        forces()
+        ctx.push_f_v(0.5 * DT)
+
+    rebuild(first=True)
+    forces()
+    total_nbh, max_nbh = ctx.chunk_neighbors_stats()
+    n_l = total_nbh / max(1, ctx.n)
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    ctx.profile_enable(True)
+    l0 = ctx.launches; rb0 = state["rebuilds"]
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_dev = ctx.timer_stop_ms()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches - l0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clk = clocks.stop() if clocks else None
+    ms = max(ms_dev, 0.0)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        cnt = torch.tensor([float(n_own)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt); atoms_total = int(cnt.item())
+    else:
+        atoms_total = n_own
+    value = atoms_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the plugin use case.  The host application owns the particle arrays (pinned host memory): every step
+    # it hands positions to the C ABI and reads forces + energies back.
+    e2e = None
+    if not args.no_e2e:
+        n_all = ctx.n
+        pin = [torch.empty(n_all, dtype=torch.float64).pin_memory() for _ in range(7)]
+        for k, f in enumerate(POS):
+            ctx.download_ptr(f, pin[k].data_ptr())
+        ke = max(3, min(args.steps, args.e2e_steps))
+
+        def e2e_step(i):
+            for k, f in enumerate(POS):
+                ctx.upload_ptr(f, pin[k].data_ptr())
+            if i % args.rebuild_every == 0:
+                ctx.chunk_neighbors(RCUT + SKIN)
+            ctx.zero_force_energy()
+            ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_EFLAG)
+            ctx.ghost_update([xsb.F_RHO_DEMB])
+            ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE | xsb.EAM_EFLAG)
+            for k, f in enumerate((xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)):
+                ctx.download_ptr(f, pin[3 + k].data_ptr())
+
+        for i in range(2):
+            e2e_step(i + 1)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            e2e_step(i)
+        barrier()
+        te = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); te = float(t.item())
+        e2e = {"value": atoms_total * ke / te, "unit": UNIT, "h2d_bytes_per_step": int(24 * n_all), "d2h_bytes_per_step": int(32 * n_all),
+               "steps": ke, "what": "host pinned r -> xsb_field_upload, chunk_neighbors every %d steps, zero + eam_alloy_force phases with energies, "
+                                    "xsb_field_download of fx,fy,fz,ep" % args.rebuild_every}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (eam_alloy force pass), algorithmic bytes per SURVEY.md 8(d)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    f_ms, f_cnt = prof["eam_force"]
+    b_force = 24 + 1 + 8 + 2 * (1 + 2 * 27 + n_l) + 32
+    roof = None
+    if f_cnt:
+        dur = f_ms / f_cnt * 1e-3
+        ach = b_force * n_own / dur / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("eam_alloy_force_kernel", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": "eam_alloy_force_kernel", "avg_launch_ms": dur * 1e3, "algorithmic_bytes_per_atom": b_force,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "note": "FP64 pair math: this kernel sits on the FP64-pipe side of the ridge (SURVEY.md 8d); hbm frac is reported as the contract asks"}
+    breakdown = {k: {"ms_total": v[0], "intervals": v[1], "share": v[0] / ms if ms else None} for k, v in prof.items() if v[1]}
+    cpu = None
+    if not args.no_cpu:
+        v, info = cpu_reference_run(args.cpu_sample_cells, 2, args.rebuild_every)
+        cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
+               "sample": "EAM Cu FCC %d^3 unit cells = %d atoms, same potential/cutoffs; 2 force steps + list build/%d (oracle restatement, OpenMP)" % (
+                   args.cpu_sample_cells, info["atoms"], args.rebuild_every)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
+                       "rebuilds_in_timed_region": state["rebuilds"] - rb0, "host_wall_s": wall, "breakdown": breakdown}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="xsb", choices=["xsb", "reference"])
+    ap.add_argument("--cells", type=int, default=79, help="FCC unit cells per axis per GPU (79 -> 1 972 156 atoms)")
+    ap.add_argument("--rebuild-every", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-sample-cells", type=int, default=24)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_xsb(args)
+
+
+if __name__ == "__main__":
+    main()

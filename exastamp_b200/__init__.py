@@ -22,6 +22,7 @@ _FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
 # every symbol include/xsb200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "xsb_create", "xsb_destroy", "xsb_last_error", "xsb_sync", "xsb_version", "xsb_kernel_launch_count",
+    "xsb_profile_enable", "xsb_profile_read", "xsb_timer_record", "xsb_timer_elapsed_ms",
     "xsb_grid_set", "xsb_particles_set_cells", "xsb_num_particles", "xsb_num_cells", "xsb_field_upload",
     "xsb_field_download", "xsb_field_device_ptr", "xsb_zero_force_energy",
     "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
@@ -86,6 +87,10 @@ def load_library():
     L.xsb_sync.argtypes = [vp]
     L.xsb_kernel_launch_count.restype = u64
     L.xsb_kernel_launch_count.argtypes = [vp]
+    L.xsb_timer_record.argtypes = [vp, i32]
+    L.xsb_timer_elapsed_ms.argtypes = [vp, C.POINTER(dbl)]
+    L.xsb_profile_enable.argtypes = [vp, i32]
+    L.xsb_profile_read.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(u64)]
     L.xsb_grid_set.argtypes = [vp, C.POINTER(GridDesc)]
     L.xsb_particles_set_cells.argtypes = [vp, vp]
     L.xsb_num_particles.restype = u64
@@ -273,6 +278,36 @@ class Context:
 
     def eam_alloy_force(self, rcut, phases=EAM_RHO | EAM_RHO2EMB | EAM_GHOST | EAM_FORCE, flags=0):
         self._ck(self.L.xsb_eam_alloy_force(self.h, float(rcut), int(phases), int(flags)), "xsb_eam_alloy_force")
+
+    # ---- profiling (CUDA events on the context's stream)
+    PROF_TAGS = ["nbr_build", "pair", "eam_rho", "eam_rho2emb", "eam_force", "ghost", "integrate", "snap", "move"]
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.xsb_profile_enable(self.h, int(on)), "xsb_profile_enable")
+
+    def profile_read(self):
+        out = {}
+        for t, name in enumerate(self.PROF_TAGS):
+            ms, cnt = C.c_double(), C.c_uint64()
+            self._ck(self.L.xsb_profile_read(self.h, t, C.byref(ms), C.byref(cnt)), "xsb_profile_read")
+            out[name] = (ms.value, cnt.value)
+        return out
+
+    def timer_start(self):
+        self._ck(self.L.xsb_timer_record(self.h, 0), "xsb_timer_record")
+
+    def timer_stop_ms(self):
+        self._ck(self.L.xsb_timer_record(self.h, 1), "xsb_timer_record")
+        ms = C.c_double()
+        self._ck(self.L.xsb_timer_elapsed_ms(self.h, C.byref(ms)), "xsb_timer_elapsed_ms")
+        return ms.value
+
+    # raw-pointer variants for callers that manage their own (pinned) host buffers
+    def upload_ptr(self, field, ptr):
+        self._ck(self.L.xsb_field_upload(self.h, field, ptr), "xsb_field_upload")
+
+    def download_ptr(self, field, ptr):
+        self._ck(self.L.xsb_field_download(self.h, field, ptr), "xsb_field_download")
 
     # ---- a10
     def comm_init(self, nranks, rank, unique_id=None):

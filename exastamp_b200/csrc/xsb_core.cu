@@ -184,12 +184,60 @@ void xsb_destroy(xsb_ctx* ctx)
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->scratch.release(); ctx->scratch64.release();
   ctx->eam.frho.release(); ctx->eam.rtab.release();
   xsb_ghost_release(ctx);
+  for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 const char* xsb_last_error(const xsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t xsb_kernel_launch_count(const xsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int xsb_profile_enable(xsb_ctx* ctx, int on)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_on = on != 0;
+  for(int t = 0; t < XSB_PROF_COUNT_; t++) ctx->prof_used[t] = 0;
+  return XSB_OK;
+}
+
+int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* intervals)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, tag >= 0 && tag < XSB_PROF_COUNT_, XSB_ERR_INVALID, "unknown profile tag");
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for(size_t i = 0; i + 1 < ctx->prof_used[tag]; i += 2)
+  {
+    float ms = 0.f;
+    XSB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[tag][i], ctx->prof_ev[tag][i + 1]));
+    tot += ms;
+  }
+  if( ms_total ) *ms_total = tot;
+  if( intervals ) *intervals = ctx->prof_used[tag] / 2;
+  return XSB_OK;
+}
+
+// two-slot stopwatch on the context's stream: slot 0 = start, slot 1 = stop
+int xsb_timer_record(xsb_ctx* ctx, int slot)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, slot == 0 || slot == 1, XSB_ERR_INVALID, "timer slot must be 0 or 1");
+  if( !ctx->timer_ev[slot] ) XSB_CUDA(ctx, cudaEventCreate(&ctx->timer_ev[slot]));
+  XSB_CUDA(ctx, cudaEventRecord(ctx->timer_ev[slot], ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, ms && ctx->timer_ev[0] && ctx->timer_ev[1], XSB_ERR_STATE, "timer not recorded");
+  XSB_CUDA(ctx, cudaEventSynchronize(ctx->timer_ev[1]));
+  float f = 0.f;
+  XSB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->timer_ev[0], ctx->timer_ev[1]));
+  *ms = f;
+  return XSB_OK;
+}
 
 int xsb_sync(xsb_ctx* ctx)
 {

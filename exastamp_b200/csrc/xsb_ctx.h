@@ -118,6 +118,24 @@ struct xsb_ctx
   xsb::DevBuf<unsigned> gseg_send, gseg_recv, goff_send, goff_recv;   // ghost segment tables (device)
   xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
 
+  // per-operator device timing (CUDA events on this context's stream), see xsb_profile_*
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev[XSB_PROF_COUNT_];   // begin/end pairs
+  size_t prof_used[XSB_PROF_COUNT_] = {};
+  cudaEvent_t timer_ev[2] = { nullptr, nullptr };
+  void prof_begin(int tag)
+  {
+    if( !prof_on ) return;
+    if( prof_used[tag] + 2 > prof_ev[tag].size() ) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_ev[tag].push_back(a); prof_ev[tag].push_back(b); }
+    cudaEventRecord(prof_ev[tag][prof_used[tag]], stream);
+  }
+  void prof_end(int tag)
+  {
+    if( !prof_on ) return;
+    cudaEventRecord(prof_ev[tag][prof_used[tag] + 1], stream);
+    prof_used[tag] += 2;
+  }
+
   int fail(int code, const char* fmt, ...)
   {
     char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);

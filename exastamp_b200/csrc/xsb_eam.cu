@@ -461,14 +461,18 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     if( nsel )
     {
       const unsigned grid = groups_grid<TPA>(nsel, block);
+      ctx->prof_begin(XSB_PROF_EAM_RHO);
       if( xf ) eam_alloy_rho_kernel<TPA, true ><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb);
       else     eam_alloy_rho_kernel<TPA, false><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb);
+      ctx->prof_end(XSB_PROF_EAM_RHO);
       XSB_LAUNCH_CHECK(ctx);
     }
   }
   if( (phases & XSB_EAM_RHO2EMB) && nsel )
   {
+    ctx->prof_begin(XSB_PROF_EAM_RHO2EMB);
     eam_alloy_rho2emb_kernel<<<(nsel + 255) / 256, 256, 0, ctx->stream>>>(sel, nsel, T, ctx->type.p, emb, eflag ? ctx->f64[XSB_F_EP].p : nullptr);
+    ctx->prof_end(XSB_PROF_EAM_RHO2EMB);
     XSB_LAUNCH_CHECK(ctx);
   }
   if( (phases & XSB_EAM_FORCE) && ctx->n_own )
@@ -478,8 +482,10 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
     double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
 #   define XSB_EAM_GO(XF, EF, VIR) eam_alloy_force_kernel<TPA, XF, EF, VIR><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb, fx, fy, fz, ep, vir)
+    ctx->prof_begin(XSB_PROF_EAM_FORCE);
     if( xf ) { if( virial ) XSB_EAM_GO(true, true, true); else if( eflag ) XSB_EAM_GO(true, true, false); else XSB_EAM_GO(true, false, false); }
     else     { if( virial ) XSB_EAM_GO(false, true, true); else if( eflag ) XSB_EAM_GO(false, true, false); else XSB_EAM_GO(false, false, false); }
+    ctx->prof_end(XSB_PROF_EAM_FORCE);
 #   undef XSB_EAM_GO
     XSB_LAUNCH_CHECK(ctx);
   }

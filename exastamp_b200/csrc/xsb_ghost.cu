@@ -427,13 +427,19 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
-  return exchange(ctx, field_mask, false);
+  ctx->prof_begin(XSB_PROF_GHOST);
+  const int rc = exchange(ctx, field_mask, false);
+  ctx->prof_end(XSB_PROF_GHOST);
+  return rc;
 }
 
 int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
-  return exchange(ctx, field_mask, true);
+  ctx->prof_begin(XSB_PROF_GHOST);
+  const int rc = exchange(ctx, field_mask, true);
+  ctx->prof_end(XSB_PROF_GHOST);
+  return rc;
 }
 
 } // extern "C"

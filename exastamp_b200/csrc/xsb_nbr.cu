@@ -195,7 +195,9 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, ctx->nbh_count.reserve(n + 1, 1.02));
   XSB_CUDA(ctx, ctx->nbh_off.reserve(n + 2, 1.02));
   XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, 1.02));
+  XSB_CUDA(ctx, cudaMemsetAsync(ctx->nbh_off.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if( n == 0 ) { ctx->nbh_built = true; return XSB_OK; }
+  ctx->prof_begin(XSB_PROF_NBR_BUILD);
   NbrParams P; P.g = ctx->view(); P.n = n; P.d2max = nbh_dist_lab * nbh_dist_lab;
   int R[3]; search_range(ctx->grid, nbh_dist_lab, R); P.Rx = R[0]; P.Ry = R[1]; P.Rz = R[2];
   const int block = 256; const unsigned grid = unsigned((uint64_t(n) * 32 + block - 1) / block);
@@ -222,6 +224,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, ctx->nbh_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
   if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
   else                     nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
+  ctx->prof_end(XSB_PROF_NBR_BUILD);
   XSB_LAUNCH_CHECK(ctx);
   ctx->nbh_built = true;
   return XSB_OK;

@@ -118,11 +118,13 @@ static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int fl
   const double rc2 = rcut_max * rcut_max;
   const bool xf = !ctx->grid.xform_is_identity;
 # define XSB_PAIR_GO(XF, VIR, REAL) pair_force_kernel<TPA, XF, MULTI, VIR, REAL><<<grid, block, 0, ctx->stream>>>(P, X, prm, rc2, fx, fy, fz, ep, vir)
+  ctx->prof_begin(XSB_PROF_PAIR);
   if( mixed ) { if( xf ) { if( virial ) XSB_PAIR_GO(true, true, float); else XSB_PAIR_GO(true, false, float); }
                 else     { if( virial ) XSB_PAIR_GO(false, true, float); else XSB_PAIR_GO(false, false, float); } }
   else        { if( xf ) { if( virial ) XSB_PAIR_GO(true, true, double); else XSB_PAIR_GO(true, false, double); }
                 else     { if( virial ) XSB_PAIR_GO(false, true, double); else XSB_PAIR_GO(false, false, double); } }
 # undef XSB_PAIR_GO
+  ctx->prof_end(XSB_PROF_PAIR);
   XSB_LAUNCH_CHECK(ctx);
   return XSB_OK;
 }

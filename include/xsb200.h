@@ -85,6 +85,18 @@ int         xsb_sync(xsb_ctx* ctx);
 const char* xsb_version(void);
 uint64_t    xsb_kernel_launch_count(const xsb_ctx* ctx);   /* CUDA kernels launched by this context so far */
 
+/* per-operator device time, measured with CUDA events on the context's own stream (onika's              */
+/* `profiling.exectime`, data/config/config_defaults.msp:21-23).  tag = xsb_prof_tag.                      */
+typedef enum xsb_prof_tag {
+  XSB_PROF_NBR_BUILD = 0, XSB_PROF_PAIR, XSB_PROF_EAM_RHO, XSB_PROF_EAM_RHO2EMB, XSB_PROF_EAM_FORCE,
+  XSB_PROF_GHOST, XSB_PROF_INTEGRATE, XSB_PROF_SNAP, XSB_PROF_MOVE, XSB_PROF_COUNT_
+} xsb_prof_tag;
+int xsb_profile_enable(xsb_ctx* ctx, int on);               /* also resets the accumulators */
+int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* intervals);   /* syncs the stream */
+/* stopwatch on the context's stream: record slot 0 (start) and 1 (stop), then read the device time      */
+int xsb_timer_record(xsb_ctx* ctx, int slot);
+int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms);
+
 /* ---------------------------------------------------------------------------------------------------- */
 /* a1  Grid / GridCellParticles                                                                         */
 int      xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* grid);
