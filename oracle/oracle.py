@@ -76,6 +76,8 @@ def lib():
         L.orc_eam_alloy_eval.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dpp]
         L.orc_eam_alloy.argtypes = [gp, _u64p, _dp, _dp, _dp, _u8p, vp, vp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
         L.orc_num_threads.restype = C.c_int
+        L.orc_lj_eval.argtypes = [C.c_double, C.c_double, C.c_double, dpp, dpp]
+        L.orc_johnson_eval.argtypes = [_dp, C.c_int, C.c_double, dpp, dpp]
         L.orc_ev_internal.restype = C.c_double
         _lib = L
     return _lib

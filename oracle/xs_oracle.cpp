@@ -555,6 +555,16 @@ void orc_eam_alloy(const orc_grid_t* g, const uint64_t* cell_off, const double* 
   }
 }
 
+// scalar entry points used to pin the restated math against oracle/_ref and tests/golden/ref_math.json
+void orc_lj_eval(double epsilon, double sigma, double r, double* e, double* de) { lj_compute_energy(LJParams{epsilon, sigma}, r, *e, *de); }
+void orc_johnson_eval(const double* params19, int what, double x, double* f, double* df)
+{
+  JohnsonParams p; std::memcpy(&p, params19, sizeof(p));
+  if( what == 0 ) johnson_phi(p, x, *f, *df);
+  else if( what == 1 ) johnson_rho(p, x, *f, *df);
+  else johnson_fEmbed(p, x, *f, *df);
+}
+
 int orc_num_threads() { return omp_get_max_threads(); }
 double orc_ev_internal() { return EV_INTERNAL; }
 
