@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Summaries of ncu outputs for profiles/ (run in the build container; no GPU needed).
+
+  python tools/ncu_summary.py launches gpurun_out/x_launches.csv          > profiles/rNN_launches.txt
+  python tools/ncu_summary.py full     gpurun_out/x.ncu-rep [regex]       > profiles/rNN_full.txt
+"""
+import csv
+import re
+import subprocess
+import sys
+from collections import defaultdict
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+        "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio", "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
+        "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio",
+        "smsp__average_warp_latency_issue_stalled_wait.ratio", "smsp__average_warp_latency_issue_stalled_not_selected.ratio"]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[h]; kn = hdr.index("Kernel Name"); mv = hdr.index("Metric Value"); mu = hdr.index("Metric Unit")
+    d = defaultdict(lambda: [0, 0.0])
+    unit = None
+    for r in rows[h + 1:]:
+        if len(r) <= mv:
+            continue
+        unit = r[mu]
+        name = re.sub(r"\(.*", "", r[kn])[:70]
+        d[name][0] += 1; d[name][1] += float(r[mv].replace(",", ""))
+    tot = sum(v[1] for v in d.values())
+    print("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)  source: %s  unit: %s" % (path, unit))
+    print("%-72s %6s %14s %12s %7s" % ("kernel", "n", "total", "avg", "share"))
+    for k, v in sorted(d.items(), key=lambda kv: -kv[1][1]):
+        print("%-72s %6d %14.0f %12.0f %7.3f" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
+
+
+def full(path, pat=None):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kn = hdr.index("Kernel Name")
+    print("# ncu --set full --clock-control none  source: %s" % path)
+    for r in rows[2:]:
+        if pat and not re.search(pat, r[kn]):
+            continue
+        print("== %s" % r[kn][:150])
+        for k in KEYS:
+            if k in hdr:
+                print("   %-75s %18s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
