@@ -206,16 +206,20 @@ def run_xsb(args):
     ctx.eam_alloy_load(setfl)
     POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
     n_own = ctx.n_own
-    state = {"rebuilds": 0, "since": 0}
+    state = {"rebuilds": 0, "since": 0, "rebuild_s": 0.0, "move_s": 0.0}
 
     def rebuild(first=False):
+        ctx.sync(); t0 = time.perf_counter()
         if not first:
             if world == 1:
                 ctx.particles_rebin()
             ctx.ghost_comm_scheme()
+        ctx.sync(); t1 = time.perf_counter()
         ctx.chunk_neighbors(RCUT + SKIN)
         ctx.backup_r()
+        ctx.sync()
         state["rebuilds"] += 1; state["since"] = 0
+        state["move_s"] += t1 - t0; state["rebuild_s"] += time.perf_counter() - t0
 
     def forces():
         ctx.zero_force_energy()
@@ -250,7 +254,7 @@ def run_xsb(args):
     barrier()
     clocks = Clocks(local) if rank == 0 else None
     ctx.profile_enable(True)
-    l0 = ctx.launches; rb0 = state["rebuilds"]
+    l0 = ctx.launches; rb0 = state["rebuilds"]; state["rebuild_s"] = 0.0; state["move_s"] = 0.0
     t0 = time.perf_counter()
     ctx.timer_start()
     for _ in range(args.steps):
@@ -347,7 +351,8 @@ def run_xsb(args):
             "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
-                       "rebuilds_in_timed_region": state["rebuilds"] - rb0, "host_wall_s": wall, "breakdown": breakdown}}
+                       "rebuilds_in_timed_region": state["rebuilds"] - rb0, "rebuild_wall_s_total": state["rebuild_s"],
+                       "move_particles_wall_s_total": state["move_s"], "host_wall_s": wall, "breakdown": breakdown}}
     print(json.dumps(line))
 
 

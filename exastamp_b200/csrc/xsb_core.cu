@@ -182,7 +182,7 @@ void xsb_destroy(xsb_ctx* ctx)
   for(auto& b : ctx->f64) b.release();
   ctx->type.release(); ctx->id.release();
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->scratch.release(); ctx->scratch64.release();
-  ctx->eam.frho.release(); ctx->eam.rtab.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release();
   xsb_ghost_release(ctx);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);

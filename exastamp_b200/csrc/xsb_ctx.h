@@ -66,7 +66,8 @@ struct EamAlloyDev
   int nelements = 0, nr = 0, nrho = 0;
   double rdr = 0, rdrho = 0, rc = 0, rhomax = 0, conv_z2r = 0, conv_frho = 0;
   DevBuf<double> frho;      // reference layout [nel][nrho+1][8]
-  DevBuf<double> rtab;      // fused r-tables, see xsb_eam.cu
+  DevBuf<double> rtab;      // r-tables in the reference layout: rhor [nel][nr+1][8] then z2r [npairs][nr+1][8]
+  DevBuf<double> fc;        // the same r-tables as Hermite knots {f, c5} : [nel + npairs][nr+1][2] (xsb_eam.cu)
   bool set = false;
 };
 
@@ -103,6 +104,12 @@ struct xsb_ctx
   xsb::DevBuf<unsigned> nbh_idx;              // [total]
   uint64_t nbh_total = 0;
   unsigned nbh_max = 0;
+  // tile-local view of the same list (xsb_tile.cuh): uint16 stage indices, same offsets as nbh_off
+  bool tile_ok = false;                       // false -> force operators use the generic CSR-gather kernels
+  int tile_TX = 1, tile_R[3] = {1, 1, 1};
+  unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
+  double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time
+  xsb::DevBuf<unsigned short> tl_idx;         // [total]
   xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.
   xsb::DevBuf<unsigned long long> scratch64;  // misc u64 scratch
 

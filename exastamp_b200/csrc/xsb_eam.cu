@@ -5,7 +5,9 @@
 //  * eam_alloy_force: multi-species tabulated (setfl) EAM, phases rho / rho2emb / force.
 //      operator eam_potential_multimat.cu:65-259, functors eam_force_op_multimat.h:107-343,
 //      tables + evaluation src/potential/eam_potentials/eam_alloy/eam_alloy.h:37-313, reader eam_alloy.cpp:66-278.
-#include "xsb_traverse.cuh"
+#include "xsb_tilepass.cuh"
+#include <climits>
+#include <cmath>
 #include <fstream>
 #include <limits>
 #include <string>
@@ -164,6 +166,59 @@ __global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XFor
   }
 }
 
+// ---- the same two passes as functors for the persistent tile kernel (xsb_tilepass.cuh) ----------------------------
+struct JohnsonEmbTileOp
+{
+  static constexpr bool HAS_W = false, TYPES = false;
+  double rcut2; JohnsonP p; double *ep, *rho_dEmb;
+  __host__ __device__ size_t table_bytes() const { return 0; }
+  __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
+  struct Acc { double rho; unsigned cnt; };
+  __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; A.cnt = 0; }
+  __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<false, false>&, const unsigned char*) const {}
+  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
+  {
+    double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
+    A.rho += rho; ++A.cnt;
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.rho = group_sum<TPA>(A.rho);
+#   pragma unroll
+    for(int o = TPA / 2; o > 0; o >>= 1) A.cnt += __shfl_xor_sync(0xffffffffu, A.cnt, o);
+    if( valid && sub == 0 && A.cnt > 0 ) { double f, df; johnson_fEmbed(p, A.rho, f, df); ep[a] += f; rho_dEmb[a] = df; }
+  }
+};
+
+template<bool VIRIAL>
+struct JohnsonForceTileOp
+{
+  static constexpr bool HAS_W = true, TYPES = false;
+  double rcut2; JohnsonP p; double *fx, *fy, *fz, *ep, *vir;
+  __host__ __device__ size_t table_bytes() const { return 0; }
+  __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
+  struct Acc { double fx, fy, fz, ep, fpi; Vir9 v; };
+  __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; if( VIRIAL ) A.v.zero(); }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<true, false>& B, const unsigned char*) const { A.fpi = B.w[sa]; }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*) const
+  {
+    const double r = sqrt(d2);
+    double rho, drho, phi, dphi;
+    johnson_rho(p, r, rho, drho);
+    johnson_phi(p, r, phi, dphi);
+    const double de = (drho * (A.fpi + B.w[j]) + dphi) / r;
+    const double fex = de * dx, fey = de * dy, fez = de * dz;
+    A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * phi;
+    if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz); A.ep = group_sum<TPA>(A.ep);
+    if( VIRIAL ) A.v.template reduce<TPA>();
+    if( valid && sub == 0 ) { fx[a] += A.fx; fy[a] += A.fy; fz[a] += A.fz; ep[a] += A.ep; if( VIRIAL ) A.v.store_add(vir, a); }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // eam/alloy tabulated EAM
 // ------------------------------------------------------------------------------------------------
@@ -297,6 +352,135 @@ __global__ void __launch_bounds__(256) eam_alloy_force_kernel(ParticleView P, XF
   }
 }
 
+// ---- tile path: the r-tables as Hermite knots {f, c5} (16 B/row instead of 64 B) ------------------------------------
+// The reference rows hold c6=f[m], c5=f'[m]*delta and c4, c3, c2..c0 derived from (f[m], f[m+1], c5[m], c5[m+1])
+// (interpolate(), eam_alloy.cpp:29-58).  Re-deriving c4, c3 per pair costs 5 FP64 ops and shrinks a table 4x, so the
+// window of rows a simulation can touch (r >= ~0.9 r_min) fits in shared memory next to the stage buffers:
+// a 5000-row table is 61 KiB instead of 320 KiB.  Values agree with the 7-coefficient rows to rounding (~1e-16 rel).
+struct EamFcView
+{
+  const double2* __restrict__ g;   // global {f, c5}: [ntab][nr+1], tables ordered rhor[nel] then z2r[npairs]
+  int nr, m_lo, rows, ntab_smem;   // smem window = rows [m_lo, m_lo+rows) of the first ntab_smem tables (rows = 0: none)
+  double rdr;
+  __host__ __device__ size_t table_bytes() const { return size_t(rows) * size_t(ntab_smem) * sizeof(double2); }
+  __device__ __forceinline__ void load(unsigned char* smem, int nt) const
+  {
+    double2* sm = reinterpret_cast<double2*>(smem);
+    const int tot = rows * ntab_smem;
+    for(int i = threadIdx.x; i < tot; i += nt) { const int t = i / rows, r = i - t * rows; sm[i] = g[size_t(t) * (nr + 1) + m_lo + r]; }
+  }
+  __device__ __forceinline__ void lookup(double r, int& m, double& p) const
+  {
+    p = r * rdr + 1.0;
+    m = __double2int_rz(p);
+    m = min(m, nr - 1);
+    p -= m;
+    p = fmin(p, 1.0);
+  }
+  // knots m and m+1 of table t
+  __device__ __forceinline__ void knots(const unsigned char* smem, int t, int m, double2& k0, double2& k1) const
+  {
+    if( m >= m_lo ) { const double2* sm = reinterpret_cast<const double2*>(smem) + t * rows + (m - m_lo); k0 = sm[0]; k1 = sm[1]; }
+    else { const double2* q = g + size_t(t) * (nr + 1) + m; k0 = q[0]; k1 = q[1]; }
+  }
+};
+
+__device__ __forceinline__ void hermite_c(const double2 k0, const double2 k1, double& c3, double& c4)
+{
+  const double df = k1.x - k0.x;
+  c4 = 3.0 * df - 2.0 * k0.y - k1.y;
+  c3 = k0.y + k1.y - 2.0 * df;
+}
+
+template<bool MULTI>
+struct EamRhoTileOp
+{
+  static constexpr bool HAS_W = false, TYPES = MULTI;
+  double rcut2; EamFcView T; double* rho_dEmb;
+  __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
+  __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
+  struct Acc { double rho; };
+  __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; }
+  __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<HAS_W, TYPES>&, const unsigned char*) const {}
+  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  {
+    const double r = d2 * rsqrt(d2);
+    int m; double p; T.lookup(r, m, p);
+    double2 k0, k1; T.knots(tab, MULTI ? int(B.t[j]) : 0, m, k0, k1);    // density table of the NEIGHBOUR's element
+    double c3, c4; hermite_c(k0, k1, c3, c4);
+    A.rho += ((c3 * p + c4) * p + k0.y) * p + k0.x;
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.rho = group_sum<TPA>(A.rho);
+    if( valid && sub == 0 ) rho_dEmb[a] += A.rho;
+  }
+};
+
+template<bool MULTI, bool EFLAG, bool VIRIAL>
+struct EamForceTileOp
+{
+  static constexpr bool HAS_W = true, TYPES = MULTI;
+  double rcut2; EamFcView T; int nel; double conv_z2r;
+  double *fx, *fy, *fz, *ep, *vir;
+  __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
+  __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
+  struct Acc { double fx, fy, fz, ep, fpi; int ta; Vir9 v; };
+  __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; A.ta = 0; if( VIRIAL ) A.v.zero(); }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const
+  { A.fpi = B.w[sa]; if( MULTI ) A.ta = B.t[sa]; }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  {
+    const double recip = rsqrt(d2), r = d2 * recip;
+    int m; double p; T.lookup(r, m, p);
+    const int tb = MULTI ? int(B.t[j]) : 0;
+    double2 k0, k1; double c3, c4;
+    T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4);
+    const double rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr;
+    double rhojp = rhoip;
+    if( MULTI && tb != A.ta ) { T.knots(tab, tb, m, k0, k1); hermite_c(k0, k1, c3, c4); rhojp = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+    T.knots(tab, nel + z2r_index(A.ta, tb), m, k0, k1); hermite_c(k0, k1, c3, c4);
+    const double z2p = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr;
+    const double z2 = ((c3 * p + c4) * p + k0.y) * p + k0.x;
+    double phi = z2 * recip;
+    const double phip = (z2p * recip - phi * recip) * conv_z2r;
+    phi *= conv_z2r;
+    const double fpair = (A.fpi * rhojp + B.w[j] * rhoip + phip) * recip;
+    const double fex = dx * fpair, fey = dy * fpair, fez = dz * fpair;
+    A.fx += fex; A.fy += fey; A.fz += fez;
+    if( EFLAG ) A.ep += 0.5 * phi;
+    if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz);
+    if( EFLAG ) A.ep = group_sum<TPA>(A.ep);
+    if( VIRIAL ) A.v.template reduce<TPA>();
+    if( valid && sub == 0 ) { fx[a] += A.fx; fy[a] += A.fy; fz[a] += A.fz; if( EFLAG ) ep[a] += A.ep; if( VIRIAL ) A.v.store_add(vir, a); }
+  }
+};
+
+// shared-memory window of the {f,c5} tables for a tile pass: rows [m_lo, nr] of the first ntab tables, as large a
+// window as the 227 KiB budget allows next to the 2 stage buffers (pairs below the window read the global copy)
+template<bool HAS_W, bool TYPES>
+static EamFcView make_fc_view(const xsb_ctx* ctx, int ntab)
+{
+  const EamAlloyDev& E = ctx->eam;
+  EamFcView T{ reinterpret_cast<const double2*>(E.fc.p), E.nr, INT_MAX, 0, ntab, E.rdr };
+  const size_t fixed = tile_smem_bytes<HAS_W, TYPES>(ctx->tile_s_cap, 0) + 64;
+  if( fixed >= TILE_SMEM_MAX ) return T;
+  const size_t max_rows = (TILE_SMEM_MAX - fixed) / (sizeof(double2) * size_t(ntab));
+  // rows a pair can reach: m >= floor(r_min * rdr + 1); keep a 10 % margin in r for the drift until the next rebuild
+  const double rmin = 0.9 * std::sqrt(ctx->nbh_d2min > 0.0 ? ctx->nbh_d2min : 0.0);
+  int m_lo = std::max(1, int(rmin * E.rdr + 1.0) - 1);
+  int rows = E.nr + 1 - m_lo;
+  if( rows < 2 ) return T;
+  if( size_t(rows) > max_rows ) { rows = int(max_rows); m_lo = E.nr + 1 - rows; }   // keep the far end (most pairs are at large r)
+  if( rows < 64 ) return T;
+  T.m_lo = m_lo; T.rows = rows;
+  return T;
+}
+
 // LAMMPS-style 7-coefficient spline rows (eam_alloy.cpp:29-58), rows padded to 8 doubles, row 0 unused
 static void interpolate(int n, double delta, const double* f, double* s)
 {
@@ -336,6 +520,29 @@ int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int
   constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
   ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr, 0 };
   double* emb = ctx->f64[XSB_F_RHO_DEMB].p;
+  if( ctx->tile_ok )
+  {
+    if( (phases & 1) && ctx->n )
+    {
+      XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
+      JohnsonEmbTileOp op{ rc2, p, ctx->f64[XSB_F_EP].p, emb };
+      ctx->prof_begin(XSB_PROF_EAM_RHO);
+      int rc = launch_tile_pass<16, 1024>(ctx, (phases & 2) != 0, op, nullptr);
+      ctx->prof_end(XSB_PROF_EAM_RHO);
+      if( rc ) return rc;
+    }
+    if( (phases & 4) && ctx->n_own )
+    {
+      double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+      int rc;
+      ctx->prof_begin(XSB_PROF_EAM_FORCE);
+      if( virial ) { JohnsonForceTileOp<true> op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb); }
+      else         { JohnsonForceTileOp<false> op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb); }
+      ctx->prof_end(XSB_PROF_EAM_FORCE);
+      if( rc ) return rc;
+    }
+    return XSB_OK;
+  }
   if( (phases & 1) && ctx->n )
   {
     const bool ghost = phases & 2;
@@ -430,6 +637,15 @@ int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
   XSB_CUDA(ctx, cudaMemcpyAsync(E.frho.p, t->frho, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(E.rtab.p, t->rhor, nrr * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(E.rtab.p + nrr, t->z2r, nzz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // Hermite-knot view {f = c6, c5} of the r-tables for the tile kernels
+    std::vector<double> fc(2 * (nrr + nzz) / 8);
+    for(size_t row = 0; row < nrr / 8; row++) { fc[2*row] = t->rhor[8*row + 6]; fc[2*row + 1] = t->rhor[8*row + 5]; }
+    for(size_t row = 0; row < nzz / 8; row++) { fc[2*(nrr/8 + row)] = t->z2r[8*row + 6]; fc[2*(nrr/8 + row) + 1] = t->z2r[8*row + 5]; }
+    XSB_CUDA(ctx, E.fc.reserve(fc.size() + 2));
+    XSB_CUDA(ctx, cudaMemcpyAsync(E.fc.p, fc.data(), fc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   E.nelements = t->nelements; E.nr = t->nr; E.nrho = t->nrho; E.rdr = t->rdr; E.rdrho = t->rdrho; E.rc = t->rc; E.rhomax = t->rhomax;
   E.conv_z2r = t->conversion_z2r; E.conv_frho = t->conversion_frho; E.set = true;
@@ -454,7 +670,18 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
   ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr, 0 };
   double* emb = ctx->f64[XSB_F_RHO_DEMB].p;
   const unsigned* sel = ghost ? nullptr : ctx->own_atoms.p; const unsigned nsel = unsigned(ghost ? ctx->n : ctx->n_own);
-  if( (phases & XSB_EAM_RHO) && ctx->n )
+  const bool tile = ctx->tile_ok, multi = E.nelements > 1;
+  if( tile && (phases & XSB_EAM_RHO) && ctx->n )
+  {
+    XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
+    int rc;
+    ctx->prof_begin(XSB_PROF_EAM_RHO);
+    if( multi ) { EamRhoTileOp<true>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements), emb }; rc = launch_tile_pass<16, 1024>(ctx, ghost, op, nullptr); }
+    else        { EamRhoTileOp<false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements), emb }; rc = launch_tile_pass<16, 1024>(ctx, ghost, op, nullptr); }
+    ctx->prof_end(XSB_PROF_EAM_RHO);
+    if( rc ) return rc;
+  }
+  if( !tile && (phases & XSB_EAM_RHO) && ctx->n )
   {
     XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
     P.atoms = sel; P.n_atoms = nsel;
@@ -475,7 +702,22 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     ctx->prof_end(XSB_PROF_EAM_RHO2EMB);
     XSB_LAUNCH_CHECK(ctx);
   }
-  if( (phases & XSB_EAM_FORCE) && ctx->n_own )
+  if( tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
+  {
+    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+    const int ntab = E.nelements + E.nelements * (E.nelements + 1) / 2;
+    int rc;
+    ctx->prof_begin(XSB_PROF_EAM_FORCE);
+#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { EamForceTileOp<MU, EF, VIR> op{ rc2, make_fc_view<true, MU>(ctx, ntab), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; \
+                                                  rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb); }
+    if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
+    else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
+#   undef XSB_EAM_TILE
+    ctx->prof_end(XSB_PROF_EAM_FORCE);
+    if( rc ) return rc;
+  }
+  if( !tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
   {
     P.atoms = ctx->own_atoms.p; P.n_atoms = unsigned(ctx->n_own);
     const unsigned grid = groups_grid<TPA>(P.n_atoms, block);

@@ -9,7 +9,9 @@
 // Build = two warp-per-particle sweeps (count, then fill) over the (2Ry+1)(2Rz+1) x-rows of cells around the
 // particle's cell: cells of one row are contiguous in the flat SoA (i fastest), so each row is one coalesced
 // run of candidates; lanes test 32 candidates per step and ballot-compact the survivors.
-#include "xsb_ctx.h"
+#include "xsb_tile.cuh"
+#include <algorithm>
+#include <cmath>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 
@@ -44,7 +46,8 @@ __device__ __forceinline__ double nbh_d2(const GridView& g, double dx, double dy
 template<bool XFORM, bool FILL>
 __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_of,
                                                          const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-                                                         unsigned* __restrict__ counts, const unsigned long long* __restrict__ off, unsigned* __restrict__ idx)
+                                                         unsigned* __restrict__ counts, const unsigned long long* __restrict__ off, unsigned* __restrict__ idx,
+                                                         unsigned long long* __restrict__ d2min_bits)
 {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
   const double xa = rx[a], ya = ry[a], za = rz[a];
   const int ilo = max(0, ia - P.Rx), ihi = min(nx - 1, ia + P.Rx);
   unsigned cnt = 0;
+  double dmin = 1.0e300;
   unsigned long long w = FILL ? off[a] : 0ull;
   for(int rk = -P.Rz; rk <= P.Rz; rk++)
   {
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
         {
           const double d2 = nbh_d2<XFORM>(P.g, rx[b] - xa, ry[b] - ya, rz[b] - za);
           keep = d2 > 0.0 && d2 < P.d2max;
+          if( !FILL && keep ) dmin = fmin(dmin, d2);
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if( FILL )
@@ -83,7 +88,40 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
       }
     }
   }
-  if( !FILL && lane == 0 ) counts[a] = cnt;
+  if( !FILL )
+  {
+    if( lane == 0 ) counts[a] = cnt;
+    // smallest pair distance of the list (positive doubles order like their bit patterns): sizes the shared-memory
+    // window of the EAM spline tables (xsb_eam.cu)
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if( lane == 0 && dmin < 1.0e300 && (unsigned long long)__double_as_longlong(dmin) < *d2min_bits ) atomicMin(d2min_bits, (unsigned long long)__double_as_longlong(dmin));
+  }
+}
+
+// CSR (flat u32 neighbour index) -> tile list (u16 index into the stage of the central atom's tile), warp per atom
+__global__ void __launch_bounds__(256) tile_convert_kernel(TileGeom G, unsigned n, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_of,
+                                                           const unsigned long long* __restrict__ off, const unsigned* __restrict__ idx32,
+                                                           unsigned short* __restrict__ idx16)
+{
+  __shared__ TileMeta Ms[8];
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned a = blockIdx.x * 8u + w;
+  if( a >= n ) return;
+  TileMeta& M = Ms[w];
+  const unsigned c = cell_of[a];
+  const int i = int(c % unsigned(G.nx)), j = int((c / unsigned(G.nx)) % unsigned(G.ny)), k = int(c / (unsigned(G.nx) * unsigned(G.ny)));
+  tile_meta_compute(G, cell_start, i / G.TX, j, k, M);
+  __syncwarp();
+  const unsigned nrows = unsigned((2 * G.Ry + 1) * (2 * G.Rz + 1));
+  const unsigned long long e1 = off[a + 1];
+  for(unsigned long long e = off[a] + lane; e < e1; e += 32u)
+  {
+    const unsigned b = idx32[e];
+    unsigned r = 0;
+    while( r + 1 < nrows && !( b >= M.g0[r] && b - M.g0[r] < M.s0[r + 1] - M.s0[r] ) ) ++r;
+    idx16[e] = (unsigned short)(M.s0[r] + (b - M.g0[r]));
+  }
 }
 
 // ---- export to the reference uint16 stream ---------------------------------------------------------
@@ -171,6 +209,49 @@ static int exclusive_scan_u64(xsb_ctx* ctx, const unsigned long long* in, unsign
   return XSB_OK;
 }
 
+// Tile geometry for this grid + search range: TX cells per tile along x, largest stage over all tiles (host copy of
+// the cell offsets).  Returns false when the tile path cannot serve the list (search range > 2 cells in y/z, or a
+// stage larger than a uint16 index / the shared-memory budget): the generic CSR kernels are used then.
+static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap)
+{
+  const xsb_grid_desc& g = ctx->grid;
+  G = TileGeom{};
+  G.nx = g.dims[0]; G.ny = g.dims[1]; G.nz = g.dims[2]; G.gl = g.ghost_layers;
+  G.Rx = R[0]; G.Ry = R[1]; G.Rz = R[2]; G.TX = 1; G.ghost = 1;
+  G.tiles_x = (G.nx + G.TX - 1) / G.TX;
+  s_cap = 0;
+  if( (2 * R[1] + 1) * (2 * R[2] + 1) > TILE_MAX_ROWS ) return false;
+  const std::vector<uint64_t>& off = ctx->h_cell_off;
+  // per x-row prefix: atoms in cells [i-Rx, i+TX+Rx) of row (j,k); stage = sum over the rows around (j,k)
+  std::vector<unsigned> rowwin(size_t(G.tiles_x) * G.ny * G.nz);
+  for(int k = 0; k < G.nz; k++) for(int j = 0; j < G.ny; j++)
+  {
+    const size_t row = size_t(G.nx) * (size_t(j) + size_t(G.ny) * k);
+    for(int ti = 0; ti < G.tiles_x; ti++)
+    {
+      const int i0 = ti * G.TX, i1 = std::min(G.nx, i0 + G.TX);
+      rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(j) + size_t(G.ny) * k)] = unsigned(off[row + std::min(G.nx, i1 + G.Rx)] - off[row + std::max(0, i0 - G.Rx)]);
+    }
+  }
+  for(int k = 0; k < G.nz; k++) for(int j = 0; j < G.ny; j++) for(int ti = 0; ti < G.tiles_x; ti++)
+  {
+    unsigned S = 0;
+    for(int dk = -G.Rz; dk <= G.Rz; dk++) for(int dj = -G.Ry; dj <= G.Ry; dj++)
+    {
+      const int jj = j + dj, kk = k + dk;
+      if( jj < 0 || jj >= G.ny || kk < 0 || kk >= G.nz ) continue;
+      S += rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(jj) + size_t(G.ny) * kk)];
+    }
+    s_cap = std::max(s_cap, S);
+  }
+  s_cap = (s_cap + 7u) & ~7u;
+  if( s_cap == 0 ) s_cap = 8;
+  // 2 stage buffers of x,y,z,w + types must leave room for the operator tables: cap a buffer at 64 KiB
+  if( s_cap > 65535u || size_t(s_cap) * 33 > 64 * 1024 ) return false;
+  G.s_cap = s_cap;
+  return true;
+}
+
 } // namespace xsb
 
 using namespace xsb;
@@ -197,13 +278,17 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, 1.02));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->nbh_off.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if( n == 0 ) { ctx->nbh_built = true; return XSB_OK; }
+  XSB_CUDA(ctx, ctx->tmp64.reserve(16));
+  unsigned long long* d2min = ctx->tmp64.p;
+  XSB_CUDA(ctx, cudaMemsetAsync(d2min, 0xff, sizeof(unsigned long long), ctx->stream));
+  ctx->tile_ok = false;
   ctx->prof_begin(XSB_PROF_NBR_BUILD);
   NbrParams P; P.g = ctx->view(); P.n = n; P.d2max = nbh_dist_lab * nbh_dist_lab;
   int R[3]; search_range(ctx->grid, nbh_dist_lab, R); P.Rx = R[0]; P.Ry = R[1]; P.Rz = R[2];
   const int block = 256; const unsigned grid = unsigned((uint64_t(n) * 32 + block - 1) / block);
   const double *rx = ctx->f64[XSB_F_RX].p, *ry = ctx->f64[XSB_F_RY].p, *rz = ctx->f64[XSB_F_RZ].p;
-  if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr);
-  else                     nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr);
+  if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
+  else                     nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
   XSB_LAUNCH_CHECK(ctx);
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->scratch64.p + n, 0, sizeof(unsigned long long), ctx->stream));
   widen_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->nbh_count.p, ctx->scratch64.p);
@@ -222,10 +307,27 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->nbh_total = total;
   XSB_CUDA(ctx, ctx->nbh_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-  if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
-  else                     nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p);
-  ctx->prof_end(XSB_PROF_NBR_BUILD);
+  if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
+  else                     nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
   XSB_LAUNCH_CHECK(ctx);
+  // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh)
+  {
+    unsigned long long bits = 0;
+    XSB_CUDA(ctx, cudaMemcpyAsync(&bits, d2min, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    TileGeom G; unsigned s_cap = 0;
+    const bool ok = tile_plan(ctx, R, G, s_cap);
+    if( ok )
+    {
+      XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+      tile_convert_kernel<<<(n + 7) / 8, 256, 0, ctx->stream>>>(G, n, ctx->cell_start.p, ctx->cell_of.p, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p);
+      XSB_LAUNCH_CHECK(ctx);
+    }
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double d2 = 0.0; if( bits != ~0ull ) std::memcpy(&d2, &bits, sizeof(d2));
+    ctx->nbh_d2min = d2;
+    ctx->tile_ok = ok; ctx->tile_TX = G.TX; ctx->tile_R[0] = R[0]; ctx->tile_R[1] = R[1]; ctx->tile_R[2] = R[2]; ctx->tile_s_cap = s_cap;
+  }
+  ctx->prof_end(XSB_PROF_NBR_BUILD);
   ctx->nbh_built = true;
   return XSB_OK;
 }

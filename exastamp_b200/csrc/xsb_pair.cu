@@ -2,7 +2,7 @@
 // Reference functors: src/potential/pair_potential_template/pair_potential_force_op_singlemat.h:45-218 with body
 // force_op_impl2.hxx:22-78 (single species) and pair_potential_force_op_multiparam.h:76-223 (per type pair).
 // Potential math: src/potential/pair_potentials/lennard_jones/include/.../lennard_jones.h:40-50.
-#include "xsb_traverse.cuh"
+#include "xsb_tilepass.cuh"
 
 namespace xsb
 {
@@ -88,6 +88,44 @@ __global__ void __launch_bounds__(256) pair_force_kernel(ParticleView P, XForm X
   }
 }
 
+// the same functor for the persistent tile kernel (xsb_tilepass.cuh)
+template<bool MULTI, bool VIRIAL, class real>
+struct LJTileOp
+{
+  static constexpr bool HAS_W = false, TYPES = MULTI;
+  double rcut2;
+  LJMulti prm;
+  double *fx, *fy, *fz, *ep, *vir;
+  __host__ __device__ size_t table_bytes() const { return 0; }
+  __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
+  struct Acc { double fx, fy, fz, ep; unsigned ta; Vir9 v; };
+  __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = 0.0; A.ta = 0; if( VIRIAL ) A.v.zero(); }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const { if( MULTI ) A.ta = B.t[sa]; }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const
+  {
+    const LJPair& pp = MULTI ? prm.pp[unique_pair_id(A.ta, B.t[j])] : prm.pp[0];
+    if( !MULTI || d2 <= pp.rcut2 )
+    {
+      real e_, de_r;
+      lj_eval<real>(pp, real(d2), e_, de_r);
+      const double fex = double(de_r) * dx, fey = double(de_r) * dy, fez = double(de_r) * dz;
+      A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * double(e_);
+      if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
+    }
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz); A.ep = group_sum<TPA>(A.ep);
+    if( VIRIAL ) A.v.template reduce<TPA>();
+    if( valid && sub == 0 )
+    {
+      fx[a] += A.fx; fy[a] += A.fy; fz[a] += A.fz;
+      if( ep ) ep[a] += A.ep;
+      if( VIRIAL ) A.v.store_add(vir, a);
+    }
+  }
+};
+
 static LJPair make_lj(double eps, double sigma, double rcut)
 {
   LJPair p; p.eps4 = 4.0 * eps; p.eps24 = 24.0 * eps; p.sigma2 = sigma * sigma; p.rcut2 = rcut * rcut; p.ecut = 0.0;
@@ -110,6 +148,19 @@ static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int fl
   ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p,
                   ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own) };
   if( P.n_atoms == 0 ) return XSB_OK;
+  if( ctx->tile_ok )
+  {
+    double *tfx = ctx->f64[XSB_F_FX].p, *tfy = ctx->f64[XSB_F_FY].p, *tfz = ctx->f64[XSB_F_FZ].p;
+    double *tep = (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr, *tvir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+    int rc;
+    ctx->prof_begin(XSB_PROF_PAIR);
+#   define XSB_LJ_TILE(VIR, REAL, TPA_, NT_) { LJTileOp<MULTI, VIR, REAL> op{ rcut_max * rcut_max, prm, tfx, tfy, tfz, tep, tvir }; rc = launch_tile_pass<TPA_, NT_>(ctx, ghost, op, nullptr); }
+    if( mixed ) { if( virial ) XSB_LJ_TILE(true, float, 8, 512) else XSB_LJ_TILE(false, float, 16, 1024) }
+    else        { if( virial ) XSB_LJ_TILE(true, double, 8, 512) else XSB_LJ_TILE(false, double, 16, 1024) }
+#   undef XSB_LJ_TILE
+    ctx->prof_end(XSB_PROF_PAIR);
+    return rc;
+  }
   const XForm X = make_xform(ctx->grid);
   constexpr int TPA = 8; const int block = 256;
   const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
