@@ -275,6 +275,7 @@ int xsb_push_f_v_r(xsb_ctx* ctx, double dt)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
   const unsigned n = unsigned(ctx->n_own); if( !n ) return XSB_OK;
+  ctx->pos_epoch++;
   XFormInv Xi; Xi.identity = ctx->grid.xform_is_identity; invert3(ctx->grid.xform, Xi.m);
   push_f_v_r_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->own_atoms.p, dt, 0.5 * dt * dt, Xi,
       ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->f64[XSB_F_VX].p, ctx->f64[XSB_F_VY].p, ctx->f64[XSB_F_VZ].p,

@@ -68,7 +68,7 @@ int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
     const bool ghost = gv.is_ghost_cell(unsigned(c));
     for(uint64_t p = off[c]; p < off[c+1]; p++) { cellof[p] = unsigned(c); if( !ghost ) own.push_back(unsigned(p)); }
   }
-  ctx->n = n; ctx->n_own = own.size();
+  ctx->n = n; ctx->n_own = own.size(); ctx->pos_epoch++;
   XSB_CUDA(ctx, ctx->cell_start.reserve(nc + 1));
   XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, 1.02));
   XSB_CUDA(ctx, ctx->own_atoms.reserve(own.size() + 1, 1.02));
@@ -182,7 +182,7 @@ void xsb_destroy(xsb_ctx* ctx)
   for(auto& b : ctx->f64) b.release();
   ctx->type.release(); ctx->id.release();
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->scratch.release(); ctx->scratch64.release();
-  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release();
   xsb_ghost_release(ctx);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);
@@ -256,7 +256,7 @@ int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
   XSB_REQUIRE(ctx, g->cell_size > 0.0, XSB_ERR_INVALID, "cell_size must be > 0");
   const uint64_t nc = uint64_t(g->dims[0]) * uint64_t(g->dims[1]) * uint64_t(g->dims[2]);
   XSB_REQUIRE(ctx, nc < (1ull << 31), XSB_ERR_OVERFLOW, "too many cells");
-  ctx->grid = *g;
+  ctx->grid = *g; ctx->pos_epoch++;
   ctx->ncells = nc;
   ctx->grid_set = true;
   ctx->nbh_built = false;
@@ -321,6 +321,7 @@ int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
   void* p = nullptr; size_t bytes = 0;
   int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
   if( bytes ) XSB_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_epoch++;
   return XSB_OK;
 }
 
@@ -340,6 +341,7 @@ void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
   if( !ctx || !ctx->stream ) return nullptr;
   void* p = nullptr; size_t bytes = 0;
   if( field_ptr(ctx, field, &p, &bytes) ) return nullptr;
+  if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_external = true;   // caller may move particles behind our back
   return p;
 }
 

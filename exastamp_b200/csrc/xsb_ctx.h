@@ -110,6 +110,15 @@ struct xsb_ctx
   unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
   double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time
   xsb::DevBuf<unsigned short> tl_idx;         // [total]
+  // in-range sub-list written by the first pair pass of a step (EAM rho/emb) for the second (force): valid only while
+  // positions, grid and cutoff are unchanged -- pos_epoch counts every API call that can move a particle
+  xsb::DevBuf<unsigned short> sub_idx;        // [total]
+  xsb::DevBuf<unsigned> sub_cnt;              // [n]
+  uint64_t pos_epoch = 1, sub_epoch = 0;
+  double sub_rcut = 0.0; bool sub_ghost = false;
+  bool pos_external = false;                  // a position device pointer was handed out: epochs cannot be trusted
+  bool sub_valid(double rcut, bool need_ghost) const
+  { return !pos_external && sub_epoch == pos_epoch && sub_rcut == rcut && (sub_ghost || !need_ghost); }
   xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.
   xsb::DevBuf<unsigned long long> scratch64;  // misc u64 scratch
 

@@ -169,18 +169,19 @@ __global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XFor
 // ---- the same two passes as functors for the persistent tile kernel (xsb_tilepass.cuh) ----------------------------
 struct JohnsonEmbTileOp
 {
-  static constexpr bool HAS_W = false, TYPES = false;
+  static constexpr bool HAS_W = false, TYPES = false, D2_ONLY = true;
   double rcut2; JohnsonP p; double *ep, *rho_dEmb;
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
   struct Acc { double rho; unsigned cnt; };
   __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; A.cnt = 0; }
   __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<false, false>&, const unsigned char*) const {}
-  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
+  __device__ __forceinline__ void pair_d2(Acc& A, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
   {
     double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
     A.rho += rho; ++A.cnt;
   }
+  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<false, false>& B, const unsigned char* t) const { pair_d2(A, d2, j, B, t); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
     A.rho = group_sum<TPA>(A.rho);
@@ -193,7 +194,7 @@ struct JohnsonEmbTileOp
 template<bool VIRIAL>
 struct JohnsonForceTileOp
 {
-  static constexpr bool HAS_W = true, TYPES = false;
+  static constexpr bool HAS_W = true, TYPES = false, D2_ONLY = false;
   double rcut2; JohnsonP p; double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
@@ -395,14 +396,15 @@ __device__ __forceinline__ void hermite_c(const double2 k0, const double2 k1, do
 template<bool MULTI>
 struct EamRhoTileOp
 {
-  static constexpr bool HAS_W = false, TYPES = MULTI;
+  static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = true;
   double rcut2; EamFcView T; double* rho_dEmb;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
   __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
   struct Acc { double rho; };
   __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; }
   __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<HAS_W, TYPES>&, const unsigned char*) const {}
-  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const { pair_d2(A, d2, j, B, tab); }
+  __device__ __forceinline__ void pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
   {
     const double r = d2 * rsqrt(d2);
     int m; double p; T.lookup(r, m, p);
@@ -420,7 +422,7 @@ struct EamRhoTileOp
 template<bool MULTI, bool EFLAG, bool VIRIAL>
 struct EamForceTileOp
 {
-  static constexpr bool HAS_W = true, TYPES = MULTI;
+  static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false;
   double rcut2; EamFcView T; int nel; double conv_z2r;
   double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
@@ -463,11 +465,11 @@ struct EamForceTileOp
 // shared-memory window of the {f,c5} tables for a tile pass: rows [m_lo, nr] of the first ntab tables, as large a
 // window as the 227 KiB budget allows next to the 2 stage buffers (pairs below the window read the global copy)
 template<bool HAS_W, bool TYPES>
-static EamFcView make_fc_view(const xsb_ctx* ctx, int ntab)
+static EamFcView make_fc_view(const xsb_ctx* ctx, int ntab, size_t queue_bytes)
 {
   const EamAlloyDev& E = ctx->eam;
   EamFcView T{ reinterpret_cast<const double2*>(E.fc.p), E.nr, INT_MAX, 0, ntab, E.rdr };
-  const size_t fixed = tile_smem_bytes<HAS_W, TYPES>(ctx->tile_s_cap, 0) + 64;
+  const size_t fixed = tile_smem_bytes<HAS_W, TYPES>(ctx->tile_s_cap, 0, queue_bytes, 2) + 256;
   if( fixed >= TILE_SMEM_MAX ) return T;
   const size_t max_rows = (TILE_SMEM_MAX - fixed) / (sizeof(double2) * size_t(ntab));
   // rows a pair can reach: m >= floor(r_min * rdr + 1); keep a 10 % margin in r for the drift until the next rebuild
@@ -527,17 +529,19 @@ int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int
       XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
       JohnsonEmbTileOp op{ rc2, p, ctx->f64[XSB_F_EP].p, emb };
       ctx->prof_begin(XSB_PROF_EAM_RHO);
-      int rc = launch_tile_pass<16, 1024>(ctx, (phases & 2) != 0, op, nullptr);
+      int rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB);
       ctx->prof_end(XSB_PROF_EAM_RHO);
       if( rc ) return rc;
+      ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = (phases & 2) != 0;
     }
     if( (phases & 4) && ctx->n_own )
     {
       double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
       int rc;
+      const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
       ctx->prof_begin(XSB_PROF_EAM_FORCE);
-      if( virial ) { JohnsonForceTileOp<true> op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb); }
-      else         { JohnsonForceTileOp<false> op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb); }
+      if( virial ) { JohnsonForceTileOp<true> op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); }
+      else         { JohnsonForceTileOp<false> op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); }
       ctx->prof_end(XSB_PROF_EAM_FORCE);
       if( rc ) return rc;
     }
@@ -676,10 +680,13 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
     int rc;
     ctx->prof_begin(XSB_PROF_EAM_RHO);
-    if( multi ) { EamRhoTileOp<true>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements), emb }; rc = launch_tile_pass<16, 1024>(ctx, ghost, op, nullptr); }
-    else        { EamRhoTileOp<false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements), emb }; rc = launch_tile_pass<16, 1024>(ctx, ghost, op, nullptr); }
+    // one warp per atom + compaction queue; the in-range sub-list it leaves behind serves the force pass of this step
+    const size_t qb = tile_queue_bytes<1024>();
+    if( multi ) { EamRhoTileOp<true>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+    else        { EamRhoTileOp<false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
     ctx->prof_end(XSB_PROF_EAM_RHO);
     if( rc ) return rc;
+    ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = ghost;
   }
   if( !tile && (phases & XSB_EAM_RHO) && ctx->n )
   {
@@ -709,8 +716,9 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     const int ntab = E.nelements + E.nelements * (E.nelements + 1) / 2;
     int rc;
     ctx->prof_begin(XSB_PROF_EAM_FORCE);
-#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { EamForceTileOp<MU, EF, VIR> op{ rc2, make_fc_view<true, MU>(ctx, ntab), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; \
-                                                  rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb); }
+    const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
+#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { EamForceTileOp<MU, EF, VIR> op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; \
+                                                  rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); }
     if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
     else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
 #   undef XSB_EAM_TILE

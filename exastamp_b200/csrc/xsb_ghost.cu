@@ -210,6 +210,7 @@ static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
   GhostState* G = ctx->ghost;
   XSB_REQUIRE(ctx, G != nullptr, XSB_ERR_STATE, "xsb_ghost_comm_scheme must be called first");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if( mask & ((1u << XSB_F_RX) | (1u << XSB_F_RY) | (1u << XSB_F_RZ)) ) ctx->pos_epoch++;
   FieldPtrs F; int rc = make_fields(ctx, mask, reverse, F); if( rc ) return rc;
   ShiftTab S; std::memcpy(S.s, G->shift, sizeof(S.s));
   const int me = ctx->rank, P = G->nranks;

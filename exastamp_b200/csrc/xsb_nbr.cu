@@ -230,7 +230,8 @@ static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap
     for(int ti = 0; ti < G.tiles_x; ti++)
     {
       const int i0 = ti * G.TX, i1 = std::min(G.nx, i0 + G.TX);
-      rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(j) + size_t(G.ny) * k)] = unsigned(off[row + std::min(G.nx, i1 + G.Rx)] - off[row + std::max(0, i0 - G.Rx)]);
+      const uint64_t gb = off[row + std::max(0, i0 - G.Rx)], ge = off[row + std::min(G.nx, i1 + G.Rx)];
+      rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(j) + size_t(G.ny) * k)] = ge > gb ? unsigned(((ge + 1) & ~uint64_t(1)) - (gb & ~uint64_t(1))) : 0u;   // 16-byte widened, as tile_meta_compute
     }
   }
   for(int k = 0; k < G.nz; k++) for(int j = 0; j < G.ny; j++) for(int ti = 0; ti < G.tiles_x; ti++)

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) pair_force_kernel(ParticleView P, XForm X
 template<bool MULTI, bool VIRIAL, class real>
 struct LJTileOp
 {
-  static constexpr bool HAS_W = false, TYPES = MULTI;
+  static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = false;
   double rcut2;
   LJMulti prm;
   double *fx, *fy, *fz, *ep, *vir;

@@ -3,9 +3,13 @@
 //
 //   tile      = TX consecutive cells of one x-row (j,k); its central atoms are one contiguous flat range.
 //   stage     = the (TX+2Rx) x (2Ry+1) x (2Rz+1) block of cells around the tile.  Cells of one x-row are
-//               contiguous in the flat SoA, so the stage is (2Ry+1)(2Rz+1) contiguous runs ("rows") of atoms;
-//               they are copied global -> shared with cp.async (LDGSTS, 8-byte granules: no alignment
-//               constraint on the runs), double buffered: tile n+1 lands while tile n is computed.
+//               contiguous in the flat SoA, so the stage is (2Ry+1)(2Rz+1) contiguous runs ("rows") of atoms.
+//               A dedicated producer warp copies them global -> shared with 1-D TMA bulk copies
+//               (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) into a ring of stage buffers; rows are widened
+//               to 16-byte boundaries (the pad slots hold real neighbouring atoms and are never indexed).
+//               Consumer warps never meet at a CTA barrier: full/empty mbarriers per buffer, and a per-buffer
+//               atom cursor from which warps grab central atoms, so a warp that runs out of work in tile n
+//               starts on tile n+1 while slower warps finish.
 //   list      = per central atom, uint16 indices INTO THE STAGE (ascending = the canonical (cell_b,p_b) order of
 //               the reference stream), built once per chunk_neighbors call (xsb_nbr.cu).  2 B/entry of HBM
 //               traffic instead of a 4-byte global index plus 3-4 scattered 8-byte gathers through L1/L2.
@@ -30,6 +34,7 @@ struct TileGeom
   int ti_lo, ti_n, j_lo, j_n, k_lo, k_n;
   unsigned ntiles;             // ti_n * j_n * k_n
   unsigned s_cap;              // stage capacity (atoms) of one buffer
+  int nbuf;                    // stage buffers in the ring (2 or 3)
   int ghost;                   // central atoms of ghost cells are processed too
 };
 
@@ -39,8 +44,8 @@ struct TileMeta                // lives in shared memory, one per stage buffer
   unsigned c_off;              // stage index of central atom a = a + c_off (unsigned wrap-around arithmetic)
   unsigned S;                  // atoms in the stage
   unsigned nrows;
-  unsigned g0[TILE_MAX_ROWS];      // flat index of the first atom of each row
-  unsigned s0[TILE_MAX_ROWS + 1];  // stage index of the first atom of each row; s0[nrows] = S
+  unsigned g0[TILE_MAX_ROWS];      // flat index of the first staged atom of each row (even: 16-byte aligned doubles)
+  unsigned s0[TILE_MAX_ROWS + 1];  // stage index of the first atom of each row (even); s0[nrows] = S
 };
 
 // executed by ONE FULL WARP (all 32 lanes converged).  (ti,j,k) = tile coordinates in the fixed tiling of the grid.
@@ -56,8 +61,8 @@ __device__ __forceinline__ void tile_meta_compute(const TileGeom& G, const unsig
     if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz )
     {
       const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
-      g = cell_start[row + max(0, i0 - G.Rx)];
-      len = cell_start[row + min(G.nx, i1 + G.Rx)] - g;
+      const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
+      if( ge > gb ) { g = gb & ~1u; len = ((ge + 1u) & ~1u) - g; }   // widen to even bounds: TMA bulk copies need 16-byte alignment
     }
   }
   unsigned s = len;
@@ -93,13 +98,26 @@ __device__ __forceinline__ void tile_coords(const TileGeom& G, unsigned t, int& 
   k = G.k_lo + int(u / unsigned(G.j_n));
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+// ---- mbarrier + TMA bulk copy (PTX; SASS: SYNCS.*, UBLKCP) --------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }\n" :: "r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{ asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
-  const unsigned d = unsigned(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(d), "l"(gsrc) : "memory");
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+// global -> shared, bytes a multiple of 16, both addresses 16-byte aligned; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // stage buffer: SoA doubles x,y,z,(w) of s_cap atoms each, then s_cap type bytes (when TYPES)
 template<bool HAS_W, bool TYPES>
@@ -122,62 +140,61 @@ struct StageBuf
 
 struct TileFields { const double* __restrict__ rx; const double* __restrict__ ry; const double* __restrict__ rz; const double* __restrict__ w; const unsigned char* __restrict__ type; };
 
-// all threads of the CTA: enqueue the asynchronous copies of one stage (no wait)
-template<bool HAS_W, bool TYPES, int NT>
-__device__ __forceinline__ void stage_issue(const TileMeta& M, const TileFields& F, StageBuf<HAS_W, TYPES>& B)
+// ring of stage buffers in shared memory
+constexpr int TILE_MAX_BUFS = 3;
+struct TileRing
 {
-  const unsigned S = M.S;
-  for(unsigned s = threadIdx.x; s < S; s += NT)
-  {
-    unsigned r = 0;
-    while( s >= M.s0[r + 1] ) ++r;
-    const unsigned g = M.g0[r] + (s - M.s0[r]);
-    cp_async8(B.x + s, F.rx + g); cp_async8(B.y + s, F.ry + g); cp_async8(B.z + s, F.rz + g);
-    if( HAS_W ) cp_async8(B.w + s, F.w + g);
-    if( TYPES ) B.t[s] = F.type[g];     // 1-byte granule: plain load/store (visible after the next barrier)
-  }
-}
+  unsigned long long full[TILE_MAX_BUFS];    // mbarrier: the stage of buffer b has landed (producer arrive + TMA bytes)
+  unsigned long long empty[TILE_MAX_BUFS];   // mbarrier: every consumer warp is done with buffer b
+  unsigned cursor[TILE_MAX_BUFS];            // next central atom (offset from a_begin) to hand out
+  unsigned pad_;
+  TileMeta meta[TILE_MAX_BUFS];
+};
 
-// The persistent tile loop.  `body(M, B)` is called by every thread of the CTA once per non-empty tile with the
-// stage resident in shared memory; it must not return early (barriers follow).
-template<bool HAS_W, bool TYPES, int NT, class Body>
-__device__ __forceinline__ void tile_loop(const TileGeom& G, const unsigned* __restrict__ cell_start, const TileFields& F,
-                                          unsigned char* stage_mem /* 2 buffers */, TileMeta* meta /* [3] in smem */, Body body)
-{
-  const size_t bb = (StageBuf<HAS_W, TYPES>::bytes(G.s_cap) + 15) & ~size_t(15);
-  auto stage = [&](int b) { StageBuf<HAS_W, TYPES> B; B.bind(stage_mem + size_t(b) * bb, G.s_cap); return B; };
-  // meta slots rotate mod 3: the slot written at the top of iteration n was last read by the body of iteration
-  // n-2, which every thread has left before passing the barriers of iteration n-1 (stage buffers rotate mod 2).
-  const bool w0 = threadIdx.x < 32;
-  unsigned t = blockIdx.x;
-  if( t >= G.ntiles ) return;
-  if( w0 ) { int ti, j, k; tile_coords(G, t, ti, j, k); tile_meta_compute(G, cell_start, ti, j, k, meta[0]); }
-  __syncthreads();
-  { StageBuf<HAS_W, TYPES> B = stage(0); stage_issue<HAS_W, TYPES, NT>(meta[0], F, B); }
-  cp_async_commit();
-  int cur = 0, mcur = 0;
-  for(; t < G.ntiles; t += gridDim.x)
-  {
-    const unsigned tn = t + gridDim.x;
-    const int nxt = cur ^ 1, mnxt = mcur == 2 ? 0 : mcur + 1;
-    if( tn < G.ntiles && w0 ) { int ti, j, k; tile_coords(G, tn, ti, j, k); tile_meta_compute(G, cell_start, ti, j, k, meta[mnxt]); }
-    __syncthreads();                       // meta[mnxt] visible; every thread is done computing on buf[nxt]
-    if( tn < G.ntiles ) { StageBuf<HAS_W, TYPES> B = stage(nxt); stage_issue<HAS_W, TYPES, NT>(meta[mnxt], F, B); }
-    cp_async_commit();
-    cp_async_wait<1>();                    // this thread's copies of the CURRENT tile have landed
-    __syncthreads();                       // ... and everybody else's
-    if( meta[mcur].a_begin < meta[mcur].a_end ) { StageBuf<HAS_W, TYPES> B = stage(cur); body(meta[mcur], B); }
-    cur = nxt; mcur = mnxt;
-  }
-  cp_async_wait<0>();
-}
-
-// shared-memory carve-up used by the host to size launches: [user tables][meta x3][stage x2]
+// Producer side, executed by one full warp: publish tile n = (ti,j,k) into buffer b.
 template<bool HAS_W, bool TYPES>
-inline size_t tile_smem_bytes(unsigned s_cap, size_t table_bytes)
+__device__ __forceinline__ void tile_produce(const TileGeom& G, const unsigned* __restrict__ cell_start, const TileFields& F, TileRing& R, int b,
+                                             StageBuf<HAS_W, TYPES>& B, int ti, int j, int k)
 {
-  const size_t bb = (StageBuf<HAS_W, TYPES>::bytes(s_cap) + 15) & ~size_t(15);
-  return ((table_bytes + 15) & ~size_t(15)) + ((3 * sizeof(TileMeta) + 15) & ~size_t(15)) + 2 * bb;
+  const int lane = threadIdx.x & 31;
+  TileMeta& M = R.meta[b];
+  tile_meta_compute(G, cell_start, ti, j, k, M);
+  __syncwarp();
+  const unsigned S = M.S, nrows = M.nrows;
+  if( TYPES )
+  {
+    for(unsigned s = lane; s < S; s += 32)
+    {
+      unsigned r = 0;
+      while( s >= M.s0[r + 1] ) ++r;
+      B.t[s] = F.type[M.g0[r] + (s - M.s0[r])];
+    }
+  }
+  if( lane == 0 )
+  {
+    R.cursor[b] = 0;
+    mbar_arrive_expect_tx(&R.full[b], S * 8u * (HAS_W ? 4u : 3u));    // releases meta, cursor (and the type bytes after the syncwarp)
+  }
+  __syncwarp();
+  if( S && unsigned(lane) < nrows )
+  {
+    const unsigned s0 = M.s0[lane], cnt = M.s0[lane + 1] - s0, g = M.g0[lane];
+    if( cnt )
+    {
+      bulk_g2s(B.x + s0, F.rx + g, cnt * 8u, &R.full[b]);
+      bulk_g2s(B.y + s0, F.ry + g, cnt * 8u, &R.full[b]);
+      bulk_g2s(B.z + s0, F.rz + g, cnt * 8u, &R.full[b]);
+      if( HAS_W ) bulk_g2s(B.w + s0, F.w + g, cnt * 8u, &R.full[b]);
+    }
+  }
+}
+
+// shared-memory carve-up used by the host to size launches: [user tables][ring][queues][stage x nbuf]
+template<bool HAS_W, bool TYPES>
+inline size_t tile_smem_bytes(unsigned s_cap, size_t table_bytes, size_t queue_bytes, int nbuf)
+{
+  const size_t bb = (StageBuf<HAS_W, TYPES>::bytes(s_cap) + 127) & ~size_t(127);
+  return ((table_bytes + 127) & ~size_t(127)) + ((sizeof(TileRing) + 127) & ~size_t(127)) + ((queue_bytes + 127) & ~size_t(127)) + size_t(nbuf) * bb;
 }
 
 // launch-side geometry: the fixed tiling recorded by chunk_neighbors + the window of tiles this launch visits
@@ -204,6 +221,12 @@ struct TileList
 {
   const unsigned long long* __restrict__ off;   // [n+1] entry offsets (shared with the CSR list)
   const unsigned short* __restrict__ idx;       // stage indices
+  // in-range sub-list of the current positions: the entries with d2 <= rcut2, compacted in place (same offsets),
+  // written by the first pair pass of a step (EAM rho / emb) and consumed by the second (EAM force)
+  unsigned short* __restrict__ sub_idx;
+  unsigned* __restrict__ sub_cnt;               // [n]
 };
+
+enum { LIST_FULL = 0, LIST_FULL_WRITE_SUB = 1, LIST_SUB = 2 };
 
 } // namespace xsb

@@ -17,25 +17,68 @@ namespace xsb
 
 constexpr size_t TILE_SMEM_MAX = 227 * 1024;
 
-template<int TPA, int NT, bool XFORM, class Op>
+// per-warp compaction queue of the d2-only passes: 64 slots of {d2, stage index}
+constexpr int TILE_QUEUE_SLOTS = 64;
+template<int NT> constexpr size_t tile_queue_bytes() { return size_t(NT / 32) * TILE_QUEUE_SLOTS * (sizeof(double) + sizeof(unsigned short)); }
+
+template<int TPA, int NT, bool XFORM, int LMODE, class Op>
 __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, const unsigned* __restrict__ cell_start, const TileFields F, const TileList L,
                                                           const XForm X, const Op op)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const size_t tb = (op.table_bytes() + 15) & ~size_t(15);
-  op.load_tables(smem, NT);
-  TileMeta* meta = reinterpret_cast<TileMeta*>(smem + tb);
-  unsigned char* stage_mem = smem + tb + ((3 * sizeof(TileMeta) + 15) & ~size_t(15));
-  // (the first barrier inside tile_loop also publishes the tables)
-  constexpr unsigned NG = NT / TPA;
-  const unsigned g = threadIdx.x / TPA, sub = threadIdx.x % TPA;
-  tile_loop<Op::HAS_W, Op::TYPES, NT>(G, cell_start, F, stage_mem, meta, [&](const TileMeta& M, const StageBuf<Op::HAS_W, Op::TYPES>& B)
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr bool QUEUE = Op::D2_ONLY && TPA == 32 && LMODE != LIST_SUB;
+  constexpr unsigned NWC = NT / 32 - 1;          // consumer warps; the last warp is the TMA producer
+  constexpr unsigned GPW = 32 / TPA;             // central atoms per warp and grab
+  typedef StageBuf<Op::HAS_W, Op::TYPES> Stage;
+  const size_t tb = (op.table_bytes() + 127) & ~size_t(127);
+  TileRing& R = *reinterpret_cast<TileRing*>(smem + tb);
+  unsigned char* qmem = smem + tb + ((sizeof(TileRing) + 127) & ~size_t(127));
+  unsigned char* stage_mem = qmem + (QUEUE ? ((tile_queue_bytes<NT>() + 127) & ~size_t(127)) : 0);
+  const size_t bb = (Stage::bytes(G.s_cap) + 127) & ~size_t(127);
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const int nbuf = G.nbuf;
+  if( threadIdx.x == 0 )
   {
-    const unsigned a_begin = M.a_begin, a_end = M.a_end, c_off = M.c_off;
-    for(unsigned base = a_begin; base < a_end; base += NG)
+    for(int b = 0; b < nbuf; b++) { mbar_init(&R.full[b], 1); mbar_init(&R.empty[b], NWC); }
+    mbar_fence_init();
+  }
+  op.load_tables(smem, NT);
+  __syncthreads();                                // the only CTA-wide barrier of the kernel
+
+  if( warp == NWC )
+  {
+    // ---- producer warp: meta + TMA bulk copies of tile n into buffer n % nbuf, as soon as that buffer is free
+    unsigned n = 0;
+    for(unsigned t = blockIdx.x; t < G.ntiles; t += gridDim.x, ++n)
     {
-      const unsigned a = base + g;
-      const bool valid = a < a_end;
+      const int b = int(n % unsigned(nbuf));
+      if( n >= unsigned(nbuf) ) mbar_wait(&R.empty[b], ((n / unsigned(nbuf)) - 1u) & 1u);
+      Stage B; B.bind(stage_mem + size_t(b) * bb, G.s_cap);
+      int ti, j, k; tile_coords(G, t, ti, j, k);
+      tile_produce<Op::HAS_W, Op::TYPES>(G, cell_start, F, R, b, B, ti, j, k);
+    }
+    return;
+  }
+
+  // ---- consumer warps
+  const unsigned sub = lane % TPA, gsel = lane / TPA;
+  const unsigned gmask = TPA == 32 ? 0xffffffffu : (((1u << TPA) - 1u) << (gsel * TPA));
+  unsigned n = 0;
+  for(unsigned t = blockIdx.x; t < G.ntiles; t += gridDim.x, ++n)
+  {
+    const int b = int(n % unsigned(nbuf));
+    mbar_wait(&R.full[b], (n / unsigned(nbuf)) & 1u);
+    const TileMeta& M = R.meta[b];
+    const unsigned a_begin = M.a_begin, na = M.a_end - M.a_begin, c_off = M.c_off;
+    Stage B; B.bind(stage_mem + size_t(b) * bb, G.s_cap);
+    for(;;)
+    {
+      unsigned k0 = 0;
+      if( lane == 0 ) k0 = atomicAdd(&R.cursor[b], GPW);
+      k0 = __shfl_sync(0xffffffffu, k0, 0);
+      if( k0 >= na ) break;
+      const bool valid = k0 + gsel < na;
+      const unsigned a = a_begin + k0 + gsel;
       typename Op::Acc acc;
       op.init(acc);
       if( valid )
@@ -43,30 +86,120 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         const unsigned sa = a + c_off;
         const double xa = B.x[sa], ya = B.y[sa], za = B.z[sa];
         op.start(acc, a, sa, B, smem);
-        const unsigned long long e1 = L.off[a + 1];
-        for(unsigned long long e = L.off[a] + sub; e < e1; e += TPA)
+        const unsigned long long e0 = L.off[a];
+        if constexpr ( LMODE == LIST_SUB )
         {
-          const unsigned j = __ldcs(L.idx + e);
-          double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
-          apply_xform<XFORM>(X, dx, dy, dz);
-          const double d2 = dx * dx + dy * dy + dz * dz;
-          if( d2 <= op.rcut2 ) op.pair(acc, dx, dy, dz, d2, j, B, smem);
+          // dense: every entry is in range (filtered by the pass that wrote the sub-list on these positions)
+          const unsigned long long e1 = e0 + L.sub_cnt[a];
+          unsigned long long e = e0 + sub;
+          unsigned jn = e < e1 ? __ldcs(L.sub_idx + e) : 0u;
+          while( e < e1 )
+          {
+            const unsigned j = jn;
+            e += TPA;
+            if( e < e1 ) jn = __ldcs(L.sub_idx + e);       // next entry in flight while this pair is evaluated
+            double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
+            apply_xform<XFORM>(X, dx, dy, dz);
+            op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
+          }
+        }
+        else if constexpr ( QUEUE )
+        {
+          // one warp per atom: filter 32 entries per step, ballot-compact the in-range ones into the warp's queue
+          // (and into the global sub-list), evaluate the functor on full warps only
+          double* qd = reinterpret_cast<double*>(qmem) + warp * TILE_QUEUE_SLOTS;
+          unsigned short* qj = reinterpret_cast<unsigned short*>(qmem + size_t(NT / 32) * TILE_QUEUE_SLOTS * sizeof(double)) + warp * TILE_QUEUE_SLOTS;
+          const unsigned long long e1 = L.off[a + 1];
+          unsigned qn = 0, cnt = 0;
+          unsigned jn = e0 + sub < e1 ? __ldcs(L.idx + e0 + sub) : 0u;
+          for(unsigned long long e = e0; e < e1; e += 32)
+          {
+            const unsigned long long ee = e + sub;
+            const unsigned j = jn;
+            if( ee + 32 < e1 ) jn = __ldcs(L.idx + ee + 32);
+            bool in = false; double d2 = 0.0;
+            if( ee < e1 )
+            {
+              double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
+              apply_xform<XFORM>(X, dx, dy, dz);
+              d2 = dx * dx + dy * dy + dz * dz;
+              in = d2 <= op.rcut2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            const unsigned rank = __popc(m & ((1u << sub) - 1u));
+            if( in )
+            {
+              qd[qn + rank] = d2; qj[qn + rank] = (unsigned short)j;
+              if( LMODE == LIST_FULL_WRITE_SUB ) L.sub_idx[e0 + cnt + rank] = (unsigned short)j;
+            }
+            const unsigned k = __popc(m);
+            qn += k; cnt += k;
+            __syncwarp();
+            if( qn >= 32 )
+            {
+              qn -= 32;
+              op.pair_d2(acc, qd[qn + sub], qj[qn + sub], B, smem);
+              __syncwarp();
+            }
+          }
+          if( sub < qn ) op.pair_d2(acc, qd[sub], qj[sub], B, smem);
+          __syncwarp();
+          if( LMODE == LIST_FULL_WRITE_SUB && sub == 0 ) L.sub_cnt[a] = cnt;
+        }
+        else
+        {
+          const unsigned long long e1 = L.off[a + 1];
+          unsigned cnt = 0;
+          unsigned jn = e0 + sub < e1 ? __ldcs(L.idx + e0 + sub) : 0u;
+          for(unsigned long long e = e0; e < e1; e += TPA)
+          {
+            const unsigned long long ee = e + sub;
+            const unsigned j = jn;
+            if( ee + TPA < e1 ) jn = __ldcs(L.idx + ee + TPA);
+            bool in = false;
+            if( ee < e1 )
+            {
+              double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
+              apply_xform<XFORM>(X, dx, dy, dz);
+              const double d2 = dx * dx + dy * dy + dz * dz;
+              in = d2 <= op.rcut2;
+              if( in ) op.pair(acc, dx, dy, dz, d2, j, B, smem);
+            }
+            if( LMODE == LIST_FULL_WRITE_SUB )
+            {
+              const unsigned m = __ballot_sync(gmask, in) & gmask;
+              if( in ) L.sub_idx[e0 + cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+              cnt += __popc(m);
+            }
+          }
+          if( LMODE == LIST_FULL_WRITE_SUB && sub == 0 ) L.sub_cnt[a] = cnt;
         }
       }
       op.template finish<TPA>(acc, a, valid, sub);
     }
-  });
+    __syncwarp();
+    if( lane == 0 ) mbar_arrive(&R.empty[b]);       // this warp will not touch buffer b again until it is refilled
+  }
 }
 
+// lmode: LIST_FULL / LIST_FULL_WRITE_SUB / LIST_SUB
 template<int TPA, int NT, class Op>
-static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double* w)
+static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double* w, int lmode = LIST_FULL)
 {
-  const TileGeom G = make_tile_geom(ctx, ghost);
+  TileGeom G = make_tile_geom(ctx, ghost);
   if( G.ntiles == 0 ) return XSB_OK;
-  const size_t smem = tile_smem_bytes<Op::HAS_W, Op::TYPES>(G.s_cap, op.table_bytes());
+  const bool queue = Op::D2_ONLY && TPA == 32 && lmode != LIST_SUB;
+  const size_t qb = queue ? tile_queue_bytes<NT>() : 0;
+  G.nbuf = tile_smem_bytes<Op::HAS_W, Op::TYPES>(G.s_cap, op.table_bytes(), qb, 3) <= TILE_SMEM_MAX ? 3 : 2;
+  const size_t smem = tile_smem_bytes<Op::HAS_W, Op::TYPES>(G.s_cap, op.table_bytes(), qb, G.nbuf);
   XSB_REQUIRE(ctx, smem <= TILE_SMEM_MAX, XSB_ERR_STATE, "tile pass: shared-memory plan exceeds 227 KiB (caller must pick a smaller table window)");
   const TileFields F{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, w, ctx->type.p };
-  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p };
+  if( lmode != LIST_FULL )
+  {
+    XSB_CUDA(ctx, ctx->sub_idx.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+    XSB_CUDA(ctx, ctx->sub_cnt.reserve(size_t(ctx->n) + 1, 1.02));
+  }
+  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p };
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
   auto go = [&](auto kern) -> int
@@ -80,7 +213,9 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
     XSB_LAUNCH_CHECK(ctx);
     return XSB_OK;
   };
-  return xf ? go(tile_pass_kernel<TPA, NT, true, Op>) : go(tile_pass_kernel<TPA, NT, false, Op>);
+  if( lmode == LIST_SUB )                 return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB, Op>);
+  if( lmode == LIST_FULL_WRITE_SUB )      return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL_WRITE_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL_WRITE_SUB, Op>);
+  return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL, Op>);
 }
 
 // 9-component virial accumulator shared by the force ops: vir += -1/2 f (x) dr, Mat3d row-major (ext tensor())
