@@ -221,9 +221,9 @@ int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const doubl
   XSB_REQUIRE(ctx, n == 0 || (rx && ry && rz), XSB_ERR_INVALID, "null positions");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   // stage host arrays on the device (8-byte words: 6 real fields + id, then type bytes)
-  DevBuf<double> st; DevBuf<unsigned char> stt;
-  cudaError_t e = st.reserve(7 * (n + 1)); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
-  e = stt.reserve(n + 16); if( e != cudaSuccess ) { st.release(); return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e)); }
+  DevBuf<double>& st = ctx->move_stage; DevBuf<unsigned char>& stt = ctx->move_stage8;
+  cudaError_t e = st.reserve(7 * (n + 1), 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
+  e = stt.reserve(n + 16, 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
   const double* hsrc[6] = { rx, ry, rz, vx, vy, vz }; double* d[7];
   for(int k = 0; k < 7; k++) d[k] = st.p + size_t(k) * (n + 1);
   int rc = XSB_OK;
@@ -235,8 +235,7 @@ int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const doubl
   if( rc == XSB_OK )
     rc = assign_device(ctx, unsigned(n), d[0], d[1], d[2], vx ? d[3] : nullptr, vy ? d[4] : nullptr, vz ? d[5] : nullptr,
                        type ? stt.p : nullptr, reinterpret_cast<unsigned long long*>(d[6]), nullptr, nullptr);
-  cudaStreamSynchronize(ctx->stream);
-  st.release(); stt.release();
+  cudaStreamSynchronize(ctx->stream);   // the caller's host arrays may die after the call
   return rc;
 }
 
@@ -250,9 +249,10 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
   XSB_REQUIRE(ctx, dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2] == 1, XSB_ERR_UNSUPPORTED, "rebin: cross-rank migration is not implemented yet");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   const unsigned n = unsigned(ctx->n_own);
-  DevBuf<double> st; DevBuf<unsigned char> stt;
-  cudaError_t e = st.reserve(7 * (size_t(n) + 1)); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
-  e = stt.reserve(size_t(n) + 16); if( e != cudaSuccess ) { st.release(); return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e)); }
+  // staging buffers persist in the context: steady-state rebuilds must not touch cudaMalloc/cudaFree
+  DevBuf<double>& st = ctx->move_stage; DevBuf<unsigned char>& stt = ctx->move_stage8;
+  cudaError_t e = st.reserve(7 * (size_t(n) + 1), 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
+  e = stt.reserve(size_t(n) + 16, 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
   double* d[7]; for(int k = 0; k < 7; k++) d[k] = st.p + size_t(k) * (n + 1);
   const int srcf[6] = { XSB_F_RX, XSB_F_RY, XSB_F_RZ, XSB_F_VX, XSB_F_VY, XSB_F_VZ };
   const unsigned grid = (n + 255) / 256;
@@ -264,9 +264,9 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
     ctx->launches += 8;
   }
   const int wrap[3] = { dom->periodic[0], dom->periodic[1], dom->periodic[2] };
+  ctx->prof_begin(XSB_PROF_MOVE);
   int rc = assign_device(ctx, n, d[0], d[1], d[2], d[3], d[4], d[5], stt.p, reinterpret_cast<unsigned long long*>(d[6]), wrap, dom->box);
-  cudaStreamSynchronize(ctx->stream);
-  st.release(); stt.release();
+  ctx->prof_end(XSB_PROF_MOVE);
   return rc;
 }
 

@@ -55,27 +55,52 @@ int xsb_internal_ensure_virial(xsb_ctx* ctx)
   return XSB_OK;
 }
 
-// host-side cell tables (flat start, cell of each particle, list of particles in non-ghost cells) -> device
+namespace xsb
+{
+// one warp per cell: cell_of[] of its particles and, for non-ghost cells, their slots in the own-particle list
+__global__ void __launch_bounds__(256) cell_tables_kernel(unsigned ncells, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ own_prefix,
+                                                          unsigned* __restrict__ cell_of, unsigned* __restrict__ own_atoms)
+{
+  const unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if( c >= ncells ) return;
+  const unsigned s = cell_start[c], e = cell_start[c + 1], o = own_prefix[c];
+  const bool own = own_prefix[c + 1] - o == e - s;   // ghost cells add nothing to the own-particle prefix
+  for(unsigned p = s + lane; p < e; p += 32u)
+  {
+    cell_of[p] = c;
+    if( own ) own_atoms[o + (p - s)] = p;
+  }
+}
+}
+
+// cell tables (flat start, cell of each particle, list of particles in non-ghost cells): the per-cell prefix sums are
+// done on the host (ncells entries), everything per particle on the device
 int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
 {
   const uint64_t nc = ctx->ncells, n = off[nc];
   ctx->h_cell_off.assign(off, off + nc + 1);
-  std::vector<unsigned> start(nc + 1), cellof(n), own; own.reserve(n);
+  std::vector<unsigned> tab(2 * (nc + 1));            // [0, nc] cell start ; [nc+1, 2nc+1] own-particle prefix
+  unsigned* start = tab.data(); unsigned* ownp = tab.data() + nc + 1;
   const GridView gv = ctx->view();
-  for(uint64_t c = 0; c <= nc; c++) start[c] = unsigned(off[c]);
+  uint64_t nown = 0;
   for(uint64_t c = 0; c < nc; c++)
   {
-    const bool ghost = gv.is_ghost_cell(unsigned(c));
-    for(uint64_t p = off[c]; p < off[c+1]; p++) { cellof[p] = unsigned(c); if( !ghost ) own.push_back(unsigned(p)); }
+    start[c] = unsigned(off[c]); ownp[c] = unsigned(nown);
+    if( !gv.is_ghost_cell(unsigned(c)) ) nown += off[c + 1] - off[c];
   }
-  ctx->n = n; ctx->n_own = own.size(); ctx->pos_epoch++;
-  XSB_CUDA(ctx, ctx->cell_start.reserve(nc + 1));
+  start[nc] = unsigned(off[nc]); ownp[nc] = unsigned(nown);
+  ctx->n = n; ctx->n_own = nown; ctx->pos_epoch++;
+  XSB_CUDA(ctx, ctx->cell_start.reserve(2 * (nc + 1)));
   XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, 1.02));
-  XSB_CUDA(ctx, ctx->own_atoms.reserve(own.size() + 1, 1.02));
-  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, start.data(), (nc + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  if( n ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_of.p, cellof.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  if( !own.empty() ) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->own_atoms.p, own.data(), own.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
+  XSB_CUDA(ctx, ctx->own_atoms.reserve(nown + 1, 1.02));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+  if( n )
+  {
+    xsb::cell_tables_kernel<<<unsigned((nc * 32 + 255) / 256), 256, 0, ctx->stream>>>(unsigned(nc), ctx->cell_start.p, ctx->cell_start.p + nc + 1,
+                                                                                     ctx->cell_of.p, ctx->own_atoms.p);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `tab` dies here
   ctx->nbh_built = false;
   return XSB_OK;
 }
@@ -182,7 +207,7 @@ void xsb_destroy(xsb_ctx* ctx)
   for(auto& b : ctx->f64) b.release();
   ctx->type.release(); ctx->id.release();
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->scratch.release(); ctx->scratch64.release();
-  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);

@@ -132,6 +132,7 @@ struct xsb_ctx
   xsb::DevBuf<unsigned long long> tmp64;      // relayout / sort scratch (8-byte words)
   xsb::DevBuf<unsigned> tmp32a, tmp32b, tmp32c, tmp32d;
   xsb::DevBuf<unsigned> gseg_send, gseg_recv, goff_send, goff_recv;   // ghost segment tables (device)
+  xsb::DevBuf<double> move_stage; xsb::DevBuf<unsigned char> move_stage8;   // move_particles staging (persistent)
   xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
 
   // per-operator device timing (CUDA events on this context's stream), see xsb_profile_*

@@ -185,6 +185,22 @@ __global__ void ghost_self_kernel(unsigned n, FieldPtrs F, ShiftTab S, const uns
   }
 }
 
+// ghost scheme lists: one warp per (ghost cell, owner cell) entry expands its particle range
+struct RangeEntry { unsigned start, count, out, seg_code; };   // seg_code = peer | code << 16
+__global__ void __launch_bounds__(256) expand_ranges_kernel(unsigned n_entries, const RangeEntry* __restrict__ E, unsigned* __restrict__ idx,
+                                                            unsigned char* __restrict__ code, unsigned* __restrict__ seg)
+{
+  const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if( i >= n_entries ) return;
+  const RangeEntry e = E[i];
+  for(unsigned p = lane; p < e.count; p += 32u)
+  {
+    idx[e.out + p] = e.start + p;
+    if( code ) code[e.out + p] = (unsigned char)(e.seg_code >> 16);
+    seg[e.out + p] = e.seg_code & 0xffffu;
+  }
+}
+
 static int make_fields(xsb_ctx* ctx, uint32_t mask, bool reverse, FieldPtrs& F)
 {
   F.nf = 0;
@@ -384,39 +400,52 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
   // particle-level lists
   const double box[3] = { dom->box[0], dom->box[1], dom->box[2] };
   for(int c = 0; c < 27; c++) { G->shift[c][0] = (c % 3 - 1) * box[0]; G->shift[c][1] = ((c / 3) % 3 - 1) * box[1]; G->shift[c][2] = (c / 9 - 1) * box[2]; }
-  std::vector<unsigned> sidx, ridx, sseg, rseg; std::vector<unsigned char> scode;
+  std::vector<RangeEntry> es, er;
   G->send_off.assign(P + 1, 0); G->recv_off.assign(P + 1, 0);
+  unsigned ns = 0, nr = 0;
   for(int q = 0; q < P; q++)
   {
     for(const GhostCell& g : to_peer[q])
     {
       XSB_REQUIRE(ctx, std::abs(g.w[0]) <= 1 && std::abs(g.w[1]) <= 1 && std::abs(g.w[2]) <= 1, XSB_ERR_UNSUPPORTED, "ghost layers wider than the periodic domain");
-      const unsigned code = unsigned(shift_code(g.w));
-      for(uint64_t p = new_off[g.owner_cell]; p < new_off[g.owner_cell + 1]; p++) { sidx.push_back(unsigned(p)); scode.push_back((unsigned char)code); sseg.push_back(unsigned(q)); }
+      const unsigned cnt = unsigned(new_off[g.owner_cell + 1] - new_off[g.owner_cell]);
+      if( cnt ) es.push_back(RangeEntry{ unsigned(new_off[g.owner_cell]), cnt, ns, unsigned(q) | (unsigned(shift_code(g.w)) << 16) });
+      ns += cnt;
     }
-    G->send_off[q + 1] = unsigned(sidx.size());
+    G->send_off[q + 1] = ns;
   }
   for(int q = 0; q < P; q++)
   {
     for(unsigned i = rc_off[q]; i < rc_off[q + 1]; i++)
-      for(uint64_t p = new_off[mine[i].ghost_cell]; p < new_off[mine[i].ghost_cell + 1]; p++) { ridx.push_back(unsigned(p)); rseg.push_back(unsigned(q)); }
-    G->recv_off[q + 1] = unsigned(ridx.size());
+    {
+      const unsigned cnt = unsigned(new_off[mine[i].ghost_cell + 1] - new_off[mine[i].ghost_cell]);
+      if( cnt ) er.push_back(RangeEntry{ unsigned(new_off[mine[i].ghost_cell]), cnt, nr, unsigned(q) });
+      nr += cnt;
+    }
+    G->recv_off[q + 1] = nr;
   }
-  G->n_send = unsigned(sidx.size()); G->n_recv = unsigned(ridx.size());
+  G->n_send = ns; G->n_recv = nr;
   XSB_REQUIRE(ctx, G->send_off[me + 1] - G->send_off[me] == G->recv_off[me + 1] - G->recv_off[me], XSB_ERR_STATE, "ghost scheme: self segment mismatch");
-  XSB_CUDA(ctx, G->send_idx.reserve(sidx.size() + 16, 1.05)); XSB_CUDA(ctx, G->send_code.reserve(scode.size() + 16, 1.05)); XSB_CUDA(ctx, G->recv_idx.reserve(ridx.size() + 16, 1.05));
-  XSB_CUDA(ctx, ctx->gseg_send.reserve(sseg.size() + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_send.reserve(P + 2));
-  XSB_CUDA(ctx, ctx->gseg_recv.reserve(rseg.size() + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_recv.reserve(P + 2));
-  if( !sidx.empty() )
+  XSB_CUDA(ctx, G->send_idx.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, G->send_code.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, G->recv_idx.reserve(size_t(nr) + 16, 1.05));
+  XSB_CUDA(ctx, ctx->gseg_send.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_send.reserve(P + 2));
+  XSB_CUDA(ctx, ctx->gseg_recv.reserve(size_t(nr) + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_recv.reserve(P + 2));
   {
-    XSB_CUDA(ctx, cudaMemcpyAsync(G->send_idx.p, sidx.data(), sidx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    XSB_CUDA(ctx, cudaMemcpyAsync(G->send_code.p, scode.data(), scode.size(), cudaMemcpyHostToDevice, ctx->stream));
-    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->gseg_send.p, sseg.data(), sseg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  if( !ridx.empty() )
-  {
-    XSB_CUDA(ctx, cudaMemcpyAsync(G->recv_idx.p, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->gseg_recv.p, rseg.data(), rseg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // per-cell entries travel (a few thousand), the per-particle lists are expanded on the device
+    const size_t words = (es.size() + er.size()) * (sizeof(RangeEntry) / 8) + 2;
+    XSB_CUDA(ctx, ctx->tmp64.reserve(words + 16, 1.5));
+    RangeEntry* d_es = reinterpret_cast<RangeEntry*>(ctx->tmp64.p); RangeEntry* d_er = d_es + es.size();
+    if( !es.empty() )
+    {
+      XSB_CUDA(ctx, cudaMemcpyAsync(d_es, es.data(), es.size() * sizeof(RangeEntry), cudaMemcpyHostToDevice, ctx->stream));
+      expand_ranges_kernel<<<unsigned((es.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>(unsigned(es.size()), d_es, G->send_idx.p, G->send_code.p, ctx->gseg_send.p);
+      XSB_LAUNCH_CHECK(ctx);
+    }
+    if( !er.empty() )
+    {
+      XSB_CUDA(ctx, cudaMemcpyAsync(d_er, er.data(), er.size() * sizeof(RangeEntry), cudaMemcpyHostToDevice, ctx->stream));
+      expand_ranges_kernel<<<unsigned((er.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>(unsigned(er.size()), d_er, G->recv_idx.p, nullptr, ctx->gseg_recv.p);
+      XSB_LAUNCH_CHECK(ctx);
+    }
   }
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_send.p, G->send_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_recv.p, G->recv_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
