@@ -29,13 +29,14 @@ def build(force=False):
     need = force or not os.path.exists(os.path.join(HERE, "liboracle.so"))
     if not need:
         so_t = os.path.getmtime(os.path.join(HERE, "liboracle.so"))
-        for f in ("xs_oracle.cpp", "snap_oracle.cpp", "orc_math.h"):
+        for f in ("xs_oracle.cpp", "snap_oracle.cpp", "orc_math.h"):  # noqa
             p = os.path.join(HERE, f)
             if os.path.exists(p) and os.path.getmtime(p) > so_t:
                 need = True
     if need:
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src/potential") and (force or not os.path.exists(os.path.join(HERE, "_ref", "libxsref.so"))):
+    if os.path.isdir("/root/reference/src/potential") and (force or not os.path.exists(os.path.join(HERE, "_ref", "libxsref.so"))
+                                                             or not os.path.exists(os.path.join(HERE, "_ref", "libxsref_snap.so"))):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -75,6 +76,14 @@ def lib():
         L.orc_eam_alloy_eval.restype = C.c_double
         L.orc_eam_alloy_eval.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dpp]
         L.orc_eam_alloy.argtypes = [gp, _u64p, _dp, _dp, _dp, _u8p, vp, vp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
+        L.orc_snap_create.restype = vp
+        L.orc_snap_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_double, vp]
+        L.orc_snap_free.argtypes = [vp]
+        L.orc_snap_ncoeff.argtypes = [vp]
+        L.orc_snap_idxb.argtypes = [vp, vp]
+        L.orc_snap_sizes.argtypes = [vp, ip, ip, ip, ip]
+        L.orc_snap_atom.argtypes = [vp, C.c_int, _dp, _dp, _dp, vp, C.c_int, vp, vp, vp, vp]
+        L.orc_snap_force.argtypes = [gp, _u64p, _dp, _dp, _dp, vp, vp, vp, C.c_double, C.c_int, _dp, _dp, _dp, vp, vp]
         L.orc_num_threads.restype = C.c_int
         L.orc_lj_eval.argtypes = [C.c_double, C.c_double, C.c_double, dpp, dpp]
         L.orc_johnson_eval.argtypes = [_dp, C.c_int, C.c_double, dpp, dpp]
@@ -219,3 +228,60 @@ class EamAlloy:
 def eam_alloy(grid, cell_off, rx, ry, rz, typ, nbh, eam, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb):
     assert not eam.use_ref
     lib().orc_eam_alloy(C.byref(grid), cell_off, rx, ry, rz, typ, nbh.h, eam.h, float(rcut), int(flags), fx, fy, fz, ep, _opt(vir), rho_dEmb)
+
+
+class Snap:
+    """SNAP parameters held by the oracle (LAMMPS SNA conventions; beta[nelements][ncoeff+1] in output energy units)."""
+
+    def __init__(self, twojmax, rcutfac, radelem, wjelem, beta=None, rfac0=0.99363, rmin0=0.0, switchflag=1, bzeroflag=0):
+        rad = np.ascontiguousarray(radelem, dtype=np.float64); wj = np.ascontiguousarray(wjelem, dtype=np.float64)
+        self.nelements = len(rad)
+        b = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+        self.h = lib().orc_snap_create(int(twojmax), float(rfac0), float(rmin0), int(switchflag), int(bzeroflag), self.nelements, rad, wj,
+                                       float(rcutfac), None if b is None else b.ctypes.data_as(C.c_void_p))
+        self.ncoeff = lib().orc_snap_ncoeff(self.h)
+        self.twojmax, self.rcutfac, self.radelem, self.wjelem, self.beta = twojmax, rcutfac, rad, wj, b
+        self.rfac0, self.rmin0, self.switchflag, self.bzeroflag = rfac0, rmin0, switchflag, bzeroflag
+        if b is not None:
+            assert b.shape == (self.nelements, self.ncoeff + 1)
+
+    def idxb(self):
+        t = np.zeros((self.ncoeff, 3), dtype=np.int32)
+        lib().orc_snap_idxb(self.h, t.ctypes.data_as(C.c_void_p))
+        return t
+
+    def rcut_max(self):
+        return 2.0 * float(self.radelem.max()) * self.rcutfac
+
+    def atom(self, dx, dy, dz, elem_j=None, elem_i=0, want_db=False, want_force=False):
+        """(B[ncoeff], dB[n][ncoeff][3] or None, energy, dE/dr_j [n][3] or None) for one neighbourhood"""
+        dx, dy, dz = [np.ascontiguousarray(v, dtype=np.float64) for v in (dx, dy, dz)]
+        n = len(dx)
+        ej = None if elem_j is None else np.ascontiguousarray(elem_j, dtype=np.int32)
+        B = np.zeros(self.ncoeff); dB = np.zeros((n, self.ncoeff, 3)) if want_db else None
+        e = C.c_double(); dedr = np.zeros((n, 3)) if want_force else None
+        lib().orc_snap_atom(self.h, n, dx, dy, dz, _opt(ej), int(elem_i), B.ctypes.data_as(C.c_void_p), _opt(dB), C.cast(C.byref(e), C.c_void_p), _opt(dedr))
+        return B, dB, e.value, dedr
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_snap_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
+def snap_force(grid, cell_off, rx, ry, rz, typ, nbh, snap, flags, fx, fy, fz, ep=None, vir=None):
+    """flags: bit0 ghost, bit1 energy, bit2 virial"""
+    lib().orc_snap_force(C.byref(grid), cell_off, rx, ry, rz, _opt(typ), nbh.h, snap.h, snap.rcut_max(), int(flags), fx, fy, fz, _opt(ep), _opt(vir))
+
+
+def ref_snap():
+    """the reference's in-tree SnapLegacyBS (LAMMPS mode); None when oracle/_ref/libxsref_snap.so was never built"""
+    p = os.path.join(HERE, "_ref", "libxsref_snap.so")
+    if not os.path.exists(p):
+        return None
+    R = C.CDLL(p)
+    R.xsref_snap_nidx.argtypes = [C.c_double]
+    R.xsref_snap_bs.argtypes = [C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, _dp, C.c_void_p, C.POINTER(C.c_double)]
+    return R

@@ -555,6 +555,61 @@ void orc_eam_alloy(const orc_grid_t* g, const uint64_t* cell_off, const double* 
   }
 }
 
+// ---- snap_force: traversal + the call sequence of src/potential/snaplmp/snap_force_op.h:177-337 ----------------------
+// (filter rsq < cutsq_ij && rsq > 1e-20 :191 ; compute_ui :214 ; compute_yi :246 ; per neighbour duidrj + deidrj :248-257 ;
+//  f_i += fij, f_j -= fij :277-294 ; virial -fij (x) rij on the centre :267-268 ; energy e0 + beta.B :297-337).
+// The per-atom arithmetic lives in snap_oracle.cpp.  flags: bit0 ghost, bit1 energy, bit2 virial.
+void orc_snap_atom(void* h, int n, const double* dx, const double* dy, const double* dz, const int* elem_j, int elem_i, double* B, double* dB, double* energy, double* dedr);
+void orc_snap_cut(void* h, int elem_i, int elem_j, double* rcut);
+void orc_snap_force(const orc_grid_t* g, const uint64_t* cell_off, const double* rx, const double* ry, const double* rz, const uint8_t* type,
+                    void* nbh, void* snap, double rcut_max, int flags, double* fx, double* fy, double* fz, double* ep, double* vir)
+{
+  const Particles P{ cell_off, rx, ry, rz, type };
+  const bool ghost = flags & 1, eflag = flags & 2, vflag = flags & 4;
+  // f_j -= fij crosses cell boundaries: serial over cells keeps the oracle race-free and deterministic
+  const size_t ncells = size_t(g->dims[0]) * g->dims[1] * g->dims[2];
+  const Nbh& nb = *static_cast<Nbh*>(nbh);
+  const double rcut2 = rcut_max * rcut_max;
+  std::vector<double> dx, dy, dz, dedr; std::vector<int> ej; std::vector<size_t> gj;
+  for(size_t cell_a = 0; cell_a < ncells; cell_a++)
+  {
+    if( !ghost && is_ghost_cell(*g, cell_a) ) continue;
+    walk_cell(*g, cell_off, nb, cell_a,
+      [&](size_t) { dx.clear(); dy.clear(); dz.clear(); ej.clear(); gj.clear(); },
+      [&](size_t p_a, size_t cell_b, size_t p_b)
+      {
+        const size_t ga = cell_off[cell_a] + p_a, gb = cell_off[cell_b] + p_b;
+        Vec3 dr = xform_apply(*g, Vec3{ rx[gb] - rx[ga], ry[gb] - ry[ga], rz[gb] - rz[ga] });
+        const double d2 = dr.x*dr.x + dr.y*dr.y + dr.z*dr.z;
+        if( d2 > rcut2 ) return;
+        double rc = 0.0; orc_snap_cut(snap, type ? type[ga] : 0, type ? type[gb] : 0, &rc);
+        if( d2 < rc * rc && d2 > 1e-20 ) { dx.push_back(dr.x); dy.push_back(dr.y); dz.push_back(dr.z); ej.push_back(type ? type[gb] : 0); gj.push_back(gb); }
+      },
+      [&](size_t p_a)
+      {
+        const size_t ga = cell_off[cell_a] + p_a;
+        const int n = int(dx.size());
+        dedr.assign(3 * size_t(n) + 3, 0.0);
+        double e = 0.0;
+        orc_snap_atom(snap, n, dx.data(), dy.data(), dz.data(), ej.data(), type ? type[ga] : 0, nullptr, nullptr, &e, dedr.data());
+        for(int i = 0; i < n; i++)
+        {
+          const double* f = &dedr[3 * i];
+          fx[ga] += f[0]; fy[ga] += f[1]; fz[ga] += f[2];
+          fx[gj[i]] -= f[0]; fy[gj[i]] -= f[1]; fz[gj[i]] -= f[2];
+          if( vflag && vir )
+          {
+            double* v = vir + 9 * ga;
+            v[0] -= f[0]*dx[i]; v[1] -= f[0]*dy[i]; v[2] -= f[0]*dz[i];
+            v[3] -= f[1]*dx[i]; v[4] -= f[1]*dy[i]; v[5] -= f[1]*dz[i];
+            v[6] -= f[2]*dx[i]; v[7] -= f[2]*dy[i]; v[8] -= f[2]*dz[i];
+          }
+        }
+        if( eflag && ep ) ep[ga] += e;
+      });
+  }
+}
+
 // scalar entry points used to pin the restated math against oracle/_ref and tests/golden/ref_math.json
 void orc_lj_eval(double epsilon, double sigma, double r, double* e, double* de) { lj_compute_energy(LJParams{epsilon, sigma}, r, *e, *de); }
 void orc_johnson_eval(const double* params19, int what, double x, double* f, double* df)
