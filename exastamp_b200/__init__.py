@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
     "xsb_chunk_neighbors_export", "xsb_chunk_neighbors_download_flat",
     "xsb_pair_force", "xsb_pair_multi_force", "xsb_eam_johnson_force",
+    "xsb_snap_ncoeff", "xsb_snap_set", "xsb_snap_rcut_max", "xsb_snap_force", "xsb_snap_overflow",
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
@@ -54,6 +55,13 @@ class EamAlloyTables(C.Structure):
                 ("rdr", C.c_double), ("rdrho", C.c_double), ("rc", C.c_double), ("rhomax", C.c_double),
                 ("conversion_z2r", C.c_double), ("conversion_frho", C.c_double),
                 ("frho", C.POINTER(C.c_double)), ("rhor", C.POINTER(C.c_double)), ("z2r", C.POINTER(C.c_double))]
+
+
+class SnapParams(C.Structure):
+    _fields_ = [("twojmax", C.c_int32), ("switchflag", C.c_int32), ("bzeroflag", C.c_int32), ("nelements", C.c_int32),
+                ("quadraticflag", C.c_int32), ("chemflag", C.c_int32), ("switchinnerflag", C.c_int32), ("pad_", C.c_int32),
+                ("rfac0", C.c_double), ("rmin0", C.c_double), ("rcutfac", C.c_double),
+                ("radelem", C.POINTER(C.c_double)), ("wjelem", C.POINTER(C.c_double)), ("beta", C.POINTER(C.c_double))]
 
 
 class DomainDesc(C.Structure):
@@ -114,6 +122,12 @@ def load_library():
     L.xsb_eam_alloy_free.argtypes = [C.POINTER(EamAlloyTables)]
     L.xsb_eam_alloy_set.argtypes = [vp, C.POINTER(EamAlloyTables)]
     L.xsb_eam_alloy_force.argtypes = [vp, dbl, i32, i32]
+    L.xsb_snap_ncoeff.argtypes = [i32]
+    L.xsb_snap_set.argtypes = [vp, C.POINTER(SnapParams)]
+    L.xsb_snap_rcut_max.restype = dbl
+    L.xsb_snap_rcut_max.argtypes = [vp]
+    L.xsb_snap_force.argtypes = [vp, i32]
+    L.xsb_snap_overflow.argtypes = [vp, C.POINTER(i32)]
     L.xsb_particles_assign.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.xsb_particles_rebin.argtypes = [vp, C.POINTER(DomainDesc)]
     L.xsb_push_f_v_r.argtypes = [vp, dbl]
@@ -278,6 +292,26 @@ class Context:
 
     def eam_alloy_force(self, rcut, phases=EAM_RHO | EAM_RHO2EMB | EAM_GHOST | EAM_FORCE, flags=0):
         self._ck(self.L.xsb_eam_alloy_force(self.h, float(rcut), int(phases), int(flags)), "xsb_eam_alloy_force")
+
+    # ---- a9
+    def snap_set(self, twojmax, rcutfac, radelem, wjelem, beta, rfac0=0.99363, rmin0=0.0, switchflag=1, bzeroflag=0):
+        rad = np.ascontiguousarray(radelem, dtype=np.float64); wj = np.ascontiguousarray(wjelem, dtype=np.float64)
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        nc = self.L.xsb_snap_ncoeff(int(twojmax))
+        if b.shape != (len(rad), nc + 1):
+            raise XsbError("snap_set: beta must be [nelements][ncoeff+1] = [%d][%d]" % (len(rad), nc + 1))
+        p = SnapParams(int(twojmax), int(switchflag), int(bzeroflag), len(rad), 0, 0, 0, 0, float(rfac0), float(rmin0), float(rcutfac),
+                       rad.ctypes.data_as(C.POINTER(C.c_double)), wj.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)))
+        self._ck(self.L.xsb_snap_set(self.h, C.byref(p)), "xsb_snap_set")
+        return self.L.xsb_snap_rcut_max(self.h)
+
+    def snap_force(self, flags=FLAG_ENERGY):
+        self._ck(self.L.xsb_snap_force(self.h, int(flags)), "xsb_snap_force")
+
+    def snap_overflow(self):
+        f = C.c_int()
+        self._ck(self.L.xsb_snap_overflow(self.h, C.byref(f)), "xsb_snap_overflow")
+        return bool(f.value)
 
     # ---- profiling (CUDA events on the context's stream)
     PROF_TAGS = ["nbr_build", "pair", "eam_rho", "eam_rho2emb", "eam_force", "ghost", "integrate", "snap", "move"]

@@ -177,6 +177,7 @@ int  xsb_internal_ensure_virial(xsb_ctx* ctx);
 int  xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* cell_off);
 int  xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_cell_off);
 void xsb_ghost_release(xsb_ctx* ctx);
+void xsb_snap_release(xsb_ctx* ctx);
 
 namespace xsb
 {

@@ -1,0 +1,598 @@
+// xsb_snap.cu -- snap_force: SNAP bispectrum energy and forces.
+//
+// Reference operator: src/potential/snap/snap_force.cu:18-37 registers md::SnapForceGeneric of the un-vendored exaNBody
+// (contribs/md/snap); its call sequence is the one visible in src/potential/snaplmp/snap_force_op.h:177-337
+// (neighbour filter rsq < cutsq_ij && rsq > 1e-20, compute_ui, compute_yi(beta), per neighbour compute_duidrj +
+// compute_deidrj, f_i += fij, f_j -= fij, virial -fij (x) rij on the centre, energy e0 + beta.B) with the LAMMPS SNA
+// conventions (constructor arguments snaplmp.cpp:205-216).  Written from the published algorithm (Thompson et al. 2015;
+// adjoint Y: Wood & Thompson 2018), FP64.
+//
+// B200 mapping: one CTA per central atom, 32 x (J+1) threads: lane = neighbour, warp = row mb of the Wigner matrices.
+// The U recursion of row mb over the levels j = 2mb..2J is a chain that only needs the same row of level j-1, so a
+// thread keeps its row in registers through all levels (fully unrolled); the only cross-thread dependency -- the birth
+// of row mb at level 2mb from the mirrored row mb-1 -- goes through a small shared-memory mailbox.  Utot is the
+// shuffle-reduction over the lanes (neighbours); Y is accumulated in shared memory over the idxz table; the second
+// sweep recomputes the chains together with their three derivatives and contracts them with Y on the fly, so neither
+// U_ij nor dU_ij is ever stored.  The energy comes from Euler's theorem for the trilinear B: sum_k beta_k B_k =
+// (1/3) 2 sum_half Re(conj(Utot) Y) -- no separate Z/B pass.
+#include "xsb_ctx.h"
+#include "xsb_traverse.cuh"
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <type_traits>
+#include <vector>
+
+namespace xsb
+{
+
+constexpr int SNAP_NN_MAX = 64;      // in-range neighbours of one atom held in shared memory (2 batches of 32)
+
+struct SnapZ { unsigned char j1, j2, j, ma1min, ma2max, na, mb1min, mb2max, nb, pad; unsigned short jju; int cgoff; };   // 16 B
+
+struct SnapConst
+{
+  double rootpq[10][10];
+  int idxu_block[10];
+  int twojmax, idxu_max, idxz_max, ncoeff, nelements, switchflag, bzeroflag;
+  double rfac0, rmin0, rcutfac, wself;
+  double radelem[8], wjelem[8], beta0[8], bzero_e[8];    // bzero_e[elem] = sum_k beta_k bzero[j_k]
+};
+
+struct SnapDev
+{
+  bool set = false;
+  SnapConst K{};
+  DevBuf<SnapZ> idxz; DevBuf<double> cglist; DevBuf<double> betaz;   // betaz[elem][jjz]: beta_k with the multiplicity / (j1+1)/(j+1) factors of compute_yi
+  DevBuf<int> err;
+  double rcut_max = 0.0;
+};
+
+// the SNAP state hangs off the context through a map kept in this translation unit
+static std::map<xsb_ctx*, SnapDev*> g_snap;
+static SnapDev* g_snap_of(xsb_ctx* ctx) { auto it = g_snap.find(ctx); return it == g_snap.end() ? nullptr : it->second; }
+
+__device__ __forceinline__ double snap_sfac(const SnapConst& K, double r, double rcut)
+{
+  if( K.switchflag == 0 || r <= K.rmin0 ) return 1.0;
+  if( r > rcut ) return 0.0;
+  return 0.5 * (cos((r - K.rmin0) * M_PI / (rcut - K.rmin0)) + 1.0);
+}
+__device__ __forceinline__ double snap_dsfac(const SnapConst& K, double r, double rcut)
+{
+  if( K.switchflag == 0 || r <= K.rmin0 || r > rcut ) return 0.0;
+  const double f = M_PI / (rcut - K.rmin0);
+  return -0.5 * sin((r - K.rmin0) * f) * f;
+}
+
+// mailbox layout per neighbour: source row m (published at level 2m+1, 2m+2 elements) starts at m(m+1)
+__device__ __forceinline__ int mbox_off(int m) { return m * (m + 1); }
+
+// One sweep over the levels for the thread's (neighbour, row mb).  DERIV = false: accumulate sfac*wj*u into utot (shuffle
+// reduction over the lanes).  DERIV = true: carry du/dr_k, contract with Y -> dedr[3].
+template<int TJ, bool DERIV>
+__device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool valid, double x, double y, double z, double wj, double rcut,
+                                           double2* __restrict__ utot, const double2* __restrict__ ylist,
+                                           double2* __restrict__ mbox /* this neighbour's mailbox: [ (TJ/2)(TJ/2+1) ] x (DERIV ? 4 : 1) */,
+                                           double dedr[3])
+{
+  constexpr int NE = TJ + 1;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1);     // mailbox entries per field
+  double ur[NE], ui[NE];
+  double dur[DERIV ? NE : 1][3], dui[DERIV ? NE : 1][3];
+  const double rsq = x * x + y * y + z * z, r = sqrt(rsq);
+  const double rscale0 = K.rfac0 * M_PI / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+  double sn, cs; sincos(theta0, &sn, &cs);
+  const double z0 = r * cs / sn;
+  const double r0inv = rsqrt(rsq + z0 * z0);
+  const double a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
+  const double sfac = valid ? snap_sfac(K, r, rcut) * wj : 0.0;
+  double da_r[3], da_i[3], db_r[3], db_i[3], uvec[3], dsfac = 0.0;
+  if( DERIV )
+  {
+    const double rinv = 1.0 / r;
+    uvec[0] = x * rinv; uvec[1] = y * rinv; uvec[2] = z * rinv;
+    const double dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
+    const double dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
+#   pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      const double dr0inv = dr0invdr * uvec[k], dz0 = dz0dr * uvec[k];
+      da_r[k] = dz0 * r0inv + z0 * dr0inv; da_i[k] = -z * dr0inv;
+      db_r[k] = y * dr0inv; db_i[k] = -x * dr0inv;
+    }
+    da_i[2] += -r0inv; db_i[0] += -r0inv; db_r[1] += r0inv;
+    dsfac = valid ? snap_dsfac(K, r, rcut) * wj : 0.0;
+    dedr[0] = dedr[1] = dedr[2] = 0.0;
+  }
+# pragma unroll
+  for(int e = 0; e < NE; e++) { ur[e] = 0.0; ui[e] = 0.0; if( DERIV ) { for(int k = 0; k < 3; k++) { dur[e][k] = 0.0; dui[e][k] = 0.0; } } }
+  if( mb == 0 ) ur[0] = 1.0;        // level 0: u = 1
+
+  // contribution of the thread's row at level j (called after the row has been advanced to level j)
+  auto emit = [&](int j, auto jc)
+  {
+    constexpr int J = decltype(jc)::value;
+    const int base = K.idxu_block[J] + (J + 1) * mb;
+    if( !DERIV )
+    {
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++)
+      {
+        double vr = sfac * ur[ma], vi = sfac * ui[ma];
+#       pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o); vi += __shfl_xor_sync(0xffffffffu, vi, o); }
+        if( (threadIdx.x & 31) == 0 ) { utot[base + ma].x += vr; utot[base + ma].y += vi; }
+      }
+    }
+    else
+    {
+      const bool middle = 2 * mb == J;
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++)
+      {
+        double w = 1.0;
+        if( middle ) w = ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0);
+        const double2 Y = ylist[base + ma];
+#       pragma unroll
+        for(int k = 0; k < 3; k++)
+        {
+          const double fr = dsfac * ur[ma] * uvec[k] + sfac * dur[ma][k];
+          const double fi = dsfac * ui[ma] * uvec[k] + sfac * dui[ma][k];
+          dedr[k] += w * (fr * Y.x + fi * Y.y);
+        }
+      }
+    }
+    (void)j;
+  };
+
+  if( mb == 0 ) emit(0, std::integral_constant<int, 0>{});
+
+  auto level = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;        // advance from level J-1 to level J
+    if( 2 * mb <= J )
+    {
+      if( 2 * mb == J )
+      {
+        // birth of the row: level J-1 row mb is the mirror of row mb-1 (published to the mailbox at level J-1):
+        // u[J-1][mb][ma] = (-1)^(mb-1+ma') conj(u[J-1][mb-1][ma']),  ma' = J-1-ma
+        const int o = mbox_off(mb - 1);
+#       pragma unroll
+        for(int ma = 0; ma < J; ma++)
+        {
+          const int mp = J - 1 - ma;
+          const double sgn = ((mb - 1 + mp) & 1) ? -1.0 : 1.0;
+          const double2 v = mbox[o + mp];
+          ur[ma] = sgn * v.x; ui[ma] = -sgn * v.y;
+          if( DERIV )
+          {
+#           pragma unroll
+            for(int k = 0; k < 3; k++) { const double2 d = mbox[MB * (1 + k) + o + mp]; dur[ma][k] = sgn * d.x; dui[ma][k] = -sgn * d.y; }
+          }
+        }
+      }
+      double nr[J + 1], ni[J + 1], dnr[DERIV ? J + 1 : 1][3], dni[DERIV ? J + 1 : 1][3];
+      nr[0] = 0.0; ni[0] = 0.0;
+      if( DERIV ) { for(int k = 0; k < 3; k++) { dnr[0][k] = 0.0; dni[0][k] = 0.0; } }
+#     pragma unroll
+      for(int ma = 0; ma < J; ma++)
+      {
+        double q = K.rootpq[J - ma][J - mb];
+        nr[ma] += q * (a_r * ur[ma] + a_i * ui[ma]);
+        ni[ma] += q * (a_r * ui[ma] - a_i * ur[ma]);
+        if( DERIV )
+        {
+#         pragma unroll
+          for(int k = 0; k < 3; k++)
+          {
+            dnr[ma][k] += q * (da_r[k] * ur[ma] + da_i[k] * ui[ma] + a_r * dur[ma][k] + a_i * dui[ma][k]);
+            dni[ma][k] += q * (da_r[k] * ui[ma] - da_i[k] * ur[ma] + a_r * dui[ma][k] - a_i * dur[ma][k]);
+          }
+        }
+        q = K.rootpq[ma + 1][J - mb];
+        nr[ma + 1] = -q * (b_r * ur[ma] + b_i * ui[ma]);
+        ni[ma + 1] = -q * (b_r * ui[ma] - b_i * ur[ma]);
+        if( DERIV )
+        {
+#         pragma unroll
+          for(int k = 0; k < 3; k++)
+          {
+            dnr[ma + 1][k] = -q * (db_r[k] * ur[ma] + db_i[k] * ui[ma] + b_r * dur[ma][k] + b_i * dui[ma][k]);
+            dni[ma + 1][k] = -q * (db_r[k] * ui[ma] - db_i[k] * ur[ma] + b_r * dui[ma][k] - b_i * dur[ma][k]);
+          }
+        }
+      }
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++)
+      {
+        ur[ma] = nr[ma]; ui[ma] = ni[ma];
+        if( DERIV ) { for(int k = 0; k < 3; k++) { dur[ma][k] = dnr[ma][k]; dui[ma][k] = dni[ma][k]; } }
+      }
+      emit(J, jc);
+      if( J == 2 * mb + 1 && J < TJ )
+      {
+        // publish for the birth of row mb+1 at the next level
+        const int o = mbox_off(mb);
+#       pragma unroll
+        for(int ma = 0; ma <= J; ma++)
+        {
+          mbox[o + ma] = make_double2(ur[ma], ui[ma]);
+          if( DERIV ) { for(int k = 0; k < 3; k++) mbox[MB * (1 + k) + o + ma] = make_double2(dur[ma][k], dui[ma][k]); }
+        }
+      }
+    }
+    __syncthreads();
+  };
+  // levels 1..TJ, unrolled at compile time
+  if constexpr ( TJ >= 1 ) level(std::integral_constant<int, 1>{});
+  if constexpr ( TJ >= 2 ) level(std::integral_constant<int, 2>{});
+  if constexpr ( TJ >= 3 ) level(std::integral_constant<int, 3>{});
+  if constexpr ( TJ >= 4 ) level(std::integral_constant<int, 4>{});
+  if constexpr ( TJ >= 5 ) level(std::integral_constant<int, 5>{});
+  if constexpr ( TJ >= 6 ) level(std::integral_constant<int, 6>{});
+  if constexpr ( TJ >= 7 ) level(std::integral_constant<int, 7>{});
+  if constexpr ( TJ >= 8 ) level(std::integral_constant<int, 8>{});
+}
+
+struct SnapArgs
+{
+  const double* __restrict__ rx; const double* __restrict__ ry; const double* __restrict__ rz; const unsigned char* __restrict__ type;
+  const unsigned long long* __restrict__ nbh_off; const unsigned* __restrict__ nbh_idx;
+  const unsigned* __restrict__ atoms; unsigned n_atoms;
+  const SnapZ* __restrict__ idxz; const double* __restrict__ cglist; const double* __restrict__ betaz;
+  double *fx, *fy, *fz, *ep, *vir; int* err;
+};
+
+template<int TJ, bool XFORM>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+{
+  constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
+  double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
+  double2* mbox = ylist + K.idxu_max;                                   // [32][4 * MB]
+  double* nb_x = reinterpret_cast<double*>(mbox + 32 * 4 * (MB ? MB : 1));   // [SNAP_NN_MAX] x 5
+  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
+  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32][3] + scratch
+  __shared__ unsigned s_nn;
+  const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
+  const unsigned ai = A.atoms ? A.atoms[blockIdx.x] : blockIdx.x;
+  const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
+  const int ei = A.type ? A.type[ai] : 0;
+
+  // ---- Utot = wself on the diagonal, Y = 0
+  for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = make_double2(0.0, 0.0); ylist[k] = make_double2(0.0, 0.0); }
+  __syncthreads();
+  for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
+
+  // ---- neighbour filter (warp 0, ballot compaction keeps the list order): rsq < cutsq_ij && rsq > 1e-20
+  if( mb == 0 )
+  {
+    unsigned nn = 0;
+    const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
+    for(unsigned long long e = e0; e < e1; e += 32)
+    {
+      const unsigned long long ee = e + lane;
+      bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
+      if( ee < e1 )
+      {
+        g = A.nbh_idx[ee];
+        dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
+        apply_xform<XFORM>(X, dx, dy, dz);
+        const int ej = A.type ? A.type[g] : 0;
+        rc = (K.radelem[ei] + K.radelem[ej]) * K.rcutfac; wj = K.wjelem[ej];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        in = d2 < rc * rc && d2 > 1e-20;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      const unsigned slot = nn + __popc(m & ((1u << lane) - 1u));
+      if( in && slot < SNAP_NN_MAX ) { nb_x[slot] = dx; nb_y[slot] = dy; nb_z[slot] = dz; nb_w[slot] = wj; nb_rc[slot] = rc; nb_g[slot] = g; }
+      nn += __popc(m);
+    }
+    if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
+  }
+  __syncthreads();
+  const unsigned nn = s_nn;
+
+  // ---- sweep 1: Utot
+  double dummy[3];
+  for(unsigned b0 = 0; b0 < nn; b0 += 32)
+  {
+    const unsigned n = b0 + lane; const bool valid = n < nn;
+    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
+    snap_sweep<TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * 4 * (MB ? MB : 1), dummy);
+  }
+  __syncthreads();
+  // right half by inversion symmetry u[j-mb][j-ma] = (-1)^(mb+ma) conj(u[mb][ma]); middle row: second half from the first
+  for(int j = 1; j <= TJ; j++)
+  {
+    const int jb = K.idxu_block[j], half = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 : 0);   // elements strictly before the mirror centre
+    for(int k = int(tid); k < half; k += NT)
+    {
+      const int mbb = k / (j + 1), ma = k % (j + 1);
+      const double sgn = ((mbb + ma) & 1) ? -1.0 : 1.0;
+      const double2 v = utot[jb + k];
+      utot[jb + (j + 1) * (j - mbb) + (j - ma)] = make_double2(sgn * v.x, -sgn * v.y);
+    }
+  }
+  __syncthreads();
+
+  // ---- Y = sum over idxz of betaj * Z  (compute_yi), shared-memory accumulation
+  const double* betaz = A.betaz + size_t(ei) * K.idxz_max;
+  for(int jjz = int(tid); jjz < K.idxz_max; jjz += NT)
+  {
+    const SnapZ q = A.idxz[jjz];
+    const double* cg = A.cglist + q.cgoff;
+    double zr = 0.0, zi = 0.0;
+    int jju1 = K.idxu_block[q.j1] + (q.j1 + 1) * q.mb1min, jju2 = K.idxu_block[q.j2] + (q.j2 + 1) * q.mb2max, icgb = q.mb1min * (q.j2 + 1) + q.mb2max;
+    for(int ib = 0; ib < q.nb; ib++)
+    {
+      double sr = 0.0, si = 0.0;
+      int ma1 = q.ma1min, ma2 = q.ma2max, icga = q.ma1min * (q.j2 + 1) + q.ma2max;
+      for(int ia = 0; ia < q.na; ia++)
+      {
+        const double2 u1 = utot[jju1 + ma1], u2 = utot[jju2 + ma2];
+        const double c = __ldg(cg + icga);
+        sr += c * (u1.x * u2.x - u1.y * u2.y);
+        si += c * (u1.x * u2.y + u1.y * u2.x);
+        ma1++; ma2--; icga += q.j2;
+      }
+      const double c = __ldg(cg + icgb);
+      zr += c * sr; zi += c * si;
+      jju1 += q.j1 + 1; jju2 -= q.j2 + 1; icgb += q.j2;
+    }
+    const double bj = __ldg(betaz + jjz);
+    atomicAdd(&ylist[q.jju].x, bj * zr); atomicAdd(&ylist[q.jju].y, bj * zi);
+  }
+  __syncthreads();
+
+  // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
+  if( A.ep )
+  {
+    double s = 0.0;
+    for(int j = 0; j <= TJ; j++)
+    {
+      const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
+      for(int k = int(tid); k < cnt; k += NT)
+      {
+        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
+        s += w * (utot[jb + k].x * ylist[jb + k].x + utot[jb + k].y * ylist[jb + k].y);
+      }
+    }
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if( lane == 0 ) red[mb] = s;
+    __syncthreads();
+    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    __syncthreads();
+  }
+
+  // ---- sweep 2: dU/dr contracted with Y -> fij ; f_i += fij, f_j -= fij, virial -fij (x) rij on the centre
+  double fix = 0.0, fiy = 0.0, fiz = 0.0, v[9];
+# pragma unroll
+  for(int k = 0; k < 9; k++) v[k] = 0.0;
+  for(unsigned b0 = 0; b0 < nn; b0 += 32)
+  {
+    const unsigned n = b0 + lane; const bool valid = n < nn;
+    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
+    double dedr[3];
+    snap_sweep<TJ, true>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * 4 * (MB ? MB : 1), dedr);
+    red[(mb * 32 + lane) * 3 + 0] = dedr[0]; red[(mb * 32 + lane) * 3 + 1] = dedr[1]; red[(mb * 32 + lane) * 3 + 2] = dedr[2];
+    __syncthreads();
+    if( mb == 0 && valid )
+    {
+      double f[3] = { 0.0, 0.0, 0.0 };
+      for(int w2 = 0; w2 < NR; w2++) for(int k = 0; k < 3; k++) f[k] += red[(w2 * 32 + lane) * 3 + k];
+      for(int k = 0; k < 3; k++) f[k] *= 2.0;
+      fix += f[0]; fiy += f[1]; fiz += f[2];
+      const unsigned g = nb_g[n];
+      atomicAdd(A.fx + g, -f[0]); atomicAdd(A.fy + g, -f[1]); atomicAdd(A.fz + g, -f[2]);
+      if( A.vir )
+      {
+        v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
+        v[3] -= f[1] * x; v[4] -= f[1] * y; v[5] -= f[1] * z;
+        v[6] -= f[2] * x; v[7] -= f[2] * y; v[8] -= f[2] * z;
+      }
+    }
+    __syncthreads();
+  }
+  if( mb == 0 )
+  {
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { fix += __shfl_xor_sync(0xffffffffu, fix, o); fiy += __shfl_xor_sync(0xffffffffu, fiy, o); fiz += __shfl_xor_sync(0xffffffffu, fiz, o); }
+    if( A.vir )
+    {
+#     pragma unroll
+      for(int k = 0; k < 9; k++) { for(int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o); }
+    }
+    if( lane == 0 )
+    {
+      atomicAdd(A.fx + ai, fix); atomicAdd(A.fy + ai, fiy); atomicAdd(A.fz + ai, fiz);
+      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += v[k]; }
+    }
+  }
+}
+
+// ---- host: index tables of the published algorithm ------------------------------------------------------------
+static double fact(int n) { double f = 1.0; for(int i = 2; i <= n; i++) f *= i; return f; }
+
+struct SnapTables
+{
+  int twojmax, jdim, idxu_max = 0, ncoeff = 0;
+  std::vector<int> idxu_block, cg_block, b_block;
+  std::vector<SnapZ> idxz; std::vector<double> cglist; std::vector<int> b_j;     // b_j[k] = j of component k
+  int b3(int a, int b, int c) const { return (a * jdim + b) * jdim + c; }
+  explicit SnapTables(int tj) : twojmax(tj), jdim(tj + 1)
+  {
+    idxu_block.assign(jdim, 0); cg_block.assign(size_t(jdim) * jdim * jdim, -1); b_block = cg_block;
+    for(int j = 0; j <= tj; j++) { idxu_block[j] = idxu_max; idxu_max += (j + 1) * (j + 1); }
+    // triples j2 <= j1, |j1-j2| <= j <= min(2J, j1+j2), same parity
+    auto triples = [&](auto f) { for(int j1 = 0; j1 <= tj; j1++) for(int j2 = 0; j2 <= j1; j2++) for(int j = j1 - j2; j <= std::min(tj, j1 + j2); j += 2) f(j1, j2, j); };
+    triples([&](int j1, int j2, int j)
+    {
+      cg_block[b3(j1, j2, j)] = int(cglist.size());
+      for(int m1 = 0; m1 <= j1; m1++) for(int m2 = 0; m2 <= j2; m2++)
+      {
+        const int aa2 = 2 * m1 - j1, bb2 = 2 * m2 - j2, m = (aa2 + bb2 + j) / 2;
+        if( m < 0 || m > j ) { cglist.push_back(0.0); continue; }
+        double sum = 0.0;
+        const int zlo = std::max(0, std::max(-(j - j2 + aa2) / 2, -(j - j1 - bb2) / 2)), zhi = std::min((j1 + j2 - j) / 2, std::min((j1 - aa2) / 2, (j2 + bb2) / 2));
+        for(int z = zlo; z <= zhi; z++)
+          sum += ((z & 1) ? -1.0 : 1.0) / (fact(z) * fact((j1 + j2 - j) / 2 - z) * fact((j1 - aa2) / 2 - z) * fact((j2 + bb2) / 2 - z) * fact((j - j2 + aa2) / 2 + z) * fact((j - j1 - bb2) / 2 + z));
+        const int cc2 = 2 * m - j;
+        const double dcg = std::sqrt(fact((j1 + j2 - j) / 2) * fact((j1 - j2 + j) / 2) * fact((-j1 + j2 + j) / 2) / fact((j1 + j2 + j) / 2 + 1));
+        const double sf = std::sqrt(fact((j1 + aa2) / 2) * fact((j1 - aa2) / 2) * fact((j2 + bb2) / 2) * fact((j2 - bb2) / 2) * fact((j + cc2) / 2) * fact((j - cc2) / 2) * (j + 1));
+        cglist.push_back(sum * dcg * sf);
+      }
+      if( j >= j1 ) { b_block[b3(j1, j2, j)] = ncoeff++; b_j.push_back(j); }
+    });
+    triples([&](int j1, int j2, int j)
+    {
+      for(int mb = 0; 2 * mb <= j; mb++) for(int ma = 0; ma <= j; ma++)
+      {
+        SnapZ z{}; z.j1 = (unsigned char)j1; z.j2 = (unsigned char)j2; z.j = (unsigned char)j;
+        const int ma1min = std::max(0, (2 * ma - j - j2 + j1) / 2), mb1min = std::max(0, (2 * mb - j - j2 + j1) / 2);
+        z.ma1min = (unsigned char)ma1min; z.ma2max = (unsigned char)((2 * ma - j - (2 * ma1min - j1) + j2) / 2);
+        z.na = (unsigned char)(std::min(j1, (2 * ma - j + j2 + j1) / 2) - ma1min + 1);
+        z.mb1min = (unsigned char)mb1min; z.mb2max = (unsigned char)((2 * mb - j - (2 * mb1min - j1) + j2) / 2);
+        z.nb = (unsigned char)(std::min(j1, (2 * mb - j + j2 + j1) / 2) - mb1min + 1);
+        z.jju = (unsigned short)(idxu_block[j] + (j + 1) * mb + ma);
+        z.cgoff = cg_block[b3(j1, j2, j)];
+        idxz.push_back(z);
+      }
+    });
+  }
+  // beta_k with the multiplicity and (j1+1)/(j+1) factors with which component k enters Y through z(j1,j2,j)
+  double betaj(const SnapZ& z, const double* beta) const
+  {
+    const int j1 = z.j1, j2 = z.j2, j = z.j;
+    if( j >= j1 ) { const double b = beta[b_block[b3(j1, j2, j)]]; return j1 == j ? (j2 == j ? 3.0 * b : 2.0 * b) : b; }
+    if( j >= j2 ) { const double b = beta[b_block[b3(j, j2, j1)]]; return (j2 == j ? 2.0 * b : b) * (j1 + 1) / (j + 1.0); }
+    return beta[b_block[b3(j2, j, j1)]] * (j1 + 1) / (j + 1.0);
+  }
+};
+
+} // namespace xsb
+
+using namespace xsb;
+
+void xsb_snap_release(xsb_ctx* ctx)
+{
+  auto it = g_snap.find(ctx);
+  if( it == g_snap.end() ) return;
+  it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
+  delete it->second; g_snap.erase(it);
+}
+
+template<int TJ>
+static int snap_launch(xsb_ctx* ctx, SnapDev* S, const SnapArgs& A)
+{
+  constexpr int NR = TJ / 2 + 1, NT = 32 * NR, MB = (TJ / 2) * (TJ / 2 + 1);
+  const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * 4 * (MB ? MB : 1) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
+                    + size_t(NR) * 32 * 3 * sizeof(double) + 64;
+  const XForm X = make_xform(ctx->grid);
+  auto go = [&](auto kern) -> int
+  {
+    XSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K);
+    XSB_LAUNCH_CHECK(ctx);
+    return XSB_OK;
+  };
+  return ctx->grid.xform_is_identity ? go(snap_force_kernel<TJ, false>) : go(snap_force_kernel<TJ, true>);
+}
+
+extern "C" {
+
+int xsb_snap_ncoeff(int twojmax)
+{
+  if( twojmax < 0 || twojmax > 8 ) return -1;
+  int n = 0;
+  for(int j1 = 0; j1 <= twojmax; j1++) for(int j2 = 0; j2 <= j1; j2++) for(int j = j1 - j2; j <= std::min(twojmax, j1 + j2); j += 2) if( j >= j1 ) ++n;
+  return n;
+}
+
+int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, p != nullptr && p->radelem && p->wjelem && p->beta, XSB_ERR_INVALID, "snap: null parameters");
+  XSB_REQUIRE(ctx, p->twojmax >= 1 && p->twojmax <= 8, XSB_ERR_UNSUPPORTED, "snap: twojmax must be in 1..8");
+  XSB_REQUIRE(ctx, p->nelements >= 1 && p->nelements <= 8, XSB_ERR_INVALID, "snap: 1..8 elements");
+  XSB_REQUIRE(ctx, p->quadraticflag == 0 && p->chemflag == 0 && p->switchinnerflag == 0, XSB_ERR_UNSUPPORTED, "snap: quadratic / chem / inner-switch variants are not implemented");
+  XSB_REQUIRE(ctx, p->rcutfac > 0.0, XSB_ERR_INVALID, "snap: rcutfac must be > 0");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  SnapDev*& S = g_snap[ctx];
+  if( !S ) S = new SnapDev;
+  SnapTables T(p->twojmax);
+  SnapConst& K = S->K; K = SnapConst{};
+  for(int a = 1; a <= p->twojmax; a++) for(int b = 1; b <= p->twojmax; b++) K.rootpq[a][b] = std::sqrt(double(a) / b);
+  for(int j = 0; j <= p->twojmax; j++) K.idxu_block[j] = T.idxu_block[j];
+  K.twojmax = p->twojmax; K.idxu_max = T.idxu_max; K.idxz_max = int(T.idxz.size()); K.ncoeff = T.ncoeff; K.nelements = p->nelements;
+  K.switchflag = p->switchflag; K.bzeroflag = p->bzeroflag; K.rfac0 = p->rfac0; K.rmin0 = p->rmin0; K.rcutfac = p->rcutfac; K.wself = 1.0;
+  std::vector<double> betaz(size_t(p->nelements) * T.idxz.size());
+  double radmax = 0.0;
+  for(int e = 0; e < p->nelements; e++)
+  {
+    const double* be = p->beta + size_t(e) * (T.ncoeff + 1);
+    K.radelem[e] = p->radelem[e]; K.wjelem[e] = p->wjelem[e]; K.beta0[e] = be[0]; K.bzero_e[e] = 0.0;
+    radmax = std::max(radmax, p->radelem[e]);
+    if( p->bzeroflag ) for(int k = 0; k < T.ncoeff; k++) K.bzero_e[e] += be[1 + k] * (K.wself * K.wself * K.wself) * (T.b_j[k] + 1);
+    for(size_t z = 0; z < T.idxz.size(); z++) betaz[size_t(e) * T.idxz.size() + z] = T.betaj(T.idxz[z], be + 1);
+  }
+  S->rcut_max = 2.0 * radmax * p->rcutfac;
+  XSB_CUDA(ctx, S->idxz.reserve(T.idxz.size())); XSB_CUDA(ctx, S->cglist.reserve(T.cglist.size())); XSB_CUDA(ctx, S->betaz.reserve(betaz.size())); XSB_CUDA(ctx, S->err.reserve(4));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->idxz.p, T.idxz.data(), T.idxz.size() * sizeof(SnapZ), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->cglist.p, T.cglist.data(), T.cglist.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz.p, betaz.data(), betaz.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, 4 * sizeof(int), ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  S->set = true;
+  return XSB_OK;
+}
+
+double xsb_snap_rcut_max(xsb_ctx* ctx) { SnapDev* S = ctx ? g_snap_of(ctx) : nullptr; return S && S->set ? S->rcut_max : 0.0; }
+
+int xsb_snap_force(xsb_ctx* ctx, int flags)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  SnapDev* S = g_snap_of(ctx);
+  XSB_REQUIRE(ctx, S && S->set, XSB_ERR_STATE, "xsb_snap_set must be called first");
+  XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
+  XSB_REQUIRE(ctx, S->rcut_max <= ctx->nbh_dist, XSB_ERR_INVALID, "snap cutoff exceeds the neighbour-list distance nbh_dist_lab");
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool ghost = flags & XSB_FLAG_GHOST, virial = flags & XSB_FLAG_VIRIAL;
+  if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
+  SnapArgs A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, S->K.nelements > 1 ? ctx->type.p : nullptr, ctx->nbh_off.p, ctx->nbh_idx.p,
+              ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own), S->idxz.p, S->cglist.p, S->betaz.p,
+              ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr,
+              virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr, S->err.p };
+  if( A.n_atoms == 0 ) return XSB_OK;
+  int rc = XSB_ERR_UNSUPPORTED;
+  ctx->prof_begin(XSB_PROF_SNAP);
+  switch( S->K.twojmax )
+  {
+    case 1: rc = snap_launch<1>(ctx, S, A); break; case 2: rc = snap_launch<2>(ctx, S, A); break;
+    case 3: rc = snap_launch<3>(ctx, S, A); break; case 4: rc = snap_launch<4>(ctx, S, A); break;
+    case 5: rc = snap_launch<5>(ctx, S, A); break; case 6: rc = snap_launch<6>(ctx, S, A); break;
+    case 7: rc = snap_launch<7>(ctx, S, A); break; case 8: rc = snap_launch<8>(ctx, S, A); break;
+    default: break;
+  }
+  ctx->prof_end(XSB_PROF_SNAP);
+  return rc;
+}
+
+// 1 when some atom had more than SNAP_NN_MAX in-range neighbours since the last call (forces are then incomplete)
+int xsb_snap_overflow(xsb_ctx* ctx, int* flag)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  SnapDev* S = g_snap_of(ctx);
+  XSB_REQUIRE(ctx, S && S->set && flag, XSB_ERR_STATE, "xsb_snap_set must be called first");
+  XSB_CUDA(ctx, cudaMemcpyAsync(flag, S->err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, sizeof(int), ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return XSB_OK;
+}
+
+} // extern "C"

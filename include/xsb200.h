@@ -171,6 +171,29 @@ int  xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t);   /* upload
 int  xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags);
 
 /* ---------------------------------------------------------------------------------------------------- */
+/* a9  snap_force (src/potential/snap/snap_force.cu:26-36 -> ext md::SnapForceGeneric; call sequence            */
+/*     src/potential/snaplmp/snap_force_op.h:177-337; SNA constructor arguments snaplmp.cpp:205-216).           */
+/*     LAMMPS conventions: ncoeff = number of bispectrum components for twojmax (55 for 8, 30 for 6),           */
+/*     beta[nelements][ncoeff+1] with beta0 first, ALREADY in internal energy units (the reference scales the   */
+/*     eV coefficients by EXASTAMP_CONST_QUANTITY(1 eV), snap_force_op.h:77); cutoff of a pair =                */
+/*     (radelem[i]+radelem[j])*rcutfac; neighbour weight wjelem[j].                                             */
+typedef struct xsb_snap_params {
+  int32_t twojmax, switchflag, bzeroflag, nelements;
+  int32_t quadraticflag, chemflag, switchinnerflag, pad_;   /* must be 0 (variants not implemented)            */
+  double  rfac0, rmin0, rcutfac;
+  const double* radelem;    /* [nelements] */
+  const double* wjelem;     /* [nelements] */
+  const double* beta;       /* [nelements][ncoeff+1] */
+} xsb_snap_params;
+int    xsb_snap_ncoeff(int twojmax);                        /* -1 if twojmax is outside 0..8                    */
+int    xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p);
+double xsb_snap_rcut_max(xsb_ctx* ctx);                     /* rcut_max output slot: 2 max(radelem) rcutfac     */
+/* f_i += fij, f_j -= fij (Newton-on like the reference, forces of ghost neighbours land on the ghost copies:   */
+/* follow with xsb_ghost_reduce_add of fx,fy,fz = update_force_energy_from_ghost); flags: GHOST, ENERGY, VIRIAL */
+int    xsb_snap_force(xsb_ctx* ctx, int flags);
+int    xsb_snap_overflow(xsb_ctx* ctx, int* flag);          /* 1: an atom exceeded the in-range neighbour cap   */
+
+/* ---------------------------------------------------------------------------------------------------- */
 /* a10 ghost operators.  Single rank: ghosts are periodic images inside the same context.                */
 typedef struct xsb_domain_desc {
   int32_t global_cells[3];   /* own (non-ghost) cells of the whole domain                               */

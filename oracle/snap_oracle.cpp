@@ -411,4 +411,29 @@ void orc_snap_atom(void* h, int n, const double* dx, const double* dy, const dou
   }
 }
 
+// debug/identity helper: 2*sum_half Re(conj(Utot).Y) for the neighbourhood (Euler: = 3 * sum_k beta_k B_k when bzeroflag = 0),
+// the form in which the CUDA kernel obtains the energy without a separate compute_bi pass
+double orc_snap_uy(void* h, int n, const double* dx, const double* dy, const double* dz, const int* elem_j, int elem_i)
+{
+  const Sna& s = *static_cast<Sna*>(h);
+  Sna::Work w; s.alloc(w);
+  std::vector<double> wj(n), rc(n);
+  for(int i = 0; i < n; i++) { const int ej = elem_j ? elem_j[i] : 0; wj[i] = s.wjelem[ej]; rc[i] = (s.radelem[elem_i] + s.radelem[ej]) * s.rcutfac; }
+  s.compute_ui(w, n, dx, dy, dz, wj.data(), rc.data());
+  s.compute_yi(w, s.beta.data() + size_t(elem_i) * (s.ncoeff + 1) + 1);
+  double sum = 0.0;
+  for(int j = 0; j <= s.twojmax; j++)
+  {
+    int jju = s.idxu_block[j];
+    for(int mb = 0; 2 * mb < j; mb++) for(int ma = 0; ma <= j; ma++) { sum += w.utot_r[jju] * w.y_r[jju] + w.utot_i[jju] * w.y_i[jju]; jju++; }
+    if( j % 2 == 0 )
+    {
+      const int mb = j / 2;
+      for(int ma = 0; ma < mb; ma++) { sum += w.utot_r[jju] * w.y_r[jju] + w.utot_i[jju] * w.y_i[jju]; jju++; }
+      sum += 0.5 * (w.utot_r[jju] * w.y_r[jju] + w.utot_i[jju] * w.y_i[jju]);
+    }
+  }
+  return 2.0 * sum;
+}
+
 } // extern "C"

@@ -378,3 +378,68 @@ def test_nve_loop_pieces_and_rebin():
     assert np.array_equal(ctx.cell_offsets(), gs2.cell_off)
     assert np.max(np.abs(ctx.download(xsb.F_RX) - gs2.rx)) < 1e-9
     assert np.array_equal(ctx.download(xsb.F_ID), ids[gs2.src_index])
+
+
+# ---- a9 snap_force ---------------------------------------------------------------------------------------------------
+def snap_case(twoj, nel, seed=4, structure="BCC", ncells=5, a=3.3, gl=1):
+    O = oracle()
+    rng = np.random.default_rng(seed)
+    types = None if nel == 1 else [0, 1]
+    pos, typ, box = lattice(structure, ncells, a, 0.07, seed=seed, types=types)
+    gs = GridSystem(pos, typ, box, box[0] / 3, gl)
+    rad = [0.5, 0.46][:nel]; wj = [1.0, 0.8][:nel]
+    nc = xsb.load_library().xsb_snap_ncoeff(twoj)
+    beta = rng.normal(0.0, 1.0, (nel, nc + 1)) * EV * 1e-3
+    return gs, O.Snap(twoj, 4.7, rad, wj, beta), (twoj, 4.7, rad, wj, beta)
+
+
+@pytest.mark.parametrize("twoj,nel,virial", [(8, 1, True), (6, 2, False), (3, 1, False), (4, 1, True)])
+def test_snap_force_parity(twoj, nel, virial):
+    O = oracle()
+    gs, S, args = snap_case(twoj, nel)
+    g = gs.oracle_grid()
+    nbh_dist = S.rcut_max() + 0.5
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh_dist, 1, True)
+    rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    rvir = np.zeros((gs.n, 9)) if virial else None
+    O.snap_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, S, 2 | (4 if virial else 0), rfx, rfy, rfz, rep, rvir)
+    ctx = make_ctx(gs)
+    rc = ctx.snap_set(*args)
+    assert abs(rc - S.rcut_max()) < 1e-12
+    ctx.chunk_neighbors(nbh_dist)
+    ctx.zero_force_energy(ghost=True)
+    ctx.snap_force(xsb.FLAG_ENERGY | (xsb.FLAG_VIRIAL if virial else 0))
+    assert not ctx.snap_overflow()
+    fx, fy, fz, ep = [ctx.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+    fmax = max(np.abs(rfx).max(), np.abs(rfy).max(), np.abs(rfz).max())
+    # FP64 mode tolerance of the north star: 1e-10 relative (forces on ghost copies included: Newton-on scatter)
+    for a, b in ((fx, rfx), (fy, rfy), (fz, rfz)):
+        assert np.abs(a - b).max() <= 1e-10 * fmax
+    own = ~gs.is_ghost
+    assert np.abs(ep[own] - rep[own]).max() <= 1e-10 * np.abs(rep[own]).max()
+    if virial:
+        vir = ctx.download(xsb.F_VIRIAL)
+        assert np.abs(vir[own] - rvir[own]).max() <= 1e-10 * np.abs(rvir[own]).max()
+
+
+def test_eam_force_after_positions_changed_does_not_reuse_stale_sublist(tmp_path):
+    """the rho pass leaves an in-range sub-list for the force pass of the SAME positions; if the caller moves atoms in
+    between (here: uploads new positions, keeps rho_dEmb), the force pass must fall back to the full list"""
+    O = oracle()
+    gs = system(ncells=5, a=3.615, sigma=0.05, cell=3.615 * 5 / 2, gl=1, seed=3)
+    path = write_setfl(str(tmp_path / "cu.eam.alloy"), [SC_CU], nrho=800, drho=0.25, nr=900, rc=5.6)
+    g = gs.oracle_grid(); eam = O.EamAlloy(path)
+    ctx = make_ctx(gs); ctx.eam_alloy_load(path); ctx.chunk_neighbors(8.0)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(5.6, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST)
+    emb = ctx.download(xsb.F_RHO_DEMB)
+    rng = np.random.default_rng(9)
+    own_shift = rng.normal(0, 0.12, (int(gs.src_index.max()) + 1, 3))
+    rx2, ry2, rz2 = gs.rx + own_shift[gs.src_index, 0], gs.ry + own_shift[gs.src_index, 1], gs.rz + own_shift[gs.src_index, 2]
+    ctx.upload(xsb.F_RX, rx2); ctx.upload(xsb.F_RY, ry2); ctx.upload(xsb.F_RZ, rz2)
+    ctx.eam_alloy_force(5.6, xsb.EAM_FORCE)
+    fx = ctx.download(xsb.F_FX)
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 8.0, 1, True)     # the list is still the old one
+    rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    O.eam_alloy(g, gs.cell_off, rx2, ry2, rz2, gs.type, nb, eam, 5.6, 8, rfx, rfy, rfz, rep, None, emb.copy())
+    assert rel_err(fx, rfx) < TOL64
