@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxsb200.so")
-SOURCES = ["xsb_core.cu", "xsb_nbr.cu", "xsb_pair.cu", "xsb_eam.cu", "xsb_ghost.cu", "xsb_assign.cu", "xsb_snap.cu"]
+SOURCES = ["xsb_core.cu", "xsb_nbr.cu", "xsb_pair.cu", "xsb_eam.cu", "xsb_ghost.cu", "xsb_assign.cu", "xsb_snap.cu", "xsb_thermo.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

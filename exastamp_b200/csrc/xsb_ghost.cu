@@ -329,6 +329,19 @@ int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host)
   return XSB_OK;
 }
 
+} // extern "C" (reopened below)
+
+// sum-allreduce of `count` doubles in device memory (thermodynamic state: the reference's MPI_Allreduce(SUM))
+int xsb_internal_allreduce_sum(xsb_ctx* ctx, double* dev_inout, int count)
+{
+  if( ctx->nranks == 1 ) return XSB_OK;
+  XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "xsb_comm_init must be called first");
+  XSB_NCCL(ctx, g_nccl.AllReduce(dev_inout, dev_inout, size_t(count), NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream));
+  return XSB_OK;
+}
+
+extern "C" {
+
 int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;

@@ -233,6 +233,12 @@ int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass);
 int xsb_backup_r(xsb_ctx* ctx);
 int xsb_particle_displ_over(xsb_ctx* ctx, double threshold, int* result, double* max_displ);
 
+/* simulation_thermodynamic_state (src/thermo_state/simulation_thermodynamic_state.cpp:81-230): sums over
+ * the particles of own cells, all-reduced over ranks, in the reference's 27-double layout: virial[9] (zeros when no
+ * operator produced it), ke_tensor[9] = 1/2 sum m v(x)v, momentum[3] = sum m v, kinetic_energy[3] = 1/2 sum m v_a^2,
+ * potential_energy = sum ep, mass, particle count.  mass: n_types entries indexed by field::type.                  */
+int xsb_thermo_state(xsb_ctx* ctx, int n_types, const double* mass, double* out27);
+
 #ifdef __cplusplus
 }
 #endif
