@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
+    "xsb_thermo_state",
 ]
 
 
@@ -135,6 +136,7 @@ def load_library():
     L.xsb_force_to_accel.argtypes = [vp, i32, vp]
     L.xsb_backup_r.argtypes = [vp]
     L.xsb_particle_displ_over.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(dbl)]
+    L.xsb_thermo_state.argtypes = [vp, i32, vp, vp]
     L.xsb_comm_unique_id.argtypes = [vp]
     L.xsb_comm_init.argtypes = [vp, i32, i32, vp]
     L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc)]
@@ -389,6 +391,14 @@ class Context:
         r, d = C.c_int(), C.c_double()
         self._ck(self.L.xsb_particle_displ_over(self.h, float(threshold), C.byref(r), C.byref(d)), "xsb_particle_displ_over")
         return bool(r.value), d.value
+
+    def thermo_state(self, masses):
+        """simulation_thermodynamic_state: dict of the reference's 27 sums (own cells, all ranks)"""
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        out = np.zeros(27)
+        self._ck(self.L.xsb_thermo_state(self.h, m.size, _ptr(m), _ptr(out)), "xsb_thermo_state")
+        return dict(virial=out[0:9].reshape(3, 3), ke_tensor=out[9:18].reshape(3, 3), momentum=out[18:21], kinetic_energy=out[21:24],
+                    potential_energy=out[24], mass=out[25], particle_count=int(out[26]))
 
     def ghost_update(self, fields):
         self._ck(self.L.xsb_ghost_update(self.h, sum(1 << f for f in fields)), "xsb_ghost_update")

@@ -443,3 +443,43 @@ def test_eam_force_after_positions_changed_does_not_reuse_stale_sublist(tmp_path
     rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
     O.eam_alloy(g, gs.cell_off, rx2, ry2, rz2, gs.type, nb, eam, 5.6, 8, rfx, rfy, rfz, rep, None, emb.copy())
     assert rel_err(fx, rfx) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ f2 thermodynamic state
+@pytest.mark.parametrize("virial", [False, True])
+def test_thermo_state_matches_the_reference_sums(virial):
+    """simulation_thermodynamic_state (src/thermo_state/simulation_thermodynamic_state.cpp:81-230): the 27 sums over own
+    cells, restated with numpy on the same arrays; reproducible bit for bit from call to call."""
+    pos, typ, box = lattice("FCC", 6, 5.0, 0.1, seed=21, types=[0, 1, 0, 1])
+    rng = np.random.default_rng(23)
+    vel = rng.normal(0, 1.0, pos.shape)
+    gs = GridSystem(pos, typ, box, 10.0, 1)
+    ctx = assigned_ctx(pos, typ, box, 10.0, 1, vel=vel)
+    own = ~gs.is_ghost
+    ep = rng.normal(0, 1, gs.n)
+    ctx.upload(xsb.F_EP, ep)
+    vir = None
+    if virial:
+        ctx.zero_force_energy(ghost=True)
+        ctx.upload(xsb.F_EP, ep)
+        ctx.chunk_neighbors(9.0)
+        ctx.pair_force([0.0104 * EV, 3.4], 8.0, xsb.FLAG_VIRIAL)          # allocates and fills the virial field
+        vir = ctx.download(xsb.F_VIRIAL)
+    masses = np.array([39.948, 63.546])
+    t = ctx.thermo_state(masses)
+    m = masses[gs.type[own]]
+    v = vel[gs.src_index[own]]
+    assert t["particle_count"] == own.sum() == len(pos)
+    assert t["mass"] == pytest.approx(m.sum(), rel=1e-13)
+    assert np.allclose(t["momentum"], (v * m[:, None]).sum(axis=0), rtol=0, atol=1e-9 * np.abs(v * m[:, None]).sum())
+    assert np.allclose(t["kinetic_energy"], 0.5 * (v * v * m[:, None]).sum(axis=0), rtol=1e-12)
+    ket = 0.5 * np.einsum("n,ni,nj->ij", m, v, v)
+    assert np.allclose(t["ke_tensor"], ket, rtol=0, atol=1e-12 * np.abs(ket).max())
+    assert t["potential_energy"] == pytest.approx(ep[own].sum(), abs=1e-10 * np.abs(ep).sum())
+    if virial:
+        ref = vir[own].sum(axis=0).reshape(3, 3)
+        assert np.allclose(t["virial"], ref, rtol=0, atol=1e-12 * np.abs(vir[own]).sum())
+    else:
+        assert not t["virial"].any()
+    t2 = ctx.thermo_state(masses)
+    assert all(np.array_equal(np.asarray(t[k]), np.asarray(t2[k])) for k in t)
