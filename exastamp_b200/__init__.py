@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
-    "xsb_thermo_state",
+    "xsb_thermo_state", "xsb_ghost_plan",
 ]
 
 
@@ -137,6 +137,7 @@ def load_library():
     L.xsb_backup_r.argtypes = [vp]
     L.xsb_particle_displ_over.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(dbl)]
     L.xsb_thermo_state.argtypes = [vp, i32, vp, vp]
+    L.xsb_ghost_plan.argtypes = [vp, i32, vp, vp, u64, vp]
     L.xsb_comm_unique_id.argtypes = [vp]
     L.xsb_comm_init.argtypes = [vp, i32, i32, vp]
     L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc)]
@@ -414,6 +415,24 @@ class Context:
     @property
     def n_own(self):
         return int(self.L.xsb_num_own_particles(self.h))
+
+
+def ghost_plan(global_cells, periodic, rank_dims, rank_coord, ghost_layers):
+    """receive list of one brick (host only, no GPU): int32 array [n, 6] = ghost_cell, owner_rank, owner_cell, wrap xyz"""
+    L = load_library()
+    d = DomainDesc()
+    d.global_cells[:] = [int(v) for v in global_cells]; d.periodic[:] = [int(v) for v in periodic]
+    d.rank_dims[:] = [int(v) for v in rank_dims]; d.rank_coord[:] = [int(v) for v in rank_coord]
+    rc = np.ascontiguousarray(rank_coord, dtype=np.int32)
+    n = C.c_uint64()
+    r = L.xsb_ghost_plan(C.byref(d), int(ghost_layers), _ptr(rc), None, 0, C.byref(n))
+    if r != 0:
+        raise XsbError("xsb_ghost_plan failed (%d)" % r)
+    out = np.zeros((max(1, n.value), 6), dtype=np.int32)
+    r = L.xsb_ghost_plan(C.byref(d), int(ghost_layers), _ptr(rc), _ptr(out), n.value, C.byref(n))
+    if r != 0:
+        raise XsbError("xsb_ghost_plan failed (%d)" % r)
+    return out[:n.value]
 
 
 def comm_unique_id():

@@ -342,6 +342,29 @@ int xsb_internal_allreduce_sum(xsb_ctx* ctx, double* dev_inout, int count)
 
 extern "C" {
 
+// host-only view of the exchange plan (no context, no GPU): the receive list of brick `rank_coord`, i.e. for every
+// ghost cell of its local grid that mirrors a domain cell: { ghost_cell, owner_rank, owner_cell (in the owner's local
+// grid), wrap_x, wrap_y, wrap_z }, sorted by owner rank.  xsb_ghost_comm_scheme derives both its receive list and
+// (from its peers' lists) its send lists from this function; tests drive it with gloo at world_size 2 on CPU.
+int xsb_ghost_plan(const xsb_domain_desc* dom, int ghost_layers, const int32_t* rank_coord, int32_t* out6, uint64_t capacity, uint64_t* count)
+{
+  if( !dom || !rank_coord || !count || ghost_layers < 1 ) return XSB_ERR_INVALID;
+  for(int a = 0; a < 3; a++)
+    if( dom->rank_dims[a] < 1 || rank_coord[a] < 0 || rank_coord[a] >= dom->rank_dims[a] || dom->global_cells[a] < dom->rank_dims[a] ) return XSB_ERR_INVALID;
+  std::vector<GhostCell> v;
+  const int rc[3] = { rank_coord[0], rank_coord[1], rank_coord[2] };
+  ghost_list(*dom, ghost_layers, rc, v);
+  *count = v.size();
+  if( !out6 ) return XSB_OK;
+  if( capacity < v.size() ) return XSB_ERR_OVERFLOW;
+  for(size_t i = 0; i < v.size(); i++)
+  {
+    int32_t* o = out6 + 6 * i;
+    o[0] = v[i].ghost_cell; o[1] = v[i].owner_rank; o[2] = v[i].owner_cell; o[3] = v[i].w[0]; o[4] = v[i].w[1]; o[5] = v[i].w[2];
+  }
+  return XSB_OK;
+}
+
 int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;

@@ -212,6 +212,10 @@ int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host);   /* MPI_Allreduce
 /* images, and r (shifted by the periodic box), v, type, id are copied owner -> ghost.  The particle count    */
 /* and cell offsets change: re-read them with xsb_num_particles / xsb_cell_offsets_download.                  */
 int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom);
+/* the exchange plan behind xsb_ghost_comm_scheme as a pure host function (no context, no GPU): receive list of the   */
+/* brick at rank_coord, 6 int32 per ghost cell { ghost_cell, owner_rank, owner_cell, wrap_x, wrap_y, wrap_z }, sorted  */
+/* by owner rank; out6 may be NULL to query *count.  A rank's send list to peer q = the entries of q's plan it owns.   */
+int xsb_ghost_plan(const xsb_domain_desc* dom, int ghost_layers, const int32_t* rank_coord, int32_t* out6, uint64_t capacity, uint64_t* count);
 /* ghost_update_r / ghost_update_opt: owner -> ghost copy of the fields in field_mask (bit = xsb_field)   */
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
 /* update_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29): ghost -> owner add                  */
