@@ -211,8 +211,7 @@ def run_xsb(args):
     def rebuild(first=False):
         ctx.sync(); t0 = time.perf_counter()
         if not first:
-            if world == 1:
-                ctx.particles_rebin()
+            ctx.particles_rebin()          # move_particles + migrate_cell_particles (cross-rank over NCCL when world > 1)
             ctx.ghost_comm_scheme()
         ctx.sync(); t1 = time.perf_counter()
         ctx.chunk_neighbors(RCUT + SKIN)

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
-    "xsb_thermo_state", "xsb_ghost_plan",
+    "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
 ]
 
 
@@ -138,6 +138,7 @@ def load_library():
     L.xsb_particle_displ_over.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(dbl)]
     L.xsb_thermo_state.argtypes = [vp, i32, vp, vp]
     L.xsb_ghost_plan.argtypes = [vp, i32, vp, vp, u64, vp]
+    L.xsb_migration_stats.argtypes = [vp, vp, vp]
     L.xsb_comm_unique_id.argtypes = [vp]
     L.xsb_comm_init.argtypes = [vp, i32, i32, vp]
     L.xsb_ghost_comm_scheme.argtypes = [vp, C.POINTER(DomainDesc)]
@@ -374,6 +375,11 @@ class Context:
 
     def particles_rebin(self):
         self._ck(self.L.xsb_particles_rebin(self.h, C.byref(self.domain)), "xsb_particles_rebin")
+
+    def migration_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.xsb_migration_stats(self.h, C.byref(a), C.byref(b)), "xsb_migration_stats")
+        return a.value, b.value
 
     def push_f_v_r(self, dt):
         self._ck(self.L.xsb_push_f_v_r(self.h, float(dt)), "xsb_push_f_v_r")

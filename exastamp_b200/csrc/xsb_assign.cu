@@ -156,7 +156,7 @@ using namespace xsb;
 
 // sort `n` particles given by device arrays into own cells and install them as the context's particle set
 // (ghost cells empty).  in_* are device pointers; they may alias nothing owned by ctx->f64[].
-static int assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry, double* rz, const double* vx, const double* vy, const double* vz,
+int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry, double* rz, const double* vx, const double* vy, const double* vz,
                          const unsigned char* type, const unsigned long long* id, const int wrap[3], const double box[3])
 {
   const unsigned nc = unsigned(ctx->ncells);
@@ -233,7 +233,7 @@ int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const doubl
   if( n && !id ) { iota64_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(unsigned(n), reinterpret_cast<unsigned long long*>(d[6])); ctx->launches++; }
   if( n && type ) { e = cudaMemcpyAsync(stt.p, type, n, cudaMemcpyHostToDevice, ctx->stream); if( e != cudaSuccess ) rc = ctx->fail(XSB_ERR_CUDA, "assign H2D: %s", cudaGetErrorString(e)); }
   if( rc == XSB_OK )
-    rc = assign_device(ctx, unsigned(n), d[0], d[1], d[2], vx ? d[3] : nullptr, vy ? d[4] : nullptr, vz ? d[5] : nullptr,
+    rc = xsb_internal_assign_device(ctx, unsigned(n), d[0], d[1], d[2], vx ? d[3] : nullptr, vy ? d[4] : nullptr, vz ? d[5] : nullptr,
                        type ? stt.p : nullptr, reinterpret_cast<unsigned long long*>(d[6]), nullptr, nullptr);
   cudaStreamSynchronize(ctx->stream);   // the caller's host arrays may die after the call
   return rc;
@@ -246,7 +246,8 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
   XSB_REQUIRE(ctx, dom != nullptr, XSB_ERR_INVALID, "null domain");
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
-  XSB_REQUIRE(ctx, dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2] == 1, XSB_ERR_UNSUPPORTED, "rebin: cross-rank migration is not implemented yet");
+  const int P = dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2];
+  XSB_REQUIRE(ctx, P == ctx->nranks, XSB_ERR_INVALID, "rank_dims product differs from the communicator size");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   const unsigned n = unsigned(ctx->n_own);
   // staging buffers persist in the context: steady-state rebuilds must not touch cudaMalloc/cudaFree
@@ -263,11 +264,31 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
     permute_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>(n, ctx->own_atoms.p, ctx->type.p, stt.p);
     ctx->launches += 8;
   }
-  const int wrap[3] = { dom->periodic[0], dom->periodic[1], dom->periodic[2] };
   ctx->prof_begin(XSB_PROF_MOVE);
-  int rc = assign_device(ctx, n, d[0], d[1], d[2], d[3], d[4], d[5], stt.p, reinterpret_cast<unsigned long long*>(d[6]), wrap, dom->box);
+  int rc;
+  if( P == 1 )
+  {
+    const int wrap[3] = { dom->periodic[0], dom->periodic[1], dom->periodic[2] };
+    rc = xsb_internal_assign_device(ctx, n, d[0], d[1], d[2], d[3], d[4], d[5], stt.p, reinterpret_cast<unsigned long long*>(d[6]), wrap, dom->box);
+  }
+  else
+  {
+    // migrate_cell_particles: particles whose (wrapped) position now belongs to another brick travel to that rank
+    unsigned n_new = 0; double* en[7]; unsigned char* tn = nullptr;
+    rc = xsb_internal_migrate(ctx, dom, n, d, stt.p, &n_new, en, &tn);
+    if( rc == XSB_OK )
+      rc = xsb_internal_assign_device(ctx, n_new, en[0], en[1], en[2], en[3], en[4], en[5], tn, reinterpret_cast<unsigned long long*>(en[6]), nullptr, nullptr);
+  }
   ctx->prof_end(XSB_PROF_MOVE);
   return rc;
+}
+
+int xsb_migration_stats(xsb_ctx* ctx, uint64_t* sent, uint64_t* received)
+{
+  if( !ctx ) return XSB_ERR_STATE;
+  if( sent ) *sent = ctx->migrated_out;
+  if( received ) *received = ctx->migrated_in;
+  return XSB_OK;
 }
 
 // ---- Verlet pieces ---------------------------------------------------------------------------------------------

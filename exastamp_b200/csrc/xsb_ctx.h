@@ -133,6 +133,8 @@ struct xsb_ctx
   xsb::DevBuf<unsigned> tmp32a, tmp32b, tmp32c, tmp32d;
   xsb::DevBuf<unsigned> gseg_send, gseg_recv, goff_send, goff_recv;   // ghost segment tables (device)
   xsb::DevBuf<double> move_stage; xsb::DevBuf<unsigned char> move_stage8;   // move_particles staging (persistent)
+  xsb::DevBuf<double> move_stage_b, move_stage_c; xsb::DevBuf<unsigned char> move_stage8_b, move_stage8_c;   // cross-rank migration
+  uint64_t migrated_out = 0, migrated_in = 0;   // particles that changed rank in the last xsb_particles_rebin
   xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
 
   // per-operator device timing (CUDA events on this context's stream), see xsb_profile_*
@@ -177,6 +179,11 @@ int  xsb_internal_ensure_virial(xsb_ctx* ctx);
 int  xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* cell_off);
 int  xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_cell_off);
 void xsb_ghost_release(xsb_ctx* ctx);
+int  xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry, double* rz, const double* vx, const double* vy, const double* vz,
+                                const unsigned char* type, const unsigned long long* id, const int wrap[3], const double box[3]);
+// cross-rank part of move_particles (xsb_ghost.cu): n staged particles in d[0..6] (+types) -> particles this rank owns now
+int  xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, double* const d[7], unsigned char* types,
+                          unsigned* n_new, double* e[7], unsigned char** types_new);
 void xsb_snap_release(xsb_ctx* ctx);
 
 namespace xsb

@@ -12,6 +12,7 @@
 #include "xsb_ctx.h"
 #include <algorithm>
 #include <dlfcn.h>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace xsb
 {
@@ -29,11 +30,12 @@ struct NcclApi
   int (*Send)(const void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
 static NcclApi g_nccl;
-static const int NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+static const int NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_MAX = 2, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 static bool nccl_load(std::string& why)
 {
@@ -45,7 +47,7 @@ static bool nccl_load(std::string& why)
   g_nccl.lib = h;
 # define XSB_SYM(name) *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name); if( !g_nccl.name ) { why = "missing symbol nccl" #name; return false; }
   XSB_SYM(GetUniqueId) XSB_SYM(CommInitRank) XSB_SYM(CommDestroy) XSB_SYM(GroupStart) XSB_SYM(GroupEnd) XSB_SYM(Send) XSB_SYM(Recv)
-  XSB_SYM(AllReduce) XSB_SYM(GetErrorString)
+  XSB_SYM(AllReduce) XSB_SYM(AllGather) XSB_SYM(GetErrorString)
 # undef XSB_SYM
   g_nccl.ok = true;
   return true;
@@ -286,6 +288,7 @@ void xsb_ghost_release(xsb_ctx* ctx)
     delete ctx->ghost; ctx->ghost = nullptr;
   }
   ctx->old_cell_start.release(); ctx->tmp64.release(); ctx->tmp32a.release(); ctx->tmp32b.release(); ctx->tmp32c.release(); ctx->tmp32d.release(); ctx->gseg_send.release(); ctx->gseg_recv.release(); ctx->goff_send.release(); ctx->goff_recv.release(); ctx->backup.release();
+  ctx->move_stage_b.release(); ctx->move_stage_c.release(); ctx->move_stage8_b.release(); ctx->move_stage8_c.release();
   if( ctx->comm && g_nccl.ok ) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
 }
 
@@ -330,6 +333,122 @@ int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host)
 }
 
 } // extern "C" (reopened below)
+
+// ---- migrate_cell_particles across ranks (config_move_particles.msp:89-96; impl ext exaNBody, MPI) --------------------
+namespace xsb
+{
+struct MigrateParams
+{
+  double g0[3], box[3], cell;     // grid-space corner of the global domain, its extent, cell edge
+  int periodic[3], gcells[3], rdims[3];
+};
+
+// wraps positions into the global box, finds the brick that owns the particle's cell
+__global__ void migrate_dest_kernel(unsigned n, MigrateParams M, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ rz,
+                                    unsigned* __restrict__ key, unsigned* __restrict__ val, unsigned long long* __restrict__ counts)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i >= n ) return;
+  double r[3] = { rx[i], ry[i], rz[i] };
+  int rk[3];
+# pragma unroll
+  for(int a = 0; a < 3; a++)
+  {
+    if( M.periodic[a] ) { r[a] -= floor((r[a] - M.g0[a]) / M.box[a]) * M.box[a]; if( r[a] - M.g0[a] >= M.box[a] ) r[a] = M.g0[a]; }
+    int c = int(floor((r[a] - M.g0[a]) / M.cell));
+    c = min(max(c, 0), M.gcells[a] - 1);
+    int q = int(((long long)(c + 1) * M.rdims[a] - 1) / M.gcells[a]);
+    while( q > 0 && int((long long)q * M.gcells[a] / M.rdims[a]) > c ) --q;
+    while( q + 1 < M.rdims[a] && int((long long)(q + 1) * M.gcells[a] / M.rdims[a]) <= c ) ++q;
+    rk[a] = q;
+  }
+  rx[i] = r[0]; ry[i] = r[1]; rz[i] = r[2];
+  const unsigned dest = unsigned(rk[0] + M.rdims[0] * (rk[1] + M.rdims[1] * rk[2]));
+  key[i] = dest; val[i] = i;
+  atomicAdd(&counts[dest], 1ull);
+}
+
+template<class T> __global__ void migrate_gather_kernel(unsigned n, const unsigned* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if( i < n ) dst[i] = src[perm[i]];
+}
+} // namespace xsb
+
+int xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, double* const d[7], unsigned char* types,
+                         unsigned* n_new, double* e[7], unsigned char** types_new)
+{
+  const int P = ctx->nranks, me = ctx->rank;
+  XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "multi-rank move_particles needs xsb_comm_init");
+  XSB_REQUIRE(ctx, P <= 64, XSB_ERR_UNSUPPORTED, "more than 64 ranks");
+  const xsb_grid_desc& g = ctx->grid;
+  MigrateParams M;
+  for(int a = 0; a < 3; a++)
+  {
+    M.g0[a] = g.origin[a] + g.ghost_layers * g.cell_size - block_start(dom->rank_coord[a], dom->global_cells[a], dom->rank_dims[a]) * g.cell_size;
+    M.box[a] = dom->global_cells[a] * g.cell_size; M.periodic[a] = dom->periodic[a]; M.gcells[a] = dom->global_cells[a]; M.rdims[a] = dom->rank_dims[a];
+  }
+  M.cell = g.cell_size;
+  XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, 1.02));
+  XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32d.reserve(n + 16, 1.02));
+  unsigned *key = ctx->tmp32a.p, *val = ctx->tmp32b.p, *key2 = ctx->tmp32c.p, *perm = ctx->tmp32d.p;
+  XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(P) * (P + 1) + 16));
+  unsigned long long* counts = ctx->scratch64.p;            // [P] mine, then [P][P] gathered
+  unsigned long long* mat = counts + P;
+  XSB_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * size_t(P) * (P + 1), ctx->stream));
+  const unsigned grid = (n + 255) / 256;
+  if( n )
+  {
+    migrate_dest_kernel<<<grid, 256, 0, ctx->stream>>>(n, M, d[0], d[1], d[2], key, val, counts);
+    XSB_LAUNCH_CHECK(ctx);
+    int end_bit = 1; while( (1 << end_bit) < P ) ++end_bit;
+    size_t tmp = 0;
+    XSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, val, perm, int(n), 0, end_bit, ctx->stream));
+    XSB_CUDA(ctx, ctx->scratch.reserve(tmp + 16));
+    XSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->scratch.p, tmp, key, key2, val, perm, int(n), 0, end_bit, ctx->stream));   // stable
+    ctx->launches += 3;
+  }
+  XSB_NCCL(ctx, g_nccl.AllGather(counts, mat, size_t(P), NCCL_UINT64, ctx->comm, ctx->stream));
+  std::vector<unsigned long long> hm(size_t(P) * P);
+  XSB_CUDA(ctx, cudaMemcpyAsync(hm.data(), mat, hm.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<size_t> soff(P + 1, 0), roff(P + 1, 0);
+  for(int q = 0; q < P; q++) { soff[q + 1] = soff[q] + size_t(hm[size_t(me) * P + q]); roff[q + 1] = roff[q] + size_t(hm[size_t(q) * P + me]); }
+  XSB_REQUIRE(ctx, soff[P] == n, XSB_ERR_STATE, "migrate: destination counts do not add up");
+  const size_t nn = roff[P];
+  XSB_REQUIRE(ctx, nn < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU after migration");
+  // sorted-by-destination copies, then the receive arrays (segment q = particles arriving from rank q, self included)
+  XSB_CUDA(ctx, ctx->move_stage_b.reserve(7 * (size_t(n) + 1), 1.02)); XSB_CUDA(ctx, ctx->move_stage8_b.reserve(size_t(n) + 16, 1.02));
+  XSB_CUDA(ctx, ctx->move_stage_c.reserve(7 * (nn + 1), 1.05)); XSB_CUDA(ctx, ctx->move_stage8_c.reserve(nn + 16, 1.05));
+  double* s[7]; for(int k = 0; k < 7; k++) { s[k] = ctx->move_stage_b.p + size_t(k) * (n + 1); e[k] = ctx->move_stage_c.p + size_t(k) * (nn + 1); }
+  unsigned char* st8 = ctx->move_stage8_b.p; unsigned char* et8 = ctx->move_stage8_c.p;
+  if( n )
+  {
+    for(int k = 0; k < 7; k++) migrate_gather_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(n, perm, reinterpret_cast<const unsigned long long*>(d[k]), reinterpret_cast<unsigned long long*>(s[k]));
+    migrate_gather_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>(n, perm, types, st8);
+    ctx->launches += 8; cudaError_t le = cudaGetLastError(); if( le != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "migrate gather: %s", cudaGetErrorString(le));
+  }
+  const size_t stay = soff[me + 1] - soff[me];
+  for(int k = 0; k < 7 && stay; k++) XSB_CUDA(ctx, cudaMemcpyAsync(e[k] + roff[me], s[k] + soff[me], stay * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if( stay ) XSB_CUDA(ctx, cudaMemcpyAsync(et8 + roff[me], st8 + soff[me], stay, cudaMemcpyDeviceToDevice, ctx->stream));
+  XSB_NCCL(ctx, g_nccl.GroupStart());
+  for(int q = 0; q < P; q++)
+  {
+    if( q == me ) continue;
+    const size_t sc = soff[q + 1] - soff[q], rcnt = roff[q + 1] - roff[q];
+    for(int k = 0; k < 7; k++)
+    {
+      if( sc ) XSB_NCCL(ctx, g_nccl.Send(s[k] + soff[q], sc, NCCL_UINT64, q, ctx->comm, ctx->stream));
+      if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(e[k] + roff[q], rcnt, NCCL_UINT64, q, ctx->comm, ctx->stream));
+    }
+    if( sc ) XSB_NCCL(ctx, g_nccl.Send(st8 + soff[q], sc, NCCL_UINT8, q, ctx->comm, ctx->stream));
+    if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(et8 + roff[q], rcnt, NCCL_UINT8, q, ctx->comm, ctx->stream));
+  }
+  XSB_NCCL(ctx, g_nccl.GroupEnd());
+  ctx->migrated_out = n - stay; ctx->migrated_in = nn - stay;
+  *n_new = unsigned(nn); *types_new = et8;
+  return XSB_OK;
+}
 
 // sum-allreduce of `count` doubles in device memory (thermodynamic state: the reference's MPI_Allreduce(SUM))
 int xsb_internal_allreduce_sum(xsb_ctx* ctx, double* dev_inout, int count)

@@ -221,9 +221,11 @@ int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
 /* update_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29): ghost -> owner add                  */
 int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask);
 
-/* move_particles (config_move_particles.msp:121-125) for a single rank: wrap into the periodic box,     */
-/* re-bin own particles into cells; ghost cells are emptied (call xsb_ghost_comm_scheme next).           */
+/* move_particles + migrate_cell_particles (config_move_particles.msp:89-96,121-125): wrap into the periodic box,   */
+/* send every own particle whose cell now belongs to another brick to that rank (NCCL P2P, any distance), re-bin     */
+/* into cells; ghost cells are emptied (call xsb_ghost_comm_scheme next).  Collective over the communicator.         */
 int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom);
+int xsb_migration_stats(xsb_ctx* ctx, uint64_t* sent, uint64_t* received);   /* of the last xsb_particles_rebin */
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* "next" rows: the per-particle operators either side of the force path               */

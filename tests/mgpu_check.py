@@ -125,6 +125,26 @@ def main():
     ctx.pair_force([0.0104 * EV, 3.4], rc_lj)
     collect("lj_moved", {"fx": xsb.F_FX, "ep": xsb.F_EP})
     results["dmax"] = dmax
+    # --- move_particles + migrate_cell_particles: a large random move sends many particles to other bricks (and across
+    #     the periodic boundary); after rebin + ghost scheme + list rebuild the forces must match a fresh oracle run
+    big = np.random.default_rng(200).uniform(-4.0, 4.0, pos.shape)
+    big[::7] += np.array([box[0] * 0.5, 0.0, 0.0])            # some travel half the box: arbitrary-distance migration
+    for k, f in enumerate((xsb.F_RX, xsb.F_RY, xsb.F_RZ)):
+        cur = ctx.download(f)
+        cur[own] = cur[own] + big[idl[own], k]
+        ctx.upload(f, cur)
+    n_before = ctx.n_own
+    ctx.particles_rebin()
+    sent, received = ctx.migration_stats()
+    ctx.ghost_comm_scheme()
+    ctx.chunk_neighbors(nbh)
+    own2 = own_mask(ctx, dims, 1)
+    assert own2.sum() == ctx.n_own == n_before - sent + received
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_force([0.0104 * EV, 5.5], rc_lj)                 # soft, wide LJ: random overlaps stay finite-ish
+    results["migrated"] = {"id": ctx.download(xsb.F_ID)[own2], "fx": ctx.download(xsb.F_FX)[own2], "ep": ctx.download(xsb.F_EP)[own2],
+                           "vx": ctx.download(xsb.F_VX)[own2], "type": ctx.download(xsb.F_TYPE)[own2], "rx": ctx.download(xsb.F_RX)[own2]}
+    results["migration"] = (sent, received, n_before, ctx.n_own)
 
     gathered = [None] * world
     dist.all_gather_object(gathered, results)
@@ -188,6 +208,24 @@ def main():
     r2 = np.zeros(len(pos)); r2[gs2.src_index[o2]] = f2[o2]
     e2a = np.zeros(len(pos)); e2a[gs2.src_index[o2]] = e2[o2]
     check("lj_moved", "fx", r2); check("lj_moved", "ep", e2a)
+    # migration: nothing lost, velocities and types travelled with their particle, forces equal a fresh oracle build
+    sent_tot = sum(r["migration"][0] for r in gathered); recv_tot = sum(r["migration"][1] for r in gathered)
+    assert sent_tot == recv_tot and sent_tot > 100, (sent_tot, recv_tot)
+    assert sum(r["migration"][3] for r in gathered) == len(pos)
+    assert np.array_equal(merged("migrated", "vx"), vel[:, 0]) and np.array_equal(merged("migrated", "type"), typ.astype(np.float64))
+    pos3 = np.mod(newpos + big, box)
+    pos3 = np.where(pos3 >= box, 0.0, pos3)
+    assert np.max(np.abs(np.mod(merged("migrated", "rx") - pos3[:, 0] + 0.5 * box[0], box[0]) - 0.5 * box[0])) < 1e-9
+    gs3 = GridSystem(pos3, typ, box, cell, 1)
+    g3 = gs3.oracle_grid()
+    nb3 = O.Neighbors.build(g3, gs3.cell_off, gs3.rx, gs3.ry, gs3.rz, nbh, 1, True)
+    f3, e3 = gs3.zeros(), gs3.zeros()
+    O.pair_force(g3, gs3.cell_off, gs3.rx, gs3.ry, gs3.rz, nb3, [0.0104 * EV, 5.5], rc_lj, 0, f3, gs3.zeros(), gs3.zeros(), e3, None)
+    o3 = ~gs3.is_ghost
+    r3 = np.zeros(len(pos)); r3[gs3.src_index[o3]] = f3[o3]
+    e3a = np.zeros(len(pos)); e3a[gs3.src_index[o3]] = e3[o3]
+    check("migrated", "fx", r3); check("migrated", "ep", e3a)
+    print("  migration: %d particles changed rank" % sent_tot)
     dm = max(r["dmax"] for r in gathered)
     assert all(abs(r["dmax"] - dm) < 1e-15 for r in gathered), "particle_displ_over: ranks disagree on the allreduced maximum"
     assert abs(dm - np.sqrt((d ** 2).sum(axis=1)).max()) < 1e-9
