@@ -99,6 +99,95 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
   }
 }
 
+// Tile variant of the sweep (used whenever the tile path serves the grid, i.e. search range <= 2 cells in y/z): one CTA per
+// tile (= cell) stages the 27-cell block once in shared memory (coalesced row copies) and its warps take the tile's
+// atoms in turn; every candidate test reads the stage, and the FILL pass emits the uint16 stage index (what the force
+// kernels stream) and the u32 flat index (CSR view for the exporter / SNAP) in one go -- no separate conversion pass.
+// Same membership arithmetic (nbh_d2) and the same traversal order as nbr_sweep_kernel, so the lists are identical.
+template<bool XFORM, bool FILL>
+__global__ void __launch_bounds__(256) nbr_tile_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
+                                                        const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                                        unsigned* __restrict__ counts, const unsigned long long* __restrict__ off,
+                                                        unsigned* __restrict__ idx32, unsigned short* __restrict__ idx16, unsigned long long* __restrict__ d2min_bits)
+{
+  extern __shared__ __align__(16) unsigned char nbr_smem[];
+  __shared__ TileMeta M;
+  __shared__ unsigned vb[TILE_MAX_ROWS], ve[TILE_MAX_ROWS];     // valid (un-widened) part of each staged row, stage-relative to s0
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
+  if( warp == 0 )
+  {
+    tile_meta_compute(G, cell_start, ti, j, k, M);
+    const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX);
+    const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
+    if( int(lane) < nrows )
+    {
+      unsigned b = 0, e = 0;
+      const int kk = k + int(lane) / nry - G.Rz, jj = j + int(lane) % nry - G.Ry;
+      if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz )
+      {
+        const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
+        const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
+        if( ge > gb ) { b = gb - (gb & ~1u); e = ge - (gb & ~1u); }
+      }
+      vb[lane] = b; ve[lane] = e;
+    }
+  }
+  __syncthreads();
+  const unsigned S = M.S, nrows = M.nrows;
+  if( M.a_begin == M.a_end ) return;
+  double* sx = reinterpret_cast<double*>(nbr_smem); double* sy = sx + G.s_cap; double* sz = sy + G.s_cap;
+  for(unsigned r = warp; r < nrows; r += nwarps)
+  {
+    const unsigned s0 = M.s0[r], len = M.s0[r + 1] - s0, g0 = M.g0[r];
+    for(unsigned t = lane; t < len; t += 32u) { sx[s0 + t] = rx[g0 + t]; sy[s0 + t] = ry[g0 + t]; sz[s0 + t] = rz[g0 + t]; }
+  }
+  __syncthreads();
+  (void)S;
+  double dmin = 1.0e300;
+  for(unsigned a = M.a_begin + warp; a < M.a_end; a += nwarps)
+  {
+    const unsigned sa = a + M.c_off;
+    const double xa = sx[sa], ya = sy[sa], za = sz[sa];
+    unsigned cnt = 0;
+    unsigned long long w = FILL ? off[a] : 0ull;
+    for(unsigned r = 0; r < nrows; r++)
+    {
+      const unsigned s0 = M.s0[r], e = s0 + ve[r], g0 = M.g0[r];
+      for(unsigned base = s0 + vb[r]; base < e; base += 32u)
+      {
+        const unsigned sidx = base + lane;
+        bool keep = false;
+        if( sidx < e && sidx != sa )
+        {
+          const double d2 = nbh_d2<XFORM>(gv, sx[sidx] - xa, sy[sidx] - ya, sz[sidx] - za);
+          keep = d2 > 0.0 && d2 < d2max;
+          if( !FILL && keep ) dmin = fmin(dmin, d2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if( FILL )
+        {
+          if( keep )
+          {
+            const unsigned long long o = w + __popc(m & ((1u << lane) - 1u));
+            idx16[o] = (unsigned short)sidx;
+            idx32[o] = g0 + (sidx - s0);
+          }
+          w += __popc(m);
+        }
+        else cnt += __popc(m);
+      }
+    }
+    if( !FILL && lane == 0 ) counts[a] = cnt;
+  }
+  if( !FILL )
+  {
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if( lane == 0 && dmin < 1.0e300 && (unsigned long long)__double_as_longlong(dmin) < *d2min_bits ) atomicMin(d2min_bits, (unsigned long long)__double_as_longlong(dmin));
+  }
+}
+
 // CSR (flat u32 neighbour index) -> tile list (u16 index into the stage of the central atom's tile), warp per atom
 __global__ void __launch_bounds__(256) tile_convert_kernel(TileGeom G, unsigned n, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_of,
                                                            const unsigned long long* __restrict__ off, const unsigned* __restrict__ idx32,
@@ -288,8 +377,29 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   int R[3]; search_range(ctx->grid, nbh_dist_lab, R); P.Rx = R[0]; P.Ry = R[1]; P.Rz = R[2];
   const int block = 256; const unsigned grid = unsigned((uint64_t(n) * 32 + block - 1) / block);
   const double *rx = ctx->f64[XSB_F_RX].p, *ry = ctx->f64[XSB_F_RY].p, *rz = ctx->f64[XSB_F_RZ].p;
-  if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
-  else                     nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
+  // tile path: the same fixed tiling the force kernels use; one CTA per tile with its 27-cell block staged in shared memory
+  TileGeom TG; unsigned s_cap = 0;
+  const bool tile = tile_plan(ctx, R, TG, s_cap);
+  size_t tile_smem = 0;
+  if( tile )
+  {
+    TG.ghost = 1; TG.ti_lo = 0; TG.ti_n = TG.tiles_x; TG.j_lo = 0; TG.j_n = TG.ny; TG.k_lo = 0; TG.k_n = TG.nz;
+    TG.ntiles = unsigned(TG.ti_n) * unsigned(TG.j_n) * unsigned(TG.k_n); TG.nbuf = 1;
+    tile_smem = size_t(s_cap) * 24;
+    static bool attr_done = false;
+    if( !attr_done )
+    {
+      cudaFuncSetAttribute(nbr_tile_kernel<false,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(nbr_tile_kernel<true ,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(nbr_tile_kernel<false,true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(nbr_tile_kernel<true ,true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_done = true;
+    }
+    if( P.g.xform_identity ) nbr_tile_kernel<false,false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, nullptr, d2min);
+    else                     nbr_tile_kernel<true ,false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, nullptr, d2min);
+  }
+  else if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
+  else                          nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
   XSB_LAUNCH_CHECK(ctx);
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->scratch64.p + n, 0, sizeof(unsigned long long), ctx->stream));
   widen_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->nbh_count.p, ctx->scratch64.p);
@@ -308,21 +418,20 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->nbh_total = total;
   XSB_CUDA(ctx, ctx->nbh_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-  if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
-  else                     nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
+  if( tile )
+  {
+    // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh) and the CSR view, written together
+    XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+    if( P.g.xform_identity ) nbr_tile_kernel<false,true><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p, nullptr);
+    else                     nbr_tile_kernel<true ,true><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p, nullptr);
+  }
+  else if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
+  else                          nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
   XSB_LAUNCH_CHECK(ctx);
-  // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh)
   {
     unsigned long long bits = 0;
     XSB_CUDA(ctx, cudaMemcpyAsync(&bits, d2min, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
-    TileGeom G; unsigned s_cap = 0;
-    const bool ok = tile_plan(ctx, R, G, s_cap);
-    if( ok )
-    {
-      XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-      tile_convert_kernel<<<(n + 7) / 8, 256, 0, ctx->stream>>>(G, n, ctx->cell_start.p, ctx->cell_of.p, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p);
-      XSB_LAUNCH_CHECK(ctx);
-    }
+    const TileGeom& G = TG; const bool ok = tile;
     XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double d2 = 0.0; if( bits != ~0ull ) std::memcpy(&d2, &bits, sizeof(d2));
     ctx->nbh_d2min = d2;
