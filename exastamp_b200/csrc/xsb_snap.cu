@@ -17,6 +17,7 @@
 // (1/3) 2 sum_half Re(conj(Utot) Y) -- no separate Z/B pass.
 #include "xsb_ctx.h"
 #include "xsb_traverse.cuh"
+#include "xsb_tile.cuh"
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -45,6 +46,9 @@ struct SnapDev
   SnapConst K{};
   DevBuf<SnapZ> idxz; DevBuf<double> cglist; DevBuf<double> betaz;   // betaz[elem][jjz]: beta_k with the multiplicity / (j1+1)/(j+1) factors of compute_yi
   DevBuf<int> err;
+  DevBuf<unsigned long long> clk; bool clocks = false;
+  DevBuf<SnapZ> zsort; DevBuf<double> betaz_sort; DevBuf<int4> ytask; int n_ytask = 0;   // snap_y_kernel work items
+  DevBuf<double2> ubuf, ybuf;                                                          // chunk staging (AoSoA)
   double rcut_max = 0.0;
 };
 
@@ -242,9 +246,15 @@ struct SnapArgs
   const unsigned* __restrict__ atoms; unsigned n_atoms;
   const SnapZ* __restrict__ idxz; const double* __restrict__ cglist; const double* __restrict__ betaz;
   double *fx, *fy, *fz, *ep, *vir; int* err;
+  unsigned long long* clk;     // optional per-phase cycle counters (tools/snap_bench.py --clocks), nullptr in production
+  // split pipeline (snap_u -> snap_y -> snap_f): Utot and Y of the atoms of one chunk, AoSoA [atom / 32][jju][atom % 32]
+  double2* ubuf; double2* ybuf; unsigned base;      // base = first central atom (position in the launch's atom list) of the chunk
+  const SnapZ* __restrict__ zsort; const double* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
 };
 
-template<int TJ, bool XFORM>
+// PHASE 0: fused (everything in one CTA, kept for reference / small runs); PHASE 1: Utot only -> A.ubuf; PHASE 3: reads Utot
+// and Y of its atom back from A.ubuf / A.ybuf, then energy + force sweep.
+template<int TJ, bool XFORM, int PHASE>
 __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const SnapArgs A, const XForm X, const SnapConst K)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
@@ -259,14 +269,25 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32][3] + scratch
   __shared__ unsigned s_nn;
   const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
-  const unsigned ai = A.atoms ? A.atoms[blockIdx.x] : blockIdx.x;
+  const unsigned slot = A.base + blockIdx.x;
+  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
+  const size_t soa = (size_t(blockIdx.x >> 5) * K.idxu_max) * 32 + (blockIdx.x & 31u);    // + jju * 32
   const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
   const int ei = A.type ? A.type[ai] : 0;
 
+  long long tc = A.clk ? clock64() : 0;
+  auto mark = [&](int ph) { if( A.clk && tid == 0 ) { const long long t = clock64(); atomicAdd(A.clk + ph, (unsigned long long)(t - tc)); tc = t; } };
   // ---- Utot = wself on the diagonal, Y = 0
-  for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = make_double2(0.0, 0.0); ylist[k] = make_double2(0.0, 0.0); }
-  __syncthreads();
-  for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
+  if( PHASE != 3 )
+  {
+    for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = make_double2(0.0, 0.0); ylist[k] = make_double2(0.0, 0.0); }
+    __syncthreads();
+    for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
+  }
+  else
+  {
+    for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = A.ubuf[soa + size_t(k) * 32]; ylist[k] = A.ybuf[soa + size_t(k) * 32]; }
+  }
 
   // ---- neighbour filter (warp 0, ballot compaction keeps the list order): rsq < cutsq_ij && rsq > 1e-20
   if( mb == 0 )
@@ -296,9 +317,11 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   }
   __syncthreads();
   const unsigned nn = s_nn;
+  mark(0);
 
   // ---- sweep 1: Utot
   double dummy[3];
+  if( PHASE != 3 )
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
@@ -306,7 +329,9 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     snap_sweep<TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * 4 * (MB ? MB : 1), dummy);
   }
   __syncthreads();
+  mark(1);
   // right half by inversion symmetry u[j-mb][j-ma] = (-1)^(mb+ma) conj(u[mb][ma]); middle row: second half from the first
+  if( PHASE != 3 )
   for(int j = 1; j <= TJ; j++)
   {
     const int jb = K.idxu_block[j], half = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 : 0);   // elements strictly before the mirror centre
@@ -320,8 +345,15 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   }
   __syncthreads();
 
+  mark(2);
+  if( PHASE == 1 )
+  {
+    for(int k = tid; k < K.idxu_max; k += NT) A.ubuf[soa + size_t(k) * 32] = utot[k];
+    return;
+  }
   // ---- Y = sum over idxz of betaj * Z  (compute_yi), shared-memory accumulation
   const double* betaz = A.betaz + size_t(ei) * K.idxz_max;
+  if( PHASE == 0 )
   for(int jjz = int(tid); jjz < K.idxz_max; jjz += NT)
   {
     const SnapZ q = A.idxz[jjz];
@@ -349,6 +381,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   }
   __syncthreads();
 
+  mark(3);
   // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
   if( A.ep )
   {
@@ -370,6 +403,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     __syncthreads();
   }
 
+  mark(4);
   // ---- sweep 2: dU/dr contracted with Y -> fij ; f_i += fij, f_j -= fij, virial -fij (x) rij on the centre
   double fix = 0.0, fiy = 0.0, fiz = 0.0, v[9];
 # pragma unroll
@@ -413,6 +447,76 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
       atomicAdd(A.fx + ai, fix); atomicAdd(A.fy + ai, fiy); atomicAdd(A.fz + ai, fiz);
       if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += v[k]; }
     }
+  }
+  mark(5);
+}
+
+// ---- compute_yi for 32 atoms at a time: lane = atom -------------------------------------------------------------------
+// One CTA owns one AoSoA block of 32 central atoms: their Utot (idxu_max x 32 complex doubles, 146 KB at 2J = 8) arrives
+// in shared memory with ONE TMA bulk copy, every warp-wide U access is then 32 consecutive 16-byte words (conflict-free),
+// and all index / Clebsch-Gordan bookkeeping is warp-uniform.  Work items are the distinct Y elements (jju) with the
+// list of idxz entries that feed them (sorted by cost, handed out through a shared counter), so each Y element has one
+// writer: no atomics, no zero-fill.
+template<int TJ>
+__global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgs A, const SnapConst K)
+{
+  extern __shared__ __align__(128) unsigned char ysm[];
+  double2* U = reinterpret_cast<double2*>(ysm);                  // [idxu_max][32]
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int next_task;
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const size_t blk = size_t(blockIdx.x) * K.idxu_max * 32;
+  if( tid == 0 ) { mbar_init(&bar, 1); mbar_fence_init(); next_task = 0; }
+  __syncthreads();
+  if( tid == 0 )
+  {
+    const unsigned bytes = unsigned(K.idxu_max) * 32u * 16u;
+    mbar_arrive_expect_tx(&bar, bytes);
+    bulk_g2s(U, A.ubuf + blk, bytes, &bar);
+  }
+  // element of this lane's atom (selects the beta row); lanes past the end of the atom list compute on stale data and
+  // write into the padding of ybuf
+  const unsigned slot = A.base + blockIdx.x * 32u + lane;
+  int ei = 0;
+  if( A.type && slot < A.n_atoms ) ei = A.type[A.atoms ? A.atoms[slot] : slot];
+  const double* betaz = A.betaz_sort + size_t(ei) * K.idxz_max;
+  mbar_wait(&bar, 0);
+  for(;;)
+  {
+    int t = 0;
+    if( lane == 0 ) t = atomicAdd(&next_task, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if( t >= A.n_ytask ) break;
+    const int4 task = A.ytask[t];                      // x = jju, y = first entry in zsort, z = entry count
+    double yr = 0.0, yi = 0.0;
+    for(int e = task.y; e < task.y + task.z; e++)
+    {
+      const SnapZ q = A.zsort[e];
+      const double* cg = A.cglist + q.cgoff;
+      double zr = 0.0, zi = 0.0;
+      int jju1 = K.idxu_block[q.j1] + (q.j1 + 1) * q.mb1min, jju2 = K.idxu_block[q.j2] + (q.j2 + 1) * q.mb2max, icgb = q.mb1min * (q.j2 + 1) + q.mb2max;
+      for(int ib = 0; ib < q.nb; ib++)
+      {
+        double sr = 0.0, si = 0.0;
+        const double2* u1p = U + size_t(jju1 + q.ma1min) * 32 + lane;
+        const double2* u2p = U + size_t(jju2 + q.ma2max) * 32 + lane;
+        int icga = q.ma1min * (q.j2 + 1) + q.ma2max;
+        for(int ia = 0; ia < q.na; ia++)
+        {
+          const double2 u1 = *u1p, u2 = *u2p;
+          const double c = __ldg(cg + icga);
+          sr += c * (u1.x * u2.x - u1.y * u2.y);
+          si += c * (u1.x * u2.y + u1.y * u2.x);
+          u1p += 32; u2p -= 32; icga += q.j2;
+        }
+        const double c = __ldg(cg + icgb);
+        zr += c * sr; zi += c * si;
+        jju1 += q.j1 + 1; jju2 -= q.j2 + 1; icgb += q.j2;
+      }
+      const double bj = __ldg(betaz + e);
+      yr += bj * zr; yi += bj * zi;
+    }
+    A.ybuf[blk + size_t(task.x) * 32 + lane] = make_double2(yr, yi);
   }
 }
 
@@ -484,24 +588,52 @@ void xsb_snap_release(xsb_ctx* ctx)
   auto it = g_snap.find(ctx);
   if( it == g_snap.end() ) return;
   it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
+  it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->clk.release();
   delete it->second; g_snap.erase(it);
 }
 
+constexpr unsigned SNAP_CHUNK = 65536;     // central atoms per pass of the split pipeline (Utot + Y staging: 2 x 285 x 16 B per atom)
+
 template<int TJ>
-static int snap_launch(xsb_ctx* ctx, SnapDev* S, const SnapArgs& A)
+static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR, MB = (TJ / 2) * (TJ / 2 + 1);
   const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * 4 * (MB ? MB : 1) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
                     + size_t(NR) * 32 * 3 * sizeof(double) + 64;
   const XForm X = make_xform(ctx->grid);
-  auto go = [&](auto kern) -> int
+  const bool xf = !ctx->grid.xform_is_identity;
+  const size_t ysmem = size_t(S->K.idxu_max) * 32 * sizeof(double2);
+  const bool fused = getenv("XSB_SNAP_FUSED") != nullptr;        // development switch: the single-kernel version
+  auto setattr = [&](auto kern, size_t bytes) -> int { XSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); return XSB_OK; };
+  int rc;
+  if( fused )
   {
-    XSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K);
+    if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 0>, smem)) ) return rc; snap_force_kernel<TJ, true, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K); }
+    else     { if( (rc = setattr(snap_force_kernel<TJ, false, 0>, smem)) ) return rc; snap_force_kernel<TJ, false, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K); }
     XSB_LAUNCH_CHECK(ctx);
     return XSB_OK;
-  };
-  return ctx->grid.xform_is_identity ? go(snap_force_kernel<TJ, false>) : go(snap_force_kernel<TJ, true>);
+  }
+  const unsigned chunk = std::min(A.n_atoms, SNAP_CHUNK);
+  const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
+  XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
+  A.ubuf = S->ubuf.p; A.ybuf = S->ybuf.p;
+  if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, true, 3>, smem)) ) return rc; }
+  else     { if( (rc = setattr(snap_force_kernel<TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, false, 3>, smem)) ) return rc; }
+  if( (rc = setattr(snap_y_kernel<TJ>, ysmem)) ) return rc;
+  for(unsigned base = 0; base < A.n_atoms; base += chunk)
+  {
+    const unsigned cnt = std::min(chunk, A.n_atoms - base);
+    A.base = base;
+    if( xf ) snap_force_kernel<TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    else     snap_force_kernel<TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    XSB_LAUNCH_CHECK(ctx);
+    snap_y_kernel<TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, S->K);
+    XSB_LAUNCH_CHECK(ctx);
+    if( xf ) snap_force_kernel<TJ, true, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    else     snap_force_kernel<TJ, false, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  return XSB_OK;
 }
 
 extern "C" {
@@ -547,6 +679,33 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
   XSB_CUDA(ctx, cudaMemcpyAsync(S->cglist.p, T.cglist.data(), T.cglist.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz.p, betaz.data(), betaz.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, 4 * sizeof(int), ctx->stream));
+  // snap_y_kernel work items: one per distinct Y element, with the idxz entries that feed it; most expensive first
+  std::vector<int4> tasks; std::vector<SnapZ> zsort; std::vector<double> bsort(betaz.size());
+  {
+    std::vector<int> order(T.idxz.size());
+    for(size_t i = 0; i < order.size(); i++) order[i] = int(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return T.idxz[a].jju < T.idxz[b].jju; });
+    std::vector<std::pair<long, int4>> tmp;
+    for(size_t i = 0; i < order.size(); )
+    {
+      size_t e = i; long cost = 0;
+      while( e < order.size() && T.idxz[order[e]].jju == T.idxz[order[i]].jju ) { cost += long(T.idxz[order[e]].na) * T.idxz[order[e]].nb + 4; ++e; }
+      tmp.push_back({ cost, make_int4(int(T.idxz[order[i]].jju), int(i), int(e - i), 0) });
+      i = e;
+    }
+    std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<long, int4>& a, const std::pair<long, int4>& b) { return a.first > b.first; });
+    for(auto& t : tmp) tasks.push_back(t.second);
+    for(size_t i = 0; i < order.size(); i++)
+    {
+      zsort.push_back(T.idxz[order[i]]);
+      for(int e = 0; e < p->nelements; e++) bsort[size_t(e) * order.size() + i] = betaz[size_t(e) * order.size() + order[i]];
+    }
+  }
+  S->n_ytask = int(tasks.size());
+  XSB_CUDA(ctx, S->zsort.reserve(zsort.size())); XSB_CUDA(ctx, S->betaz_sort.reserve(bsort.size())); XSB_CUDA(ctx, S->ytask.reserve(tasks.size()));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->zsort.p, zsort.data(), zsort.size() * sizeof(SnapZ), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz_sort.p, bsort.data(), bsort.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->ytask.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   S->set = true;
   return XSB_OK;
@@ -567,7 +726,8 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   SnapArgs A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, S->K.nelements > 1 ? ctx->type.p : nullptr, ctx->nbh_off.p, ctx->nbh_idx.p,
               ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own), S->idxz.p, S->cglist.p, S->betaz.p,
               ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr,
-              virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr, S->err.p };
+              virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr, S->err.p, S->clocks ? S->clk.p : nullptr,
+              nullptr, nullptr, 0u, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
   if( A.n_atoms == 0 ) return XSB_OK;
   int rc = XSB_ERR_UNSUPPORTED;
   ctx->prof_begin(XSB_PROF_SNAP);
@@ -581,6 +741,17 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   }
   ctx->prof_end(XSB_PROF_SNAP);
   return rc;
+}
+
+// development aid (not part of the ABI header): per-phase cycle sums of the snap kernel, summed over CTAs
+extern "C" int xsbdbg_snap_clocks(xsb_ctx* ctx, int enable, unsigned long long* out8)
+{
+  SnapDev* S = g_snap_of(ctx);
+  if( !S ) return XSB_ERR_STATE;
+  if( enable && !S->clocks ) { if( S->clk.reserve(8) != cudaSuccess ) return XSB_ERR_CUDA; cudaMemsetAsync(S->clk.p, 0, 64, ctx->stream); S->clocks = true; }
+  if( out8 && S->clocks ) { cudaMemcpyAsync(out8, S->clk.p, 64, cudaMemcpyDeviceToHost, ctx->stream); cudaStreamSynchronize(ctx->stream); cudaMemsetAsync(S->clk.p, 0, 64, ctx->stream); }
+  if( !enable ) S->clocks = false;
+  return XSB_OK;
 }
 
 // 1 when some atom had more than SNAP_NN_MAX in-range neighbours since the last call (forces are then incomplete)

@@ -22,6 +22,14 @@ def main(nc=63, twoj=8, reps=5):
     ctx.chunk_neighbors(rcut + skin)
     ctx.zero_force_energy(ghost=True)
     ctx.snap_force(xsb.FLAG_ENERGY); ctx.sync()
+    if os.environ.get("XSB_SNAP_CLOCKS"):
+        import ctypes as C
+        L = xsb.load_library(); L.xsbdbg_snap_clocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.xsbdbg_snap_clocks(ctx.h, 1, None)
+        ctx.snap_force(xsb.FLAG_ENERGY); ctx.sync()
+        out = (C.c_uint64 * 8)(); L.xsbdbg_snap_clocks(ctx.h, 0, out)
+        tot = float(sum(out)) or 1.0
+        print("phase cycles: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(["init+filter", "sweepU", "mirror", "Y", "energy", "sweep_dU+force"], out)))
     ctx.profile_enable(True)
     t0 = time.perf_counter()
     for _ in range(reps):
