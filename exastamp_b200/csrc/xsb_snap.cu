@@ -239,6 +239,117 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
   if constexpr ( TJ >= 8 ) level(std::integral_constant<int, 8>{});
 }
 
+// Force sweep for ONE Cartesian direction kd: the thread's (neighbour, row mb) chain of u and du/dr_kd through all levels,
+// contracted with Y on the fly.  The three directions of a neighbour run in three different warps (snap_f_kernel), which
+// cuts the per-thread state from 4 rows to 2 (fits ~128 registers) and triples the warps an SM can hold; the price is
+// that the u chain itself is carried three times.
+template<int TJ>
+__device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int kd, bool valid, double x, double y, double z, double wj, double rcut,
+                                                 const double2* __restrict__ ylist, double2* __restrict__ mbox /* [2][MB] of this (neighbour, kd) */)
+{
+  constexpr int NE = TJ + 1;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1);
+  double ur[NE], ui[NE], dur[NE], dui[NE];
+  const double rsq = x * x + y * y + z * z, r = sqrt(rsq);
+  const double rscale0 = K.rfac0 * M_PI / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+  double sn, cs; sincos(theta0, &sn, &cs);
+  const double z0 = r * cs / sn;
+  const double r0inv = rsqrt(rsq + z0 * z0);
+  const double a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
+  const double sfac = valid ? snap_sfac(K, r, rcut) * wj : 0.0;
+  const double rinv = 1.0 / r;
+  const double uv = (kd == 0 ? x : (kd == 1 ? y : z)) * rinv;
+  const double dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
+  const double dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
+  const double dr0inv = dr0invdr * uv, dz0 = dz0dr * uv;
+  const double da_r = dz0 * r0inv + z0 * dr0inv, da_i = -z * dr0inv + (kd == 2 ? -r0inv : 0.0);
+  const double db_r = y * dr0inv + (kd == 1 ? r0inv : 0.0), db_i = -x * dr0inv + (kd == 0 ? -r0inv : 0.0);
+  const double dsfac = valid ? snap_dsfac(K, r, rcut) * wj : 0.0;
+  const double dsu = dsfac * uv;
+  double dedr = 0.0;
+# pragma unroll
+  for(int e = 0; e < NE; e++) { ur[e] = 0.0; ui[e] = 0.0; dur[e] = 0.0; dui[e] = 0.0; }
+  if( mb == 0 ) ur[0] = 1.0;
+
+  auto emit = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;
+    const int base = K.idxu_block[J] + (J + 1) * mb;
+    const bool middle = 2 * mb == J;
+#   pragma unroll
+    for(int ma = 0; ma <= J; ma++)
+    {
+      double w = 1.0;
+      if( middle ) w = ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0);
+      const double2 Y = ylist[base + ma];
+      const double fr = dsu * ur[ma] + sfac * dur[ma];
+      const double fi = dsu * ui[ma] + sfac * dui[ma];
+      dedr += w * (fr * Y.x + fi * Y.y);
+    }
+  };
+  if( mb == 0 ) emit(std::integral_constant<int, 0>{});
+
+  auto level = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;
+    if( 2 * mb <= J )
+    {
+      if( 2 * mb == J )
+      {
+        const int o = mbox_off(mb - 1);
+#       pragma unroll
+        for(int ma = 0; ma < J; ma++)
+        {
+          const int mp = J - 1 - ma;
+          const double sgn = ((mb - 1 + mp) & 1) ? -1.0 : 1.0;
+          const double2 v = mbox[o + mp], d = mbox[MB + o + mp];
+          ur[ma] = sgn * v.x; ui[ma] = -sgn * v.y; dur[ma] = sgn * d.x; dui[ma] = -sgn * d.y;
+        }
+      }
+      // in place, descending ma: new[ma] = qa a* old[ma] - qb b* old[ma-1]
+#     pragma unroll
+      for(int ma = J; ma >= 0; ma--)
+      {
+        double nr = 0.0, ni = 0.0, dnr = 0.0, dni = 0.0;
+        if( ma < J )
+        {
+          const double q = K.rootpq[J - ma][J - mb];
+          nr = q * (a_r * ur[ma] + a_i * ui[ma]);
+          ni = q * (a_r * ui[ma] - a_i * ur[ma]);
+          dnr = q * (da_r * ur[ma] + da_i * ui[ma] + a_r * dur[ma] + a_i * dui[ma]);
+          dni = q * (da_r * ui[ma] - da_i * ur[ma] + a_r * dui[ma] - a_i * dur[ma]);
+        }
+        if( ma > 0 )
+        {
+          const double q = K.rootpq[ma][J - mb];
+          nr -= q * (b_r * ur[ma - 1] + b_i * ui[ma - 1]);
+          ni -= q * (b_r * ui[ma - 1] - b_i * ur[ma - 1]);
+          dnr -= q * (db_r * ur[ma - 1] + db_i * ui[ma - 1] + b_r * dur[ma - 1] + b_i * dui[ma - 1]);
+          dni -= q * (db_r * ui[ma - 1] - db_i * ur[ma - 1] + b_r * dui[ma - 1] - b_i * dur[ma - 1]);
+        }
+        ur[ma] = nr; ui[ma] = ni; dur[ma] = dnr; dui[ma] = dni;
+      }
+      emit(jc);
+      if( J == 2 * mb + 1 && J < TJ )
+      {
+        const int o = mbox_off(mb);
+#       pragma unroll
+        for(int ma = 0; ma <= J; ma++) { mbox[o + ma] = make_double2(ur[ma], ui[ma]); mbox[MB + o + ma] = make_double2(dur[ma], dui[ma]); }
+      }
+    }
+    __syncthreads();
+  };
+  if constexpr ( TJ >= 1 ) level(std::integral_constant<int, 1>{});
+  if constexpr ( TJ >= 2 ) level(std::integral_constant<int, 2>{});
+  if constexpr ( TJ >= 3 ) level(std::integral_constant<int, 3>{});
+  if constexpr ( TJ >= 4 ) level(std::integral_constant<int, 4>{});
+  if constexpr ( TJ >= 5 ) level(std::integral_constant<int, 5>{});
+  if constexpr ( TJ >= 6 ) level(std::integral_constant<int, 6>{});
+  if constexpr ( TJ >= 7 ) level(std::integral_constant<int, 7>{});
+  if constexpr ( TJ >= 8 ) level(std::integral_constant<int, 8>{});
+  return dedr;
+}
+
 struct SnapArgs
 {
   const double* __restrict__ rx; const double* __restrict__ ry; const double* __restrict__ rz; const unsigned char* __restrict__ type;
@@ -451,6 +562,119 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   mark(5);
 }
 
+// ---- force kernel of the split pipeline: CTA per atom, 3 x (J/2+1) warps = (direction, row), lane = neighbour ----------
+template<int TJ, bool XFORM>
+__global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+{
+  constexpr int NR = TJ / 2 + 1, NW = 3 * NR, NT = 32 * NW;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = 2 * (MB ? MB : 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
+  double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
+  double2* mbox = ylist + K.idxu_max;                                   // [32][3][MBS]
+  double* nb_x = reinterpret_cast<double*>(mbox + 32 * 3 * MBS);        // [SNAP_NN_MAX] x 5
+  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
+  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NW][32]
+  __shared__ unsigned s_nn;
+  const unsigned tid = threadIdx.x, lane = tid & 31u; const int wrp = int(tid >> 5), mb = wrp % NR, kd = wrp / NR;
+  const unsigned slot = A.base + blockIdx.x;
+  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
+  const size_t soa = (size_t(blockIdx.x >> 5) * K.idxu_max) * 32 + (blockIdx.x & 31u);
+  const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
+  const int ei = A.type ? A.type[ai] : 0;
+  for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = A.ubuf[soa + size_t(k) * 32]; ylist[k] = A.ybuf[soa + size_t(k) * 32]; }
+  if( wrp == 0 )
+  {
+    unsigned nn = 0;
+    const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
+    for(unsigned long long e = e0; e < e1; e += 32)
+    {
+      const unsigned long long ee = e + lane;
+      bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
+      if( ee < e1 )
+      {
+        g = A.nbh_idx[ee];
+        dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
+        apply_xform<XFORM>(X, dx, dy, dz);
+        const int ej = A.type ? A.type[g] : 0;
+        rc = (K.radelem[ei] + K.radelem[ej]) * K.rcutfac; wj = K.wjelem[ej];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        in = d2 < rc * rc && d2 > 1e-20;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      const unsigned sl = nn + __popc(m & ((1u << lane) - 1u));
+      if( in && sl < SNAP_NN_MAX ) { nb_x[sl] = dx; nb_y[sl] = dy; nb_z[sl] = dz; nb_w[sl] = wj; nb_rc[sl] = rc; nb_g[sl] = g; }
+      nn += __popc(m);
+    }
+    if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
+  }
+  __syncthreads();
+  const unsigned nn = s_nn;
+  // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
+  if( A.ep )
+  {
+    double sE = 0.0;
+    for(int j = 0; j <= TJ; j++)
+    {
+      const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
+      for(int k = int(tid); k < cnt; k += NT)
+      {
+        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
+        sE += w * (utot[jb + k].x * ylist[jb + k].x + utot[jb + k].y * ylist[jb + k].y);
+      }
+    }
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
+    if( lane == 0 ) red[wrp] = sE;
+    __syncthreads();
+    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NW; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    __syncthreads();
+  }
+  double fix = 0.0, fiy = 0.0, fiz = 0.0, v[9];
+# pragma unroll
+  for(int k = 0; k < 9; k++) v[k] = 0.0;
+  for(unsigned b0 = 0; b0 < nn; b0 += 32)
+  {
+    const unsigned n = b0 + lane; const bool valid = n < nn;
+    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
+    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + (lane * 3 + kd) * MBS);
+    red[wrp * 32 + lane] = d;
+    __syncthreads();
+    if( wrp == 0 && valid )
+    {
+      double f[3] = { 0.0, 0.0, 0.0 };
+      for(int k = 0; k < 3; k++) for(int w2 = 0; w2 < NR; w2++) f[k] += red[(k * NR + w2) * 32 + lane];
+      for(int k = 0; k < 3; k++) f[k] *= 2.0;
+      fix += f[0]; fiy += f[1]; fiz += f[2];
+      const unsigned g = nb_g[n];
+      atomicAdd(A.fx + g, -f[0]); atomicAdd(A.fy + g, -f[1]); atomicAdd(A.fz + g, -f[2]);
+      if( A.vir )
+      {
+        v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
+        v[3] -= f[1] * x; v[4] -= f[1] * y; v[5] -= f[1] * z;
+        v[6] -= f[2] * x; v[7] -= f[2] * y; v[8] -= f[2] * z;
+      }
+    }
+    __syncthreads();
+  }
+  if( wrp == 0 )
+  {
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { fix += __shfl_xor_sync(0xffffffffu, fix, o); fiy += __shfl_xor_sync(0xffffffffu, fiy, o); fiz += __shfl_xor_sync(0xffffffffu, fiz, o); }
+    if( A.vir )
+    {
+#     pragma unroll
+      for(int k = 0; k < 9; k++) { for(int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o); }
+    }
+    if( lane == 0 )
+    {
+      atomicAdd(A.fx + ai, fix); atomicAdd(A.fy + ai, fiy); atomicAdd(A.fz + ai, fiz);
+      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += v[k]; }
+    }
+  }
+}
+
 // ---- compute_yi for 32 atoms at a time: lane = atom -------------------------------------------------------------------
 // One CTA owns one AoSoA block of 32 central atoms: their Utot (idxu_max x 32 complex doubles, 146 KB at 2J = 8) arrives
 // in shared memory with ONE TMA bulk copy, every warp-wide U access is then 32 consecutive 16-byte words (conflict-free),
@@ -617,8 +841,13 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
   const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
   XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
   A.ubuf = S->ubuf.p; A.ybuf = S->ybuf.p;
-  if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, true, 3>, smem)) ) return rc; }
-  else     { if( (rc = setattr(snap_force_kernel<TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, false, 3>, smem)) ) return rc; }
+  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * 3 * 2 * (MB ? MB : 1) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
+                     + size_t(3 * NR) * 32 * sizeof(double) + 64;
+  // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
+  // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)
+  constexpr bool DIRSPLIT = TJ >= 7;
+  if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, true, 3>, smem)) ) return rc; }
+  else     { if( (rc = setattr(snap_force_kernel<TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, false, 3>, smem)) ) return rc; }
   if( (rc = setattr(snap_y_kernel<TJ>, ysmem)) ) return rc;
   for(unsigned base = 0; base < A.n_atoms; base += chunk)
   {
@@ -629,8 +858,16 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
     XSB_LAUNCH_CHECK(ctx);
     snap_y_kernel<TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, S->K);
     XSB_LAUNCH_CHECK(ctx);
-    if( xf ) snap_force_kernel<TJ, true, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
-    else     snap_force_kernel<TJ, false, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    if( DIRSPLIT )
+    {
+      if( xf ) snap_f_kernel<TJ, true><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
+      else     snap_f_kernel<TJ, false><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
+    }
+    else
+    {
+      if( xf ) snap_force_kernel<TJ, true, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+      else     snap_force_kernel<TJ, false, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    }
     XSB_LAUNCH_CHECK(ctx);
   }
   return XSB_OK;
