@@ -88,6 +88,9 @@ def lib():
         L.orc_lj_eval.argtypes = [C.c_double, C.c_double, C.c_double, dpp, dpp]
         L.orc_johnson_eval.argtypes = [_dp, C.c_int, C.c_double, dpp, dpp]
         L.orc_ev_internal.restype = C.c_double
+        L.orc_pair_eval.argtypes = [C.c_int, _dp, C.c_double, dpp, dpp]
+        L.orc_pair_ecut.restype = C.c_double
+        L.orc_pair_ecut.argtypes = [C.c_int, _dp, C.c_double]
         _lib = L
     return _lib
 
@@ -117,6 +120,8 @@ def ref():
         R.xsref_eam_alloy_eval.restype = C.c_double
         R.xsref_eam_alloy_eval.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dpp]
         R.xsref_ev_internal.restype = C.c_double
+        if hasattr(R, "xsref_pair"):
+            R.xsref_pair.argtypes = [C.c_int, _dp, C.c_double, dpp, dpp]
         _ref = R
     return _ref
 
@@ -180,6 +185,20 @@ class Neighbors:
 
 def _opt(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM = 0, 1, 2, 3
+
+
+def pair_eval(pot, params, r):
+    """(e, de) of one pair evaluation of the restated potential"""
+    e, de = C.c_double(), C.c_double()
+    lib().orc_pair_eval(int(pot), np.ascontiguousarray(params, dtype=np.float64), float(r), C.byref(e), C.byref(de))
+    return e.value, de.value
+
+
+def pair_ecut(pot, params, rcut):
+    return lib().orc_pair_ecut(int(pot), np.ascontiguousarray(params, dtype=np.float64), float(rcut))
 
 
 def pair_force(grid, cell_off, rx, ry, rz, nbh, params, rcut, ghost, fx, fy, fz, ep=None, vir=None, pot=0):

@@ -47,6 +47,125 @@ static inline double lj_energy_cutoff(const LJParams& p, double rcut)
   return e;
 }
 
+// ---- further pair potentials behind the same <pot>_compute_force / <pot>_multi_force template ----------------------
+// pot ids (include/xsb200.h xsb_pair_pot): 0 lj {epsilon, sigma}; 1 zbl {r1, rc, z_a, z_b}; 2 exp6 {A, B, C, D};
+// 3 buckingham {A, Rho, C}.
+
+// src/potential/pair_potentials/zbl/potential.h:36-57 (constants), :89-178 (e_zbl, dzbldr, d2zbldr2), :180-303
+// (zbl_compute_energy: LAMMPS pair_zbl with the inner/outer switching polynomial; e and de stay 0 for r >= rc).
+// Energies come out in eV and are scaled by 1e-4 e / amu = 1 eV in internal units (:298-301); the onika constants
+// behind that factor are not in the reference tree (CODATA 2018 values assumed: parity of this factor is unpinned).
+struct ZBLParams { double r1, rc; };
+namespace zblc { constexpr double pzbl = 0.23, a0 = 0.46850, c1 = 0.02817, c2 = 0.28022, c3 = 0.50986, c4 = 0.18175,
+                                  d1 = 0.20162, d2 = 0.40290, d3 = 0.94229, d4 = 3.19980; }
+static inline double zbl_e(double r, double d1a, double d2a, double d3a, double d4a, double zze)
+{
+  const double rinv = 1.0 / r;
+  double sum = zblc::c1 * exp(-d1a * r);
+  sum += zblc::c2 * exp(-d2a * r);
+  sum += zblc::c3 * exp(-d3a * r);
+  sum += zblc::c4 * exp(-d4a * r);
+  return zze * sum * rinv;
+}
+static inline double zbl_dedr(double r, double d1a, double d2a, double d3a, double d4a, double zze)
+{
+  const double rinv = 1.0 / r;
+  const double e1 = exp(-d1a * r), e2 = exp(-d2a * r), e3 = exp(-d3a * r), e4 = exp(-d4a * r);
+  double sum = zblc::c1 * e1; sum += zblc::c2 * e2; sum += zblc::c3 * e3; sum += zblc::c4 * e4;
+  double sum_p = -zblc::c1 * d1a * e1; sum_p -= zblc::c2 * d2a * e2; sum_p -= zblc::c3 * d3a * e3; sum_p -= zblc::c4 * d4a * e4;
+  return zze * (sum_p - sum * rinv) * rinv;
+}
+static inline double zbl_d2edr2(double r, double d1a, double d2a, double d3a, double d4a, double zze)
+{
+  const double rinv = 1.0 / r;
+  const double e1 = exp(-d1a * r), e2 = exp(-d2a * r), e3 = exp(-d3a * r), e4 = exp(-d4a * r);
+  double sum = zblc::c1 * e1; sum += zblc::c2 * e2; sum += zblc::c3 * e3; sum += zblc::c4 * e4;
+  double sum_p = zblc::c1 * e1 * d1a; sum_p += zblc::c2 * e2 * d2a; sum_p += zblc::c3 * e3 * d3a; sum_p += zblc::c4 * e4 * d4a;
+  double sum_pp = zblc::c1 * e1 * d1a * d1a; sum_pp += zblc::c2 * e2 * d2a * d2a; sum_pp += zblc::c3 * e3 * d3a * d3a; sum_pp += zblc::c4 * e4 * d4a * d4a;
+  return zze * (sum_pp + 2.0 * sum_p * rinv + 2.0 * sum * rinv * rinv) * rinv;
+}
+// per type-pair constants of zbl_compute_energy (everything that does not depend on r)
+struct ZBLPair { double d1a, d2a, d3a, d4a, zze, sw1, sw2, sw3, sw4, sw5, r1, rc; };
+static inline ZBLPair zbl_pair(const ZBLParams& p, double z_a, double z_b)
+{
+  ZBLPair q;
+  const double qqr2e = 14.399645, qelectron = 1.0;
+  const double ainv = (pow(z_a, zblc::pzbl) + pow(z_b, zblc::pzbl)) / zblc::a0;
+  q.d1a = zblc::d1 * ainv; q.d2a = zblc::d2 * ainv; q.d3a = zblc::d3 * ainv; q.d4a = zblc::d4 * ainv;
+  q.zze = z_a * z_b * qqr2e * qelectron * qelectron;
+  const double tc = p.rc - p.r1;
+  const double fc = zbl_e(p.rc, q.d1a, q.d2a, q.d3a, q.d4a, q.zze);
+  const double fcp = zbl_dedr(p.rc, q.d1a, q.d2a, q.d3a, q.d4a, q.zze);
+  const double fcpp = zbl_d2edr2(p.rc, q.d1a, q.d2a, q.d3a, q.d4a, q.zze);
+  const double swa = (-3.0 * fcp + tc * fcpp) / (tc * tc);
+  const double swb = (2.0 * fcp - tc * fcpp) / (tc * tc * tc);
+  const double swc = -fc + (tc / 2.0) * fcp - (tc * tc / 12.0) * fcpp;
+  q.sw1 = swa; q.sw2 = swb; q.sw3 = swa / 3.0; q.sw4 = swb / 4.0; q.sw5 = swc; q.r1 = p.r1; q.rc = p.rc;
+  return q;
+}
+static inline void zbl_compute_energy(const ZBLPair& q, double rij, double& e, double& de)
+{
+  const double rsq = rij * rij, cut_innersq = q.r1 * q.r1, cut_globalsq = q.rc * q.rc;
+  if( rsq < cut_globalsq )
+  {
+    const double r = sqrt(rsq);
+    de = zbl_dedr(r, q.d1a, q.d2a, q.d3a, q.d4a, q.zze);
+    if( rsq > cut_innersq ) { const double t = r - q.r1; de += t * t * (q.sw1 + q.sw2 * t); }
+    e = zbl_e(r, q.d1a, q.d2a, q.d3a, q.d4a, q.zze);
+    e += q.sw5;
+    if( rsq > cut_innersq ) { const double t = r - q.r1; e += t * t * t * (q.sw3 + q.sw4 * t); }
+  }
+  e *= EV_INTERNAL; de *= EV_INTERNAL;
+}
+
+// src/potential/pair_potentials/exp6/include/exaStamp/potential/pair_potentials/exp6/exp6.h:66-84
+static inline void exp6_compute_energy(const double* p /* A B C D */, double r, double& e, double& de)
+{
+  const double one_rB = 1 / (r * p[1]);
+  const double r2 = r * r, r6 = r2 * r2 * r2;
+  const double Cr6 = p[2] / r6;
+  const double twelve_rB = 12 * one_rB, twelve_rB2 = twelve_rB * twelve_rB, twelve_rB4 = twelve_rB2 * twelve_rB2;
+  const double twelve_rB12 = twelve_rB4 * twelve_rB4 * twelve_rB4;
+  const double Dtwelve_rB12 = p[3] * twelve_rB12;
+  const double AexpmBr = p[0] * exp(-p[1] * r);
+  e = AexpmBr - Cr6 + Dtwelve_rB12;
+  de = -p[1] * AexpmBr + (6 * Cr6 - 12 * Dtwelve_rB12) / r;
+}
+
+// src/potential/pair_potentials/buckingham/buckingham.h:41-52
+static inline void buckingham_energy(const double* p /* A Rho C */, double x, double& e, double& de)
+{
+  const double x2 = x * x, x6 = x2 * x2 * x2, x7 = x6 * x;
+  e = p[0] * exp(-x / p[1]) - (p[2] / x6);
+  de = (6 * p[2] / x7) - (p[0] * exp(-x / p[1]) / p[1]);
+}
+
+// one pair evaluation of potential `pot` with its raw parameter vector (what USTAMP_POTENTIAL_COMPUTE expands to)
+struct PairPot
+{
+  int pot = 0; double prm[4] = {0, 0, 0, 0}; ZBLPair zbl{};
+  PairPot() = default;
+  PairPot(int pot_, const double* params) : pot(pot_)
+  {
+    const int n = pot == 0 ? 2 : (pot == 3 ? 3 : 4);
+    for(int i = 0; i < n; i++) prm[i] = params[i];
+    if( pot == 1 ) zbl = zbl_pair(ZBLParams{ params[0], params[1] }, params[2], params[3]);
+  }
+  static int nparams(int pot) { return pot == 0 ? 2 : (pot == 3 ? 3 : 4); }
+  inline void compute(double r, double& e, double& de) const
+  {
+    switch( pot )
+    {
+      case 0: lj_compute_energy(LJParams{ prm[0], prm[1] }, r, e, de); break;
+      case 1: zbl_compute_energy(zbl, r, e, de); break;
+      case 2: exp6_compute_energy(prm, r, e, de); break;
+      default: buckingham_energy(prm, r, e, de); break;
+    }
+  }
+  // pair_potential_impl.hxx:488-498 (energy_cutoff)
+  inline double energy_cutoff(double rcut) const { double e = 0.0, de = 0.0; if( rcut > 0.0 ) compute(rcut, e, de); return e; }
+};
+
 // src/potential/eam_potentials/johnson/johnson.h:29-50 (19 scalars, same order)
 struct JohnsonParams
 {

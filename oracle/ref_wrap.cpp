@@ -5,7 +5,11 @@
 #include <exaStamp/potential/pair_potentials/lennard_jones/lennard_jones.h>   // src/potential/pair_potentials/lennard_jones/include
 #include "johnson.h"                                                           // src/potential/eam_potentials/johnson
 #include "eam_alloy.h"                                                         // src/potential/eam_potentials/eam_alloy
+#include <exaStamp/potential/pair_potentials/exp6/exp6.h>                      // src/potential/pair_potentials/exp6/include
+#include "buckingham.h"                                                        // src/potential/pair_potentials/buckingham
 #include <cstring>
+// zbl/potential.h also defines the USTAMP_* template macros: harmless here, nothing expands them
+#include "zbl/potential.h"                                                     // src/potential/pair_potentials/zbl
 
 using namespace exaStamp;
 
@@ -16,6 +20,18 @@ void xsref_lj(double epsilon, double sigma, double r, double* e, double* de)
   LennardJonesParms p{ epsilon, sigma };
   PairPotentialMinimalParameters pp{};
   lj_compute_energy(p, pp, r, *e, *de);
+}
+
+// pot ids as in include/xsb200.h: 1 zbl {r1, rc, z_a, z_b}, 2 exp6 {A, B, C, D}, 3 buckingham {A, Rho, C}
+void xsref_pair(int pot, const double* prm, double r, double* e, double* de)
+{
+  PairPotentialMinimalParameters pp{};
+  double a = 0.0, b = 0.0;       // the operators initialise e, de to 0 before the call (force_op_impl2.hxx:37)
+  if( pot == 0 ) { LennardJonesParms p{ prm[0], prm[1] }; lj_compute_energy(p, pp, r, a, b); }
+  else if( pot == 1 ) { ZBLParms p{}; p.r1 = prm[0]; p.rc = prm[1]; pp.m_atom_a.m_z = unsigned(prm[2]); pp.m_atom_b.m_z = unsigned(prm[3]); zbl_compute_energy(p, pp, r, a, b); }
+  else if( pot == 2 ) { Exp6Parms p{ prm[0], prm[1], prm[2], prm[3] }; exp6_compute_energy(p, pp, r, a, b); }
+  else { BuckinghamParms p{ prm[0], prm[1], prm[2] }; buckingham_energy(p, pp, r, a, b); }
+  *e = a; *de = b;
 }
 
 void xsref_johnson(const double* params19, int what, double x, double* f, double* df)

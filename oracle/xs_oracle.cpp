@@ -337,6 +337,10 @@ void orc_nbh_bruteforce_counts(const orc_grid_t* g, uint64_t N, const double* rx
   }
 }
 
+// one evaluation of a pair potential and its energy cutoff (pins the restatement against the reference headers)
+void orc_pair_eval(int pot, const double* params, double r, double* e, double* de) { double a = 0.0, b = 0.0; PairPot(pot, params).compute(r, a, b); *e = a; *de = b; }
+double orc_pair_ecut(int pot, const double* params, double rcut) { return PairPot(pot, params).energy_cutoff(rcut); }
+
 // ---- <pot>_compute_force, single species, buffered protocol ------------------------------------
 // ForceOp body: src/potential/pair_potential_template/force_op_impl2.hxx:22-78 ; operator slots and
 // ecut: pair_potential_impl.hxx:373-377,488-498.  pot: 0 = lj.  vir may be null (9 doubles/atom, AoS Mat3d).
@@ -344,10 +348,9 @@ void orc_pair_force(const orc_grid_t* g, const uint64_t* cell_off, const double*
                     void* nbh, int pot, const double* params, double rcut, int ghost,
                     double* fx, double* fy, double* fz, double* ep, double* vir)
 {
-  (void)pot;
   const Particles P{ cell_off, rx, ry, rz, nullptr };
-  const LJParams p{ params[0], params[1] };
-  const double ecut = lj_energy_cutoff(p, rcut);
+  const PairPot p(pot, params);
+  const double ecut = p.energy_cutoff(rcut);
   compute_cell_particle_pairs(*g, P, *static_cast<Nbh*>(nbh), rcut, ghost != 0, [&](size_t ga, const PairBuf& tab)
   {
     double _ep = 0., _fx = 0., _fy = 0., _fz = 0.; double _vir[9] = {0,0,0,0,0,0,0,0,0};
@@ -356,7 +359,7 @@ void orc_pair_force(const orc_grid_t* g, const uint64_t* cell_off, const double*
     {
       const double r = std::sqrt(tab.d2[i]);
       double e = 0.0, de = 0.0;
-      lj_compute_energy(p, r, e, de);
+      p.compute(r, e, de);
       e *= weight; de *= weight;
       e -= ecut * weight;
       de /= r;
@@ -373,12 +376,15 @@ void orc_pair_force(const orc_grid_t* g, const uint64_t* cell_off, const double*
 
 // ---- <pot>_multi_force, buffer-less protocol with per type-pair parameters ------------------------
 // PairMultiForceOp: pair_potential_force_op_multiparam.h:76-223 (overload with ep: :78-118 / :121-150).
-// pair_params[pair_id] = {epsilon, sigma, rcut, ecut}; traversal radius = rcut_max (pair_potential_impl.hxx:196,478).
+// pair_params[pair_id] = {params..., rcut, ecut} (params: PairPot::nparams(pot) scalars); traversal radius = rcut_max
+// (pair_potential_impl.hxx:196,478).
 void orc_pair_multi_force(const orc_grid_t* g, const uint64_t* cell_off, const double* rx, const double* ry, const double* rz, const uint8_t* type,
                           void* nbh, int pot, int n_pair_params, const double* pair_params, double rcut_max, int ghost,
                           double* fx, double* fy, double* fz, double* ep, double* vir)
 {
-  (void)pot; (void)n_pair_params;
+  const int np = PairPot::nparams(pot), stride = np + 2;
+  std::vector<PairPot> pots(n_pair_params);
+  for(int i = 0; i < n_pair_params; i++) pots[i] = PairPot(pot, pair_params + size_t(stride) * i);
   const Particles P{ cell_off, rx, ry, rz, type };
   compute_cell_particle_pairs(*g, P, *static_cast<Nbh*>(nbh), rcut_max, ghost != 0, [&](size_t ga, const PairBuf& tab)
   {
@@ -388,14 +394,15 @@ void orc_pair_multi_force(const orc_grid_t* g, const uint64_t* cell_off, const d
     {
       const double r = std::sqrt(tab.d2[i]);
       const unsigned type_b = type[tab.gb[i]];
-      const double* pp = pair_params + 4 * unique_pair_id(type_a, type_b);
-      if( r <= pp[2] )
+      const unsigned pid = unique_pair_id(type_a, type_b);
+      const double* pp = pair_params + size_t(stride) * pid + np;     // {rcut, ecut}
+      if( r <= pp[0] )
       {
         double e = 0.0, de = 0.0;
-        lj_compute_energy(LJParams{pp[0], pp[1]}, r, e, de);
+        pots[pid].compute(r, e, de);
         const double weight = 1.0;
-        if( vir && ep ) { e *= weight; de *= weight; e -= pp[3] * weight; de /= r; }   // :106-109
-        else            { e -= pp[3]; de /= r; e *= weight; de *= weight; }               // :142-145
+        if( vir && ep ) { e *= weight; de *= weight; e -= pp[1] * weight; de /= r; }   // :106-109
+        else            { e -= pp[1]; de /= r; e *= weight; de *= weight; }               // :142-145
         const double fe_x = de * tab.drx[i], fe_y = de * tab.dry[i], fe_z = de * tab.drz[i];
         fx[ga] += fe_x; fy[ga] += fe_y; fz[ga] += fe_z;
         if( ep ) ep[ga] += .5 * e;
