@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libxsb200.so")
 F_RX, F_RY, F_RZ, F_FX, F_FY, F_FZ, F_EP, F_VX, F_VY, F_VZ, F_VIRIAL, F_RHO_DEMB, F_TYPE, F_ID = range(14)
 FLAG_GHOST, FLAG_ENERGY, FLAG_VIRIAL, FLAG_MIXED = 1, 2, 4, 8
 EAM_RHO, EAM_RHO2EMB, EAM_GHOST, EAM_FORCE, EAM_EFLAG = 1, 2, 4, 8, 16
-POT_LJ = 0
+POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM = 0, 1, 2, 3
 _FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
 
 # every symbol include/xsb200.h declares (tests check the library exports all of them)

@@ -7,23 +7,81 @@
 namespace xsb
 {
 
-struct LJPair { double eps4, eps24, sigma2, ecut, rcut2; };   // 4*eps, 24*eps, sigma^2, e(rcut), rcut^2
+// per type-pair coefficients of one pair potential: everything that does not depend on r, precomputed on the host
+//   lj         k = { 4 eps, 24 eps, sigma^2 }                                  (lennard_jones.h:40-50)
+//   zbl        k = { d1a, d2a, d3a, d4a, zze, sw1, sw2, sw3, sw4, sw5, r1, - }   (zbl/potential.h:180-303)
+//   exp6       k = { A, B, C, D }                                               (exp6.h:66-84)
+//   buckingham k = { A, Rho, C }                                                (buckingham.h:41-52)
+struct LJPair { double k[12]; double ecut, rcut2, rc2_pot; int pot, pad_; };   // ecut = e(rcut) ; rc2_pot: zbl's own rc^2
 
 struct LJMulti { LJPair pp[16]; };   // indexed by unique_pair_id (MAX_TYPE_PAIR_IDS = 16, multiparam.h:68)
 
 __host__ __device__ inline unsigned unique_pair_id(unsigned a, unsigned b) { return a > b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
-// LJ from d2 only (algebraically identical to lj_compute_energy followed by de/r):
-//   e = 4 eps (s^12 - s^6) - ecut ;  de/r = -24 eps (2 s^12 - s^6) / r^2
+constexpr double XSB_EV_INTERNAL = 1.602176634e-19 / (1.66053906660e-27 * 1.0e4);   // 1e-4 e / amu (zbl/potential.h:298)
+
+__host__ __device__ __forceinline__ float  xexp(float x)  { return expf(x); }
+__host__ __device__ __forceinline__ double xexp(double x) { return exp(x); }
+__host__ __device__ __forceinline__ float  xsqrt(float x)  { return sqrtf(x); }
+__host__ __device__ __forceinline__ double xsqrt(double x) { return sqrt(x); }
+
+// pair energy (cut-off shift applied) and de/r from d2.  lj needs no square root: e = 4 eps (s^12 - s^6),
+// de/r = -24 eps (2 s^12 - s^6) / r^2 (algebraically identical to lj_compute_energy followed by de/r).
 template<class real>
-__device__ __forceinline__ void lj_eval(const LJPair& p, real d2, real& e, real& de_r)
+__host__ __device__ __forceinline__ void lj_eval(const LJPair& p, real d2, real& e, real& de_r)
 {
   const real rinv2 = real(1) / d2;
-  const real s2 = real(p.sigma2) * rinv2;
-  const real s6 = s2 * s2 * s2;
-  const real s12 = s6 * s6;
-  e = real(p.eps4) * (s12 - s6) - real(p.ecut);
-  de_r = -real(p.eps24) * (real(2) * s12 - s6) * rinv2;
+  if( p.pot == XSB_POT_LJ )
+  {
+    const real s2 = real(p.k[2]) * rinv2;
+    const real s6 = s2 * s2 * s2;
+    const real s12 = s6 * s6;
+    e = real(p.k[0]) * (s12 - s6) - real(p.ecut);
+    de_r = -real(p.k[1]) * (real(2) * s12 - s6) * rinv2;
+    return;
+  }
+  const real r = xsqrt(d2), rinv = real(1) / r;
+  real ee = real(0), de = real(0);
+  if( p.pot == XSB_POT_ZBL )
+  {
+    if( d2 < real(p.rc2_pot) )
+    {
+      const real e1 = xexp(-real(p.k[0]) * r), e2 = xexp(-real(p.k[1]) * r), e3 = xexp(-real(p.k[2]) * r), e4 = xexp(-real(p.k[3]) * r);
+      real sum = real(0.02817) * e1; sum += real(0.28022) * e2; sum += real(0.50986) * e3; sum += real(0.18175) * e4;
+      real sum_p = -real(0.02817) * real(p.k[0]) * e1; sum_p -= real(0.28022) * real(p.k[1]) * e2; sum_p -= real(0.50986) * real(p.k[2]) * e3; sum_p -= real(0.18175) * real(p.k[3]) * e4;
+      const real zze = real(p.k[4]);
+      de = zze * (sum_p - sum * rinv) * rinv;
+      ee = zze * sum * rinv + real(p.k[9]);
+      const real r1 = real(p.k[10]);
+      if( d2 > r1 * r1 )
+      {
+        const real t = r - r1;
+        de += t * t * (real(p.k[5]) + real(p.k[6]) * t);
+        ee += t * t * t * (real(p.k[7]) + real(p.k[8]) * t);
+      }
+    }
+    ee *= real(XSB_EV_INTERNAL); de *= real(XSB_EV_INTERNAL);
+  }
+  else if( p.pot == XSB_POT_EXP6 )
+  {
+    const real one_rB = real(1) / (r * real(p.k[1]));
+    const real r6 = d2 * d2 * d2;
+    const real Cr6 = real(p.k[2]) / r6;
+    const real t12 = real(12) * one_rB, t2 = t12 * t12, t4 = t2 * t2;
+    const real D12 = real(p.k[3]) * (t4 * t4 * t4);
+    const real Ae = real(p.k[0]) * xexp(-real(p.k[1]) * r);
+    ee = Ae - Cr6 + D12;
+    de = -real(p.k[1]) * Ae + (real(6) * Cr6 - real(12) * D12) / r;
+  }
+  else
+  {
+    const real x6 = d2 * d2 * d2, x7 = x6 * r;
+    const real Ae = real(p.k[0]) * xexp(-r / real(p.k[1]));
+    ee = Ae - (real(p.k[2]) / x6);
+    de = (real(6) * real(p.k[2]) / x7) - (Ae / real(p.k[1]));
+  }
+  e = ee - real(p.ecut);
+  de_r = de * rinv;
 }
 
 template<int TPA, bool XFORM, bool MULTI, bool VIRIAL, class real>
@@ -126,13 +184,48 @@ struct LJTileOp
   }
 };
 
-static LJPair make_lj(double eps, double sigma, double rcut)
+static int pair_nparams(int pot) { return pot == XSB_POT_LJ ? 2 : (pot == XSB_POT_BUCKINGHAM ? 3 : (pot == XSB_POT_ZBL || pot == XSB_POT_EXP6 ? 4 : -1)); }
+
+// host-side zbl helpers: the r-independent part of zbl_compute_energy (zbl/potential.h:180-246)
+static double zbl_e_h(double r, const double* d, double zze) { return zze * (0.02817 * exp(-d[0] * r) + 0.28022 * exp(-d[1] * r) + 0.50986 * exp(-d[2] * r) + 0.18175 * exp(-d[3] * r)) / r; }
+static double zbl_de_h(double r, const double* d, double zze)
 {
-  LJPair p; p.eps4 = 4.0 * eps; p.eps24 = 24.0 * eps; p.sigma2 = sigma * sigma; p.rcut2 = rcut * rcut; p.ecut = 0.0;
-  if( rcut > 0.0 )   // energy_cutoff(): e(rcut) through the reference formula (pair_potential_impl.hxx:488-498)
+  const double e1 = exp(-d[0] * r), e2 = exp(-d[1] * r), e3 = exp(-d[2] * r), e4 = exp(-d[3] * r), rinv = 1.0 / r;
+  const double sum = 0.02817 * e1 + 0.28022 * e2 + 0.50986 * e3 + 0.18175 * e4;
+  const double sum_p = -0.02817 * d[0] * e1 - 0.28022 * d[1] * e2 - 0.50986 * d[2] * e3 - 0.18175 * d[3] * e4;
+  return zze * (sum_p - sum * rinv) * rinv;
+}
+static double zbl_d2e_h(double r, const double* d, double zze)
+{
+  const double e1 = exp(-d[0] * r), e2 = exp(-d[1] * r), e3 = exp(-d[2] * r), e4 = exp(-d[3] * r), rinv = 1.0 / r;
+  const double sum = 0.02817 * e1 + 0.28022 * e2 + 0.50986 * e3 + 0.18175 * e4;
+  const double sum_p = 0.02817 * e1 * d[0] + 0.28022 * e2 * d[1] + 0.50986 * e3 * d[2] + 0.18175 * e4 * d[3];
+  const double sum_pp = 0.02817 * e1 * d[0] * d[0] + 0.28022 * e2 * d[1] * d[1] + 0.50986 * e3 * d[2] * d[2] + 0.18175 * e4 * d[3] * d[3];
+  return zze * (sum_pp + 2.0 * sum_p * rinv + 2.0 * sum * rinv * rinv) * rinv;
+}
+
+// coefficients of potential `pot` for one type pair from its raw parameters (reference order) and the operator cutoff
+static LJPair make_pair(int pot, const double* prm, double rcut)
+{
+  LJPair p{}; p.pot = pot; p.rcut2 = rcut * rcut; p.ecut = 0.0; p.rc2_pot = 0.0;
+  if( pot == XSB_POT_LJ ) { p.k[0] = 4.0 * prm[0]; p.k[1] = 24.0 * prm[0]; p.k[2] = prm[1] * prm[1]; }
+  else if( pot == XSB_POT_ZBL )
   {
-    const double ratio = sigma / rcut, r2 = ratio * ratio, r6 = r2 * r2 * r2, r12 = r6 * r6;
-    p.ecut = 4. * eps * (r12 - r6);
+    const double r1 = prm[0], rc = prm[1], za = prm[2], zb = prm[3];
+    const double ainv = (pow(za, 0.23) + pow(zb, 0.23)) / 0.46850;
+    p.k[0] = 0.20162 * ainv; p.k[1] = 0.40290 * ainv; p.k[2] = 0.94229 * ainv; p.k[3] = 3.19980 * ainv;
+    p.k[4] = za * zb * 14.399645;
+    const double tc = rc - r1, fc = zbl_e_h(rc, p.k, p.k[4]), fcp = zbl_de_h(rc, p.k, p.k[4]), fcpp = zbl_d2e_h(rc, p.k, p.k[4]);
+    const double swa = (-3.0 * fcp + tc * fcpp) / (tc * tc), swb = (2.0 * fcp - tc * fcpp) / (tc * tc * tc);
+    p.k[5] = swa; p.k[6] = swb; p.k[7] = swa / 3.0; p.k[8] = swb / 4.0; p.k[9] = -fc + (tc / 2.0) * fcp - (tc * tc / 12.0) * fcpp;
+    p.k[10] = r1; p.rc2_pot = rc * rc;
+  }
+  else { for(int i = 0; i < pair_nparams(pot); i++) p.k[i] = prm[i]; }
+  if( rcut > 0.0 )   // energy_cutoff(): e(rcut) through the same evaluation (pair_potential_impl.hxx:488-498)
+  {
+    double e = 0.0, de = 0.0;
+    lj_eval<double>(p, rcut * rcut, e, de);
+    p.ecut = e;     // lj_eval subtracted ecut = 0
   }
   return p;
 }
@@ -189,26 +282,26 @@ extern "C" {
 int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
-  XSB_REQUIRE(ctx, pot == XSB_POT_LJ, XSB_ERR_UNSUPPORTED, "pair potential not implemented (only lj)");
-  XSB_REQUIRE(ctx, params != nullptr && nparams == 2, XSB_ERR_INVALID, "lj expects 2 parameters: epsilon, sigma");
+  XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
+  XSB_REQUIRE(ctx, params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "wrong parameter count: lj {epsilon, sigma}, zbl {r1, rc, z_a, z_b}, exp6 {A, B, C, D}, buckingham {A, Rho, C}");
   XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
-  LJMulti prm; prm.pp[0] = make_lj(params[0], params[1], rcut);
+  LJMulti prm; prm.pp[0] = make_pair(pot, params, rcut);
   return launch_pair<false>(ctx, prm, rcut, flags);
 }
 
 int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, double rcut_max, int flags)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
-  XSB_REQUIRE(ctx, pot == XSB_POT_LJ, XSB_ERR_UNSUPPORTED, "pair potential not implemented (only lj)");
-  XSB_REQUIRE(ctx, pair_params != nullptr && nparams == 2, XSB_ERR_INVALID, "lj expects rows of {epsilon, sigma, rcut}");
+  XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
+  XSB_REQUIRE(ctx, pair_params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "rows of {params..., rcut} expected");
   const int npairs = n_types * (n_types + 1) / 2;
   XSB_REQUIRE(ctx, n_types >= 1 && npairs <= 16, XSB_ERR_INVALID, "too many type pairs (MAX_TYPE_PAIR_IDS = 16)");
   LJMulti prm; double rmax = 0.0;
   for(int i = 0; i < npairs; i++)
   {
-    const double* row = pair_params + 3 * i;
-    prm.pp[i] = make_lj(row[0], row[1], row[2]);
-    if( row[2] > rmax ) rmax = row[2];
+    const double* row = pair_params + size_t(nparams + 1) * i;
+    prm.pp[i] = make_pair(pot, row, row[nparams]);
+    if( row[nparams] > rmax ) rmax = row[nparams];
   }
   XSB_REQUIRE(ctx, rcut_max >= rmax, XSB_ERR_INVALID, "rcut_max is smaller than a pair rcut");
   return launch_pair<true>(ctx, prm, rcut_max, flags);

@@ -71,7 +71,8 @@ preinit_rcut_max: [ compute_force, nbh_dist ]
 init_rcut_max: [ nbh_dist ]
 hw_device_init: [ mpi_comm_world, init_cuda, update_ghost_config ]
 hw_device_finalize: [ finalize_cuda ]
-setup_system: nop
+input_data: nop            # older decks populate the system here
+setup_system: input_data
 begin_iteration: [ trigger_restart, trigger_analysis, trigger_snapshot, trigger_thermostate_screen, trigger_thermostate_file, trigger_thermostate_compute ]
 end_iteration: [ thermostate_compute_if_triggered, thermostate_screen_if_triggered, thermostate_file_if_triggered,
                  write_restart_if_triggered, perform_analysis_if_triggered, write_snapshot_if_triggered ]

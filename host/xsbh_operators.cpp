@@ -344,6 +344,34 @@ public:
 XSBH_REGISTER_OPERATOR("read_xyz_file_with_xform", ReadXyz);
 static OperatorRegistrar reg_read_xyz("read_xyz_file", []() { return std::unique_ptr<Operator>(new ReadXyz()); });
 
+// replicate_domain { repeat: [nx, ny, nz] } (ext exanb operator used by the snap decks): tiles the staged particles
+class ReplicateDomain : public Operator {
+public:
+  void execute(Simulation& sim) override {
+    TRACE(sim);
+    check_slots({"repeat"});
+    if (!sim.staged_dirty) throw OperatorError("replicate_domain: must follow a reader / lattice inside setup_system");
+    if (sim.nranks > 1) throw OperatorError("replicate_domain: single-rank only (readers keep the particles of the local brick)");
+    const Node& r = required("repeat");
+    long long rep[3]; for (int k = 0; k < 3; ++k) rep[k] = r[k].as_int();
+    const size_t n0 = sim.hx.size();
+    double L[3]; for (int k = 0; k < 3; ++k) L[k] = sim.bounds_max[k] - sim.bounds_min[k];
+    for (long long i = 0; i < rep[0]; ++i) for (long long j = 0; j < rep[1]; ++j) for (long long k = 0; k < rep[2]; ++k) {
+      if (i == 0 && j == 0 && k == 0) continue;
+      const uint64_t img = uint64_t((i * rep[1] + j) * rep[2] + k);
+      for (size_t p = 0; p < n0; ++p) {
+        sim.hx.push_back(sim.hx[p] + i * L[0]); sim.hy.push_back(sim.hy[p] + j * L[1]); sim.hz.push_back(sim.hz[p] + k * L[2]);
+        sim.hvx.push_back(sim.hvx[p]); sim.hvy.push_back(sim.hvy[p]); sim.hvz.push_back(sim.hvz[p]);
+        sim.htype.push_back(sim.htype[p]); sim.hid.push_back(sim.hid[p] + img * n0);
+      }
+    }
+    for (int k = 0; k < 3; ++k) sim.bounds_max[k] = sim.bounds_min[k] + rep[k] * L[k];
+    int gd[3] = {0, 0, 0};
+    DomainOp::finalize(sim, 0.0, gd);
+  }
+};
+XSBH_REGISTER_OPERATOR("replicate_domain", ReplicateDomain);
+
 // staged host particles -> device grid.  Not a reference operator: upstream readers insert straight into the grid.
 class PlaceParticles : public Operator {
 public:
@@ -540,73 +568,115 @@ static OperatorRegistrar reg_pfvr("push_f_v_r", []() { return std::unique_ptr<Op
 static OperatorRegistrar reg_pfv("push_f_v", []() { return std::unique_ptr<Operator>(new PushFVR(false)); });
 
 // ================================================================================================ force operators
-// <pot>_compute_force (pair_potential_impl.hxx:104-122 slots; lennard_jones.h:60-71 parameters)
-class LjComputeForce : public Operator {
+// ---- <pot>_compute_force / <pot>_multi_force for the pair potentials of the C ABI (xsb_pair_pot) --------------------
+// slots: pair_potential_impl.hxx:104-122; parameter maps: lennard_jones.h:60-71 {epsilon, sigma}, zbl/potential.h:64-79
+// {r1, rc} (+ the atomic numbers of the pair from `species`, USTAMP_POTENTIAL_PAIR_PARAMS_EXTRACT zbl/potential.h:312),
+// exp6.h:44-57 {A, B, C, D}, buckingham.h:60-70 {A, Rho, C}.
+struct PairPotDesc { int pot; std::vector<const char*> names; bool needs_z; };
+static const PairPotDesc& pot_desc(int pot) {
+  static const PairPotDesc d[4] = {{XSB_POT_LJ, {"epsilon", "sigma"}, false}, {XSB_POT_ZBL, {"r1", "rc"}, true},
+                                   {XSB_POT_EXP6, {"A", "B", "C", "D"}, false}, {XSB_POT_BUCKINGHAM, {"A", "Rho", "C"}, false}};
+  return d[pot];
+}
+// raw parameter vector in C-ABI order; absent entries of `common_parameters` default to 0 like the reference's structs
+static std::vector<double> pot_params(const std::string& op, const PairPotDesc& d, const Node* map, bool required, double za, double zb) {
+  std::vector<double> v;
+  for (const char* n : d.names) {
+    const Node* x = map && map->is_map() ? map->find(n) : nullptr;
+    if (!x && required) throw OperatorError(op + ": parameter '" + n + "' is missing");
+    v.push_back(x ? quantity(*x) : 0.0);
+  }
+  if (d.needs_z) { v.push_back(za); v.push_back(zb); }
+  return v;
+}
+
+class PairComputeForce : public Operator {
 public:
+  int pot;
+  explicit PairComputeForce(int p) : pot(p) {}
   void execute(Simulation& sim) override {
     TRACE(sim);
     check_slots({"parameters", "rcut", "rcut_max", "chunk_neighbors", "species", "type", "ghost", "grid", "domain", "compact_nbh_weight", "enable_pair_weights", "particle_locks"});
+    const PairPotDesc& d = pot_desc(pot);
     const double rcut = quantity(required("rcut"));
     const Node& p = required("parameters");
-    double prm[2] = {quantity(p["epsilon"]), quantity(p["sigma"])};
     sim.rcut_max = std::max(sim.rcut_max, rcut);       // IN_OUT slot rcut_max (pair_potential_impl.hxx:131-140)
+    int t = -1;
+    if (optional("type")) {
+      t = sim.species_index(required("type").as_string());
+      if (t < 0 && !sim.preinit) throw OperatorError(name + ": unknown species '" + required("type").as_string() + "'");
+    }
+    const double z = sim.species.empty() ? 0.0 : sim.species[t >= 0 ? t : 0].z;     // single-material operator: the pair is (species, species)
+    std::vector<double> prm = pot_params(name, d, &p, true, z, z);
     if (sim.preinit) return;
     need_gpu(sim, name);
-    if (optional("type")) {
-      // slot `type` restricts the operator to one species (pair_potential_impl.hxx:143-158): expressed as a 1-pair multi table
-      int t = sim.species_index(required("type").as_string());
-      if (t < 0) throw OperatorError(name + ": unknown species '" + required("type").as_string() + "'");
+    const int fl = force_flags(sim, bool_slot("ghost", false)) | (sim.mixed_precision ? XSB_FLAG_MIXED : 0);
+    if (t >= 0) {
+      // slot `type` restricts the operator to one species (pair_potential_impl.hxx:143-158): a multi table with one live pair
       const int nt = (int)std::max<size_t>(1, sim.species.size());
-      std::vector<double> rows(size_t(nt) * (nt + 1) / 2 * 3, 0.0);
+      const size_t w = prm.size() + 1;
+      std::vector<double> rows(size_t(nt) * (nt + 1) / 2 * w, 0.0);
       size_t id = size_t(t) * (t + 1) / 2 + t;
-      rows[3 * id] = prm[0]; rows[3 * id + 1] = prm[1]; rows[3 * id + 2] = rcut;
-      sim.check(xsb_pair_multi_force(sim.ctx, XSB_POT_LJ, nt, rows.data(), 2, rcut, force_flags(sim, bool_slot("ghost", false)) | (sim.mixed_precision ? XSB_FLAG_MIXED : 0)), "xsb_pair_multi_force");
+      std::copy(prm.begin(), prm.end(), rows.begin() + id * w); rows[id * w + prm.size()] = rcut;
+      sim.check(xsb_pair_multi_force(sim.ctx, pot, nt, rows.data(), (int)prm.size(), rcut, fl), "xsb_pair_multi_force");
       return;
     }
-    sim.check(xsb_pair_force(sim.ctx, XSB_POT_LJ, prm, 2, rcut, force_flags(sim, bool_slot("ghost", false)) | (sim.mixed_precision ? XSB_FLAG_MIXED : 0)), "xsb_pair_force");
+    sim.check(xsb_pair_force(sim.ctx, pot, prm.data(), (int)prm.size(), rcut, fl), "xsb_pair_force");
   }
 };
-XSBH_REGISTER_OPERATOR("lj_compute_force", LjComputeForce);
-// lj_compute_force_symetric (pair_potential_singlemat_symetric.cpp:335-346): the reference walks half lists and
-// scatters -f to the neighbour under particle locks, then folds ghost forces back (config_update_symmetric_forces.msp).
-// Here the same totals come from the full-list kernel (one writer per atom, nothing lands on ghosts), so the
-// surrounding zero-ghost / update_force_energy_from_ghost nodes of those decks add zeros.
-static OperatorRegistrar reg_lj_sym("lj_compute_force_symetric", []() { return std::unique_ptr<Operator>(new LjComputeForce()); });
 
 // <pot>_multi_force (pair_potential_force_op_multiparam.h:249-284 YAML; table build pair_potential_impl.hxx:209-368)
-class LjMultiForce : public Operator {
+class PairMultiForce : public Operator {
 public:
+  int pot;
+  explicit PairMultiForce(int p) : pot(p) {}
   void execute(Simulation& sim) override {
     TRACE(sim);
     check_slots({"parameters", "common_parameters", "rcut", "rcut_max", "chunk_neighbors", "species", "ghost", "grid", "domain", "compact_nbh_weight", "enable_pair_weights"});
+    const PairPotDesc& d = pot_desc(pot);
     const double rcut = quantity(required("rcut"));
     const Node& list = required("parameters");
     if (!list.is_seq()) throw OperatorError(name + ": `parameters` must be a list of { type_a, type_b, rcut, parameters }");
-    double common[2] = {0.0, 0.0};
-    if (const Node* c = optional("common_parameters")) { common[0] = quantity_or(c->find("epsilon"), 0.0); common[1] = quantity_or(c->find("sigma"), 0.0); }
-    double rmax = 0.0;
+    double rmax = rcut;
     for (auto& e : list.seq) rmax = std::max(rmax, quantity_or(e.find("rcut"), rcut));
-    rmax = std::max(rmax, rcut);
     sim.rcut_max = std::max(sim.rcut_max, rmax);
     if (sim.preinit) return;
     need_gpu(sim, name);
     const int nt = (int)sim.species.size();
     if (nt < 1) throw OperatorError(name + ": no species defined");
-    const size_t np = size_t(nt) * (nt + 1) / 2;
-    std::vector<double> rows(np * 3);
-    for (size_t i = 0; i < np; ++i) { rows[3 * i] = common[0]; rows[3 * i + 1] = common[1]; rows[3 * i + 2] = rcut; }   // pairs without user parameters
+    const size_t np = size_t(nt) * (nt + 1) / 2, w = d.names.size() + (d.needs_z ? 2 : 0) + 1;
+    std::vector<double> rows(np * w);
+    // pairs without user parameters use common_parameters and the operator rcut (pair_potential_impl.hxx:295-321)
+    for (int hi = 0; hi < nt; ++hi) for (int lo = 0; lo <= hi; ++lo) {
+      std::vector<double> prm = pot_params(name, d, optional("common_parameters"), false, sim.species[lo].z, sim.species[hi].z);
+      size_t id = size_t(hi) * (hi + 1) / 2 + lo;
+      std::copy(prm.begin(), prm.end(), rows.begin() + id * w); rows[id * w + w - 1] = rcut;
+    }
     for (auto& e : list.seq) {
       int a = sim.species_index(e["type_a"].as_string()), b = sim.species_index(e["type_b"].as_string());
       if (a < 0 || b < 0) throw OperatorError(name + ": unknown species in pair " + e["type_a"].as_string() + "/" + e["type_b"].as_string());
       int hi = std::max(a, b), lo = std::min(a, b);
       size_t id = size_t(hi) * (hi + 1) / 2 + lo;            // unique_pair_id (ext, symmetric triangular index)
-      const Node& pp = e["parameters"];
-      rows[3 * id] = quantity(pp["epsilon"]); rows[3 * id + 1] = quantity(pp["sigma"]); rows[3 * id + 2] = quantity_or(e.find("rcut"), rcut);
+      std::vector<double> prm = pot_params(name, d, &e["parameters"], true, sim.species[lo].z, sim.species[hi].z);
+      std::copy(prm.begin(), prm.end(), rows.begin() + id * w); rows[id * w + w - 1] = quantity_or(e.find("rcut"), rcut);
     }
-    sim.check(xsb_pair_multi_force(sim.ctx, XSB_POT_LJ, nt, rows.data(), 2, rmax, force_flags(sim, bool_slot("ghost", false)) | (sim.mixed_precision ? XSB_FLAG_MIXED : 0)), "xsb_pair_multi_force");
+    sim.check(xsb_pair_multi_force(sim.ctx, pot, nt, rows.data(), (int)w - 1, rmax, force_flags(sim, bool_slot("ghost", false)) | (sim.mixed_precision ? XSB_FLAG_MIXED : 0)),
+              "xsb_pair_multi_force");
   }
 };
-XSBH_REGISTER_OPERATOR("lj_multi_force", LjMultiForce);
+#define XSBH_PAIR_OPS(potname, POT) \
+  static OperatorRegistrar reg_##potname##_cf(#potname "_compute_force", []() { return std::unique_ptr<Operator>(new PairComputeForce(POT)); }); \
+  static OperatorRegistrar reg_##potname##_mf(#potname "_multi_force", []() { return std::unique_ptr<Operator>(new PairMultiForce(POT)); });
+XSBH_PAIR_OPS(lj, XSB_POT_LJ)
+XSBH_PAIR_OPS(zbl, XSB_POT_ZBL)
+XSBH_PAIR_OPS(exp6, XSB_POT_EXP6)
+XSBH_PAIR_OPS(buckingham, XSB_POT_BUCKINGHAM)
+// lj_compute_force_symetric (pair_potential_singlemat_symetric.cpp:335-346): the reference walks half lists and
+// scatters -f to the neighbour under particle locks, then folds ghost forces back (config_update_symmetric_forces.msp).
+// Here the same totals come from the full-list kernel (one writer per atom, nothing lands on ghosts), so the
+// surrounding zero-ghost / update_force_energy_from_ghost nodes of those decks add zeros.
+static OperatorRegistrar reg_lj_sym("lj_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(XSB_POT_LJ)); });
+static OperatorRegistrar reg_zbl_sym("zbl_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(XSB_POT_ZBL)); });
 
 // johnson_force / johnson_emb / johnson_force_reuse_emb / johnson_init (eam_potential.cu:92-100,178-193; johnson.h:176-204)
 class JohnsonForce : public Operator {
@@ -733,6 +803,8 @@ public:
   }
 };
 XSBH_REGISTER_OPERATOR("snap_force", SnapForce);
+// snaplmp_force (snaplmp.cpp:59-360) is the same operator computed through LAMMPS' sna.cpp upstream: same slots, same files
+static OperatorRegistrar reg_snaplmp("snaplmp_force", []() { return std::unique_ptr<Operator>(new SnapForce()); });
 
 // ================================================================================================ thermodynamic state, loop control
 class TriggerThermoState : public Operator {     // config_thermostate.msp: screen frequency trigger

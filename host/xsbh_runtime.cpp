@@ -145,7 +145,8 @@ static const std::set<std::string>& passive_names() {
       "load_balance_auto_tune_end", "loadbalance_log_helper", "lb_event_counter", "profile_ghost_comm_scheme", "trigger_restart", "trigger_analysis",
       "trigger_snapshot", "write_restart_if_triggered", "perform_analysis_if_triggered", "write_snapshot_if_triggered", "write_final_restart",
       "write_restart", "default_thermostate_file", "thermostate_file_if_triggered", "trigger_thermostate_file", "nose_hoover_additional_step",
-      "md_loop_prolog", "md_loop_epilog", "simulation_epilog_extra"};
+      "md_loop_prolog", "md_loop_epilog", "simulation_epilog_extra", "check_values", "grid_stats", "chunk_neighbors_stats",
+      "final_dump", "species", "input_data"};
   return s;
 }
 
@@ -232,6 +233,8 @@ void apply_globals(const Node& deck, Simulation& sim) {
     sim.dt = quantity_or(g->find("dt"), sim.dt);
     sim.rcut_inc = quantity_or(g->find("rcut_inc"), sim.rcut_inc);
     if (const Node* n = g->find("max_iteration")) sim.max_iteration = n->as_int();
+    if (const Node* n = g->find("simulation_end_iteration")) sim.max_iteration = n->as_int();      // older deck vocabulary
+    if (const Node* n = g->find("simulation_log_frequency")) sim.thermo_screen_frequency = n->as_int();
     if (const Node* n = g->find("timestep")) sim.timestep = n->as_int();
     if (const Node* n = g->find("simulation_thermostate_screen_frequency")) sim.thermo_screen_frequency = n->as_int();
     if (const Node* n = g->find("enable_mixed_precision")) sim.mixed_precision = n->as_bool();     // xsb extension

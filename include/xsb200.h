@@ -74,7 +74,12 @@ enum {
 };
 
 /* pair potentials behind <pot>_compute_force / <pot>_multi_force (src/potential/pair_potentials/) */
-typedef enum xsb_pair_pot { XSB_POT_LJ = 0 /* params: epsilon, sigma */ } xsb_pair_pot;
+typedef enum xsb_pair_pot {
+  XSB_POT_LJ = 0,          /* params: epsilon, sigma                  (lennard_jones/.../lennard_jones.h:40-50)     */
+  XSB_POT_ZBL = 1,         /* params: r1, rc, z_a, z_b                (zbl/potential.h:36-57,180-303; z from species) */
+  XSB_POT_EXP6 = 2,        /* params: A, B, C, D                      (exp6/.../exp6.h:66-84)                        */
+  XSB_POT_BUCKINGHAM = 3   /* params: A, Rho, C                       (buckingham/buckingham.h:41-52)                */
+} xsb_pair_pot;
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* context                                                                                              */

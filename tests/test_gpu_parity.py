@@ -483,3 +483,68 @@ def test_thermo_state_matches_the_reference_sums(virial):
         assert not t["virial"].any()
     t2 = ctx.thermo_state(masses)
     assert all(np.array_equal(np.asarray(t[k]), np.asarray(t2[k])) for k in t)
+
+
+# ------------------------------------------------------------------------------------------------ f3: zbl / exp6 / buckingham
+PAIR_CASES = {
+    # pot id, raw parameters (C-ABI order), operator rcut, nbh_dist
+    "zbl_Ta": (1, [0.1, 4.615858, 73, 73], 4.615858, 5.6),          # potentials/snap/monomat_zbl.msp
+    "zbl_rcut_inside_rc": (1, [2.0, 4.8, 74, 4], 4.2, 5.2),          # operator cutoff below the potential's own rc: ecut != 0
+    "zbl_rcut_beyond_rc": (1, [1.0, 3.6, 29, 29], 4.4, 5.4),         # pairs between rc and rcut contribute -ecut = 0 and no force
+    "exp6": (2, [3.0e5 * EV, 3.6, 60.0 * EV, 1.0e-6 * EV], 5.5, 6.5),
+    "buckingham": (3, [1.2e3 * EV, 0.32, 25.0 * EV], 5.5, 6.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PAIR_CASES))
+@pytest.mark.parametrize("virial", [False, True])
+def test_pair_potentials_parity(name, virial):
+    pot, prm, rcut, nbh = PAIR_CASES[name]
+    O = oracle()
+    gs = system(ncells=6, a=3.3, sigma=0.08, cell=3.3, gl=2)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    fx, fy, fz, ep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    O.pair_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, prm, rcut, 0, fx, fy, fz, ep, vir, pot=pot)
+    assert np.abs(fx).max() > 0
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_force(prm, rcut, xsb.FLAG_ENERGY | (xsb.FLAG_VIRIAL if virial else 0), pot=pot)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64, (name, f)
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+
+
+def test_zbl_multi_force_parity_and_mixed_precision():
+    """zbl_multi_force as in potentials/snap/multi_WBe.msp: one row per type pair, z from the species"""
+    O = oracle()
+    gs = system(ncells=6, a=3.3, sigma=0.08, cell=3.3, gl=2, types=[0, 1, 1, 0])
+    z = [74, 4]
+    rows, orows = [], []
+    for hi in range(2):
+        for lo in range(hi + 1):
+            prm = [4.0, 4.8, z[lo], z[hi]]
+            rows.append(prm + [4.8])
+            orows.append(prm + [4.8, O.pair_ecut(1, prm, 4.8)])
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 5.8, 1, True)
+    fx, fy, fz, ep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, np.array(orows), 4.8, 0, fx, fy, fz, ep, None, pot=1)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(5.8)
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_multi_force(2, np.array(rows), 4.8, xsb.FLAG_ENERGY, pot=1)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_multi_force(2, np.array(rows), 4.8, xsb.FLAG_ENERGY | xsb.FLAG_MIXED, pot=1)
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < 1e-5            # mixed mode tolerance of the north star
+    # wrong parameter count is rejected, nothing is computed on the host
+    with pytest.raises(xsb.XsbError):
+        ctx.pair_force([0.1, 4.6], 4.6, pot=1)
+    with pytest.raises(xsb.XsbError):
+        ctx.pair_force([1.0, 2.0], 4.6, pot=7)

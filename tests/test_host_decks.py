@@ -170,12 +170,14 @@ def test_no_cpu_fallback_in_the_host_layer():
     ("pair/lj/single_specy_nosym.msp", 8.0), ("pair/lj/multi_species_nosym.msp", 8.0), ("pair/lj/single_specy_sym.msp", 8.0),
     ("eam/eam_alloy/single_specy_nosym_cs1.msp", 5.3), ("eam/eam_alloy/multi_species_nosym_cs4.msp", 6.6825),
     ("eam/eam_alloy/multi_species_singlepass_cs1.msp", 6.6825), ("eam/eam_alloy/multi_species_sym_cs1.msp", 6.6825),
-    ("eam/eam_alloy/benchmark_Al_Cu.msp", 6.6825), ("eam/eam_johnson/single_specy.msp", 6.1)])
+    ("eam/eam_alloy/benchmark_Al_Cu.msp", 6.6825), ("eam/eam_johnson/single_specy.msp", 6.1), ("snap/multi_WBe.msp", 4.8123)])
 def test_unmodified_reference_decks_resolve(deck, rcut_max):
     """the reference's own regression decks build a graph here: same names, same slots, same layering"""
     g, v = graph_of(os.path.join("/root/reference/data/regression_new/potentials", deck), "--data-dir", "/root/reference/data/config")
     assert v["rcut_max"] == pytest.approx(rcut_max, rel=1e-15)
     assert "chunk_neighbors" in g and "force_to_accel" in g
+    if "multi_WBe" in deck:   # zbl_multi_force + snap_force with the reference's own WBe_Wood_PRB2019 files, symmetric-force epilog
+        assert " ".join(g).count("zero_force_energy zbl_multi_force snap_force update_force_energy_from_ghost force_to_accel") >= 2
 
 
 # ------------------------------------------------------------------------------------------------ GPU: decks against the oracle
@@ -359,3 +361,42 @@ def test_deck_failure_behaviour_on_gpu(tmp_path):
     (tmp_path / "bad.msp").write_text(open(os.path.join(DECKS, "lj_single_specy_nosym.msp")).read() + "\nchunk_neighbors:\n  config: { chunk_size: 3 }\n")
     p = run(tmp_path / "bad.msp", cwd=tmp_path, check=False)
     assert p.returncode != 0 and "power of two" in p.stderr
+
+
+@pytest.mark.gpu
+def test_snap_zbl_two_species_deck_matches_oracle(tmp_path):
+    """the operator pairing of the reference's multi_WBe.msp: zbl_multi_force + snap_force, two elements, bzeroflag 1"""
+    import exastamp_b200 as xsb
+    twoj = 4
+    ncoef = xsb.load_library().xsb_snap_ncoeff(twoj)
+    rng = np.random.default_rng(7)
+    beta = rng.normal(0, 1, (2, ncoef + 1)) * 1e-2
+    (tmp_path / "synthetic_WBe.snapparam").write_text("rcutfac 4.8123\ntwojmax %d\nrfac0 0.99363\nrmin0 0\nbzeroflag 1\nquadraticflag 0\n" % twoj)
+    (tmp_path / "synthetic_WBe.snapcoeff").write_text("# synthetic\n2 %d\nW 0.5 1\n%s\nBe 0.417932 0.959049\n%s\n" % (
+        ncoef + 1, "\n".join("%.17g" % b for b in beta[0]), "\n".join("%.17g" % b for b in beta[1])))
+    run(os.path.join(DECKS, "snap_zbl_multi.msp"), "--data-dir", tmp_path, cwd=tmp_path)
+    d = read_dump(tmp_path / "snap_zbl.xsbdump")
+    rad, wj = [0.5, 0.417932], [1.0, 0.959049]
+    rc_snap = 2 * 0.5 * 4.8123
+    O, gs, g, nb = oracle_system(d, rc_snap + 1.0)
+    S = O.Snap(twoj, 4.8123, rad, wj, beta * EV, bzeroflag=1)
+    fx, fy, fz, ep = [gs.zeros() for _ in range(4)]
+    z = [74, 4]
+    rows = []
+    for hi in range(2):
+        for lo in range(hi + 1):
+            prm = [4.0, 4.8, z[lo], z[hi]]
+            rows.append(prm + [4.8, O.pair_ecut(1, prm, 4.8)])
+    O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, np.array(rows), 4.8, 0, fx, fy, fz, ep, None, pot=1)
+    O.snap_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, S, 2, fx, fy, fz, ep, None)
+    n = len(d["id"])
+    tot = [np.zeros(n) for _ in range(3)]
+    for t, a in zip(tot, (fx, fy, fz)):
+        np.add.at(t, gs.src_index, a)
+    own = ~gs.is_ghost
+    e = np.zeros(n); e[gs.src_index[own]] = ep[own]
+    m = np.array([183.84, 9.012182])[d["type"]]
+    fmax = max(np.abs(t).max() for t in tot)
+    for got, ref in zip((d["ax"], d["ay"], d["az"]), tot):
+        assert np.abs(got * m - ref).max() <= TOL * fmax
+    assert np.abs(d["ep"] - e).max() <= TOL * np.abs(e).max()
