@@ -86,18 +86,20 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         const unsigned sa = a + c_off;
         const double xa = B.x[sa], ya = B.y[sa], za = B.z[sa];
         op.start(acc, a, sa, B, smem);
+        // per-atom list window: 64-bit base pointers once, 32-bit indices inside the loops
         const unsigned long long e0 = L.off[a];
         if constexpr ( LMODE == LIST_SUB )
         {
           // dense: every entry is in range (filtered by the pass that wrote the sub-list on these positions)
-          const unsigned long long e1 = e0 + L.sub_cnt[a];
-          unsigned long long e = e0 + sub;
-          unsigned jn = e < e1 ? __ldcs(L.sub_idx + e) : 0u;
-          while( e < e1 )
+          const unsigned short* __restrict__ sp = L.sub_idx + e0;
+          const unsigned len = L.sub_cnt[a];
+          unsigned e = sub;
+          unsigned jn = e < len ? __ldcs(sp + e) : 0u;
+          while( e < len )
           {
             const unsigned j = jn;
             e += TPA;
-            if( e < e1 ) jn = __ldcs(L.sub_idx + e);       // next entry in flight while this pair is evaluated
+            if( e < len ) jn = __ldcs(sp + e);       // next entry in flight while this pair is evaluated
             double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
             apply_xform<XFORM>(X, dx, dy, dz);
             op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
@@ -109,16 +111,19 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           // (and into the global sub-list), evaluate the functor on full warps only
           double* qd = reinterpret_cast<double*>(qmem) + warp * TILE_QUEUE_SLOTS;
           unsigned short* qj = reinterpret_cast<unsigned short*>(qmem + size_t(NT / 32) * TILE_QUEUE_SLOTS * sizeof(double)) + warp * TILE_QUEUE_SLOTS;
-          const unsigned long long e1 = L.off[a + 1];
+          const unsigned short* __restrict__ lp = L.idx + e0;
+          unsigned short* __restrict__ wp = L.sub_idx + e0;
+          const unsigned len = unsigned(L.off[a + 1] - e0);
+          const unsigned lt = (1u << sub) - 1u;
           unsigned qn = 0, cnt = 0;
-          unsigned jn = e0 + sub < e1 ? __ldcs(L.idx + e0 + sub) : 0u;
-          for(unsigned long long e = e0; e < e1; e += 32)
+          unsigned jn = sub < len ? __ldcs(lp + sub) : 0u;
+          for(unsigned e = 0; e < len; e += 32)
           {
-            const unsigned long long ee = e + sub;
+            const unsigned ee = e + sub;
             const unsigned j = jn;
-            if( ee + 32 < e1 ) jn = __ldcs(L.idx + ee + 32);
+            if( ee + 32 < len ) jn = __ldcs(lp + ee + 32);
             bool in = false; double d2 = 0.0;
-            if( ee < e1 )
+            if( ee < len )
             {
               double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
               apply_xform<XFORM>(X, dx, dy, dz);
@@ -126,11 +131,11 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
               in = d2 <= op.rcut2;
             }
             const unsigned m = __ballot_sync(0xffffffffu, in);
-            const unsigned rank = __popc(m & ((1u << sub) - 1u));
+            const unsigned rank = __popc(m & lt);
             if( in )
             {
               qd[qn + rank] = d2; qj[qn + rank] = (unsigned short)j;
-              if( LMODE == LIST_FULL_WRITE_SUB ) L.sub_idx[e0 + cnt + rank] = (unsigned short)j;
+              if( LMODE == LIST_FULL_WRITE_SUB ) wp[cnt + rank] = (unsigned short)j;
             }
             const unsigned k = __popc(m);
             qn += k; cnt += k;
@@ -148,16 +153,18 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         }
         else
         {
-          const unsigned long long e1 = L.off[a + 1];
+          const unsigned short* __restrict__ lp = L.idx + e0;
+          unsigned short* __restrict__ wp = L.sub_idx + e0;
+          const unsigned len = unsigned(L.off[a + 1] - e0);
           unsigned cnt = 0;
-          unsigned jn = e0 + sub < e1 ? __ldcs(L.idx + e0 + sub) : 0u;
-          for(unsigned long long e = e0; e < e1; e += TPA)
+          unsigned jn = sub < len ? __ldcs(lp + sub) : 0u;
+          for(unsigned e = 0; e < len; e += TPA)
           {
-            const unsigned long long ee = e + sub;
+            const unsigned ee = e + sub;
             const unsigned j = jn;
-            if( ee + TPA < e1 ) jn = __ldcs(L.idx + ee + TPA);
+            if( ee + TPA < len ) jn = __ldcs(lp + ee + TPA);
             bool in = false;
-            if( ee < e1 )
+            if( ee < len )
             {
               double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
               apply_xform<XFORM>(X, dx, dy, dz);
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             if( LMODE == LIST_FULL_WRITE_SUB )
             {
               const unsigned m = __ballot_sync(gmask, in) & gmask;
-              if( in ) L.sub_idx[e0 + cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+              if( in ) wp[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
               cnt += __popc(m);
             }
           }
