@@ -110,6 +110,7 @@ struct xsb_ctx
   unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
   double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time
   xsb::DevBuf<unsigned short> tl_idx;         // [total]
+  xsb::DevBuf<unsigned> nbh_masks;            // build scratch: survivor masks of the count sweep (xsb_nbr.cu)
   // in-range sub-list written by the first pair pass of a step (EAM rho/emb) for the second (force): valid only while
   // positions, grid and cutoff are unchanged -- pos_epoch counts every API call that can move a particle
   xsb::DevBuf<unsigned short> sub_idx;        // [total]

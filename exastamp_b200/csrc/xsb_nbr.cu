@@ -99,92 +99,160 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
   }
 }
 
-// Tile variant of the sweep (used whenever the tile path serves the grid, i.e. search range <= 2 cells in y/z): one CTA per
-// tile (= cell) stages the 27-cell block once in shared memory (coalesced row copies) and its warps take the tile's
-// atoms in turn; every candidate test reads the stage, and the FILL pass emits the uint16 stage index (what the force
-// kernels stream) and the u32 flat index (CSR view for the exporter / SNAP) in one go -- no separate conversion pass.
-// Same membership arithmetic (nbh_d2) and the same traversal order as nbr_sweep_kernel, so the lists are identical.
-template<bool XFORM, bool FILL>
-__global__ void __launch_bounds__(256) nbr_tile_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
-                                                        const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
-                                                        unsigned* __restrict__ counts, const unsigned long long* __restrict__ off,
-                                                        unsigned* __restrict__ idx32, unsigned short* __restrict__ idx16, unsigned long long* __restrict__ d2min_bits)
+// ---- tile build: count sweep with survivor masks, then mask replay ------------------------------------------------------
+// One CTA per tile (= cell): warp 0 lays out the tile's 27-cell block (same stage indexing as the force kernels,
+// tile_meta_compute) and a table of 32-candidate "words" (stage index / flat index / end of the row, per word); the CTA
+// copies the block's positions into shared memory once (AoS x,y,z: a warp's 64-bit loads at 24-byte stride are
+// conflict-free), then its warps take the tile's atoms in turn.  For every word the 32 lanes test one candidate each with
+// the oracle's arithmetic (nbh_d2) and the ballot mask is kept: lane q of the warp holds the mask of word q, flushed as
+// one coalesced store per 32 words.  nbr_expand_kernel replays the masks into the uint16 stage-index list (what the
+// force kernels stream) and the u32 flat-index list (CSR view for the exporter / SNAP): no positions, no FP64 there.
+constexpr int NBR_MAX_WORDS = 2048 / 32 + TILE_MAX_ROWS + 1;      // s_cap <= 2048 on this path
+
+struct NbrWords
+{
+  unsigned short s[NBR_MAX_WORDS];     // stage index of bit 0
+  unsigned short e[NBR_MAX_WORDS];     // stage index one past the last valid candidate of the word's row
+  unsigned g[NBR_MAX_WORDS];           // flat particle index of bit 0
+  unsigned n;
+};
+
+// executed by one full warp after tile_meta_compute(G, ..., M)
+__device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWords& W)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX);
+  const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
+  unsigned b = 0, e = 0;
+  if( int(lane) < nrows )
+  {
+    const int kk = k + int(lane) / nry - G.Rz, jj = j + int(lane) % nry - G.Ry;
+    if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz )
+    {
+      const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
+      const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
+      if( ge > gb ) { b = gb - (gb & ~1u); e = ge - (gb & ~1u); }      // valid (un-widened) part of the staged row
+    }
+  }
+  const unsigned nw = (e - b + 31u) >> 5;
+  unsigned pre = nw;
+# pragma unroll
+  for(int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if( int(lane) >= o ) pre += v; }
+  if( int(lane) < nrows )
+    for(unsigned q = 0; q < nw; q++)
+    {
+      W.s[pre - nw + q] = (unsigned short)(M.s0[lane] + b + 32u * q);
+      W.e[pre - nw + q] = (unsigned short)(M.s0[lane] + e);
+      W.g[pre - nw + q] = M.g0[lane] + b + 32u * q;
+    }
+  if( lane == 31 ) W.n = pre;
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ double lds_f64_8(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ double lds_f64_16(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(v) : "r"(addr)); return v; }
+
+template<bool XFORM>
+__global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
+                                                         const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                                         unsigned* __restrict__ counts, unsigned* __restrict__ masks, unsigned mask_stride,
+                                                         unsigned long long* __restrict__ d2min_bits)
 {
   extern __shared__ __align__(16) unsigned char nbr_smem[];
   __shared__ TileMeta M;
-  __shared__ unsigned vb[TILE_MAX_ROWS], ve[TILE_MAX_ROWS];     // valid (un-widened) part of each staged row, stage-relative to s0
+  __shared__ NbrWords W;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
   if( warp == 0 )
   {
     tile_meta_compute(G, cell_start, ti, j, k, M);
-    const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX);
-    const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
-    if( int(lane) < nrows )
-    {
-      unsigned b = 0, e = 0;
-      const int kk = k + int(lane) / nry - G.Rz, jj = j + int(lane) % nry - G.Ry;
-      if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz )
-      {
-        const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
-        const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
-        if( ge > gb ) { b = gb - (gb & ~1u); e = ge - (gb & ~1u); }
-      }
-      vb[lane] = b; ve[lane] = e;
-    }
+    __syncwarp();
+    nbr_words_compute(G, cell_start, ti, j, k, M, W);
   }
   __syncthreads();
-  const unsigned S = M.S, nrows = M.nrows;
   if( M.a_begin == M.a_end ) return;
-  double* sx = reinterpret_cast<double*>(nbr_smem); double* sy = sx + G.s_cap; double* sz = sy + G.s_cap;
-  for(unsigned r = warp; r < nrows; r += nwarps)
+  double* sxyz = reinterpret_cast<double*>(nbr_smem);
+  for(unsigned r = warp; r < M.nrows; r += nwarps)
   {
     const unsigned s0 = M.s0[r], len = M.s0[r + 1] - s0, g0 = M.g0[r];
-    for(unsigned t = lane; t < len; t += 32u) { sx[s0 + t] = rx[g0 + t]; sy[s0 + t] = ry[g0 + t]; sz[s0 + t] = rz[g0 + t]; }
+    for(unsigned t = lane; t < len; t += 32u) { double* p = sxyz + 3u * (s0 + t); p[0] = rx[g0 + t]; p[1] = ry[g0 + t]; p[2] = rz[g0 + t]; }
   }
   __syncthreads();
-  (void)S;
-  double dmin = 1.0e300;
+  const unsigned sbase = smem_u32(sxyz), nw = W.n, a_end = M.a_end, c_off = M.c_off;
+  int dmin_hi = 0x7fffffff;          // smallest d2 among the kept pairs, high word only (a lower bound within 2^-20)
+  for(unsigned a = M.a_begin + warp; a < a_end; a += nwarps)
+  {
+    const unsigned sa = a + c_off;
+    const double xa = lds_f64(sbase + 24u * sa), ya = lds_f64_8(sbase + 24u * sa), za = lds_f64_16(sbase + 24u * sa);
+    unsigned cnt = 0, held = 0;
+    unsigned* mrow = masks + size_t(a) * mask_stride;
+    for(unsigned q = 0; q < nw; q++)
+    {
+      const unsigned sidx = unsigned(W.s[q]) + lane;
+      bool keep = false;
+      if( sidx < unsigned(W.e[q]) && sidx != sa )
+      {
+        const unsigned ad = sbase + 24u * sidx;
+        const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
+        keep = d2 > 0.0 && d2 < d2max;
+        if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      cnt += __popc(m);
+      if( (q & 31u) == lane ) held = m;
+      if( (q & 31u) == 31u ) mrow[q - 31u + lane] = held;          // 32 words -> one coalesced 128-byte store
+    }
+    if( (nw & 31u) && lane < (nw & 31u) ) mrow[(nw & ~31u) + lane] = held;
+    if( lane == 0 ) counts[a] = cnt;
+  }
+# pragma unroll
+  for(int o = 16; o > 0; o >>= 1) dmin_hi = min(dmin_hi, __shfl_xor_sync(0xffffffffu, dmin_hi, o));
+  if( lane == 0 && dmin_hi != 0x7fffffff )
+  {
+    const unsigned long long bits = (unsigned long long)(unsigned)dmin_hi << 32;
+    if( bits < *d2min_bits ) atomicMin(d2min_bits, bits);
+  }
+}
+
+__global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsigned* __restrict__ cell_start, const unsigned long long* __restrict__ off,
+                                                          const unsigned* __restrict__ masks, unsigned mask_stride,
+                                                          unsigned* __restrict__ idx32, unsigned short* __restrict__ idx16)
+{
+  __shared__ TileMeta M;
+  __shared__ NbrWords W;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
+  if( warp == 0 )
+  {
+    tile_meta_compute(G, cell_start, ti, j, k, M);
+    __syncwarp();
+    nbr_words_compute(G, cell_start, ti, j, k, M, W);
+  }
+  __syncthreads();
+  if( M.a_begin == M.a_end ) return;
+  const unsigned nw = W.n, lt = (1u << lane) - 1u;
   for(unsigned a = M.a_begin + warp; a < M.a_end; a += nwarps)
   {
-    const unsigned sa = a + M.c_off;
-    const double xa = sx[sa], ya = sy[sa], za = sz[sa];
-    unsigned cnt = 0;
-    unsigned long long w = FILL ? off[a] : 0ull;
-    for(unsigned r = 0; r < nrows; r++)
+    const unsigned* mrow = masks + size_t(a) * mask_stride;
+    unsigned short* o16 = idx16 + off[a];
+    unsigned* o32 = idx32 + off[a];
+    unsigned w = 0;
+    for(unsigned q0 = 0; q0 < nw; q0 += 32u)
     {
-      const unsigned s0 = M.s0[r], e = s0 + ve[r], g0 = M.g0[r];
-      for(unsigned base = s0 + vb[r]; base < e; base += 32u)
+      const unsigned mine = q0 + lane < nw ? mrow[q0 + lane] : 0u;      // 32 words per coalesced load
+      const unsigned qe = min(32u, nw - q0);
+      for(unsigned t = 0; t < qe; t++)
       {
-        const unsigned sidx = base + lane;
-        bool keep = false;
-        if( sidx < e && sidx != sa )
+        const unsigned m = __shfl_sync(0xffffffffu, mine, t);
+        if( m >> lane & 1u )
         {
-          const double d2 = nbh_d2<XFORM>(gv, sx[sidx] - xa, sy[sidx] - ya, sz[sidx] - za);
-          keep = d2 > 0.0 && d2 < d2max;
-          if( !FILL && keep ) dmin = fmin(dmin, d2);
+          const unsigned o = w + __popc(m & lt);
+          o16[o] = (unsigned short)(unsigned(W.s[q0 + t]) + lane);
+          o32[o] = W.g[q0 + t] + lane;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if( FILL )
-        {
-          if( keep )
-          {
-            const unsigned long long o = w + __popc(m & ((1u << lane) - 1u));
-            idx16[o] = (unsigned short)sidx;
-            idx32[o] = g0 + (sidx - s0);
-          }
-          w += __popc(m);
-        }
-        else cnt += __popc(m);
+        w += __popc(m);
       }
     }
-    if( !FILL && lane == 0 ) counts[a] = cnt;
-  }
-  if( !FILL )
-  {
-#   pragma unroll
-    for(int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    if( lane == 0 && dmin < 1.0e300 && (unsigned long long)__double_as_longlong(dmin) < *d2min_bits ) atomicMin(d2min_bits, (unsigned long long)__double_as_longlong(dmin));
   }
 }
 
@@ -381,6 +449,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   TileGeom TG; unsigned s_cap = 0;
   const bool tile = tile_plan(ctx, R, TG, s_cap);
   size_t tile_smem = 0;
+  unsigned mask_stride = 0;
   if( tile )
   {
     TG.ghost = 1; TG.ti_lo = 0; TG.ti_n = TG.tiles_x; TG.j_lo = 0; TG.j_n = TG.ny; TG.k_lo = 0; TG.k_n = TG.nz;
@@ -389,14 +458,15 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     static bool attr_done = false;
     if( !attr_done )
     {
-      cudaFuncSetAttribute(nbr_tile_kernel<false,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(nbr_tile_kernel<true ,false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(nbr_tile_kernel<false,true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(nbr_tile_kernel<true ,true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(nbr_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(nbr_count_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       attr_done = true;
     }
-    if( P.g.xform_identity ) nbr_tile_kernel<false,false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, nullptr, d2min);
-    else                     nbr_tile_kernel<true ,false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, nullptr, d2min);
+    // survivor masks of the count sweep (one word per 32-candidate step), replayed by nbr_expand_kernel
+    mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
+    XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, 1.02));
+    if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
+    else                     nbr_count_kernel<true ><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
   }
   else if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
   else                          nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
@@ -422,8 +492,8 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   {
     // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh) and the CSR view, written together
     XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-    if( P.g.xform_identity ) nbr_tile_kernel<false,true><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p, nullptr);
-    else                     nbr_tile_kernel<true ,true><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, ctx->tl_idx.p, nullptr);
+    nbr_expand_kernel<<<TG.ntiles, 256, 0, ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p);
+    if( ctx->nbh_cfg.free_scratch_memory ) ctx->nbh_masks.release();
   }
   else if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
   else                          nbr_sweep_kernel<true ,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);
