@@ -115,27 +115,35 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           unsigned short* __restrict__ wp = L.sub_idx + e0;
           const unsigned len = unsigned(L.off[a + 1] - e0);
           const unsigned lt = (1u << sub) - 1u;
+          // branch-free filter step with 32-bit shared addressing: lanes past the end of the list test stage slot 0 and are
+          // masked out of the ballot
+          const unsigned xad = smem_u32(B.x), fstride = G.s_cap * 8u;
+          const unsigned qda = smem_u32(qd), qja = smem_u32(qj);
+          const double rc2 = op.rcut2;
           unsigned qn = 0, cnt = 0;
-          unsigned jn = sub < len ? __ldcs(lp + sub) : 0u;
-          for(unsigned e = 0; e < len; e += 32)
+          const unsigned short* lpn = lp + sub;
+          unsigned jn = sub < len ? __ldcs(lpn) : 0u;
+          for(unsigned e = sub; e < len + sub; e += 32)          // e - sub < len : same trip count on every lane
           {
-            const unsigned ee = e + sub;
             const unsigned j = jn;
-            if( ee + 32 < len ) jn = __ldcs(lp + ee + 32);
-            bool in = false; double d2 = 0.0;
-            if( ee < len )
-            {
-              double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
-              apply_xform<XFORM>(X, dx, dy, dz);
-              d2 = dx * dx + dy * dy + dz * dz;
-              in = d2 <= op.rcut2;
-            }
+            lpn += 32;
+            jn = e + 32 < len ? __ldcs(lpn) : 0u;
+            const unsigned ad = xad + 8u * j;
+            double dx, dy, dz;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(ad));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dy) : "r"(ad + fstride));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dz) : "r"(ad + 2u * fstride));
+            dx -= xa; dy -= ya; dz -= za;
+            apply_xform<XFORM>(X, dx, dy, dz);
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            const bool in = (e < len) & (d2 <= rc2);
             const unsigned m = __ballot_sync(0xffffffffu, in);
-            const unsigned rank = __popc(m & lt);
             if( in )
             {
-              qd[qn + rank] = d2; qj[qn + rank] = (unsigned short)j;
-              if( LMODE == LIST_FULL_WRITE_SUB ) wp[cnt + rank] = (unsigned short)j;
+              const unsigned slot = qn + __popc(m & lt);
+              asm volatile("st.shared.f64 [%0], %1;" :: "r"(qda + 8u * slot), "d"(d2) : "memory");
+              asm volatile("st.shared.u16 [%0], %1;" :: "r"(qja + 2u * slot), "h"((unsigned short)j) : "memory");
+              if( LMODE == LIST_FULL_WRITE_SUB ) wp[cnt + __popc(m & lt)] = (unsigned short)j;
             }
             const unsigned k = __popc(m);
             qn += k; cnt += k;
