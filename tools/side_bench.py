@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Side workloads of BASELINE.json (not the judged bench line, that is bench.py = configs[1]):
+   configs[0]  Lennard-Jones FCC argon 32^3 unit cells (131 072 atoms), NVE Verlet       python tools/side_bench.py lj
+   configs[2]  SNAP tantalum BCC 2J=8, 63^3 unit cells (500 094 atoms), NVE Verlet       python tools/side_bench.py snap
+Same step structure as bench.py (push_f_v_r, push_f_v, displacement trigger, ghost_update_r or rebuild, forces,
+force_to_accel, push_f_v), device-timed with CUDA events on the context stream; prints one JSON line."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import exastamp_b200 as xsb  # noqa: E402
+from helpers import EV, lattice  # noqa: E402
+
+KB = 8.617333262e-5 * EV
+W = {"lj": dict(structure="FCC", a=5.0, cells=32, rcut=8.0, skin=1.0, mass=39.948, noise=0.1, label="configs[0] LJ Ar FCC 32^3 (131072 atoms) NVE"),
+     "snap": dict(structure="BCC", a=3.316, cells=63, rcut=4.7, skin=1.0, mass=180.95, noise=0.05, label="configs[2] SNAP Ta BCC 2J=8 (500094 atoms) NVE")}
+
+
+def main(which, steps=100, warmup=10, mixed=0):
+    w = W[which]
+    pos, typ, box = lattice(w["structure"], w["cells"], w["a"], w["noise"], seed=1)
+    vel = np.random.default_rng(2).normal(0.0, np.sqrt(KB * 300.0 / w["mass"]), pos.shape); vel -= vel.mean(axis=0)
+    nc = int(box[0] // (w["rcut"] + w["skin"])); cell = box[0] / nc
+    ctx = xsb.Context(0)
+    ctx.grid_set(xsb.make_grid([nc + 2] * 3, 1, cell, [-cell] * 3))
+    ctx.particles_assign(pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2], typ)
+    ctx.set_domain([nc] * 3); ctx.ghost_comm_scheme()
+    if which == "snap":
+        ncoef = xsb.load_library().xsb_snap_ncoeff(8)
+        beta = np.random.default_rng(1).normal(0, 1, (1, ncoef + 1)) * 1e-3 * EV
+        ctx.snap_set(8, w["rcut"], [0.5], [1.0], beta)
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    state = {"since": 0, "rebuilds": 0}
+
+    def rebuild(first=False):
+        if not first:
+            ctx.particles_rebin(); ctx.ghost_comm_scheme()
+        ctx.chunk_neighbors(w["rcut"] + w["skin"]); ctx.backup_r()
+        state["since"] = 0; state["rebuilds"] += 1
+
+    def forces():
+        if which == "lj":
+            ctx.zero_force_energy()
+            ctx.pair_force([0.0104 * EV, 3.4], w["rcut"], xsb.FLAG_MIXED if mixed else 0)
+        else:
+            ctx.zero_force_energy(ghost=True)
+            ctx.snap_force(0)
+            ctx.ghost_reduce_add([xsb.F_FX, xsb.F_FY, xsb.F_FZ])
+        ctx.force_to_accel([w["mass"]])
+
+    def step():
+        ctx.push_f_v_r(1e-3); ctx.push_f_v(0.5e-3)
+        state["since"] += 1
+        over, _ = ctx.particle_displ_over(0.5 * w["skin"])
+        if over or state["since"] >= 20:
+            rebuild()
+        else:
+            ctx.ghost_update(POS)
+        forces()
+        ctx.push_f_v(0.5e-3)
+
+    rebuild(first=True); forces()
+    for _ in range(warmup):
+        step()
+    ctx.sync(); ctx.profile_enable(True)
+    r0 = state["rebuilds"]; l0 = ctx.launches
+    ctx.timer_start()
+    for _ in range(steps):
+        step()
+    ms = ctx.timer_stop_ms()
+    prof = ctx.profile_read()
+    tot, mx = ctx.chunk_neighbors_stats()
+    print(json.dumps({"workload": w["label"], "metric": "atom-timesteps/s (neighbor+force)", "value": ctx.n_own * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+                      "atoms": ctx.n_own, "steps": steps, "dtype": "f32 pair math / f64 accumulation" if mixed else "f64", "list_entries_per_atom": tot / max(1, ctx.n),
+                      "rebuilds": state["rebuilds"] - r0, "gpu_launches": ctx.launches - l0,
+                      "breakdown_ms_per_call": {k: round(v[0] / v[1], 4) for k, v in prof.items() if v[1]}}))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], *[int(a) for a in sys.argv[2:]])
