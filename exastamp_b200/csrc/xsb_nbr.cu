@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
 // tile_meta_compute) and a table of 32-candidate "words" (stage index / flat index / end of the row, per word); the CTA
 // copies the block's positions into shared memory once (AoS x,y,z: a warp's 64-bit loads at 24-byte stride are
 // conflict-free), then its warps take the tile's atoms in turn.  For every word the 32 lanes test one candidate each with
-// the oracle's arithmetic (nbh_d2) and the ballot mask is kept: lane q of the warp holds the mask of word q, flushed as
+// the reference's operation order (nbh_d2) and the ballot mask is kept: lane q of the warp holds the mask of word q, flushed as
 // one coalesced store per 32 words.  nbr_expand_kernel replays the masks into the uint16 stage-index list (what the
 // force kernels stream) and the u32 flat-index list (CSR view for the exporter / SNAP): no positions, no FP64 there.
 constexpr int NBR_MAX_WORDS = 2048 / 32 + TILE_MAX_ROWS + 1;      // s_cap <= 2048 on this path
