@@ -1,5 +1,6 @@
 // xsb_core.cu -- context, grid + particle storage, zero_force_energy.
 #include "xsb_ctx.h"
+#include <cstdlib>
 #include <cmath>
 #include <new>
 
@@ -190,6 +191,8 @@ int xsb_create(int device, xsb_ctx** out)
     return ctx->fail(XSB_ERR_CUDA, "device %d is sm_%d%d; libxsb200 is built for sm_100a only", device, prop.major, prop.minor);
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->tile_canonical = getenv("XSB_TILE_CANONICAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
+  ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
   XSB_CUDA(ctx, cudaSetDevice(device));
   XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   return XSB_OK;
@@ -207,7 +210,7 @@ void xsb_destroy(xsb_ctx* ctx)
   for(auto& b : ctx->f64) b.release();
   ctx->type.release(); ctx->id.release();
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->nbh_masks.release(); ctx->scratch.release(); ctx->scratch64.release();
-  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->move_stage.release(); ctx->move_stage8.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   xsb_snap_release(ctx);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
@@ -348,6 +351,7 @@ int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
   int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
   if( bytes ) XSB_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_epoch++;
+  if( field == XSB_F_TYPE ) ctx->sub_pw_kind = 0;      // cached per-pair values depend on the neighbour's element
   return XSB_OK;
 }
 
@@ -368,6 +372,7 @@ void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
   void* p = nullptr; size_t bytes = 0;
   if( field_ptr(ctx, field, &p, &bytes) ) return nullptr;
   if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_external = true;   // caller may move particles behind our back
+  if( field == XSB_F_TYPE ) ctx->type_external = true;
   return p;
 }
 

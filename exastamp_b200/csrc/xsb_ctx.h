@@ -106,6 +106,7 @@ struct xsb_ctx
   unsigned nbh_max = 0;
   // tile-local view of the same list (xsb_tile.cuh): uint16 stage indices, same offsets as nbh_off
   bool tile_ok = false;                       // false -> force operators use the generic CSR-gather kernels
+  bool tile_canonical = false;                // debug switch (env XSB_TILE_CANONICAL=1): keep tl_idx in canonical order
   int tile_TX = 1, tile_R[3] = {1, 1, 1};
   unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
   double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time
@@ -115,9 +116,14 @@ struct xsb_ctx
   // positions, grid and cutoff are unchanged -- pos_epoch counts every API call that can move a particle
   xsb::DevBuf<unsigned short> sub_idx;        // [total]
   xsb::DevBuf<unsigned> sub_cnt;              // [n]
+  xsb::DevBuf<double> pair_w;                 // [total] per-pair value cached by the pass that wrote the sub-list
+  int sub_pw_kind = 0;                        // what pair_w holds for the current sub-list: 0 nothing, 1 eam_alloy rho'(r), 2 johnson rho'(r)
+  double sub_pw_johnson[19] = {};             // parameter set behind a kind-2 cache
+  bool pair_cache_off = false;                // env XSB_NO_PAIR_CACHE=1: second pass re-evaluates instead (A/B profiling)
   uint64_t pos_epoch = 1, sub_epoch = 0;
   double sub_rcut = 0.0; bool sub_ghost = false;
   bool pos_external = false;                  // a position device pointer was handed out: epochs cannot be trusted
+  bool type_external = false;                 // same for the type bytes (the per-pair cache of a multi-element pass depends on them)
   bool sub_valid(double rcut, bool need_ghost) const
   { return !pos_external && sub_epoch == pos_epoch && sub_rcut == rcut && (sub_ghost || !need_ghost); }
   xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.

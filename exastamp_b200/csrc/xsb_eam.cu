@@ -167,19 +167,22 @@ __global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XFor
 }
 
 // ---- the same two passes as functors for the persistent tile kernel (xsb_tilepass.cuh) ----------------------------
+template<bool PWO_>
 struct JohnsonEmbTileOp
 {
-  static constexpr bool HAS_W = false, TYPES = false, D2_ONLY = true;
+  static constexpr bool HAS_W = false, TYPES = false, D2_ONLY = true, PW_OUT = PWO_;
   double rcut2; JohnsonP p; double *ep, *rho_dEmb;
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
   struct Acc { double rho; unsigned cnt; };
   __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; A.cnt = 0; }
   __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<false, false>&, const unsigned char*) const {}
-  __device__ __forceinline__ void pair_d2(Acc& A, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
+  // returns rho'(r): kept per pair for the force pass of the step (PW_OUT), which then skips one exp + one power
+  __device__ __forceinline__ double pair_d2(Acc& A, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
   {
     double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
     A.rho += rho; ++A.cnt;
+    return drho;
   }
   __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<false, false>& B, const unsigned char* t) const { pair_d2(A, d2, j, B, t); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
@@ -191,27 +194,32 @@ struct JohnsonEmbTileOp
   }
 };
 
-template<bool VIRIAL>
+template<bool VIRIAL, bool PWI_>
 struct JohnsonForceTileOp
 {
-  static constexpr bool HAS_W = true, TYPES = false, D2_ONLY = false;
+  static constexpr bool HAS_W = true, TYPES = false, D2_ONLY = false, PW_IN = PWI_;
   double rcut2; JohnsonP p; double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
   struct Acc { double fx, fy, fz, ep, fpi; Vir9 v; };
   __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; if( VIRIAL ) A.v.zero(); }
   __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<true, false>& B, const unsigned char*) const { A.fpi = B.w[sa]; }
-  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*) const
+  template<bool HAVE>
+  __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, double drho_in) const
   {
     const double r = sqrt(d2);
-    double rho, drho, phi, dphi;
-    johnson_rho(p, r, rho, drho);
+    double rho, drho = drho_in, phi, dphi;
+    if( !HAVE ) johnson_rho(p, r, rho, drho);
     johnson_phi(p, r, phi, dphi);
     const double de = (drho * (A.fpi + B.w[j]) + dphi) / r;
     const double fex = de * dx, fey = de * dy, fez = de * dz;
     A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * phi;
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*) const
+  { eval<false>(A, dx, dy, dz, d2, j, B, 0.0); }
+  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*, double pv) const
+  { eval<true>(A, dx, dy, dz, d2, j, B, pv); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
     A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz); A.ep = group_sum<TPA>(A.ep);
@@ -393,10 +401,10 @@ __device__ __forceinline__ void hermite_c(const double2 k0, const double2 k1, do
   c3 = k0.y + k1.y - 2.0 * df;
 }
 
-template<bool MULTI>
+template<bool MULTI, bool PWO_>
 struct EamRhoTileOp
 {
-  static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = true;
+  static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = true, PW_OUT = PWO_;
   double rcut2; EamFcView T; double* rho_dEmb;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
   __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
@@ -404,13 +412,16 @@ struct EamRhoTileOp
   __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; }
   __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<HAS_W, TYPES>&, const unsigned char*) const {}
   __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const { pair_d2(A, d2, j, B, tab); }
-  __device__ __forceinline__ void pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  // returns rho'(r) of the neighbour's element (what the force pass calls rhojp): with PW_OUT the traversal keeps it
+  // next to the sub-list entry, so the force pass does not fetch these two knots again
+  __device__ __forceinline__ double pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
   {
     const double r = d2 * rsqrt(d2);
     int m; double p; T.lookup(r, m, p);
     double2 k0, k1; T.knots(tab, MULTI ? int(B.t[j]) : 0, m, k0, k1);    // density table of the NEIGHBOUR's element
     double c3, c4; hermite_c(k0, k1, c3, c4);
     A.rho += ((c3 * p + c4) * p + k0.y) * p + k0.x;
+    return PWO_ ? ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr : 0.0;
   }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
@@ -419,10 +430,10 @@ struct EamRhoTileOp
   }
 };
 
-template<bool MULTI, bool EFLAG, bool VIRIAL>
+template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_>
 struct EamForceTileOp
 {
-  static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false;
+  static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false, PW_IN = PWI_;
   double rcut2; EamFcView T; int nel; double conv_z2r;
   double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
@@ -431,16 +442,27 @@ struct EamForceTileOp
   __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; A.ta = 0; if( VIRIAL ) A.v.zero(); }
   __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const
   { A.fpi = B.w[sa]; if( MULTI ) A.ta = B.t[sa]; }
-  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  // HAVE: rhojp_in = rho'(r) of the neighbour's element, cached by the rho pass of this step (same arithmetic)
+  template<bool HAVE>
+  __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double rhojp_in) const
   {
     const double recip = rsqrt(d2), r = d2 * recip;
     int m; double p; T.lookup(r, m, p);
     const int tb = MULTI ? int(B.t[j]) : 0;
     double2 k0, k1; double c3, c4;
-    T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4);
-    const double rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr;
-    double rhojp = rhoip;
-    if( MULTI && tb != A.ta ) { T.knots(tab, tb, m, k0, k1); hermite_c(k0, k1, c3, c4); rhojp = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+    double rhoip, rhojp;
+    if( HAVE )
+    {
+      rhojp = rhojp_in; rhoip = rhojp_in;
+      if( MULTI && tb != A.ta ) { T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4); rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+    }
+    else
+    {
+      T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4);
+      rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr;
+      rhojp = rhoip;
+      if( MULTI && tb != A.ta ) { T.knots(tab, tb, m, k0, k1); hermite_c(k0, k1, c3, c4); rhojp = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+    }
     T.knots(tab, nel + z2r_index(A.ta, tb), m, k0, k1); hermite_c(k0, k1, c3, c4);
     const double z2p = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr;
     const double z2 = ((c3 * p + c4) * p + k0.y) * p + k0.x;
@@ -453,6 +475,10 @@ struct EamForceTileOp
     if( EFLAG ) A.ep += 0.5 * phi;
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  { eval<false>(A, dx, dy, dz, d2, j, B, tab, 0.0); }
+  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double pv) const
+  { eval<true>(A, dx, dy, dz, d2, j, B, tab, pv); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
     A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz);
@@ -527,21 +553,29 @@ int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int
     if( (phases & 1) && ctx->n )
     {
       XSB_CUDA(ctx, cudaMemsetAsync(emb, 0, ctx->n * sizeof(double), ctx->stream));
-      JohnsonEmbTileOp op{ rc2, p, ctx->f64[XSB_F_EP].p, emb };
+      const bool pwo = !ctx->pair_cache_off;
+      ctx->sub_pw_kind = 0;
       ctx->prof_begin(XSB_PROF_EAM_RHO);
-      int rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB);
+      int rc;
+      if( pwo ) { JohnsonEmbTileOp<true>  op{ rc2, p, ctx->f64[XSB_F_EP].p, emb }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
+      else      { JohnsonEmbTileOp<false> op{ rc2, p, ctx->f64[XSB_F_EP].p, emb }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
       ctx->prof_end(XSB_PROF_EAM_RHO);
       if( rc ) return rc;
       ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = (phases & 2) != 0;
+      if( pwo ) { ctx->sub_pw_kind = 2; std::memcpy(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)); }
     }
     if( (phases & 4) && ctx->n_own )
     {
       double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
       int rc;
       const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
+      // the cached rho'(r) is only good for the parameter set that produced it
+      const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == 2 && std::memcmp(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)) == 0;
       ctx->prof_begin(XSB_PROF_EAM_FORCE);
-      if( virial ) { JohnsonForceTileOp<true> op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); }
-      else         { JohnsonForceTileOp<false> op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); }
+      if( virial ) { if( pwi ) { JohnsonForceTileOp<true, true>   op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); }
+                     else      { JohnsonForceTileOp<true, false>  op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); } }
+      else         { if( pwi ) { JohnsonForceTileOp<false, true>  op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); }
+                     else      { JohnsonForceTileOp<false, false> op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); } }
       ctx->prof_end(XSB_PROF_EAM_FORCE);
       if( rc ) return rc;
     }
@@ -653,6 +687,7 @@ int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   E.nelements = t->nelements; E.nr = t->nr; E.nrho = t->nrho; E.rdr = t->rdr; E.rdrho = t->rdrho; E.rc = t->rc; E.rhomax = t->rhomax;
   E.conv_z2r = t->conversion_z2r; E.conv_frho = t->conversion_frho; E.set = true;
+  ctx->sub_pw_kind = 0;     // a cached rho'(r) belongs to the previous tables
   return XSB_OK;
 }
 
@@ -682,11 +717,17 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     ctx->prof_begin(XSB_PROF_EAM_RHO);
     // one warp per atom + compaction queue; the in-range sub-list it leaves behind serves the force pass of this step
     const size_t qb = tile_queue_bytes<1024>();
-    if( multi ) { EamRhoTileOp<true>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
-    else        { EamRhoTileOp<false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+    // the force pass of this step reuses rho'(r) of every in-range pair: cache it only when that pass can follow
+    const bool pwo = !ctx->pair_cache_off;
+    ctx->sub_pw_kind = 0;
+    if( multi ) { if( pwo ) { EamRhoTileOp<true, true>   op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+                  else      { EamRhoTileOp<true, false>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
+    else        { if( pwo ) { EamRhoTileOp<false, true>  op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+                  else      { EamRhoTileOp<false, false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
     ctx->prof_end(XSB_PROF_EAM_RHO);
     if( rc ) return rc;
     ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = ghost;
+    if( pwo ) ctx->sub_pw_kind = 1;
   }
   if( !tile && (phases & XSB_EAM_RHO) && ctx->n )
   {
@@ -717,8 +758,10 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     int rc;
     ctx->prof_begin(XSB_PROF_EAM_FORCE);
     const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
-#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { EamForceTileOp<MU, EF, VIR> op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; \
-                                                  rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); }
+    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == 1 && !(multi && ctx->type_external);
+#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { \
+      if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
     if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
     else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
 #   undef XSB_EAM_TILE

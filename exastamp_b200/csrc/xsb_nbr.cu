@@ -214,12 +214,21 @@ __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv,
   }
 }
 
+// DEAL: the uint16 list of an atom is written in "bank-dealt" order instead of the canonical one (which the u32 list
+// keeps): entries are dealt out in rounds, each round holding at most one entry per residue (stage index mod 16),
+// ascending residue inside a round.  The force kernels gather x,y,z (8-byte words, SoA) from the stage with 16
+// consecutive list entries per half-warp, so an aligned run of 16 entries with distinct residues is one conflict-free
+// shared-memory wavefront per field instead of ~3 (ncu: >50 % of the wavefronts of the EAM passes were bank conflicts).
+// lcap = per-warp capacity (entries) of the shared-memory work area.
+template<bool DEAL>
 __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsigned* __restrict__ cell_start, const unsigned long long* __restrict__ off,
                                                           const unsigned* __restrict__ masks, unsigned mask_stride,
-                                                          unsigned* __restrict__ idx32, unsigned short* __restrict__ idx16)
+                                                          unsigned* __restrict__ idx32, unsigned short* __restrict__ idx16, unsigned lcap)
 {
+  extern __shared__ __align__(16) unsigned short deal_smem[];
   __shared__ TileMeta M;
   __shared__ NbrWords W;
+  __shared__ unsigned rcnt[8][16];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
   if( warp == 0 )
@@ -231,6 +240,8 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
   __syncthreads();
   if( M.a_begin == M.a_end ) return;
   const unsigned nw = W.n, lt = (1u << lane) - 1u;
+  unsigned short* bidx = deal_smem + size_t(warp) * 2u * lcap;   // canonical stage indices of the current atom
+  unsigned short* brk = bidx + lcap;                             // rank of each entry inside its residue class
   for(unsigned a = M.a_begin + warp; a < M.a_end; a += nwarps)
   {
     const unsigned* mrow = masks + size_t(a) * mask_stride;
@@ -247,11 +258,43 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
         if( m >> lane & 1u )
         {
           const unsigned o = w + __popc(m & lt);
-          o16[o] = (unsigned short)(unsigned(W.s[q0 + t]) + lane);
+          const unsigned short sv = (unsigned short)(unsigned(W.s[q0 + t]) + lane);
+          if( DEAL ) bidx[o] = sv; else o16[o] = sv;
           o32[o] = W.g[q0 + t] + lane;
         }
         w += __popc(m);
       }
+    }
+    if( DEAL )
+    {
+      const unsigned L = w;
+      if( lane < 16u ) rcnt[warp][lane] = 0u;
+      __syncwarp();
+      for(unsigned i0 = 0; i0 < L; i0 += 32u)
+      {
+        const unsigned i = i0 + lane; const bool act = i < L;
+        const unsigned res = act ? (unsigned(bidx[i]) & 15u) : 16u + lane;    // idle lanes only match themselves
+        const unsigned mm = __match_any_sync(0xffffffffu, res);
+        if( act ) brk[i] = (unsigned short)(rcnt[warp][res] + __popc(mm & lt));
+        __syncwarp();
+        if( act && (mm & lt) == 0u ) rcnt[warp][res] += __popc(mm);
+        __syncwarp();
+      }
+      const unsigned c = lane < 16u ? rcnt[warp][lane] : 0u;
+      for(unsigned i0 = 0; i0 < L; i0 += 32u)
+      {
+        const unsigned i = i0 + lane; const bool act = i < L;
+        const unsigned v = act ? bidx[i] : 0u, r = act ? brk[i] : 0u, res = v & 15u;
+        unsigned pos = 0;
+#       pragma unroll
+        for(unsigned q = 0; q < 16u; q++)
+        {
+          const unsigned cq = __shfl_sync(0xffffffffu, c, q);
+          pos += min(cq, r) + ((q < res && cq > r) ? 1u : 0u);
+        }
+        if( act ) o16[pos] = (unsigned short)v;
+      }
+      __syncwarp();
     }
   }
 }
@@ -431,6 +474,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   const unsigned n = unsigned(ctx->n);
   ctx->nbh_built = false; ctx->nbh_total = 0; ctx->nbh_max = 0; ctx->nbh_dist = nbh_dist_lab;
+  ctx->sub_epoch = 0; ctx->sub_pw_kind = 0;      // a sub-list left by an earlier pass indexes the previous list
   XSB_CUDA(ctx, ctx->nbh_count.reserve(n + 1, 1.02));
   XSB_CUDA(ctx, ctx->nbh_off.reserve(n + 2, 1.02));
   XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, 1.02));
@@ -492,7 +536,12 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   {
     // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh) and the CSR view, written together
     XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-    nbr_expand_kernel<<<TG.ntiles, 256, 0, ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p);
+    // uint16 list in bank-dealt order whenever an atom's list fits the per-warp work area (else canonical order)
+    const unsigned lcap = (ctx->nbh_max + 31u) & ~31u;
+    if( lcap && lcap <= 1024u && !ctx->tile_canonical )
+      nbr_expand_kernel<true ><<<TG.ntiles, 256, size_t(8) * 2 * lcap * sizeof(unsigned short), ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p, lcap);
+    else
+      nbr_expand_kernel<false><<<TG.ntiles, 256, 0, ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p, 0u);
     if( ctx->nbh_cfg.free_scratch_memory ) ctx->nbh_masks.release();
   }
   else if( P.g.xform_identity ) nbr_sweep_kernel<false,true><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, nullptr, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr);

@@ -225,6 +225,7 @@ struct TileList
   // written by the first pair pass of a step (EAM rho / emb) and consumed by the second (EAM force)
   unsigned short* __restrict__ sub_idx;
   unsigned* __restrict__ sub_cnt;               // [n]
+  double* __restrict__ pair_w;                  // per-pair cache aligned with sub_idx (xsb_tilepass.cuh), may be null
 };
 
 enum { LIST_FULL = 0, LIST_FULL_WRITE_SUB = 1, LIST_SUB = 2 };

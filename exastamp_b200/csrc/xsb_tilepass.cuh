@@ -9,8 +9,13 @@
 //   void   load_tables(unsigned char* smem, int nt);   cooperative fill by the whole CTA (caller barriers)
 //   struct Acc;  void init(Acc&);  void start(Acc&, a, sa, B, tab);  void pair(Acc&, dx,dy,dz,d2, j, B, tab);   (tab = smem tables)
 //   template<int TPA> void finish(Acc&, a, valid, sub);   group reduction + the single writer's stores
+// Optional per-pair cache (TileList::pair_w, one double per in-range sub-list entry): an Op with PW_OUT = true returns
+// from pair_d2() a value the second pass of the step needs again for the same pair (EAM: rho'(r)), the queue path stores
+// it next to the sub-list entry (coalesced 256-byte stores); an Op with PW_IN = true receives it in pair_pw() when it
+// walks that sub-list, instead of repeating the spline / transcendental evaluation.
 #pragma once
 #include "xsb_tile.cuh"
+#include <type_traits>
 
 namespace xsb
 {
@@ -21,12 +26,19 @@ constexpr size_t TILE_SMEM_MAX = 227 * 1024;
 constexpr int TILE_QUEUE_SLOTS = 64;
 template<int NT> constexpr size_t tile_queue_bytes() { return size_t(NT / 32) * TILE_QUEUE_SLOTS * (sizeof(double) + sizeof(unsigned short)); }
 
+template<class Op, class = void> struct op_pw_out : std::false_type {};
+template<class Op> struct op_pw_out<Op, std::void_t<decltype(Op::PW_OUT)>> : std::bool_constant<Op::PW_OUT> {};
+template<class Op, class = void> struct op_pw_in : std::false_type {};
+template<class Op> struct op_pw_in<Op, std::void_t<decltype(Op::PW_IN)>> : std::bool_constant<Op::PW_IN> {};
+
 template<int TPA, int NT, bool XFORM, int LMODE, class Op>
 __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, const unsigned* __restrict__ cell_start, const TileFields F, const TileList L,
                                                           const XForm X, const Op op)
 {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr bool QUEUE = Op::D2_ONLY && TPA == 32 && LMODE != LIST_SUB;
+  constexpr bool PWO = op_pw_out<Op>::value && QUEUE && LMODE == LIST_FULL_WRITE_SUB;
+  constexpr bool PWI = op_pw_in<Op>::value && LMODE == LIST_SUB;
   constexpr unsigned NWC = NT / 32 - 1;          // consumer warps; the last warp is the TMA producer
   constexpr unsigned GPW = 32 / TPA;             // central atoms per warp and grab
   typedef StageBuf<Op::HAS_W, Op::TYPES> Stage;
@@ -92,17 +104,22 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         {
           // dense: every entry is in range (filtered by the pass that wrote the sub-list on these positions)
           const unsigned short* __restrict__ sp = L.sub_idx + e0;
+          const double* __restrict__ pwp = L.pair_w + e0;
           const unsigned len = L.sub_cnt[a];
           unsigned e = sub;
           unsigned jn = e < len ? __ldcs(sp + e) : 0u;
+          double pvn = 0.0;
+          if( PWI && e < len ) pvn = __ldcs(pwp + e);
           while( e < len )
           {
             const unsigned j = jn;
+            const double pv = pvn;
             e += TPA;
-            if( e < len ) jn = __ldcs(sp + e);       // next entry in flight while this pair is evaluated
+            if( e < len ) { jn = __ldcs(sp + e); if( PWI ) pvn = __ldcs(pwp + e); }   // next entry in flight while this pair is evaluated
             double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
             apply_xform<XFORM>(X, dx, dy, dz);
-            op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
+            if constexpr ( PWI ) op.pair_pw(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem, pv);
+            else                 op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
           }
         }
         else if constexpr ( QUEUE )
@@ -120,7 +137,10 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           const unsigned xad = smem_u32(B.x), fstride = G.s_cap * 8u;
           const unsigned qda = smem_u32(qd), qja = smem_u32(qj);
           const double rc2 = op.rcut2;
-          unsigned qn = 0, cnt = 0;
+          // FIFO over a 64-slot ring: qt entries queued, qh evaluated so far; the k-th queued entry IS the k-th entry of
+          // the atom's in-range sub-list, so a batch [qh, qh+32) maps to 32 consecutive sub-list positions
+          double* __restrict__ pw = L.pair_w + e0;
+          unsigned qt = 0, qh = 0;
           const unsigned short* lpn = lp + sub;
           unsigned jn = sub < len ? __ldcs(lpn) : 0u;
           for(unsigned e = sub; e < len + sub; e += 32)          // e - sub < len : same trip count on every lane
@@ -140,24 +160,30 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             const unsigned m = __ballot_sync(0xffffffffu, in);
             if( in )
             {
-              const unsigned slot = qn + __popc(m & lt);
+              const unsigned k = qt + __popc(m & lt), slot = k & 63u;
               asm volatile("st.shared.f64 [%0], %1;" :: "r"(qda + 8u * slot), "d"(d2) : "memory");
               asm volatile("st.shared.u16 [%0], %1;" :: "r"(qja + 2u * slot), "h"((unsigned short)j) : "memory");
-              if( LMODE == LIST_FULL_WRITE_SUB ) wp[cnt + __popc(m & lt)] = (unsigned short)j;
+              if( LMODE == LIST_FULL_WRITE_SUB ) wp[k] = (unsigned short)j;
             }
-            const unsigned k = __popc(m);
-            qn += k; cnt += k;
+            qt += __popc(m);
             __syncwarp();
-            if( qn >= 32 )
+            if( qt - qh >= 32 )
             {
-              qn -= 32;
-              op.pair_d2(acc, qd[qn + sub], qj[qn + sub], B, smem);
+              const unsigned slot = (qh + sub) & 63u;
+              if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+              else                 op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+              qh += 32;
               __syncwarp();
             }
           }
-          if( sub < qn ) op.pair_d2(acc, qd[sub], qj[sub], B, smem);
+          if( sub < qt - qh )
+          {
+            const unsigned slot = (qh + sub) & 63u;
+            if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+            else                 op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+          }
           __syncwarp();
-          if( LMODE == LIST_FULL_WRITE_SUB && sub == 0 ) L.sub_cnt[a] = cnt;
+          if( LMODE == LIST_FULL_WRITE_SUB && sub == 0 ) L.sub_cnt[a] = qt;
         }
         else
         {
@@ -214,7 +240,9 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
     XSB_CUDA(ctx, ctx->sub_idx.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
     XSB_CUDA(ctx, ctx->sub_cnt.reserve(size_t(ctx->n) + 1, 1.02));
   }
-  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p };
+  if( op_pw_out<Op>::value && queue && lmode == LIST_FULL_WRITE_SUB )
+    XSB_CUDA(ctx, ctx->pair_w.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p, ctx->pair_w.p };
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
   auto go = [&](auto kern) -> int
@@ -228,9 +256,17 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
     XSB_LAUNCH_CHECK(ctx);
     return XSB_OK;
   };
-  if( lmode == LIST_SUB )                 return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB, Op>);
-  if( lmode == LIST_FULL_WRITE_SUB )      return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL_WRITE_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL_WRITE_SUB, Op>);
-  return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL, Op>);
+  if constexpr ( op_pw_in<Op>::value )      // such an Op only exists for the walk over a sub-list that carries the cache
+  {
+    XSB_REQUIRE(ctx, lmode == LIST_SUB && ctx->pair_w.p != nullptr, XSB_ERR_STATE, "tile pass: per-pair cache requested without a valid sub-list");
+    return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB, Op>);
+  }
+  else
+  {
+    if( lmode == LIST_SUB )                 return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB, Op>);
+    if( lmode == LIST_FULL_WRITE_SUB )      return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL_WRITE_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL_WRITE_SUB, Op>);
+    return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL, Op>);
+  }
 }
 
 // 9-component virial accumulator shared by the force ops: vir += -1/2 f (x) dr, Mat3d row-major (ext tensor())
