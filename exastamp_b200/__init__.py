@@ -22,7 +22,7 @@ _FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
 # every symbol include/xsb200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "xsb_create", "xsb_destroy", "xsb_last_error", "xsb_sync", "xsb_version", "xsb_kernel_launch_count",
-    "xsb_profile_enable", "xsb_profile_read", "xsb_timer_record", "xsb_timer_elapsed_ms",
+    "xsb_profile_enable", "xsb_profile_read", "xsb_timer_record", "xsb_timer_elapsed_ms", "xsb_measure_peaks",
     "xsb_grid_set", "xsb_particles_set_cells", "xsb_num_particles", "xsb_num_cells", "xsb_field_upload",
     "xsb_field_download", "xsb_field_device_ptr", "xsb_zero_force_energy",
     "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
@@ -98,6 +98,7 @@ def load_library():
     L.xsb_kernel_launch_count.argtypes = [vp]
     L.xsb_timer_record.argtypes = [vp, i32]
     L.xsb_timer_elapsed_ms.argtypes = [vp, C.POINTER(dbl)]
+    L.xsb_measure_peaks.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
     L.xsb_profile_enable.argtypes = [vp, i32]
     L.xsb_profile_read.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(u64)]
     L.xsb_grid_set.argtypes = [vp, C.POINTER(GridDesc)]
@@ -330,6 +331,12 @@ class Context:
             self._ck(self.L.xsb_profile_read(self.h, t, C.byref(ms), C.byref(cnt)), "xsb_profile_read")
             out[name] = (ms.value, cnt.value)
         return out
+
+    def measure_peaks(self):
+        """(FP64 TFLOP/s of a DFMA loop, FP32 TFLOP/s of an FFMA loop, HBM GB/s of a 1 GiB copy) measured on this device"""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.xsb_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)), "xsb_measure_peaks")
+        return a.value, b.value, c.value
 
     def timer_start(self):
         self._ck(self.L.xsb_timer_record(self.h, 0), "xsb_timer_record")

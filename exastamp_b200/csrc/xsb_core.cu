@@ -169,6 +169,31 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
   return XSB_OK;
 }
 
+namespace xsb
+{
+// roofline denominators: 8 independent FMA chains per thread, 4096 steps
+template<class real>
+__global__ void __launch_bounds__(256) peak_fma_kernel(real* out, real a, real b, int iters)
+{
+  real v[8];
+# pragma unroll
+  for(int k = 0; k < 8; k++) v[k] = real(threadIdx.x + k);
+  for(int i = 0; i < iters; i++)
+  {
+#   pragma unroll
+    for(int k = 0; k < 8; k++) v[k] = v[k] * a + b;
+  }
+  real s = 0;
+# pragma unroll
+  for(int k = 0; k < 8; k++) s += v[k];
+  if( s == real(-1) ) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // never true: keeps the chains alive
+}
+__global__ void __launch_bounds__(256) peak_copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n)
+{
+  for(size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) out[i] = in[i];
+}
+}
+
 extern "C" {
 
 const char* xsb_version(void) { return "xsb200 0.1 (sm_100a)"; }
@@ -191,7 +216,7 @@ int xsb_create(int device, xsb_ctx** out)
     return ctx->fail(XSB_ERR_CUDA, "device %d is sm_%d%d; libxsb200 is built for sm_100a only", device, prop.major, prop.minor);
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->tile_canonical = getenv("XSB_TILE_CANONICAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
+  ctx->tile_deal = getenv("XSB_TILE_DEAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
   ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
   XSB_CUDA(ctx, cudaSetDevice(device));
   XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -254,6 +279,41 @@ int xsb_timer_record(xsb_ctx* ctx, int slot)
   XSB_REQUIRE(ctx, slot == 0 || slot == 1, XSB_ERR_INVALID, "timer slot must be 0 or 1");
   if( !ctx->timer_ev[slot] ) XSB_CUDA(ctx, cudaEventCreate(&ctx->timer_ev[slot]));
   XSB_CUDA(ctx, cudaEventRecord(ctx->timer_ev[slot], ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, double* hbm_gbs)
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t e0, e1;
+  XSB_CUDA(ctx, cudaEventCreate(&e0)); XSB_CUDA(ctx, cudaEventCreate(&e1));
+  const int iters = 4096, grid = ctx->sm_count * 8, block = 256;
+  auto best_ms = [&](auto launch) -> double
+  {
+    double best = 1.0e30;
+    for(int rep = 0; rep < 6; rep++)
+    {
+      cudaEventRecord(e0, ctx->stream); launch(); cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+      if( rep > 0 && ms < best ) best = ms;
+    }
+    return best;
+  };
+  xsb::DevBuf<double> buf;
+  XSB_CUDA(ctx, buf.reserve(size_t(1) << 28));          // 2 GiB: source and destination halves of 1 GiB each
+  const double flop = 2.0 * 8.0 * iters * double(grid) * block;
+  if( fp64_tflops ) { const double ms = best_ms([&]{ xsb::peak_fma_kernel<double><<<grid, block, 0, ctx->stream>>>(buf.p, 1.0000001, 1.0e-9, iters); }); *fp64_tflops = flop / (ms * 1.0e-3) * 1.0e-12; ctx->launches += 6; }
+  if( fp32_tflops ) { const double ms = best_ms([&]{ xsb::peak_fma_kernel<float><<<grid, block, 0, ctx->stream>>>(reinterpret_cast<float*>(buf.p), 1.0000001f, 1.0e-9f, iters); }); *fp32_tflops = flop / (ms * 1.0e-3) * 1.0e-12; ctx->launches += 6; }
+  if( hbm_gbs )
+  {
+    const size_t n16 = (size_t(1) << 30) / 16;
+    const double ms = best_ms([&]{ xsb::peak_copy_kernel<<<ctx->sm_count * 16, block, 0, ctx->stream>>>(reinterpret_cast<const double2*>(buf.p), reinterpret_cast<double2*>(buf.p) + n16, n16); });
+    *hbm_gbs = 2.0 * double(size_t(1) << 30) / (ms * 1.0e-3) * 1.0e-9; ctx->launches += 6;
+  }
+  cudaError_t e = cudaGetLastError();
+  buf.release(); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "xsb_measure_peaks: %s", cudaGetErrorString(e));
   return XSB_OK;
 }
 

@@ -106,7 +106,7 @@ struct xsb_ctx
   unsigned nbh_max = 0;
   // tile-local view of the same list (xsb_tile.cuh): uint16 stage indices, same offsets as nbh_off
   bool tile_ok = false;                       // false -> force operators use the generic CSR-gather kernels
-  bool tile_canonical = false;                // debug switch (env XSB_TILE_CANONICAL=1): keep tl_idx in canonical order
+  bool tile_deal = false;                     // A/B switch (env XSB_TILE_DEAL=1): tl_idx in bank-dealt order (xsb_nbr.cu)
   int tile_TX = 1, tile_R[3] = {1, 1, 1};
   unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
   double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time

@@ -12,6 +12,7 @@
 #include "xsb_tile.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 
@@ -109,13 +110,49 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
 // force kernels stream) and the u32 flat-index list (CSR view for the exporter / SNAP): no positions, no FP64 there.
 constexpr int NBR_MAX_WORDS = 2048 / 32 + TILE_MAX_ROWS + 1;      // s_cap <= 2048 on this path
 
+constexpr int NBR_MAX_TX = 8;                                       // widest tile (tile_plan)
+
 struct NbrWords
 {
   unsigned short s[NBR_MAX_WORDS];     // stage index of bit 0
   unsigned short e[NBR_MAX_WORDS];     // stage index one past the last valid candidate of the word's row
   unsigned g[NBR_MAX_WORDS];           // flat particle index of bit 0
+  unsigned char r[NBR_MAX_WORDS];      // row of the stage the word belongs to
   unsigned n;
 };
+
+// candidates of a central atom = the cells [i-Rx, i+Rx] of every staged row, i = its own cell: with TX > 1 that is a
+// sub-range [lo, hi) of each row, kept per (cell of the tile, row)
+struct NbrWindows
+{
+  unsigned short lo[NBR_MAX_TX][TILE_MAX_ROWS], hi[NBR_MAX_TX][TILE_MAX_ROWS];
+  unsigned cbeg[NBR_MAX_TX + 1];       // flat index of the first atom of each cell of the tile (cbeg[ncell] = end)
+  unsigned ncell;
+};
+
+// executed by one full warp after tile_meta_compute(G, ..., M)
+__device__ __forceinline__ void nbr_windows_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWindows& V)
+{
+  const int lane = threadIdx.x & 31;
+  const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX), nc = i1 - i0;
+  const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
+  for(int it = lane; it < nc * nrows; it += 32)
+  {
+    const int t = it / nrows, r = it - t * nrows, i = i0 + t;
+    const int kk = k + r / nry - G.Rz, jj = j + r % nry - G.Ry;
+    unsigned lo = 0, hi = 0;
+    if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz && M.s0[r + 1] > M.s0[r] )
+    {
+      const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
+      lo = M.s0[r] + (cell_start[row + max(0, i - G.Rx)] - M.g0[r]);
+      hi = M.s0[r] + (cell_start[row + min(G.nx, i + G.Rx + 1)] - M.g0[r]);
+    }
+    V.lo[t][r] = (unsigned short)lo; V.hi[t][r] = (unsigned short)hi;
+  }
+  const unsigned rowc = unsigned(G.nx) * (unsigned(j) + unsigned(G.ny) * unsigned(k));
+  if( lane <= nc ) V.cbeg[lane] = cell_start[rowc + i0 + lane];
+  if( lane == 0 ) V.ncell = unsigned(nc);
+}
 
 // executed by one full warp after tile_meta_compute(G, ..., M)
 __device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWords& W)
@@ -143,6 +180,7 @@ __device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsig
     {
       W.s[pre - nw + q] = (unsigned short)(M.s0[lane] + b + 32u * q);
       W.e[pre - nw + q] = (unsigned short)(M.s0[lane] + e);
+      W.r[pre - nw + q] = (unsigned char)lane;
       W.g[pre - nw + q] = M.g0[lane] + b + 32u * q;
     }
   if( lane == 31 ) W.n = pre;
@@ -153,7 +191,7 @@ __device__ __forceinline__ double lds_f64_8(unsigned addr) { double v; asm volat
 __device__ __forceinline__ double lds_f64_16(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(v) : "r"(addr)); return v; }
 
 template<bool XFORM>
-__global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
+__global__ void __launch_bounds__(512) nbr_count_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
                                                          const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
                                                          unsigned* __restrict__ counts, unsigned* __restrict__ masks, unsigned mask_stride,
                                                          unsigned long long* __restrict__ d2min_bits)
@@ -161,6 +199,7 @@ __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv,
   extern __shared__ __align__(16) unsigned char nbr_smem[];
   __shared__ TileMeta M;
   __shared__ NbrWords W;
+  __shared__ NbrWindows V;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
   if( warp == 0 )
@@ -168,6 +207,7 @@ __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv,
     tile_meta_compute(G, cell_start, ti, j, k, M);
     __syncwarp();
     nbr_words_compute(G, cell_start, ti, j, k, M, W);
+    nbr_windows_compute(G, cell_start, ti, j, k, M, V);
   }
   __syncthreads();
   if( M.a_begin == M.a_end ) return;
@@ -186,18 +226,26 @@ __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv,
     const double xa = lds_f64(sbase + 24u * sa), ya = lds_f64_8(sbase + 24u * sa), za = lds_f64_16(sbase + 24u * sa);
     unsigned cnt = 0, held = 0;
     unsigned* mrow = masks + size_t(a) * mask_stride;
+    unsigned t = 0;                                    // cell of the tile that holds atom a (warp-uniform)
+    while( t + 1 < V.ncell && a >= V.cbeg[t + 1] ) ++t;
     for(unsigned q = 0; q < nw; q++)
     {
-      const unsigned sidx = unsigned(W.s[q]) + lane;
-      bool keep = false;
-      if( sidx < unsigned(W.e[q]) && sidx != sa )
+      const unsigned s0 = W.s[q], r = W.r[q];
+      const unsigned lo = V.lo[t][r], hi = V.hi[t][r];
+      unsigned m = 0u;
+      if( s0 < hi && s0 + 32u > lo )                   // the word overlaps the atom's window of this row
       {
-        const unsigned ad = sbase + 24u * sidx;
-        const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
-        keep = d2 > 0.0 && d2 < d2max;
-        if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
+        const unsigned sidx = s0 + lane;
+        bool keep = false;
+        if( sidx >= lo && sidx < hi && sidx != sa )
+        {
+          const unsigned ad = sbase + 24u * sidx;
+          const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
+          keep = d2 > 0.0 && d2 < d2max;
+          if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
+        }
+        m = __ballot_sync(0xffffffffu, keep);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
       cnt += __popc(m);
       if( (q & 31u) == lane ) held = m;
       if( (q & 31u) == 31u ) mrow[q - 31u + lane] = held;          // 32 words -> one coalesced 128-byte store
@@ -255,6 +303,7 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
       for(unsigned t = 0; t < qe; t++)
       {
         const unsigned m = __shfl_sync(0xffffffffu, mine, t);
+        if( m == 0u ) continue;                                           // words outside the atom's window
         if( m >> lane & 1u )
         {
           const unsigned o = w + __popc(m & lt);
@@ -412,12 +461,12 @@ static int exclusive_scan_u64(xsb_ctx* ctx, const unsigned long long* in, unsign
 // Tile geometry for this grid + search range: TX cells per tile along x, largest stage over all tiles (host copy of
 // the cell offsets).  Returns false when the tile path cannot serve the list (search range > 2 cells in y/z, or a
 // stage larger than a uint16 index / the shared-memory budget): the generic CSR kernels are used then.
-static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap)
+static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, TileGeom& G, unsigned& s_cap)
 {
   const xsb_grid_desc& g = ctx->grid;
   G = TileGeom{};
   G.nx = g.dims[0]; G.ny = g.dims[1]; G.nz = g.dims[2]; G.gl = g.ghost_layers;
-  G.Rx = R[0]; G.Ry = R[1]; G.Rz = R[2]; G.TX = 1; G.ghost = 1;
+  G.Rx = R[0]; G.Ry = R[1]; G.Rz = R[2]; G.TX = TX; G.ghost = 1;
   G.tiles_x = (G.nx + G.TX - 1) / G.TX;
   s_cap = 0;
   if( (2 * R[1] + 1) * (2 * R[2] + 1) > TILE_MAX_ROWS ) return false;
@@ -447,10 +496,33 @@ static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap
   }
   s_cap = (s_cap + 7u) & ~7u;
   if( s_cap == 0 ) s_cap = 8;
-  // 2 stage buffers of x,y,z,w + types must leave room for the operator tables: cap a buffer at 64 KiB
-  if( s_cap > 65535u || size_t(s_cap) * 33 > 64 * 1024 ) return false;
+  // 2 stage buffers of x,y,z,w + types must leave room for the operator tables: cap a buffer at 64 KiB; the build
+  // kernels index at most 2048 staged atoms (NBR_MAX_WORDS)
+  if( s_cap > 2048u || size_t(s_cap) * 33 > 64 * 1024 ) return false;
   G.s_cap = s_cap;
   return true;
+}
+
+// Tile width: up to 3 cells per tile when the stage limits allow.  A wider tile stages (TX+2Rx)/TX times fewer
+// neighbour cells per central atom and gives the consumer warps more atoms between two mbarrier hand-overs: with one
+// cell per tile and ~27 atoms per cell (LJ argon) ncu showed 18 % of the executed instructions in the barrier spin
+// loops.  Measured on B200 (profiles/r01x_lj_tile_width.txt), LJ Ar 2 M atoms, pair pass / list build in ms:
+// TX=1 1.356 / 5.65, TX=2 1.026 / 5.48, TX=3 0.978 / 5.88, TX=4 1.044 / 6.28, TX=6 1.037 / 7.28 -- beyond 3 the build
+// and the balance over the persistent CTAs lose more than the pair pass gains.  Dense cells (EAM Cu, ~58 atoms)
+// fill the stage with TX = 1.  XSB_TILE_TX=n forces a width (A/B runs).
+static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap)
+{
+  const xsb_grid_desc& g = ctx->grid;
+  const char* fixed = getenv("XSB_TILE_TX");
+  const int tx_max = fixed ? std::min(NBR_MAX_TX, std::max(1, atoi(fixed))) : 3;
+  for(int TX = std::min(tx_max, std::max(1, g.dims[0])); TX >= 1; TX--)
+  {
+    const size_t tiles = size_t((g.dims[0] + TX - 1) / TX) * g.dims[1] * g.dims[2];
+    if( TX > 1 && !fixed && tiles < size_t(ctx->sm_count) * 8 ) continue;
+    if( tile_plan_tx(ctx, R, TX, G, s_cap) ) return true;
+    if( (2 * R[1] + 1) * (2 * R[2] + 1) > TILE_MAX_ROWS ) return false;
+  }
+  return false;
 }
 
 } // namespace xsb
@@ -509,8 +581,10 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     // survivor masks of the count sweep (one word per 32-candidate step), replayed by nbr_expand_kernel
     mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
     XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, 1.02));
-    if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
-    else                     nbr_count_kernel<true ><<<TG.ntiles, 256, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
+    // a large stage limits the CTAs per SM: keep the SM full of warps with wider CTAs
+    const int cblock = tile_smem > 26 * 1024 ? 512 : 256;
+    if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
+    else                     nbr_count_kernel<true ><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
   }
   else if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
   else                          nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
@@ -536,9 +610,11 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   {
     // tile-local uint16 view for the persistent tile kernels (xsb_tile.cuh) and the CSR view, written together
     XSB_CUDA(ctx, ctx->tl_idx.reserve(size_t(total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-    // uint16 list in bank-dealt order whenever an atom's list fits the per-warp work area (else canonical order)
+    // uint16 list in canonical order; bank-dealt order only on request (env XSB_TILE_DEAL=1).  Measured at C2 on B200
+    // (profiles/r01s_*): wavefronts per position load 3.0 -> 1.41 on the full list (2.14 on a compacted sub-list), but
+    // the EAM passes only gain 0.03 ms per step while the deal costs 2.7 ms per rebuild: not worth it for FP64 EAM.
     const unsigned lcap = (ctx->nbh_max + 31u) & ~31u;
-    if( lcap && lcap <= 1024u && !ctx->tile_canonical )
+    if( lcap && lcap <= 1024u && ctx->tile_deal )
       nbr_expand_kernel<true ><<<TG.ntiles, 256, size_t(8) * 2 * lcap * sizeof(unsigned short), ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p, lcap);
     else
       nbr_expand_kernel<false><<<TG.ntiles, 256, 0, ctx->stream>>>(TG, ctx->cell_start.p, ctx->nbh_off.p, ctx->nbh_masks.p, mask_stride, ctx->nbh_idx.p, ctx->tl_idx.p, 0u);

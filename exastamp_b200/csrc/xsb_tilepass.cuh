@@ -141,13 +141,18 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           // the atom's in-range sub-list, so a batch [qh, qh+32) maps to 32 consecutive sub-list positions
           double* __restrict__ pw = L.pair_w + e0;
           unsigned qt = 0, qh = 0;
+          // list indices are fetched two steps ahead (a step is too short to cover an HBM round trip: ncu showed ~20 % of
+          // the stall samples on the first use of the index)
+          constexpr bool QJ = Op::TYPES;        // the functor only looks at j for the neighbour's type
           const unsigned short* lpn = lp + sub;
           unsigned jn = sub < len ? __ldcs(lpn) : 0u;
+          unsigned jnn = sub + 32 < len ? __ldcs(lpn + 32) : 0u;
           for(unsigned e = sub; e < len + sub; e += 32)          // e - sub < len : same trip count on every lane
           {
             const unsigned j = jn;
+            jn = jnn;
             lpn += 32;
-            jn = e + 32 < len ? __ldcs(lpn) : 0u;
+            jnn = e + 64 < len ? __ldcs(lpn + 32) : 0u;
             const unsigned ad = xad + 8u * j;
             double dx, dy, dz;
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(ad));
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             {
               const unsigned k = qt + __popc(m & lt), slot = k & 63u;
               asm volatile("st.shared.f64 [%0], %1;" :: "r"(qda + 8u * slot), "d"(d2) : "memory");
-              asm volatile("st.shared.u16 [%0], %1;" :: "r"(qja + 2u * slot), "h"((unsigned short)j) : "memory");
+              if( QJ ) asm volatile("st.shared.u16 [%0], %1;" :: "r"(qja + 2u * slot), "h"((unsigned short)j) : "memory");
               if( LMODE == LIST_FULL_WRITE_SUB ) wp[k] = (unsigned short)j;
             }
             qt += __popc(m);
@@ -170,8 +175,9 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             if( qt - qh >= 32 )
             {
               const unsigned slot = (qh + sub) & 63u;
-              if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qj[slot], B, smem);
-              else                 op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+              const unsigned qjv = QJ ? unsigned(qj[slot]) : 0u;
+              if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qjv, B, smem);
+              else                 op.pair_d2(acc, qd[slot], qjv, B, smem);
               qh += 32;
               __syncwarp();
             }
@@ -179,8 +185,9 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           if( sub < qt - qh )
           {
             const unsigned slot = (qh + sub) & 63u;
-            if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qj[slot], B, smem);
-            else                 op.pair_d2(acc, qd[slot], qj[slot], B, smem);
+            const unsigned qjv = QJ ? unsigned(qj[slot]) : 0u;
+            if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qjv, B, smem);
+            else                 op.pair_d2(acc, qd[slot], qjv, B, smem);
           }
           __syncwarp();
           if( LMODE == LIST_FULL_WRITE_SUB && sub == 0 ) L.sub_cnt[a] = qt;

@@ -101,6 +101,10 @@ int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* interval
 /* stopwatch on the context's stream: record slot 0 (start) and 1 (stop), then read the device time      */
 int xsb_timer_record(xsb_ctx* ctx, int slot);
 int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms);
+/* roofline denominators measured on this device ("peaks must be measured on the box"):     */
+/* a DFMA loop (FP64 pipe, TFLOP/s), an FFMA loop (FP32 pipe, TFLOP/s) and a 1 GiB copy (HBM, GB/s       */
+/* read+write); best of 5 after a warm-up, CUDA events on the context's stream.  Any output may be null. */
+int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, double* hbm_gbs);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* a1  Grid / GridCellParticles                                                                         */

@@ -548,3 +548,128 @@ def test_zbl_multi_force_parity_and_mixed_precision():
         ctx.pair_force([0.1, 4.6], 4.6, pot=1)
     with pytest.raises(xsb.XsbError):
         ctx.pair_force([1.0, 2.0], 4.6, pot=7)
+
+
+# ------------------------------------------------------------------------------------------------ kernel switches / caches
+def _eam_forces(gs, path, rcut, nbh, two_species, env=None):
+    """fx,fy,fz,ep,rho_dEmb of eam_alloy_force (rho | rho2emb | ghost, then force: the bench's call pattern) under `env`"""
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        ctx = make_ctx(gs)              # the switches are read when the context is created
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    ctx.eam_alloy_load(path); ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG)
+    ctx.eam_alloy_force(rcut, xsb.EAM_FORCE | xsb.EAM_EFLAG)
+    return [ctx.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP, xsb.F_RHO_DEMB)]
+
+
+@pytest.mark.parametrize("two_species", [False, True])
+def test_eam_pair_cache_and_list_order_switches_do_not_change_results(tmp_path, two_species):
+    """the force pass either re-evaluates rho'(r) or takes it from the per-pair cache left by the rho pass (same
+    arithmetic: identical bits), and the tile list may be in canonical or bank-dealt order (other summation order:
+    rounding only); every variant matches the oracle at the FP64 bar"""
+    O = oracle()
+    els = [SC_CU, SC_XX] if two_species else [SC_CU]
+    path = write_setfl(str(tmp_path / "t.eam.alloy"), els, nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    gs = system(ncells=6, a=3.615, sigma=0.08, cell=3.615 * 2, gl=1, types=[0, 1, 1, 0] if two_species else None, seed=11)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 7.0, 1, True)
+    ref = [gs.zeros() for _ in range(5)]
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 1 | 2 | 4 | 8 | 16, ref[0], ref[1], ref[2], ref[3], None, ref[4])
+    base = _eam_forces(gs, path, 6.0, 7.0, two_species)
+    nocache = _eam_forces(gs, path, 6.0, 7.0, two_species, {"XSB_NO_PAIR_CACHE": "1"})
+    dealt = _eam_forces(gs, path, 6.0, 7.0, two_species, {"XSB_TILE_DEAL": "1"})
+    for k in range(5):
+        assert rel_err(base[k], ref[k]) < TOL64 and rel_err(dealt[k], ref[k]) < TOL64
+        assert np.array_equal(base[k], nocache[k]), "field %d: cached rho'(r) differs from the re-evaluated one" % k
+        assert rel_err(dealt[k], base[k]) < 1e-13
+
+
+def test_dealt_list_order_keeps_the_canonical_export_and_lj_parity():
+    O = oracle()
+    gs = system(ncells=6, a=5.0, sigma=0.15, cell=10.0, gl=1, seed=5)
+    os.environ["XSB_TILE_DEAL"] = "1"
+    try:
+        ctx = make_ctx(gs)
+    finally:
+        os.environ.pop("XSB_TILE_DEAL", None)
+    ctx.chunk_neighbors(9.0)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 9.0, 1, True)
+    goff, gdata = ctx.chunk_neighbors_export(); ooff, odata = nb.export()
+    assert np.array_equal(goff, ooff) and gdata.tobytes() == odata.tobytes()
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_force([0.0104 * EV, 3.4], 8.0)
+    rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    O.pair_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, [0.0104 * EV, 3.4], 8.0, 0, rfx, rfy, rfz, rep, None)
+    own = ~gs.is_ghost
+    for f, r in ((xsb.F_FX, rfx), (xsb.F_FY, rfy), (xsb.F_FZ, rfz), (xsb.F_EP, rep)):
+        assert rel_err(ctx.download(f)[own], r[own]) < TOL64
+
+
+def test_johnson_pair_cache_parity_two_phase():
+    """johnson_emb then johnson_force_reuse_emb as two calls: the force pass takes rho'(r) from the emb pass's cache"""
+    O = oracle()
+    gs = system(ncells=6, a=3.615, sigma=0.06, cell=3.615 * 2, gl=1, seed=4)
+    p = johnson_params()
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 6.5, 1, True)
+    rfx, rfy, rfz, rep, emb = [gs.zeros() for _ in range(5)]
+    O.eam_johnson(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, p, 5.8, 1 | 2 | 4, rfx, rfy, rfz, rep, None, emb)
+    ctx = make_ctx(gs); ctx.chunk_neighbors(6.5); ctx.zero_force_energy(ghost=True)
+    ctx.eam_johnson_force(p, 5.8, 1 | 2)
+    ctx.eam_johnson_force(p, 5.8, 4)
+    own = ~gs.is_ghost
+    for f, r in ((xsb.F_FX, rfx), (xsb.F_FY, rfy), (xsb.F_FZ, rfz), (xsb.F_EP, rep)):
+        assert rel_err(ctx.download(f)[own], r[own]) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ C2 at full size
+def test_c2_full_size_parity_and_properties(tmp_path):
+    """BASELINE configs[1] at full size (FCC Cu 79^3 unit cells = 1 972 156 atoms, the bench's potential and cutoffs):
+    the whole force field against the oracle (OpenMP, tens of seconds), plus size-independent properties:
+    momentum conservation, the in-range sub-list equals the list filtered at rcut, cohesive energy in the Cu range."""
+    O = oracle()
+    from bench import A_CU, RCUT, SKIN, make_setfl, n_cells_for
+    path = make_setfl(str(tmp_path))
+    pos, typ, box = lattice("FCC", 79, A_CU, 0.1, seed=1)
+    nc = n_cells_for(box[0])
+    gs = GridSystem(pos, typ, box, box[0] / nc, 1)
+    assert gs.n_owned == 1972156
+    ctx = make_ctx(gs); ctx.eam_alloy_load(path); ctx.chunk_neighbors(RCUT + SKIN)
+    own = ~gs.is_ghost
+    owner_of = np.zeros(len(pos), dtype=np.int64); owner_of[gs.src_index[own]] = np.nonzero(own)[0]
+    ctx.zero_force_energy(ghost=True)
+    # one ghost layer: rho on own atoms, F'(rho) copied owner -> ghost image (ghost_update_opt in the decks), then forces
+    ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_EFLAG)
+    demb = ctx.download(xsb.F_RHO_DEMB)
+    ctx.upload(xsb.F_RHO_DEMB, demb[owner_of[gs.src_index]])
+    ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE | xsb.EAM_EFLAG)
+    fx, fy, fz, ep = [ctx.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+    fmax = max(np.abs(f[own]).max() for f in (fx, fy, fz))
+    for f in (fx, fy, fz):
+        assert abs(f[own].sum()) < 1e-9 * fmax * np.sqrt(own.sum())          # Newton's third law, globally
+    assert -4.2 < ep[own].mean() / EV < -2.8                                   # Sutton-Chen Cu cohesive energy (eV/atom)
+    total, mx = ctx.chunk_neighbors_stats()
+    assert 190 < total / gs.n < 200 and mx < 260
+    # the same fields from the CPU restatement on the same 2.37 M particles (ghost images included)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, RCUT + SKIN, 1, True)
+    cnt, off, idx = ctx.chunk_neighbors_flat()
+    ocnt, ooff, oidx = nb.decode()
+    assert np.array_equal(cnt, ocnt) and np.array_equal(off, ooff) and np.array_equal(idx, oidx)      # neighbour list bit-exact at 4.6e8 entries
+    del ocnt, ooff, oidx, cnt, off, idx
+    rfx, rfy, rfz, rep, emb = [gs.zeros() for _ in range(5)]
+    eam = O.EamAlloy(path)
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, RCUT, 1 | 2 | 16, rfx, rfy, rfz, rep, None, emb)
+    emb[:] = emb[owner_of[gs.src_index]]
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, RCUT, 8 | 16, rfx, rfy, rfz, rep, None, emb)
+    for a, b in ((fx, rfx), (fy, rfy), (fz, rfz), (ep, rep)):
+        assert rel_err(a[own], b[own]) < TOL64

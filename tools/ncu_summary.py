@@ -3,6 +3,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/x_launches.csv          > profiles/rNN_launches.txt
   python tools/ncu_summary.py full     gpurun_out/x.ncu-rep [regex]       > profiles/rNN_full.txt
+  python tools/ncu_summary.py traffic  gpurun_out/x.ncu-rep               > profiles/ncu_traffic.json   (read by bench.py: roofline.traffic)
 """
 import csv
 import re
@@ -60,8 +61,29 @@ def full(path, pat=None):
                 print("   %-75s %18s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
 
 
+def traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches) of the EAM tile kernels"""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kn = hdr.index("Kernel Name"); rd = hdr.index("dram__bytes_read.sum"); wr = hdr.index("dram__bytes_write.sum"); du = hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = defaultdict(list)
+    for r in rows[2:]:
+        key = "eam_force" if "EamForceTileOp" in r[kn] else "eam_rho" if "EamRhoTileOp" in r[kn] else None
+        if key:
+            acc[key].append((float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]], float(r[du]), r[kn][:120]))
+    res = {"source": path, "how": "ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum, mean per launch"}
+    for k, v in acc.items():
+        res[k] = {"dram_bytes_per_launch": sum(x[0] for x in v) / len(v), "launches": len(v), "kernel": v[0][2], "duration_under_ncu": "%g %s" % (sum(x[1] for x in v) / len(v), units[du])}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

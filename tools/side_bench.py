@@ -17,6 +17,7 @@ from helpers import EV, lattice  # noqa: E402
 
 KB = 8.617333262e-5 * EV
 W = {"lj": dict(structure="FCC", a=5.0, cells=32, rcut=8.0, skin=1.0, mass=39.948, noise=0.1, label="configs[0] LJ Ar FCC 32^3 (131072 atoms) NVE"),
+     "lj2m": dict(structure="FCC", a=5.0, cells=80, rcut=8.0, skin=1.0, mass=39.948, noise=0.1, label="LJ Ar FCC 80^3 (2048000 atoms) NVE (configs[0] potential at the C2 size)"),
      "snap": dict(structure="BCC", a=3.316, cells=63, rcut=4.7, skin=1.0, mass=180.95, noise=0.05, label="configs[2] SNAP Ta BCC 2J=8 (500094 atoms) NVE")}
 
 
@@ -43,7 +44,7 @@ def main(which, steps=100, warmup=10, mixed=0):
         state["since"] = 0; state["rebuilds"] += 1
 
     def forces():
-        if which == "lj":
+        if which != "snap":
             ctx.zero_force_energy()
             ctx.pair_force([0.0104 * EV, 3.4], w["rcut"], xsb.FLAG_MIXED if mixed else 0)
         else:
