@@ -23,7 +23,7 @@ _FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
 ABI_SYMBOLS = [
     "xsb_create", "xsb_destroy", "xsb_last_error", "xsb_sync", "xsb_version", "xsb_kernel_launch_count",
     "xsb_profile_enable", "xsb_profile_read", "xsb_timer_record", "xsb_timer_elapsed_ms", "xsb_measure_peaks",
-    "xsb_grid_set", "xsb_particles_set_cells", "xsb_num_particles", "xsb_num_cells", "xsb_field_upload",
+    "xsb_grid_set", "xsb_grid_set_xform", "xsb_particles_set_cells", "xsb_num_particles", "xsb_num_cells", "xsb_field_upload",
     "xsb_field_download", "xsb_field_device_ptr", "xsb_zero_force_energy",
     "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
     "xsb_chunk_neighbors_export", "xsb_chunk_neighbors_download_flat",
@@ -98,6 +98,7 @@ def load_library():
     L.xsb_kernel_launch_count.argtypes = [vp]
     L.xsb_timer_record.argtypes = [vp, i32]
     L.xsb_timer_elapsed_ms.argtypes = [vp, C.POINTER(dbl)]
+    L.xsb_grid_set_xform.argtypes = [vp, C.POINTER(dbl)]
     L.xsb_measure_peaks.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
     L.xsb_profile_enable.argtypes = [vp, i32]
     L.xsb_profile_read.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(u64)]
@@ -202,6 +203,12 @@ class Context:
     def grid_set(self, grid):
         self.grid = grid
         self._ck(self.L.xsb_grid_set(self.h, C.byref(grid)), "xsb_grid_set")
+
+    def grid_set_xform(self, xform):
+        X = np.ascontiguousarray(xform, dtype=np.float64).reshape(9)
+        self._ck(self.L.xsb_grid_set_xform(self.h, X.ctypes.data_as(C.POINTER(C.c_double))), "xsb_grid_set_xform")
+        self.grid.xform[:] = [float(v) for v in X]
+        self.grid.xform_is_identity = int(np.array_equal(X.reshape(3, 3), np.eye(3)))
 
     def particles_set_cells(self, cell_off):
         off = np.ascontiguousarray(cell_off, dtype=np.uint64)

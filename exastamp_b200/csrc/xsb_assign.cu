@@ -195,7 +195,7 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
   {
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 1), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), 1.02));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (size_t(n) + 1) * sizeof(double), ctx->stream));
   }
   XSB_CUDA(ctx, ctx->type.reserve(size_t(n) + 16, 1.02)); XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, size_t(n) + 16, ctx->stream));

@@ -141,7 +141,7 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
     DevBuf<double>& b = ctx->f64[moved[k]];
     relayout_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p, b.p, reinterpret_cast<double*>(ctx->tmp64.p));
     XSB_LAUNCH_CHECK(ctx);
-    XSB_CUDA(ctx, b.reserve_keep(n + 1, 1.02, ctx->stream));
+    XSB_CUDA(ctx, b.reserve_keep(n + 16, 1.02, ctx->stream));      // stage rows are read up to the next 16-atom boundary
     XSB_CUDA(ctx, cudaMemcpyAsync(b.p, ctx->tmp64.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   if( n )
@@ -163,7 +163,7 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
     const int f = zeroed[k];
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 1), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), 1.02));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (size_t(n) + 1) * sizeof(double), ctx->stream));
   }
   return XSB_OK;
@@ -353,6 +353,23 @@ int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
   return XSB_OK;
 }
 
+int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
+{
+  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_REQUIRE(ctx, xform != nullptr, XSB_ERR_INVALID, "null xform");
+  XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
+  bool ident = true;
+  for(int i = 0; i < 9; i++)
+  {
+    XSB_REQUIRE(ctx, std::isfinite(xform[i]), XSB_ERR_INVALID, "xform is not finite");
+    ctx->grid.xform[i] = xform[i];
+    ident = ident && xform[i] == ((i % 4 == 0) ? 1.0 : 0.0);
+  }
+  ctx->grid.xform_is_identity = ident ? 1 : 0;
+  ctx->pos_epoch++;                 // physical distances changed: an in-range sub-list of the old cell is stale
+  return XSB_OK;
+}
+
 int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
@@ -368,7 +385,7 @@ int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
   {
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;   // allocated on first use
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (n + 1), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (n + 16), 1.02));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (n + 1) * sizeof(double), ctx->stream));
   }
   XSB_CUDA(ctx, ctx->type.reserve(n + 16, 1.02));

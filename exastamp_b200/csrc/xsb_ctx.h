@@ -108,6 +108,7 @@ struct xsb_ctx
   bool tile_ok = false;                       // false -> force operators use the generic CSR-gather kernels
   bool tile_deal = false;                     // A/B switch (env XSB_TILE_DEAL=1): tl_idx in bank-dealt order (xsb_nbr.cu)
   int tile_TX = 1, tile_R[3] = {1, 1, 1};
+  unsigned tile_align = 2;                    // row alignment (atoms) of the stage the list was built for (TileGeom::align)
   unsigned tile_s_cap = 0;                    // largest stage (atoms) over all tiles at build time
   double nbh_d2min = 0.0;                     // smallest pair distance^2 in the list at build time
   xsb::DevBuf<unsigned short> tl_idx;         // [total]
@@ -117,7 +118,7 @@ struct xsb_ctx
   xsb::DevBuf<unsigned short> sub_idx;        // [total]
   xsb::DevBuf<unsigned> sub_cnt;              // [n]
   xsb::DevBuf<double> pair_w;                 // [total] per-pair value cached by the pass that wrote the sub-list
-  int sub_pw_kind = 0;                        // what pair_w holds for the current sub-list: 0 nothing, 1 eam_alloy rho'(r), 2 johnson rho'(r)
+  int sub_pw_kind = 0;                        // what pair_w holds for the current sub-list: 0 nothing, 1 eam_alloy rho'(r), 2 johnson rho'(r), 3 eam_alloy multi-element (rhojp, rhoip)
   double sub_pw_johnson[19] = {};             // parameter set behind a kind-2 cache
   bool pair_cache_off = false;                // env XSB_NO_PAIR_CACHE=1: second pass re-evaluates instead (A/B profiling)
   uint64_t pos_epoch = 1, sub_epoch = 0;

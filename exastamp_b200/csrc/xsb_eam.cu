@@ -218,7 +218,7 @@ struct JohnsonForceTileOp
   }
   __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*) const
   { eval<false>(A, dx, dy, dz, d2, j, B, 0.0); }
-  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*, double pv) const
+  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*, double pv, double) const
   { eval<true>(A, dx, dy, dz, d2, j, B, pv); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
@@ -369,14 +369,15 @@ __global__ void __launch_bounds__(256) eam_alloy_force_kernel(ParticleView P, XF
 struct EamFcView
 {
   const double2* __restrict__ g;   // global {f, c5}: [ntab][nr+1], tables ordered rhor[nel] then z2r[npairs]
-  int nr, m_lo, rows, ntab_smem;   // smem window = rows [m_lo, m_lo+rows) of the first ntab_smem tables (rows = 0: none)
+  int nr, m_lo, rows, ntab_smem;   // smem window = rows [m_lo, m_lo+rows) of the tables [t0, t0+ntab_smem) (rows = 0: none)
+  int t0;
   double rdr;
   __host__ __device__ size_t table_bytes() const { return size_t(rows) * size_t(ntab_smem) * sizeof(double2); }
   __device__ __forceinline__ void load(unsigned char* smem, int nt) const
   {
     double2* sm = reinterpret_cast<double2*>(smem);
     const int tot = rows * ntab_smem;
-    for(int i = threadIdx.x; i < tot; i += nt) { const int t = i / rows, r = i - t * rows; sm[i] = g[size_t(t) * (nr + 1) + m_lo + r]; }
+    for(int i = threadIdx.x; i < tot; i += nt) { const int t = i / rows, r = i - t * rows; sm[i] = g[size_t(t0 + t) * (nr + 1) + m_lo + r]; }
   }
   __device__ __forceinline__ void lookup(double r, int& m, double& p) const
   {
@@ -389,7 +390,7 @@ struct EamFcView
   // knots m and m+1 of table t
   __device__ __forceinline__ void knots(const unsigned char* smem, int t, int m, double2& k0, double2& k1) const
   {
-    if( m >= m_lo ) { const double2* sm = reinterpret_cast<const double2*>(smem) + t * rows + (m - m_lo); k0 = sm[0]; k1 = sm[1]; }
+    if( m >= m_lo && t >= t0 ) { const double2* sm = reinterpret_cast<const double2*>(smem) + (t - t0) * rows + (m - m_lo); k0 = sm[0]; k1 = sm[1]; }
     else { const double2* q = g + size_t(t) * (nr + 1) + m; k0 = q[0]; k1 = q[1]; }
   }
 };
@@ -405,23 +406,33 @@ template<bool MULTI, bool PWO_>
 struct EamRhoTileOp
 {
   static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = true, PW_OUT = PWO_;
+  static constexpr int PW_N = MULTI ? 2 : 1;
   double rcut2; EamFcView T; double* rho_dEmb;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
   __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
-  struct Acc { double rho; };
-  __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; }
-  __device__ __forceinline__ void start(Acc&, unsigned, unsigned, const StageBuf<HAS_W, TYPES>&, const unsigned char*) const {}
+  struct Acc { double rho; int ta; };
+  __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; A.ta = 0; }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const { if( MULTI ) A.ta = B.t[sa]; }
   __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const { pair_d2(A, d2, j, B, tab); }
-  // returns rho'(r) of the neighbour's element (what the force pass calls rhojp): with PW_OUT the traversal keeps it
-  // next to the sub-list entry, so the force pass does not fetch these two knots again
-  __device__ __forceinline__ double pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  // Returns what the force pass of the same step needs again for this pair (PW_OUT: the traversal keeps it next to the
+  // sub-list entry, so that pass does not fetch the density knots again): rho'(r) of the neighbour's element (rhojp
+  // there) and, for a multi-element system, also rho'(r) of the central atom's element (rhoip).
+  __device__ __forceinline__ auto pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
   {
     const double r = d2 * rsqrt(d2);
     int m; double p; T.lookup(r, m, p);
-    double2 k0, k1; T.knots(tab, MULTI ? int(B.t[j]) : 0, m, k0, k1);    // density table of the NEIGHBOUR's element
+    const int tb = MULTI ? int(B.t[j]) : 0;
+    double2 k0, k1; T.knots(tab, tb, m, k0, k1);    // density table of the NEIGHBOUR's element
     double c3, c4; hermite_c(k0, k1, c3, c4);
     A.rho += ((c3 * p + c4) * p + k0.y) * p + k0.x;
-    return PWO_ ? ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr : 0.0;
+    const double rhojp = PWO_ ? ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr : 0.0;
+    if constexpr ( MULTI )
+    {
+      double rhoip = rhojp;
+      if( PWO_ && tb != A.ta ) { T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4); rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+      return make_double2(rhojp, rhoip);
+    }
+    else return rhojp;
   }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
@@ -434,6 +445,7 @@ template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_>
 struct EamForceTileOp
 {
   static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false, PW_IN = PWI_;
+  static constexpr int PW_N = MULTI ? 2 : 1;
   double rcut2; EamFcView T; int nel; double conv_z2r;
   double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
@@ -442,9 +454,10 @@ struct EamForceTileOp
   __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; A.ta = 0; if( VIRIAL ) A.v.zero(); }
   __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const
   { A.fpi = B.w[sa]; if( MULTI ) A.ta = B.t[sa]; }
-  // HAVE: rhojp_in = rho'(r) of the neighbour's element, cached by the rho pass of this step (same arithmetic)
+  // HAVE: rhojp_in / rhoip_in = rho'(r) of the neighbour's / the central atom's element, cached by the rho pass of this
+  // step (same arithmetic): only the pair table z2r is looked up here
   template<bool HAVE>
-  __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double rhojp_in) const
+  __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double rhojp_in, double rhoip_in) const
   {
     const double recip = rsqrt(d2), r = d2 * recip;
     int m; double p; T.lookup(r, m, p);
@@ -453,8 +466,7 @@ struct EamForceTileOp
     double rhoip, rhojp;
     if( HAVE )
     {
-      rhojp = rhojp_in; rhoip = rhojp_in;
-      if( MULTI && tb != A.ta ) { T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4); rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+      rhojp = rhojp_in; rhoip = MULTI ? rhoip_in : rhojp_in;
     }
     else
     {
@@ -476,9 +488,9 @@ struct EamForceTileOp
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
   __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
-  { eval<false>(A, dx, dy, dz, d2, j, B, tab, 0.0); }
-  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double pv) const
-  { eval<true>(A, dx, dy, dz, d2, j, B, tab, pv); }
+  { eval<false>(A, dx, dy, dz, d2, j, B, tab, 0.0, 0.0); }
+  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double pv, double pv2) const
+  { eval<true>(A, dx, dy, dz, d2, j, B, tab, pv, pv2); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
   {
     A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz);
@@ -491,10 +503,10 @@ struct EamForceTileOp
 // shared-memory window of the {f,c5} tables for a tile pass: rows [m_lo, nr] of the first ntab tables, as large a
 // window as the 227 KiB budget allows next to the 2 stage buffers (pairs below the window read the global copy)
 template<bool HAS_W, bool TYPES>
-static EamFcView make_fc_view(const xsb_ctx* ctx, int ntab, size_t queue_bytes)
+static EamFcView make_fc_view(const xsb_ctx* ctx, int t0, int ntab, size_t queue_bytes)
 {
   const EamAlloyDev& E = ctx->eam;
-  EamFcView T{ reinterpret_cast<const double2*>(E.fc.p), E.nr, INT_MAX, 0, ntab, E.rdr };
+  EamFcView T{ reinterpret_cast<const double2*>(E.fc.p), E.nr, INT_MAX, 0, ntab, t0, E.rdr };
   const size_t fixed = tile_smem_bytes<HAS_W, TYPES>(ctx->tile_s_cap, 0, queue_bytes, 2) + 256;
   if( fixed >= TILE_SMEM_MAX ) return T;
   const size_t max_rows = (TILE_SMEM_MAX - fixed) / (sizeof(double2) * size_t(ntab));
@@ -720,14 +732,14 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     // the force pass of this step reuses rho'(r) of every in-range pair: cache it only when that pass can follow
     const bool pwo = !ctx->pair_cache_off;
     ctx->sub_pw_kind = 0;
-    if( multi ) { if( pwo ) { EamRhoTileOp<true, true>   op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
-                  else      { EamRhoTileOp<true, false>  op{ rc2, make_fc_view<false, true >(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
-    else        { if( pwo ) { EamRhoTileOp<false, true>  op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
-                  else      { EamRhoTileOp<false, false> op{ rc2, make_fc_view<false, false>(ctx, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
+    if( multi ) { if( pwo ) { EamRhoTileOp<true, true>   op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+                  else      { EamRhoTileOp<true, false>  op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
+    else        { if( pwo ) { EamRhoTileOp<false, true>  op{ rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+                  else      { EamRhoTileOp<false, false> op{ rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
     ctx->prof_end(XSB_PROF_EAM_RHO);
     if( rc ) return rc;
     ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = ghost;
-    if( pwo ) ctx->sub_pw_kind = 1;
+    if( pwo ) ctx->sub_pw_kind = multi ? 3 : 1;      // 3: two values per pair (rhojp, rhoip)
   }
   if( !tile && (phases & XSB_EAM_RHO) && ctx->n )
   {
@@ -758,10 +770,11 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     int rc;
     ctx->prof_begin(XSB_PROF_EAM_FORCE);
     const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
-    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == 1 && !(multi && ctx->type_external);
+    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == (multi ? 3 : 1) && !(multi && ctx->type_external);
+    const int npair = E.nelements * (E.nelements + 1) / 2;
 #   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { \
-      if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
-      else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
+      if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, E.nelements, npair, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, 0, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
     if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
     else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
 #   undef XSB_EAM_TILE

@@ -112,63 +112,31 @@ constexpr int NBR_MAX_WORDS = 2048 / 32 + TILE_MAX_ROWS + 1;      // s_cap <= 20
 
 constexpr int NBR_MAX_TX = 8;                                       // widest tile (tile_plan)
 
+// 32-candidate "words" of ONE central cell: the cells [i-Rx, i+Rx] of every staged row, i = that cell (for TX > 1 a
+// sub-range of each staged row).  All atoms of the cell share the table; their survivor masks are indexed by word.
 struct NbrWords
 {
   unsigned short s[NBR_MAX_WORDS];     // stage index of bit 0
-  unsigned short e[NBR_MAX_WORDS];     // stage index one past the last valid candidate of the word's row
+  unsigned short e[NBR_MAX_WORDS];     // stage index one past the last candidate of the word's row window
   unsigned g[NBR_MAX_WORDS];           // flat particle index of bit 0
-  unsigned char r[NBR_MAX_WORDS];      // row of the stage the word belongs to
   unsigned n;
+  unsigned a_end;                      // flat index one past the last atom of the cell
 };
 
-// candidates of a central atom = the cells [i-Rx, i+Rx] of every staged row, i = its own cell: with TX > 1 that is a
-// sub-range [lo, hi) of each row, kept per (cell of the tile, row)
-struct NbrWindows
-{
-  unsigned short lo[NBR_MAX_TX][TILE_MAX_ROWS], hi[NBR_MAX_TX][TILE_MAX_ROWS];
-  unsigned cbeg[NBR_MAX_TX + 1];       // flat index of the first atom of each cell of the tile (cbeg[ncell] = end)
-  unsigned ncell;
-};
-
-// executed by one full warp after tile_meta_compute(G, ..., M)
-__device__ __forceinline__ void nbr_windows_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWindows& V)
-{
-  const int lane = threadIdx.x & 31;
-  const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX), nc = i1 - i0;
-  const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
-  for(int it = lane; it < nc * nrows; it += 32)
-  {
-    const int t = it / nrows, r = it - t * nrows, i = i0 + t;
-    const int kk = k + r / nry - G.Rz, jj = j + r % nry - G.Ry;
-    unsigned lo = 0, hi = 0;
-    if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz && M.s0[r + 1] > M.s0[r] )
-    {
-      const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
-      lo = M.s0[r] + (cell_start[row + max(0, i - G.Rx)] - M.g0[r]);
-      hi = M.s0[r] + (cell_start[row + min(G.nx, i + G.Rx + 1)] - M.g0[r]);
-    }
-    V.lo[t][r] = (unsigned short)lo; V.hi[t][r] = (unsigned short)hi;
-  }
-  const unsigned rowc = unsigned(G.nx) * (unsigned(j) + unsigned(G.ny) * unsigned(k));
-  if( lane <= nc ) V.cbeg[lane] = cell_start[rowc + i0 + lane];
-  if( lane == 0 ) V.ncell = unsigned(nc);
-}
-
-// executed by one full warp after tile_meta_compute(G, ..., M)
-__device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWords& W)
+// executed by one full warp after tile_meta_compute(G, ..., M): table of cell i (a cell of the tile (ti, j, k))
+__device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsigned* __restrict__ cell_start, int i, int j, int k, const TileMeta& M, NbrWords& W)
 {
   const unsigned lane = threadIdx.x & 31u;
-  const int i0 = ti * G.TX, i1 = min(G.nx, i0 + G.TX);
   const int nry = 2 * G.Ry + 1, nrows = nry * (2 * G.Rz + 1);
   unsigned b = 0, e = 0;
   if( int(lane) < nrows )
   {
     const int kk = k + int(lane) / nry - G.Rz, jj = j + int(lane) % nry - G.Ry;
-    if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz )
+    if( jj >= 0 && jj < G.ny && kk >= 0 && kk < G.nz && M.s0[lane + 1] > M.s0[lane] )
     {
       const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
-      const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
-      if( ge > gb ) { b = gb - (gb & ~1u); e = ge - (gb & ~1u); }      // valid (un-widened) part of the staged row
+      const unsigned gb = cell_start[row + max(0, i - G.Rx)], ge = cell_start[row + min(G.nx, i + G.Rx + 1)];
+      if( ge > gb ) { b = gb - M.g0[lane]; e = ge - M.g0[lane]; }      // window of this cell inside the staged (widened) row
     }
   }
   const unsigned nw = (e - b + 31u) >> 5;
@@ -180,10 +148,19 @@ __device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsig
     {
       W.s[pre - nw + q] = (unsigned short)(M.s0[lane] + b + 32u * q);
       W.e[pre - nw + q] = (unsigned short)(M.s0[lane] + e);
-      W.r[pre - nw + q] = (unsigned char)lane;
       W.g[pre - nw + q] = M.g0[lane] + b + 32u * q;
     }
   if( lane == 31 ) W.n = pre;
+  if( lane == 0 ) W.a_end = cell_start[unsigned(G.nx) * (unsigned(j) + unsigned(G.ny) * unsigned(k)) + unsigned(i) + 1u];
+}
+
+// the CTA's warps fill the tables of the tile's cells (after M is visible to all of them); caller barriers afterwards
+__device__ __forceinline__ unsigned nbr_tile_words(const TileGeom& G, const unsigned* __restrict__ cell_start, int ti, int j, int k, const TileMeta& M, NbrWords* Wc)
+{
+  const int i0 = ti * G.TX, nc = min(G.nx, i0 + G.TX) - i0;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for(int t = warp; t < nc; t += nwarps) nbr_words_compute(G, cell_start, i0 + t, j, k, M, Wc[t]);
+  return unsigned(nc);
 }
 
 __device__ __forceinline__ double lds_f64(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
@@ -198,19 +175,13 @@ __global__ void __launch_bounds__(512) nbr_count_kernel(TileGeom G, GridView gv,
 {
   extern __shared__ __align__(16) unsigned char nbr_smem[];
   __shared__ TileMeta M;
-  __shared__ NbrWords W;
-  __shared__ NbrWindows V;
+  __shared__ NbrWords Wc[NBR_MAX_TX];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
-  if( warp == 0 )
-  {
-    tile_meta_compute(G, cell_start, ti, j, k, M);
-    __syncwarp();
-    nbr_words_compute(G, cell_start, ti, j, k, M, W);
-    nbr_windows_compute(G, cell_start, ti, j, k, M, V);
-  }
+  if( warp == 0 ) tile_meta_compute(G, cell_start, ti, j, k, M);
   __syncthreads();
   if( M.a_begin == M.a_end ) return;
+  const unsigned ncell = nbr_tile_words(G, cell_start, ti, j, k, M, Wc);
   double* sxyz = reinterpret_cast<double*>(nbr_smem);
   for(unsigned r = warp; r < M.nrows; r += nwarps)
   {
@@ -218,34 +189,30 @@ __global__ void __launch_bounds__(512) nbr_count_kernel(TileGeom G, GridView gv,
     for(unsigned t = lane; t < len; t += 32u) { double* p = sxyz + 3u * (s0 + t); p[0] = rx[g0 + t]; p[1] = ry[g0 + t]; p[2] = rz[g0 + t]; }
   }
   __syncthreads();
-  const unsigned sbase = smem_u32(sxyz), nw = W.n, a_end = M.a_end, c_off = M.c_off;
+  const unsigned sbase = smem_u32(sxyz), a_end = M.a_end, c_off = M.c_off;
   int dmin_hi = 0x7fffffff;          // smallest d2 among the kept pairs, high word only (a lower bound within 2^-20)
   for(unsigned a = M.a_begin + warp; a < a_end; a += nwarps)
   {
+    unsigned t = 0;                                    // cell of the tile that holds atom a (warp-uniform)
+    while( t + 1 < ncell && a >= Wc[t].a_end ) ++t;
+    const NbrWords& W = Wc[t];
+    const unsigned nw = W.n;
     const unsigned sa = a + c_off;
     const double xa = lds_f64(sbase + 24u * sa), ya = lds_f64_8(sbase + 24u * sa), za = lds_f64_16(sbase + 24u * sa);
     unsigned cnt = 0, held = 0;
     unsigned* mrow = masks + size_t(a) * mask_stride;
-    unsigned t = 0;                                    // cell of the tile that holds atom a (warp-uniform)
-    while( t + 1 < V.ncell && a >= V.cbeg[t + 1] ) ++t;
     for(unsigned q = 0; q < nw; q++)
     {
-      const unsigned s0 = W.s[q], r = W.r[q];
-      const unsigned lo = V.lo[t][r], hi = V.hi[t][r];
-      unsigned m = 0u;
-      if( s0 < hi && s0 + 32u > lo )                   // the word overlaps the atom's window of this row
+      const unsigned sidx = unsigned(W.s[q]) + lane;
+      bool keep = false;
+      if( sidx < unsigned(W.e[q]) && sidx != sa )
       {
-        const unsigned sidx = s0 + lane;
-        bool keep = false;
-        if( sidx >= lo && sidx < hi && sidx != sa )
-        {
-          const unsigned ad = sbase + 24u * sidx;
-          const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
-          keep = d2 > 0.0 && d2 < d2max;
-          if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
-        }
-        m = __ballot_sync(0xffffffffu, keep);
+        const unsigned ad = sbase + 24u * sidx;
+        const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
+        keep = d2 > 0.0 && d2 < d2max;
+        if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
       }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
       cnt += __popc(m);
       if( (q & 31u) == lane ) held = m;
       if( (q & 31u) == 31u ) mrow[q - 31u + lane] = held;          // 32 words -> one coalesced 128-byte store
@@ -275,23 +242,24 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
 {
   extern __shared__ __align__(16) unsigned short deal_smem[];
   __shared__ TileMeta M;
-  __shared__ NbrWords W;
+  __shared__ NbrWords Wc[NBR_MAX_TX];
   __shared__ unsigned rcnt[8][16];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   int ti, j, k; tile_coords(G, blockIdx.x, ti, j, k);
-  if( warp == 0 )
-  {
-    tile_meta_compute(G, cell_start, ti, j, k, M);
-    __syncwarp();
-    nbr_words_compute(G, cell_start, ti, j, k, M, W);
-  }
+  if( warp == 0 ) tile_meta_compute(G, cell_start, ti, j, k, M);
   __syncthreads();
   if( M.a_begin == M.a_end ) return;
-  const unsigned nw = W.n, lt = (1u << lane) - 1u;
+  const unsigned ncell = nbr_tile_words(G, cell_start, ti, j, k, M, Wc);
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
   unsigned short* bidx = deal_smem + size_t(warp) * 2u * lcap;   // canonical stage indices of the current atom
   unsigned short* brk = bidx + lcap;                             // rank of each entry inside its residue class
   for(unsigned a = M.a_begin + warp; a < M.a_end; a += nwarps)
   {
+    unsigned tc = 0;
+    while( tc + 1 < ncell && a >= Wc[tc].a_end ) ++tc;
+    const NbrWords& W = Wc[tc];
+    const unsigned nw = W.n;
     const unsigned* mrow = masks + size_t(a) * mask_stride;
     unsigned short* o16 = idx16 + off[a];
     unsigned* o32 = idx32 + off[a];
@@ -303,7 +271,6 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
       for(unsigned t = 0; t < qe; t++)
       {
         const unsigned m = __shfl_sync(0xffffffffu, mine, t);
-        if( m == 0u ) continue;                                           // words outside the atom's window
         if( m >> lane & 1u )
         {
           const unsigned o = w + __popc(m & lt);
@@ -461,14 +428,15 @@ static int exclusive_scan_u64(xsb_ctx* ctx, const unsigned long long* in, unsign
 // Tile geometry for this grid + search range: TX cells per tile along x, largest stage over all tiles (host copy of
 // the cell offsets).  Returns false when the tile path cannot serve the list (search range > 2 cells in y/z, or a
 // stage larger than a uint16 index / the shared-memory budget): the generic CSR kernels are used then.
-static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, TileGeom& G, unsigned& s_cap)
+static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, unsigned align, TileGeom& G, unsigned& s_cap)
 {
   const xsb_grid_desc& g = ctx->grid;
   G = TileGeom{};
   G.nx = g.dims[0]; G.ny = g.dims[1]; G.nz = g.dims[2]; G.gl = g.ghost_layers;
-  G.Rx = R[0]; G.Ry = R[1]; G.Rz = R[2]; G.TX = TX; G.ghost = 1;
+  G.Rx = R[0]; G.Ry = R[1]; G.Rz = R[2]; G.TX = TX; G.ghost = 1; G.align = align;
   G.tiles_x = (G.nx + G.TX - 1) / G.TX;
   s_cap = 0;
+  const uint64_t am = align - 1;
   if( (2 * R[1] + 1) * (2 * R[2] + 1) > TILE_MAX_ROWS ) return false;
   const std::vector<uint64_t>& off = ctx->h_cell_off;
   // per x-row prefix: atoms in cells [i-Rx, i+TX+Rx) of row (j,k); stage = sum over the rows around (j,k)
@@ -480,7 +448,7 @@ static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, TileGeom& G, unsi
     {
       const int i0 = ti * G.TX, i1 = std::min(G.nx, i0 + G.TX);
       const uint64_t gb = off[row + std::max(0, i0 - G.Rx)], ge = off[row + std::min(G.nx, i1 + G.Rx)];
-      rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(j) + size_t(G.ny) * k)] = ge > gb ? unsigned(((ge + 1) & ~uint64_t(1)) - (gb & ~uint64_t(1))) : 0u;   // 16-byte widened, as tile_meta_compute
+      rowwin[size_t(ti) + size_t(G.tiles_x) * (size_t(j) + size_t(G.ny) * k)] = ge > gb ? unsigned(((ge + am) & ~am) - (gb & ~am)) : 0u;   // widened, as tile_meta_compute
     }
   }
   for(int k = 0; k < G.nz; k++) for(int j = 0; j < G.ny; j++) for(int ti = 0; ti < G.tiles_x; ti++)
@@ -494,8 +462,8 @@ static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, TileGeom& G, unsi
     }
     s_cap = std::max(s_cap, S);
   }
-  s_cap = (s_cap + 7u) & ~7u;
-  if( s_cap == 0 ) s_cap = 8;
+  s_cap = (s_cap + 15u) & ~15u;
+  if( s_cap == 0 ) s_cap = 16;
   // 2 stage buffers of x,y,z,w + types must leave room for the operator tables: cap a buffer at 64 KiB; the build
   // kernels index at most 2048 staged atoms (NBR_MAX_WORDS)
   if( s_cap > 2048u || size_t(s_cap) * 33 > 64 * 1024 ) return false;
@@ -510,7 +478,7 @@ static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, TileGeom& G, unsi
 // TX=1 1.356 / 5.65, TX=2 1.026 / 5.48, TX=3 0.978 / 5.88, TX=4 1.044 / 6.28, TX=6 1.037 / 7.28 -- beyond 3 the build
 // and the balance over the persistent CTAs lose more than the pair pass gains.  Dense cells (EAM Cu, ~58 atoms)
 // fill the stage with TX = 1.  XSB_TILE_TX=n forces a width (A/B runs).
-static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap)
+static bool tile_plan(xsb_ctx* ctx, const int R[3], unsigned align, TileGeom& G, unsigned& s_cap)
 {
   const xsb_grid_desc& g = ctx->grid;
   const char* fixed = getenv("XSB_TILE_TX");
@@ -519,7 +487,7 @@ static bool tile_plan(xsb_ctx* ctx, const int R[3], TileGeom& G, unsigned& s_cap
   {
     const size_t tiles = size_t((g.dims[0] + TX - 1) / TX) * g.dims[1] * g.dims[2];
     if( TX > 1 && !fixed && tiles < size_t(ctx->sm_count) * 8 ) continue;
-    if( tile_plan_tx(ctx, R, TX, G, s_cap) ) return true;
+    if( tile_plan_tx(ctx, R, TX, align, G, s_cap) ) return true;
     if( (2 * R[1] + 1) * (2 * R[2] + 1) > TILE_MAX_ROWS ) return false;
   }
   return false;
@@ -563,7 +531,20 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   const double *rx = ctx->f64[XSB_F_RX].p, *ry = ctx->f64[XSB_F_RY].p, *rz = ctx->f64[XSB_F_RZ].p;
   // tile path: the same fixed tiling the force kernels use; one CTA per tile with its 27-cell block staged in shared memory
   TileGeom TG; unsigned s_cap = 0;
-  const bool tile = tile_plan(ctx, R, TG, s_cap);
+  // multi-species system (any type byte != 0): stage rows on 16-atom boundaries so the type bytes travel by TMA as well
+  unsigned align = 2;
+  {
+    size_t tmp = 0; unsigned char* tmax = reinterpret_cast<unsigned char*>(ctx->tmp64.p + 1);
+    XSB_CUDA(ctx, cub::DeviceReduce::Max(nullptr, tmp, ctx->type.p, tmax, int(n), ctx->stream));
+    XSB_CUDA(ctx, ctx->scratch.reserve(tmp + 16));
+    XSB_CUDA(ctx, cub::DeviceReduce::Max(ctx->scratch.p, tmp, ctx->type.p, tmax, int(n), ctx->stream));
+    ctx->launches += 1;
+    unsigned char h = 0;
+    XSB_CUDA(ctx, cudaMemcpyAsync(&h, tmax, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if( h != 0 ) align = 16;
+  }
+  const bool tile = tile_plan(ctx, R, align, TG, s_cap);
   size_t tile_smem = 0;
   unsigned mask_stride = 0;
   if( tile )
@@ -581,8 +562,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     // survivor masks of the count sweep (one word per 32-candidate step), replayed by nbr_expand_kernel
     mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
     XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, 1.02));
-    // a large stage limits the CTAs per SM: keep the SM full of warps with wider CTAs
-    const int cblock = tile_smem > 26 * 1024 ? 512 : 256;
+    const int cblock = 256;      // 512-thread CTAs for large stages measured slower (C2: 6.96 -> 8.99 ms per rebuild)
     if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
     else                     nbr_count_kernel<true ><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
   }
@@ -630,7 +610,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double d2 = 0.0; if( bits != ~0ull ) std::memcpy(&d2, &bits, sizeof(d2));
     ctx->nbh_d2min = d2;
-    ctx->tile_ok = ok; ctx->tile_TX = G.TX; ctx->tile_R[0] = R[0]; ctx->tile_R[1] = R[1]; ctx->tile_R[2] = R[2]; ctx->tile_s_cap = s_cap;
+    ctx->tile_ok = ok; ctx->tile_TX = G.TX; ctx->tile_R[0] = R[0]; ctx->tile_R[1] = R[1]; ctx->tile_R[2] = R[2]; ctx->tile_s_cap = s_cap; ctx->tile_align = align;
   }
   ctx->prof_end(XSB_PROF_NBR_BUILD);
   ctx->nbh_built = true;

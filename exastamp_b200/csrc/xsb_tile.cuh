@@ -36,6 +36,8 @@ struct TileGeom
   unsigned s_cap;              // stage capacity (atoms) of one buffer
   int nbuf;                    // stage buffers in the ring (2 or 3)
   int ghost;                   // central atoms of ghost cells are processed too
+  unsigned align;              // staged rows start / end on multiples of `align` atoms: 2 (16-byte doubles for TMA), or 16
+                               // when the list was built for a multi-species system, so the type bytes can be TMA-copied too
 };
 
 struct TileMeta                // lives in shared memory, one per stage buffer
@@ -62,7 +64,8 @@ __device__ __forceinline__ void tile_meta_compute(const TileGeom& G, const unsig
     {
       const unsigned row = unsigned(G.nx) * (unsigned(jj) + unsigned(G.ny) * unsigned(kk));
       const unsigned gb = cell_start[row + max(0, i0 - G.Rx)], ge = cell_start[row + min(G.nx, i1 + G.Rx)];
-      if( ge > gb ) { g = gb & ~1u; len = ((ge + 1u) & ~1u) - g; }   // widen to even bounds: TMA bulk copies need 16-byte alignment
+      const unsigned am = G.align - 1u;
+      if( ge > gb ) { g = gb & ~am; len = ((ge + am) & ~am) - g; }   // widen to aligned bounds: TMA bulk copies need 16-byte alignment
     }
   }
   unsigned s = len;
@@ -161,19 +164,20 @@ __device__ __forceinline__ void tile_produce(const TileGeom& G, const unsigned* 
   tile_meta_compute(G, cell_start, ti, j, k, M);
   __syncwarp();
   const unsigned S = M.S, nrows = M.nrows;
-  if( TYPES )
+  const bool types_tma = TYPES && G.align >= 16u;
+  if( TYPES && !types_tma )
   {
-    for(unsigned s = lane; s < S; s += 32)
+    // rows only aligned to 2 atoms (list built before the types became multi-species): byte copy row by row
+    for(unsigned r = 0; r < nrows; r++)
     {
-      unsigned r = 0;
-      while( s >= M.s0[r + 1] ) ++r;
-      B.t[s] = F.type[M.g0[r] + (s - M.s0[r])];
+      const unsigned s0 = M.s0[r], cnt = M.s0[r + 1] - s0, g = M.g0[r];
+      for(unsigned i = lane; i < cnt; i += 32) B.t[s0 + i] = F.type[g + i];
     }
   }
   if( lane == 0 )
   {
     R.cursor[b] = 0;
-    mbar_arrive_expect_tx(&R.full[b], S * 8u * (HAS_W ? 4u : 3u));    // releases meta, cursor (and the type bytes after the syncwarp)
+    mbar_arrive_expect_tx(&R.full[b], S * 8u * (HAS_W ? 4u : 3u) + (types_tma ? S : 0u));    // releases meta, cursor (and byte-copied types after the syncwarp)
   }
   __syncwarp();
   if( S && unsigned(lane) < nrows )
@@ -185,6 +189,7 @@ __device__ __forceinline__ void tile_produce(const TileGeom& G, const unsigned* 
       bulk_g2s(B.y + s0, F.ry + g, cnt * 8u, &R.full[b]);
       bulk_g2s(B.z + s0, F.rz + g, cnt * 8u, &R.full[b]);
       if( HAS_W ) bulk_g2s(B.w + s0, F.w + g, cnt * 8u, &R.full[b]);
+      if( types_tma ) bulk_g2s(B.t + s0, F.type + g, cnt, &R.full[b]);
     }
   }
 }
@@ -203,7 +208,7 @@ inline TileGeom make_tile_geom(const xsb_ctx* ctx, bool ghost)
   TileGeom G{};
   const xsb_grid_desc& g = ctx->grid;
   G.nx = g.dims[0]; G.ny = g.dims[1]; G.nz = g.dims[2]; G.gl = g.ghost_layers;
-  G.TX = ctx->tile_TX; G.Rx = ctx->tile_R[0]; G.Ry = ctx->tile_R[1]; G.Rz = ctx->tile_R[2];
+  G.TX = ctx->tile_TX; G.Rx = ctx->tile_R[0]; G.Ry = ctx->tile_R[1]; G.Rz = ctx->tile_R[2]; G.align = ctx->tile_align;
   G.tiles_x = (G.nx + G.TX - 1) / G.TX;
   G.ghost = ghost ? 1 : 0;
   G.s_cap = ctx->tile_s_cap;
@@ -226,6 +231,7 @@ struct TileList
   unsigned short* __restrict__ sub_idx;
   unsigned* __restrict__ sub_cnt;               // [n]
   double* __restrict__ pair_w;                  // per-pair cache aligned with sub_idx (xsb_tilepass.cuh), may be null
+  size_t pw_plane;                              // offset (elements) of the second cached value of a pair, when an Op keeps two
 };
 
 enum { LIST_FULL = 0, LIST_FULL_WRITE_SUB = 1, LIST_SUB = 2 };

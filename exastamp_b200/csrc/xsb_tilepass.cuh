@@ -28,6 +28,11 @@ template<int NT> constexpr size_t tile_queue_bytes() { return size_t(NT / 32) * 
 
 template<class Op, class = void> struct op_pw_out : std::false_type {};
 template<class Op> struct op_pw_out<Op, std::void_t<decltype(Op::PW_OUT)>> : std::bool_constant<Op::PW_OUT> {};
+// number of cached values per pair (planes of TileList::pair_w): 1 unless the Op says PW_N = 2
+template<class Op, class = void> struct op_pw_n : std::integral_constant<int, 1> {};
+template<class Op> struct op_pw_n<Op, std::void_t<decltype(Op::PW_N)>> : std::integral_constant<int, Op::PW_N> {};
+__device__ __forceinline__ void pw_store(double* __restrict__ pw, size_t, unsigned k, double v) { pw[k] = v; }
+__device__ __forceinline__ void pw_store(double* __restrict__ pw, size_t plane, unsigned k, double2 v) { pw[k] = v.x; pw[plane + k] = v.y; }
 template<class Op, class = void> struct op_pw_in : std::false_type {};
 template<class Op> struct op_pw_in<Op, std::void_t<decltype(Op::PW_IN)>> : std::bool_constant<Op::PW_IN> {};
 
@@ -108,17 +113,18 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           const unsigned len = L.sub_cnt[a];
           unsigned e = sub;
           unsigned jn = e < len ? __ldcs(sp + e) : 0u;
-          double pvn = 0.0;
-          if( PWI && e < len ) pvn = __ldcs(pwp + e);
+          constexpr bool PW2 = PWI && op_pw_n<Op>::value == 2;
+          double pvn = 0.0, pvn2 = 0.0;
+          if( PWI && e < len ) { pvn = __ldcs(pwp + e); if( PW2 ) pvn2 = __ldcs(pwp + L.pw_plane + e); }
           while( e < len )
           {
             const unsigned j = jn;
-            const double pv = pvn;
+            const double pv = pvn, pv2 = pvn2;
             e += TPA;
-            if( e < len ) { jn = __ldcs(sp + e); if( PWI ) pvn = __ldcs(pwp + e); }   // next entry in flight while this pair is evaluated
+            if( e < len ) { jn = __ldcs(sp + e); if( PWI ) pvn = __ldcs(pwp + e); if( PW2 ) pvn2 = __ldcs(pwp + L.pw_plane + e); }   // next entry in flight while this pair is evaluated
             double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
             apply_xform<XFORM>(X, dx, dy, dz);
-            if constexpr ( PWI ) op.pair_pw(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem, pv);
+            if constexpr ( PWI ) op.pair_pw(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem, pv, pv2);
             else                 op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
           }
         }
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             {
               const unsigned slot = (qh + sub) & 63u;
               const unsigned qjv = QJ ? unsigned(qj[slot]) : 0u;
-              if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qjv, B, smem);
+              if constexpr ( PWO ) pw_store(pw, L.pw_plane, qh + sub, op.pair_d2(acc, qd[slot], qjv, B, smem));
               else                 op.pair_d2(acc, qd[slot], qjv, B, smem);
               qh += 32;
               __syncwarp();
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           {
             const unsigned slot = (qh + sub) & 63u;
             const unsigned qjv = QJ ? unsigned(qj[slot]) : 0u;
-            if constexpr ( PWO ) pw[qh + sub] = op.pair_d2(acc, qd[slot], qjv, B, smem);
+            if constexpr ( PWO ) pw_store(pw, L.pw_plane, qh + sub, op.pair_d2(acc, qd[slot], qjv, B, smem));
             else                 op.pair_d2(acc, qd[slot], qjv, B, smem);
           }
           __syncwarp();
@@ -247,9 +253,10 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
     XSB_CUDA(ctx, ctx->sub_idx.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
     XSB_CUDA(ctx, ctx->sub_cnt.reserve(size_t(ctx->n) + 1, 1.02));
   }
+  const size_t pw_plane = (size_t(ctx->nbh_total) + 63) & ~size_t(31);      // second cached value of a pair lives one plane further
   if( op_pw_out<Op>::value && queue && lmode == LIST_FULL_WRITE_SUB )
-    XSB_CUDA(ctx, ctx->pair_w.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p, ctx->pair_w.p };
+    XSB_CUDA(ctx, ctx->pair_w.reserve(pw_plane * size_t(op_pw_n<Op>::value) + 32, ctx->nbh_cfg.stream_prealloc_factor));
+  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p, ctx->pair_w.p, pw_plane };
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
   auto go = [&](auto kern) -> int

@@ -109,6 +109,10 @@ int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, do
 /* ---------------------------------------------------------------------------------------------------- */
 /* a1  Grid / GridCellParticles                                                                         */
 int      xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* grid);
+/* Domain::xform() changes every step under NPT / deformation (BASELINE configs[4]) while  */
+/* the grid, the particles and the neighbour list stay: only the 3x3 matrix (row-major) is replaced.  Like in  */
+/* the reference, rebuilding chunk_neighbors when the deformation has eaten the skin is the caller's decision. */
+int      xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9]);
 /* cell_particle_offset: host array of ncells+1 entries (exanb::Grid::cell_particle_offset_data()).     */
 int      xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* cell_particle_offset);
 uint64_t xsb_num_particles(const xsb_ctx* ctx);

@@ -673,3 +673,74 @@ def test_c2_full_size_parity_and_properties(tmp_path):
     O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, RCUT, 8 | 16, rfx, rfy, rfz, rep, None, emb)
     for a, b in ((fx, rfx), (fy, rfy), (fz, rfz), (ep, rep)):
         assert rel_err(a[own], b[own]) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ C5 kernel configuration
+@pytest.mark.parametrize("virial", [False, True])
+def test_c5_two_species_alloy_triclinic_two_phase(tmp_path, virial):
+    """BASELINE configs[4] in small: random two-species FCC alloy under an upper-triangular xform (NPT cell), eam_alloy_force
+    driven in two calls (rho | rho2emb | ghost, then force through the in-range sub-list + per-pair cache), energy and
+    virial on, plus lj_multi_force accumulated on top of it in the same force arrays"""
+    O = oracle()
+    X = np.array([[1.015, 0.02, -0.01], [0.0, 0.99, 0.015], [0.0, 0.0, 1.005]])
+    path = write_setfl(str(tmp_path / "ab.eam.alloy"), [SC_CU, SC_XX], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    rng = np.random.default_rng(21)
+    pos, typ, box = lattice("FCC", 6, 3.615, 0.06, seed=8)
+    typ = (rng.random(len(pos)) < 0.4).astype(np.uint8)                      # random alloy, 40 % of species 1
+    gs = GridSystem(pos, typ, box, 3.615 * 2, 2, xform=X)
+    g = gs.oracle_grid()
+    nbh, rcut = 6.9, 6.0
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    rfx, rfy, rfz, rep, emb = [gs.zeros() for _ in range(5)]
+    rvir = np.zeros((gs.n, 9)) if virial else None
+    fl = 16 | (32 if virial else 0)
+    eam = O.EamAlloy(path)
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, rcut, 1 | 2 | 4 | fl, rfx, rfy, rfz, rep, rvir, emb)
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, rcut, 8 | fl, rfx, rfy, rfz, rep, rvir, emb)
+    rows = np.array([[0.0104 * EV, 2.3, 6.0], [0.0150 * EV, 2.2, 5.5], [0.0200 * EV, 2.1, 5.0]])
+    ecut = [4 * e * ((s / rc) ** 12 - (s / rc) ** 6) for e, s, rc in rows]
+    O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, np.column_stack([rows, ecut]), rcut, 0, rfx, rfy, rfz, rep, rvir)
+    ctx = make_ctx(gs); ctx.eam_alloy_load(path); ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    vf = xsb.FLAG_VIRIAL if virial else 0
+    ctx.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG, vf)
+    ctx.eam_alloy_force(rcut, xsb.EAM_FORCE | xsb.EAM_EFLAG, vf)
+    ctx.pair_multi_force(2, rows, rcut, xsb.FLAG_ENERGY | vf)
+    own = ~gs.is_ghost
+    assert rel_err(ctx.download(xsb.F_RHO_DEMB), emb) < TOL64
+    for f, r in ((xsb.F_FX, rfx), (xsb.F_FY, rfy), (xsb.F_FZ, rfz), (xsb.F_EP, rep)):
+        assert rel_err(ctx.download(f)[own], r[own]) < TOL64
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL).reshape(-1, 9)[own], rvir[own]) < TOL64
+
+
+def test_grid_set_xform_keeps_list_and_matches_fresh_context(tmp_path):
+    """NPT: the cell matrix changes between steps, the grid / particles / neighbour list stay.  Forces after
+    xsb_grid_set_xform equal the oracle evaluated with the new matrix on the OLD list, and the stale sub-list is not reused"""
+    O = oracle()
+    X0 = np.array([[1.0, 0.02, 0.0], [0.0, 1.0, 0.01], [0.0, 0.0, 1.0]])
+    X1 = X0 * 1.004
+    path = write_setfl(str(tmp_path / "cu.eam.alloy"), [SC_CU], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    gs = system(ncells=6, a=3.615, sigma=0.05, cell=3.615 * 2, gl=2, xform=X0, seed=12)
+    g0 = gs.oracle_grid()
+    nb = O.Neighbors.build(g0, gs.cell_off, gs.rx, gs.ry, gs.rz, 7.0, 1, True)       # list of the old cell matrix
+    g1 = O.make_grid(gs.dims, gs.gl, gs.cell_size, gs.origin, X1)
+    ref = [gs.zeros() for _ in range(5)]
+    O.eam_alloy(g1, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 1 | 2 | 4 | 8 | 16, ref[0], ref[1], ref[2], ref[3], None, ref[4])
+    ctx = make_ctx(gs); ctx.eam_alloy_load(path); ctx.chunk_neighbors(7.0)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST)          # leaves a sub-list for X0
+    ctx.grid_set_xform(X1)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG)
+    ctx.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG)
+    own = ~gs.is_ghost
+    for f, r in ((xsb.F_FX, ref[0]), (xsb.F_FY, ref[1]), (xsb.F_FZ, ref[2]), (xsb.F_EP, ref[3])):
+        assert rel_err(ctx.download(f)[own], r[own]) < TOL64
+    # a force pass right after a matrix change must not walk the sub-list of the previous matrix
+    ctx.grid_set_xform(X0)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(6.0, xsb.EAM_FORCE)
+    ref0 = [gs.zeros() for _ in range(4)]
+    O.eam_alloy(g0, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 8, ref0[0], ref0[1], ref0[2], ref0[3], None, ctx.download(xsb.F_RHO_DEMB))
+    assert rel_err(ctx.download(xsb.F_FX)[own], ref0[0][own]) < TOL64
