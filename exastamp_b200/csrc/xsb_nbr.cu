@@ -119,6 +119,7 @@ struct NbrWords
   unsigned short s[NBR_MAX_WORDS];     // stage index of bit 0
   unsigned short e[NBR_MAX_WORDS];     // stage index one past the last candidate of the word's row window
   unsigned g[NBR_MAX_WORDS];           // flat particle index of bit 0
+  uint2 sc[NBR_MAX_WORDS];             // count sweep: { stage index of bit 0, valid candidates in the word (1..32) }
   unsigned n;
   unsigned a_end;                      // flat index one past the last atom of the cell
 };
@@ -149,6 +150,7 @@ __device__ __forceinline__ void nbr_words_compute(const TileGeom& G, const unsig
       W.s[pre - nw + q] = (unsigned short)(M.s0[lane] + b + 32u * q);
       W.e[pre - nw + q] = (unsigned short)(M.s0[lane] + e);
       W.g[pre - nw + q] = M.g0[lane] + b + 32u * q;
+      W.sc[pre - nw + q] = make_uint2(M.s0[lane] + b + 32u * q, min(32u, e - b - 32u * q));
     }
   if( lane == 31 ) W.n = pre;
   if( lane == 0 ) W.a_end = cell_start[unsigned(G.nx) * (unsigned(j) + unsigned(G.ny) * unsigned(k)) + unsigned(i) + 1u];
@@ -167,8 +169,16 @@ __device__ __forceinline__ double lds_f64(unsigned addr) { double v; asm volatil
 __device__ __forceinline__ double lds_f64_8(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ double lds_f64_16(unsigned addr) { double v; asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(v) : "r"(addr)); return v; }
 
+// Distance test of the count sweep.  Out of ~1500 staged candidates per atom only ~13 % survive, so the sweep runs in
+// FP32 on coordinates relative to the tile (12 B per staged atom instead of 24, FP32 pipe instead of FP64) and only
+// a candidate whose FP32 distance falls inside a guard band around the two thresholds (0 and nbh_dist^2) is decided by
+// the exact FP64 test in the reference's operation order (nbh_d2, positions re-read from global memory).  The band is
+// a bound on |d2_fp32 - d2_exact| for any candidate within 1 % of the cut-off (host: nbr_fp32_band); everything
+// farther away is classified correctly by a wide margin.  The resulting list is bit-identical to the all-FP64 sweep.
+struct NbrF32 { float m[9]; float d2max, band; int xform; };
+
 template<bool XFORM>
-__global__ void __launch_bounds__(512) nbr_count_kernel(TileGeom G, GridView gv, double d2max, const unsigned* __restrict__ cell_start,
+__global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv, double d2max, NbrF32 F, const unsigned* __restrict__ cell_start,
                                                          const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
                                                          unsigned* __restrict__ counts, unsigned* __restrict__ masks, unsigned mask_stride,
                                                          unsigned long long* __restrict__ d2min_bits)
@@ -182,49 +192,89 @@ __global__ void __launch_bounds__(512) nbr_count_kernel(TileGeom G, GridView gv,
   __syncthreads();
   if( M.a_begin == M.a_end ) return;
   const unsigned ncell = nbr_tile_words(G, cell_start, ti, j, k, M, Wc);
-  double* sxyz = reinterpret_cast<double*>(nbr_smem);
+  // coordinates relative to the first central atom of the tile, rounded to FP32 once
+  const double ox = rx[M.a_begin], oy = ry[M.a_begin], oz = rz[M.a_begin];
+  float* sxyz = reinterpret_cast<float*>(nbr_smem);
   for(unsigned r = warp; r < M.nrows; r += nwarps)
   {
     const unsigned s0 = M.s0[r], len = M.s0[r + 1] - s0, g0 = M.g0[r];
-    for(unsigned t = lane; t < len; t += 32u) { double* p = sxyz + 3u * (s0 + t); p[0] = rx[g0 + t]; p[1] = ry[g0 + t]; p[2] = rz[g0 + t]; }
+    for(unsigned t = lane; t < len; t += 32u)
+    {
+      float* p = sxyz + 3u * (s0 + t);
+      p[0] = float(rx[g0 + t] - ox); p[1] = float(ry[g0 + t] - oy); p[2] = float(rz[g0 + t] - oz);
+    }
   }
   __syncthreads();
-  const unsigned sbase = smem_u32(sxyz), a_end = M.a_end, c_off = M.c_off;
-  int dmin_hi = 0x7fffffff;          // smallest d2 among the kept pairs, high word only (a lower bound within 2^-20)
+  unsigned sbase = smem_u32(sxyz);
+  const unsigned a_end = M.a_end, c_off = M.c_off;
+  float lo_sure = F.band, hi_sure = F.d2max - F.band, hi_out = F.d2max + F.band;
+  // keep the loop invariants in registers (ptxas otherwise rebuilds the shared-memory base and the thresholds per word)
+  asm volatile("" : "+r"(sbase), "+f"(lo_sure), "+f"(hi_sure), "+f"(hi_out));
+  const unsigned lane12 = sbase + 12u * lane;
+  float dmin_f = 3.0e38f;            // smallest FP32 d2 among the kept pairs (sizes the EAM table window: a bound within 1e-3 is enough)
   for(unsigned a = M.a_begin + warp; a < a_end; a += nwarps)
   {
     unsigned t = 0;                                    // cell of the tile that holds atom a (warp-uniform)
     while( t + 1 < ncell && a >= Wc[t].a_end ) ++t;
     const NbrWords& W = Wc[t];
     const unsigned nw = W.n;
-    const unsigned sa = a + c_off;
-    const double xa = lds_f64(sbase + 24u * sa), ya = lds_f64_8(sbase + 24u * sa), za = lds_f64_16(sbase + 24u * sa);
-    unsigned cnt = 0, held = 0;
+    const unsigned ada = sbase + 12u * (a + c_off);
+    float xa, ya, za;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xa) : "r"(ada));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(ya) : "r"(ada));
+    asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(za) : "r"(ada));
+    unsigned cnt = 0;
     unsigned* mrow = masks + size_t(a) * mask_stride;
-    for(unsigned q = 0; q < nw; q++)
+    const unsigned wsc = smem_u32(&W.sc[0]);
+    for(unsigned q0 = 0; q0 < nw; q0 += 32u)
     {
-      const unsigned sidx = unsigned(W.s[q]) + lane;
-      bool keep = false;
-      if( sidx < unsigned(W.e[q]) && sidx != sa )
+      const unsigned qe = min(32u, nw - q0);
+      unsigned held = 0;
+      for(unsigned tq = 0; tq < qe; tq++)
       {
-        const unsigned ad = sbase + 24u * sidx;
-        const double d2 = nbh_d2<XFORM>(gv, lds_f64(ad) - xa, lds_f64_8(ad) - ya, lds_f64_16(ad) - za);
-        keep = d2 > 0.0 && d2 < d2max;
-        if( keep ) dmin_hi = min(dmin_hi, __double2hiint(d2));
+        unsigned ws, wc;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ws), "=r"(wc) : "r"(wsc + 8u * (q0 + tq)));
+        // branch-free body: lanes past the end of the word read a valid slot and are masked out
+        const unsigned ad = lane12 + 12u * ws;
+        float dx, dy, dz;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dx) : "r"(ad));
+        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(dy) : "r"(ad));
+        asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(dz) : "r"(ad));
+        dx -= xa; dy -= ya; dz -= za;
+        if( XFORM )
+        {
+          const float x = F.m[0] * dx + F.m[1] * dy + F.m[2] * dz, y = F.m[3] * dx + F.m[4] * dy + F.m[5] * dz, z = F.m[6] * dx + F.m[7] * dy + F.m[8] * dz;
+          dx = x; dy = y; dz = z;
+        }
+        const float d2f = dx * dx + dy * dy + dz * dz;
+        const bool valid = (lane < wc) & (ad != ada);
+        bool keep = valid & (d2f >= lo_sure) & (d2f < hi_sure);
+        const bool maybe = valid & !keep & (d2f <= hi_out);
+        if( __any_sync(0xffffffffu, maybe) )
+        {
+          // guard band (rare): the exact FP64 test in the reference's operation order decides
+          if( maybe )
+          {
+            const unsigned b = W.g[q0 + tq] + lane;
+            const double d2 = nbh_d2<XFORM>(gv, rx[b] - rx[a], ry[b] - ry[a], rz[b] - rz[a]);
+            keep = d2 > 0.0 && d2 < d2max;
+          }
+        }
+        dmin_f = fminf(dmin_f, keep ? d2f : 3.0e38f);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        cnt += __popc(m);
+        held = tq == lane ? m : held;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      cnt += __popc(m);
-      if( (q & 31u) == lane ) held = m;
-      if( (q & 31u) == 31u ) mrow[q - 31u + lane] = held;          // 32 words -> one coalesced 128-byte store
+      if( lane < qe ) mrow[q0 + lane] = held;          // up to 32 words -> one coalesced store
     }
-    if( (nw & 31u) && lane < (nw & 31u) ) mrow[(nw & ~31u) + lane] = held;
     if( lane == 0 ) counts[a] = cnt;
   }
 # pragma unroll
-  for(int o = 16; o > 0; o >>= 1) dmin_hi = min(dmin_hi, __shfl_xor_sync(0xffffffffu, dmin_hi, o));
-  if( lane == 0 && dmin_hi != 0x7fffffff )
+  for(int o = 16; o > 0; o >>= 1) dmin_f = fminf(dmin_f, __shfl_xor_sync(0xffffffffu, dmin_f, o));
+  if( lane == 0 && dmin_f < 3.0e38f )
   {
-    const unsigned long long bits = (unsigned long long)(unsigned)dmin_hi << 32;
+    const double lb = fmax(0.0, double(dmin_f) * (1.0 - 1.0e-3) - double(F.band));      // lower bound of the exact minimum
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(lb);
     if( bits < *d2min_bits ) atomicMin(d2min_bits, bits);
   }
 }
@@ -267,9 +317,10 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
     for(unsigned q0 = 0; q0 < nw; q0 += 32u)
     {
       const unsigned mine = q0 + lane < nw ? mrow[q0 + lane] : 0u;      // 32 words per coalesced load
-      const unsigned qe = min(32u, nw - q0);
-      for(unsigned t = 0; t < qe; t++)
+      unsigned todo = __ballot_sync(0xffffffffu, mine != 0u);             // most words have no survivor: visit the others only
+      while( todo )
       {
+        const unsigned t = __ffs(todo) - 1u; todo &= todo - 1u;
         const unsigned m = __shfl_sync(0xffffffffu, mine, t);
         if( m >> lane & 1u )
         {
@@ -428,6 +479,26 @@ static int exclusive_scan_u64(xsb_ctx* ctx, const unsigned long long* in, unsign
 // Tile geometry for this grid + search range: TX cells per tile along x, largest stage over all tiles (host copy of
 // the cell offsets).  Returns false when the tile path cannot serve the list (search range > 2 cells in y/z, or a
 // stage larger than a uint16 index / the shared-memory budget): the generic CSR kernels are used then.
+// bound on |d2_fp32 - d2_exact| of the count sweep for a candidate within 1 % of the cut-off (see nbr_count_kernel):
+// coordinates relative to a tile atom are below `ext` in magnitude, FP32 keeps them to 2^-24 * pow2(ext); the
+// difference of two of them adds one rounding; the xform (row sums <= mrow) three products and two sums per component.
+static NbrF32 nbr_fp32_band(const xsb_grid_desc& g, int TX, const int R[3], double dist)
+{
+  NbrF32 F{};
+  double mrow = 0.0;
+  for(int r = 0; r < 3; r++) { double s = 0; for(int c = 0; c < 3; c++) { s += std::fabs(g.xform[3*r + c]); F.m[3*r + c] = float(g.xform[3*r + c]); } mrow = std::max(mrow, s); }
+  F.xform = g.xform_is_identity ? 0 : 1;
+  if( g.xform_is_identity ) mrow = 1.0;
+  const double ext = (TX + 2 * std::max(R[0], std::max(R[1], R[2])) + 1) * g.cell_size;
+  double p2 = 1.0; while( p2 < ext ) p2 *= 2.0;
+  const double eps = std::ldexp(1.0, -24);
+  const double e_comp = 3.0 * eps * p2;                               // two roundings to FP32 + the subtraction
+  const double dv = mrow * (e_comp + 8.0 * eps * p2);                 // per physical component, products/sums in FP32 (and the FP32 copy of the matrix)
+  const double band = 2.0 * (2.0 * std::sqrt(3.0) * 1.01 * dist * dv + 16.0 * eps * dist * dist);
+  F.d2max = float(dist * dist); F.band = float(band + 2.0 * eps * dist * dist);      // + the rounding of d2max itself
+  return F;
+}
+
 static bool tile_plan_tx(xsb_ctx* ctx, const int R[3], int TX, unsigned align, TileGeom& G, unsigned& s_cap)
 {
   const xsb_grid_desc& g = ctx->grid;
@@ -551,7 +622,8 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   {
     TG.ghost = 1; TG.ti_lo = 0; TG.ti_n = TG.tiles_x; TG.j_lo = 0; TG.j_n = TG.ny; TG.k_lo = 0; TG.k_n = TG.nz;
     TG.ntiles = unsigned(TG.ti_n) * unsigned(TG.j_n) * unsigned(TG.k_n); TG.nbuf = 1;
-    tile_smem = size_t(s_cap) * 24;
+    tile_smem = (size_t(s_cap) + 32) * 12;      // + 32 slots: lanes past the end of the last word read (and discard) them
+    const NbrF32 F32 = nbr_fp32_band(ctx->grid, TG.TX, R, nbh_dist_lab);
     static bool attr_done = false;
     if( !attr_done )
     {
@@ -563,8 +635,8 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
     XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, 1.02));
     const int cblock = 256;      // 512-thread CTAs for large stages measured slower (C2: 6.96 -> 8.99 ms per rebuild)
-    if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
-    else                     nbr_count_kernel<true ><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
+    if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, F32, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
+    else                     nbr_count_kernel<true ><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, F32, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
   }
   else if( P.g.xform_identity ) nbr_sweep_kernel<false,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);
   else                          nbr_sweep_kernel<true ,false><<<grid, block, 0, ctx->stream>>>(P, ctx->cell_start.p, ctx->cell_of.p, rx, ry, rz, ctx->nbh_count.p, nullptr, nullptr, d2min);

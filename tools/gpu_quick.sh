@@ -7,6 +7,7 @@ timeout 300 python tools/side_bench.py lj 100 10 0 >> $O/${TAG}_side.json 2>> $O
 timeout 300 python tools/side_bench.py lj2m 40 5 0 >> $O/${TAG}_side.json 2>> $O/${TAG}.err
 timeout 600 python tools/side_bench.py c5 30 5 0 >> $O/${TAG}_side.json 2>> $O/${TAG}.err
 timeout 600 python bench.py --steps 40 --warmup 5 --no-e2e --no-cpu > $O/${TAG}_bench_short.json 2>> $O/${TAG}.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $O/${TAG}_launches.out 2>&1
 python - $O/${TAG}_side.json <<'PY'
 import json,sys
 for l in open(sys.argv[1]):
