@@ -21,6 +21,8 @@ from helpers import EV, lattice  # noqa: E402
 KB = 8.617333262e-5 * EV
 W = {"lj": dict(structure="FCC", a=5.0, cells=32, rcut=8.0, skin=1.0, mass=39.948, noise=0.1, label="configs[0] LJ Ar FCC 32^3 (131072 atoms) NVE"),
      "lj2m": dict(structure="FCC", a=5.0, cells=80, rcut=8.0, skin=1.0, mass=39.948, noise=0.1, label="LJ Ar FCC 80^3 (2048000 atoms) NVE (configs[0] potential at the C2 size)"),
+     "c2j": dict(structure="FCC", a=3.6, cells=79, rcut=5.8, skin=1.0, mass=63.546, noise=0.1,
+                 label="configs[1] analytic variant: johnson_force (Zhou/Johnson/Wadley Cu set) FCC 79^3 (1972156 atoms) NVE"),
      "c5": dict(structure="FCC", a=3.8, cells=126, rcut=6.6825, skin=1.0, mass=45.0, noise=0.08,
                 label="configs[4] two-species eam/alloy FCC 126^3 (8001504 atoms), NPT-like time-varying xform, periodic rebuild"),
      "snap": dict(structure="BCC", a=3.316, cells=63, rcut=4.7, skin=1.0, mass=180.95, noise=0.05, label="configs[2] SNAP Ta BCC 2J=8 (500094 atoms) NVE")}
@@ -66,6 +68,12 @@ def main(which, steps=100, warmup=10, mixed=0, cells=0):
             ctx.eam_alloy_force(w["rcut"], xsb.EAM_RHO | xsb.EAM_RHO2EMB | vf[0], vf[1])
             ctx.ghost_update([xsb.F_RHO_DEMB])
             ctx.eam_alloy_force(w["rcut"], xsb.EAM_FORCE | vf[0], vf[1])
+        elif which == "c2j":
+            from helpers import johnson_params
+            ctx.zero_force_energy()
+            ctx.eam_johnson_force(johnson_params(), w["rcut"], 1)                 # johnson_emb: rho -> F'(rho)
+            ctx.ghost_update([xsb.F_RHO_DEMB])
+            ctx.eam_johnson_force(johnson_params(), w["rcut"], 4)                 # johnson_force_reuse_emb
         elif which != "snap":
             ctx.zero_force_energy()
             ctx.pair_force([0.0104 * EV, 3.4], w["rcut"], xsb.FLAG_MIXED if mixed else 0)
