@@ -177,8 +177,8 @@ struct LJTileOp
     if( VIRIAL ) A.v.template reduce<TPA>();
     if( valid && sub == 0 )
     {
-      fx[a] += A.fx; fy[a] += A.fy; fz[a] += A.fz;
-      if( ep ) ep[a] += A.ep;
+      red_add(fx + a, A.fx); red_add(fy + a, A.fy); red_add(fz + a, A.fz);
+      if( ep ) red_add(ep + a, A.ep);
       if( VIRIAL ) A.v.store_add(vir, a);
     }
   }

@@ -71,6 +71,10 @@ __device__ __forceinline__ double snap_dsfac(const SnapConst& K, double r, doubl
 
 // mailbox layout per neighbour: source row m (published at level 2m+1, 2m+2 elements) starts at m(m+1)
 __device__ __forceinline__ int mbox_off(int m) { return m * (m + 1); }
+// a lane's mailbox is n double2 words; the 32 mailboxes of a warp are laid out with an odd stride (in 16-byte words) so
+// that the lanes of a quarter-warp hit 8 different bank groups: with the natural stride (a multiple of 128 bytes at
+// 2J = 8) every mailbox access was an 8-way bank conflict (ncu: 590 M shared wavefronts for 149 M ideal)
+#define SNAP_MBOX_STRIDE(n) (((n) | 1))
 
 // One sweep over the levels for the thread's (neighbour, row mb).  DERIV = false: accumulate sfac*wj*u into utot (shuffle
 // reduction over the lanes).  DERIV = true: carry du/dr_k, contract with Y -> dedr[3].
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
   double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
   double2* mbox = ylist + K.idxu_max;                                   // [32][4 * MB]
-  double* nb_x = reinterpret_cast<double*>(mbox + 32 * 4 * (MB ? MB : 1));   // [SNAP_NN_MAX] x 5
+  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)));   // [SNAP_NN_MAX] x 5
   double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
   unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
   double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32][3] + scratch
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
     const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    snap_sweep<TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * 4 * (MB ? MB : 1), dummy);
+    snap_sweep<TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dummy);
   }
   __syncthreads();
   mark(1);
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     const unsigned n = b0 + lane; const bool valid = n < nn;
     const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
     double dedr[3];
-    snap_sweep<TJ, true>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * 4 * (MB ? MB : 1), dedr);
+    snap_sweep<TJ, true>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dedr);
     red[(mb * 32 + lane) * 3 + 0] = dedr[0]; red[(mb * 32 + lane) * 3 + 1] = dedr[1]; red[(mb * 32 + lane) * 3 + 2] = dedr[2];
     __syncthreads();
     if( mb == 0 && valid )
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
   double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
   double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
   double2* mbox = ylist + K.idxu_max;                                   // [32][3][MBS]
-  double* nb_x = reinterpret_cast<double*>(mbox + 32 * 3 * MBS);        // [SNAP_NN_MAX] x 5
+  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(3 * MBS));        // [SNAP_NN_MAX] x 5
   double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
   unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
   double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NW][32]
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
     const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + (lane * 3 + kd) * MBS);
+    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(3 * MBS) + kd * MBS);
     red[wrp * 32 + lane] = d;
     __syncthreads();
     if( wrp == 0 && valid )
@@ -822,7 +826,7 @@ template<int TJ>
 static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR, MB = (TJ / 2) * (TJ / 2 + 1);
-  const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * 4 * (MB ? MB : 1) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
+  const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
                     + size_t(NR) * 32 * 3 * sizeof(double) + 64;
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
@@ -841,7 +845,7 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
   const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
   XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
   A.ubuf = S->ubuf.p; A.ybuf = S->ybuf.p;
-  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * 3 * 2 * (MB ? MB : 1) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
+  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
                      + size_t(3 * NR) * 32 * sizeof(double) + 64;
   // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
   // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)

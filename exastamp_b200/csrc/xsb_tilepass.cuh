@@ -33,6 +33,9 @@ template<class Op, class = void> struct op_pw_n : std::integral_constant<int, 1>
 template<class Op> struct op_pw_n<Op, std::void_t<decltype(Op::PW_N)>> : std::integral_constant<int, Op::PW_N> {};
 __device__ __forceinline__ void pw_store(double* __restrict__ pw, size_t, unsigned k, double v) { pw[k] = v; }
 __device__ __forceinline__ void pw_store(double* __restrict__ pw, size_t plane, unsigned k, double2 v) { pw[k] = v.x; pw[plane + k] = v.y; }
+// an Op at the register limit of its launch shape opts out of the one-atom-ahead window prefetch (NO_AHEAD = true)
+template<class Op, class = void> struct op_no_ahead : std::false_type {};
+template<class Op> struct op_no_ahead<Op, std::void_t<decltype(Op::NO_AHEAD)>> : std::bool_constant<Op::NO_AHEAD> {};
 template<class Op, class = void> struct op_pw_in : std::false_type {};
 template<class Op> struct op_pw_in<Op, std::void_t<decltype(Op::PW_IN)>> : std::bool_constant<Op::PW_IN> {};
 
@@ -88,12 +91,28 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
     const TileMeta& M = R.meta[b];
     const unsigned a_begin = M.a_begin, na = M.a_end - M.a_begin, c_off = M.c_off;
     Stage B; B.bind(stage_mem + size_t(b) * bb, G.s_cap);
-    for(;;)
+    // Atoms are grabbed one ahead: the list window (offset, length) of the next atom is loaded while the current one is
+    // processed, so a warp starts an atom with one dependent global load (its first list entry) instead of two or three
+    // (ncu: 39 % of the force pass's stall samples were in the per-atom prologue / epilogue).
+    auto grab = [&]() -> unsigned { unsigned k = 0; if( lane == 0 ) k = atomicAdd(&R.cursor[b], GPW); return __shfl_sync(0xffffffffu, k, 0); };
+    auto window = [&](unsigned k, unsigned long long& e0w, unsigned& lenw)
     {
-      unsigned k0 = 0;
-      if( lane == 0 ) k0 = atomicAdd(&R.cursor[b], GPW);
-      k0 = __shfl_sync(0xffffffffu, k0, 0);
-      if( k0 >= na ) break;
+      e0w = 0ull; lenw = 0u;
+      if( k + gsel < na )
+      {
+        const unsigned aw = a_begin + k + gsel;
+        e0w = L.off[aw];
+        lenw = LMODE == LIST_SUB ? L.sub_cnt[aw] : unsigned(L.off[aw + 1] - e0w);
+      }
+    };
+    unsigned k0 = grab();
+    unsigned long long e0 = 0ull; unsigned len = 0u;
+    window(k0, e0, len);
+    constexpr bool AHEAD = !op_no_ahead<Op>::value;
+    while( k0 < na )
+    {
+      unsigned k0n = 0; unsigned long long e0n = 0ull; unsigned lenn = 0u;
+      if constexpr ( AHEAD ) { k0n = grab(); window(k0n, e0n, lenn); }
       const bool valid = k0 + gsel < na;
       const unsigned a = a_begin + k0 + gsel;
       typename Op::Acc acc;
@@ -103,14 +122,12 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         const unsigned sa = a + c_off;
         const double xa = B.x[sa], ya = B.y[sa], za = B.z[sa];
         op.start(acc, a, sa, B, smem);
-        // per-atom list window: 64-bit base pointers once, 32-bit indices inside the loops
-        const unsigned long long e0 = L.off[a];
+        // per-atom list window [e0, e0 + len): 64-bit base pointers once, 32-bit indices inside the loops
         if constexpr ( LMODE == LIST_SUB )
         {
           // dense: every entry is in range (filtered by the pass that wrote the sub-list on these positions)
           const unsigned short* __restrict__ sp = L.sub_idx + e0;
           const double* __restrict__ pwp = L.pair_w + e0;
-          const unsigned len = L.sub_cnt[a];
           unsigned e = sub;
           unsigned jn = e < len ? __ldcs(sp + e) : 0u;
           constexpr bool PW2 = PWI && op_pw_n<Op>::value == 2;
@@ -136,7 +153,6 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           unsigned short* qj = reinterpret_cast<unsigned short*>(qmem + size_t(NT / 32) * TILE_QUEUE_SLOTS * sizeof(double)) + warp * TILE_QUEUE_SLOTS;
           const unsigned short* __restrict__ lp = L.idx + e0;
           unsigned short* __restrict__ wp = L.sub_idx + e0;
-          const unsigned len = unsigned(L.off[a + 1] - e0);
           const unsigned lt = (1u << sub) - 1u;
           // branch-free filter step with 32-bit shared addressing: lanes past the end of the list test stage slot 0 and are
           // masked out of the ballot
@@ -202,7 +218,6 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         {
           const unsigned short* __restrict__ lp = L.idx + e0;
           unsigned short* __restrict__ wp = L.sub_idx + e0;
-          const unsigned len = unsigned(L.off[a + 1] - e0);
           unsigned cnt = 0;
           unsigned jn = sub < len ? __ldcs(lp + sub) : 0u;
           for(unsigned e = 0; e < len; e += TPA)
@@ -230,6 +245,8 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         }
       }
       op.template finish<TPA>(acc, a, valid, sub);
+      if constexpr ( AHEAD ) { k0 = k0n; e0 = e0n; len = lenn; }
+      else { k0 = grab(); window(k0, e0, len); }
     }
     __syncwarp();
     if( lane == 0 ) mbar_arrive(&R.empty[b]);       // this warp will not touch buffer b again until it is refilled
@@ -301,7 +318,7 @@ struct Vir9
     for(int k = 0; k < 9; k++) v[k] = group_sum<TPA>(v[k]); }
   __device__ __forceinline__ void store_add(double* vir, unsigned a) const { double* p = vir + 9ull * a;
 #   pragma unroll
-    for(int k = 0; k < 9; k++) p[k] += v[k]; }
+    for(int k = 0; k < 9; k++) red_add(p + k, v[k]); }
 };
 
 } // namespace xsb

@@ -16,6 +16,10 @@ __device__ __forceinline__ double group_sum(double v)
   return v;
 }
 
+// `*p += v` by the single writer of an atom as a fire-and-forget reduction (RED.E.ADD.F64 at L2): same IEEE addition as
+// load-add-store, but the warp does not wait for the load (ncu: ~9 % of the force pass's stall samples sat on those loads)
+__device__ __forceinline__ void red_add(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
+
 struct XForm { double m[9]; };
 
 template<bool XFORM>
