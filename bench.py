@@ -324,6 +324,7 @@ def run_xsb(args):
                                     "xsb_field_download of fx,fy,fz,ep" % args.rebuild_every}
 
     if rank != 0:
+        dist.barrier(); dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernels (eam_alloy rho and force passes), algorithmic bytes / flops per SURVEY.md 8(d)
     peaks = {}
@@ -373,7 +374,7 @@ def run_xsb(args):
                                      "fp64": {"achieved": fl_rho * n_own / dr / 1e12, "peak": live_fp64, "frac": fl_rho * n_own / dr / 1e12 / live_fp64 if live_fp64 else None}}
     breakdown = {k: {"ms_total": v[0], "intervals": v[1], "share": v[0] / ms if ms else None} for k, v in prof.items() if v[1]}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:          # the CPU baseline is timed beside the 1-GPU run only
         v, info = cpu_reference_run(args.cpu_sample_cells, 2, args.rebuild_every)
         cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
                "sample": "EAM Cu FCC %d^3 unit cells = %d atoms, same potential/cutoffs; 2 force steps + list build/%d (oracle restatement, OpenMP)" % (
@@ -385,7 +386,9 @@ def run_xsb(args):
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
                        "rebuilds_in_timed_region": state["rebuilds"] - rb0, "rebuild_wall_s_total": state["rebuild_s"],
                        "move_particles_wall_s_total": state["move_s"], "host_wall_s": wall, "breakdown": breakdown}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
 
 
 def main():

@@ -368,10 +368,37 @@ __global__ void migrate_dest_kernel(unsigned n, MigrateParams M, double* __restr
   atomicAdd(&counts[dest], 1ull);
 }
 
-template<class T> __global__ void migrate_gather_kernel(unsigned n, const unsigned* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst)
+// particles that stay on this rank: sorted positions [lo, lo + stay) -> their slots [r0, r0 + stay) of the new arrays
+struct MigFields { const unsigned long long* src[7]; unsigned long long* dst[7]; };
+__global__ void migrate_stay_kernel(unsigned stay, unsigned lo, unsigned r0, const unsigned* __restrict__ perm, MigFields F,
+                                    const unsigned char* __restrict__ tsrc, unsigned char* __restrict__ tdst)
 {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if( i < n ) dst[i] = src[perm[i]];
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= stay ) return;
+  const unsigned s = perm[lo + t];
+# pragma unroll
+  for(int k = 0; k < 7; k++) F.dst[k][r0 + t] = F.src[k][s];
+  tdst[r0 + t] = tsrc[s];
+}
+// particles that leave: one 64-byte record each (7 fields + type), in destination order, so a peer gets ONE message
+__global__ void migrate_pack_kernel(unsigned nl, unsigned lo, unsigned stay, const unsigned* __restrict__ perm, MigFields F,
+                                    const unsigned char* __restrict__ tsrc, unsigned long long* __restrict__ rec)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= nl ) return;
+  const unsigned s = perm[t < lo ? t : t + stay];
+# pragma unroll
+  for(int k = 0; k < 7; k++) rec[8ull * t + k] = F.src[k][s];
+  rec[8ull * t + 7] = tsrc[s];
+}
+__global__ void migrate_unpack_kernel(unsigned nin, unsigned r0, unsigned stay, const unsigned long long* __restrict__ rec, MigFields F, unsigned char* __restrict__ tdst)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= nin ) return;
+  const unsigned d = t < r0 ? t : t + stay;
+# pragma unroll
+  for(int k = 0; k < 7; k++) F.dst[k][d] = rec[8ull * t + k];
+  tdst[d] = (unsigned char)rec[8ull * t + 7];
 }
 } // namespace xsb
 
@@ -417,34 +444,30 @@ int xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, d
   XSB_REQUIRE(ctx, soff[P] == n, XSB_ERR_STATE, "migrate: destination counts do not add up");
   const size_t nn = roff[P];
   XSB_REQUIRE(ctx, nn < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU after migration");
-  // sorted-by-destination copies, then the receive arrays (segment q = particles arriving from rank q, self included)
-  XSB_CUDA(ctx, ctx->move_stage_b.reserve(7 * (size_t(n) + 1), 1.02)); XSB_CUDA(ctx, ctx->move_stage8_b.reserve(size_t(n) + 16, 1.02));
+  // receive arrays: segment q = particles arriving from rank q, self included.  Stayers are gathered straight into
+  // their segment; leavers travel as 64-byte records, one grouped send/recv per peer (not one per field).
+  const size_t stay = soff[me + 1] - soff[me], nl = n - stay, nin = nn - stay;
+  XSB_CUDA(ctx, ctx->move_stage_b.reserve(8 * std::max<size_t>(nl + nin, size_t(n) / 16 + 4096) + 16, 2.0));      // record buffers: sized once, well above the usual traffic (a re-allocation synchronises the device)
   XSB_CUDA(ctx, ctx->move_stage_c.reserve(7 * (nn + 1), 1.05)); XSB_CUDA(ctx, ctx->move_stage8_c.reserve(nn + 16, 1.05));
-  double* s[7]; for(int k = 0; k < 7; k++) { s[k] = ctx->move_stage_b.p + size_t(k) * (n + 1); e[k] = ctx->move_stage_c.p + size_t(k) * (nn + 1); }
-  unsigned char* st8 = ctx->move_stage8_b.p; unsigned char* et8 = ctx->move_stage8_c.p;
-  if( n )
-  {
-    for(int k = 0; k < 7; k++) migrate_gather_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(n, perm, reinterpret_cast<const unsigned long long*>(d[k]), reinterpret_cast<unsigned long long*>(s[k]));
-    migrate_gather_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>(n, perm, types, st8);
-    ctx->launches += 8; cudaError_t le = cudaGetLastError(); if( le != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "migrate gather: %s", cudaGetErrorString(le));
-  }
-  const size_t stay = soff[me + 1] - soff[me];
-  for(int k = 0; k < 7 && stay; k++) XSB_CUDA(ctx, cudaMemcpyAsync(e[k] + roff[me], s[k] + soff[me], stay * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  if( stay ) XSB_CUDA(ctx, cudaMemcpyAsync(et8 + roff[me], st8 + soff[me], stay, cudaMemcpyDeviceToDevice, ctx->stream));
+  for(int k = 0; k < 7; k++) e[k] = ctx->move_stage_c.p + size_t(k) * (nn + 1);
+  unsigned char* et8 = ctx->move_stage8_c.p;
+  unsigned long long* srec = reinterpret_cast<unsigned long long*>(ctx->move_stage_b.p);
+  unsigned long long* rrec = srec + 8 * nl;
+  MigFields F;
+  for(int k = 0; k < 7; k++) { F.src[k] = reinterpret_cast<const unsigned long long*>(d[k]); F.dst[k] = reinterpret_cast<unsigned long long*>(e[k]); }
+  if( stay ) { migrate_stay_kernel<<<unsigned((stay + 255) / 256), 256, 0, ctx->stream>>>(unsigned(stay), unsigned(soff[me]), unsigned(roff[me]), perm, F, types, et8); XSB_LAUNCH_CHECK(ctx); }
+  if( nl ) { migrate_pack_kernel<<<unsigned((nl + 255) / 256), 256, 0, ctx->stream>>>(unsigned(nl), unsigned(soff[me]), unsigned(stay), perm, F, types, srec); XSB_LAUNCH_CHECK(ctx); }
   XSB_NCCL(ctx, g_nccl.GroupStart());
   for(int q = 0; q < P; q++)
   {
     if( q == me ) continue;
     const size_t sc = soff[q + 1] - soff[q], rcnt = roff[q + 1] - roff[q];
-    for(int k = 0; k < 7; k++)
-    {
-      if( sc ) XSB_NCCL(ctx, g_nccl.Send(s[k] + soff[q], sc, NCCL_UINT64, q, ctx->comm, ctx->stream));
-      if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(e[k] + roff[q], rcnt, NCCL_UINT64, q, ctx->comm, ctx->stream));
-    }
-    if( sc ) XSB_NCCL(ctx, g_nccl.Send(st8 + soff[q], sc, NCCL_UINT8, q, ctx->comm, ctx->stream));
-    if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(et8 + roff[q], rcnt, NCCL_UINT8, q, ctx->comm, ctx->stream));
+    const size_t cs = soff[q] - (q > me ? stay : 0), cr = roff[q] - (q > me ? stay : 0);      // offsets without the self segment
+    if( sc ) XSB_NCCL(ctx, g_nccl.Send(srec + 8 * cs, 8 * sc, NCCL_UINT64, q, ctx->comm, ctx->stream));
+    if( rcnt ) XSB_NCCL(ctx, g_nccl.Recv(rrec + 8 * cr, 8 * rcnt, NCCL_UINT64, q, ctx->comm, ctx->stream));
   }
   XSB_NCCL(ctx, g_nccl.GroupEnd());
+  if( nin ) { migrate_unpack_kernel<<<unsigned((nin + 255) / 256), 256, 0, ctx->stream>>>(unsigned(nin), unsigned(roff[me]), unsigned(stay), rrec, F, et8); XSB_LAUNCH_CHECK(ctx); }
   ctx->migrated_out = n - stay; ctx->migrated_in = nn - stay;
   *n_new = unsigned(nn); *types_new = et8;
   return XSB_OK;
