@@ -49,6 +49,7 @@ struct SnapDev
   DevBuf<unsigned long long> clk; bool clocks = false;
   DevBuf<SnapZ> zsort; DevBuf<double> betaz_sort; DevBuf<int4> ytask; int n_ytask = 0;   // snap_y_kernel work items
   DevBuf<double2> ubuf, ybuf;                                                          // chunk staging (AoSoA)
+  DevBuf<double> nbtab; DevBuf<unsigned> nbcnt;                                        // in-range neighbours of the chunk's atoms (Utot kernel -> force kernel)
   double rcut_max = 0.0;
 };
 
@@ -364,6 +365,8 @@ struct SnapArgs
   unsigned long long* clk;     // optional per-phase cycle counters (tools/snap_bench.py --clocks), nullptr in production
   // split pipeline (snap_u -> snap_y -> snap_f): Utot and Y of the atoms of one chunk, AoSoA [atom / 32][jju][atom % 32]
   double2* ubuf; double2* ybuf; unsigned base;      // base = first central atom (position in the launch's atom list) of the chunk
+  // in-range neighbours found by the Utot kernel, per chunk slot: 6 rows of SNAP_NN_MAX doubles (dx, dy, dz, wj, rc, index bits)
+  double* nbtab; unsigned* nbcnt;
   const SnapZ* __restrict__ zsort; const double* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
 };
 
@@ -432,6 +435,16 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   }
   __syncthreads();
   const unsigned nn = s_nn;
+  if( PHASE == 1 && A.nbtab && mb == 0 )
+  {
+    double* t = A.nbtab + size_t(blockIdx.x) * 6 * SNAP_NN_MAX;
+    for(unsigned i = lane; i < nn; i += 32)
+    {
+      t[i] = nb_x[i]; t[SNAP_NN_MAX + i] = nb_y[i]; t[2 * SNAP_NN_MAX + i] = nb_z[i]; t[3 * SNAP_NN_MAX + i] = nb_w[i]; t[4 * SNAP_NN_MAX + i] = nb_rc[i];
+      t[5 * SNAP_NN_MAX + i] = __longlong_as_double((long long)nb_g[i]);
+    }
+    if( lane == 0 ) A.nbcnt[blockIdx.x] = nn;
+  }
   mark(0);
 
   // ---- sweep 1: Utot
@@ -679,6 +692,108 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
   }
 }
 
+// ---- force kernel, one CTA per (atom, Cartesian direction): J/2+1 warps = rows, lane = neighbour ------------------------
+// Same sweep as snap_f_kernel, but the three directions of an atom are three independent CTAs of 160 threads (2J = 8):
+// three of them fit the register file of an SM, so the serial prologue of one (neighbour filter: four dependent global
+// loads; Y fetch) overlaps the sweeps of the others, and a barrier only joins 5 warps instead of 15.  The neighbour
+// filter and the Y fetch are repeated per direction (cheap against the sweep); the energy is computed by direction 0.
+template<int TJ, bool XFORM>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+{
+  constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = 2 * (MB ? MB : 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* ylist = reinterpret_cast<double2*>(smem_raw);                // [idxu_max]
+  double2* mbox = ylist + K.idxu_max;                                   // [32][MBS] (odd stride)
+  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(MBS));        // [SNAP_NN_MAX] x 5
+  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
+  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32]
+  __shared__ unsigned s_nn;
+  const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
+  const unsigned at = blockIdx.x / 3u; const int kd = int(blockIdx.x % 3u);
+  const unsigned slot = A.base + at;
+  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
+  const size_t soa = (size_t(at >> 5) * K.idxu_max) * 32 + (at & 31u);
+  const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
+  const int ei = A.type ? A.type[ai] : 0;
+  if( mb == 0 )
+  {
+    // the Utot kernel of this chunk left the in-range neighbours of every slot: one coalesced read instead of the list walk
+    const unsigned nn = A.nbcnt[at];
+    const double* t = A.nbtab + size_t(at) * 6 * SNAP_NN_MAX;
+    for(unsigned i = lane; i < nn; i += 32)
+    {
+      nb_x[i] = t[i]; nb_y[i] = t[SNAP_NN_MAX + i]; nb_z[i] = t[2 * SNAP_NN_MAX + i]; nb_w[i] = t[3 * SNAP_NN_MAX + i]; nb_rc[i] = t[4 * SNAP_NN_MAX + i];
+      nb_g[i] = unsigned(__double_as_longlong(t[5 * SNAP_NN_MAX + i]));
+    }
+    if( lane == 0 ) s_nn = nn;
+  }
+  else
+  {
+    // the other rows fetch Y while row 0 walks the neighbour list
+    for(int k = int(tid) - 32; k < K.idxu_max; k += NT - 32) ylist[k] = A.ybuf[soa + size_t(k) * 32];
+  }
+  __syncthreads();
+  const unsigned nn = s_nn;
+  // ---- energy (direction 0 only): e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero ; Utot straight from global
+  if( A.ep && kd == 0 )
+  {
+    double sE = 0.0;
+    for(int j = 0; j <= TJ; j++)
+    {
+      const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
+      for(int k = int(tid); k < cnt; k += NT)
+      {
+        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
+        const double2 u = A.ubuf[soa + size_t(jb + k) * 32];
+        sE += w * (u.x * ylist[jb + k].x + u.y * ylist[jb + k].y);
+      }
+    }
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
+    if( lane == 0 ) red[mb] = sE;
+    __syncthreads();
+    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    __syncthreads();
+  }
+  double* const fout = kd == 0 ? A.fx : (kd == 1 ? A.fy : A.fz);
+  double fi = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  for(unsigned b0 = 0; b0 < nn; b0 += 32)
+  {
+    const unsigned n = b0 + lane; const bool valid = n < nn;
+    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
+    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(MBS));
+    red[mb * 32 + lane] = d;
+    __syncthreads();
+    if( mb == 0 && valid )
+    {
+      double f = 0.0;
+      for(int w2 = 0; w2 < NR; w2++) f += red[w2 * 32 + lane];
+      f *= 2.0;
+      fi += f;
+      atomicAdd(fout + nb_g[n], -f);
+      if( A.vir ) { v0 -= f * x; v1 -= f * y; v2 -= f * z; }
+    }
+    __syncthreads();
+  }
+  if( mb == 0 )
+  {
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) fi += __shfl_xor_sync(0xffffffffu, fi, o);
+    if( A.vir )
+    {
+#     pragma unroll
+      for(int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); v2 += __shfl_xor_sync(0xffffffffu, v2, o); }
+    }
+    if( lane == 0 )
+    {
+      atomicAdd(fout + ai, fi);
+      if( A.vir ) { double* p = A.vir + 9ull * ai + 3 * kd; atomicAdd(p, v0); atomicAdd(p + 1, v1); atomicAdd(p + 2, v2); }
+    }
+  }
+}
+
 // ---- compute_yi for 32 atoms at a time: lane = atom -------------------------------------------------------------------
 // One CTA owns one AoSoA block of 32 central atoms: their Utot (idxu_max x 32 complex doubles, 146 KB at 2J = 8) arrives
 // in shared memory with ONE TMA bulk copy, every warp-wide U access is then 32 consecutive 16-byte words (conflict-free),
@@ -816,7 +931,7 @@ void xsb_snap_release(xsb_ctx* ctx)
   auto it = g_snap.find(ctx);
   if( it == g_snap.end() ) return;
   it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
-  it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->clk.release();
+  it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->nbtab.release(); it->second->nbcnt.release(); it->second->clk.release();
   delete it->second; g_snap.erase(it);
 }
 
@@ -845,11 +960,17 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
   const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
   XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
   A.ubuf = S->ubuf.p; A.ybuf = S->ybuf.p;
+  XSB_CUDA(ctx, S->nbtab.reserve(size_t(chunk) * 6 * SNAP_NN_MAX)); XSB_CUDA(ctx, S->nbcnt.reserve(chunk));
+  A.nbtab = S->nbtab.p; A.nbcnt = S->nbcnt.p;
   const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
                      + size_t(3 * NR) * 32 * sizeof(double) + 64;
   // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
   // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)
   constexpr bool DIRSPLIT = TJ >= 7;
+  const bool dircta = DIRSPLIT && getenv("XSB_SNAP_FKERNEL") == nullptr;      // A/B switch: XSB_SNAP_FKERNEL=1 -> the 15-warp CTA per atom
+  const size_t fdsmem = size_t(S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(2 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
+                      + size_t(NR) * 32 * sizeof(double) + 64;
+  if( dircta ) { if( xf ) { if( (rc = setattr(snap_fd_kernel<TJ, true>, fdsmem)) ) return rc; } else { if( (rc = setattr(snap_fd_kernel<TJ, false>, fdsmem)) ) return rc; } }
   if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, true, 3>, smem)) ) return rc; }
   else     { if( (rc = setattr(snap_force_kernel<TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, false, 3>, smem)) ) return rc; }
   if( (rc = setattr(snap_y_kernel<TJ>, ysmem)) ) return rc;
@@ -862,7 +983,12 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
     XSB_LAUNCH_CHECK(ctx);
     snap_y_kernel<TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, S->K);
     XSB_LAUNCH_CHECK(ctx);
-    if( DIRSPLIT )
+    if( dircta )
+    {
+      if( xf ) snap_fd_kernel<TJ, true><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, S->K);
+      else     snap_fd_kernel<TJ, false><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, S->K);
+    }
+    else if( DIRSPLIT )
     {
       if( xf ) snap_f_kernel<TJ, true><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
       else     snap_f_kernel<TJ, false><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
@@ -968,7 +1094,7 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
               ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own), S->idxz.p, S->cglist.p, S->betaz.p,
               ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr,
               virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr, S->err.p, S->clocks ? S->clk.p : nullptr,
-              nullptr, nullptr, 0u, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
+              nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
   if( A.n_atoms == 0 ) return XSB_OK;
   int rc = XSB_ERR_UNSUPPORTED;
   ctx->prof_begin(XSB_PROF_SNAP);
