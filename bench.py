@@ -174,10 +174,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def brick_cells(args, n):
+    """FCC unit cells per axis of one rank's brick: fixed per GPU (weak, the default) or a fixed total split over the ranks"""
+    rd = rank_dims(n)
+    if args.scaling == "strong":
+        assert all(args.total_cells % d == 0 for d in rd), "--total-cells must be divisible by the rank grid"
+        return [args.total_cells // d for d in rd]
+    return [args.cells] * 3
+
+
 def workload_config(args, n):
-    return {"workload": "EAM Cu FCC %d^3 unit cells x %d GPU = %d atoms, NVE Verlet, eam_alloy_force (setfl Sutton-Chen Cu, rc %.2f, skin %.1f)" % (
-                args.cells, n, 4 * args.cells ** 3 * n, RCUT, SKIN),
-            "baseline_config": "configs[1] EAM Cu FCC 2M atoms NVE on 1xB200",
+    uc = brick_cells(args, n)
+    if args.scaling == "strong":
+        what = "EAM Cu FCC %d^3 unit cells = %d atoms over %d GPU (bricks of %dx%dx%d unit cells)" % (args.total_cells, 4 * args.total_cells ** 3, n, uc[0], uc[1], uc[2])
+        base = "configs[3] EAM Cu 16M atoms strong scaling over 1/2/4/8 B200 with ghost exchange"
+    else:
+        what = "EAM Cu FCC %d^3 unit cells x %d GPU = %d atoms" % (args.cells, n, 4 * args.cells ** 3 * n)
+        base = "configs[1] EAM Cu FCC 2M atoms NVE on 1xB200"
+    return {"workload": what + ", NVE Verlet, eam_alloy_force (setfl Sutton-Chen Cu, rc %.2f, skin %.1f)" % (RCUT, SKIN),
+            "baseline_config": base,
             "rebuild": "particle_displ_over(skin/2) trigger, forced at least every %d steps" % args.rebuild_every,
             "l2": "inputs larger than L2 (positions + neighbour lists > 1 GB per GPU)",
             "parallelism": "bricks %s" % "x".join(str(d) for d in rank_dims(n))}
@@ -200,17 +215,23 @@ def run_xsb(args):
     setfl = make_setfl(tmp)
     rd = rank_dims(world)
     coord = (rank % rd[0], (rank // rd[0]) % rd[1], rank // (rd[0] * rd[1]))
-    pos, vel, typ, brick = brick_system(args.cells, coord, seed=1 + rank)
-    ncb = n_cells_for(brick[0])                        # cells per brick axis
-    cell = brick[0] / ncb
-    gcells = [ncb * d for d in rd]
-    origin = [(c * ncb - 1) * cell for c in coord]
+    pos, vel, typ, brick = brick_system(brick_cells(args, world), coord, seed=1 + rank)
+    # one cell size for the whole domain: as many cells per axis as fit rc + skin, a multiple of the rank grid
+    gbox = brick * np.asarray(rd, dtype=np.float64)
+    gc = min(n_cells_for(gbox[a]) for a in range(3))
+    while any(gc % d for d in rd):
+        gc -= 1
+    cell = gbox[0] / gc
+    assert np.allclose(gbox, gbox[0]), "the global box is cubic in both scaling modes"
+    ncb3 = [gc // d for d in rd]                       # cells per brick axis
+    gcells = [gc] * 3
+    origin = [(coord[a] * ncb3[a] - 1) * cell for a in range(3)]
     ctx = xsb.Context(local)
     if world > 1:
         ids = [xsb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(world, rank, ids[0])
-    ctx.grid_set(xsb.make_grid([ncb + 2] * 3, 1, cell, origin))
+    ctx.grid_set(xsb.make_grid([c + 2 for c in ncb3], 1, cell, origin))
     ctx.particles_assign(pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2], typ)
     ctx.set_domain(gcells, (1, 1, 1), rd, coord)
     ctx.ghost_comm_scheme()
@@ -380,7 +401,7 @@ def run_xsb(args):
                "sample": "EAM Cu FCC %d^3 unit cells = %d atoms, same potential/cutoffs; 2 force steps + list build/%d (oracle restatement, OpenMP)" % (
                    args.cpu_sample_cells, info["atoms"], args.rebuild_every)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu,
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
@@ -398,6 +419,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="xsb", choices=["xsb", "reference"])
     ap.add_argument("--cells", type=int, default=79, help="FCC unit cells per axis per GPU (79 -> 1 972 156 atoms)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --total-cells^3 unit cells split over the GPUs (configs[3])")
+    ap.add_argument("--total-cells", type=int, default=160, help="strong scaling: FCC unit cells per axis of the whole system (160 -> 16 384 000 atoms)")
     ap.add_argument("--rebuild-every", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-cells", type=int, default=24)

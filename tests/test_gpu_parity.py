@@ -744,3 +744,25 @@ def test_grid_set_xform_keeps_list_and_matches_fresh_context(tmp_path):
     ref0 = [gs.zeros() for _ in range(4)]
     O.eam_alloy(g0, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 8, ref0[0], ref0[1], ref0[2], ref0[3], None, ctx.download(xsb.F_RHO_DEMB))
     assert rel_err(ctx.download(xsb.F_FX)[own], ref0[0][own]) < TOL64
+
+
+def test_types_uploaded_after_the_list_build_use_the_byte_copy_stage(tmp_path):
+    """chunk_neighbors aligns the stage rows for TMA-copied type bytes only when it sees a multi-species system; if the
+    types arrive later (list built on an all-zero type array), the multi-element passes must still stage them correctly"""
+    O = oracle()
+    path = write_setfl(str(tmp_path / "ab.eam.alloy"), [SC_CU, SC_XX], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    gs = system(ncells=6, a=3.615, sigma=0.05, cell=3.615 * 2, gl=2, types=[0, 1, 1, 0], seed=14)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 7.0, 1, True)
+    ref = [gs.zeros() for _ in range(5)]
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 1 | 2 | 4 | 8 | 16, ref[0], ref[1], ref[2], ref[3], None, ref[4])
+    ctx = make_ctx(gs)
+    ctx.upload(xsb.F_TYPE, np.zeros_like(gs.type))
+    ctx.eam_alloy_load(path); ctx.chunk_neighbors(7.0)            # single-species as far as the build can tell
+    ctx.upload(xsb.F_TYPE, gs.type)
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG)
+    ctx.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG)
+    own = ~gs.is_ghost
+    for f, r in ((xsb.F_FX, ref[0]), (xsb.F_FY, ref[1]), (xsb.F_FZ, ref[2]), (xsb.F_EP, ref[3])):
+        assert rel_err(ctx.download(f)[own], r[own]) < TOL64
