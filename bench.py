@@ -11,7 +11,9 @@ generated at run time), rcut_inc (skin) 1.0 ang, dt 1 fs, eam_alloy_force driven
 (rho, rho2emb | ghost_update_opt rho_dEmb | force) exactly as data/regression_new/potentials/eam/eam_alloy decks do.
 One "step" = one full NVE Verlet step: push_f_v_r, push_f_v, particle_displ_over trigger, ghost_update_r (or, when the
 trigger fires / every --rebuild-every steps: move_particles + ghost_comm_scheme + chunk_neighbors), zero_force_energy,
-the EAM phases, force_to_accel, push_f_v.  N>1 is weak scaling: every rank owns a 79^3-unit-cell brick.
+the EAM phases, force_to_accel, push_f_v; the timed loop is cut at the displacement check, so the five integrator
+operators around a step boundary run as one pass (xsb_verlet_boundary; --separate-integrator runs them one by one).
+N>1 is weak scaling: every rank owns a 79^3-unit-cell brick (--scaling strong: a 160^3 system split over the ranks).
 """
 import argparse
 import json
@@ -257,18 +259,22 @@ def run_xsb(args):
         ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB)
         ctx.ghost_update([xsb.F_RHO_DEMB])
         ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE)
-        ctx.force_to_accel([MASS_CU])
 
     def step():
-        ctx.push_f_v_r(DT); ctx.push_f_v(0.5 * DT)
+        # one velocity-Verlet step, cut at the displacement check: force_to_accel + push_f_v close the previous step,
+        # push_f_v_r + push_f_v + particle_displ_over open this one (xsb_verlet_boundary = those five operators in one pass)
+        if args.separate_integrator:
+            ctx.force_to_accel([MASS_CU]); ctx.push_f_v(0.5 * DT)
+            ctx.push_f_v_r(DT); ctx.push_f_v(0.5 * DT)
+            over, _ = ctx.particle_displ_over(0.5 * SKIN)
+        else:
+            over, _ = ctx.verlet_boundary([MASS_CU], DT, 0.5 * SKIN)
         state["since"] += 1
-        over, _ = ctx.particle_displ_over(0.5 * SKIN)
         if over or state["since"] >= args.rebuild_every:
             rebuild()
         else:
             ctx.ghost_update(POS)
         forces()
-        ctx.push_f_v(0.5 * DT)
 
     rebuild(first=True)
     forces()
@@ -424,6 +430,7 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-cells", type=int, default=24)
+    ap.add_argument("--separate-integrator", action="store_true", help="five integrator operators as separate kernels instead of xsb_verlet_boundary")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "xsb_snap_ncoeff", "xsb_snap_set", "xsb_snap_rcut_max", "xsb_snap_force", "xsb_snap_overflow",
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
-    "xsb_particle_displ_over", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
+    "xsb_particle_displ_over", "xsb_verlet_boundary", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
 ]
 
@@ -138,6 +138,7 @@ def load_library():
     L.xsb_force_to_accel.argtypes = [vp, i32, vp]
     L.xsb_backup_r.argtypes = [vp]
     L.xsb_particle_displ_over.argtypes = [vp, dbl, C.POINTER(i32), C.POINTER(dbl)]
+    L.xsb_verlet_boundary.argtypes = [vp, i32, vp, dbl, dbl, C.POINTER(i32), C.POINTER(dbl)]
     L.xsb_thermo_state.argtypes = [vp, i32, vp, vp]
     L.xsb_ghost_plan.argtypes = [vp, i32, vp, vp, u64, vp]
     L.xsb_migration_stats.argtypes = [vp, vp, vp]
@@ -411,6 +412,13 @@ class Context:
     def particle_displ_over(self, threshold):
         r, d = C.c_int(), C.c_double()
         self._ck(self.L.xsb_particle_displ_over(self.h, float(threshold), C.byref(r), C.byref(d)), "xsb_particle_displ_over")
+        return bool(r.value), d.value
+
+    def verlet_boundary(self, masses, dt, threshold):
+        """force_to_accel, push_f_v(dt/2) | push_f_v_r(dt), push_f_v(dt/2), particle_displ_over(threshold) in one pass"""
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        r, d = C.c_int(), C.c_double()
+        self._ck(self.L.xsb_verlet_boundary(self.h, m.size, _ptr(m), float(dt), float(threshold), C.byref(r), C.byref(d)), "xsb_verlet_boundary")
         return bool(r.value), d.value
 
     def thermo_state(self, masses):

@@ -251,6 +251,10 @@ int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass);
 /* backup_r + particle_displ_over (config_move_particles.msp:19-23): result = max |r - r_backup| > thr   */
 int xsb_backup_r(xsb_ctx* ctx);
 int xsb_particle_displ_over(xsb_ctx* ctx, double threshold, int* result, double* max_displ);
+/* The operators on both sides of a step boundary of the velocity-Verlet scheme in one pass over the own atoms  */
+/* (config_numerical_schemes.msp:23-52): force_to_accel, push_f_v(dt/2) | push_f_v_r(dt), push_f_v(dt/2),       */
+/* particle_displ_over(threshold).  Same per-atom arithmetic as the five separate calls.                        */
+int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt, double threshold, int* result, double* max_displ);
 
 /* simulation_thermodynamic_state (src/thermo_state/simulation_thermodynamic_state.cpp:81-230): sums over
  * the particles of own cells, all-reduced over ranks, in the reference's 27-double layout: virial[9] (zeros when no

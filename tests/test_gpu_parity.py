@@ -766,3 +766,34 @@ def test_types_uploaded_after_the_list_build_use_the_byte_copy_stage(tmp_path):
     own = ~gs.is_ghost
     for f, r in ((xsb.F_FX, ref[0]), (xsb.F_FY, ref[1]), (xsb.F_FZ, ref[2]), (xsb.F_EP, ref[3])):
         assert rel_err(ctx.download(f)[own], r[own]) < TOL64
+
+
+@pytest.mark.parametrize("triclinic", [False, True])
+def test_verlet_boundary_equals_the_five_separate_operators(triclinic):
+    """xsb_verlet_boundary = force_to_accel, push_f_v(dt/2) | push_f_v_r(dt), push_f_v(dt/2), particle_displ_over in one pass"""
+    pos, typ, box = lattice("FCC", 6, 5.0, 0.1, seed=3, types=[0, 1, 0, 1])
+    rng = np.random.default_rng(5)
+    vel = rng.normal(0.0, 2.0, pos.shape)
+    X = np.array([[1.02, 0.03, 0.01], [0.0, 0.98, 0.02], [0.0, 0.0, 1.01]]) if triclinic else None
+    masses, dt = [39.948, 83.798], 2.0e-3
+    out = []
+    for fused in (False, True):
+        ctx = assigned_ctx(pos, typ, box, 10.0, 1, vel)
+        if X is not None:
+            ctx.grid_set_xform(X)
+        ctx.backup_r()
+        n = ctx.n
+        f = np.random.default_rng(9).normal(0.0, 50.0, (3, n))
+        for k, fld in enumerate((xsb.F_FX, xsb.F_FY, xsb.F_FZ)):
+            ctx.upload(fld, f[k])
+        if fused:
+            over, d = ctx.verlet_boundary(masses, dt, 0.004)
+        else:
+            ctx.force_to_accel(masses); ctx.push_f_v(0.5 * dt)
+            ctx.push_f_v_r(dt); ctx.push_f_v(0.5 * dt)
+            over, d = ctx.particle_displ_over(0.004)
+        out.append((over, d, [ctx.download(x) for x in (xsb.F_RX, xsb.F_RY, xsb.F_RZ, xsb.F_VX, xsb.F_VY, xsb.F_VZ, xsb.F_FX, xsb.F_FY, xsb.F_FZ)]))
+    (o0, d0, a0), (o1, d1, a1) = out
+    assert o0 == o1 and abs(d0 - d1) <= 1e-15 * max(d0, 1e-300) + 1e-18 and d0 > 0
+    for u, v in zip(a0, a1):
+        assert np.abs(u - v).max() <= 4e-16 * max(np.abs(u).max(), 1e-300)

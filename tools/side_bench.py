@@ -81,20 +81,17 @@ def main(which, steps=100, warmup=10, mixed=0, cells=0):
             ctx.zero_force_energy(ghost=True)
             ctx.snap_force(0)
             ctx.ghost_reduce_add([xsb.F_FX, xsb.F_FY, xsb.F_FZ])
-        ctx.force_to_accel([w["mass"]])
 
     def step():
-        ctx.push_f_v_r(1e-3); ctx.push_f_v(0.5e-3)
+        over, _ = ctx.verlet_boundary([w["mass"]] * 2, 1e-3, 0.5 * w["skin"])     # force_to_accel, push_f_v | push_f_v_r, push_f_v, particle_displ_over
         state["since"] += 1; state["step"] += 1
         if X0 is not None:                                # barostat-like drift of the cell matrix, 2e-6 per step
             ctx.grid_set_xform(X0 * (1.0 + 2e-6 * state["step"]))
-        over, _ = ctx.particle_displ_over(0.5 * w["skin"])
         if over or state["since"] >= 20:
             rebuild()
         else:
             ctx.ghost_update(POS)
         forces()
-        ctx.push_f_v(0.5e-3)
 
     rebuild(first=True); forces()
     for _ in range(warmup):
