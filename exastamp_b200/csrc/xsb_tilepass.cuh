@@ -156,9 +156,12 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           const unsigned lt = (1u << sub) - 1u;
           // branch-free filter step with 32-bit shared addressing: lanes past the end of the list test stage slot 0 and are
           // masked out of the ballot
-          const unsigned xad = smem_u32(B.x), fstride = G.s_cap * 8u;
-          const unsigned qda = smem_u32(qd), qja = smem_u32(qj);
-          const double rc2 = op.rcut2;
+          unsigned xad = smem_u32(B.x), yad = xad + G.s_cap * 8u, zad = xad + G.s_cap * 16u;
+          unsigned qda = smem_u32(qd), qja = smem_u32(qj);
+          double rc2 = op.rcut2;
+          // keep the loop invariants in registers (ptxas otherwise re-reads s_cap / rcut2 from the constant bank and rebuilds
+          // the three field bases every step)
+          asm volatile("" : "+r"(xad), "+r"(yad), "+r"(zad), "+r"(qda), "+r"(qja), "+d"(rc2));
           // FIFO over a 64-slot ring: qt entries queued, qh evaluated so far; the k-th queued entry IS the k-th entry of
           // the atom's in-range sub-list, so a batch [qh, qh+32) maps to 32 consecutive sub-list positions
           double* __restrict__ pw = L.pair_w + e0;
@@ -175,11 +178,11 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             jn = jnn;
             lpn += 32;
             jnn = e + 64 < len ? __ldcs(lpn + 32) : 0u;
-            const unsigned ad = xad + 8u * j;
+            const unsigned j8 = 8u * j;
             double dx, dy, dz;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(ad));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dy) : "r"(ad + fstride));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dz) : "r"(ad + 2u * fstride));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dx) : "r"(xad + j8));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dy) : "r"(yad + j8));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dz) : "r"(zad + j8));
             dx -= xa; dy -= ya; dz -= za;
             apply_xform<XFORM>(X, dx, dy, dz);
             const double d2 = dx * dx + dy * dy + dz * dz;
