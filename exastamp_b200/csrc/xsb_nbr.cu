@@ -6,9 +6,10 @@
 // produced on demand by xsb_chunk_neighbors_export() from the same list, honouring chunk_size and
 // build_particle_offset (data/config/config_move_particles.msp:54-61).
 //
-// Build = two warp-per-particle sweeps (count, then fill) over the (2Ry+1)(2Rz+1) x-rows of cells around the
-// particle's cell: cells of one row are contiguous in the flat SoA (i fastest), so each row is one coalesced
-// run of candidates; lanes test 32 candidates per step and ballot-compact the survivors.
+// Build (tile path): nbr_count_kernel stages the cell block of a tile in shared memory, tests 32 candidates per step and
+// keeps the survivor masks; after a scan of the counts nbr_expand_kernel replays the masks into the two index lists.
+// Grids the tile path cannot serve fall back to two warp-per-particle sweeps (nbr_sweep_kernel: count, then fill) over
+// the (2Ry+1)(2Rz+1) x-rows of cells around the particle's cell.
 #include "xsb_tile.cuh"
 #include <algorithm>
 #include <cmath>
@@ -363,31 +364,6 @@ __global__ void __launch_bounds__(256) nbr_expand_kernel(TileGeom G, const unsig
       }
       __syncwarp();
     }
-  }
-}
-
-// CSR (flat u32 neighbour index) -> tile list (u16 index into the stage of the central atom's tile), warp per atom
-__global__ void __launch_bounds__(256) tile_convert_kernel(TileGeom G, unsigned n, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ cell_of,
-                                                           const unsigned long long* __restrict__ off, const unsigned* __restrict__ idx32,
-                                                           unsigned short* __restrict__ idx16)
-{
-  __shared__ TileMeta Ms[8];
-  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  const unsigned a = blockIdx.x * 8u + w;
-  if( a >= n ) return;
-  TileMeta& M = Ms[w];
-  const unsigned c = cell_of[a];
-  const int i = int(c % unsigned(G.nx)), j = int((c / unsigned(G.nx)) % unsigned(G.ny)), k = int(c / (unsigned(G.nx) * unsigned(G.ny)));
-  tile_meta_compute(G, cell_start, i / G.TX, j, k, M);
-  __syncwarp();
-  const unsigned nrows = unsigned((2 * G.Ry + 1) * (2 * G.Rz + 1));
-  const unsigned long long e1 = off[a + 1];
-  for(unsigned long long e = off[a] + lane; e < e1; e += 32u)
-  {
-    const unsigned b = idx32[e];
-    unsigned r = 0;
-    while( r + 1 < nrows && !( b >= M.g0[r] && b - M.g0[r] < M.s0[r + 1] - M.s0[r] ) ) ++r;
-    idx16[e] = (unsigned short)(M.s0[r] + (b - M.g0[r]));
   }
 }
 
