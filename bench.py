@@ -254,11 +254,13 @@ def run_xsb(args):
         state["rebuilds"] += 1; state["since"] = 0
         state["move_s"] += t1 - t0; state["rebuild_s"] += time.perf_counter() - t0
 
+    mode = {"flags": 0}                               # xsb.FLAG_MIXED during the extra mixed-precision measurement
+
     def forces():
         ctx.zero_force_energy()
-        ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB)
+        ctx.eam_alloy_force(RCUT, xsb.EAM_RHO | xsb.EAM_RHO2EMB, mode["flags"])
         ctx.ghost_update([xsb.F_RHO_DEMB])
-        ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE)
+        ctx.eam_alloy_force(RCUT, xsb.EAM_FORCE, mode["flags"])
 
     def step():
         # one velocity-Verlet step, cut at the displacement check: force_to_accel + push_f_v close the previous step,
@@ -312,6 +314,26 @@ def run_xsb(args):
     else:
         atoms_total = n_own
     value = atoms_total * args.steps / (ms * 1e-3)
+
+    # ---- the same steps in mixed precision (FP32 spline + pair math, tolerance 1e-5): reported beside, not as, the metric
+    mixed = None
+    if not args.no_mixed:
+        mode["flags"] = xsb.FLAG_MIXED
+        for _ in range(3):
+            step()
+        barrier()
+        km = max(5, min(args.steps, 40))
+        ctx.timer_start()
+        for _ in range(km):
+            step()
+        msm = ctx.timer_stop_ms()
+        barrier()
+        if dist is not None:
+            t = torch.tensor([msm], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX); msm = float(t.item())
+        mixed = {"value": atoms_total * km / (msm * 1e-3), "unit": UNIT, "ms_per_step": msm / km, "steps": km,
+                 "dtype": "f32 spline + pair math, f64 positions / distances / accumulation", "tolerance": 1e-5}
+        mode["flags"] = 0
 
     # ---- e2e: the plugin use case.  The host application owns the particle arrays (pinned host memory): every step
     # it hands positions to the C ABI and reads forces + energies back.
@@ -409,7 +431,7 @@ def run_xsb(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "mixed_precision": mixed,
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
                        "rebuilds_in_timed_region": state["rebuilds"] - rb0, "rebuild_wall_s_total": state["rebuild_s"],
                        "move_particles_wall_s_total": state["move_s"], "host_wall_s": wall, "breakdown": breakdown}}
@@ -431,6 +453,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-cells", type=int, default=24)
     ap.add_argument("--separate-integrator", action="store_true", help="five integrator operators as separate kernels instead of xsb_verlet_boundary")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the extra mixed-precision measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -235,7 +235,7 @@ void xsb_destroy(xsb_ctx* ctx)
   for(auto& b : ctx->f64) b.release();
   ctx->type.release(); ctx->id.release();
   ctx->nbh_count.release(); ctx->nbh_off.release(); ctx->nbh_idx.release(); ctx->nbh_masks.release(); ctx->scratch.release(); ctx->scratch64.release();
-  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
+  ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->eam.fc32.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   xsb_snap_release(ctx);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);

@@ -68,6 +68,7 @@ struct EamAlloyDev
   DevBuf<double> frho;      // reference layout [nel][nrho+1][8]
   DevBuf<double> rtab;      // r-tables in the reference layout: rhor [nel][nr+1][8] then z2r [npairs][nr+1][8]
   DevBuf<double> fc;        // the same r-tables as Hermite knots {f, c5} : [nel + npairs][nr+1][2] (xsb_eam.cu)
+  DevBuf<float> fc32;       // mixed precision: knot pairs {f[m], c5[m], f[m+1], c5[m+1]} as floats: [nel + npairs][nr+1][4]
   bool set = false;
 };
 

@@ -501,6 +501,147 @@ struct EamForceTileOp
   }
 };
 
+// ---- mixed precision (XSB_FLAG_MIXED, tolerance 1e-5): FP64 positions, distances and accumulation as before, the spline
+// lookup and the pair expression in FP32.  A row of the FP32 table holds the four cubic coefficients of its interval
+// {c6 = f[m], c5, c4, c3} (16 B; derived in FP64 on the host -- re-deriving c4, c3 from FP32 knots would cancel to ~1e-4),
+// so a lookup is one 16-byte shared-memory load instead of two, and the FP64 rsqrt + ~30 FP64 operations per pair
+// become FP32.
+struct EamFcView32
+{
+  const float4* __restrict__ g;    // global [ntab][nr+1]
+  int nr, m_lo, rows, ntab_smem, t0;
+  float rdr;
+  __host__ __device__ size_t table_bytes() const { return size_t(rows) * size_t(ntab_smem) * sizeof(float4); }
+  __device__ __forceinline__ void load(unsigned char* smem, int nt) const
+  {
+    float4* sm = reinterpret_cast<float4*>(smem);
+    const int tot = rows * ntab_smem;
+    for(int i = threadIdx.x; i < tot; i += nt) { const int t = i / rows, r = i - t * rows; sm[i] = g[size_t(t0 + t) * (nr + 1) + m_lo + r]; }
+  }
+  __device__ __forceinline__ void lookup(float r, int& m, float& p) const
+  {
+    p = r * rdr + 1.0f;
+    m = __float2int_rz(p);
+    m = min(m, nr - 1);
+    p -= float(m);
+    p = fminf(p, 1.0f);
+  }
+  __device__ __forceinline__ float4 knots(const unsigned char* smem, int t, int m) const
+  {
+    if( m >= m_lo && t >= t0 ) return reinterpret_cast<const float4*>(smem)[(t - t0) * rows + (m - m_lo)];
+    return g[size_t(t) * (nr + 1) + m];
+  }
+};
+
+__device__ __forceinline__ void hermite_c32(const float4 k, float& c3, float& c4) { c4 = k.z; c3 = k.w; }
+
+template<bool MULTI, bool PWO_>
+struct EamRhoTileOp32
+{
+  static constexpr bool HAS_W = false, TYPES = MULTI, D2_ONLY = true, PW_OUT = PWO_;
+  static constexpr int PW_N = MULTI ? 2 : 1;
+  double rcut2; EamFcView32 T; double* rho_dEmb;
+  __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
+  __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
+  struct Acc { double rho; int ta; };
+  __device__ __forceinline__ void init(Acc& A) const { A.rho = 0.0; A.ta = 0; }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const { if( MULTI ) A.ta = B.t[sa]; }
+  __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const { pair_d2(A, d2, j, B, tab); }
+  __device__ __forceinline__ auto pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  {
+    const float d2f = float(d2), r = d2f * rsqrtf(d2f);
+    int m; float p; T.lookup(r, m, p);
+    const int tb = MULTI ? int(B.t[j]) : 0;
+    float4 k = T.knots(tab, tb, m);
+    float c3, c4; hermite_c32(k, c3, c4);
+    A.rho += double(((c3 * p + c4) * p + k.y) * p + k.x);
+    const double rhojp = PWO_ ? double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr) : 0.0;
+    if constexpr ( MULTI )
+    {
+      double rhoip = rhojp;
+      if( PWO_ && tb != A.ta ) { k = T.knots(tab, A.ta, m); hermite_c32(k, c3, c4); rhoip = double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr); }
+      return make_double2(rhojp, rhoip);
+    }
+    else return rhojp;
+  }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.rho = group_sum<TPA>(A.rho);
+    if( valid && sub == 0 ) red_add(rho_dEmb + a, A.rho);
+  }
+};
+
+template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_>
+struct EamForceTileOp32
+{
+  static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false, PW_IN = PWI_;
+  static constexpr int PW_N = MULTI ? 2 : 1;
+  double rcut2; EamFcView32 T; int nel; float conv_z2r;
+  double *fx, *fy, *fz, *ep, *vir;
+  __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
+  __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
+  struct Acc { double fx, fy, fz, ep, fpi; int ta; Vir9 v; };
+  __device__ __forceinline__ void init(Acc& A) const { A.fx = A.fy = A.fz = A.ep = A.fpi = 0.0; A.ta = 0; if( VIRIAL ) A.v.zero(); }
+  __device__ __forceinline__ void start(Acc& A, unsigned, unsigned sa, const StageBuf<HAS_W, TYPES>& B, const unsigned char*) const
+  { A.fpi = B.w[sa]; if( MULTI ) A.ta = B.t[sa]; }
+  template<bool HAVE>
+  __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double rhojp_in, double rhoip_in) const
+  {
+    const float d2f = float(d2), recip = rsqrtf(d2f), r = d2f * recip;
+    int m; float p; T.lookup(r, m, p);
+    const int tb = MULTI ? int(B.t[j]) : 0;
+    float4 k; float c3, c4, rhoip, rhojp;
+    if( HAVE ) { rhojp = float(rhojp_in); rhoip = MULTI ? float(rhoip_in) : rhojp; }
+    else
+    {
+      k = T.knots(tab, A.ta, m); hermite_c32(k, c3, c4);
+      rhoip = ((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr;
+      rhojp = rhoip;
+      if( MULTI && tb != A.ta ) { k = T.knots(tab, tb, m); hermite_c32(k, c3, c4); rhojp = ((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr; }
+    }
+    k = T.knots(tab, nel + z2r_index(A.ta, tb), m); hermite_c32(k, c3, c4);
+    const float z2p = ((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr;
+    const float z2 = ((c3 * p + c4) * p + k.y) * p + k.x;
+    float phi = z2 * recip;
+    const float phip = (z2p * recip - phi * recip) * conv_z2r;
+    phi *= conv_z2r;
+    const double fpair = double((float(A.fpi) * rhojp + float(B.w[j]) * rhoip + phip) * recip);
+    const double fex = dx * fpair, fey = dy * fpair, fez = dz * fpair;
+    A.fx += fex; A.fy += fey; A.fz += fez;
+    if( EFLAG ) A.ep += 0.5 * double(phi);
+    if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
+  }
+  __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
+  { eval<false>(A, dx, dy, dz, d2, j, B, tab, 0.0, 0.0); }
+  __device__ __forceinline__ void pair_pw(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab, double pv, double pv2) const
+  { eval<true>(A, dx, dy, dz, d2, j, B, tab, pv, pv2); }
+  template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
+  {
+    A.fx = group_sum<TPA>(A.fx); A.fy = group_sum<TPA>(A.fy); A.fz = group_sum<TPA>(A.fz);
+    if( EFLAG ) A.ep = group_sum<TPA>(A.ep);
+    if( VIRIAL ) A.v.template reduce<TPA>();
+    if( valid && sub == 0 ) { red_add(fx + a, A.fx); red_add(fy + a, A.fy); red_add(fz + a, A.fz); if( EFLAG ) red_add(ep + a, A.ep); if( VIRIAL ) A.v.store_add(vir, a); }
+  }
+};
+
+template<bool HAS_W, bool TYPES>
+static EamFcView32 make_fc_view32(const xsb_ctx* ctx, int t0, int ntab, size_t queue_bytes)
+{
+  const EamAlloyDev& E = ctx->eam;
+  EamFcView32 T{ reinterpret_cast<const float4*>(E.fc32.p), E.nr, INT_MAX, 0, ntab, t0, float(E.rdr) };
+  const size_t fixed = tile_smem_bytes<HAS_W, TYPES>(ctx->tile_s_cap, 0, queue_bytes, 2) + 256;
+  if( fixed >= TILE_SMEM_MAX ) return T;
+  const size_t max_rows = (TILE_SMEM_MAX - fixed) / (sizeof(float4) * size_t(ntab));
+  const double rmin = 0.9 * std::sqrt(ctx->nbh_d2min > 0.0 ? ctx->nbh_d2min : 0.0);
+  int m_lo = std::max(1, int(rmin * E.rdr + 1.0) - 1);
+  int rows = E.nr + 1 - m_lo;
+  if( rows < 2 ) return T;
+  if( size_t(rows) > max_rows ) { rows = int(max_rows); m_lo = E.nr + 1 - rows; }
+  if( rows < 64 ) return T;
+  T.m_lo = m_lo; T.rows = rows;
+  return T;
+}
+
 // shared-memory window of the {f,c5} tables for a tile pass: rows [m_lo, nr] of the first ntab tables, as large a
 // window as the 227 KiB budget allows next to the 2 stage buffers (pairs below the window read the global copy)
 template<bool HAS_W, bool TYPES>
@@ -695,6 +836,14 @@ int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
     for(size_t row = 0; row < nzz / 8; row++) { fc[2*(nrr/8 + row)] = t->z2r[8*row + 6]; fc[2*(nrr/8 + row) + 1] = t->z2r[8*row + 5]; }
     XSB_CUDA(ctx, E.fc.reserve(fc.size() + 2));
     XSB_CUDA(ctx, cudaMemcpyAsync(E.fc.p, fc.data(), fc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // FP32 rows of the mixed-precision passes: the cubic of interval m of table t as {c6, c5, c4, c3} (interpolate()'s
+    // coefficients, rounded once from FP64)
+    const size_t nrow = fc.size() / 2;
+    std::vector<float> f32(4 * nrow);
+    for(size_t row = 0; row < nrr / 8; row++) { const double* c = t->rhor + 8 * row; f32[4*row] = float(c[6]); f32[4*row + 1] = float(c[5]); f32[4*row + 2] = float(c[4]); f32[4*row + 3] = float(c[3]); }
+    for(size_t row = 0; row < nzz / 8; row++) { const double* c = t->z2r + 8 * row; const size_t o = 4 * (nrr / 8 + row); f32[o] = float(c[6]); f32[o + 1] = float(c[5]); f32[o + 2] = float(c[4]); f32[o + 3] = float(c[3]); }
+    XSB_CUDA(ctx, E.fc32.reserve(f32.size() + 4));
+    XSB_CUDA(ctx, cudaMemcpyAsync(E.fc32.p, f32.data(), f32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -716,6 +865,7 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
   EamAlloyView T{ E.frho.p, E.rtab.p, E.rtab.p + size_t(E.nelements) * (E.nr + 1) * 8, E.nr, E.nrho, E.rdr, E.rdrho, E.rhomax, E.conv_z2r, E.conv_frho };
   const bool eflag = phases & XSB_EAM_EFLAG, ghost = phases & XSB_EAM_GHOST;
   const bool virial = eflag && (flags & XSB_FLAG_VIRIAL);
+  const bool mixed = (flags & XSB_FLAG_MIXED) && ctx->tile_ok;      // FP32 spline + pair math on the tile path (tolerance 1e-5)
   if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
   const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;
   constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
@@ -733,6 +883,12 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     // the force pass of this step reuses rho'(r) of every in-range pair: cache it only when that pass can follow
     const bool pwo = !ctx->pair_cache_off;
     ctx->sub_pw_kind = 0;
+    if( mixed )
+    {
+      if( multi ) { EamRhoTileOp32<true, true>  op{ rc2, make_fc_view32<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+      else        { EamRhoTileOp32<false, true> op{ rc2, make_fc_view32<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+    }
+    else
     if( multi ) { if( pwo ) { EamRhoTileOp<true, true>   op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
                   else      { EamRhoTileOp<true, false>  op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
     else        { if( pwo ) { EamRhoTileOp<false, true>  op{ rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
@@ -740,7 +896,7 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     ctx->prof_end(XSB_PROF_EAM_RHO);
     if( rc ) return rc;
     ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = ghost;
-    if( pwo ) ctx->sub_pw_kind = multi ? 3 : 1;      // 3: two values per pair (rhojp, rhoip)
+    if( pwo || mixed ) ctx->sub_pw_kind = (multi ? 3 : 1) | (mixed ? 16 : 0);      // 3: two values per pair (rhojp, rhoip); +16: computed in FP32
   }
   if( !tile && (phases & XSB_EAM_RHO) && ctx->n )
   {
@@ -771,13 +927,23 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     int rc;
     ctx->prof_begin(XSB_PROF_EAM_FORCE);
     const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
-    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == (multi ? 3 : 1) && !(multi && ctx->type_external);
+    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == ((multi ? 3 : 1) | (mixed ? 16 : 0)) && !(multi && ctx->type_external);
     const int npair = E.nelements * (E.nelements + 1) / 2;
 #   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { \
       if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, E.nelements, npair, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
       else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, 0, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
+#   define XSB_EAM_TILE32(MU, EF, VIR, TPA_, NT_) { \
+      if( pwi ) { EamForceTileOp32<MU, EF, VIR, true>  op{ rc2, make_fc_view32<true, MU>(ctx, E.nelements, npair, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else      { EamForceTileOp32<MU, EF, VIR, false> op{ rc2, make_fc_view32<true, MU>(ctx, 0, ntab, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
+    if( mixed )
+    {
+      if( multi ) { if( virial ) XSB_EAM_TILE32(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(true, true, false, 16, 1024) else XSB_EAM_TILE32(true, false, false, 16, 1024) }
+      else        { if( virial ) XSB_EAM_TILE32(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(false, true, false, 16, 1024) else XSB_EAM_TILE32(false, false, false, 16, 1024) }
+    }
+    else
     if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
     else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
+#   undef XSB_EAM_TILE32
 #   undef XSB_EAM_TILE
     ctx->prof_end(XSB_PROF_EAM_FORCE);
     if( rc ) return rc;

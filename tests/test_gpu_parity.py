@@ -797,3 +797,31 @@ def test_verlet_boundary_equals_the_five_separate_operators(triclinic):
     assert o0 == o1 and abs(d0 - d1) <= 1e-15 * max(d0, 1e-300) + 1e-18 and d0 > 0
     for u, v in zip(a0, a1):
         assert np.abs(u - v).max() <= 4e-16 * max(np.abs(u).max(), 1e-300)
+
+
+@pytest.mark.parametrize("two_species,virial", [(False, False), (True, True)])
+def test_eam_alloy_mixed_precision_parity(tmp_path, two_species, virial):
+    """XSB_FLAG_MIXED on eam_alloy_force: FP32 spline + pair math (FP64 distances and accumulation) against the FP64 oracle
+    at the mixed-mode bar (1e-5 of the field maximum); two-call pattern, so the force pass consumes the FP32 pair cache"""
+    O = oracle()
+    els = [SC_CU, SC_XX] if two_species else [SC_CU]
+    path = write_setfl(str(tmp_path / "m.eam.alloy"), els, nrho=10000, drho=0.02, nr=5000, rc=6.0)
+    gs = system(ncells=6, a=3.615, sigma=0.08, cell=3.615 * 2, gl=2, types=[0, 1, 1, 0] if two_species else None, seed=17)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 7.0, 1, True)
+    ref = [gs.zeros() for _ in range(5)]
+    rvir = np.zeros((gs.n, 9)) if virial else None
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, O.EamAlloy(path), 6.0, 1 | 2 | 4 | 8 | 16 | (32 if virial else 0),
+                ref[0], ref[1], ref[2], ref[3], rvir, ref[4])
+    ctx = make_ctx(gs); ctx.eam_alloy_load(path); ctx.chunk_neighbors(7.0)
+    ctx.zero_force_energy(ghost=True)
+    fl = xsb.FLAG_MIXED | (xsb.FLAG_VIRIAL if virial else 0)
+    ctx.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG, fl)
+    ctx.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG, fl)
+    own = ~gs.is_ghost
+    assert rel_err(ctx.download(xsb.F_RHO_DEMB), ref[4]) < TOLMIX
+    errs = [rel_err(ctx.download(f)[own], r[own]) for f, r in ((xsb.F_FX, ref[0]), (xsb.F_FY, ref[1]), (xsb.F_FZ, ref[2]), (xsb.F_EP, ref[3]))]
+    assert max(errs) < TOLMIX, errs
+    assert max(errs) > 1e-12, "mixed mode produced FP64-exact results: the FP32 path did not run"
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL).reshape(-1, 9)[own], rvir[own]) < TOLMIX
