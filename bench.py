@@ -70,6 +70,23 @@ def in_range_sample(pos, box, nsample=400):
     return float(((d2 <= RCUT * RCUT) & (d2 > 0)).sum() / len(core))
 
 
+def domain_cells(scaling, brick, rd):
+    """one cell size for the whole domain, bricks made of whole cells: (cell size, cells per brick axis, global cells per axis)"""
+    brick = np.asarray(brick, dtype=np.float64)
+    if scaling == "strong":
+        # cubic global box: as many cells per axis as fit rc + skin, a multiple of the rank grid
+        gbox = brick * np.asarray(rd, dtype=np.float64)
+        assert np.allclose(gbox, gbox[0]), "strong scaling splits a cubic box"
+        gc = n_cells_for(gbox[0])
+        while any(gc % d for d in rd):
+            gc -= 1
+        return gbox[0] / gc, [gc // d for d in rd], [gc] * 3
+    # weak scaling: cubic bricks, the global box is rd[a] bricks long along axis a
+    assert np.allclose(brick, brick[0]), "weak scaling uses cubic bricks"
+    ncb = n_cells_for(brick[0])
+    return brick[0] / ncb, [ncb] * 3, [ncb * d for d in rd]
+
+
 def n_cells_for(box_len):
     return int(np.floor(box_len / (RCUT + SKIN)))
 
@@ -218,15 +235,7 @@ def run_xsb(args):
     rd = rank_dims(world)
     coord = (rank % rd[0], (rank // rd[0]) % rd[1], rank // (rd[0] * rd[1]))
     pos, vel, typ, brick = brick_system(brick_cells(args, world), coord, seed=1 + rank)
-    # one cell size for the whole domain: as many cells per axis as fit rc + skin, a multiple of the rank grid
-    gbox = brick * np.asarray(rd, dtype=np.float64)
-    gc = min(n_cells_for(gbox[a]) for a in range(3))
-    while any(gc % d for d in rd):
-        gc -= 1
-    cell = gbox[0] / gc
-    assert np.allclose(gbox, gbox[0]), "the global box is cubic in both scaling modes"
-    ncb3 = [gc // d for d in rd]                       # cells per brick axis
-    gcells = [gc] * 3
+    cell, ncb3, gcells = domain_cells(args.scaling, brick, rd)
     origin = [(coord[a] * ncb3[a] - 1) * cell for a in range(3)]
     ctx = xsb.Context(local)
     if world > 1:
@@ -290,6 +299,8 @@ def run_xsb(args):
 
     for _ in range(args.warmup):
         step()
+    if args.warmup:
+        rebuild(); forces()      # warm-up also covers the rebuild path (migration buffers, lazily set up NCCL channels)
     barrier()
     clocks = Clocks(local) if rank == 0 else None
     ctx.profile_enable(True)
