@@ -313,6 +313,7 @@ def run_xsb(args):
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.launches - l0
+    rebuilds_timed = state["rebuilds"] - rb0; rebuild_s_timed = state["rebuild_s"]; move_s_timed = state["move_s"]
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     clk = clocks.stop() if clocks else None
@@ -423,7 +424,7 @@ def run_xsb(args):
                          "algorithmic_flops_per_atom": fl_force, "n_c_in_range": n_c,
                          "peak_source": "DFMA loop measured in this run (xsb_measure_peaks)"},
                 "live_peaks": {"fp64_tflops": live_fp64, "fp32_tflops": live_fp32, "hbm_copy_gbs": live_hbm},
-                "note": "FP64 pair math: ncu (profiles/) shows this kernel limited by L1/shared-memory wavefronts (79 %) and the FP64 pipe (34 %), "
+                "note": "FP64 pair math: ncu (profiles/r01zn_eam_nbr_ncu_full.txt) shows this kernel limited by L1/shared-memory wavefronts (91 %) with the FP64 pipe at 39 %, "
                         "DRAM at 22 %; the contract's hbm frac is reported next to the fp64 frac (SURVEY.md 8d asks for both bounds). "
                         "traffic > algorithmic bytes is deliberate: the rho pass leaves rho'(r) per in-range pair (8 B) for this pass"}
         if r_cnt:
@@ -444,8 +445,8 @@ def run_xsb(args):
             "config": workload_config(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "mixed_precision": mixed,
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
-                       "rebuilds_in_timed_region": state["rebuilds"] - rb0, "rebuild_wall_s_total": state["rebuild_s"],
-                       "move_particles_wall_s_total": state["move_s"], "host_wall_s": wall, "breakdown": breakdown}}
+                       "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
+                       "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
