@@ -71,6 +71,10 @@ struct GhostState
   DevBuf<unsigned> recv_idx;            // ghost particle (flat)   [n_recv]
   DevBuf<unsigned long long> send_buf, recv_buf;   // 8-byte words, [nfields][segment] per peer
   double shift[27][3];
+  // cell-level exchange plan: depends on the decomposition only, built once (ghost_list walks every cell of every rank's
+  // grid: ~2-3 ms of host time per rebuild at 8 ranks when it was recomputed)
+  std::vector<GhostCell> plan_mine; std::vector< std::vector<GhostCell> > plan_to_peer;
+  xsb_domain_desc plan_dom{}; int plan_gl = -1;
 };
 
 static inline int block_start(int r, int G, int P) { return int((long long)r * G / P); }
@@ -530,14 +534,20 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
   for(int c = 0; c < 27; c++) { const int w[3] = { c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1 }; for(int a = 0; a < 3; a++) G->shift[c][a] = 0.0; (void)w; }
 
   // receive list (mine) and send lists (entries of every peer's receive list that I own)
-  std::vector<GhostCell> mine; ghost_list(*dom, gl, dom->rank_coord, mine);
-  std::vector< std::vector<GhostCell> > to_peer(P);
-  for(int q = 0; q < P; q++)
+  if( G->plan_gl != gl || std::memcmp(&G->plan_dom, dom, sizeof(*dom)) != 0 || int(G->plan_to_peer.size()) != P )
   {
-    const int qc[3] = { q % dom->rank_dims[0], (q / dom->rank_dims[0]) % dom->rank_dims[1], q / (dom->rank_dims[0] * dom->rank_dims[1]) };
-    std::vector<GhostCell> theirs; ghost_list(*dom, gl, qc, theirs);
-    for(const GhostCell& g : theirs) if( g.owner_rank == me ) to_peer[q].push_back(g);
+    ghost_list(*dom, gl, dom->rank_coord, G->plan_mine);
+    G->plan_to_peer.assign(P, std::vector<GhostCell>());
+    for(int q = 0; q < P; q++)
+    {
+      const int qc[3] = { q % dom->rank_dims[0], (q / dom->rank_dims[0]) % dom->rank_dims[1], q / (dom->rank_dims[0] * dom->rank_dims[1]) };
+      std::vector<GhostCell> theirs; ghost_list(*dom, gl, qc, theirs);
+      for(const GhostCell& g : theirs) if( g.owner_rank == me ) G->plan_to_peer[q].push_back(g);
+    }
+    G->plan_dom = *dom; G->plan_gl = gl;
   }
+  const std::vector<GhostCell>& mine = G->plan_mine;
+  const std::vector< std::vector<GhostCell> >& to_peer = G->plan_to_peer;
   const GridView gv = ctx->view();
   const std::vector<uint64_t>& off = ctx->h_cell_off;
   for(int q = 0; q < P; q++) for(const GhostCell& g : to_peer[q])
