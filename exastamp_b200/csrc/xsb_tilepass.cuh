@@ -9,10 +9,11 @@
 //   void   load_tables(unsigned char* smem, int nt);   cooperative fill by the whole CTA (caller barriers)
 //   struct Acc;  void init(Acc&);  void start(Acc&, a, sa, B, tab);  void pair(Acc&, dx,dy,dz,d2, j, B, tab);   (tab = smem tables)
 //   template<int TPA> void finish(Acc&, a, valid, sub);   group reduction + the single writer's stores
-// Optional per-pair cache (TileList::pair_w, one double per in-range sub-list entry): an Op with PW_OUT = true returns
-// from pair_d2() a value the second pass of the step needs again for the same pair (EAM: rho'(r)), the queue path stores
-// it next to the sub-list entry (coalesced 256-byte stores); an Op with PW_IN = true receives it in pair_pw() when it
-// walks that sub-list, instead of repeating the spline / transcendental evaluation.
+// Optional per-pair cache (TileList::pair_w, PW_N = 1 or 2 doubles per in-range sub-list entry): an Op with PW_OUT = true
+// returns from pair_d2() what the second pass of the step needs again for the same pair (EAM: rho'(r); double or double2),
+// the queue path stores it next to the sub-list entry (coalesced 256-byte stores); an Op with PW_IN = true receives it in
+// pair_pw(..., pv, pv2) when it walks that sub-list, instead of repeating the spline / transcendental evaluation.
+// NO_AHEAD = true opts an Op out of the one-atom-ahead list-window prefetch (ops at the register limit).
 #pragma once
 #include "xsb_tile.cuh"
 #include <type_traits>
