@@ -54,3 +54,12 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt, "%s mentions the oracle" % f
+
+
+def test_every_abi_symbol_has_a_typed_ctypes_binding():
+    """the ctypes mirror declares argument (or result) types for every entry point: an untyped call would pass
+    doubles and 64-bit sizes through the default int conversion"""
+    import re
+    src = open(os.path.join(ROOT, "exastamp_b200", "__init__.py")).read()
+    for s in xsb.ABI_SYMBOLS:
+        assert ("L.%s.argtypes" % s) in src or ("L.%s.restype" % s) in src, "%s is not typed" % s
