@@ -749,6 +749,7 @@ public:
     bool eflag = optional("trigger_thermo_state") ? bool_slot("trigger_thermo_state", true) : sim.trigger_thermo_state;   // eam_potential_multimat.cu:125-149
     if (eflag) phases |= XSB_EAM_EFLAG;
     int fl = eflag && (bool_slot("compute_virial", false) || sim.compute_virial) ? XSB_FLAG_VIRIAL : 0;
+    if (sim.mixed_precision) fl |= XSB_FLAG_MIXED;      // xsb extension (global `enable_mixed_precision`): FP32 spline + pair math, tolerance 1e-5
     sim.check(xsb_eam_alloy_force(sim.ctx, rcut, phases, fl), "xsb_eam_alloy_force");
   }
 };
