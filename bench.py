@@ -394,7 +394,11 @@ def run_xsb(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    live_fp64, live_fp32, live_hbm = ctx.measure_peaks()          # DFMA / FFMA loops and a 1 GiB copy on this device, now
+    try:
+        live_fp64, live_fp32, live_hbm = ctx.measure_peaks()      # DFMA / FFMA loops and a 1 GiB copy on this device, now
+    except Exception as e:                                        # the metric line must not depend on the side measurement
+        sys.stderr.write("xsb_measure_peaks failed: %s\n" % e)
+        live_fp64 = live_fp32 = live_hbm = None
     n_c = in_range_sample(pos, brick)
     f_ms, f_cnt = prof["eam_force"]
     r_ms, r_cnt = prof["eam_rho"]
