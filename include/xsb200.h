@@ -109,7 +109,8 @@ int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, do
 /* ---------------------------------------------------------------------------------------------------- */
 /* a1  Grid / GridCellParticles                                                                         */
 int      xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* grid);
-/* Domain::xform() changes every step under NPT / deformation (BASELINE configs[4]) while  */
+/* Domain::xform() changes every step under NPT / deformation (`domain->set_xform(newXForm)`,                    */
+/* src/parrinellorahman/update_xform_parrinellorahman.cpp:164; SURVEY.md 8a row a1, BASELINE configs[4]) while   */
 /* the grid, the particles and the neighbour list stay: only the 3x3 matrix (row-major) is replaced.  Like in  */
 /* the reference, rebuilding chunk_neighbors when the deformation has eaten the skin is the caller's decision. */
 int      xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9]);
