@@ -665,6 +665,19 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   return XSB_OK;
 }
 
+// host-only view of the FP32 guard band of the count sweep (no context, no GPU): CPU tests sample candidate pairs in
+// FP32 and check |d2_fp32 - d2_exact| against it
+double xsbdbg_nbr_fp32_band(double cell_size, const double* xform9, int tile_tx, int search_range, double nbh_dist)
+{
+  xsb_grid_desc g{};
+  g.cell_size = cell_size;
+  bool ident = true;
+  for(int i = 0; i < 9; i++) { g.xform[i] = xform9 ? xform9[i] : ((i % 4 == 0) ? 1.0 : 0.0); ident = ident && g.xform[i] == ((i % 4 == 0) ? 1.0 : 0.0); }
+  g.xform_is_identity = ident ? 1 : 0;
+  const int R[3] = { search_range, search_range, search_range };
+  return double(nbr_fp32_band(g, tile_tx, R, nbh_dist).band);
+}
+
 int xsb_chunk_neighbors_stats(xsb_ctx* ctx, uint64_t* total, uint32_t* maxn)
 {
   if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
