@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_verlet_boundary", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
+    "xsb_fields_upload_async", "xsb_fields_download_async", "xsb_copy_wait", "xsb_out_of_domain_count",
 ]
 
 
@@ -150,6 +151,10 @@ def load_library():
     L.xsb_num_own_particles.argtypes = [vp]
     L.xsb_cell_offsets_download.argtypes = [vp, vp]
     L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
+    L.xsb_fields_upload_async.argtypes = [vp, i32, vp, vp, i32]
+    L.xsb_fields_download_async.argtypes = [vp, i32, vp, vp, i32]
+    L.xsb_copy_wait.argtypes = [vp]
+    L.xsb_out_of_domain_count.argtypes = [vp, C.POINTER(u64)]
     L.xsb_ghost_reduce_add.argtypes = [vp, C.c_uint32]
     _lib = L
     return L
@@ -361,6 +366,23 @@ class Context:
 
     def download_ptr(self, field, ptr):
         self._ck(self.L.xsb_field_download(self.h, field, ptr), "xsb_field_download")
+
+    # asynchronous own-atom / whole-array transfers of scalar double fields from / to pinned host memory (raw pointers)
+    def fields_upload_async(self, fields, ptrs, own_only=True):
+        f = (C.c_int * len(fields))(*[int(x) for x in fields]); p = (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+        self._ck(self.L.xsb_fields_upload_async(self.h, len(fields), f, p, int(own_only)), "xsb_fields_upload_async")
+
+    def fields_download_async(self, fields, ptrs, own_only=True):
+        f = (C.c_int * len(fields))(*[int(x) for x in fields]); p = (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+        self._ck(self.L.xsb_fields_download_async(self.h, len(fields), f, p, int(own_only)), "xsb_fields_download_async")
+
+    def copy_wait(self):
+        self._ck(self.L.xsb_copy_wait(self.h), "xsb_copy_wait")
+
+    def out_of_domain_count(self):
+        c = C.c_uint64()
+        self._ck(self.L.xsb_out_of_domain_count(self.h, C.byref(c)), "xsb_out_of_domain_count")
+        return c.value
 
     # ---- a10
     def comm_init(self, nranks, rank, unique_id=None):

@@ -23,9 +23,14 @@ struct BinParams
   double box[3]; int wrap[3];          // periodic wrap (only when this rank spans the whole axis)
 };
 
-__device__ __forceinline__ int own_cell_coord(double r, double o, double cell, int n_own)
+// cell of a coordinate along one axis.  A particle outside the own cells is clamped into the border cell (the
+// reference's move_particles keeps such "otb" particles aside, ext exaNBody): `how` gets 1 when that happened and 2
+// when the particle is more than one cell outside, which the callers turn into an error -- the list build's search
+// range and its FP32 guard band (xsb_nbr.cu) assume atoms lie within a cell of the cell that holds them.
+__device__ __forceinline__ int own_cell_coord(double r, double o, double cell, int n_own, int& how)
 {
   int c = int(floor((r - o) / cell));
+  if( c < 0 || c >= n_own ) how = max(how, (c < -1 || c > n_own) ? 2 : 1);
   return min(max(c, 0), n_own - 1);
 }
 
@@ -38,12 +43,14 @@ __global__ void bin_kernel(unsigned n, BinParams B, double* __restrict__ rx, dou
   if( B.wrap[0] ) { x -= floor((x - B.ox) / B.box[0]) * B.box[0]; if( x - B.ox >= B.box[0] ) x = B.ox; rx[i] = x; }
   if( B.wrap[1] ) { y -= floor((y - B.oy) / B.box[1]) * B.box[1]; if( y - B.oy >= B.box[1] ) y = B.oy; ry[i] = y; }
   if( B.wrap[2] ) { z -= floor((z - B.oz) / B.box[2]) * B.box[2]; if( z - B.oz >= B.box[2] ) z = B.oz; rz[i] = z; }
-  const int ci = own_cell_coord(x, B.ox, B.cell, B.nx - 2 * B.gl) + B.gl;
-  const int cj = own_cell_coord(y, B.oy, B.cell, B.ny - 2 * B.gl) + B.gl;
-  const int ck = own_cell_coord(z, B.oz, B.cell, B.nz - 2 * B.gl) + B.gl;
+  int how = 0;
+  const int ci = own_cell_coord(x, B.ox, B.cell, B.nx - 2 * B.gl, how) + B.gl;
+  const int cj = own_cell_coord(y, B.oy, B.cell, B.ny - 2 * B.gl, how) + B.gl;
+  const int ck = own_cell_coord(z, B.oz, B.cell, B.nz - 2 * B.gl, how) + B.gl;
   const unsigned c = unsigned(ci) + unsigned(B.nx) * (unsigned(cj) + unsigned(B.ny) * unsigned(ck));
   key[i] = c; val[i] = i;
   atomicAdd(counts + c, 1u);
+  if( how ) atomicAdd(counts + B.nx * B.ny * B.nz + (how - 1), 1u);      // [ncells]: clamped, [ncells+1]: lost (> 1 cell outside)
 }
 
 template<class T>
@@ -168,9 +175,9 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
   XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, 1.02));
   XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32d.reserve(std::max(n, nc) + 16, 1.02));
   unsigned *key = ctx->tmp32a.p, *val = ctx->tmp32b.p, *key2 = ctx->tmp32c.p, *perm = ctx->tmp32d.p;
-  XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(nc) + 2));
+  XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(nc) + 4));
   unsigned* counts = reinterpret_cast<unsigned*>(ctx->scratch64.p);
-  XSB_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t(nc) + 1) * sizeof(unsigned), ctx->stream));
+  XSB_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t(nc) + 2) * sizeof(unsigned), ctx->stream));
   if( n )
   {
     bin_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, B, rx, ry, rz, key, val, counts);
@@ -182,9 +189,11 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
     XSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->scratch.p, tmp, key, key2, val, perm, int(n), 0, end_bit, ctx->stream));
     ctx->launches += 4;
   }
-  std::vector<unsigned> hc(nc);
-  XSB_CUDA(ctx, cudaMemcpyAsync(hc.data(), counts, size_t(nc) * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<unsigned> hc(size_t(nc) + 2);
+  XSB_CUDA(ctx, cudaMemcpyAsync(hc.data(), counts, (size_t(nc) + 2) * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->otb_clamped = hc[nc] + hc[nc + 1];
+  if( hc[nc + 1] ) return ctx->fail(XSB_ERR_INVALID, "%u particle(s) lie more than one cell outside the own cells of this grid (lost particles: the list build assumes atoms sit in their cells)", hc[nc + 1]);
   std::vector<uint64_t> off(size_t(nc) + 1, 0);
   for(unsigned c = 0; c < nc; c++) off[c + 1] = off[c] + hc[c];
   if( off[nc] != n ) return ctx->fail(XSB_ERR_STATE, "assign: binned %llu of %u particles", (unsigned long long)off[nc], n);
@@ -215,7 +224,7 @@ extern "C" {
 int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const double* ry, const double* rz,
                          const double* vx, const double* vy, const double* vz, const uint8_t* type, const uint64_t* id)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
   XSB_REQUIRE(ctx, n < 0xFFFFFFF0ull, XSB_ERR_OVERFLOW, "more than 2^32 particles per GPU");
   XSB_REQUIRE(ctx, n == 0 || (rx && ry && rz), XSB_ERR_INVALID, "null positions");
@@ -243,7 +252,7 @@ int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const doubl
 // cells (stable), leaving ghost cells empty -- call xsb_ghost_comm_scheme and xsb_chunk_neighbors_build afterwards.
 int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, dom != nullptr, XSB_ERR_INVALID, "null domain");
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
   const int P = dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2];
@@ -281,6 +290,13 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
   }
   ctx->prof_end(XSB_PROF_MOVE);
   return rc;
+}
+
+int xsb_out_of_domain_count(xsb_ctx* ctx, uint64_t* clamped)
+{
+  if( !ctx || !clamped ) return XSB_ERR_STATE;
+  *clamped = ctx->otb_clamped;
+  return XSB_OK;
 }
 
 int xsb_migration_stats(xsb_ctx* ctx, uint64_t* sent, uint64_t* received)
@@ -353,7 +369,7 @@ extern "C" {
 // ---- Verlet pieces ---------------------------------------------------------------------------------------------
 int xsb_push_f_v_r(xsb_ctx* ctx, double dt)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   const unsigned n = unsigned(ctx->n_own); if( !n ) return XSB_OK;
   ctx->pos_epoch++;
   XFormInv Xi; Xi.identity = ctx->grid.xform_is_identity; invert3(ctx->grid.xform, Xi.m);
@@ -366,7 +382,7 @@ int xsb_push_f_v_r(xsb_ctx* ctx, double dt)
 
 int xsb_push_f_v(xsb_ctx* ctx, double dt)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   const unsigned n = unsigned(ctx->n_own); if( !n ) return XSB_OK;
   push_f_v_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->own_atoms.p, dt, ctx->f64[XSB_F_VX].p, ctx->f64[XSB_F_VY].p, ctx->f64[XSB_F_VZ].p,
       ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p);
@@ -376,7 +392,7 @@ int xsb_push_f_v(xsb_ctx* ctx, double dt)
 
 int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, mass != nullptr && n_types >= 1 && n_types <= 16, XSB_ERR_INVALID, "1..16 species masses expected");
   const unsigned n = unsigned(ctx->n_own); if( !n ) return XSB_OK;
   MassTab M; for(int i = 0; i < 16; i++) M.inv_mass[i] = i < n_types ? 1.0 / mass[i] : 0.0;
@@ -387,7 +403,7 @@ int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass)
 
 int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt, double threshold, int* result, double* max_displ)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, mass != nullptr && n_types >= 1 && n_types <= 16, XSB_ERR_INVALID, "1..16 species masses expected");
   XSB_REQUIRE(ctx, result != nullptr, XSB_ERR_INVALID, "null result");
   const unsigned n = unsigned(ctx->n_own);
@@ -418,7 +434,7 @@ int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt
 
 int xsb_backup_r(xsb_ctx* ctx)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   const unsigned n = unsigned(ctx->n_own);
   XSB_CUDA(ctx, ctx->backup.reserve(3 * (size_t(n) + 1), 1.02));
   ctx->backup_n = n;
@@ -431,7 +447,7 @@ int xsb_backup_r(xsb_ctx* ctx)
 
 int xsb_particle_displ_over(xsb_ctx* ctx, double threshold, int* result, double* max_displ)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, result != nullptr, XSB_ERR_INVALID, "null result");
   const unsigned n = unsigned(ctx->n_own);
   XSB_REQUIRE(ctx, ctx->backup_n == n, XSB_ERR_STATE, "xsb_backup_r must be called after the last rebuild");

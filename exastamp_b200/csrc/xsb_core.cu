@@ -16,7 +16,7 @@ static void inverse3(const double* m, double* inv)
   inv[6] =  (m[3]*m[7]-m[4]*m[6])*id; inv[7] = -(m[0]*m[7]-m[1]*m[6])*id; inv[8] =  (m[0]*m[4]-m[1]*m[3])*id;
 }
 
-void search_range(const xsb_grid_desc& g, double dist, int R[3])
+void search_range_unclamped(const xsb_grid_desc& g, double dist, int R[3])
 {
   double inv[9] = {1,0,0,0,1,0,0,0,1};
   if( !g.xform_is_identity ) inverse3(g.xform, inv);
@@ -25,8 +25,13 @@ void search_range(const xsb_grid_desc& g, double dist, int R[3])
     const double nrm = std::sqrt(inv[3*a]*inv[3*a] + inv[3*a+1]*inv[3*a+1] + inv[3*a+2]*inv[3*a+2]);
     R[a] = int(std::ceil(dist * nrm / g.cell_size));
     if( R[a] < 1 ) R[a] = 1;
-    if( R[a] > 15 ) R[a] = 15;   // range of the 5-bit relative cell index of the exported stream
   }
+}
+
+void search_range(const xsb_grid_desc& g, double dist, int R[3])
+{
+  search_range_unclamped(g, dist, R);
+  for(int a = 0; a < 3; a++) if( R[a] > 15 ) R[a] = 15;   // range of the 5-bit relative cell index of the exported stream (callers reject more)
 }
 
 __global__ void zero_fields_kernel(const unsigned* __restrict__ atoms, unsigned n_atoms, unsigned n_all, bool all,
@@ -43,9 +48,50 @@ __global__ void zero_fields_kernel(const unsigned* __restrict__ atoms, unsigned 
   }
 }
 
+// own-only transfers: staging[f][t] <-> field_f[own_atoms[t]]
+struct XferFields { double* p[8]; int nf; };
+__global__ void xfer_scatter_kernel(unsigned n, const unsigned* __restrict__ atoms, XferFields F, const double* __restrict__ stage, size_t pitch)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= n ) return;
+  const unsigned a = atoms[t];
+  for(int f = 0; f < F.nf; f++) F.p[f][a] = stage[size_t(f) * pitch + t];
+}
+__global__ void xfer_gather_kernel(unsigned n, const unsigned* __restrict__ atoms, XferFields F, double* __restrict__ stage, size_t pitch)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if( t >= n ) return;
+  const unsigned a = atoms[t];
+  for(int f = 0; f < F.nf; f++) stage[size_t(f) * pitch + t] = F.p[f][a];
+}
+
 } // namespace xsb
 
 using namespace xsb;
+
+static int xfer_setup(xsb_ctx* ctx)
+{
+  if( ctx->copy_up ) return XSB_OK;
+  XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_up, cudaStreamNonBlocking));
+  XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_down, cudaStreamNonBlocking));
+  cudaEvent_t* ev[4] = { &ctx->ev_up_done, &ctx->ev_up_free, &ctx->ev_down_ready, &ctx->ev_down_done };
+  for(int i = 0; i < 4; i++) XSB_CUDA(ctx, cudaEventCreateWithFlags(ev[i], cudaEventDisableTiming));
+  return XSB_OK;
+}
+
+static int xfer_fields(xsb_ctx* ctx, int nfields, const int* fields, xsb::XferFields& F)
+{
+  XSB_REQUIRE(ctx, nfields >= 1 && nfields <= 8 && fields != nullptr, XSB_ERR_INVALID, "1..8 fields per asynchronous transfer");
+  XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "xsb_particles_set_cells must be called first");
+  F.nf = nfields;
+  for(int k = 0; k < nfields; k++)
+  {
+    const int f = fields[k];
+    XSB_REQUIRE(ctx, f >= 0 && f < XSB_F_TYPE && f != XSB_F_VIRIAL, XSB_ERR_INVALID, "asynchronous transfers carry the scalar double fields (r, f, ep, v, rho_dEmb)");
+    F.p[k] = ctx->f64[f].p;
+  }
+  return XSB_OK;
+}
 
 int xsb_internal_ensure_virial(xsb_ctx* ctx)
 {
@@ -62,7 +108,7 @@ namespace xsb
 __global__ void __launch_bounds__(256) cell_tables_kernel(unsigned ncells, const unsigned* __restrict__ cell_start, const unsigned* __restrict__ own_prefix,
                                                           unsigned* __restrict__ cell_of, unsigned* __restrict__ own_atoms)
 {
-  const unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  const unsigned c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
   if( c >= ncells ) return;
   const unsigned s = cell_start[c], e = cell_start[c + 1], o = own_prefix[c];
   const bool own = own_prefix[c + 1] - o == e - s;   // ghost cells add nothing to the own-particle prefix
@@ -91,6 +137,8 @@ int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
   }
   start[nc] = unsigned(off[nc]); ownp[nc] = unsigned(nown);
   ctx->n = n; ctx->n_own = nown; ctx->pos_epoch++;
+  ctx->backup_n = 0xffffffffu;      // the own particles were re-ordered: a backup_r of the old order compares different atoms
+  ctx->ghost_valid = false;         // exchange lists index the old layout (xsb_ghost_comm_scheme sets it again)
   XSB_CUDA(ctx, ctx->cell_start.reserve(2 * (nc + 1)));
   XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, 1.02));
   XSB_CUDA(ctx, ctx->own_atoms.reserve(nown + 1, 1.02));
@@ -238,6 +286,10 @@ void xsb_destroy(xsb_ctx* ctx)
   ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->eam.fc32.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   xsb_snap_release(ctx);
+  ctx->stage_up.release(); ctx->stage_down.release();
+  if( ctx->copy_up ) { cudaStreamSynchronize(ctx->copy_up); cudaStreamDestroy(ctx->copy_up); }
+  if( ctx->copy_down ) { cudaStreamSynchronize(ctx->copy_down); cudaStreamDestroy(ctx->copy_down); }
+  for(cudaEvent_t e : { ctx->ev_up_done, ctx->ev_up_free, ctx->ev_down_ready, ctx->ev_down_done }) if( e ) cudaEventDestroy(e);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -248,7 +300,7 @@ uint64_t xsb_kernel_launch_count(const xsb_ctx* ctx) { return ctx ? ctx->launche
 
 int xsb_profile_enable(xsb_ctx* ctx, int on)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->prof_on = on != 0;
   for(int t = 0; t < XSB_PROF_COUNT_; t++) ctx->prof_used[t] = 0;
@@ -257,7 +309,7 @@ int xsb_profile_enable(xsb_ctx* ctx, int on)
 
 int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* intervals)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, tag >= 0 && tag < XSB_PROF_COUNT_, XSB_ERR_INVALID, "unknown profile tag");
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double tot = 0.0;
@@ -275,7 +327,7 @@ int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* interval
 // two-slot stopwatch on the context's stream: slot 0 = start, slot 1 = stop
 int xsb_timer_record(xsb_ctx* ctx, int slot)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, slot == 0 || slot == 1, XSB_ERR_INVALID, "timer slot must be 0 or 1");
   if( !ctx->timer_ev[slot] ) XSB_CUDA(ctx, cudaEventCreate(&ctx->timer_ev[slot]));
   XSB_CUDA(ctx, cudaEventRecord(ctx->timer_ev[slot], ctx->stream));
@@ -284,7 +336,7 @@ int xsb_timer_record(xsb_ctx* ctx, int slot)
 
 int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, double* hbm_gbs)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaEvent_t e0, e1;
   XSB_CUDA(ctx, cudaEventCreate(&e0)); XSB_CUDA(ctx, cudaEventCreate(&e1));
@@ -319,7 +371,7 @@ int xsb_measure_peaks(xsb_ctx* ctx, double* fp64_tflops, double* fp32_tflops, do
 
 int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ms && ctx->timer_ev[0] && ctx->timer_ev[1], XSB_ERR_STATE, "timer not recorded");
   XSB_CUDA(ctx, cudaEventSynchronize(ctx->timer_ev[1]));
   float f = 0.f;
@@ -330,14 +382,14 @@ int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms)
 
 int xsb_sync(xsb_ctx* ctx)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return XSB_OK;
 }
 
 int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, g != nullptr, XSB_ERR_INVALID, "null grid");
   XSB_REQUIRE(ctx, g->dims[0] > 0 && g->dims[1] > 0 && g->dims[2] > 0, XSB_ERR_INVALID, "grid dims must be positive");
   XSB_REQUIRE(ctx, g->ghost_layers >= 0 && 2 * g->ghost_layers < g->dims[0] && 2 * g->ghost_layers < g->dims[1] && 2 * g->ghost_layers < g->dims[2],
@@ -355,7 +407,7 @@ int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
 
 int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, xform != nullptr, XSB_ERR_INVALID, "null xform");
   XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
   bool ident = true;
@@ -372,7 +424,7 @@ int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
 
 int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
   XSB_REQUIRE(ctx, off != nullptr && off[0] == 0, XSB_ERR_INVALID, "cell_particle_offset[0] must be 0");
   const uint64_t nc = ctx->ncells;
@@ -398,7 +450,7 @@ int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
 
 int xsb_cell_offsets_download(xsb_ctx* ctx, uint64_t* off)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, off != nullptr && ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
   std::memcpy(off, ctx->h_cell_off.data(), (ctx->ncells + 1) * sizeof(uint64_t));
   return XSB_OK;
@@ -422,7 +474,7 @@ static int field_ptr(xsb_ctx* ctx, int field, void** p, size_t* bytes)
 
 int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, src != nullptr, XSB_ERR_INVALID, "null source");
   void* p = nullptr; size_t bytes = 0;
   int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
@@ -434,7 +486,7 @@ int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
 
 int xsb_field_download(xsb_ctx* ctx, int field, void* dst)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, dst != nullptr, XSB_ERR_INVALID, "null destination");
   void* p = nullptr; size_t bytes = 0;
   int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
@@ -443,9 +495,95 @@ int xsb_field_download(xsb_ctx* ctx, int field, void* dst)
   return XSB_OK;
 }
 
+// ---- asynchronous transfers ------------------------------------------------------------------------------------------
+// upload: [copy_up] wait(staging free) -> H2D into staging -> record(up_done)
+//         [stream]  wait(up_done) -> scatter staging -> fields -> record(staging free)
+// The H2D overlaps with everything enqueued on the compute stream before this call (the force passes of the step in
+// flight still read the old positions); work enqueued after it sees the new values.
+int xsb_fields_upload_async(xsb_ctx* ctx, int nfields, const int* fields, const void* const* host_src, int own_only)
+{
+  XSB_ENTER(ctx);
+  xsb::XferFields F; int rc = xfer_fields(ctx, nfields, fields, F); if( rc ) return rc;
+  XSB_REQUIRE(ctx, host_src != nullptr, XSB_ERR_INVALID, "null host array list");
+  if( (rc = xfer_setup(ctx)) ) return rc;
+  const size_t n = own_only ? ctx->n_own : ctx->n;
+  if( n == 0 ) return XSB_OK;
+  const size_t pitch = (n + 15) & ~size_t(15);
+  if( ctx->stage_up.cap < pitch * 8 )
+  {
+    if( ctx->up_pending ) XSB_CUDA(ctx, cudaEventSynchronize(ctx->ev_up_free));
+    XSB_CUDA(ctx, ctx->stage_up.reserve(pitch * 8, 1.05));
+  }
+  if( ctx->up_pending ) XSB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_up, ctx->ev_up_free, 0));
+  for(int k = 0; k < nfields; k++)
+  {
+    XSB_REQUIRE(ctx, host_src[k] != nullptr, XSB_ERR_INVALID, "null host array");
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_up.p + size_t(k) * pitch, host_src[k], n * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_up));
+  }
+  XSB_CUDA(ctx, cudaEventRecord(ctx->ev_up_done, ctx->copy_up));
+  XSB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up_done, 0));
+  if( own_only )
+  {
+    xsb::xfer_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(unsigned(n), ctx->own_atoms.p, F, ctx->stage_up.p, pitch);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  else
+    for(int k = 0; k < nfields; k++) XSB_CUDA(ctx, cudaMemcpyAsync(F.p[k], ctx->stage_up.p + size_t(k) * pitch, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaEventRecord(ctx->ev_up_free, ctx->stream));
+  ctx->up_pending = true;
+  for(int k = 0; k < nfields; k++) if( fields[k] == XSB_F_RX || fields[k] == XSB_F_RY || fields[k] == XSB_F_RZ ) { ctx->pos_epoch++; break; }
+  return XSB_OK;
+}
+
+// download: [stream]    wait(previous D2H done) -> gather fields -> staging -> record(down_ready)
+//           [copy_down] wait(down_ready) -> D2H -> record(down_done)
+// The snapshot is taken at this point of the compute stream; the D2H overlaps with what is enqueued afterwards.
+// The host arrays are valid after xsb_copy_wait().
+int xsb_fields_download_async(xsb_ctx* ctx, int nfields, const int* fields, void* const* host_dst, int own_only)
+{
+  XSB_ENTER(ctx);
+  xsb::XferFields F; int rc = xfer_fields(ctx, nfields, fields, F); if( rc ) return rc;
+  XSB_REQUIRE(ctx, host_dst != nullptr, XSB_ERR_INVALID, "null host array list");
+  if( (rc = xfer_setup(ctx)) ) return rc;
+  const size_t n = own_only ? ctx->n_own : ctx->n;
+  if( n == 0 ) return XSB_OK;
+  const size_t pitch = (n + 15) & ~size_t(15);
+  if( ctx->stage_down.cap < pitch * 8 )
+  {
+    if( ctx->down_pending ) XSB_CUDA(ctx, cudaEventSynchronize(ctx->ev_down_done));
+    XSB_CUDA(ctx, ctx->stage_down.reserve(pitch * 8, 1.05));
+  }
+  if( ctx->down_pending ) XSB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_down_done, 0));
+  if( own_only )
+  {
+    xsb::xfer_gather_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(unsigned(n), ctx->own_atoms.p, F, ctx->stage_down.p, pitch);
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  else
+    for(int k = 0; k < nfields; k++) XSB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_down.p + size_t(k) * pitch, F.p[k], n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaEventRecord(ctx->ev_down_ready, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_down, ctx->ev_down_ready, 0));
+  for(int k = 0; k < nfields; k++)
+  {
+    XSB_REQUIRE(ctx, host_dst[k] != nullptr, XSB_ERR_INVALID, "null host array");
+    XSB_CUDA(ctx, cudaMemcpyAsync(host_dst[k], ctx->stage_down.p + size_t(k) * pitch, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_down));
+  }
+  XSB_CUDA(ctx, cudaEventRecord(ctx->ev_down_done, ctx->copy_down));
+  ctx->down_pending = true;
+  return XSB_OK;
+}
+
+int xsb_copy_wait(xsb_ctx* ctx)
+{
+  XSB_ENTER(ctx);
+  if( ctx->down_pending ) XSB_CUDA(ctx, cudaEventSynchronize(ctx->ev_down_done));
+  if( ctx->up_pending ) XSB_CUDA(ctx, cudaEventSynchronize(ctx->ev_up_free));
+  return XSB_OK;
+}
+
 void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
 {
-  if( !ctx || !ctx->stream ) return nullptr;
+  if( !ctx || !ctx->stream || cudaSetDevice(ctx->device) != cudaSuccess ) return nullptr;
   void* p = nullptr; size_t bytes = 0;
   if( field_ptr(ctx, field, &p, &bytes) ) return nullptr;
   if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_external = true;   // caller may move particles behind our back
@@ -455,7 +593,7 @@ void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
 
 int xsb_zero_force_energy(xsb_ctx* ctx, int ghost)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "no particles");
   if( ctx->n == 0 ) return XSB_OK;
   const unsigned n = ghost ? unsigned(ctx->n) : unsigned(ctx->n_own);

@@ -134,9 +134,13 @@ struct xsb_ctx
   // a8
   xsb::EamAlloyDev eam;
 
+  // a9
+  void* snap = nullptr;                       // xsb::SnapDev (xsb_snap.cu), owned by the context
+
   // a10
   ncclComm* comm = nullptr; int nranks = 1, rank = 0;
   xsb::GhostState* ghost = nullptr;           // built by xsb_ghost_comm_scheme (xsb_ghost.cu)
+  bool ghost_valid = false;                   // its lists index the current particle layout
   xsb::DevBuf<unsigned> old_cell_start;       // relayout scratch
   xsb::DevBuf<unsigned long long> tmp64;      // relayout / sort scratch (8-byte words)
   xsb::DevBuf<unsigned> tmp32a, tmp32b, tmp32c, tmp32d;
@@ -144,7 +148,15 @@ struct xsb_ctx
   xsb::DevBuf<double> move_stage; xsb::DevBuf<unsigned char> move_stage8;   // move_particles staging (persistent)
   xsb::DevBuf<double> move_stage_b, move_stage_c; xsb::DevBuf<unsigned char> move_stage8_b, move_stage8_c;   // cross-rank migration
   uint64_t migrated_out = 0, migrated_in = 0;   // particles that changed rank in the last xsb_particles_rebin
+  uint64_t otb_clamped = 0;                     // particles the last binning clamped into a border cell (xsb_out_of_domain_count)
   xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
+
+  // asynchronous host <-> device field transfers (xsb_fields_upload_async / _download_async, xsb_core.cu): one copy stream
+  // per direction so H2D and D2H use both DMA engines while the compute stream runs the passes
+  cudaStream_t copy_up = nullptr, copy_down = nullptr;
+  cudaEvent_t ev_up_done = nullptr, ev_up_free = nullptr, ev_down_ready = nullptr, ev_down_done = nullptr;
+  bool up_pending = false, down_pending = false;
+  xsb::DevBuf<double> stage_up, stage_down;
 
   // per-operator device timing (CUDA events on this context's stream), see xsb_profile_*
   bool prof_on = false;
@@ -179,6 +191,9 @@ struct xsb_ctx
 
 #define XSB_CUDA(ctx, call) do { cudaError_t e__ = (call); if( e__ != cudaSuccess ) \
   return (ctx)->fail(XSB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } while(0)
+// first statement of every extern "C" entry that touches the stream or allocates: one context per GPU, several contexts
+// (devices) may live in one process, so the calling thread's current device must follow the context
+#define XSB_ENTER(ctx) do { if( !(ctx) || !(ctx)->stream ) return XSB_ERR_STATE; XSB_CUDA(ctx, cudaSetDevice((ctx)->device)); } while(0)
 #define XSB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if( e__ != cudaSuccess ) \
   return (ctx)->fail(XSB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } while(0)
 #define XSB_REQUIRE(ctx, cond, code, msg) do { if( !(cond) ) return (ctx)->fail(code, "%s", msg); } while(0)
@@ -199,4 +214,5 @@ namespace xsb
 {
 // search range (cell layers per axis) covering every grid-space displacement of physical length < dist
 void search_range(const xsb_grid_desc& g, double dist, int R[3]);
+void search_range_unclamped(const xsb_grid_desc& g, double dist, int R[3]);
 }

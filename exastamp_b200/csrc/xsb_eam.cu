@@ -690,7 +690,7 @@ extern "C" {
 
 int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int phases, int flags)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, params19 != nullptr && rcut > 0.0, XSB_ERR_INVALID, "johnson: null parameters or rcut <= 0");
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
   XSB_REQUIRE(ctx, rcut <= ctx->nbh_dist, XSB_ERR_INVALID, "rcut exceeds the neighbour-list distance nbh_dist_lab");
@@ -817,7 +817,7 @@ void xsb_eam_alloy_free(xsb_eam_alloy_tables* t)
 
 int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, t && t->frho && t->rhor && t->z2r, XSB_ERR_INVALID, "null eam tables");
   XSB_REQUIRE(ctx, t->nelements >= 1 && t->nelements <= 7 && t->nr >= 5 && t->nrho >= 5, XSB_ERR_INVALID, "bad eam table sizes");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -855,7 +855,7 @@ int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
 
 int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->eam.set, XSB_ERR_STATE, "xsb_eam_alloy_set must be called first");
   XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");

@@ -196,7 +196,7 @@ struct RangeEntry { unsigned start, count, out, seg_code; };   // seg_code = pee
 __global__ void __launch_bounds__(256) expand_ranges_kernel(unsigned n_entries, const RangeEntry* __restrict__ E, unsigned* __restrict__ idx,
                                                             unsigned char* __restrict__ code, unsigned* __restrict__ seg)
 {
-  const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  const unsigned i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
   if( i >= n_entries ) return;
   const RangeEntry e = E[i];
   for(unsigned p = lane; p < e.count; p += 32u)
@@ -230,8 +230,7 @@ static int make_fields(xsb_ctx* ctx, uint32_t mask, bool reverse, FieldPtrs& F)
 static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
 {
   GhostState* G = ctx->ghost;
-  XSB_REQUIRE(ctx, G != nullptr, XSB_ERR_STATE, "xsb_ghost_comm_scheme must be called first");
-  XSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  XSB_REQUIRE(ctx, G != nullptr && ctx->ghost_valid, XSB_ERR_STATE, "xsb_ghost_comm_scheme must be called first (and again after every particle re-layout)");
   if( mask & ((1u << XSB_F_RX) | (1u << XSB_F_RY) | (1u << XSB_F_RZ)) ) ctx->pos_epoch++;
   FieldPtrs F; int rc = make_fields(ctx, mask, reverse, F); if( rc ) return rc;
   ShiftTab S; std::memcpy(S.s, G->shift, sizeof(S.s));
@@ -310,7 +309,7 @@ int xsb_comm_unique_id(void* id128)
 
 int xsb_comm_init(xsb_ctx* ctx, int nranks, int rank, const void* id128)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, XSB_ERR_INVALID, "bad rank / nranks");
   ctx->nranks = nranks; ctx->rank = rank;
   if( nranks == 1 ) return XSB_OK;
@@ -325,7 +324,7 @@ int xsb_comm_init(xsb_ctx* ctx, int nranks, int rank, const void* id128)
 
 int xsb_comm_allreduce_max(xsb_ctx* ctx, double* inout_host)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   if( ctx->nranks == 1 ) return XSB_OK;
   XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "xsb_comm_init must be called first");
   XSB_CUDA(ctx, ctx->scratch64.reserve(16));
@@ -513,7 +512,7 @@ int xsb_ghost_plan(const xsb_domain_desc* dom, int ghost_layers, const int32_t* 
 
 int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, dom != nullptr, XSB_ERR_INVALID, "null domain");
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "grid/particles not set");
   const int P = dom->rank_dims[0] * dom->rank_dims[1] * dom->rank_dims[2];
@@ -638,13 +637,14 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_send.p, G->send_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_recv.p, G->recv_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ghost_valid = true;
   // ghost_update_all_no_fv: every persistent field travels once
   return exchange(ctx, (1u << XSB_F_RX) | (1u << XSB_F_RY) | (1u << XSB_F_RZ) | (1u << XSB_F_VX) | (1u << XSB_F_VY) | (1u << XSB_F_VZ) | (1u << XSB_F_TYPE) | (1u << XSB_F_ID), false);
 }
 
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   ctx->prof_begin(XSB_PROF_GHOST);
   const int rc = exchange(ctx, field_mask, false);
   ctx->prof_end(XSB_PROF_GHOST);
@@ -653,7 +653,7 @@ int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask)
 
 int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   ctx->prof_begin(XSB_PROF_GHOST);
   const int rc = exchange(ctx, field_mask, true);
   ctx->prof_end(XSB_PROF_GHOST);

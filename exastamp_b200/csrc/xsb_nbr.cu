@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) nbr_sweep_kernel(NbrParams P, const unsig
                                                          unsigned long long* __restrict__ d2min_bits)
 {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // no 32-bit overflow of the thread index above 2^27 atoms
   if( a >= P.n ) return;
   const unsigned ca = cell_of[a];
   const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
@@ -548,7 +548,7 @@ extern "C" {
 
 int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk_neighbors_config* cfg)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "grid/particles not set");
   XSB_REQUIRE(ctx, nbh_dist_lab > 0.0, XSB_ERR_INVALID, "nbh_dist_lab must be > 0");
   if( cfg )
@@ -574,6 +574,18 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   ctx->prof_begin(XSB_PROF_NBR_BUILD);
   NbrParams P; P.g = ctx->view(); P.n = n; P.d2max = nbh_dist_lab * nbh_dist_lab;
   int R[3]; search_range(ctx->grid, nbh_dist_lab, R); P.Rx = R[0]; P.Ry = R[1]; P.Rz = R[2];
+  {
+    // the cells a list can reach must exist around every own cell: with ghost layers thinner than the search range the
+    // own atoms next to the ghost border would silently get truncated lists (the reference sizes ghost_layers from
+    // ghost_dist / cell_size, so the two always agree there); 15 = range of the 5-bit relative cell index of the stream
+    int Ru[3]; search_range_unclamped(ctx->grid, nbh_dist_lab, Ru);
+    for(int a = 0; a < 3; a++)
+    {
+      if( Ru[a] > 15 ) return ctx->fail(XSB_ERR_INVALID, "chunk_neighbors: nbh_dist_lab %g spans %d cells along axis %d (limit 15: relative cell index of the stream)", nbh_dist_lab, Ru[a], a);
+      if( ctx->grid.ghost_layers > 0 && Ru[a] > ctx->grid.ghost_layers )
+        return ctx->fail(XSB_ERR_INVALID, "chunk_neighbors: nbh_dist_lab %g needs %d cell layers along axis %d but the grid has ghost_layers = %d", nbh_dist_lab, Ru[a], a, ctx->grid.ghost_layers);
+    }
+  }
   const int block = 256; const unsigned grid = unsigned((uint64_t(n) * 32 + block - 1) / block);
   const double *rx = ctx->f64[XSB_F_RX].p, *ry = ctx->f64[XSB_F_RY].p, *rz = ctx->f64[XSB_F_RZ].p;
   // tile path: the same fixed tiling the force kernels use; one CTA per tile with its 27-cell block staged in shared memory
@@ -680,7 +692,7 @@ double xsbdbg_nbr_fp32_band(double cell_size, const double* xform9, int tile_tx,
 
 int xsb_chunk_neighbors_stats(xsb_ctx* ctx, uint64_t* total, uint32_t* maxn)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors not built");
   if( total ) *total = ctx->nbh_total;
   if( maxn ) *maxn = ctx->nbh_max;
@@ -714,7 +726,7 @@ static int export_prepare(xsb_ctx* ctx, DevBuf<unsigned long long>& poff, DevBuf
 
 int xsb_chunk_neighbors_export_size(xsb_ctx* ctx, uint64_t* total_u16)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, total_u16 != nullptr, XSB_ERR_INVALID, "null output");
   DevBuf<unsigned long long> poff, soff;
   int rc = export_prepare(ctx, poff, soff, total_u16);
@@ -724,7 +736,7 @@ int xsb_chunk_neighbors_export_size(xsb_ctx* ctx, uint64_t* total_u16)
 
 int xsb_chunk_neighbors_export(xsb_ctx* ctx, uint64_t* stream_off, uint16_t* data)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, stream_off != nullptr && data != nullptr, XSB_ERR_INVALID, "null output");
   DevBuf<unsigned long long> poff, soff; DevBuf<unsigned short> dd;
   uint64_t tot = 0;
@@ -755,7 +767,7 @@ int xsb_chunk_neighbors_export(xsb_ctx* ctx, uint64_t* stream_off, uint16_t* dat
 
 int xsb_chunk_neighbors_download_flat(xsb_ctx* ctx, uint32_t* counts, uint64_t* offsets, uint32_t* idx)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors not built");
   if( counts && ctx->n ) XSB_CUDA(ctx, cudaMemcpyAsync(counts, ctx->nbh_count.p, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if( offsets ) XSB_CUDA(ctx, cudaMemcpyAsync(offsets, ctx->nbh_off.p, (ctx->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));

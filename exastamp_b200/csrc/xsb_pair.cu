@@ -281,7 +281,7 @@ extern "C" {
 
 int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
   XSB_REQUIRE(ctx, params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "wrong parameter count: lj {epsilon, sigma}, zbl {r1, rc, z_a, z_b}, exp6 {A, B, C, D}, buckingham {A, Rho, C}");
   XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
@@ -291,7 +291,7 @@ int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, dou
 
 int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, double rcut_max, int flags)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
   XSB_REQUIRE(ctx, pair_params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "rows of {params..., rcut} expected");
   const int npairs = n_types * (n_types + 1) / 2;

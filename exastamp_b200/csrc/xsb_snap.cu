@@ -20,7 +20,6 @@
 #include "xsb_tile.cuh"
 #include <algorithm>
 #include <cmath>
-#include <map>
 #include <type_traits>
 #include <vector>
 
@@ -51,11 +50,11 @@ struct SnapDev
   DevBuf<double2> ubuf, ybuf;                                                          // chunk staging (AoSoA)
   DevBuf<double> nbtab; DevBuf<unsigned> nbcnt;                                        // in-range neighbours of the chunk's atoms (Utot kernel -> force kernel)
   double rcut_max = 0.0;
+  bool overflowed = false;       // a call hit SNAP_NN_MAX since xsb_snap_overflow() was last read
 };
 
-// the SNAP state hangs off the context through a map kept in this translation unit
-static std::map<xsb_ctx*, SnapDev*> g_snap;
-static SnapDev* g_snap_of(xsb_ctx* ctx) { auto it = g_snap.find(ctx); return it == g_snap.end() ? nullptr : it->second; }
+// the SNAP state of a context hangs off the context itself (xsb_ctx::snap), like GhostState: no process-global table
+static SnapDev* g_snap_of(xsb_ctx* ctx) { return static_cast<SnapDev*>(ctx->snap); }
 
 __device__ __forceinline__ double snap_sfac(const SnapConst& K, double r, double rcut)
 {
@@ -928,11 +927,12 @@ using namespace xsb;
 
 void xsb_snap_release(xsb_ctx* ctx)
 {
-  auto it = g_snap.find(ctx);
-  if( it == g_snap.end() ) return;
+  SnapDev* sd = g_snap_of(ctx);
+  if( !sd ) return;
+  struct { SnapDev* second; } itv{ sd }; auto* it = &itv;
   it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
   it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->nbtab.release(); it->second->nbcnt.release(); it->second->clk.release();
-  delete it->second; g_snap.erase(it);
+  delete it->second; ctx->snap = nullptr;
 }
 
 constexpr unsigned SNAP_CHUNK = 65536;     // central atoms per pass of the split pipeline (Utot + Y staging: 2 x 285 x 16 B per atom)
@@ -1015,15 +1015,15 @@ int xsb_snap_ncoeff(int twojmax)
 
 int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, p != nullptr && p->radelem && p->wjelem && p->beta, XSB_ERR_INVALID, "snap: null parameters");
   XSB_REQUIRE(ctx, p->twojmax >= 1 && p->twojmax <= 8, XSB_ERR_UNSUPPORTED, "snap: twojmax must be in 1..8");
   XSB_REQUIRE(ctx, p->nelements >= 1 && p->nelements <= 8, XSB_ERR_INVALID, "snap: 1..8 elements");
   XSB_REQUIRE(ctx, p->quadraticflag == 0 && p->chemflag == 0 && p->switchinnerflag == 0, XSB_ERR_UNSUPPORTED, "snap: quadratic / chem / inner-switch variants are not implemented");
   XSB_REQUIRE(ctx, p->rcutfac > 0.0, XSB_ERR_INVALID, "snap: rcutfac must be > 0");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
-  SnapDev*& S = g_snap[ctx];
-  if( !S ) S = new SnapDev;
+  SnapDev* S = g_snap_of(ctx);
+  if( !S ) { S = new SnapDev; ctx->snap = S; }
   SnapTables T(p->twojmax);
   SnapConst& K = S->K; K = SnapConst{};
   for(int a = 1; a <= p->twojmax; a++) for(int b = 1; b <= p->twojmax; b++) K.rootpq[a][b] = std::sqrt(double(a) / b);
@@ -1082,7 +1082,7 @@ double xsb_snap_rcut_max(xsb_ctx* ctx) { SnapDev* S = ctx ? g_snap_of(ctx) : nul
 
 int xsb_snap_force(xsb_ctx* ctx, int flags)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   SnapDev* S = g_snap_of(ctx);
   XSB_REQUIRE(ctx, S && S->set, XSB_ERR_STATE, "xsb_snap_set must be called first");
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
@@ -1107,7 +1107,19 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
     default: break;
   }
   ctx->prof_end(XSB_PROF_SNAP);
-  return rc;
+  if( rc ) return rc;
+  // an atom with more than SNAP_NN_MAX in-range neighbours had the excess pairs dropped: never hand such forces back as a
+  // success (the read-back costs one stream sync per call; a SNAP call is tens of milliseconds of kernels)
+  int over = 0;
+  XSB_CUDA(ctx, cudaMemcpyAsync(&over, S->err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if( over )
+  {
+    S->overflowed = true;      // sticky until xsb_snap_overflow() is read
+    XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, sizeof(int), ctx->stream));
+    return ctx->fail(XSB_ERR_OVERFLOW, "snap_force: an atom has more than %d neighbours inside the SNAP cutoff; forces and energies of this call are incomplete", SNAP_NN_MAX);
+  }
+  return XSB_OK;
 }
 
 // development aid (not part of the ABI header): per-phase cycle sums of the snap kernel, summed over CTAs
@@ -1124,12 +1136,13 @@ extern "C" int xsbdbg_snap_clocks(xsb_ctx* ctx, int enable, unsigned long long* 
 // 1 when some atom had more than SNAP_NN_MAX in-range neighbours since the last call (forces are then incomplete)
 int xsb_snap_overflow(xsb_ctx* ctx, int* flag)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   SnapDev* S = g_snap_of(ctx);
   XSB_REQUIRE(ctx, S && S->set && flag, XSB_ERR_STATE, "xsb_snap_set must be called first");
   XSB_CUDA(ctx, cudaMemcpyAsync(flag, S->err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, sizeof(int), ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if( S->overflowed ) { *flag = 1; S->overflowed = false; }
   return XSB_OK;
 }
 

@@ -76,7 +76,7 @@ using namespace xsb;
 
 extern "C" int xsb_thermo_state(xsb_ctx* ctx, int n_types, const double* mass, double* out27)
 {
-  if( !ctx || !ctx->stream ) return XSB_ERR_STATE;
+  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, out27 != nullptr && mass != nullptr, XSB_ERR_INVALID, "null argument");
   XSB_REQUIRE(ctx, n_types >= 1 && n_types <= 16, XSB_ERR_INVALID, "n_types must be in 1..16");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -174,6 +174,7 @@ __device__ __forceinline__ void tile_produce(const TileGeom& G, const unsigned* 
       for(unsigned i = lane; i < cnt; i += 32) B.t[s0 + i] = F.type[g + i];
     }
   }
+  __syncwarp();      // the byte-copied types of all lanes are ordered before lane 0's releasing arrive
   if( lane == 0 )
   {
     R.cursor[b] = 0;

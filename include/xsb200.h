@@ -125,9 +125,26 @@ int      xsb_cell_offsets_download(xsb_ctx* ctx, uint64_t* cell_particle_offset)
 /* decks).  Follow with xsb_ghost_comm_scheme.                                                            */
 int      xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const double* ry, const double* rz,
                               const double* vx, const double* vy, const double* vz, const uint8_t* type, const uint64_t* id);
+/* Particles found outside the own cells by the last xsb_particles_assign / xsb_particles_rebin on a non-periodic (or  */
+/* brick) axis.  Less than one cell outside: clamped into the border cell and counted here (the reference's             */
+/* move_particles keeps such "otb" particles aside, ext exaNBody); further out the call fails with XSB_ERR_INVALID.      */
+int      xsb_out_of_domain_count(xsb_ctx* ctx, uint64_t* clamped);
 /* whole-array copies between host buffers and the context's device SoA (N or 9N elements)              */
 int      xsb_field_upload(xsb_ctx* ctx, int field, const void* host_src);
 int      xsb_field_download(xsb_ctx* ctx, int field, void* host_dst);
+/* Asynchronous transfers for a host application that owns the particle arrays in PINNED host memory (the plugin    */
+/* use case: positions in, forces out, every step).  Scalar double fields only (r, f, ep, v, rho_dEmb).             */
+/* own_only = 1: the host arrays hold the xsb_num_own_particles() particles of the non-ghost cells in flat order      */
+/* (ghost images are produced on the device by xsb_ghost_update); 0: all xsb_num_particles() slots.                   */
+/*  upload:   the H2D copy runs on a copy stream concurrently with the work already enqueued on the context's         */
+/*            stream (which still sees the old values); work enqueued after the call sees the new ones.               */
+/*  download: snapshots the fields at this point of the context's stream, the D2H copy runs on a second copy stream   */
+/*            concurrently with later work; host arrays are valid after xsb_copy_wait().                              */
+/* The host arrays of a call must stay untouched until the next xsb_copy_wait() / xsb_sync() resp. until a later      */
+/* upload call returns.                                                                                               */
+int      xsb_fields_upload_async(xsb_ctx* ctx, int nfields, const int* fields, const void* const* host_src, int own_only);
+int      xsb_fields_download_async(xsb_ctx* ctx, int nfields, const int* fields, void* const* host_dst, int own_only);
+int      xsb_copy_wait(xsb_ctx* ctx);
 /* device pointer of a field (zero-copy for callers that already live on the GPU, e.g. managed grids)   */
 void*    xsb_field_device_ptr(xsb_ctx* ctx, int field);
 /* zero_force_energy operator (src/compute/zero_force_energy.cu:98-135): fx,fy,fz,ep,(virial) = 0       */
@@ -204,8 +221,10 @@ int    xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p);
 double xsb_snap_rcut_max(xsb_ctx* ctx);                     /* rcut_max output slot: 2 max(radelem) rcutfac     */
 /* f_i += fij, f_j -= fij (Newton-on like the reference, forces of ghost neighbours land on the ghost copies:   */
 /* follow with xsb_ghost_reduce_add of fx,fy,fz = update_force_energy_from_ghost); flags: GHOST, ENERGY, VIRIAL */
+/* At most 64 neighbours inside the SNAP cutoff per atom (the reference has no cap; BCC/FCC metals at the shipped     */
+/* rcutfac have 14-42): beyond that the call returns XSB_ERR_OVERFLOW (it syncs the stream to find out).              */
 int    xsb_snap_force(xsb_ctx* ctx, int flags);
-int    xsb_snap_overflow(xsb_ctx* ctx, int* flag);          /* 1: an atom exceeded the in-range neighbour cap   */
+int    xsb_snap_overflow(xsb_ctx* ctx, int* flag);          /* 1: a call since the last read exceeded the cap    */
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* a10 ghost operators.  Single rank: ghosts are periodic images inside the same context.                */

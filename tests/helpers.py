@@ -134,3 +134,50 @@ def write_setfl(path, elements, nrho=2000, drho=0.1, nr=2000, rc=7.29, rmin=0.6)
 # made-up element so that multi-species paths can be exercised where /root/reference is absent.
 SC_CU = dict(name="Cu", z=29, mass=63.546, a0=3.27, c=33.17, eps=3.605e-21 / 1.6021892e-19, a=3.27, n=9.050, m=5.005)
 SC_XX = dict(name="Xx", z=13, mass=26.982, a0=3.50, c=30.00, eps=0.0200, a=3.40, n=8.5, m=5.5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter files the reference ships, committed as fixtures (tests/golden/make_potential_fixtures.py)
+# ---------------------------------------------------------------------------------------------------
+def potential_file(name):
+    """path of an uncompressed copy of tests/golden/potentials/<name>.gz (checked against SHA256SUMS)"""
+    import gzip
+    import hashlib
+    import os
+    import tempfile
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "potentials")
+    want = {l.split()[1]: l.split()[0] for l in open(os.path.join(gold, "SHA256SUMS")) if l.strip()}
+    cache = os.path.join(tempfile.gettempdir(), "xsb200_potentials_%d" % os.getuid())
+    os.makedirs(cache, exist_ok=True)
+    out = os.path.join(cache, name)
+    if not os.path.exists(out) or hashlib.sha256(open(out, "rb").read()).hexdigest() != want[name]:
+        raw = gzip.open(os.path.join(gold, name + ".gz"), "rb").read()
+        assert hashlib.sha256(raw).hexdigest() == want[name], "fixture %s does not match its recorded checksum" % name
+        tmp = out + ".%d.tmp" % os.getpid()
+        with open(tmp, "wb") as f:
+            f.write(raw)
+        os.replace(tmp, out)
+    return out
+
+
+def read_snap_files(param_path, coeff_path):
+    """LAMMPS .snapparam / .snapcoeff (reference reader: src/potential/snaplegacy/lib/snap_read_lammps.cpp:25-93; the C++
+    twin used by the deck layer is host/xsbh_readers.cpp).  Coefficients stay in eV: callers scale by EV."""
+    prm = {}
+    for line in open(param_path):
+        t = line.split("#")[0].split()
+        if len(t) >= 2:
+            prm[t[0]] = t[1]
+    tok = []
+    for line in open(coeff_path):
+        tok += line.split("#")[0].split()
+    nel, ncoef = int(tok[0]), int(tok[1])
+    k = 2
+    els = []
+    for _ in range(nel):
+        name, rad, wj = tok[k], float(tok[k + 1]), float(tok[k + 2]); k += 3
+        beta = np.array([float(v) for v in tok[k:k + ncoef]]); k += ncoef
+        els.append(dict(name=name, radius=rad, weight=wj, beta=beta))
+    return dict(twojmax=int(prm["twojmax"]), rcutfac=float(prm["rcutfac"]), rfac0=float(prm.get("rfac0", 0.99363)),
+                rmin0=float(prm.get("rmin0", 0.0)), bzeroflag=int(prm.get("bzeroflag", 1)), quadraticflag=int(prm.get("quadraticflag", 0)),
+                switchflag=int(prm.get("switchflag", 1)), elements=els, ncoeff_with_beta0=ncoef)
