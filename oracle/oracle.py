@@ -42,6 +42,7 @@ def build(force=False):
 
 _lib = None
 _ref = None
+_SIGS = []      # entry points declared by lib()
 
 
 def lib():
@@ -91,8 +92,36 @@ def lib():
         L.orc_pair_eval.argtypes = [C.c_int, _dp, C.c_double, dpp, dpp]
         L.orc_pair_ecut.restype = C.c_double
         L.orc_pair_ecut.argtypes = [C.c_int, _dp, C.c_double]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        _SIGS[:] = [n for n in dir(L) if n.startswith("orc_")]
         _lib = L
     return _lib
+
+
+def lib_timed():
+    """bench.py's CPU arm only: switch this module to a build of the same sources with -O3 -march=native (made on the
+    machine that runs the timing; falls back to the pinned -march=x86-64-v3 build when g++ is unavailable).
+    Returns (library, compiler flags)."""
+    global _lib
+    flags = "-O3 -march=x86-64-v3 -fopenmp -ffp-contract=off (pinned build; native build unavailable)"
+    base = lib()
+    import tempfile
+    d = os.path.join(tempfile.gettempdir(), "xsb200_oracle_native_%d" % os.getuid())
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, "liboracle_native.so")      # outside the tree: -march=native code must not travel to another CPU
+    try:
+        subprocess.check_call(["make", "-s", "-C", HERE, "native", "NATIVE_OUT=" + so], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        for name in _SIGS:
+            f = getattr(L, name); b = getattr(base, name)
+            f.argtypes = b.argtypes; f.restype = b.restype
+        _lib = L
+        flags = "-O3 -march=native -fopenmp"
+    except Exception:      # noqa: BLE001
+        L = base
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_num_threads.restype = C.c_int
+    return L, flags
 
 
 def ref():

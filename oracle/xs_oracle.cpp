@@ -628,6 +628,8 @@ void orc_johnson_eval(const double* params19, int what, double x, double* f, dou
 }
 
 int orc_num_threads() { return omp_get_max_threads(); }
+// bench.py's CPU arm sets the team size explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank
+void orc_set_num_threads(int n) { if( n > 0 ) omp_set_num_threads(n); }
 double orc_ev_internal() { return EV_INTERNAL; }
 
 } // extern "C"
