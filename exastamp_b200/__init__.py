@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_verlet_boundary", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
+    "xsb_verlet_boundary_async", "xsb_displ_poll",
     "xsb_fields_upload_async", "xsb_fields_download_async", "xsb_copy_wait", "xsb_out_of_domain_count",
 ]
 
@@ -151,6 +152,8 @@ def load_library():
     L.xsb_num_own_particles.argtypes = [vp]
     L.xsb_cell_offsets_download.argtypes = [vp, vp]
     L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
+    L.xsb_verlet_boundary_async.argtypes = [vp, i32, vp, dbl]
+    L.xsb_displ_poll.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.xsb_fields_upload_async.argtypes = [vp, i32, vp, vp, i32]
     L.xsb_fields_download_async.argtypes = [vp, i32, vp, vp, i32]
     L.xsb_copy_wait.argtypes = [vp]
@@ -442,6 +445,16 @@ class Context:
         r, d = C.c_int(), C.c_double()
         self._ck(self.L.xsb_verlet_boundary(self.h, m.size, _ptr(m), float(dt), float(threshold), C.byref(r), C.byref(d)), "xsb_verlet_boundary")
         return bool(r.value), d.value
+
+    def verlet_boundary_async(self, masses, dt):
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        self._ck(self.L.xsb_verlet_boundary_async(self.h, m.size, _ptr(m), float(dt)), "xsb_verlet_boundary_async")
+
+    def displ_poll(self, lag=1):
+        """(max displacement since backup_r, max displacement of that step) recorded `lag` verlet_boundary_async calls ago"""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.xsb_displ_poll(self.h, int(lag), C.byref(a), C.byref(b)), "xsb_displ_poll")
+        return a.value, b.value
 
     def thermo_state(self, masses):
         """simulation_thermodynamic_state: dict of the reference's 27 sums (own cells, all ranks)"""

@@ -172,8 +172,8 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
   B.ox = g.origin[0] + g.ghost_layers * g.cell_size; B.oy = g.origin[1] + g.ghost_layers * g.cell_size; B.oz = g.origin[2] + g.ghost_layers * g.cell_size;
   B.nx = g.dims[0]; B.ny = g.dims[1]; B.nz = g.dims[2];
   for(int a = 0; a < 3; a++) { B.wrap[a] = wrap ? wrap[a] : 0; B.box[a] = box ? box[a] : 0.0; }
-  XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, 1.02));
-  XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32d.reserve(std::max(n, nc) + 16, 1.02));
+  XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, XSB_GROW));
+  XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32d.reserve(std::max(n, nc) + 16, XSB_GROW));
   unsigned *key = ctx->tmp32a.p, *val = ctx->tmp32b.p, *key2 = ctx->tmp32c.p, *perm = ctx->tmp32d.p;
   XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(nc) + 4));
   unsigned* counts = reinterpret_cast<unsigned*>(ctx->scratch64.p);
@@ -204,11 +204,11 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
   {
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), XSB_GROW));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (size_t(n) + 1) * sizeof(double), ctx->stream));
   }
-  XSB_CUDA(ctx, ctx->type.reserve(size_t(n) + 16, 1.02)); XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, size_t(n) + 16, ctx->stream));
-  XSB_CUDA(ctx, ctx->id.reserve(size_t(n) + 1, 1.02));
+  XSB_CUDA(ctx, ctx->type.reserve(size_t(n) + 16, XSB_GROW)); XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, size_t(n) + 16, ctx->stream));
+  XSB_CUDA(ctx, ctx->id.reserve(size_t(n) + 1, XSB_GROW));
   if( n )
   {
     const double* src[6] = { rx, ry, rz, vx, vy, vz }; const int dstf[6] = { XSB_F_RX, XSB_F_RY, XSB_F_RZ, XSB_F_VX, XSB_F_VY, XSB_F_VZ };
@@ -231,8 +231,8 @@ int xsb_particles_assign(xsb_ctx* ctx, uint64_t n, const double* rx, const doubl
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   // stage host arrays on the device (8-byte words: 6 real fields + id, then type bytes)
   DevBuf<double>& st = ctx->move_stage; DevBuf<unsigned char>& stt = ctx->move_stage8;
-  cudaError_t e = st.reserve(7 * (n + 1), 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
-  e = stt.reserve(n + 16, 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
+  cudaError_t e = st.reserve(7 * (n + 1), XSB_GROW); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
+  e = stt.reserve(n + 16, XSB_GROW); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "assign staging: %s", cudaGetErrorString(e));
   const double* hsrc[6] = { rx, ry, rz, vx, vy, vz }; double* d[7];
   for(int k = 0; k < 7; k++) d[k] = st.p + size_t(k) * (n + 1);
   int rc = XSB_OK;
@@ -261,8 +261,8 @@ int xsb_particles_rebin(xsb_ctx* ctx, const xsb_domain_desc* dom)
   const unsigned n = unsigned(ctx->n_own);
   // staging buffers persist in the context: steady-state rebuilds must not touch cudaMalloc/cudaFree
   DevBuf<double>& st = ctx->move_stage; DevBuf<unsigned char>& stt = ctx->move_stage8;
-  cudaError_t e = st.reserve(7 * (size_t(n) + 1), 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
-  e = stt.reserve(size_t(n) + 16, 1.02); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
+  cudaError_t e = st.reserve(7 * (size_t(n) + 1), XSB_GROW); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
+  e = stt.reserve(size_t(n) + 16, XSB_GROW); if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "rebin staging: %s", cudaGetErrorString(e));
   double* d[7]; for(int k = 0; k < 7; k++) d[k] = st.p + size_t(k) * (n + 1);
   const int srcf[6] = { XSB_F_RX, XSB_F_RY, XSB_F_RZ, XSB_F_VX, XSB_F_VY, XSB_F_VZ };
   const unsigned grid = (n + 255) / 256;
@@ -324,7 +324,7 @@ __global__ void verlet_boundary_kernel(unsigned n, const unsigned* __restrict__ 
                                        unsigned long long* __restrict__ out)
 {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  double d2 = 0.0;
+  double d2 = 0.0, s2 = 0.0;
   if( t < n )
   {
     const unsigned a = atoms[t];
@@ -334,6 +334,7 @@ __global__ void verlet_boundary_kernel(unsigned n, const unsigned* __restrict__ 
     double ux = vx[a], uy = vy[a], uz = vz[a];
     ux += ax * dth; uy += ay * dth; uz += az * dth;                                    // push_f_v: second half kick of the step
     double dx = ux * dt + ax * dt2h, dy = uy * dt + ay * dt2h, dz = uz * dt + az * dt2h;   // push_f_v_r of the next step
+    s2 = dx*dx + dy*dy + dz*dz;                                                            // how far this step moves the atom
     if( !Xi.identity )
     {
       const double x = Xi.m[0]*dx + Xi.m[1]*dy + Xi.m[2]*dz, y = Xi.m[3]*dx + Xi.m[4]*dy + Xi.m[5]*dz, z = Xi.m[6]*dx + Xi.m[7]*dy + Xi.m[8]*dz;
@@ -351,15 +352,16 @@ __global__ void verlet_boundary_kernel(unsigned n, const unsigned* __restrict__ 
     }
     d2 = ex*ex + ey*ey + ez*ez;
   }
-  for(int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-  __shared__ double s[8];
-  if( (threadIdx.x & 31) == 0 ) s[threadIdx.x >> 5] = d2;
+  for(int o = 16; o > 0; o >>= 1) { d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o)); s2 = fmax(s2, __shfl_xor_sync(0xffffffffu, s2, o)); }
+  __shared__ double s[8], ss[8];
+  if( (threadIdx.x & 31) == 0 ) { s[threadIdx.x >> 5] = d2; ss[threadIdx.x >> 5] = s2; }
   __syncthreads();
   if( threadIdx.x == 0 )
   {
-    double m = s[0];
-    for(unsigned w = 1; w < (blockDim.x >> 5); w++) m = fmax(m, s[w]);
+    double m = s[0], ms = ss[0];
+    for(unsigned w = 1; w < (blockDim.x >> 5); w++) { m = fmax(m, s[w]); ms = fmax(ms, ss[w]); }
     if( m > 0.0 ) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    if( ms > 0.0 ) atomicMax(out + 1, (unsigned long long)__double_as_longlong(ms));
   }
 }
 }
@@ -401,15 +403,15 @@ int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass)
   return XSB_OK;
 }
 
-int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt, double threshold, int* result, double* max_displ)
+} // extern "C"
+
+// the fused pass; out[0] = max |r - r_backup|^2, out[1] = max |step displacement|^2 (both zeroed here)
+static int verlet_boundary_launch(xsb_ctx* ctx, int n_types, const double* mass, double dt, unsigned long long* out)
 {
-  XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, mass != nullptr && n_types >= 1 && n_types <= 16, XSB_ERR_INVALID, "1..16 species masses expected");
-  XSB_REQUIRE(ctx, result != nullptr, XSB_ERR_INVALID, "null result");
   const unsigned n = unsigned(ctx->n_own);
   XSB_REQUIRE(ctx, ctx->backup_n == n, XSB_ERR_STATE, "xsb_backup_r must be called after the last rebuild");
-  XSB_CUDA(ctx, ctx->scratch64.reserve(16));
-  XSB_CUDA(ctx, cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(unsigned long long), ctx->stream));
+  XSB_CUDA(ctx, cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), ctx->stream));
   ctx->pos_epoch++;
   if( n )
   {
@@ -419,9 +421,57 @@ int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt
     const double* b = ctx->backup.p;
     verlet_boundary_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->own_atoms.p, M, ctx->type.p, dt, 0.5 * dt, 0.5 * dt * dt, Xi, Xf,
         ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->f64[XSB_F_VX].p, ctx->f64[XSB_F_VY].p, ctx->f64[XSB_F_VZ].p,
-        ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, b, b + n, b + 2 * size_t(n), ctx->scratch64.p);
+        ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, b, b + n, b + 2 * size_t(n), out);
     XSB_LAUNCH_CHECK(ctx);
   }
+  return XSB_OK;
+}
+
+int xsb_internal_allreduce_max(xsb_ctx* ctx, double* dev_inout, int count);      // xsb_ghost.cu
+
+extern "C" {
+
+// Same pass without a host read-back: the two maxima are all-reduced (MAX) over the ranks on the stream and land in a ring
+// of pinned host slots; xsb_displ_poll(lag) returns the pair recorded `lag` calls earlier, so a driver that decides on the
+// previous step's value (plus the step displacement as a margin) never waits for the GPU and never couples the ranks'
+// host threads through a blocking collective.
+int xsb_verlet_boundary_async(xsb_ctx* ctx, int n_types, const double* mass, double dt)
+{
+  XSB_ENTER(ctx);
+  if( !ctx->displ_host )
+  {
+    XSB_CUDA(ctx, cudaMallocHost((void**)&ctx->displ_host, sizeof(double) * 2 * XSB_DISPL_RING));
+    XSB_CUDA(ctx, ctx->displ_dev.reserve(2 * XSB_DISPL_RING));
+    for(int i = 0; i < XSB_DISPL_RING; i++) XSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->displ_ev[i], cudaEventDisableTiming));
+  }
+  const int slot = int(ctx->displ_seq % XSB_DISPL_RING);
+  unsigned long long* out = ctx->displ_dev.p + 2 * slot;
+  int rc = verlet_boundary_launch(ctx, n_types, mass, dt, out); if( rc ) return rc;
+  rc = xsb_internal_allreduce_max(ctx, reinterpret_cast<double*>(out), 2); if( rc ) return rc;      // squares are non-negative: MAX on the doubles
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->displ_host + 2 * slot, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaEventRecord(ctx->displ_ev[slot], ctx->stream));
+  ctx->displ_seq++;
+  return XSB_OK;
+}
+
+int xsb_displ_poll(xsb_ctx* ctx, int lag, double* max_displ, double* max_step_displ)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, lag >= 0 && lag < XSB_DISPL_RING - 1, XSB_ERR_INVALID, "lag must be in 0..6");
+  XSB_REQUIRE(ctx, ctx->displ_seq > uint64_t(lag), XSB_ERR_STATE, "xsb_displ_poll: no xsb_verlet_boundary_async call that far back");
+  const int slot = int((ctx->displ_seq - 1 - uint64_t(lag)) % XSB_DISPL_RING);
+  XSB_CUDA(ctx, cudaEventSynchronize(ctx->displ_ev[slot]));
+  if( max_displ ) *max_displ = std::sqrt(ctx->displ_host[2 * slot]);
+  if( max_step_displ ) *max_step_displ = std::sqrt(ctx->displ_host[2 * slot + 1]);
+  return XSB_OK;
+}
+
+int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt, double threshold, int* result, double* max_displ)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, result != nullptr, XSB_ERR_INVALID, "null result");
+  XSB_CUDA(ctx, ctx->scratch64.reserve(16));
+  int rcl = verlet_boundary_launch(ctx, n_types, mass, dt, ctx->scratch64.p); if( rcl ) return rcl;
   double d2 = 0.0;
   XSB_CUDA(ctx, cudaMemcpyAsync(&d2, ctx->scratch64.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -436,7 +486,7 @@ int xsb_backup_r(xsb_ctx* ctx)
 {
   XSB_ENTER(ctx);
   const unsigned n = unsigned(ctx->n_own);
-  XSB_CUDA(ctx, ctx->backup.reserve(3 * (size_t(n) + 1), 1.02));
+  XSB_CUDA(ctx, ctx->backup.reserve(3 * (size_t(n) + 1), XSB_GROW));
   ctx->backup_n = n;
   if( !n ) return XSB_OK;
   double* b = ctx->backup.p;

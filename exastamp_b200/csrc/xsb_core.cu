@@ -96,7 +96,7 @@ static int xfer_fields(xsb_ctx* ctx, int nfields, const int* fields, xsb::XferFi
 int xsb_internal_ensure_virial(xsb_ctx* ctx)
 {
   if( ctx->virial_allocated && ctx->f64[XSB_F_VIRIAL].cap >= 9 * (ctx->n + 1) ) return XSB_OK;
-  XSB_CUDA(ctx, ctx->f64[XSB_F_VIRIAL].reserve(9 * (ctx->n + 1), 1.02));
+  XSB_CUDA(ctx, ctx->f64[XSB_F_VIRIAL].reserve(9 * (ctx->n + 1), XSB_GROW));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[XSB_F_VIRIAL].p, 0, 9 * (ctx->n + 1) * sizeof(double), ctx->stream));
   ctx->virial_allocated = true;
   return XSB_OK;
@@ -140,8 +140,8 @@ int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
   ctx->backup_n = 0xffffffffu;      // the own particles were re-ordered: a backup_r of the old order compares different atoms
   ctx->ghost_valid = false;         // exchange lists index the old layout (xsb_ghost_comm_scheme sets it again)
   XSB_CUDA(ctx, ctx->cell_start.reserve(2 * (nc + 1)));
-  XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, 1.02));
-  XSB_CUDA(ctx, ctx->own_atoms.reserve(nown + 1, 1.02));
+  XSB_CUDA(ctx, ctx->cell_of.reserve(n + 1, XSB_GROW));
+  XSB_CUDA(ctx, ctx->own_atoms.reserve(nown + 1, XSB_GROW));
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->cell_start.p, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
   if( n )
   {
@@ -182,14 +182,14 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
   int rc = xsb_internal_install_cells(ctx, new_off); if( rc ) return rc;
   const unsigned n = unsigned(ctx->n);
   const unsigned grid = (n + 255) / 256;
-  XSB_CUDA(ctx, ctx->tmp64.reserve(size_t(n) + 16, 1.02));
+  XSB_CUDA(ctx, ctx->tmp64.reserve(size_t(n) + 16, XSB_GROW));
   const int moved[6] = { XSB_F_RX, XSB_F_RY, XSB_F_RZ, XSB_F_VX, XSB_F_VY, XSB_F_VZ };
   for(int k = 0; k < 6 && n; k++)
   {
     DevBuf<double>& b = ctx->f64[moved[k]];
     relayout_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p, b.p, reinterpret_cast<double*>(ctx->tmp64.p));
     XSB_LAUNCH_CHECK(ctx);
-    XSB_CUDA(ctx, b.reserve_keep(n + 16, 1.02, ctx->stream));      // stage rows are read up to the next 16-atom boundary
+    XSB_CUDA(ctx, b.reserve_keep(n + 16, XSB_GROW, ctx->stream));      // stage rows are read up to the next 16-atom boundary
     XSB_CUDA(ctx, cudaMemcpyAsync(b.p, ctx->tmp64.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   if( n )
@@ -197,12 +197,12 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
     relayout_kernel<unsigned long long><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p,
                                                                        reinterpret_cast<const unsigned long long*>(ctx->id.p), ctx->tmp64.p);
     XSB_LAUNCH_CHECK(ctx);
-    XSB_CUDA(ctx, ctx->id.reserve_keep(n + 1, 1.02, ctx->stream));
+    XSB_CUDA(ctx, ctx->id.reserve_keep(n + 1, XSB_GROW, ctx->stream));
     XSB_CUDA(ctx, cudaMemcpyAsync(ctx->id.p, ctx->tmp64.p, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     relayout_kernel<unsigned char><<<grid, 256, 0, ctx->stream>>>(n, gv, ctx->cell_of.p, ctx->cell_start.p, ctx->old_cell_start.p, ctx->type.p,
                                                                   reinterpret_cast<unsigned char*>(ctx->tmp64.p));
     XSB_LAUNCH_CHECK(ctx);
-    XSB_CUDA(ctx, ctx->type.reserve_keep(n + 16, 1.02, ctx->stream));
+    XSB_CUDA(ctx, ctx->type.reserve_keep(n + 16, XSB_GROW, ctx->stream));
     XSB_CUDA(ctx, cudaMemcpyAsync(ctx->type.p, ctx->tmp64.p, size_t(n), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   const int zeroed[6] = { XSB_F_FX, XSB_F_FY, XSB_F_FZ, XSB_F_EP, XSB_F_RHO_DEMB, XSB_F_VIRIAL };
@@ -211,7 +211,7 @@ int xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_off)
     const int f = zeroed[k];
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (size_t(n) + 16), XSB_GROW));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (size_t(n) + 1) * sizeof(double), ctx->stream));
   }
   return XSB_OK;
@@ -286,7 +286,8 @@ void xsb_destroy(xsb_ctx* ctx)
   ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->eam.fc32.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   xsb_snap_release(ctx);
-  ctx->stage_up.release(); ctx->stage_down.release();
+  ctx->stage_up.release(); ctx->stage_down.release(); ctx->displ_dev.release();
+  if( ctx->displ_host ) { cudaFreeHost(ctx->displ_host); for(cudaEvent_t e : ctx->displ_ev) if( e ) cudaEventDestroy(e); }
   if( ctx->copy_up ) { cudaStreamSynchronize(ctx->copy_up); cudaStreamDestroy(ctx->copy_up); }
   if( ctx->copy_down ) { cudaStreamSynchronize(ctx->copy_down); cudaStreamDestroy(ctx->copy_down); }
   for(cudaEvent_t e : { ctx->ev_up_done, ctx->ev_up_free, ctx->ev_down_ready, ctx->ev_down_done }) if( e ) cudaEventDestroy(e);
@@ -437,12 +438,12 @@ int xsb_particles_set_cells(xsb_ctx* ctx, const uint64_t* off)
   {
     if( f == XSB_F_VIRIAL && !ctx->virial_allocated ) continue;   // allocated on first use
     const size_t w = f == XSB_F_VIRIAL ? 9 : 1;
-    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (n + 16), 1.02));
+    XSB_CUDA(ctx, ctx->f64[f].reserve(w * (n + 16), XSB_GROW));
     XSB_CUDA(ctx, cudaMemsetAsync(ctx->f64[f].p, 0, w * (n + 1) * sizeof(double), ctx->stream));
   }
-  XSB_CUDA(ctx, ctx->type.reserve(n + 16, 1.02));
+  XSB_CUDA(ctx, ctx->type.reserve(n + 16, XSB_GROW));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->type.p, 0, n + 16, ctx->stream));
-  XSB_CUDA(ctx, ctx->id.reserve(n + 1, 1.02));
+  XSB_CUDA(ctx, ctx->id.reserve(n + 1, XSB_GROW));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->id.p, 0, (n + 1) * sizeof(uint64_t), ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return XSB_OK;

@@ -13,6 +13,13 @@ struct ncclComm;
 namespace xsb
 {
 
+// Head-room of the per-particle / per-ghost device arrays on (re)allocation.  Particle and ghost counts of a brick drift by
+// a fraction of a percent between rebuilds (migration, density fluctuations): with too little slack a rebuild in the middle
+// of a run hits cudaFree + cudaMalloc, which synchronises the device and costs milliseconds on ONE rank -- exactly the kind
+// of straggler a 20-step timing window cannot absorb.  A B200 has 180 GB; the bench's working set is ~10 GB.
+constexpr double XSB_GROW = 1.10, XSB_GROW_GHOST = 1.25;
+constexpr int XSB_DISPL_RING = 8;
+
 // RAII-less device buffer: grows geometrically, never shrinks until the context dies (steady-state MD loops
 // must not touch cudaMalloc).
 template<class T> struct DevBuf
@@ -150,6 +157,12 @@ struct xsb_ctx
   uint64_t migrated_out = 0, migrated_in = 0;   // particles that changed rank in the last xsb_particles_rebin
   uint64_t otb_clamped = 0;                     // particles the last binning clamped into a border cell (xsb_out_of_domain_count)
   xsb::DevBuf<double> backup; unsigned backup_n = 0xffffffffu;        // backup_r positions of own particles
+
+  // xsb_verlet_boundary_async / xsb_displ_poll: ring of {max displacement^2, max step displacement^2} results
+  double* displ_host = nullptr;               // pinned, [XSB_DISPL_RING][2]
+  xsb::DevBuf<unsigned long long> displ_dev;
+  cudaEvent_t displ_ev[8] = {};
+  uint64_t displ_seq = 0;
 
   // asynchronous host <-> device field transfers (xsb_fields_upload_async / _download_async, xsb_core.cu): one copy stream
   // per direction so H2D and D2H use both DMA engines while the compute stream runs the passes

@@ -248,8 +248,8 @@ static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
   const unsigned n_out = reverse ? G->n_recv : G->n_send, n_in = reverse ? G->n_send : G->n_recv;
   const std::vector<unsigned>& out_off = reverse ? G->recv_off : G->send_off;
   const std::vector<unsigned>& in_off = reverse ? G->send_off : G->recv_off;
-  XSB_CUDA(ctx, G->send_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, 1.1));
-  XSB_CUDA(ctx, G->recv_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, 1.1));
+  XSB_CUDA(ctx, G->send_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, XSB_GROW_GHOST));
+  XSB_CUDA(ctx, G->recv_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, XSB_GROW_GHOST));
   const unsigned* d_out_seg = reverse ? ctx->gseg_recv.p : ctx->gseg_send.p;   // seg_of arrays (built with the scheme)
   const unsigned* d_in_seg = reverse ? ctx->gseg_send.p : ctx->gseg_recv.p;
   const unsigned* d_out_off = reverse ? ctx->goff_recv.p : ctx->goff_send.p;
@@ -419,8 +419,8 @@ int xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, d
     M.box[a] = dom->global_cells[a] * g.cell_size; M.periodic[a] = dom->periodic[a]; M.gcells[a] = dom->global_cells[a]; M.rdims[a] = dom->rank_dims[a];
   }
   M.cell = g.cell_size;
-  XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, 1.02));
-  XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, 1.02)); XSB_CUDA(ctx, ctx->tmp32d.reserve(n + 16, 1.02));
+  XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, XSB_GROW));
+  XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32d.reserve(n + 16, XSB_GROW));
   unsigned *key = ctx->tmp32a.p, *val = ctx->tmp32b.p, *key2 = ctx->tmp32c.p, *perm = ctx->tmp32d.p;
   XSB_CUDA(ctx, ctx->scratch64.reserve(size_t(P) * (P + 1) + 16));
   unsigned long long* counts = ctx->scratch64.p;            // [P] mine, then [P][P] gathered
@@ -451,7 +451,7 @@ int xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, d
   // their segment; leavers travel as 64-byte records, one grouped send/recv per peer (not one per field).
   const size_t stay = soff[me + 1] - soff[me], nl = n - stay, nin = nn - stay;
   XSB_CUDA(ctx, ctx->move_stage_b.reserve(8 * std::max<size_t>(nl + nin, size_t(n) / 16 + 4096) + 16, 2.0));      // record buffers: sized once, well above the usual traffic (a re-allocation synchronises the device)
-  XSB_CUDA(ctx, ctx->move_stage_c.reserve(7 * (nn + 1), 1.05)); XSB_CUDA(ctx, ctx->move_stage8_c.reserve(nn + 16, 1.05));
+  XSB_CUDA(ctx, ctx->move_stage_c.reserve(7 * (nn + 1), XSB_GROW_GHOST)); XSB_CUDA(ctx, ctx->move_stage8_c.reserve(nn + 16, XSB_GROW_GHOST));
   for(int k = 0; k < 7; k++) e[k] = ctx->move_stage_c.p + size_t(k) * (nn + 1);
   unsigned char* et8 = ctx->move_stage8_c.p;
   unsigned long long* srec = reinterpret_cast<unsigned long long*>(ctx->move_stage_b.p);
@@ -482,6 +482,14 @@ int xsb_internal_allreduce_sum(xsb_ctx* ctx, double* dev_inout, int count)
   if( ctx->nranks == 1 ) return XSB_OK;
   XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "xsb_comm_init must be called first");
   XSB_NCCL(ctx, g_nccl.AllReduce(dev_inout, dev_inout, size_t(count), NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream));
+  return XSB_OK;
+}
+
+int xsb_internal_allreduce_max(xsb_ctx* ctx, double* dev_inout, int count)
+{
+  if( ctx->nranks == 1 ) return XSB_OK;
+  XSB_REQUIRE(ctx, ctx->comm != nullptr, XSB_ERR_STATE, "xsb_comm_init must be called first");
+  XSB_NCCL(ctx, g_nccl.AllReduce(dev_inout, dev_inout, size_t(count), NCCL_FLOAT64, NCCL_MAX, ctx->comm, ctx->stream));
   return XSB_OK;
 }
 
@@ -613,9 +621,9 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
   }
   G->n_send = ns; G->n_recv = nr;
   XSB_REQUIRE(ctx, G->send_off[me + 1] - G->send_off[me] == G->recv_off[me + 1] - G->recv_off[me], XSB_ERR_STATE, "ghost scheme: self segment mismatch");
-  XSB_CUDA(ctx, G->send_idx.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, G->send_code.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, G->recv_idx.reserve(size_t(nr) + 16, 1.05));
-  XSB_CUDA(ctx, ctx->gseg_send.reserve(size_t(ns) + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_send.reserve(P + 2));
-  XSB_CUDA(ctx, ctx->gseg_recv.reserve(size_t(nr) + 16, 1.05)); XSB_CUDA(ctx, ctx->goff_recv.reserve(P + 2));
+  XSB_CUDA(ctx, G->send_idx.reserve(size_t(ns) + 16, XSB_GROW_GHOST)); XSB_CUDA(ctx, G->send_code.reserve(size_t(ns) + 16, XSB_GROW_GHOST)); XSB_CUDA(ctx, G->recv_idx.reserve(size_t(nr) + 16, XSB_GROW_GHOST));
+  XSB_CUDA(ctx, ctx->gseg_send.reserve(size_t(ns) + 16, XSB_GROW_GHOST)); XSB_CUDA(ctx, ctx->goff_send.reserve(P + 2));
+  XSB_CUDA(ctx, ctx->gseg_recv.reserve(size_t(nr) + 16, XSB_GROW_GHOST)); XSB_CUDA(ctx, ctx->goff_recv.reserve(P + 2));
   {
     // per-cell entries travel (a few thousand), the per-particle lists are expanded on the device
     const size_t words = (es.size() + er.size()) * (sizeof(RangeEntry) / 8) + 2;

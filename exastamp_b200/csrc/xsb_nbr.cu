@@ -562,9 +562,9 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   const unsigned n = unsigned(ctx->n);
   ctx->nbh_built = false; ctx->nbh_total = 0; ctx->nbh_max = 0; ctx->nbh_dist = nbh_dist_lab;
   ctx->sub_epoch = 0; ctx->sub_pw_kind = 0;      // a sub-list left by an earlier pass indexes the previous list
-  XSB_CUDA(ctx, ctx->nbh_count.reserve(n + 1, 1.02));
-  XSB_CUDA(ctx, ctx->nbh_off.reserve(n + 2, 1.02));
-  XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, 1.02));
+  XSB_CUDA(ctx, ctx->nbh_count.reserve(n + 1, XSB_GROW));
+  XSB_CUDA(ctx, ctx->nbh_off.reserve(n + 2, XSB_GROW));
+  XSB_CUDA(ctx, ctx->scratch64.reserve(n + 2, XSB_GROW));
   XSB_CUDA(ctx, cudaMemsetAsync(ctx->nbh_off.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   if( n == 0 ) { ctx->nbh_built = true; return XSB_OK; }
   XSB_CUDA(ctx, ctx->tmp64.reserve(16));
@@ -621,7 +621,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     }
     // survivor masks of the count sweep (one word per 32-candidate step), replayed by nbr_expand_kernel
     mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
-    XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, 1.02));
+    XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, XSB_GROW));
     const int cblock = 256;      // 512-thread CTAs for large stages measured slower (C2: 6.96 -> 8.99 ms per rebuild)
     if( P.g.xform_identity ) nbr_count_kernel<false><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, F32, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);
     else                     nbr_count_kernel<true ><<<TG.ntiles, cblock, tile_smem, ctx->stream>>>(TG, P.g, P.d2max, F32, ctx->cell_start.p, rx, ry, rz, ctx->nbh_count.p, ctx->nbh_masks.p, mask_stride, d2min);

@@ -276,6 +276,13 @@ int xsb_particle_displ_over(xsb_ctx* ctx, double threshold, int* result, double*
 /* particle_displ_over(threshold).  Same per-atom arithmetic as the five separate calls.                        */
 int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt, double threshold, int* result, double* max_displ);
 
+/* The same pass without the host read-back of xsb_verlet_boundary: max |r - r_backup| and the largest displacement of     */
+/* this step are all-reduced over the ranks on the stream into a ring of 8 pinned slots.  xsb_displ_poll(lag) returns the   */
+/* pair recorded `lag` calls earlier (0 = the call just made, which waits for it).  A driver that rebuilds when             */
+/* max_displ(lag 1) + 2 * max_step_displ(lag 1) > threshold keeps every list valid without ever stalling on the GPU.        */
+int xsb_verlet_boundary_async(xsb_ctx* ctx, int n_types, const double* mass, double dt);
+int xsb_displ_poll(xsb_ctx* ctx, int lag, double* max_displ, double* max_step_displ);
+
 /* simulation_thermodynamic_state (src/thermo_state/simulation_thermodynamic_state.cpp:81-230): sums over
  * the particles of own cells, all-reduced over ranks, in the reference's 27-double layout: virial[9] (zeros when no
  * operator produced it), ke_tensor[9] = 1/2 sum m v(x)v, momentum[3] = sum m v, kinetic_energy[3] = 1/2 sum m v_a^2,

@@ -799,6 +799,46 @@ def test_verlet_boundary_equals_the_five_separate_operators(triclinic):
         assert np.abs(u - v).max() <= 4e-16 * max(np.abs(u).max(), 1e-300)
 
 
+def test_verlet_boundary_async_ring_and_own_atom_transfers():
+    """xsb_verlet_boundary_async + xsb_displ_poll (no host read-back) give the blocking variant's maxima, one call late on
+    request; xsb_fields_upload_async / _download_async move the own atoms only and keep stream order"""
+    pos, typ, box = lattice("FCC", 6, 5.0, 0.1, seed=3)
+    vel = np.random.default_rng(5).normal(0.0, 2.0, pos.shape)
+    masses, dt = [39.948], 2.0e-3
+    a = assigned_ctx(pos, typ, box, 10.0, 1, vel); b = assigned_ctx(pos, typ, box, 10.0, 1, vel)
+    for c in (a, b):
+        c.backup_r()
+    hist = []
+    for step in range(3):
+        over, d = a.verlet_boundary(masses, dt, 1.0)
+        b.verlet_boundary_async(masses, dt)
+        d0, s0 = b.displ_poll(0)
+        assert abs(d0 - d) <= 1e-15 * d and 0 < s0 <= d0 * (1 + 1e-12)
+        hist.append((d0, s0))
+        if step:
+            assert b.displ_poll(1) == hist[-2]
+    for f in (xsb.F_RX, xsb.F_VZ):
+        assert np.array_equal(a.download(f), b.download(f))
+    with pytest.raises(xsb.XsbError):
+        b.displ_poll(5)                     # nothing recorded that far back
+    # own-atom transfers: download -> modify -> upload -> whole-array download shows the change on own atoms only
+    import torch
+    n_own, n = b.n_own, b.n
+    pin = [torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in range(2)]
+    before = b.download(xsb.F_RX)
+    b.fields_download_async([xsb.F_RX, xsb.F_RY], [t.data_ptr() for t in pin]); b.copy_wait()
+    off = b.cell_offsets(); dims = np.array(b.grid.dims[:])
+    cells = np.arange(len(off) - 1); ci = cells % dims[0]; cj = (cells // dims[0]) % dims[1]; ck = cells // (dims[0] * dims[1])
+    own_cell = (ci >= 1) & (ci < dims[0] - 1) & (cj >= 1) & (cj < dims[1] - 1) & (ck >= 1) & (ck < dims[2] - 1)
+    own = np.repeat(own_cell, np.diff(off).astype(np.int64))
+    assert own.sum() == n_own and np.array_equal(pin[0].numpy(), before[own])
+    pin[0] += 0.125
+    b.fields_upload_async([xsb.F_RX], [pin[0].data_ptr()])
+    after = b.download(xsb.F_RX)
+    assert np.array_equal(after[own], before[own] + 0.125) and np.array_equal(after[~own], before[~own])
+    b.copy_wait()
+
+
 @pytest.mark.parametrize("two_species,virial", [(False, False), (True, True)])
 def test_eam_alloy_mixed_precision_parity(tmp_path, two_species, virial):
     """XSB_FLAG_MIXED on eam_alloy_force: FP32 spline + pair math (FP64 distances and accumulation) against the FP64 oracle
