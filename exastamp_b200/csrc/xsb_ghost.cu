@@ -127,18 +127,20 @@ static void ghost_list(const xsb_domain_desc& d, int gl, const int rc[3], std::v
 static inline int shift_code(const int w[3]) { auto c = [](int v) { return v < 0 ? 0 : (v > 0 ? 2 : 1); }; return c(w[0]) + 3 * c(w[1]) + 9 * c(w[2]); }
 
 // ---- kernels -----------------------------------------------------------------------------------------------
-struct FieldPtrs { const void* src[8]; void* dst[8]; int kind[8]; int nf; };   // kind: 0 double, 1..3 position axis (adds shift), 4 u64, 5 u8
+// kind: 0 double, 1..3 position axis (adds shift), 4 u64, 5 u8, 16+k component k of the 9-double per-atom virial (AoS Mat3d)
+struct FieldPtrs { const void* src[16]; void* dst[16]; int kind[16]; int nf; };
 struct ShiftTab { double s[27][3]; };
 
+__device__ __forceinline__ size_t word_index(int kind, unsigned i) { return kind >= 16 ? 9ull * i + unsigned(kind - 16) : size_t(i); }
 __device__ __forceinline__ unsigned long long load_word(const void* base, int kind, unsigned i)
 {
   if( kind == 5 ) return (unsigned long long)static_cast<const unsigned char*>(base)[i];
-  return static_cast<const unsigned long long*>(base)[i];
+  return static_cast<const unsigned long long*>(base)[word_index(kind, i)];
 }
 __device__ __forceinline__ void store_word(void* base, int kind, unsigned i, unsigned long long v)
 {
   if( kind == 5 ) static_cast<unsigned char*>(base)[i] = (unsigned char)v;
-  else static_cast<unsigned long long*>(base)[i] = v;
+  else static_cast<unsigned long long*>(base)[word_index(kind, i)] = v;
 }
 
 // owner -> wire : buf[peer segment][field][k] ; shift added to positions on the sender side
@@ -170,7 +172,7 @@ __global__ void ghost_unpack_kernel(unsigned n, FieldPtrs F, const unsigned* __r
   for(int f = 0; f < F.nf; f++)
   {
     const unsigned long long w = seg[size_t(f) * len + (k - s0)];
-    if( add ) atomicAdd(static_cast<double*>(F.dst[f]) + dst, __longlong_as_double((long long)w));
+    if( add ) atomicAdd(static_cast<double*>(F.dst[f]) + word_index(F.kind[f], dst), __longlong_as_double((long long)w));
     else store_word(F.dst[f], F.kind[f], dst, w);
   }
 }
@@ -184,7 +186,7 @@ __global__ void ghost_self_kernel(unsigned n, FieldPtrs F, ShiftTab S, const uns
   const unsigned o = send_idx[k], g = recv_idx[k];
   for(int f = 0; f < F.nf; f++)
   {
-    if( reverse_add ) { atomicAdd(static_cast<double*>(F.dst[f]) + o, static_cast<const double*>(F.src[f])[g]); continue; }
+    if( reverse_add ) { atomicAdd(static_cast<double*>(F.dst[f]) + word_index(F.kind[f], o), static_cast<const double*>(F.src[f])[word_index(F.kind[f], g)]); continue; }
     unsigned long long w = load_word(F.src[f], F.kind[f], o);
     if( F.kind[f] >= 1 && F.kind[f] <= 3 ) w = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)w) + S.s[code[k]][F.kind[f] - 1]);
     store_word(F.dst[f], F.kind[f], g, w);
@@ -213,8 +215,15 @@ static int make_fields(xsb_ctx* ctx, uint32_t mask, bool reverse, FieldPtrs& F)
   for(int f = 0; f < XSB_F_COUNT_; f++)
   {
     if( !(mask & (1u << f)) ) continue;
-    XSB_REQUIRE(ctx, F.nf < 8, XSB_ERR_INVALID, "at most 8 fields per ghost exchange");
-    XSB_REQUIRE(ctx, f != XSB_F_VIRIAL, XSB_ERR_UNSUPPORTED, "virial ghost exchange not supported");
+    if( f == XSB_F_VIRIAL )
+    {
+      // update_virial_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:43): the 9 components travel as 9 words per atom
+      XSB_REQUIRE(ctx, F.nf + 9 <= 16, XSB_ERR_INVALID, "at most 16 words per atom per ghost exchange");
+      int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc;
+      for(int k = 0; k < 9; k++) { F.src[F.nf] = ctx->f64[f].p; F.dst[F.nf] = ctx->f64[f].p; F.kind[F.nf] = 16 + k; ++F.nf; }
+      continue;
+    }
+    XSB_REQUIRE(ctx, F.nf < 16, XSB_ERR_INVALID, "at most 16 words per atom per ghost exchange");
     void* p; int kind = 0;
     if( f == XSB_F_TYPE ) { p = ctx->type.p; kind = 5; }
     else if( f == XSB_F_ID ) { p = ctx->id.p; kind = 4; }

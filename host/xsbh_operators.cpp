@@ -508,6 +508,10 @@ public:
 static OperatorRegistrar reg_ufg("update_force_energy_from_ghost", []() {
   return std::unique_ptr<Operator>(new UpdateFromGhosts((1u << XSB_F_FX) | (1u << XSB_F_FY) | (1u << XSB_F_FZ) | (1u << XSB_F_EP)));
 });
+// update_virial_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:43): + the 9 virial components
+static OperatorRegistrar reg_uvfg("update_virial_force_energy_from_ghost", []() {
+  return std::unique_ptr<Operator>(new UpdateFromGhosts((1u << XSB_F_FX) | (1u << XSB_F_FY) | (1u << XSB_F_FZ) | (1u << XSB_F_EP) | (1u << XSB_F_VIRIAL)));
+});
 static OperatorRegistrar reg_uog("update_opt_from_ghost", []() { return std::unique_ptr<Operator>(new UpdateFromGhosts(0)); });
 
 // particle_displ_over (config_move_particles.msp:19-23): result = max displacement since backup_r > threshold

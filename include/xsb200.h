@@ -251,7 +251,8 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom);
 int xsb_ghost_plan(const xsb_domain_desc* dom, int ghost_layers, const int32_t* rank_coord, int32_t* out6, uint64_t capacity, uint64_t* count);
 /* ghost_update_r / ghost_update_opt: owner -> ghost copy of the fields in field_mask (bit = xsb_field)   */
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
-/* update_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29): ghost -> owner add                  */
+/* update_force_energy_from_ghost / update_virial_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29,43):  */
+/* ghost -> owner add of the real-valued fields in field_mask (XSB_F_VIRIAL: all 9 components); <= 16 words/atom   */
 int xsb_ghost_reduce_add(xsb_ctx* ctx, uint32_t field_mask);
 
 /* move_particles + migrate_cell_particles (config_move_particles.msp:89-96,121-125): wrap into the periodic box,   */

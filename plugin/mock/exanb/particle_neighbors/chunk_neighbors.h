@@ -1,0 +1,2 @@
+#pragma once
+#include <exanb/core/grid.h>

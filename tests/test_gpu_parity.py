@@ -337,6 +337,17 @@ def test_ghost_update_and_reduce_add():
     got = ctx.download(xsb.F_FX)
     assert np.max(np.abs(got[own] - tot[gs.src_index[own]])) < 1e-12
     assert np.max(np.abs(ctx.download(xsb.F_EP)[own] - tot[gs.src_index[own]])) < 1e-12
+    # update_virial_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:43): virial (9 per atom) + f + ep in one exchange
+    v = rng.normal(0, 1, (gs.n, 9)); g3 = rng.normal(0, 1, (3, gs.n))
+    ctx.upload(xsb.F_VIRIAL, v)
+    for k, fld in enumerate((xsb.F_FX, xsb.F_FY, xsb.F_FZ)):
+        ctx.upload(fld, g3[k])
+    ctx.upload(xsb.F_EP, f)
+    ctx.ghost_reduce_add([xsb.F_VIRIAL, xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP])
+    vt = np.zeros((len(pos), 9)); np.add.at(vt, gs.src_index, v)
+    assert np.max(np.abs(ctx.download(xsb.F_VIRIAL)[own] - vt[gs.src_index[own]])) < 1e-12
+    ft = np.zeros(len(pos)); np.add.at(ft, gs.src_index, g3[1])
+    assert np.max(np.abs(ctx.download(xsb.F_FY)[own] - ft[gs.src_index[own]])) < 1e-12
 
 
 def test_nve_loop_pieces_and_rebin():
