@@ -24,6 +24,9 @@ template<class T> struct OperatorSlot {
 };
 class OperatorNode {
 public:
+  // in onika the slot keywords are visible inside every operator class
+  static constexpr SlotDirection INPUT = SlotDirection::INPUT, OUTPUT = SlotDirection::OUTPUT, INPUT_OUTPUT = SlotDirection::INPUT_OUTPUT, PRIVATE = SlotDirection::PRIVATE;
+  static constexpr RequiredTag REQUIRED{}; static constexpr OptionalTag OPTIONAL{};
   virtual ~OperatorNode() = default;
   virtual void execute() = 0;
   virtual std::string documentation() const { return ""; }
@@ -41,5 +44,5 @@ struct FatalStream { template<class T> FatalStream& operator<<(const T&) { retur
 inline FatalStream fatal_error() { return FatalStream(); }
 inline std::ostream& lout_stream() { return std::cout; }
 } // onika
-#define ADD_SLOT(T, name, ...) ::onika::scg::OperatorSlot< T > name { ::onika::scg::__VA_ARGS__ }
+#define ADD_SLOT(T, name, ...) ::onika::scg::OperatorSlot< T > name { __VA_ARGS__ }
 #define ONIKA_AUTORUN_INIT(name) static void xsb_mock_autorun_##name(); static const int xsb_mock_autorun_flag_##name = (xsb_mock_autorun_##name(), 0); static void xsb_mock_autorun_##name()
