@@ -553,9 +553,13 @@ def run_xsb(args):
     if args.warmup:
         rebuild(); W.forces(ctx, xsb, 0)      # warm-up also covers the rebuild path (migration buffers, lazily set up NCCL channels)
         rebuild(); W.forces(ctx, xsb, 0)
-    barrier()
+    # the clock sampler (NVML init + thread start: milliseconds) starts BEFORE the barrier: started after it, it delays rank 0
+    # behind its peers, which then wait for rank 0 in the first exchange -- a one-off skew of several ms that the MAX over
+    # ranks of a 20-step window turns into a 5-20 % "scaling loss" (round 1's N=2 point)
     clocks = Clocks(local) if rank == 0 else None
+    barrier()
     ctx.profile_enable(True)
+    barrier()
     l0 = ctx.launches; rb0 = state["rebuilds"]; state["rebuild_s"] = 0.0; state["move_s"] = 0.0
     t0 = time.perf_counter()
     if flush is None:
@@ -601,7 +605,7 @@ def run_xsb(args):
         msm = max(allranks(ctx.timer_stop_ms()))
         barrier()
         mixed = {"value": atoms_total * km / (msm * 1e-3), "unit": UNIT, "ms_per_step": msm / km, "steps": km,
-                 "dtype": "f32 spline + pair math, f64 positions / distances / accumulation", "tolerance": 1e-5}
+                 "dtype": "f32 spline / pair / bispectrum math, f64 positions, distances and accumulation (XSB_FLAG_MIXED)", "tolerance": 1e-5}
         mode["flags"] = 0
 
     # ---- e2e: the plugin use case.  The host application owns the particle arrays (pinned host memory): every step it
@@ -730,8 +734,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.workload == "c3":
-        args.no_mixed = True                # snap_force has no mixed variant yet
     args.flush_l2 = args.flush_l2 == "on" or (args.flush_l2 == "auto" and args.workload == "c1")
     if args.impl == "reference":
         run_reference(args)

@@ -30,14 +30,35 @@ constexpr int SNAP_NN_MAX = 64;      // in-range neighbours of one atom held in 
 
 struct SnapZ { unsigned char j1, j2, j, ma1min, ma2max, na, mb1min, mb2max, nb, pad; unsigned short jju; int cgoff; };   // 16 B
 
-struct SnapConst
+// per-launch constants in the arithmetic type of the kernels (double, or float for XSB_FLAG_MIXED)
+template<class real>
+struct SnapConstT
 {
-  double rootpq[10][10];
+  real rootpq[10][10];
   int idxu_block[10];
   int twojmax, idxu_max, idxz_max, ncoeff, nelements, switchflag, bzeroflag;
-  double rfac0, rmin0, rcutfac, wself;
-  double radelem[8], wjelem[8], beta0[8], bzero_e[8];    // bzero_e[elem] = sum_k beta_k bzero[j_k]
+  real rfac0, rmin0, rcutfac, wself;
+  real radelem[8], wjelem[8];
+  double beta0[8], bzero_e[8];    // bzero_e[elem] = sum_k beta_k bzero[j_k]; energies are accumulated in double
 };
+typedef SnapConstT<double> SnapConst;
+
+template<class real> struct R2;
+template<> struct R2<double> { typedef double2 type; };
+template<> struct R2<float>  { typedef float2 type; };
+template<class real> __device__ __forceinline__ typename R2<real>::type mk2(real a, real b) { typename R2<real>::type v; v.x = a; v.y = b; return v; }
+__device__ __forceinline__ void xsincos(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ void xsincos(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ double xrsqrt(double a) { return rsqrt(a); }
+__device__ __forceinline__ float xrsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ double xsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float xsqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double xcos(double a) { return cos(a); }
+__device__ __forceinline__ float xcos(float a) { return cosf(a); }
+__device__ __forceinline__ double xsin(double a) { return sin(a); }
+__device__ __forceinline__ float xsin(float a) { return sinf(a); }
+// inside the kernel templates `real2` is the complex pair of the arithmetic type
+#define real2 typename R2<real>::type
 
 struct SnapDev
 {
@@ -49,6 +70,8 @@ struct SnapDev
   DevBuf<SnapZ> zsort; DevBuf<double> betaz_sort; DevBuf<int4> ytask; int n_ytask = 0;   // snap_y_kernel work items
   DevBuf<double2> ubuf, ybuf;                                                          // chunk staging (AoSoA)
   DevBuf<double> nbtab; DevBuf<unsigned> nbcnt;                                        // in-range neighbours of the chunk's atoms (Utot kernel -> force kernel)
+  SnapConstT<float> K32{};                                                               // the same constants rounded to float (XSB_FLAG_MIXED)
+  DevBuf<float> cglist32, betaz32, betaz_sort32;
   double rcut_max = 0.0;
   bool overflowed = false;       // a call hit SNAP_NN_MAX since xsb_snap_overflow() was last read
 };
@@ -56,66 +79,66 @@ struct SnapDev
 // the SNAP state of a context hangs off the context itself (xsb_ctx::snap), like GhostState: no process-global table
 static SnapDev* g_snap_of(xsb_ctx* ctx) { return static_cast<SnapDev*>(ctx->snap); }
 
-__device__ __forceinline__ double snap_sfac(const SnapConst& K, double r, double rcut)
+template<class real> __device__ __forceinline__ real snap_sfac(const SnapConstT<real>& K, real r, real rcut)
 {
-  if( K.switchflag == 0 || r <= K.rmin0 ) return 1.0;
-  if( r > rcut ) return 0.0;
-  return 0.5 * (cos((r - K.rmin0) * M_PI / (rcut - K.rmin0)) + 1.0);
+  if( K.switchflag == 0 || r <= K.rmin0 ) return real(1.0);
+  if( r > rcut ) return real(0.0);
+  return real(0.5) * (xcos((r - K.rmin0) * real(M_PI) / (rcut - K.rmin0)) + real(1.0));
 }
-__device__ __forceinline__ double snap_dsfac(const SnapConst& K, double r, double rcut)
+template<class real> __device__ __forceinline__ real snap_dsfac(const SnapConstT<real>& K, real r, real rcut)
 {
-  if( K.switchflag == 0 || r <= K.rmin0 || r > rcut ) return 0.0;
-  const double f = M_PI / (rcut - K.rmin0);
-  return -0.5 * sin((r - K.rmin0) * f) * f;
+  if( K.switchflag == 0 || r <= K.rmin0 || r > rcut ) return real(0.0);
+  const real f = real(M_PI) / (rcut - K.rmin0);
+  return -real(0.5) * xsin((r - K.rmin0) * f) * f;
 }
 
 // mailbox layout per neighbour: source row m (published at level 2m+1, 2m+2 elements) starts at m(m+1)
 __device__ __forceinline__ int mbox_off(int m) { return m * (m + 1); }
-// a lane's mailbox is n double2 words; the 32 mailboxes of a warp are laid out with an odd stride (in 16-byte words) so
+// a lane's mailbox is n real2 words; the 32 mailboxes of a warp are laid out with an odd stride (in 16-byte words) so
 // that the lanes of a quarter-warp hit 8 different bank groups: with the natural stride (a multiple of 128 bytes at
 // 2J = 8) every mailbox access was an 8-way bank conflict (ncu: 590 M shared wavefronts for 149 M ideal)
 #define SNAP_MBOX_STRIDE(n) (((n) | 1))
 
 // One sweep over the levels for the thread's (neighbour, row mb).  DERIV = false: accumulate sfac*wj*u into utot (shuffle
 // reduction over the lanes).  DERIV = true: carry du/dr_k, contract with Y -> dedr[3].
-template<int TJ, bool DERIV>
-__device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool valid, double x, double y, double z, double wj, double rcut,
-                                           double2* __restrict__ utot, const double2* __restrict__ ylist,
-                                           double2* __restrict__ mbox /* this neighbour's mailbox: [ (TJ/2)(TJ/2+1) ] x (DERIV ? 4 : 1) */,
-                                           double dedr[3])
+template<class real, int TJ, bool DERIV>
+__device__ __forceinline__ void snap_sweep(const SnapConstT<real>& K, int mb, bool valid, real x, real y, real z, real wj, real rcut,
+                                           real2* __restrict__ utot, const real2* __restrict__ ylist,
+                                           real2* __restrict__ mbox /* this neighbour's mailbox: [ (TJ/2)(TJ/2+1) ] x (DERIV ? 4 : 1) */,
+                                           real dedr[3])
 {
   constexpr int NE = TJ + 1;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1);     // mailbox entries per field
-  double ur[NE], ui[NE];
-  double dur[DERIV ? NE : 1][3], dui[DERIV ? NE : 1][3];
-  const double rsq = x * x + y * y + z * z, r = sqrt(rsq);
-  const double rscale0 = K.rfac0 * M_PI / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
-  double sn, cs; sincos(theta0, &sn, &cs);
-  const double z0 = r * cs / sn;
-  const double r0inv = rsqrt(rsq + z0 * z0);
-  const double a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
-  const double sfac = valid ? snap_sfac(K, r, rcut) * wj : 0.0;
-  double da_r[3], da_i[3], db_r[3], db_i[3], uvec[3], dsfac = 0.0;
+  real ur[NE], ui[NE];
+  real dur[DERIV ? NE : 1][3], dui[DERIV ? NE : 1][3];
+  const real rsq = x * x + y * y + z * z, r = xsqrt(rsq);
+  const real rscale0 = K.rfac0 * real(M_PI) / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+  real sn, cs; xsincos(theta0, &sn, &cs);
+  const real z0 = r * cs / sn;
+  const real r0inv = xrsqrt(rsq + z0 * z0);
+  const real a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
+  const real sfac = valid ? snap_sfac(K, r, rcut) * wj : real(0.0);
+  real da_r[3], da_i[3], db_r[3], db_i[3], uvec[3], dsfac = real(0.0);
   if( DERIV )
   {
-    const double rinv = 1.0 / r;
+    const real rinv = real(1.0) / r;
     uvec[0] = x * rinv; uvec[1] = y * rinv; uvec[2] = z * rinv;
-    const double dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
-    const double dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
+    const real dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
+    const real dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
 #   pragma unroll
     for(int k = 0; k < 3; k++)
     {
-      const double dr0inv = dr0invdr * uvec[k], dz0 = dz0dr * uvec[k];
+      const real dr0inv = dr0invdr * uvec[k], dz0 = dz0dr * uvec[k];
       da_r[k] = dz0 * r0inv + z0 * dr0inv; da_i[k] = -z * dr0inv;
       db_r[k] = y * dr0inv; db_i[k] = -x * dr0inv;
     }
     da_i[2] += -r0inv; db_i[0] += -r0inv; db_r[1] += r0inv;
-    dsfac = valid ? snap_dsfac(K, r, rcut) * wj : 0.0;
-    dedr[0] = dedr[1] = dedr[2] = 0.0;
+    dsfac = valid ? snap_dsfac(K, r, rcut) * wj : real(0.0);
+    dedr[0] = dedr[1] = dedr[2] = real(0.0);
   }
 # pragma unroll
-  for(int e = 0; e < NE; e++) { ur[e] = 0.0; ui[e] = 0.0; if( DERIV ) { for(int k = 0; k < 3; k++) { dur[e][k] = 0.0; dui[e][k] = 0.0; } } }
-  if( mb == 0 ) ur[0] = 1.0;        // level 0: u = 1
+  for(int e = 0; e < NE; e++) { ur[e] = real(0.0); ui[e] = real(0.0); if( DERIV ) { for(int k = 0; k < 3; k++) { dur[e][k] = real(0.0); dui[e][k] = real(0.0); } } }
+  if( mb == 0 ) ur[0] = real(1.0);        // level 0: u = 1
 
   // contribution of the thread's row at level j (called after the row has been advanced to level j)
   auto emit = [&](int j, auto jc)
@@ -127,7 +150,7 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
 #     pragma unroll
       for(int ma = 0; ma <= J; ma++)
       {
-        double vr = sfac * ur[ma], vi = sfac * ui[ma];
+        real vr = sfac * ur[ma], vi = sfac * ui[ma];
 #       pragma unroll
         for(int o = 16; o > 0; o >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o); vi += __shfl_xor_sync(0xffffffffu, vi, o); }
         if( (threadIdx.x & 31) == 0 ) { utot[base + ma].x += vr; utot[base + ma].y += vi; }
@@ -139,14 +162,14 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
 #     pragma unroll
       for(int ma = 0; ma <= J; ma++)
       {
-        double w = 1.0;
-        if( middle ) w = ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0);
-        const double2 Y = ylist[base + ma];
+        real w = real(1.0);
+        if( middle ) w = ma < mb ? real(1.0) : (ma == mb ? real(0.5) : real(0.0));
+        const real2 Y = ylist[base + ma];
 #       pragma unroll
         for(int k = 0; k < 3; k++)
         {
-          const double fr = dsfac * ur[ma] * uvec[k] + sfac * dur[ma][k];
-          const double fi = dsfac * ui[ma] * uvec[k] + sfac * dui[ma][k];
+          const real fr = dsfac * ur[ma] * uvec[k] + sfac * dur[ma][k];
+          const real fi = dsfac * ui[ma] * uvec[k] + sfac * dui[ma][k];
           dedr[k] += w * (fr * Y.x + fi * Y.y);
         }
       }
@@ -170,23 +193,23 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
         for(int ma = 0; ma < J; ma++)
         {
           const int mp = J - 1 - ma;
-          const double sgn = ((mb - 1 + mp) & 1) ? -1.0 : 1.0;
-          const double2 v = mbox[o + mp];
+          const real sgn = ((mb - 1 + mp) & 1) ? -real(1.0) : real(1.0);
+          const real2 v = mbox[o + mp];
           ur[ma] = sgn * v.x; ui[ma] = -sgn * v.y;
           if( DERIV )
           {
 #           pragma unroll
-            for(int k = 0; k < 3; k++) { const double2 d = mbox[MB * (1 + k) + o + mp]; dur[ma][k] = sgn * d.x; dui[ma][k] = -sgn * d.y; }
+            for(int k = 0; k < 3; k++) { const real2 d = mbox[MB * (1 + k) + o + mp]; dur[ma][k] = sgn * d.x; dui[ma][k] = -sgn * d.y; }
           }
         }
       }
-      double nr[J + 1], ni[J + 1], dnr[DERIV ? J + 1 : 1][3], dni[DERIV ? J + 1 : 1][3];
-      nr[0] = 0.0; ni[0] = 0.0;
-      if( DERIV ) { for(int k = 0; k < 3; k++) { dnr[0][k] = 0.0; dni[0][k] = 0.0; } }
+      real nr[J + 1], ni[J + 1], dnr[DERIV ? J + 1 : 1][3], dni[DERIV ? J + 1 : 1][3];
+      nr[0] = real(0.0); ni[0] = real(0.0);
+      if( DERIV ) { for(int k = 0; k < 3; k++) { dnr[0][k] = real(0.0); dni[0][k] = real(0.0); } }
 #     pragma unroll
       for(int ma = 0; ma < J; ma++)
       {
-        double q = K.rootpq[J - ma][J - mb];
+        real q = K.rootpq[J - ma][J - mb];
         nr[ma] += q * (a_r * ur[ma] + a_i * ui[ma]);
         ni[ma] += q * (a_r * ui[ma] - a_i * ur[ma]);
         if( DERIV )
@@ -225,8 +248,8 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
 #       pragma unroll
         for(int ma = 0; ma <= J; ma++)
         {
-          mbox[o + ma] = make_double2(ur[ma], ui[ma]);
-          if( DERIV ) { for(int k = 0; k < 3; k++) mbox[MB * (1 + k) + o + ma] = make_double2(dur[ma][k], dui[ma][k]); }
+          mbox[o + ma] = mk2<real>(ur[ma], ui[ma]);
+          if( DERIV ) { for(int k = 0; k < 3; k++) mbox[MB * (1 + k) + o + ma] = mk2<real>(dur[ma][k], dui[ma][k]); }
         }
       }
     }
@@ -247,33 +270,33 @@ __device__ __forceinline__ void snap_sweep(const SnapConst& K, int mb, bool vali
 // contracted with Y on the fly.  The three directions of a neighbour run in three different warps (snap_f_kernel), which
 // cuts the per-thread state from 4 rows to 2 (fits ~128 registers) and triples the warps an SM can hold; the price is
 // that the u chain itself is carried three times.
-template<int TJ>
-__device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int kd, bool valid, double x, double y, double z, double wj, double rcut,
-                                                 const double2* __restrict__ ylist, double2* __restrict__ mbox /* [2][MB] of this (neighbour, kd) */)
+template<class real, int TJ>
+__device__ __forceinline__ real snap_sweep_dir(const SnapConstT<real>& K, int mb, int kd, bool valid, real x, real y, real z, real wj, real rcut,
+                                                 const real2* __restrict__ ylist, real2* __restrict__ mbox /* [2][MB] of this (neighbour, kd) */)
 {
   constexpr int NE = TJ + 1;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1);
-  double ur[NE], ui[NE], dur[NE], dui[NE];
-  const double rsq = x * x + y * y + z * z, r = sqrt(rsq);
-  const double rscale0 = K.rfac0 * M_PI / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
-  double sn, cs; sincos(theta0, &sn, &cs);
-  const double z0 = r * cs / sn;
-  const double r0inv = rsqrt(rsq + z0 * z0);
-  const double a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
-  const double sfac = valid ? snap_sfac(K, r, rcut) * wj : 0.0;
-  const double rinv = 1.0 / r;
-  const double uv = (kd == 0 ? x : (kd == 1 ? y : z)) * rinv;
-  const double dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
-  const double dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
-  const double dr0inv = dr0invdr * uv, dz0 = dz0dr * uv;
-  const double da_r = dz0 * r0inv + z0 * dr0inv, da_i = -z * dr0inv + (kd == 2 ? -r0inv : 0.0);
-  const double db_r = y * dr0inv + (kd == 1 ? r0inv : 0.0), db_i = -x * dr0inv + (kd == 0 ? -r0inv : 0.0);
-  const double dsfac = valid ? snap_dsfac(K, r, rcut) * wj : 0.0;
-  const double dsu = dsfac * uv;
-  double dedr = 0.0;
+  real ur[NE], ui[NE], dur[NE], dui[NE];
+  const real rsq = x * x + y * y + z * z, r = xsqrt(rsq);
+  const real rscale0 = K.rfac0 * real(M_PI) / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+  real sn, cs; xsincos(theta0, &sn, &cs);
+  const real z0 = r * cs / sn;
+  const real r0inv = xrsqrt(rsq + z0 * z0);
+  const real a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
+  const real sfac = valid ? snap_sfac(K, r, rcut) * wj : real(0.0);
+  const real rinv = real(1.0) / r;
+  const real uv = (kd == 0 ? x : (kd == 1 ? y : z)) * rinv;
+  const real dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
+  const real dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
+  const real dr0inv = dr0invdr * uv, dz0 = dz0dr * uv;
+  const real da_r = dz0 * r0inv + z0 * dr0inv, da_i = -z * dr0inv + (kd == 2 ? -r0inv : real(0.0));
+  const real db_r = y * dr0inv + (kd == 1 ? r0inv : real(0.0)), db_i = -x * dr0inv + (kd == 0 ? -r0inv : real(0.0));
+  const real dsfac = valid ? snap_dsfac(K, r, rcut) * wj : real(0.0);
+  const real dsu = dsfac * uv;
+  real dedr = real(0.0);
 # pragma unroll
-  for(int e = 0; e < NE; e++) { ur[e] = 0.0; ui[e] = 0.0; dur[e] = 0.0; dui[e] = 0.0; }
-  if( mb == 0 ) ur[0] = 1.0;
+  for(int e = 0; e < NE; e++) { ur[e] = real(0.0); ui[e] = real(0.0); dur[e] = real(0.0); dui[e] = real(0.0); }
+  if( mb == 0 ) ur[0] = real(1.0);
 
   auto emit = [&](auto jc)
   {
@@ -283,11 +306,11 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
 #   pragma unroll
     for(int ma = 0; ma <= J; ma++)
     {
-      double w = 1.0;
-      if( middle ) w = ma < mb ? 1.0 : (ma == mb ? 0.5 : 0.0);
-      const double2 Y = ylist[base + ma];
-      const double fr = dsu * ur[ma] + sfac * dur[ma];
-      const double fi = dsu * ui[ma] + sfac * dui[ma];
+      real w = real(1.0);
+      if( middle ) w = ma < mb ? real(1.0) : (ma == mb ? real(0.5) : real(0.0));
+      const real2 Y = ylist[base + ma];
+      const real fr = dsu * ur[ma] + sfac * dur[ma];
+      const real fi = dsu * ui[ma] + sfac * dui[ma];
       dedr += w * (fr * Y.x + fi * Y.y);
     }
   };
@@ -305,8 +328,8 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
         for(int ma = 0; ma < J; ma++)
         {
           const int mp = J - 1 - ma;
-          const double sgn = ((mb - 1 + mp) & 1) ? -1.0 : 1.0;
-          const double2 v = mbox[o + mp], d = mbox[MB + o + mp];
+          const real sgn = ((mb - 1 + mp) & 1) ? -real(1.0) : real(1.0);
+          const real2 v = mbox[o + mp], d = mbox[MB + o + mp];
           ur[ma] = sgn * v.x; ui[ma] = -sgn * v.y; dur[ma] = sgn * d.x; dui[ma] = -sgn * d.y;
         }
       }
@@ -314,10 +337,10 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
 #     pragma unroll
       for(int ma = J; ma >= 0; ma--)
       {
-        double nr = 0.0, ni = 0.0, dnr = 0.0, dni = 0.0;
+        real nr = real(0.0), ni = real(0.0), dnr = real(0.0), dni = real(0.0);
         if( ma < J )
         {
-          const double q = K.rootpq[J - ma][J - mb];
+          const real q = K.rootpq[J - ma][J - mb];
           nr = q * (a_r * ur[ma] + a_i * ui[ma]);
           ni = q * (a_r * ui[ma] - a_i * ur[ma]);
           dnr = q * (da_r * ur[ma] + da_i * ui[ma] + a_r * dur[ma] + a_i * dui[ma]);
@@ -325,7 +348,7 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
         }
         if( ma > 0 )
         {
-          const double q = K.rootpq[ma][J - mb];
+          const real q = K.rootpq[ma][J - mb];
           nr -= q * (b_r * ur[ma - 1] + b_i * ui[ma - 1]);
           ni -= q * (b_r * ui[ma - 1] - b_i * ur[ma - 1]);
           dnr -= q * (db_r * ur[ma - 1] + db_i * ui[ma - 1] + b_r * dur[ma - 1] + b_i * dui[ma - 1]);
@@ -338,7 +361,7 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
       {
         const int o = mbox_off(mb);
 #       pragma unroll
-        for(int ma = 0; ma <= J; ma++) { mbox[o + ma] = make_double2(ur[ma], ui[ma]); mbox[MB + o + ma] = make_double2(dur[ma], dui[ma]); }
+        for(int ma = 0; ma <= J; ma++) { mbox[o + ma] = mk2<real>(ur[ma], ui[ma]); mbox[MB + o + ma] = mk2<real>(dur[ma], dui[ma]); }
       }
     }
     __syncthreads();
@@ -354,36 +377,38 @@ __device__ __forceinline__ double snap_sweep_dir(const SnapConst& K, int mb, int
   return dedr;
 }
 
-struct SnapArgs
+template<class real>
+struct SnapArgsT
 {
+  typedef real real_t;
   const double* __restrict__ rx; const double* __restrict__ ry; const double* __restrict__ rz; const unsigned char* __restrict__ type;
   const unsigned long long* __restrict__ nbh_off; const unsigned* __restrict__ nbh_idx;
   const unsigned* __restrict__ atoms; unsigned n_atoms;
-  const SnapZ* __restrict__ idxz; const double* __restrict__ cglist; const double* __restrict__ betaz;
+  const SnapZ* __restrict__ idxz; const real* __restrict__ cglist; const real* __restrict__ betaz;
   double *fx, *fy, *fz, *ep, *vir; int* err;
   unsigned long long* clk;     // optional per-phase cycle counters (tools/snap_bench.py --clocks), nullptr in production
   // split pipeline (snap_u -> snap_y -> snap_f): Utot and Y of the atoms of one chunk, AoSoA [atom / 32][jju][atom % 32]
-  double2* ubuf; double2* ybuf; unsigned base;      // base = first central atom (position in the launch's atom list) of the chunk
+  real2* ubuf; real2* ybuf; unsigned base;      // base = first central atom (position in the launch's atom list) of the chunk
   // in-range neighbours found by the Utot kernel, per chunk slot: 6 rows of SNAP_NN_MAX doubles (dx, dy, dz, wj, rc, index bits)
   double* nbtab; unsigned* nbcnt;
-  const SnapZ* __restrict__ zsort; const double* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
+  const SnapZ* __restrict__ zsort; const real* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
 };
 
 // PHASE 0: fused (everything in one CTA, kept for reference / small runs); PHASE 1: Utot only -> A.ubuf; PHASE 3: reads Utot
 // and Y of its atom back from A.ubuf / A.ybuf, then energy + force sweep.
-template<int TJ, bool XFORM, int PHASE>
-__global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+template<class real, int TJ, bool XFORM, int PHASE>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
-  double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
-  double2* mbox = ylist + K.idxu_max;                                   // [32][4 * MB]
-  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)));   // [SNAP_NN_MAX] x 5
-  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  real2* utot = reinterpret_cast<real2*>(smem_raw);                 // [idxu_max]
+  real2* ylist = utot + K.idxu_max;                                   // [idxu_max]
+  real2* mbox = ylist + K.idxu_max;                                   // [32][4 * MB]
+  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)));   // [SNAP_NN_MAX] x 5
+  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
   unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
-  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32][3] + scratch
+  real* red = reinterpret_cast<real*>(nb_g + SNAP_NN_MAX);          // [NR][32][3] + scratch
   __shared__ unsigned s_nn;
   const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
   const unsigned slot = A.base + blockIdx.x;
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   // ---- Utot = wself on the diagonal, Y = 0
   if( PHASE != 3 )
   {
-    for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = make_double2(0.0, 0.0); ylist[k] = make_double2(0.0, 0.0); }
+    for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = mk2<real>(real(0.0), real(0.0)); ylist[k] = mk2<real>(real(0.0), real(0.0)); }
     __syncthreads();
     for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
   }
@@ -421,13 +446,13 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
         dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
         apply_xform<XFORM>(X, dx, dy, dz);
         const int ej = A.type ? A.type[g] : 0;
-        rc = (K.radelem[ei] + K.radelem[ej]) * K.rcutfac; wj = K.wjelem[ej];
-        const double d2 = dx * dx + dy * dy + dz * dz;
+        rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
+        const real d2 = dx * dx + dy * dy + dz * dz;
         in = d2 < rc * rc && d2 > 1e-20;
       }
       const unsigned m = __ballot_sync(0xffffffffu, in);
       const unsigned slot = nn + __popc(m & ((1u << lane) - 1u));
-      if( in && slot < SNAP_NN_MAX ) { nb_x[slot] = dx; nb_y[slot] = dy; nb_z[slot] = dz; nb_w[slot] = wj; nb_rc[slot] = rc; nb_g[slot] = g; }
+      if( in && slot < SNAP_NN_MAX ) { nb_x[slot] = real(dx); nb_y[slot] = real(dy); nb_z[slot] = real(dz); nb_w[slot] = real(wj); nb_rc[slot] = real(rc); nb_g[slot] = g; }
       nn += __popc(m);
     }
     if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
@@ -447,13 +472,13 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   mark(0);
 
   // ---- sweep 1: Utot
-  double dummy[3];
+  real dummy[3];
   if( PHASE != 3 )
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
-    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    snap_sweep<TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dummy);
+    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+    snap_sweep<real, TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dummy);
   }
   __syncthreads();
   mark(1);
@@ -465,9 +490,9 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     for(int k = int(tid); k < half; k += NT)
     {
       const int mbb = k / (j + 1), ma = k % (j + 1);
-      const double sgn = ((mbb + ma) & 1) ? -1.0 : 1.0;
-      const double2 v = utot[jb + k];
-      utot[jb + (j + 1) * (j - mbb) + (j - ma)] = make_double2(sgn * v.x, -sgn * v.y);
+      const real sgn = ((mbb + ma) & 1) ? -real(1.0) : real(1.0);
+      const real2 v = utot[jb + k];
+      utot[jb + (j + 1) * (j - mbb) + (j - ma)] = mk2<real>(sgn * v.x, -sgn * v.y);
     }
   }
   __syncthreads();
@@ -479,31 +504,31 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     return;
   }
   // ---- Y = sum over idxz of betaj * Z  (compute_yi), shared-memory accumulation
-  const double* betaz = A.betaz + size_t(ei) * K.idxz_max;
+  const real* betaz = A.betaz + size_t(ei) * K.idxz_max;
   if( PHASE == 0 )
   for(int jjz = int(tid); jjz < K.idxz_max; jjz += NT)
   {
     const SnapZ q = A.idxz[jjz];
-    const double* cg = A.cglist + q.cgoff;
-    double zr = 0.0, zi = 0.0;
+    const real* cg = A.cglist + q.cgoff;
+    real zr = real(0.0), zi = real(0.0);
     int jju1 = K.idxu_block[q.j1] + (q.j1 + 1) * q.mb1min, jju2 = K.idxu_block[q.j2] + (q.j2 + 1) * q.mb2max, icgb = q.mb1min * (q.j2 + 1) + q.mb2max;
     for(int ib = 0; ib < q.nb; ib++)
     {
-      double sr = 0.0, si = 0.0;
+      real sr = real(0.0), si = real(0.0);
       int ma1 = q.ma1min, ma2 = q.ma2max, icga = q.ma1min * (q.j2 + 1) + q.ma2max;
       for(int ia = 0; ia < q.na; ia++)
       {
-        const double2 u1 = utot[jju1 + ma1], u2 = utot[jju2 + ma2];
-        const double c = __ldg(cg + icga);
+        const real2 u1 = utot[jju1 + ma1], u2 = utot[jju2 + ma2];
+        const real c = __ldg(cg + icga);
         sr += c * (u1.x * u2.x - u1.y * u2.y);
         si += c * (u1.x * u2.y + u1.y * u2.x);
         ma1++; ma2--; icga += q.j2;
       }
-      const double c = __ldg(cg + icgb);
+      const real c = __ldg(cg + icgb);
       zr += c * sr; zi += c * si;
       jju1 += q.j1 + 1; jju2 -= q.j2 + 1; icgb += q.j2;
     }
-    const double bj = __ldg(betaz + jjz);
+    const real bj = __ldg(betaz + jjz);
     atomicAdd(&ylist[q.jju].x, bj * zr); atomicAdd(&ylist[q.jju].y, bj * zi);
   }
   __syncthreads();
@@ -512,13 +537,13 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
   if( A.ep )
   {
-    double s = 0.0;
+    real s = real(0.0);
     for(int j = 0; j <= TJ; j++)
     {
       const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
       for(int k = int(tid); k < cnt; k += NT)
       {
-        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
+        const real w = (j % 2 == 0 && k == cnt - 1) ? real(0.5) : real(1.0);
         s += w * (utot[jb + k].x * ylist[jb + k].x + utot[jb + k].y * ylist[jb + k].y);
       }
     }
@@ -526,31 +551,31 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     for(int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if( lane == 0 ) red[mb] = s;
     __syncthreads();
-    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    if( tid == 0 ) { real t = real(0.0); for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * double(t) - K.bzero_e[ei]; }
     __syncthreads();
   }
 
   mark(4);
   // ---- sweep 2: dU/dr contracted with Y -> fij ; f_i += fij, f_j -= fij, virial -fij (x) rij on the centre
-  double fix = 0.0, fiy = 0.0, fiz = 0.0, v[9];
+  real fix = real(0.0), fiy = real(0.0), fiz = real(0.0), v[9];
 # pragma unroll
-  for(int k = 0; k < 9; k++) v[k] = 0.0;
+  for(int k = 0; k < 9; k++) v[k] = real(0.0);
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
-    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    double dedr[3];
-    snap_sweep<TJ, true>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dedr);
+    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+    real dedr[3];
+    snap_sweep<real, TJ, true>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dedr);
     red[(mb * 32 + lane) * 3 + 0] = dedr[0]; red[(mb * 32 + lane) * 3 + 1] = dedr[1]; red[(mb * 32 + lane) * 3 + 2] = dedr[2];
     __syncthreads();
     if( mb == 0 && valid )
     {
-      double f[3] = { 0.0, 0.0, 0.0 };
+      real f[3] = { real(0.0), real(0.0), real(0.0) };
       for(int w2 = 0; w2 < NR; w2++) for(int k = 0; k < 3; k++) f[k] += red[(w2 * 32 + lane) * 3 + k];
-      for(int k = 0; k < 3; k++) f[k] *= 2.0;
+      for(int k = 0; k < 3; k++) f[k] *= real(2.0);
       fix += f[0]; fiy += f[1]; fiz += f[2];
       const unsigned g = nb_g[n];
-      atomicAdd(A.fx + g, -f[0]); atomicAdd(A.fy + g, -f[1]); atomicAdd(A.fz + g, -f[2]);
+      atomicAdd(A.fx + g, -double(f[0])); atomicAdd(A.fy + g, -double(f[1])); atomicAdd(A.fz + g, -double(f[2]));
       if( A.vir )
       {
         v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
@@ -571,27 +596,27 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     }
     if( lane == 0 )
     {
-      atomicAdd(A.fx + ai, fix); atomicAdd(A.fy + ai, fiy); atomicAdd(A.fz + ai, fiz);
-      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += v[k]; }
+      atomicAdd(A.fx + ai, double(fix)); atomicAdd(A.fy + ai, double(fiy)); atomicAdd(A.fz + ai, double(fiz));
+      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += double(v[k]); }
     }
   }
   mark(5);
 }
 
 // ---- force kernel of the split pipeline: CTA per atom, 3 x (J/2+1) warps = (direction, row), lane = neighbour ----------
-template<int TJ, bool XFORM>
-__global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+template<class real, int TJ, bool XFORM>
+__global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
 {
   constexpr int NR = TJ / 2 + 1, NW = 3 * NR, NT = 32 * NW;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = 2 * (MB ? MB : 1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* utot = reinterpret_cast<double2*>(smem_raw);                 // [idxu_max]
-  double2* ylist = utot + K.idxu_max;                                   // [idxu_max]
-  double2* mbox = ylist + K.idxu_max;                                   // [32][3][MBS]
-  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(3 * MBS));        // [SNAP_NN_MAX] x 5
-  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  real2* utot = reinterpret_cast<real2*>(smem_raw);                 // [idxu_max]
+  real2* ylist = utot + K.idxu_max;                                   // [idxu_max]
+  real2* mbox = ylist + K.idxu_max;                                   // [32][3][MBS]
+  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(3 * MBS));        // [SNAP_NN_MAX] x 5
+  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
   unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
-  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NW][32]
+  real* red = reinterpret_cast<real*>(nb_g + SNAP_NN_MAX);          // [NW][32]
   __shared__ unsigned s_nn;
   const unsigned tid = threadIdx.x, lane = tid & 31u; const int wrp = int(tid >> 5), mb = wrp % NR, kd = wrp / NR;
   const unsigned slot = A.base + blockIdx.x;
@@ -614,13 +639,13 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
         dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
         apply_xform<XFORM>(X, dx, dy, dz);
         const int ej = A.type ? A.type[g] : 0;
-        rc = (K.radelem[ei] + K.radelem[ej]) * K.rcutfac; wj = K.wjelem[ej];
-        const double d2 = dx * dx + dy * dy + dz * dz;
+        rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
+        const real d2 = dx * dx + dy * dy + dz * dz;
         in = d2 < rc * rc && d2 > 1e-20;
       }
       const unsigned m = __ballot_sync(0xffffffffu, in);
       const unsigned sl = nn + __popc(m & ((1u << lane) - 1u));
-      if( in && sl < SNAP_NN_MAX ) { nb_x[sl] = dx; nb_y[sl] = dy; nb_z[sl] = dz; nb_w[sl] = wj; nb_rc[sl] = rc; nb_g[sl] = g; }
+      if( in && sl < SNAP_NN_MAX ) { nb_x[sl] = real(dx); nb_y[sl] = real(dy); nb_z[sl] = real(dz); nb_w[sl] = real(wj); nb_rc[sl] = real(rc); nb_g[sl] = g; }
       nn += __popc(m);
     }
     if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
@@ -630,13 +655,13 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
   // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
   if( A.ep )
   {
-    double sE = 0.0;
+    real sE = real(0.0);
     for(int j = 0; j <= TJ; j++)
     {
       const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
       for(int k = int(tid); k < cnt; k += NT)
       {
-        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
+        const real w = (j % 2 == 0 && k == cnt - 1) ? real(0.5) : real(1.0);
         sE += w * (utot[jb + k].x * ylist[jb + k].x + utot[jb + k].y * ylist[jb + k].y);
       }
     }
@@ -644,27 +669,27 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
     for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
     if( lane == 0 ) red[wrp] = sE;
     __syncthreads();
-    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NW; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    if( tid == 0 ) { real t = real(0.0); for(int w = 0; w < NW; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * double(t) - K.bzero_e[ei]; }
     __syncthreads();
   }
-  double fix = 0.0, fiy = 0.0, fiz = 0.0, v[9];
+  real fix = real(0.0), fiy = real(0.0), fiz = real(0.0), v[9];
 # pragma unroll
-  for(int k = 0; k < 9; k++) v[k] = 0.0;
+  for(int k = 0; k < 9; k++) v[k] = real(0.0);
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
-    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(3 * MBS) + kd * MBS);
+    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+    const real d = snap_sweep_dir<real, TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(3 * MBS) + kd * MBS);
     red[wrp * 32 + lane] = d;
     __syncthreads();
     if( wrp == 0 && valid )
     {
-      double f[3] = { 0.0, 0.0, 0.0 };
+      real f[3] = { real(0.0), real(0.0), real(0.0) };
       for(int k = 0; k < 3; k++) for(int w2 = 0; w2 < NR; w2++) f[k] += red[(k * NR + w2) * 32 + lane];
-      for(int k = 0; k < 3; k++) f[k] *= 2.0;
+      for(int k = 0; k < 3; k++) f[k] *= real(2.0);
       fix += f[0]; fiy += f[1]; fiz += f[2];
       const unsigned g = nb_g[n];
-      atomicAdd(A.fx + g, -f[0]); atomicAdd(A.fy + g, -f[1]); atomicAdd(A.fz + g, -f[2]);
+      atomicAdd(A.fx + g, -double(f[0])); atomicAdd(A.fy + g, -double(f[1])); atomicAdd(A.fz + g, -double(f[2]));
       if( A.vir )
       {
         v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
@@ -685,8 +710,8 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
     }
     if( lane == 0 )
     {
-      atomicAdd(A.fx + ai, fix); atomicAdd(A.fy + ai, fiy); atomicAdd(A.fz + ai, fiz);
-      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += v[k]; }
+      atomicAdd(A.fx + ai, double(fix)); atomicAdd(A.fy + ai, double(fiy)); atomicAdd(A.fz + ai, double(fiz));
+      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += double(v[k]); }
     }
   }
 }
@@ -694,20 +719,20 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
 // ---- force kernel, one CTA per (atom, Cartesian direction): J/2+1 warps = rows, lane = neighbour ------------------------
 // Same sweep as snap_f_kernel, but the three directions of an atom are three independent CTAs of 160 threads (2J = 8):
 // three of them fit the register file of an SM, so the serial prologue of one (neighbour filter: four dependent global
-// loads; Y fetch) overlaps the sweeps of the others, and a barrier only joins 5 warps instead of 15.  The neighbour
-// filter and the Y fetch are repeated per direction (cheap against the sweep); the energy is computed by direction 0.
-template<int TJ, bool XFORM>
-__global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const SnapArgs A, const XForm X, const SnapConst K)
+// loads; Y fetch) overlaps the sweeps of the others, and a barrier only joins 5 warps instead of real(15.)  The neighbour
+// filter and the Y fetch are repeated per direction (cheap against the sweep); the energy is computed by direction real(0.)
+template<class real, int TJ, bool XFORM>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) snap_fd_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = 2 * (MB ? MB : 1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* ylist = reinterpret_cast<double2*>(smem_raw);                // [idxu_max]
-  double2* mbox = ylist + K.idxu_max;                                   // [32][MBS] (odd stride)
-  double* nb_x = reinterpret_cast<double*>(mbox + 32 * SNAP_MBOX_STRIDE(MBS));        // [SNAP_NN_MAX] x 5
-  double* nb_y = nb_x + SNAP_NN_MAX; double* nb_z = nb_y + SNAP_NN_MAX; double* nb_w = nb_z + SNAP_NN_MAX; double* nb_rc = nb_w + SNAP_NN_MAX;
+  real2* ylist = reinterpret_cast<real2*>(smem_raw);                // [idxu_max]
+  real2* mbox = ylist + K.idxu_max;                                   // [32][MBS] (odd stride)
+  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(MBS));        // [SNAP_NN_MAX] x 5
+  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
   unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
-  double* red = reinterpret_cast<double*>(nb_g + SNAP_NN_MAX);          // [NR][32]
+  real* red = reinterpret_cast<real*>(nb_g + SNAP_NN_MAX);          // [NR][32]
   __shared__ unsigned s_nn;
   const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
   const unsigned at = blockIdx.x / 3u; const int kd = int(blockIdx.x % 3u);
@@ -723,7 +748,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const Sna
     const double* t = A.nbtab + size_t(at) * 6 * SNAP_NN_MAX;
     for(unsigned i = lane; i < nn; i += 32)
     {
-      nb_x[i] = t[i]; nb_y[i] = t[SNAP_NN_MAX + i]; nb_z[i] = t[2 * SNAP_NN_MAX + i]; nb_w[i] = t[3 * SNAP_NN_MAX + i]; nb_rc[i] = t[4 * SNAP_NN_MAX + i];
+      nb_x[i] = real(t[i]); nb_y[i] = real(t[SNAP_NN_MAX + i]); nb_z[i] = real(t[2 * SNAP_NN_MAX + i]); nb_w[i] = real(t[3 * SNAP_NN_MAX + i]); nb_rc[i] = real(t[4 * SNAP_NN_MAX + i]);
       nb_g[i] = unsigned(__double_as_longlong(t[5 * SNAP_NN_MAX + i]));
     }
     if( lane == 0 ) s_nn = nn;
@@ -738,14 +763,14 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const Sna
   // ---- energy (direction 0 only): e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero ; Utot straight from global
   if( A.ep && kd == 0 )
   {
-    double sE = 0.0;
+    real sE = real(0.0);
     for(int j = 0; j <= TJ; j++)
     {
       const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
       for(int k = int(tid); k < cnt; k += NT)
       {
-        const double w = (j % 2 == 0 && k == cnt - 1) ? 0.5 : 1.0;
-        const double2 u = A.ubuf[soa + size_t(jb + k) * 32];
+        const real w = (j % 2 == 0 && k == cnt - 1) ? real(0.5) : real(1.0);
+        const real2 u = A.ubuf[soa + size_t(jb + k) * 32];
         sE += w * (u.x * ylist[jb + k].x + u.y * ylist[jb + k].y);
       }
     }
@@ -753,25 +778,25 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const Sna
     for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
     if( lane == 0 ) red[mb] = sE;
     __syncthreads();
-    if( tid == 0 ) { double t = 0.0; for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * t - K.bzero_e[ei]; }
+    if( tid == 0 ) { real t = real(0.0); for(int w = 0; w < NR; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * double(t) - K.bzero_e[ei]; }
     __syncthreads();
   }
   double* const fout = kd == 0 ? A.fx : (kd == 1 ? A.fy : A.fz);
-  double fi = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  real fi = real(0.0), v0 = real(0.0), v1 = real(0.0), v2 = real(0.0);
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
-    const double x = valid ? nb_x[n] : 1.0, y = valid ? nb_y[n] : 0.0, z = valid ? nb_z[n] : 0.0, w = valid ? nb_w[n] : 0.0, rc = valid ? nb_rc[n] : 4.0;
-    const double d = snap_sweep_dir<TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(MBS));
+    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+    const real d = snap_sweep_dir<real, TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(MBS));
     red[mb * 32 + lane] = d;
     __syncthreads();
     if( mb == 0 && valid )
     {
-      double f = 0.0;
+      real f = real(0.0);
       for(int w2 = 0; w2 < NR; w2++) f += red[w2 * 32 + lane];
-      f *= 2.0;
+      f *= real(2.0);
       fi += f;
-      atomicAdd(fout + nb_g[n], -f);
+      atomicAdd(fout + nb_g[n], -double(f));
       if( A.vir ) { v0 -= f * x; v1 -= f * y; v2 -= f * z; }
     }
     __syncthreads();
@@ -787,8 +812,8 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const Sna
     }
     if( lane == 0 )
     {
-      atomicAdd(fout + ai, fi);
-      if( A.vir ) { double* p = A.vir + 9ull * ai + 3 * kd; atomicAdd(p, v0); atomicAdd(p + 1, v1); atomicAdd(p + 2, v2); }
+      atomicAdd(fout + ai, double(fi));
+      if( A.vir ) { double* p = A.vir + 9ull * ai + 3 * kd; atomicAdd(p, double(v0)); atomicAdd(p + 1, double(v1)); atomicAdd(p + 2, double(v2)); }
     }
   }
 }
@@ -799,11 +824,11 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), 3) snap_fd_kernel(const Sna
 // and all index / Clebsch-Gordan bookkeeping is warp-uniform.  Work items are the distinct Y elements (jju) with the
 // list of idxz entries that feed them (sorted by cost, handed out through a shared counter), so each Y element has one
 // writer: no atomics, no zero-fill.
-template<int TJ>
-__global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgs A, const SnapConst K)
+template<class real, int TJ>
+__global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgsT<real> A, const SnapConstT<real> K)
 {
   extern __shared__ __align__(128) unsigned char ysm[];
-  double2* U = reinterpret_cast<double2*>(ysm);                  // [idxu_max][32]
+  real2* U = reinterpret_cast<real2*>(ysm);                  // [idxu_max][32]
   __shared__ __align__(8) unsigned long long bar;
   __shared__ int next_task;
   const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -812,7 +837,7 @@ __global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgs A, const 
   __syncthreads();
   if( tid == 0 )
   {
-    const unsigned bytes = unsigned(K.idxu_max) * 32u * 16u;
+    const unsigned bytes = unsigned(K.idxu_max) * 32u * unsigned(sizeof(real2));
     mbar_arrive_expect_tx(&bar, bytes);
     bulk_g2s(U, A.ubuf + blk, bytes, &bar);
   }
@@ -821,7 +846,7 @@ __global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgs A, const 
   const unsigned slot = A.base + blockIdx.x * 32u + lane;
   int ei = 0;
   if( A.type && slot < A.n_atoms ) ei = A.type[A.atoms ? A.atoms[slot] : slot];
-  const double* betaz = A.betaz_sort + size_t(ei) * K.idxz_max;
+  const real* betaz = A.betaz_sort + size_t(ei) * K.idxz_max;
   mbar_wait(&bar, 0);
   for(;;)
   {
@@ -830,35 +855,35 @@ __global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgs A, const 
     t = __shfl_sync(0xffffffffu, t, 0);
     if( t >= A.n_ytask ) break;
     const int4 task = A.ytask[t];                      // x = jju, y = first entry in zsort, z = entry count
-    double yr = 0.0, yi = 0.0;
+    real yr = real(0.0), yi = real(0.0);
     for(int e = task.y; e < task.y + task.z; e++)
     {
       const SnapZ q = A.zsort[e];
-      const double* cg = A.cglist + q.cgoff;
-      double zr = 0.0, zi = 0.0;
+      const real* cg = A.cglist + q.cgoff;
+      real zr = real(0.0), zi = real(0.0);
       int jju1 = K.idxu_block[q.j1] + (q.j1 + 1) * q.mb1min, jju2 = K.idxu_block[q.j2] + (q.j2 + 1) * q.mb2max, icgb = q.mb1min * (q.j2 + 1) + q.mb2max;
       for(int ib = 0; ib < q.nb; ib++)
       {
-        double sr = 0.0, si = 0.0;
-        const double2* u1p = U + size_t(jju1 + q.ma1min) * 32 + lane;
-        const double2* u2p = U + size_t(jju2 + q.ma2max) * 32 + lane;
+        real sr = real(0.0), si = real(0.0);
+        const real2* u1p = U + size_t(jju1 + q.ma1min) * 32 + lane;
+        const real2* u2p = U + size_t(jju2 + q.ma2max) * 32 + lane;
         int icga = q.ma1min * (q.j2 + 1) + q.ma2max;
         for(int ia = 0; ia < q.na; ia++)
         {
-          const double2 u1 = *u1p, u2 = *u2p;
-          const double c = __ldg(cg + icga);
+          const real2 u1 = *u1p, u2 = *u2p;
+          const real c = __ldg(cg + icga);
           sr += c * (u1.x * u2.x - u1.y * u2.y);
           si += c * (u1.x * u2.y + u1.y * u2.x);
           u1p += 32; u2p -= 32; icga += q.j2;
         }
-        const double c = __ldg(cg + icgb);
+        const real c = __ldg(cg + icgb);
         zr += c * sr; zi += c * si;
         jju1 += q.j1 + 1; jju2 -= q.j2 + 1; icgb += q.j2;
       }
-      const double bj = __ldg(betaz + e);
+      const real bj = __ldg(betaz + e);
       yr += bj * zr; yi += bj * zi;
     }
-    A.ybuf[blk + size_t(task.x) * 32 + lane] = make_double2(yr, yi);
+    A.ybuf[blk + size_t(task.x) * 32 + lane] = mk2<real>(yr, yi);
   }
 }
 
@@ -930,73 +955,73 @@ void xsb_snap_release(xsb_ctx* ctx)
   SnapDev* sd = g_snap_of(ctx);
   if( !sd ) return;
   struct { SnapDev* second; } itv{ sd }; auto* it = &itv;
-  it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
+  it->second->cglist32.release(); it->second->betaz32.release(); it->second->betaz_sort32.release(); it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
   it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->nbtab.release(); it->second->nbcnt.release(); it->second->clk.release();
   delete it->second; ctx->snap = nullptr;
 }
 
 constexpr unsigned SNAP_CHUNK = 65536;     // central atoms per pass of the split pipeline (Utot + Y staging: 2 x 285 x 16 B per atom)
 
-template<int TJ>
-static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgs A)
+template<class real, int TJ>
+static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapConstT<real>& KK)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR, MB = (TJ / 2) * (TJ / 2 + 1);
-  const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
-                    + size_t(NR) * 32 * 3 * sizeof(double) + 64;
+  const size_t smem = size_t(2 * S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
+                    + size_t(NR) * 32 * 3 * sizeof(real) + 64;
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
-  const size_t ysmem = size_t(S->K.idxu_max) * 32 * sizeof(double2);
+  const size_t ysmem = size_t(S->K.idxu_max) * 32 * sizeof(typename R2<real>::type);
   const bool fused = getenv("XSB_SNAP_FUSED") != nullptr;        // development switch: the single-kernel version
   auto setattr = [&](auto kern, size_t bytes) -> int { XSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); return XSB_OK; };
   int rc;
   if( fused )
   {
-    if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 0>, smem)) ) return rc; snap_force_kernel<TJ, true, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K); }
-    else     { if( (rc = setattr(snap_force_kernel<TJ, false, 0>, smem)) ) return rc; snap_force_kernel<TJ, false, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, S->K); }
+    if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 0>, smem)) ) return rc; snap_force_kernel<real, TJ, true, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, KK); }
+    else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 0>, smem)) ) return rc; snap_force_kernel<real, TJ, false, 0><<<A.n_atoms, NT, smem, ctx->stream>>>(A, X, KK); }
     XSB_LAUNCH_CHECK(ctx);
     return XSB_OK;
   }
   const unsigned chunk = std::min(A.n_atoms, SNAP_CHUNK);
   const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
   XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
-  A.ubuf = S->ubuf.p; A.ybuf = S->ybuf.p;
+  A.ubuf = reinterpret_cast<typename R2<real>::type*>(S->ubuf.p); A.ybuf = reinterpret_cast<typename R2<real>::type*>(S->ybuf.p);      // sized for double2, float2 uses half
   XSB_CUDA(ctx, S->nbtab.reserve(size_t(chunk) * 6 * SNAP_NN_MAX)); XSB_CUDA(ctx, S->nbcnt.reserve(chunk));
   A.nbtab = S->nbtab.p; A.nbcnt = S->nbcnt.p;
-  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
-                     + size_t(3 * NR) * 32 * sizeof(double) + 64;
+  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
+                     + size_t(3 * NR) * 32 * sizeof(real) + 64;
   // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
   // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)
   constexpr bool DIRSPLIT = TJ >= 7;
   const bool dircta = DIRSPLIT && getenv("XSB_SNAP_FKERNEL") == nullptr;      // A/B switch: XSB_SNAP_FKERNEL=1 -> the 15-warp CTA per atom
-  const size_t fdsmem = size_t(S->K.idxu_max) * sizeof(double2) + size_t(32) * SNAP_MBOX_STRIDE(2 * (MB ? MB : 1)) * sizeof(double2) + SNAP_NN_MAX * (5 * sizeof(double) + sizeof(unsigned))
-                      + size_t(NR) * 32 * sizeof(double) + 64;
-  if( dircta ) { if( xf ) { if( (rc = setattr(snap_fd_kernel<TJ, true>, fdsmem)) ) return rc; } else { if( (rc = setattr(snap_fd_kernel<TJ, false>, fdsmem)) ) return rc; } }
-  if( xf ) { if( (rc = setattr(snap_force_kernel<TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, true, 3>, smem)) ) return rc; }
-  else     { if( (rc = setattr(snap_force_kernel<TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<TJ, false, 3>, smem)) ) return rc; }
-  if( (rc = setattr(snap_y_kernel<TJ>, ysmem)) ) return rc;
+  const size_t fdsmem = size_t(S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
+                      + size_t(NR) * 32 * sizeof(real) + 64;
+  if( dircta ) { if( xf ) { if( (rc = setattr(snap_fd_kernel<real, TJ, true>, fdsmem)) ) return rc; } else { if( (rc = setattr(snap_fd_kernel<real, TJ, false>, fdsmem)) ) return rc; } }
+  if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, true, 3>, smem)) ) return rc; }
+  else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, false, 3>, smem)) ) return rc; }
+  if( (rc = setattr(snap_y_kernel<real, TJ>, ysmem)) ) return rc;
   for(unsigned base = 0; base < A.n_atoms; base += chunk)
   {
     const unsigned cnt = std::min(chunk, A.n_atoms - base);
     A.base = base;
-    if( xf ) snap_force_kernel<TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
-    else     snap_force_kernel<TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+    if( xf ) snap_force_kernel<real, TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
+    else     snap_force_kernel<real, TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
     XSB_LAUNCH_CHECK(ctx);
-    snap_y_kernel<TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, S->K);
+    snap_y_kernel<real, TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
     XSB_LAUNCH_CHECK(ctx);
     if( dircta )
     {
-      if( xf ) snap_fd_kernel<TJ, true><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, S->K);
-      else     snap_fd_kernel<TJ, false><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, S->K);
+      if( xf ) snap_fd_kernel<real, TJ, true><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
+      else     snap_fd_kernel<real, TJ, false><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
     }
     else if( DIRSPLIT )
     {
-      if( xf ) snap_f_kernel<TJ, true><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
-      else     snap_f_kernel<TJ, false><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, S->K);
+      if( xf ) snap_f_kernel<real, TJ, true><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, KK);
+      else     snap_f_kernel<real, TJ, false><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, KK);
     }
     else
     {
-      if( xf ) snap_force_kernel<TJ, true, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
-      else     snap_force_kernel<TJ, false, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, S->K);
+      if( xf ) snap_force_kernel<real, TJ, true, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
+      else     snap_force_kernel<real, TJ, false, 3><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
     }
     XSB_LAUNCH_CHECK(ctx);
   }
@@ -1073,6 +1098,21 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
   XSB_CUDA(ctx, cudaMemcpyAsync(S->zsort.p, zsort.data(), zsort.size() * sizeof(SnapZ), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz_sort.p, bsort.data(), bsort.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(S->ytask.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // XSB_FLAG_MIXED (the reference's SNAP_FP32_MATH build, snap_force.cu:25-29): the same tables rounded once from FP64
+    std::vector<float> c32(T.cglist.begin(), T.cglist.end()), b32(betaz.begin(), betaz.end()), bs32(bsort.begin(), bsort.end());
+    XSB_CUDA(ctx, S->cglist32.reserve(c32.size())); XSB_CUDA(ctx, S->betaz32.reserve(b32.size())); XSB_CUDA(ctx, S->betaz_sort32.reserve(bs32.size()));
+    XSB_CUDA(ctx, cudaMemcpyAsync(S->cglist32.p, c32.data(), c32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz32.p, b32.data(), b32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(S->betaz_sort32.p, bs32.data(), bs32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SnapConstT<float>& F = S->K32; F = SnapConstT<float>{};
+    for(int a = 0; a < 10; a++) for(int b = 0; b < 10; b++) F.rootpq[a][b] = float(K.rootpq[a][b]);
+    for(int j = 0; j < 10; j++) F.idxu_block[j] = K.idxu_block[j];
+    F.twojmax = K.twojmax; F.idxu_max = K.idxu_max; F.idxz_max = K.idxz_max; F.ncoeff = K.ncoeff; F.nelements = K.nelements; F.switchflag = K.switchflag; F.bzeroflag = K.bzeroflag;
+    F.rfac0 = float(K.rfac0); F.rmin0 = float(K.rmin0); F.rcutfac = float(K.rcutfac); F.wself = float(K.wself);
+    for(int e = 0; e < 8; e++) { F.radelem[e] = float(K.radelem[e]); F.wjelem[e] = float(K.wjelem[e]); F.beta0[e] = K.beta0[e]; F.bzero_e[e] = K.bzero_e[e]; }
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging vectors die here
+  }
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   S->set = true;
   return XSB_OK;
@@ -1090,21 +1130,40 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool ghost = flags & XSB_FLAG_GHOST, virial = flags & XSB_FLAG_VIRIAL;
   if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
-  SnapArgs A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, S->K.nelements > 1 ? ctx->type.p : nullptr, ctx->nbh_off.p, ctx->nbh_idx.p,
-              ghost ? nullptr : ctx->own_atoms.p, unsigned(ghost ? ctx->n : ctx->n_own), S->idxz.p, S->cglist.p, S->betaz.p,
-              ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr,
-              virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr, S->err.p, S->clocks ? S->clk.p : nullptr,
-              nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
-  if( A.n_atoms == 0 ) return XSB_OK;
+  const bool mixed = (flags & XSB_FLAG_MIXED) != 0;      // FP32 Wigner / Clebsch-Gordan arithmetic, FP64 positions, forces and energies
+  const unsigned n_atoms = unsigned(ghost ? ctx->n : ctx->n_own);
+  if( n_atoms == 0 ) return XSB_OK;
   int rc = XSB_ERR_UNSUPPORTED;
   ctx->prof_begin(XSB_PROF_SNAP);
-  switch( S->K.twojmax )
+  auto go = [&](auto Areal, const auto& KK) -> int
   {
-    case 1: rc = snap_launch<1>(ctx, S, A); break; case 2: rc = snap_launch<2>(ctx, S, A); break;
-    case 3: rc = snap_launch<3>(ctx, S, A); break; case 4: rc = snap_launch<4>(ctx, S, A); break;
-    case 5: rc = snap_launch<5>(ctx, S, A); break; case 6: rc = snap_launch<6>(ctx, S, A); break;
-    case 7: rc = snap_launch<7>(ctx, S, A); break; case 8: rc = snap_launch<8>(ctx, S, A); break;
-    default: break;
+    typedef decltype(Areal) ArgsT;
+    switch( S->K.twojmax )
+    {
+      case 1: return snap_launch<typename ArgsT::real_t, 1>(ctx, S, Areal, KK); case 2: return snap_launch<typename ArgsT::real_t, 2>(ctx, S, Areal, KK);
+      case 3: return snap_launch<typename ArgsT::real_t, 3>(ctx, S, Areal, KK); case 4: return snap_launch<typename ArgsT::real_t, 4>(ctx, S, Areal, KK);
+      case 5: return snap_launch<typename ArgsT::real_t, 5>(ctx, S, Areal, KK); case 6: return snap_launch<typename ArgsT::real_t, 6>(ctx, S, Areal, KK);
+      case 7: return snap_launch<typename ArgsT::real_t, 7>(ctx, S, Areal, KK); case 8: return snap_launch<typename ArgsT::real_t, 8>(ctx, S, Areal, KK);
+      default: return XSB_ERR_UNSUPPORTED;
+    }
+  };
+  const unsigned char* types = S->K.nelements > 1 ? ctx->type.p : nullptr;
+  const unsigned* sel = ghost ? nullptr : ctx->own_atoms.p;
+  double* epp = (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr;
+  double* virp = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+  if( mixed )
+  {
+    SnapArgsT<float> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
+                        S->idxz.p, S->cglist32.p, S->betaz32.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
+                        S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort32.p, S->ytask.p, S->n_ytask };
+    rc = go(A, S->K32);
+  }
+  else
+  {
+    SnapArgsT<double> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
+                         S->idxz.p, S->cglist.p, S->betaz.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
+                         S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
+    rc = go(A, S->K);
   }
   ctx->prof_end(XSB_PROF_SNAP);
   if( rc ) return rc;

@@ -220,7 +220,9 @@ int    xsb_snap_ncoeff(int twojmax);                        /* -1 if twojmax is 
 int    xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p);
 double xsb_snap_rcut_max(xsb_ctx* ctx);                     /* rcut_max output slot: 2 max(radelem) rcutfac     */
 /* f_i += fij, f_j -= fij (Newton-on like the reference, forces of ghost neighbours land on the ghost copies:   */
-/* follow with xsb_ghost_reduce_add of fx,fy,fz = update_force_energy_from_ghost); flags: GHOST, ENERGY, VIRIAL */
+/* follow with xsb_ghost_reduce_add of fx,fy,fz = update_force_energy_from_ghost); flags: GHOST, ENERGY, VIRIAL, MIXED */
+/* XSB_FLAG_MIXED: the reference's SNAP_FP32_MATH build (snap_force.cu:25-29): FP32 bispectrum arithmetic, FP64 positions,  */
+/* forces and energies (tolerance 1e-5).                                                                                   */
 /* At most 64 neighbours inside the SNAP cutoff per atom (the reference has no cap; BCC/FCC metals at the shipped     */
 /* rcutfac have 14-42): beyond that the call returns XSB_ERR_OVERFLOW (it syncs the stream to find out).              */
 int    xsb_snap_force(xsb_ctx* ctx, int flags);

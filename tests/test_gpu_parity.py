@@ -529,6 +529,33 @@ def test_pair_potentials_parity(name, virial):
         assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
 
 
+@pytest.mark.parametrize("twoj,nel", [(8, 1), (6, 2), (4, 1)])
+def test_snap_force_mixed_precision(twoj, nel):
+    """XSB_FLAG_MIXED on snap_force = the reference's SNAP_FP32_MATH build (src/potential/snap/snap_force.cu:25-29, deck
+    potentials/snap/multi_WBe_fp32.msp): FP32 Wigner / Clebsch-Gordan arithmetic, FP64 positions, forces and energies;
+    north-star bar for mixed mode 1e-5 of the field maximum against the FP64 oracle"""
+    O = oracle()
+    gs, S, args = snap_case(twoj, nel)
+    g = gs.oracle_grid()
+    nbh_dist = S.rcut_max() + 0.5
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh_dist, 1, True)
+    rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    O.snap_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, S, 2, rfx, rfy, rfz, rep, None)
+    ctx = make_ctx(gs)
+    ctx.snap_set(*args)
+    ctx.chunk_neighbors(nbh_dist)
+    ctx.zero_force_energy(ghost=True)
+    ctx.snap_force(xsb.FLAG_ENERGY | xsb.FLAG_MIXED)
+    fx, fy, fz, ep = [ctx.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+    fmax = max(np.abs(rfx).max(), np.abs(rfy).max(), np.abs(rfz).max())
+    ef = max(np.abs(a - b).max() for a, b in ((fx, rfx), (fy, rfy), (fz, rfz))) / fmax
+    own = ~gs.is_ghost
+    ee = np.abs(ep[own] - rep[own]).max() / np.abs(rep[own]).max()
+    print("snap mixed 2J=%d nel=%d: force err %.2e energy err %.2e" % (twoj, nel, ef, ee))
+    assert ef < 1e-5 and ee < 1e-5
+    assert ef > 1e-12                       # FP32 really ran
+
+
 def test_zbl_multi_force_parity_and_mixed_precision():
     """zbl_multi_force as in potentials/snap/multi_WBe.msp: one row per type pair, z from the species"""
     O = oracle()

@@ -23,3 +23,4 @@ for f in $O/${TAG}_tests.log $O/${TAG}_newtests.log $O/${TAG}_smoke.log; do [ -f
 for f in $O/${TAG}_microbench.txt; do [ -f $f ] && cat $f; done
 for f in $O/${TAG}_bench_reference.json $O/${TAG}_bench.json $O/${TAG}_bench100.json $O/${TAG}_bench_c1.json $O/${TAG}_bench_c3.json $O/${TAG}_bench_c5.json $O/${TAG}_bench_c4.json; do [ -f $f ] && (echo "== $f"; cut -c1-2500 $f); done
 tail -5 $O/${TAG}_bench*.err 2>/dev/null
+exit 0

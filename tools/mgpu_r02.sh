@@ -25,3 +25,4 @@ for line in open(sys.argv[1]):
     print(json.dumps({k:b.get(k) for k in ("value","ms_per_step","n_gpus")}), "e2e", (b.get("e2e") or {}).get("value"), "ranks", (d.get("ranks") or {}).get("timed_region_ms"), "rebuild", (d.get("ranks") or {}).get("rebuild_wall_s"), "ghost", (d.get("ranks") or {}).get("ghost_ms"), "move", (d.get("ranks") or {}).get("move_ms"))
 PY
 ); done
+exit 0
