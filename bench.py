@@ -389,6 +389,14 @@ def cpu_reference_run(W, ucells, steps, warmup, rebuild_every, cell=None):
     from oracle import oracle as O
     from helpers import GridSystem
     L, flags = O.lib_timed()
+    try:
+        return _cpu_reference_run(O, L, flags, nthr, W, ucells, steps, warmup, rebuild_every, cell)
+    finally:
+        O.lib_pinned()                 # the -march=native build must not leak into a process that also checks parity
+
+
+def _cpu_reference_run(O, L, flags, nthr, W, ucells, steps, warmup, rebuild_every, cell):
+    from helpers import GridSystem
     L.orc_set_num_threads(nthr)
     pos, typ0, box = lattice(W.structure, ucells, W.a, W.noise, seed=1)
     typ = W.types(len(pos), 1)

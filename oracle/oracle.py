@@ -124,6 +124,13 @@ def lib_timed():
     return L, flags
 
 
+def lib_pinned():
+    """back to the pinned build (bit-exact against the golden vectors) after lib_timed()"""
+    global _lib
+    _lib = None
+    return lib()
+
+
 def ref():
     """reference-math library; None when it was never built (no /root/reference and no prebuilt .so)."""
     global _ref
