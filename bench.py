@@ -476,7 +476,10 @@ def run_xsb(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    xsb.build()
+    if local == 0:
+        xsb.build()                       # one builder per node; the others wait (and build() itself is lock-protected)
+    if dist is not None:
+        dist.barrier()
     rd = rank_dims(world)
     coord = (rank % rd[0], (rank // rd[0]) % rd[1], rank // (rd[0] * rd[1]))
     pos, vel, typ, brick = brick_system(W, brick_cells(W, args, world), coord, seed=1 + rank)
@@ -716,7 +719,7 @@ def run_xsb(args):
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
                        "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
                        "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown, "ranks": per_rank,
-                       "clamped_at_assign": ctx.out_of_domain_count()}}
+                       "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport()}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_verlet_boundary", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
-    "xsb_verlet_boundary_async", "xsb_displ_poll",
+    "xsb_verlet_boundary_async", "xsb_displ_poll", "xsb_ghost_transport",
     "xsb_fields_upload_async", "xsb_fields_download_async", "xsb_copy_wait", "xsb_out_of_domain_count",
 ]
 
@@ -152,6 +152,7 @@ def load_library():
     L.xsb_num_own_particles.argtypes = [vp]
     L.xsb_cell_offsets_download.argtypes = [vp, vp]
     L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
+    L.xsb_ghost_transport.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.xsb_verlet_boundary_async.argtypes = [vp, i32, vp, dbl]
     L.xsb_displ_poll.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
     L.xsb_fields_upload_async.argtypes = [vp, i32, vp, vp, i32]
@@ -463,6 +464,11 @@ class Context:
         self._ck(self.L.xsb_thermo_state(self.h, m.size, _ptr(m), _ptr(out)), "xsb_thermo_state")
         return dict(virial=out[0:9].reshape(3, 3), ke_tensor=out[9:18].reshape(3, 3), momentum=out[18:21], kinetic_energy=out[21:24],
                     potential_energy=out[24], mass=out[25], particle_count=int(out[26]))
+
+    def ghost_transport(self):
+        buf = C.create_string_buffer(256)
+        self._ck(self.L.xsb_ghost_transport(self.h, buf, 256), "xsb_ghost_transport")
+        return buf.value.decode()
 
     def ghost_update(self, fields):
         self._ck(self.L.xsb_ghost_update(self.h, sum(1 << f for f in fields)), "xsb_ghost_update")

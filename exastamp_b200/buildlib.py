@@ -27,8 +27,24 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """compile + link when a source is newer than the library.  Several processes may call this at once (one rank per GPU
+    under torchrun): an exclusive file lock serialises them, the link goes to a temporary name and is renamed into place, so
+    no process ever dlopens a half-written file."""
     if not force and not stale():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if force or stale():             # somebody else may have built it while we waited
+                _build_locked(verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+    return LIB
+
+
+def _build_locked(verbose):
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
@@ -50,8 +66,10 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see exastamp_b200/build/nvcc.log")
-    link = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    tmp = LIB + ".%d.tmp" % os.getpid()
+    link = [nvcc(), "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(link)
+    os.replace(tmp, LIB)
     return LIB
 
 

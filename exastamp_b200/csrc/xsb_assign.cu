@@ -21,7 +21,16 @@ struct BinParams
   double ox, oy, oz, inv_cell, cell;   // corner of the first OWN cell, 1/cell_size
   int nx, ny, nz, gl;
   double box[3]; int wrap[3];          // periodic wrap (only when this rank spans the whole axis)
+  int sub_bits;                        // > 0: order the particles of a cell along a Morton curve of 2^sub_bits sub-cells per axis
 };
+
+// 3-D Morton code of (x,y,z) with b bits each (b <= 3)
+__device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z, int b)
+{
+  unsigned m = 0;
+  for(int i = 0; i < b; i++) m |= (((x >> i) & 1u) << (3 * i)) | (((y >> i) & 1u) << (3 * i + 1)) | (((z >> i) & 1u) << (3 * i + 2));
+  return m;
+}
 
 // cell of a coordinate along one axis.  A particle outside the own cells is clamped into the border cell (the
 // reference's move_particles keeps such "otb" particles aside, ext exaNBody): `how` gets 1 when that happened and 2
@@ -48,7 +57,16 @@ __global__ void bin_kernel(unsigned n, BinParams B, double* __restrict__ rx, dou
   const int cj = own_cell_coord(y, B.oy, B.cell, B.ny - 2 * B.gl, how) + B.gl;
   const int ck = own_cell_coord(z, B.oz, B.cell, B.nz - 2 * B.gl, how) + B.gl;
   const unsigned c = unsigned(ci) + unsigned(B.nx) * (unsigned(cj) + unsigned(B.ny) * unsigned(ck));
-  key[i] = c; val[i] = i;
+  unsigned k = c;
+  if( B.sub_bits > 0 )
+  {
+    // sub-cell of the particle inside its cell: neighbours that a cut-off sphere takes out of a cell then form a few
+    // contiguous index runs instead of a random subset, so the position gathers of the pair passes hit consecutive banks
+    const double S = double(1 << B.sub_bits);
+    auto sub = [&](double r, double o, int cc) { const double f = (r - o) / B.cell - double(cc - B.gl); return unsigned(min(max(int(f * S), 0), (1 << B.sub_bits) - 1)); };
+    k = (c << (3 * B.sub_bits)) | morton3(sub(x, B.ox, ci), sub(y, B.oy, cj), sub(z, B.oz, ck), B.sub_bits);
+  }
+  key[i] = k; val[i] = i;
   atomicAdd(counts + c, 1u);
   if( how ) atomicAdd(counts + B.nx * B.ny * B.nz + (how - 1), 1u);      // [ncells]: clamped, [ncells+1]: lost (> 1 cell outside)
 }
@@ -172,6 +190,8 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
   B.ox = g.origin[0] + g.ghost_layers * g.cell_size; B.oy = g.origin[1] + g.ghost_layers * g.cell_size; B.oz = g.origin[2] + g.ghost_layers * g.cell_size;
   B.nx = g.dims[0]; B.ny = g.dims[1]; B.nz = g.dims[2];
   for(int a = 0; a < 3; a++) { B.wrap[a] = wrap ? wrap[a] : 0; B.box[a] = box ? box[a] : 0.0; }
+  B.sub_bits = ctx->subcell_bits;
+  while( B.sub_bits > 0 && (uint64_t(nc) << (3 * B.sub_bits)) >= (1ull << 32) ) --B.sub_bits;      // the sort key is 32 bits
   XSB_CUDA(ctx, ctx->tmp32a.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32b.reserve(n + 16, XSB_GROW));
   XSB_CUDA(ctx, ctx->tmp32c.reserve(n + 16, XSB_GROW)); XSB_CUDA(ctx, ctx->tmp32d.reserve(std::max(n, nc) + 16, XSB_GROW));
   unsigned *key = ctx->tmp32a.p, *val = ctx->tmp32b.p, *key2 = ctx->tmp32c.p, *perm = ctx->tmp32d.p;
@@ -183,6 +203,7 @@ int xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry,
     bin_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, B, rx, ry, rz, key, val, counts);
     XSB_LAUNCH_CHECK(ctx);
     int end_bit = 1; while( (1ull << end_bit) < nc ) ++end_bit;
+    end_bit += 3 * B.sub_bits;
     size_t tmp = 0;
     XSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, key, key2, val, perm, int(n), 0, end_bit, ctx->stream));
     XSB_CUDA(ctx, ctx->scratch.reserve(tmp + 16));

@@ -1,5 +1,6 @@
 // xsb_core.cu -- context, grid + particle storage, zero_force_energy.
 #include "xsb_ctx.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cmath>
 #include <new>
@@ -266,6 +267,8 @@ int xsb_create(int device, xsb_ctx** out)
   ctx->sm_count = prop.multiProcessorCount;
   ctx->tile_deal = getenv("XSB_TILE_DEAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
   ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
+  ctx->exp_tpa = getenv("XSB_TPA") ? atoi(getenv("XSB_TPA")) : 0;
+  ctx->subcell_bits = getenv("XSB_SUBCELL_SORT") ? std::min(3, std::max(0, atoi(getenv("XSB_SUBCELL_SORT")))) : 0;
   XSB_CUDA(ctx, cudaSetDevice(device));
   XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   return XSB_OK;

@@ -942,7 +942,7 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     }
     else
     if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
-    else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
+    else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else if( ctx->exp_tpa == 8 ) XSB_EAM_TILE(false, false, false, 8, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
 #   undef XSB_EAM_TILE32
 #   undef XSB_EAM_TILE
     ctx->prof_end(XSB_PROF_EAM_FORCE);

@@ -75,7 +75,22 @@ struct GhostState
   // grid: ~2-3 ms of host time per rebuild at 8 ranks when it was recomputed)
   std::vector<GhostCell> plan_mine; std::vector< std::vector<GhostCell> > plan_to_peer;
   xsb_domain_desc plan_dom{}; int plan_gl = -1;
+
+  // ---- peer-memory transport (one node, NVLink / NVSwitch): every rank maps the receive block of every peer through CUDA
+  // IPC; the pack kernel of an exchange stores straight into the peers' receive buffers, a release flag per (source, buffer)
+  // tells the receiver's unpack kernel that a segment has landed.  No NCCL call, no staging copy, no host involvement.
+  bool p2p_tried = false, p2p_ok = false;
+  std::string p2p_why;                                  // why the NCCL transport is used instead
+  unsigned long long* p2p_block = nullptr;              // my block: [2][64] flags, then two receive buffers of p2p_cap words
+  size_t p2p_cap = 0;
+  std::vector<unsigned long long*> p2p_peer;            // peers' blocks mapped into this process (nullptr for myself)
+  unsigned long long p2p_epoch = 0;                     // exchanges done on this transport (identical on all ranks)
+  std::vector<unsigned> peer_send_off, peer_recv_off;   // [P][P+1] send_off / recv_off of every rank (all-gathered by the scheme)
+  bool p2p_fit = false;                                 // every rank's buffers hold the exchanges of the current scheme (decided collectively)
 };
+
+constexpr int P2P_FLAG_WORDS = 128;                     // [2 buffers][64 sources]
+
 
 static inline int block_start(int r, int G, int P) { return int((long long)r * G / P); }
 
@@ -160,10 +175,52 @@ __global__ void ghost_pack_kernel(unsigned n, FieldPtrs F, ShiftTab S, const uns
   }
 }
 
+struct P2PFlags { unsigned long long* flag[64]; };      // one address per peer: its flag word, or the base of my segment in its buffer
+
+// owner -> peer memory: like ghost_pack_kernel, but the segment base is an address inside the RECEIVER's buffer
+__global__ void ghost_pack_p2p_kernel(unsigned n, FieldPtrs F, ShiftTab S, const unsigned* __restrict__ idx, const unsigned char* __restrict__ code,
+                                      const unsigned* __restrict__ seg_of, const unsigned* __restrict__ seg_off, const P2PFlags dst_base,
+                                      bool from_ghost, unsigned me)
+{
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if( k >= n ) return;
+  const unsigned q = seg_of[k];
+  if( q == me ) return;
+  const unsigned s0 = seg_off[q], len = seg_off[q + 1] - s0, src = idx[k];
+  unsigned long long* seg = dst_base.flag[q];
+  for(int f = 0; f < F.nf; f++)
+  {
+    unsigned long long w = load_word(F.src[f], F.kind[f], src);
+    if( !from_ghost && F.kind[f] >= 1 && F.kind[f] <= 3 ) w = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)w) + S.s[code[k]][F.kind[f] - 1]);
+    seg[size_t(f) * len + (k - s0)] = w;       // 8-byte store over NVLink, consecutive k -> consecutive addresses
+  }
+}
+
+// after the pack kernel of this exchange: tell every peer that my segment of epoch `epoch` is complete in its buffer
+__global__ void ghost_signal_kernel(P2PFlags T, int P, int me, unsigned long long epoch)
+{
+  const int q = threadIdx.x;
+  if( q >= P || q == me || T.flag[q] == nullptr ) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(T.flag[q]), "l"(epoch) : "memory");
+}
+
+__device__ __forceinline__ void p2p_wait_all(const unsigned long long* __restrict__ flags, const unsigned* __restrict__ in_off, int P, int me, unsigned long long epoch)
+{
+  if( threadIdx.x < unsigned(P) && int(threadIdx.x) != me && in_off[threadIdx.x + 1] > in_off[threadIdx.x] )
+  {
+    unsigned long long v;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory"); } while( v < epoch );
+  }
+  __syncthreads();
+}
+
 // wire -> ghost (copy) or wire -> owner (add)
 __global__ void ghost_unpack_kernel(unsigned n, FieldPtrs F, const unsigned* __restrict__ idx, const unsigned* __restrict__ seg_of,
-                                    const unsigned* __restrict__ seg_off, const unsigned long long* __restrict__ buf, bool add, unsigned me)
+                                    const unsigned* __restrict__ seg_off, const unsigned long long* __restrict__ buf, bool add, unsigned me,
+                                    const unsigned long long* __restrict__ flags, int P, unsigned long long epoch)
 {
+  if( flags ) p2p_wait_all(flags, seg_off, P, int(me), epoch);      // peer-memory transport: every block waits for all incoming segments
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   if( k >= n ) return;
   if( seg_of[k] == me ) return;
@@ -257,6 +314,41 @@ static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
   const unsigned n_out = reverse ? G->n_recv : G->n_send, n_in = reverse ? G->n_send : G->n_recv;
   const std::vector<unsigned>& out_off = reverse ? G->recv_off : G->send_off;
   const std::vector<unsigned>& in_off = reverse ? G->send_off : G->recv_off;
+  const size_t words = size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16;
+  (void)words;
+  if( G->p2p_ok && G->p2p_fit )
+  {
+    // ---- peer-memory transport
+    const unsigned long long epoch = ++G->p2p_epoch;
+    const int b = int(epoch & 1ull);
+    const std::vector<unsigned>& peer_in = reverse ? G->peer_send_off : G->peer_recv_off;      // where my segment starts in peer q's list
+    P2PFlags D{}, T{};
+    for(int q = 0; q < P; q++)
+    {
+      D.flag[q] = nullptr; T.flag[q] = nullptr;
+      if( q == me || out_off[q + 1] == out_off[q] ) continue;
+      unsigned long long* blk = G->p2p_peer[q];
+      D.flag[q] = blk + P2P_FLAG_WORDS + size_t(b) * G->p2p_cap + size_t(F.nf) * peer_in[size_t(q) * (P + 1) + me];
+      T.flag[q] = blk + size_t(b) * 64 + me;
+    }
+    const unsigned n_out = reverse ? G->n_recv : G->n_send, n_in = reverse ? G->n_send : G->n_recv;
+    if( n_out )
+    {
+      ghost_pack_p2p_kernel<<<(n_out + 255) / 256, 256, 0, ctx->stream>>>(n_out, F, S, reverse ? G->recv_idx.p : G->send_idx.p, G->send_code.p,
+          reverse ? ctx->gseg_recv.p : ctx->gseg_send.p, reverse ? ctx->goff_recv.p : ctx->goff_send.p, D, reverse, unsigned(me));
+      XSB_LAUNCH_CHECK(ctx);
+    }
+    ghost_signal_kernel<<<1, 64, 0, ctx->stream>>>(T, P, me, epoch);
+    XSB_LAUNCH_CHECK(ctx);
+    if( n_in )
+    {
+      ghost_unpack_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(n_in, F, reverse ? G->send_idx.p : G->recv_idx.p, reverse ? ctx->gseg_send.p : ctx->gseg_recv.p,
+          reverse ? ctx->goff_send.p : ctx->goff_recv.p, G->p2p_block + P2P_FLAG_WORDS + size_t(b) * G->p2p_cap, reverse, unsigned(me),
+          G->p2p_block + size_t(b) * 64, P, epoch);
+      XSB_LAUNCH_CHECK(ctx);
+    }
+    return XSB_OK;
+  }
   XSB_CUDA(ctx, G->send_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, XSB_GROW_GHOST));
   XSB_CUDA(ctx, G->recv_buf.reserve(size_t(F.nf) * std::max(G->n_send, G->n_recv) + 16, XSB_GROW_GHOST));
   const unsigned* d_out_seg = reverse ? ctx->gseg_recv.p : ctx->gseg_send.p;   // seg_of arrays (built with the scheme)
@@ -281,9 +373,101 @@ static int exchange(xsb_ctx* ctx, uint32_t mask, bool reverse)
   XSB_NCCL(ctx, g_nccl.GroupEnd());
   if( n_in )
   {
-    ghost_unpack_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(n_in, F, reverse ? G->send_idx.p : G->recv_idx.p, d_in_seg, d_in_off, G->recv_buf.p, reverse, unsigned(me));
+    ghost_unpack_kernel<<<(n_in + 255) / 256, 256, 0, ctx->stream>>>(n_in, F, reverse ? G->send_idx.p : G->recv_idx.p, d_in_seg, d_in_off, G->recv_buf.p, reverse, unsigned(me), nullptr, P, 0ull);
     XSB_LAUNCH_CHECK(ctx);
   }
+  return XSB_OK;
+}
+
+// Peer-memory transport set-up.  First call: allocate my receive block, publish its CUDA IPC handle, map every peer's block.
+// Every call (= every ghost_comm_scheme): all-gather the segment offsets and the buffer capacity of every rank, so that a
+// sender knows where its segment starts in each receiver's buffer and ALL ranks take the same p2p-or-NCCL decision.
+static int p2p_prepare(xsb_ctx* ctx, GhostState* G)
+{
+  const int P = G->nranks, me = ctx->rank;
+  if( !G->p2p_tried )
+  {
+    G->p2p_tried = true;
+    int ok = 1;
+    if( getenv("XSB_GHOST_NCCL") ) { ok = 0; G->p2p_why = "XSB_GHOST_NCCL is set"; }
+    if( ok && P > 64 ) { ok = 0; G->p2p_why = "more than 64 ranks"; }
+    cudaIpcMemHandle_t mine{};
+    if( ok )
+    {
+      G->p2p_cap = std::max<size_t>(size_t(32) * std::max(G->n_send, G->n_recv), size_t(1) << 20);      // 16 words per atom, 2x head-room
+      const size_t bytes = (size_t(P2P_FLAG_WORDS) + 2 * G->p2p_cap) * sizeof(unsigned long long);
+      if( cudaMalloc((void**)&G->p2p_block, bytes) != cudaSuccess ) { ok = 0; G->p2p_why = "cudaMalloc of the receive block failed"; cudaGetLastError(); G->p2p_block = nullptr; }
+      else
+      {
+        cudaMemsetAsync(G->p2p_block, 0, P2P_FLAG_WORDS * sizeof(unsigned long long), ctx->stream);
+        if( cudaIpcGetMemHandle(&mine, G->p2p_block) != cudaSuccess ) { ok = 0; G->p2p_why = "cudaIpcGetMemHandle failed"; cudaGetLastError(); }
+      }
+    }
+    // handles (64 bytes) + my ok flag travel together: [P][72] bytes
+    const size_t rec = 72;
+    XSB_CUDA(ctx, ctx->scratch.reserve(rec * size_t(P + 1) + 64));
+    unsigned char h_rec[72] = {}; std::memcpy(h_rec, &mine, sizeof(mine)); h_rec[64] = (unsigned char)ok;
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, h_rec, rec, cudaMemcpyHostToDevice, ctx->stream));
+    XSB_NCCL(ctx, g_nccl.AllGather(ctx->scratch.p, ctx->scratch.p + rec, rec, NCCL_UINT8, ctx->comm, ctx->stream));
+    std::vector<unsigned char> all(rec * size_t(P));
+    XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->scratch.p + rec, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int q = 0; q < P; q++) if( !all[rec * size_t(q) + 64] ) { if( ok ) G->p2p_why = "a peer could not export its receive block"; ok = 0; }
+    G->p2p_peer.assign(size_t(P), nullptr);
+    int mapped_ok = ok;
+    if( ok )
+      for(int q = 0; q < P && mapped_ok; q++)
+      {
+        if( q == me ) continue;
+        cudaIpcMemHandle_t h; std::memcpy(&h, all.data() + rec * size_t(q), sizeof(h));
+        void* ptr = nullptr;
+        if( cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ) { mapped_ok = 0; G->p2p_why = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()); }
+        else G->p2p_peer[size_t(q)] = static_cast<unsigned long long*>(ptr);
+      }
+    // second round: everybody must have mapped everybody
+    h_rec[64] = (unsigned char)mapped_ok;
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, h_rec, rec, cudaMemcpyHostToDevice, ctx->stream));
+    XSB_NCCL(ctx, g_nccl.AllGather(ctx->scratch.p, ctx->scratch.p + rec, rec, NCCL_UINT8, ctx->comm, ctx->stream));
+    XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->scratch.p + rec, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int q = 0; q < P; q++) if( !all[rec * size_t(q) + 64] ) { if( mapped_ok ) G->p2p_why = "a peer could not map the receive blocks"; mapped_ok = 0; }
+    G->p2p_ok = mapped_ok != 0;
+    if( !G->p2p_ok )
+    {
+      for(auto& q : G->p2p_peer) if( q ) { cudaIpcCloseMemHandle(q); q = nullptr; }
+      if( G->p2p_block ) { cudaFree(G->p2p_block); G->p2p_block = nullptr; }
+    }
+  }
+  G->p2p_fit = false;
+  if( !G->p2p_ok ) return XSB_OK;
+  // per scheme: [P][2(P+1)+2] u32 = send_off, recv_off, capacity (lo, hi) of every rank
+  const size_t rec = size_t(2 * (P + 1) + 2);
+  std::vector<unsigned> mine(rec), all(rec * size_t(P));
+  for(int q = 0; q <= P; q++) { mine[size_t(q)] = G->send_off[size_t(q)]; mine[size_t(P + 1 + q)] = G->recv_off[size_t(q)]; }
+  mine[rec - 2] = unsigned(G->p2p_cap & 0xffffffffull); mine[rec - 1] = unsigned(G->p2p_cap >> 32);
+  XSB_CUDA(ctx, ctx->tmp32c.reserve(rec * size_t(P + 1) + 16));
+  XSB_CUDA(ctx, cudaMemcpyAsync(ctx->tmp32c.p, mine.data(), rec * 4, cudaMemcpyHostToDevice, ctx->stream));
+  XSB_NCCL(ctx, g_nccl.AllGather(ctx->tmp32c.p, ctx->tmp32c.p + rec, rec * 4, NCCL_UINT8, ctx->comm, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->tmp32c.p + rec, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  G->peer_send_off.assign(size_t(P) * (P + 1), 0u); G->peer_recv_off.assign(size_t(P) * (P + 1), 0u);
+  bool fit = true;
+  for(int q = 0; q < P; q++)
+  {
+    const unsigned* r = all.data() + rec * size_t(q);
+    for(int k = 0; k <= P; k++) { G->peer_send_off[size_t(q) * (P + 1) + k] = r[k]; G->peer_recv_off[size_t(q) * (P + 1) + k] = r[P + 1 + k]; }
+    const size_t cap = size_t(r[rec - 2]) | (size_t(r[rec - 1]) << 32);
+    if( size_t(16) * std::max(r[P], r[2 * P + 1]) + 16 > cap ) fit = false;        // 16 words per atom is the widest exchange
+  }
+  // my segment for peer q must be as long as what q expects from me
+  for(int q = 0; q < P; q++)
+  {
+    if( q == me ) continue;
+    const unsigned sl = G->send_off[size_t(q) + 1] - G->send_off[size_t(q)];
+    const unsigned ql = G->peer_recv_off[size_t(q) * (P + 1) + me + 1] - G->peer_recv_off[size_t(q) * (P + 1) + me];
+    XSB_REQUIRE(ctx, sl == ql, XSB_ERR_STATE, "ghost scheme: send / receive segment lengths of two ranks disagree");
+  }
+  G->p2p_fit = fit;
   return XSB_OK;
 }
 
@@ -297,6 +481,8 @@ void xsb_ghost_release(xsb_ctx* ctx)
   {
     ctx->ghost->send_idx.release(); ctx->ghost->send_code.release(); ctx->ghost->recv_idx.release();
     ctx->ghost->send_buf.release(); ctx->ghost->recv_buf.release();
+    for(auto& q : ctx->ghost->p2p_peer) if( q ) cudaIpcCloseMemHandle(q);
+    if( ctx->ghost->p2p_block ) cudaFree(ctx->ghost->p2p_block);
     delete ctx->ghost; ctx->ghost = nullptr;
   }
   ctx->old_cell_start.release(); ctx->tmp64.release(); ctx->tmp32a.release(); ctx->tmp32b.release(); ctx->tmp32c.release(); ctx->tmp32d.release(); ctx->gseg_send.release(); ctx->gseg_recv.release(); ctx->goff_send.release(); ctx->goff_recv.release(); ctx->backup.release();
@@ -654,9 +840,21 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom)
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_send.p, G->send_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->goff_recv.p, G->recv_off.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if( P > 1 ) { int rcp = p2p_prepare(ctx, G); if( rcp ) return rcp; }
   ctx->ghost_valid = true;
   // ghost_update_all_no_fv: every persistent field travels once
   return exchange(ctx, (1u << XSB_F_RX) | (1u << XSB_F_RY) | (1u << XSB_F_RZ) | (1u << XSB_F_VX) | (1u << XSB_F_VY) | (1u << XSB_F_VZ) | (1u << XSB_F_TYPE) | (1u << XSB_F_ID), false);
+}
+
+// which transport the exchanges of the current scheme use: "p2p" (peer memory over NVLink, CUDA IPC), "nccl: <why>", "self"
+int xsb_ghost_transport(xsb_ctx* ctx, char* out, size_t len)
+{
+  if( !ctx || !out || len == 0 ) return XSB_ERR_INVALID;
+  std::string t = "self";
+  if( ctx->ghost && ctx->ghost->nranks > 1 )
+    t = (ctx->ghost->p2p_ok && ctx->ghost->p2p_fit) ? "p2p" : ("nccl: " + (ctx->ghost->p2p_ok ? std::string("exchange larger than the peer buffers") : ctx->ghost->p2p_why));
+  std::strncpy(out, t.c_str(), len - 1); out[len - 1] = 0;
+  return XSB_OK;
 }
 
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask)

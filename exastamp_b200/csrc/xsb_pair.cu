@@ -249,7 +249,7 @@ static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int fl
     ctx->prof_begin(XSB_PROF_PAIR);
 #   define XSB_LJ_TILE(VIR, REAL, TPA_, NT_) { LJTileOp<MULTI, VIR, REAL> op{ rcut_max * rcut_max, prm, tfx, tfy, tfz, tep, tvir }; rc = launch_tile_pass<TPA_, NT_>(ctx, ghost, op, nullptr); }
     if( mixed ) { if( virial ) XSB_LJ_TILE(true, float, 8, 512) else XSB_LJ_TILE(false, float, 16, 1024) }
-    else        { if( virial ) XSB_LJ_TILE(true, double, 8, 512) else XSB_LJ_TILE(false, double, 16, 1024) }
+    else        { if( virial ) XSB_LJ_TILE(true, double, 8, 512) else if( ctx->exp_tpa == 8 ) XSB_LJ_TILE(false, double, 8, 1024) else XSB_LJ_TILE(false, double, 16, 1024) }
 #   undef XSB_LJ_TILE
     ctx->prof_end(XSB_PROF_PAIR);
     return rc;

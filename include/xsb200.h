@@ -251,6 +251,11 @@ int xsb_ghost_comm_scheme(xsb_ctx* ctx, const xsb_domain_desc* dom);
 /* brick at rank_coord, 6 int32 per ghost cell { ghost_cell, owner_rank, owner_cell, wrap_x, wrap_y, wrap_z }, sorted  */
 /* by owner rank; out6 may be NULL to query *count.  A rank's send list to peer q = the entries of q's plan it owns.   */
 int xsb_ghost_plan(const xsb_domain_desc* dom, int ghost_layers, const int32_t* rank_coord, int32_t* out6, uint64_t capacity, uint64_t* count);
+/* Transport of the exchanges below on more than one rank: by default every rank maps its peers' receive buffers (CUDA  */
+/* IPC, one node) and the pack kernel of an exchange stores straight into them over NVLink, a release flag per source    */
+/* tells the receiver's unpack kernel when a segment has landed (no NCCL call, no staging copy).  When the mapping is     */
+/* not possible (or XSB_GHOST_NCCL is set) the exchange is a grouped ncclSend/ncclRecv.  out: "p2p", "nccl: <why>", "self" */
+int xsb_ghost_transport(xsb_ctx* ctx, char* out, size_t len);
 /* ghost_update_r / ghost_update_opt: owner -> ghost copy of the fields in field_mask (bit = xsb_field)   */
 int xsb_ghost_update(xsb_ctx* ctx, uint32_t field_mask);
 /* update_force_energy_from_ghost / update_virial_force_energy_from_ghost (src/mpi/update_from_ghosts.cu:29,43):  */

@@ -125,6 +125,7 @@ def main():
     ctx.pair_force([0.0104 * EV, 3.4], rc_lj)
     collect("lj_moved", {"fx": xsb.F_FX, "ep": xsb.F_EP})
     results["dmax"] = dmax
+    results["transport"] = ctx.ghost_transport()
     # --- move_particles + migrate_cell_particles: a large random move sends many particles to other bricks (and across
     #     the periodic boundary); after rebin + ghost scheme + list rebuild the forces must match a fresh oracle run
     big = np.random.default_rng(200).uniform(-4.0, 4.0, pos.shape)
@@ -226,6 +227,7 @@ def main():
     e3a = np.zeros(len(pos)); e3a[gs3.src_index[o3]] = e3[o3]
     check("migrated", "fx", r3); check("migrated", "ep", e3a)
     print("  migration: %d particles changed rank" % sent_tot)
+    print("  ghost transport per rank: %s" % sorted(set(r["transport"] for r in gathered)))
     dm = max(r["dmax"] for r in gathered)
     assert all(abs(r["dmax"] - dm) < 1e-15 for r in gathered), "particle_displ_over: ranks disagree on the allreduced maximum"
     assert abs(dm - np.sqrt((d ** 2).sum(axis=1)).max()) < 1e-9
