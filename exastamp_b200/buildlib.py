@@ -6,9 +6,24 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxsb200.so")
-SOURCES = ["xsb_core.cu", "xsb_nbr.cu", "xsb_pair.cu", "xsb_eam.cu", "xsb_ghost.cu", "xsb_assign.cu", "xsb_snap.cu", "xsb_thermo.cu"]
+SOURCES = ["xsb_core.cu", "xsb_nbr.cu", "xsb_pair.cu", "xsb_eam.cu", "xsb_ghost.cu", "xsb_assign.cu", "xsb_snap.cu", "xsb_thermo.cu", "xsb_ncclwin.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def nccl_device_include():
+    """include directory of the NCCL >= 2.28 headers with the device API (nccl_device.h ships with the nvidia-nccl wheel that
+    torch loads); None when absent: the peer-memory ghost transport is then compiled out and ncclSend/ncclRecv is used"""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations or []):
+            inc = os.path.join(d, "include")
+            if os.path.exists(os.path.join(inc, "nccl_device.h")):
+                return inc
+    except Exception:
+        pass
+    return None
 
 
 def nvcc():
@@ -51,7 +66,10 @@ def _build_locked(verbose):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        extra = []
+        if s == "xsb_ncclwin.cu" and nccl_device_include():
+            extra = ["-DXSB_HAVE_NCCL_DEVICE=1", "-I" + nccl_device_include()]
+        cmd = [nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -14,6 +14,9 @@
 #include <dlfcn.h>
 #include <cub/device/device_radix_sort.cuh>
 
+extern "C" int xsb_internal_nccl_header_version();                                       // xsb_ncclwin.cu
+extern "C" int xsb_internal_win_peer_ptrs(void* win, int nranks, void** out_dev, cudaStream_t stream);
+
 namespace xsb
 {
 
@@ -32,6 +35,12 @@ struct NcclApi
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, ncclComm*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  // symmetric-memory windows (NCCL >= 2.27; optional: the peer-memory ghost transport needs them)
+  int (*GetVersion)(int*) = nullptr;
+  int (*MemAlloc)(void**, size_t) = nullptr;
+  int (*MemFree)(void*) = nullptr;
+  int (*CommWindowRegister)(ncclComm*, void*, size_t, void**, int) = nullptr;
+  int (*CommWindowDeregister)(ncclComm*, void*) = nullptr;
   bool ok = false;
 };
 static NcclApi g_nccl;
@@ -49,6 +58,11 @@ static bool nccl_load(std::string& why)
   XSB_SYM(GetUniqueId) XSB_SYM(CommInitRank) XSB_SYM(CommDestroy) XSB_SYM(GroupStart) XSB_SYM(GroupEnd) XSB_SYM(Send) XSB_SYM(Recv)
   XSB_SYM(AllReduce) XSB_SYM(AllGather) XSB_SYM(GetErrorString)
 # undef XSB_SYM
+  *(void**)(&g_nccl.GetVersion) = dlsym(h, "ncclGetVersion");
+  *(void**)(&g_nccl.MemAlloc) = dlsym(h, "ncclMemAlloc");
+  *(void**)(&g_nccl.MemFree) = dlsym(h, "ncclMemFree");
+  *(void**)(&g_nccl.CommWindowRegister) = dlsym(h, "ncclCommWindowRegister");
+  *(void**)(&g_nccl.CommWindowDeregister) = dlsym(h, "ncclCommWindowDeregister");
   g_nccl.ok = true;
   return true;
 }
@@ -76,12 +90,14 @@ struct GhostState
   std::vector<GhostCell> plan_mine; std::vector< std::vector<GhostCell> > plan_to_peer;
   xsb_domain_desc plan_dom{}; int plan_gl = -1;
 
-  // ---- peer-memory transport (one node, NVLink / NVSwitch): every rank maps the receive block of every peer through CUDA
-  // IPC; the pack kernel of an exchange stores straight into the peers' receive buffers, a release flag per (source, buffer)
-  // tells the receiver's unpack kernel that a segment has landed.  No NCCL call, no staging copy, no host involvement.
+  // ---- peer-memory transport (one node, NVLink / NVSwitch): the receive block of every rank is one NCCL symmetric window
+  // (ncclMemAlloc + ncclCommWindowRegister: CUDA VMM, only these blocks are peer-mapped); the pack kernel of an exchange
+  // stores straight into the peers' receive buffers, a release flag per (source, buffer) tells the receiver's unpack kernel
+  // that a segment has landed.  No NCCL call per exchange, no staging copy, no host involvement.
   bool p2p_tried = false, p2p_ok = false;
   std::string p2p_why;                                  // why the NCCL transport is used instead
   unsigned long long* p2p_block = nullptr;              // my block: [2][64] flags, then two receive buffers of p2p_cap words
+  void* p2p_win = nullptr;                              // ncclWindow_t of the block
   size_t p2p_cap = 0;
   std::vector<unsigned long long*> p2p_peer;            // peers' blocks mapped into this process (nullptr for myself)
   unsigned long long p2p_epoch = 0;                     // exchanges done on this transport (identical on all ranks)
@@ -388,54 +404,68 @@ static int p2p_prepare(xsb_ctx* ctx, GhostState* G)
   if( !G->p2p_tried )
   {
     G->p2p_tried = true;
+    // round 1: can everybody try, and how large must the (symmetric: same size everywhere) block be
     int ok = 1;
+    if( !getenv("XSB_GHOST_P2P") ) { ok = 0; G->p2p_why = "XSB_GHOST_P2P is not set (ncclSend/ncclRecv is the default transport)"; }
     if( getenv("XSB_GHOST_NCCL") ) { ok = 0; G->p2p_why = "XSB_GHOST_NCCL is set"; }
     if( ok && P > 64 ) { ok = 0; G->p2p_why = "more than 64 ranks"; }
-    cudaIpcMemHandle_t mine{};
+    int rtv = 0;
+    if( ok && (!g_nccl.GetVersion || !g_nccl.MemAlloc || !g_nccl.CommWindowRegister || g_nccl.GetVersion(&rtv) != 0) ) { ok = 0; G->p2p_why = "this NCCL has no symmetric-memory windows"; }
+    if( ok && (xsb_internal_nccl_header_version() == 0 || rtv != xsb_internal_nccl_header_version()) )
+    { ok = 0; G->p2p_why = "NCCL device-API headers of the build (" + std::to_string(xsb_internal_nccl_header_version()) + ") do not match the loaded library (" + std::to_string(rtv) + ")"; }
+    const size_t rec = 16;
+    XSB_CUDA(ctx, ctx->scratch.reserve(rec * size_t(P + 1) + 64));
+    unsigned long long h_rec[2] = { (unsigned long long)ok, (unsigned long long)std::max(G->n_send, G->n_recv) };
+    std::vector<unsigned long long> all(2 * size_t(P));
+    auto gather = [&]() -> int
+    {
+      XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, h_rec, rec, cudaMemcpyHostToDevice, ctx->stream));
+      XSB_NCCL(ctx, g_nccl.AllGather(ctx->scratch.p, ctx->scratch.p + rec, rec, NCCL_UINT8, ctx->comm, ctx->stream));
+      XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->scratch.p + rec, rec * size_t(P), cudaMemcpyDeviceToHost, ctx->stream));
+      XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      return XSB_OK;
+    };
+    int rcg = gather(); if( rcg ) return rcg;
+    unsigned long long need = 0;
+    for(int q = 0; q < P; q++) { if( !all[2 * size_t(q)] ) { if( ok ) G->p2p_why = "a peer cannot use symmetric-memory windows"; ok = 0; } need = std::max(need, all[2 * size_t(q) + 1]); }
     if( ok )
     {
-      G->p2p_cap = std::max<size_t>(size_t(32) * std::max(G->n_send, G->n_recv), size_t(1) << 20);      // 16 words per atom, 2x head-room
+      // round 2 (collective): allocate + register.  16 words per atom is the widest exchange; 2x head-room for later schemes
+      G->p2p_cap = std::max<size_t>(size_t(32) * size_t(need), size_t(1) << 20);
       const size_t bytes = (size_t(P2P_FLAG_WORDS) + 2 * G->p2p_cap) * sizeof(unsigned long long);
-      if( cudaMalloc((void**)&G->p2p_block, bytes) != cudaSuccess ) { ok = 0; G->p2p_why = "cudaMalloc of the receive block failed"; cudaGetLastError(); G->p2p_block = nullptr; }
-      else
+      void* blk = nullptr; int good = 1;
+      if( g_nccl.MemAlloc(&blk, bytes) != 0 || !blk ) { good = 0; G->p2p_why = "ncclMemAlloc failed"; }
+      G->p2p_block = static_cast<unsigned long long*>(blk);
+      if( good ) cudaMemsetAsync(G->p2p_block, 0, P2P_FLAG_WORDS * sizeof(unsigned long long), ctx->stream);
+      h_rec[0] = (unsigned long long)good;
+      if( (rcg = gather()) ) return rcg;
+      for(int q = 0; q < P; q++) if( !all[2 * size_t(q)] ) { if( good ) G->p2p_why = "a peer could not allocate its receive block"; good = 0; }
+      if( good )
       {
-        cudaMemsetAsync(G->p2p_block, 0, P2P_FLAG_WORDS * sizeof(unsigned long long), ctx->stream);
-        if( cudaIpcGetMemHandle(&mine, G->p2p_block) != cudaSuccess ) { ok = 0; G->p2p_why = "cudaIpcGetMemHandle failed"; cudaGetLastError(); }
+        if( g_nccl.CommWindowRegister(ctx->comm, G->p2p_block, bytes, &G->p2p_win, /*NCCL_WIN_COLL_SYMMETRIC*/ 0x01) != 0 || !G->p2p_win ) { good = 0; G->p2p_why = "ncclCommWindowRegister(NCCL_WIN_COLL_SYMMETRIC) failed"; G->p2p_win = nullptr; }
+        G->p2p_peer.assign(size_t(P), nullptr);
+        if( good )
+        {
+          void** d_ptrs = reinterpret_cast<void**>(ctx->scratch.p);
+          if( xsb_internal_win_peer_ptrs(G->p2p_win, P, d_ptrs, ctx->stream) != 0 ) { good = 0; G->p2p_why = "window address query failed"; }
+          std::vector<void*> hp(size_t(P), nullptr);
+          XSB_CUDA(ctx, cudaMemcpyAsync(hp.data(), d_ptrs, sizeof(void*) * size_t(P), cudaMemcpyDeviceToHost, ctx->stream));
+          XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+          for(int q = 0; q < P; q++) { G->p2p_peer[size_t(q)] = static_cast<unsigned long long*>(hp[size_t(q)]); if( !hp[size_t(q)] ) { good = 0; G->p2p_why = "window address of a peer is null"; } }
+        }
+        // round 3: everybody registered and got addresses
+        h_rec[0] = (unsigned long long)good;
+        if( (rcg = gather()) ) return rcg;
+        for(int q = 0; q < P; q++) if( !all[2 * size_t(q)] ) { if( good ) G->p2p_why = "a peer could not register its window"; good = 0; }
       }
+      ok = good;
     }
-    // handles (64 bytes) + my ok flag travel together: [P][72] bytes
-    const size_t rec = 72;
-    XSB_CUDA(ctx, ctx->scratch.reserve(rec * size_t(P + 1) + 64));
-    unsigned char h_rec[72] = {}; std::memcpy(h_rec, &mine, sizeof(mine)); h_rec[64] = (unsigned char)ok;
-    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, h_rec, rec, cudaMemcpyHostToDevice, ctx->stream));
-    XSB_NCCL(ctx, g_nccl.AllGather(ctx->scratch.p, ctx->scratch.p + rec, rec, NCCL_UINT8, ctx->comm, ctx->stream));
-    std::vector<unsigned char> all(rec * size_t(P));
-    XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->scratch.p + rec, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for(int q = 0; q < P; q++) if( !all[rec * size_t(q) + 64] ) { if( ok ) G->p2p_why = "a peer could not export its receive block"; ok = 0; }
-    G->p2p_peer.assign(size_t(P), nullptr);
-    int mapped_ok = ok;
-    if( ok )
-      for(int q = 0; q < P && mapped_ok; q++)
-      {
-        if( q == me ) continue;
-        cudaIpcMemHandle_t h; std::memcpy(&h, all.data() + rec * size_t(q), sizeof(h));
-        void* ptr = nullptr;
-        if( cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ) { mapped_ok = 0; G->p2p_why = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError()); }
-        else G->p2p_peer[size_t(q)] = static_cast<unsigned long long*>(ptr);
-      }
-    // second round: everybody must have mapped everybody
-    h_rec[64] = (unsigned char)mapped_ok;
-    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch.p, h_rec, rec, cudaMemcpyHostToDevice, ctx->stream));
-    XSB_NCCL(ctx, g_nccl.AllGather(ctx->scratch.p, ctx->scratch.p + rec, rec, NCCL_UINT8, ctx->comm, ctx->stream));
-    XSB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->scratch.p + rec, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for(int q = 0; q < P; q++) if( !all[rec * size_t(q) + 64] ) { if( mapped_ok ) G->p2p_why = "a peer could not map the receive blocks"; mapped_ok = 0; }
-    G->p2p_ok = mapped_ok != 0;
+    G->p2p_ok = ok != 0;
     if( !G->p2p_ok )
     {
-      for(auto& q : G->p2p_peer) if( q ) { cudaIpcCloseMemHandle(q); q = nullptr; }
-      if( G->p2p_block ) { cudaFree(G->p2p_block); G->p2p_block = nullptr; }
+      G->p2p_peer.clear();
+      if( G->p2p_win && g_nccl.CommWindowDeregister ) { g_nccl.CommWindowDeregister(ctx->comm, G->p2p_win); G->p2p_win = nullptr; }
+      if( G->p2p_block && g_nccl.MemFree ) { g_nccl.MemFree(G->p2p_block); G->p2p_block = nullptr; }
     }
   }
   G->p2p_fit = false;
@@ -481,8 +511,8 @@ void xsb_ghost_release(xsb_ctx* ctx)
   {
     ctx->ghost->send_idx.release(); ctx->ghost->send_code.release(); ctx->ghost->recv_idx.release();
     ctx->ghost->send_buf.release(); ctx->ghost->recv_buf.release();
-    for(auto& q : ctx->ghost->p2p_peer) if( q ) cudaIpcCloseMemHandle(q);
-    if( ctx->ghost->p2p_block ) cudaFree(ctx->ghost->p2p_block);
+    if( ctx->ghost->p2p_win && g_nccl.CommWindowDeregister && ctx->comm ) g_nccl.CommWindowDeregister(ctx->comm, ctx->ghost->p2p_win);
+    if( ctx->ghost->p2p_block && g_nccl.MemFree ) g_nccl.MemFree(ctx->ghost->p2p_block);
     delete ctx->ghost; ctx->ghost = nullptr;
   }
   ctx->old_cell_start.release(); ctx->tmp64.release(); ctx->tmp32a.release(); ctx->tmp32b.release(); ctx->tmp32c.release(); ctx->tmp32d.release(); ctx->gseg_send.release(); ctx->gseg_recv.release(); ctx->goff_send.release(); ctx->goff_recv.release(); ctx->backup.release();
