@@ -406,7 +406,6 @@ static int p2p_prepare(xsb_ctx* ctx, GhostState* G)
     G->p2p_tried = true;
     // round 1: can everybody try, and how large must the (symmetric: same size everywhere) block be
     int ok = 1;
-    if( !getenv("XSB_GHOST_P2P") ) { ok = 0; G->p2p_why = "XSB_GHOST_P2P is not set (ncclSend/ncclRecv is the default transport)"; }
     if( getenv("XSB_GHOST_NCCL") ) { ok = 0; G->p2p_why = "XSB_GHOST_NCCL is set"; }
     if( ok && P > 64 ) { ok = 0; G->p2p_why = "more than 64 ranks"; }
     int rtv = 0;
