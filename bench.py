@@ -64,7 +64,7 @@ class Workload:
     """what differs between the BASELINE configs: lattice, potential set-up, the force operators of a step, the CPU
     restatement of the same operators, and the roofline model of the dominant kernel."""
     name = ""; structure = "FCC"; a = 3.6; cells = 79; noise = 0.1; masses = [MASS_CU]; rcut = RCUT; skin = SKIN
-    baseline = ""; xform0 = None; cell_slack = 1.0; strong_total = None; dtype = "f64"
+    baseline = ""; xform0 = None; cell_slack = 1.0; strong_total = None; dtype = "f64"; inner_skin = 0.0
 
     def label(self, n_gpus, uc, scaling):
         raise NotImplementedError
@@ -133,6 +133,7 @@ class EamCu(Workload):
 
     def setup(self, ctx, xsb):
         ctx.eam_alloy_load(self.potential())
+        ctx.eam_inner_skin(self.inner_skin)
 
     def forces(self, ctx, xsb, flags=0, ef=0):
         ctx.zero_force_energy()
@@ -469,6 +470,7 @@ def run_xsb(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
     W = WORKLOADS[args.workload]()
+    W.inner_skin = args.inner_skin if W.xform0 is None else 0.0      # a cell matrix that changes every step re-filters every step anyway
     if W.strong_total and args.scaling != "strong":
         args.scaling = "strong"
     torch.cuda.set_device(local)
@@ -719,7 +721,8 @@ def run_xsb(args):
             "detail": {"atoms_per_gpu": int(n_own), "atoms_with_ghosts": int(ctx.n), "list_entries_per_atom": n_l, "max_list": int(max_nbh),
                        "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
                        "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown, "ranks": per_rank,
-                       "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport()}}
+                       "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport(),
+                       "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
@@ -738,6 +741,7 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-cells", type=int, default=0, help="unit cells per axis of the CPU arm's system (default: the full configuration for --impl reference)")
+    ap.add_argument("--inner-skin", type=float, default=0.12, help="inner skin (angstrom) of eam_alloy_force's in-range sub-list: 0 re-filters the neighbour list every step (xsb_eam_inner_skin)")
     ap.add_argument("--sync-displ", action="store_true", help="blocking particle_displ_over read-back every step (xsb_verlet_boundary) instead of the one-step-late check")
     ap.add_argument("--separate-integrator", action="store_true", help="five integrator operators as separate kernels instead of xsb_verlet_boundary")
     ap.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"], help="rewrite a 160 MiB buffer between timed steps; auto: on for c1, whose working set fits the 126 MB L2")

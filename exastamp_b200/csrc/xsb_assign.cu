@@ -394,7 +394,7 @@ int xsb_push_f_v_r(xsb_ctx* ctx, double dt)
 {
   XSB_ENTER(ctx);
   const unsigned n = unsigned(ctx->n_own); if( !n ) return XSB_OK;
-  ctx->pos_epoch++;
+  ctx->pos_epoch++; ctx->foreign_epoch++;      // no displacement accounting here: an inner-skin sub-list must be re-filtered
   XFormInv Xi; Xi.identity = ctx->grid.xform_is_identity; invert3(ctx->grid.xform, Xi.m);
   push_f_v_r_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->own_atoms.p, dt, 0.5 * dt * dt, Xi,
       ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->f64[XSB_F_VX].p, ctx->f64[XSB_F_VY].p, ctx->f64[XSB_F_VZ].p,
@@ -425,6 +425,12 @@ int xsb_force_to_accel(xsb_ctx* ctx, int n_types, const double* mass)
 }
 
 } // extern "C"
+
+namespace xsb
+{
+// inner-skin accounting (SubCtl): this step moved no atom (of any rank: s2 is all-reduced) further than sqrt(*s2)
+__global__ void sub_accum_kernel(SubCtl* ctl, const unsigned long long* s2) { ctl->acc += sqrt(__longlong_as_double((long long)*s2)); }
+}
 
 // the fused pass; out[0] = max |r - r_backup|^2, out[1] = max |step displacement|^2 (both zeroed here)
 static int verlet_boundary_launch(xsb_ctx* ctx, int n_types, const double* mass, double dt, unsigned long long* out)
@@ -469,6 +475,7 @@ int xsb_verlet_boundary_async(xsb_ctx* ctx, int n_types, const double* mass, dou
   unsigned long long* out = ctx->displ_dev.p + 2 * slot;
   int rc = verlet_boundary_launch(ctx, n_types, mass, dt, out); if( rc ) return rc;
   rc = xsb_internal_allreduce_max(ctx, reinterpret_cast<double*>(out), 2); if( rc ) return rc;      // squares are non-negative: MAX on the doubles
+  if( ctx->sub_ctl.p ) { xsb::sub_accum_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, out + 1); XSB_LAUNCH_CHECK(ctx); }
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->displ_host + 2 * slot, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaEventRecord(ctx->displ_ev[slot], ctx->stream));
   ctx->displ_seq++;
@@ -493,6 +500,12 @@ int xsb_verlet_boundary(xsb_ctx* ctx, int n_types, const double* mass, double dt
   XSB_REQUIRE(ctx, result != nullptr, XSB_ERR_INVALID, "null result");
   XSB_CUDA(ctx, ctx->scratch64.reserve(16));
   int rcl = verlet_boundary_launch(ctx, n_types, mass, dt, ctx->scratch64.p); if( rcl ) return rcl;
+  if( ctx->sub_ctl.p )
+  {
+    // blocking variant: only the displacement maximum is all-reduced (on the host, below), not the step displacement
+    if( ctx->nranks > 1 ) ctx->foreign_epoch++;
+    else { xsb::sub_accum_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, ctx->scratch64.p + 1); XSB_LAUNCH_CHECK(ctx); }
+  }
   double d2 = 0.0;
   XSB_CUDA(ctx, cudaMemcpyAsync(&d2, ctx->scratch64.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

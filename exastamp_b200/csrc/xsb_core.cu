@@ -137,7 +137,7 @@ int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
     if( !gv.is_ghost_cell(unsigned(c)) ) nown += off[c + 1] - off[c];
   }
   start[nc] = unsigned(off[nc]); ownp[nc] = unsigned(nown);
-  ctx->n = n; ctx->n_own = nown; ctx->pos_epoch++;
+  ctx->n = n; ctx->n_own = nown; ctx->pos_epoch++; ctx->foreign_epoch++;
   ctx->backup_n = 0xffffffffu;      // the own particles were re-ordered: a backup_r of the old order compares different atoms
   ctx->ghost_valid = false;         // exchange lists index the old layout (xsb_ghost_comm_scheme sets it again)
   XSB_CUDA(ctx, ctx->cell_start.reserve(2 * (nc + 1)));
@@ -268,6 +268,7 @@ int xsb_create(int device, xsb_ctx** out)
   ctx->tile_deal = getenv("XSB_TILE_DEAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
   ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
   ctx->exp_tpa = getenv("XSB_TPA") ? atoi(getenv("XSB_TPA")) : 0;
+  ctx->inner_skin = getenv("XSB_INNER_SKIN") ? std::max(0.0, atof(getenv("XSB_INNER_SKIN"))) : 0.0;
   ctx->subcell_bits = getenv("XSB_SUBCELL_SORT") ? std::min(3, std::max(0, atoi(getenv("XSB_SUBCELL_SORT")))) : 0;
   XSB_CUDA(ctx, cudaSetDevice(device));
   XSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -289,7 +290,7 @@ void xsb_destroy(xsb_ctx* ctx)
   ctx->eam.frho.release(); ctx->eam.rtab.release(); ctx->eam.fc.release(); ctx->eam.fc32.release(); ctx->tl_idx.release(); ctx->sub_idx.release(); ctx->sub_cnt.release(); ctx->pair_w.release(); ctx->move_stage.release(); ctx->move_stage8.release();
   xsb_ghost_release(ctx);
   xsb_snap_release(ctx);
-  ctx->stage_up.release(); ctx->stage_down.release(); ctx->displ_dev.release();
+  ctx->stage_up.release(); ctx->stage_down.release(); ctx->displ_dev.release(); ctx->sub_ctl.release();
   if( ctx->displ_host ) { cudaFreeHost(ctx->displ_host); for(cudaEvent_t e : ctx->displ_ev) if( e ) cudaEventDestroy(e); }
   if( ctx->copy_up ) { cudaStreamSynchronize(ctx->copy_up); cudaStreamDestroy(ctx->copy_up); }
   if( ctx->copy_down ) { cudaStreamSynchronize(ctx->copy_down); cudaStreamDestroy(ctx->copy_down); }
@@ -401,7 +402,7 @@ int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
   XSB_REQUIRE(ctx, g->cell_size > 0.0, XSB_ERR_INVALID, "cell_size must be > 0");
   const uint64_t nc = uint64_t(g->dims[0]) * uint64_t(g->dims[1]) * uint64_t(g->dims[2]);
   XSB_REQUIRE(ctx, nc < (1ull << 31), XSB_ERR_OVERFLOW, "too many cells");
-  ctx->grid = *g; ctx->pos_epoch++;
+  ctx->grid = *g; ctx->pos_epoch++; ctx->foreign_epoch++;
   ctx->ncells = nc;
   ctx->grid_set = true;
   ctx->nbh_built = false;
@@ -422,7 +423,7 @@ int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
     ident = ident && xform[i] == ((i % 4 == 0) ? 1.0 : 0.0);
   }
   ctx->grid.xform_is_identity = ident ? 1 : 0;
-  ctx->pos_epoch++;                 // physical distances changed: an in-range sub-list of the old cell is stale
+  ctx->pos_epoch++; ctx->foreign_epoch++;                 // physical distances changed: an in-range sub-list of the old cell is stale
   return XSB_OK;
 }
 
@@ -483,7 +484,7 @@ int xsb_field_upload(xsb_ctx* ctx, int field, const void* src)
   void* p = nullptr; size_t bytes = 0;
   int rc = field_ptr(ctx, field, &p, &bytes); if( rc ) return rc;
   if( bytes ) XSB_CUDA(ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_epoch++;
+  if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) { ctx->pos_epoch++; ctx->foreign_epoch++; }
   if( field == XSB_F_TYPE ) ctx->sub_pw_kind = 0;      // cached per-pair values depend on the neighbour's element
   return XSB_OK;
 }
@@ -535,7 +536,7 @@ int xsb_fields_upload_async(xsb_ctx* ctx, int nfields, const int* fields, const 
     for(int k = 0; k < nfields; k++) XSB_CUDA(ctx, cudaMemcpyAsync(F.p[k], ctx->stage_up.p + size_t(k) * pitch, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaEventRecord(ctx->ev_up_free, ctx->stream));
   ctx->up_pending = true;
-  for(int k = 0; k < nfields; k++) if( fields[k] == XSB_F_RX || fields[k] == XSB_F_RY || fields[k] == XSB_F_RZ ) { ctx->pos_epoch++; break; }
+  for(int k = 0; k < nfields; k++) if( fields[k] == XSB_F_RX || fields[k] == XSB_F_RY || fields[k] == XSB_F_RZ ) { ctx->pos_epoch++; ctx->foreign_epoch++; break; }
   return XSB_OK;
 }
 

@@ -65,6 +65,12 @@ struct GridView
   }
 };
 
+// Device-resident control block of the inner-skin sub-list (xsb_eam.cu): the integrator kernels add every step's largest
+// displacement (all-reduced over the ranks) to `acc`; the first EAM pass of a step re-filters the neighbour list (mode 0) when
+// acc exceeds half the inner skin or the host demands it, otherwise it only re-evaluates the entries of the sub-list it left
+// earlier (mode 1).  The decision never touches the host.
+struct SubCtl { double acc; int mode; int pad_; unsigned long long builds, reuses; };
+
 struct GhostState;
 struct XFormInv { double m[9]; int identity; };
 
@@ -133,6 +139,12 @@ struct xsb_ctx
   bool pair_cache_off = false;                // env XSB_NO_PAIR_CACHE=1: second pass re-evaluates instead (A/B profiling)
   uint64_t pos_epoch = 1, sub_epoch = 0;
   double sub_rcut = 0.0; bool sub_ghost = false;
+  // inner skin: the sub-list keeps pairs up to rcut + inner_skin so that it can serve several steps (see SubCtl)
+  double inner_skin = 0.0;                    // env XSB_INNER_SKIN (angstrom); 0 = filter the full list every step
+  xsb::DevBuf<xsb::SubCtl> sub_ctl;
+  uint64_t foreign_epoch = 1, sub_foreign = 0;   // position changes the displacement accounting does not see (uploads, re-binning, xform); value the sub-list was built under
+  double sub_list_rc = 0.0;                   // membership radius of the current sub-list
+  int sub_tables_id = 0, tables_id = 1, sub_pw_kind_built = 0;       // which table set / list build the sub-list belongs to
   bool pos_external = false;                  // a position device pointer was handed out: epochs cannot be trusted
   bool type_external = false;                 // same for the type bytes (the per-pair cache of a multi-element pass depends on them)
   bool sub_valid(double rcut, bool need_ghost) const

@@ -419,17 +419,20 @@ struct EamRhoTileOp
   // there) and, for a multi-element system, also rho'(r) of the central atom's element (rhoip).
   __device__ __forceinline__ auto pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
   {
+    // a sub-list with an inner skin also holds pairs just beyond rcut: they contribute nothing and are marked dead (NaN)
+    const bool live = d2 <= rcut2;
     const double r = d2 * rsqrt(d2);
     int m; double p; T.lookup(r, m, p);
     const int tb = MULTI ? int(B.t[j]) : 0;
     double2 k0, k1; T.knots(tab, tb, m, k0, k1);    // density table of the NEIGHBOUR's element
     double c3, c4; hermite_c(k0, k1, c3, c4);
-    A.rho += ((c3 * p + c4) * p + k0.y) * p + k0.x;
-    const double rhojp = PWO_ ? ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr : 0.0;
+    const double val = ((c3 * p + c4) * p + k0.y) * p + k0.x;
+    A.rho += live ? val : 0.0;
+    const double rhojp = !live ? pw_dead() : (PWO_ ? ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr : 0.0);
     if constexpr ( MULTI )
     {
       double rhoip = rhojp;
-      if( PWO_ && tb != A.ta ) { T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4); rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
+      if( PWO_ && live && tb != A.ta ) { T.knots(tab, A.ta, m, k0, k1); hermite_c(k0, k1, c3, c4); rhoip = ((3.0 * c3 * p + 2.0 * c4) * p + k0.y) * T.rdr; }
       return make_double2(rhojp, rhoip);
     }
     else return rhojp;
@@ -549,17 +552,18 @@ struct EamRhoTileOp32
   __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const { pair_d2(A, d2, j, B, tab); }
   __device__ __forceinline__ auto pair_d2(Acc& A, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
   {
+    const bool live = d2 <= rcut2;
     const float d2f = float(d2), r = d2f * rsqrtf(d2f);
     int m; float p; T.lookup(r, m, p);
     const int tb = MULTI ? int(B.t[j]) : 0;
     float4 k = T.knots(tab, tb, m);
     float c3, c4; hermite_c32(k, c3, c4);
-    A.rho += double(((c3 * p + c4) * p + k.y) * p + k.x);
-    const double rhojp = PWO_ ? double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr) : 0.0;
+    A.rho += live ? double(((c3 * p + c4) * p + k.y) * p + k.x) : 0.0;
+    const double rhojp = !live ? pw_dead() : (PWO_ ? double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr) : 0.0);
     if constexpr ( MULTI )
     {
       double rhoip = rhojp;
-      if( PWO_ && tb != A.ta ) { k = T.knots(tab, A.ta, m); hermite_c32(k, c3, c4); rhoip = double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr); }
+      if( PWO_ && live && tb != A.ta ) { k = T.knots(tab, A.ta, m); hermite_c32(k, c3, c4); rhoip = double(((3.0f * c3 * p + 2.0f * c4) * p + k.y) * T.rdr); }
       return make_double2(rhojp, rhoip);
     }
     else return rhojp;
@@ -624,6 +628,14 @@ struct EamForceTileOp32
   }
 };
 
+// first EAM pass of a step, device-side choice between re-filtering the neighbour list and re-evaluating the sub-list
+__global__ void sub_decide_kernel(SubCtl* ctl, int force_build, double half_skin)
+{
+  const bool build = force_build || !(ctl->acc <= half_skin);
+  ctl->mode = build ? 0 : 1;
+  if( build ) { ctl->acc = 0.0; ctl->builds++; } else ctl->reuses++;
+}
+
 template<bool HAS_W, bool TYPES>
 static EamFcView32 make_fc_view32(const xsb_ctx* ctx, int t0, int ntab, size_t queue_bytes)
 {
@@ -685,6 +697,7 @@ static void interpolate(int n, double delta, const double* f, double* s)
 } // namespace xsb
 
 using namespace xsb;
+#define COMMA ,
 
 extern "C" {
 
@@ -850,6 +863,31 @@ int xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t)
   E.nelements = t->nelements; E.nr = t->nr; E.nrho = t->nrho; E.rdr = t->rdr; E.rdrho = t->rdrho; E.rc = t->rc; E.rhomax = t->rhomax;
   E.conv_z2r = t->conversion_z2r; E.conv_frho = t->conversion_frho; E.set = true;
   ctx->sub_pw_kind = 0;     // a cached rho'(r) belongs to the previous tables
+  ctx->tables_id++;
+  return XSB_OK;
+}
+
+// Inner skin of the in-range sub-list of eam_alloy_force (angstrom, 0 = off; default from env XSB_INNER_SKIN): see SubCtl.
+int xsb_eam_inner_skin(xsb_ctx* ctx, double skin)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, skin >= 0.0 && skin < 1.0e3, XSB_ERR_INVALID, "inner skin must be >= 0");
+  if( skin != ctx->inner_skin ) { ctx->inner_skin = skin; ctx->sub_foreign = 0; }
+  return XSB_OK;
+}
+
+// how often the first EAM pass re-filtered the neighbour list / only re-evaluated its sub-list since the context was created
+int xsb_eam_sublist_stats(xsb_ctx* ctx, uint64_t* refiltered, uint64_t* reused)
+{
+  XSB_ENTER(ctx);
+  SubCtl h{};
+  if( ctx->sub_ctl.p )
+  {
+    XSB_CUDA(ctx, cudaMemcpyAsync(&h, ctx->sub_ctl.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if( refiltered ) *refiltered = h.builds;
+  if( reused ) *reused = h.reuses;
   return XSB_OK;
 }
 
@@ -883,16 +921,40 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     // the force pass of this step reuses rho'(r) of every in-range pair: cache it only when that pass can follow
     const bool pwo = !ctx->pair_cache_off;
     ctx->sub_pw_kind = 0;
+    // Inner skin (XSB_INNER_SKIN > 0, needs the per-pair cache): the sub-list keeps the pairs up to rcut + skin; while no atom
+    // has moved further than skin / 2 since it was filtered (SubCtl::acc, fed by the integrator kernels) the pass only
+    // re-evaluates its entries -- dense walk, no compaction, 147 instead of 196 candidates per atom at C2 -- and the
+    // device itself picks the launch that runs (the other one returns at once): no host read-back.
+    double skin = (pwo || mixed) ? std::min(ctx->inner_skin, ctx->nbh_dist - rcut) : 0.0;
+    if( !(skin > 0.0) ) skin = 0.0;
+    const double lrc2 = (rcut + skin) * (rcut + skin);
+    const int* mode = nullptr;
+    bool two = false;
+    if( skin > 0.0 )
+    {
+      if( !ctx->sub_ctl.p ) { XSB_CUDA(ctx, ctx->sub_ctl.reserve(1)); XSB_CUDA(ctx, cudaMemsetAsync(ctx->sub_ctl.p, 0, sizeof(SubCtl), ctx->stream)); ctx->sub_foreign = 0; }
+      const int kind_now = (multi ? 3 : 1) | (mixed ? 16 : 0);
+      const bool reusable = ctx->sub_foreign == ctx->foreign_epoch && ctx->sub_rcut == rcut && ctx->sub_list_rc == rcut + skin && ctx->sub_ghost == ghost &&
+                            ctx->sub_tables_id == ctx->tables_id && ctx->sub_pw_kind_built == kind_now && !ctx->pos_external && !(multi && ctx->type_external);
+      sub_decide_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, reusable ? 0 : 1, 0.5 * skin);
+      XSB_LAUNCH_CHECK(ctx);
+      mode = &ctx->sub_ctl.p->mode; two = true;
+    }
+#   define XSB_RHO_PASS(OP, ...) { OP op{ __VA_ARGS__ }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB, lrc2, mode, 0); \
+                                   if( rc == XSB_OK && two ) rc = launch_tile_pass<16, 1024>(ctx, ghost, op, nullptr, LIST_SUB_REWRITE, lrc2, mode, 1); }
     if( mixed )
     {
-      if( multi ) { EamRhoTileOp32<true, true>  op{ rc2, make_fc_view32<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
-      else        { EamRhoTileOp32<false, true> op{ rc2, make_fc_view32<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+      if( multi ) XSB_RHO_PASS(EamRhoTileOp32<true COMMA true>, rc2, make_fc_view32<false, true >(ctx, 0, E.nelements, qb), emb)
+      else        XSB_RHO_PASS(EamRhoTileOp32<false COMMA true>, rc2, make_fc_view32<false, false>(ctx, 0, E.nelements, qb), emb)
     }
     else
-    if( multi ) { if( pwo ) { EamRhoTileOp<true, true>   op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+    if( multi ) { if( pwo ) XSB_RHO_PASS(EamRhoTileOp<true COMMA true>, rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb)
                   else      { EamRhoTileOp<true, false>  op{ rc2, make_fc_view<false, true >(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
-    else        { if( pwo ) { EamRhoTileOp<false, true>  op{ rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); }
+    else        { if( pwo ) XSB_RHO_PASS(EamRhoTileOp<false COMMA true>, rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb)
                   else      { EamRhoTileOp<false, false> op{ rc2, make_fc_view<false, false>(ctx, 0, E.nelements, qb), emb }; rc = launch_tile_pass<32, 1024>(ctx, ghost, op, nullptr, LIST_FULL_WRITE_SUB); } }
+#   undef XSB_RHO_PASS
+    if( rc == XSB_OK && skin > 0.0 ) { ctx->sub_foreign = ctx->foreign_epoch; ctx->sub_list_rc = rcut + skin; ctx->sub_tables_id = ctx->tables_id; ctx->sub_pw_kind_built = (multi ? 3 : 1) | (mixed ? 16 : 0); }
+    else ctx->sub_foreign = 0;
     ctx->prof_end(XSB_PROF_EAM_RHO);
     if( rc ) return rc;
     ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = ghost;

@@ -233,8 +233,17 @@ struct TileList
   unsigned* __restrict__ sub_cnt;               // [n]
   double* __restrict__ pair_w;                  // per-pair cache aligned with sub_idx (xsb_tilepass.cuh), may be null
   size_t pw_plane;                              // offset (elements) of the second cached value of a pair, when an Op keeps two
+  // inner skin (xsb_eam.cu): the sub-list keeps the entries with d2 <= list_rc2 >= rcut2, so that it stays a superset of the
+  // in-range pairs for a few steps; entries beyond rcut2 carry a NaN in pair_w ("not live") and contribute nothing
+  double list_rc2;
+  // device-side mode switch: a launch whose want_mode differs from *mode returns at once (two launches per step, one runs)
+  const int* __restrict__ mode; int want_mode;
 };
 
-enum { LIST_FULL = 0, LIST_FULL_WRITE_SUB = 1, LIST_SUB = 2 };
+// LIST_SUB_REWRITE: walk the sub-list left by an earlier step (no compaction), re-evaluate every entry on the current
+// positions and rewrite its pair_w value (NaN when the pair is out of range now)
+enum { LIST_FULL = 0, LIST_FULL_WRITE_SUB = 1, LIST_SUB = 2, LIST_SUB_REWRITE = 3 };
+
+__device__ __forceinline__ double pw_dead() { return __longlong_as_double(0x7ff8000000000000ll); }      // quiet NaN: pair outside rcut
 
 } // namespace xsb

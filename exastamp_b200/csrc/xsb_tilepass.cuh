@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
                                                           const XForm X, const Op op)
 {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr bool QUEUE = Op::D2_ONLY && TPA == 32 && LMODE != LIST_SUB;
+  if( L.mode != nullptr && *L.mode != L.want_mode ) return;      // the other launch of this step serves the current mode
+  constexpr bool QUEUE = Op::D2_ONLY && TPA == 32 && (LMODE == LIST_FULL_WRITE_SUB || LMODE == LIST_FULL);
+  constexpr bool REWRITE = LMODE == LIST_SUB_REWRITE;
   constexpr bool PWO = op_pw_out<Op>::value && QUEUE && LMODE == LIST_FULL_WRITE_SUB;
   constexpr bool PWI = op_pw_in<Op>::value && LMODE == LIST_SUB;
   constexpr unsigned NWC = NT / 32 - 1;          // consumer warps; the last warp is the TMA producer
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
       {
         const unsigned aw = a_begin + k + gsel;
         e0w = L.off[aw];
-        lenw = LMODE == LIST_SUB ? L.sub_cnt[aw] : unsigned(L.off[aw + 1] - e0w);
+        lenw = (LMODE == LIST_SUB || REWRITE) ? L.sub_cnt[aw] : unsigned(L.off[aw + 1] - e0w);
       }
     };
     unsigned k0 = grab();
@@ -124,7 +126,25 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
         const double xa = B.x[sa], ya = B.y[sa], za = B.z[sa];
         op.start(acc, a, sa, B, smem);
         // per-atom list window [e0, e0 + len): 64-bit base pointers once, 32-bit indices inside the loops
-        if constexpr ( LMODE == LIST_SUB )
+        if constexpr ( REWRITE )
+        {
+          // sub-list of an earlier step (a superset of the in-range pairs while the inner skin holds): every entry is
+          // re-evaluated on the current positions and its cached value rewritten (pair_d2 returns NaN for a dead pair)
+          const unsigned short* __restrict__ sp = L.sub_idx + e0;
+          double* __restrict__ pwo = L.pair_w + e0;
+          unsigned e = sub;
+          unsigned jn = e < len ? __ldcs(sp + e) : 0u;
+          while( e < len )
+          {
+            const unsigned j = jn, ec = e;
+            e += TPA;
+            if( e < len ) jn = __ldcs(sp + e);
+            double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
+            apply_xform<XFORM>(X, dx, dy, dz);
+            pw_store(pwo, L.pw_plane, ec, op.pair_d2(acc, dx * dx + dy * dy + dz * dz, j, B, smem));
+          }
+        }
+        else if constexpr ( LMODE == LIST_SUB )
         {
           // dense: every entry is in range (filtered by the pass that wrote the sub-list on these positions)
           const unsigned short* __restrict__ sp = L.sub_idx + e0;
@@ -142,8 +162,9 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
             if( e < len ) { jn = __ldcs(sp + e); if( PWI ) pvn = __ldcs(pwp + e); if( PW2 ) pvn2 = __ldcs(pwp + L.pw_plane + e); }   // next entry in flight while this pair is evaluated
             double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
             apply_xform<XFORM>(X, dx, dy, dz);
-            if constexpr ( PWI ) op.pair_pw(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem, pv, pv2);
-            else                 op.pair(acc, dx, dy, dz, dx * dx + dy * dy + dz * dz, j, B, smem);
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if constexpr ( PWI ) { if( pv == pv ) op.pair_pw(acc, dx, dy, dz, d2, j, B, smem, pv, pv2); }      // NaN = dead pair (inner skin)
+            else                 { if( d2 <= op.rcut2 ) op.pair(acc, dx, dy, dz, d2, j, B, smem); }
           }
         }
         else if constexpr ( QUEUE )
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
           // masked out of the ballot
           unsigned xad = smem_u32(B.x), yad = xad + G.s_cap * 8u, zad = xad + G.s_cap * 16u;
           unsigned qda = smem_u32(qd), qja = smem_u32(qj);
-          double rc2 = op.rcut2;
+          double rc2 = LMODE == LIST_FULL_WRITE_SUB ? L.list_rc2 : op.rcut2;      // membership of the sub-list (>= the Op's own cut-off)
           // keep the loop invariants in registers (ptxas otherwise re-reads s_cap / rcut2 from the constant bank and rebuilds
           // the three field bases every step)
           asm volatile("" : "+r"(xad), "+r"(yad), "+r"(zad), "+r"(qda), "+r"(qja), "+d"(rc2));
@@ -235,8 +256,8 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
               double dx = B.x[j] - xa, dy = B.y[j] - ya, dz = B.z[j] - za;
               apply_xform<XFORM>(X, dx, dy, dz);
               const double d2 = dx * dx + dy * dy + dz * dz;
-              in = d2 <= op.rcut2;
-              if( in ) op.pair(acc, dx, dy, dz, d2, j, B, smem);
+              in = d2 <= (LMODE == LIST_FULL_WRITE_SUB ? L.list_rc2 : op.rcut2);
+              if( d2 <= op.rcut2 ) op.pair(acc, dx, dy, dz, d2, j, B, smem);
             }
             if( LMODE == LIST_FULL_WRITE_SUB )
             {
@@ -259,11 +280,12 @@ __global__ void __launch_bounds__(NT, 1) tile_pass_kernel(const TileGeom G, cons
 
 // lmode: LIST_FULL / LIST_FULL_WRITE_SUB / LIST_SUB
 template<int TPA, int NT, class Op>
-static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double* w, int lmode = LIST_FULL)
+static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double* w, int lmode = LIST_FULL,
+                            double list_rc2 = 0.0, const int* mode = nullptr, int want_mode = 0)
 {
   TileGeom G = make_tile_geom(ctx, ghost);
   if( G.ntiles == 0 ) return XSB_OK;
-  const bool queue = Op::D2_ONLY && TPA == 32 && lmode != LIST_SUB;
+  const bool queue = Op::D2_ONLY && TPA == 32 && (lmode == LIST_FULL || lmode == LIST_FULL_WRITE_SUB);
   const size_t qb = queue ? tile_queue_bytes<NT>() : 0;
   G.nbuf = tile_smem_bytes<Op::HAS_W, Op::TYPES>(G.s_cap, op.table_bytes(), qb, 3) <= TILE_SMEM_MAX ? 3 : 2;
   const size_t smem = tile_smem_bytes<Op::HAS_W, Op::TYPES>(G.s_cap, op.table_bytes(), qb, G.nbuf);
@@ -272,12 +294,13 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
   if( lmode != LIST_FULL )
   {
     XSB_CUDA(ctx, ctx->sub_idx.reserve(size_t(ctx->nbh_total) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-    XSB_CUDA(ctx, ctx->sub_cnt.reserve(size_t(ctx->n) + 1, 1.02));
+    XSB_CUDA(ctx, ctx->sub_cnt.reserve(size_t(ctx->n) + 1, XSB_GROW));
   }
   const size_t pw_plane = (size_t(ctx->nbh_total) + 63) & ~size_t(31);      // second cached value of a pair lives one plane further
   if( op_pw_out<Op>::value && queue && lmode == LIST_FULL_WRITE_SUB )
     XSB_CUDA(ctx, ctx->pair_w.reserve(pw_plane * size_t(op_pw_n<Op>::value) + 32, ctx->nbh_cfg.stream_prealloc_factor));
-  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p, ctx->pair_w.p, pw_plane };
+  const TileList L{ ctx->nbh_off.p, ctx->tl_idx.p, ctx->sub_idx.p, ctx->sub_cnt.p, ctx->pair_w.p, pw_plane,
+                    list_rc2 > op.rcut2 ? list_rc2 : op.rcut2, mode, want_mode };
   const XForm X = make_xform(ctx->grid);
   const bool xf = !ctx->grid.xform_is_identity;
   auto go = [&](auto kern) -> int
@@ -298,6 +321,15 @@ static int launch_tile_pass(xsb_ctx* ctx, bool ghost, const Op& op, const double
   }
   else
   {
+    if constexpr ( Op::D2_ONLY && op_pw_out<Op>::value && TPA != 32 )
+    {
+      if( lmode == LIST_SUB_REWRITE )
+      {
+        XSB_REQUIRE(ctx, ctx->pair_w.p != nullptr, XSB_ERR_STATE, "tile pass: sub-list re-evaluation without a per-pair cache");
+        return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB_REWRITE, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB_REWRITE, Op>);
+      }
+    }
+    XSB_REQUIRE(ctx, lmode != LIST_SUB_REWRITE, XSB_ERR_STATE, "tile pass: this operator cannot re-evaluate a sub-list");
     if( lmode == LIST_SUB )                 return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_SUB, Op>);
     if( lmode == LIST_FULL_WRITE_SUB )      return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL_WRITE_SUB, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL_WRITE_SUB, Op>);
     return xf ? go(tile_pass_kernel<TPA, NT, true, LIST_FULL, Op>) : go(tile_pass_kernel<TPA, NT, false, LIST_FULL, Op>);

@@ -200,6 +200,14 @@ int  xsb_eam_alloy_read(const char* path, xsb_eam_alloy_tables* out, char* names
 void xsb_eam_alloy_free(xsb_eam_alloy_tables* t);
 int  xsb_eam_alloy_set(xsb_ctx* ctx, const xsb_eam_alloy_tables* t);   /* uploads tables (host pointers)  */
 int  xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags);
+/* Inner skin of the rho phase (angstrom; 0 = off, the default unless XSB_INNER_SKIN is set).  The rho phase leaves the   */
+/* in-range sub-list of the step for the force phase; with an inner skin that list keeps the pairs up to rcut + skin and   */
+/* serves the rho phases of the following steps too (dense re-evaluation instead of re-filtering the whole neighbour list) */
+/* for as long as no atom has moved further than skin / 2 -- accounted on the device by xsb_verlet_boundary[_async]; any   */
+/* other way of moving particles (uploads, xsb_push_f_v_r, re-binning, a new xform) makes the next rho phase re-filter.   */
+/* Results are those of the plain path (same pairs, same arithmetic per pair; summation order differs).                   */
+int  xsb_eam_inner_skin(xsb_ctx* ctx, double skin);
+int  xsb_eam_sublist_stats(xsb_ctx* ctx, uint64_t* refiltered, uint64_t* reused);
 
 /* ---------------------------------------------------------------------------------------------------- */
 /* a9  snap_force (src/potential/snap/snap_force.cu:26-36 -> ext md::SnapForceGeneric; call sequence            */

@@ -837,6 +837,74 @@ def test_verlet_boundary_equals_the_five_separate_operators(triclinic):
         assert np.abs(u - v).max() <= 4e-16 * max(np.abs(u).max(), 1e-300)
 
 
+@pytest.mark.parametrize("two_species,mixed", [(False, False), (True, False), (False, True)])
+def test_eam_inner_skin_reuse_matches_plain_path_and_oracle(tmp_path, two_species, mixed):
+    """xsb_eam_inner_skin: the rho phase re-evaluates the sub-list of an earlier step instead of re-filtering the neighbour
+    list while the device-side displacement budget holds.  An NVE run with the skin must give the plain path's forces at
+    every step (same pairs; summation order differs), really reuse the list, re-filter when an atom jumps, and match the
+    oracle on the final positions."""
+    O = oracle()
+    path = str(tmp_path / "s.eam.alloy")
+    els = [SC_CU, SC_XX] if two_species else [SC_CU]
+    write_setfl(path, els, nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    pos, typ, box = lattice("FCC", 6, 3.615, 0.05, seed=21, types=[0, 1, 1, 0] if two_species else None)
+    vel = np.random.default_rng(3).normal(0.0, 3.0, pos.shape)
+    masses, dt, rcut, nbh = [63.5, 27.0], 1.0e-3, 6.0, 7.0
+    fl = xsb.FLAG_MIXED if mixed else 0
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    ctxs = []
+    for skin in (0.0, 0.2):
+        c = assigned_ctx(pos, typ, box, 3.615 * 2, 1, vel)
+        c.eam_alloy_load(path); c.eam_inner_skin(skin)
+        c.chunk_neighbors(nbh); c.backup_r()
+        ctxs.append(c)
+
+    def forces(c):
+        c.zero_force_energy()
+        c.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_EFLAG, fl)
+        c.ghost_update([xsb.F_RHO_DEMB])
+        c.eam_alloy_force(rcut, xsb.EAM_FORCE | xsb.EAM_EFLAG, fl)
+        return [c.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+
+    tol = 1e-5 if mixed else 1e-12
+    for step in range(7):
+        out = [forces(c) for c in ctxs]
+        for a, b in zip(*out):
+            assert rel_err(a, b) < tol, "step %d" % step
+        if step == 4:
+            # every atom drifts 0.3 ang per step from now on (more than half the inner skin) through the accounted path:
+            # the following rho phases must re-filter (relative positions, hence forces, are unaffected by the drift)
+            for c in ctxs:
+                c.upload(xsb.F_VX, c.download(xsb.F_VX) + 300.0)
+        for c in ctxs:
+            c.verlet_boundary_async(masses, dt)
+            c.ghost_update(POS)
+    built, reused = ctxs[1].eam_sublist_stats()
+    print("inner skin: %d re-filtered, %d reused" % (built, reused))
+    assert reused >= 3 and built >= 2
+    assert ctxs[0].eam_sublist_stats() == (0, 0)
+    # final positions against the oracle (ghost images included: one ghost layer, rho_dEmb copied owner -> ghost)
+    c = ctxs[1]
+    out = forces(c)
+    off = c.cell_offsets()
+    rx, ry, rz, tt = c.download(xsb.F_RX), c.download(xsb.F_RY), c.download(xsb.F_RZ), c.download(xsb.F_TYPE)
+    dims = np.array(c.grid.dims[:]); cell = c.grid.cell_size
+    g = O.make_grid(dims, 1, cell, [-cell] * 3)
+    nb = O.Neighbors.build(g, off, rx, ry, rz, nbh, 1, True)
+    n = len(rx)
+    rfx, rfy, rfz, rep, emb = [np.zeros(n) for _ in range(5)]
+    eam = O.EamAlloy(path)
+    O.eam_alloy(g, off, rx, ry, rz, tt, nb, eam, rcut, 1 | 2 | 16, rfx, rfy, rfz, rep, None, emb)
+    demb_gpu = c.download(xsb.F_RHO_DEMB)                        # already ghost-updated by forces()
+    cells = np.arange(len(off) - 1); ci = cells % dims[0]; cj = (cells // dims[0]) % dims[1]; ck = cells // (dims[0] * dims[1])
+    own_cell = (ci >= 1) & (ci < dims[0] - 1) & (cj >= 1) & (cj < dims[1] - 1) & (ck >= 1) & (ck < dims[2] - 1)
+    own = np.repeat(own_cell, np.diff(off).astype(np.int64))
+    assert rel_err(demb_gpu[own], emb[own]) < (1e-5 if mixed else TOL64)
+    O.eam_alloy(g, off, rx, ry, rz, tt, nb, eam, rcut, 8 | 16, rfx, rfy, rfz, rep, None, demb_gpu.copy())
+    for a, b in zip(out, (rfx, rfy, rfz, rep)):
+        assert rel_err(a[own], b[own]) < (1e-5 if mixed else TOL64)
+
+
 def test_verlet_boundary_async_ring_and_own_atom_transfers():
     """xsb_verlet_boundary_async + xsb_displ_poll (no host read-back) give the blocking variant's maxima, one call late on
     request; xsb_fields_upload_async / _download_async move the own atoms only and keep stream order"""
