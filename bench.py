@@ -628,6 +628,8 @@ def run_xsb(args):
     e2e = None
     if not args.no_e2e:
         outf = W.e2e_fields(xsb)
+        if hasattr(ctx, "eam_inner_skin"):
+            ctx.eam_inner_skin(0.0)       # positions arrive from the host every step: no displacement budget to reuse a sub-list under
         pin_r = [torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in range(3)]
         pin_f = [[torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in outf] for _ in range(2)]   # results of even / odd steps
         ctx.fields_download_async(POS, [t.data_ptr() for t in pin_r]); ctx.copy_wait()
