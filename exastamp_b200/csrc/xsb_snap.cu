@@ -26,7 +26,9 @@
 namespace xsb
 {
 
-constexpr int SNAP_NN_MAX = 64;      // in-range neighbours of one atom held in shared memory (2 batches of 32)
+constexpr int SNAP_NN_MAX = 64;      // in-range neighbours of one atom held in shared memory at a time (2 sweeps of 32); atoms with
+                                     // more are processed in batches (Utot, dE/dr and the forces are sums over neighbours)
+constexpr int SNAP_NN_TAB = 192;     // in-range neighbours per atom the Utot kernel can hand to the force kernel of the split pipeline
 
 struct SnapZ { unsigned char j1, j2, j, ma1min, ma2max, na, mb1min, mb2max, nb, pad; unsigned short jju; int cgoff; };   // 16 B
 
@@ -431,54 +433,77 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = A.ubuf[soa + size_t(k) * 32]; ylist[k] = A.ybuf[soa + size_t(k) * 32]; }
   }
 
-  // ---- neighbour filter (warp 0, ballot compaction keeps the list order): rsq < cutsq_ij && rsq > 1e-20
-  if( mb == 0 )
+  // ---- neighbour filter (warp 0, ballot compaction keeps the list order): rsq < cutsq_ij && rsq > 1e-20.  One call loads the
+  // next batch of in-range neighbours (whole 32-entry chunks of the list, at most SNAP_NN_MAX) starting at list position `from`;
+  // s_e = where the next batch starts (>= e1: the list is exhausted)
+  __shared__ unsigned long long s_e;
+  const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
+  auto filter = [&](unsigned long long from)
   {
-    unsigned nn = 0;
-    const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
-    for(unsigned long long e = e0; e < e1; e += 32)
+    if( mb == 0 )
     {
-      const unsigned long long ee = e + lane;
-      bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
-      if( ee < e1 )
+      unsigned nn = 0;
+      unsigned long long e = from;
+      for(; e < e1; e += 32)
       {
-        g = A.nbh_idx[ee];
-        dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
-        apply_xform<XFORM>(X, dx, dy, dz);
-        const int ej = A.type ? A.type[g] : 0;
-        rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
-        const real d2 = dx * dx + dy * dy + dz * dz;
-        in = d2 < rc * rc && d2 > 1e-20;
+        const unsigned long long ee = e + lane;
+        bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
+        if( ee < e1 )
+        {
+          g = A.nbh_idx[ee];
+          dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
+          apply_xform<XFORM>(X, dx, dy, dz);
+          const int ej = A.type ? A.type[g] : 0;
+          rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
+          const double d2 = dx * dx + dy * dy + dz * dz;
+          in = d2 < rc * rc && d2 > 1e-20;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if( nn + __popc(m) > SNAP_NN_MAX ) break;                 // this chunk opens the next batch (same decision on every lane)
+        const unsigned slot = nn + __popc(m & ((1u << lane) - 1u));
+        if( in ) { nb_x[slot] = real(dx); nb_y[slot] = real(dy); nb_z[slot] = real(dz); nb_w[slot] = real(wj); nb_rc[slot] = real(rc); nb_g[slot] = g; }
+        nn += __popc(m);
       }
-      const unsigned m = __ballot_sync(0xffffffffu, in);
-      const unsigned slot = nn + __popc(m & ((1u << lane) - 1u));
-      if( in && slot < SNAP_NN_MAX ) { nb_x[slot] = real(dx); nb_y[slot] = real(dy); nb_z[slot] = real(dz); nb_w[slot] = real(wj); nb_rc[slot] = real(rc); nb_g[slot] = g; }
-      nn += __popc(m);
+      if( lane == 0 ) { s_nn = nn; s_e = e; }
     }
-    if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
-  }
-  __syncthreads();
-  const unsigned nn = s_nn;
-  if( PHASE == 1 && A.nbtab && mb == 0 )
-  {
-    double* t = A.nbtab + size_t(blockIdx.x) * 6 * SNAP_NN_MAX;
-    for(unsigned i = lane; i < nn; i += 32)
-    {
-      t[i] = nb_x[i]; t[SNAP_NN_MAX + i] = nb_y[i]; t[2 * SNAP_NN_MAX + i] = nb_z[i]; t[3 * SNAP_NN_MAX + i] = nb_w[i]; t[4 * SNAP_NN_MAX + i] = nb_rc[i];
-      t[5 * SNAP_NN_MAX + i] = __longlong_as_double((long long)nb_g[i]);
-    }
-    if( lane == 0 ) A.nbcnt[blockIdx.x] = nn;
-  }
-  mark(0);
-
-  // ---- sweep 1: Utot
+    __syncthreads();
+  };
+  // ---- sweep 1: Utot, batch by batch
   real dummy[3];
   if( PHASE != 3 )
-  for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
-    const unsigned n = b0 + lane; const bool valid = n < nn;
-    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
-    snap_sweep<real, TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dummy);
+    unsigned tot = 0;
+    for(unsigned long long from = e0; ; )
+    {
+      filter(from);
+      const unsigned nn = s_nn; const unsigned long long nxt = s_e;
+      if( PHASE == 1 && A.nbtab && mb == 0 )
+      {
+        double* t = A.nbtab + size_t(blockIdx.x) * 6 * SNAP_NN_TAB;
+        for(unsigned i = lane; i < nn && tot + i < SNAP_NN_TAB; i += 32)
+        {
+          const unsigned o = tot + i;
+          t[o] = nb_x[i]; t[SNAP_NN_TAB + o] = nb_y[i]; t[2 * SNAP_NN_TAB + o] = nb_z[i]; t[3 * SNAP_NN_TAB + o] = nb_w[i]; t[4 * SNAP_NN_TAB + o] = nb_rc[i];
+          t[5 * SNAP_NN_TAB + o] = __longlong_as_double((long long)nb_g[i]);
+        }
+      }
+      for(unsigned b0 = 0; b0 < nn; b0 += 32)
+      {
+        const unsigned n = b0 + lane; const bool valid = n < nn;
+        const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+        snap_sweep<real, TJ, false>(K, mb, valid, x, y, z, w, rc, utot, ylist, mbox + lane * SNAP_MBOX_STRIDE(4 * (MB ? MB : 1)), dummy);
+      }
+      __syncthreads();                      // the next filter call overwrites the neighbour arrays
+      tot += nn;
+      if( nxt >= e1 ) break;
+      from = nxt;
+    }
+    if( PHASE == 1 && A.nbtab && tid == 0 )
+    {
+      if( tot > SNAP_NN_TAB ) { atomicExch(A.err, 1); tot = SNAP_NN_TAB; }
+      A.nbcnt[blockIdx.x] = tot;
+    }
+    if( PHASE == 0 ) mark(0);
   }
   __syncthreads();
   mark(1);
@@ -560,6 +585,10 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
   real fix = real(0.0), fiy = real(0.0), fiz = real(0.0), v[9];
 # pragma unroll
   for(int k = 0; k < 9; k++) v[k] = real(0.0);
+  for(unsigned long long from = e0; ; )
+  {
+  filter(from);
+  const unsigned nn = s_nn; const unsigned long long nxt = s_e;
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
@@ -584,6 +613,9 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
       }
     }
     __syncthreads();
+  }
+  if( nxt >= e1 ) break;
+  from = nxt;
   }
   if( mb == 0 )
   {
@@ -640,7 +672,7 @@ __global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const Snap
         apply_xform<XFORM>(X, dx, dy, dz);
         const int ej = A.type ? A.type[g] : 0;
         rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
-        const real d2 = dx * dx + dy * dy + dz * dz;
+        const double d2 = dx * dx + dy * dy + dz * dz;
         in = d2 < rc * rc && d2 > 1e-20;
       }
       const unsigned m = __ballot_sync(0xffffffffu, in);
@@ -741,25 +773,28 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) 
   const size_t soa = (size_t(at >> 5) * K.idxu_max) * 32 + (at & 31u);
   const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
   const int ei = A.type ? A.type[ai] : 0;
-  if( mb == 0 )
+  // the Utot kernel of this chunk left the in-range neighbours of every slot (at most SNAP_NN_TAB): coalesced reads instead of
+  // the list walk, SNAP_NN_MAX at a time
+  const unsigned ntot = A.nbcnt[at];
+  const double* t = A.nbtab + size_t(at) * 6 * SNAP_NN_TAB;
+  auto load_batch = [&](unsigned base)
   {
-    // the Utot kernel of this chunk left the in-range neighbours of every slot: one coalesced read instead of the list walk
-    const unsigned nn = A.nbcnt[at];
-    const double* t = A.nbtab + size_t(at) * 6 * SNAP_NN_MAX;
+    const unsigned nn = min(unsigned(SNAP_NN_MAX), ntot - base);
     for(unsigned i = lane; i < nn; i += 32)
     {
-      nb_x[i] = real(t[i]); nb_y[i] = real(t[SNAP_NN_MAX + i]); nb_z[i] = real(t[2 * SNAP_NN_MAX + i]); nb_w[i] = real(t[3 * SNAP_NN_MAX + i]); nb_rc[i] = real(t[4 * SNAP_NN_MAX + i]);
-      nb_g[i] = unsigned(__double_as_longlong(t[5 * SNAP_NN_MAX + i]));
+      const unsigned o = base + i;
+      nb_x[i] = real(t[o]); nb_y[i] = real(t[SNAP_NN_TAB + o]); nb_z[i] = real(t[2 * SNAP_NN_TAB + o]); nb_w[i] = real(t[3 * SNAP_NN_TAB + o]); nb_rc[i] = real(t[4 * SNAP_NN_TAB + o]);
+      nb_g[i] = unsigned(__double_as_longlong(t[5 * SNAP_NN_TAB + o]));
     }
     if( lane == 0 ) s_nn = nn;
-  }
+  };
+  if( mb == 0 ) load_batch(0u);
   else
   {
-    // the other rows fetch Y while row 0 walks the neighbour list
+    // the other rows fetch Y while row 0 reads the neighbour table
     for(int k = int(tid) - 32; k < K.idxu_max; k += NT - 32) ylist[k] = A.ybuf[soa + size_t(k) * 32];
   }
   __syncthreads();
-  const unsigned nn = s_nn;
   // ---- energy (direction 0 only): e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero ; Utot straight from global
   if( A.ep && kd == 0 )
   {
@@ -783,6 +818,10 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) 
   }
   double* const fout = kd == 0 ? A.fx : (kd == 1 ? A.fy : A.fz);
   real fi = real(0.0), v0 = real(0.0), v1 = real(0.0), v2 = real(0.0);
+  for(unsigned base = 0; base < ntot; base += SNAP_NN_MAX)
+  {
+  if( base ) { if( mb == 0 ) load_batch(base); __syncthreads(); }
+  const unsigned nn = s_nn;
   for(unsigned b0 = 0; b0 < nn; b0 += 32)
   {
     const unsigned n = b0 + lane; const bool valid = n < nn;
@@ -800,6 +839,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) 
       if( A.vir ) { v0 -= f * x; v1 -= f * y; v2 -= f * z; }
     }
     __syncthreads();
+  }
   }
   if( mb == 0 )
   {
@@ -985,7 +1025,7 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
   const size_t words = size_t((chunk + 31) / 32) * 32 * S->K.idxu_max;
   XSB_CUDA(ctx, S->ubuf.reserve(words)); XSB_CUDA(ctx, S->ybuf.reserve(words));
   A.ubuf = reinterpret_cast<typename R2<real>::type*>(S->ubuf.p); A.ybuf = reinterpret_cast<typename R2<real>::type*>(S->ybuf.p);      // sized for double2, float2 uses half
-  XSB_CUDA(ctx, S->nbtab.reserve(size_t(chunk) * 6 * SNAP_NN_MAX)); XSB_CUDA(ctx, S->nbcnt.reserve(chunk));
+  XSB_CUDA(ctx, S->nbtab.reserve(size_t(chunk) * 6 * SNAP_NN_TAB)); XSB_CUDA(ctx, S->nbcnt.reserve(chunk));
   A.nbtab = S->nbtab.p; A.nbcnt = S->nbcnt.p;
   const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
                      + size_t(3 * NR) * 32 * sizeof(real) + 64;
@@ -1176,7 +1216,7 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   {
     S->overflowed = true;      // sticky until xsb_snap_overflow() is read
     XSB_CUDA(ctx, cudaMemsetAsync(S->err.p, 0, sizeof(int), ctx->stream));
-    return ctx->fail(XSB_ERR_OVERFLOW, "snap_force: an atom has more than %d neighbours inside the SNAP cutoff; forces and energies of this call are incomplete", SNAP_NN_MAX);
+    return ctx->fail(XSB_ERR_OVERFLOW, "snap_force: an atom has more than %d neighbours inside the SNAP cutoff; forces and energies of this call are incomplete", SNAP_NN_TAB);
   }
   return XSB_OK;
 }

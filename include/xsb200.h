@@ -231,8 +231,9 @@ double xsb_snap_rcut_max(xsb_ctx* ctx);                     /* rcut_max output s
 /* follow with xsb_ghost_reduce_add of fx,fy,fz = update_force_energy_from_ghost); flags: GHOST, ENERGY, VIRIAL, MIXED */
 /* XSB_FLAG_MIXED: the reference's SNAP_FP32_MATH build (snap_force.cu:25-29): FP32 bispectrum arithmetic, FP64 positions,  */
 /* forces and energies (tolerance 1e-5).                                                                                   */
-/* At most 64 neighbours inside the SNAP cutoff per atom (the reference has no cap; BCC/FCC metals at the shipped     */
-/* rcutfac have 14-42): beyond that the call returns XSB_ERR_OVERFLOW (it syncs the stream to find out).              */
+/* Neighbours inside the SNAP cutoff are processed 64 at a time (the reference has no cap; BCC/FCC metals at the shipped */
+/* rcutfac have 14-42); beyond 192 per atom (2J >= 7 pipeline) the call returns XSB_ERR_OVERFLOW (it syncs the stream   */
+/* to find out).                                                                                                        */
 int    xsb_snap_force(xsb_ctx* ctx, int flags);
 int    xsb_snap_overflow(xsb_ctx* ctx, int* flag);          /* 1: a call since the last read exceeded the cap    */
 

@@ -529,6 +529,39 @@ def test_pair_potentials_parity(name, virial):
         assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
 
 
+@pytest.mark.parametrize("twoj", [8, 4])
+def test_snap_more_than_64_neighbours_is_batched(twoj):
+    """the reference has no cap on the neighbours inside the SNAP cut-off; the kernels hold 64 at a time in shared memory and
+    batch the rest (2J = 8: Utot kernel + per-direction force kernel through the neighbour table; 2J = 4: in-kernel re-filter)"""
+    O = oracle()
+    rng = np.random.default_rng(8)
+    pos, typ, box = lattice("BCC", 5, 3.3, 0.07, seed=6)
+    gs = GridSystem(pos, typ, box, box[0] / 3, 2)
+    nc = xsb.load_library().xsb_snap_ncoeff(twoj)
+    beta = rng.normal(0.0, 1.0, (1, nc + 1)) * EV * 1e-3
+    rcutfac = 7.2                                        # 2 * 0.5 * 7.2 = 7.2 ang: ~85 neighbours in BCC a = 3.3
+    S = O.Snap(twoj, rcutfac, [0.5], [1.0], beta)
+    g = gs.oracle_grid()
+    nbh_dist = S.rcut_max() + 0.3
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh_dist, 1, True)
+    rfx, rfy, rfz, rep = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    O.snap_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, S, 2, rfx, rfy, rfz, rep, None)
+    ctx = make_ctx(gs)
+    ctx.snap_set(twoj, rcutfac, [0.5], [1.0], beta)
+    ctx.chunk_neighbors(nbh_dist)
+    cnt, _, _ = ctx.chunk_neighbors_flat()
+    assert cnt[~gs.is_ghost].min() > 70
+    ctx.zero_force_energy(ghost=True)
+    ctx.snap_force(xsb.FLAG_ENERGY)
+    assert not ctx.snap_overflow()
+    fx, fy, fz, ep = [ctx.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+    fmax = max(np.abs(rfx).max(), np.abs(rfy).max(), np.abs(rfz).max())
+    for a, b in ((fx, rfx), (fy, rfy), (fz, rfz)):
+        assert np.abs(a - b).max() <= 1e-10 * fmax
+    own = ~gs.is_ghost
+    assert np.abs(ep[own] - rep[own]).max() <= 1e-10 * np.abs(rep[own]).max()
+
+
 @pytest.mark.parametrize("twoj,nel", [(8, 1), (6, 2), (4, 1)])
 def test_snap_force_mixed_precision(twoj, nel):
     """XSB_FLAG_MIXED on snap_force = the reference's SNAP_FP32_MATH build (src/potential/snap/snap_force.cu:25-29, deck
