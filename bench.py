@@ -604,6 +604,13 @@ def run_xsb(args):
             per_rank[k + "_ms"] = {"min": min(r), "median": float(np.median(r)), "max": max(r)}
     per_rank["rebuild_wall_s"] = dict(zip(("min", "median", "max"), (lambda r: (min(r), float(np.median(r)), max(r)))(allranks(rebuild_s_timed))))
 
+    # checksum of the forces the timed loop ended on (own atoms, all ranks): runs that differ only in a kernel switch
+    # (inner skin, ghost transport, ...) must agree on it to ~1e-10
+    fsum = 0.0
+    for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ):
+        fsum += float(np.abs(ctx.download(f)).sum())           # ghost slots hold zeros
+    fsum = sum(allranks(fsum))
+
     # ---- the same steps in mixed precision (FP32 spline / pair math, tolerance 1e-5): reported beside, not as, the metric
     mixed = None
     if not args.no_mixed:
@@ -724,7 +731,7 @@ def run_xsb(args):
                        "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
                        "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown, "ranks": per_rank,
                        "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport(),
-                       "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
+                       "force_checksum_sum_abs": fsum, "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
