@@ -124,8 +124,9 @@ class EamCu(Workload):
     def label(self, n, uc, scaling):
         tot = 4 * uc[0] * uc[1] * uc[2] * n
         if scaling == "strong":
-            return "EAM Cu FCC %d^3 unit cells = %d atoms over %d GPU (bricks of %dx%dx%d unit cells), eam_alloy_force (reference Cu.eam.alloy, rc %.2f, skin %.1f)" % (
-                self.strong_total, 4 * self.strong_total ** 3, n, uc[0], uc[1], uc[2], self.rcut, self.skin)
+            rd = rank_dims(n)
+            return "EAM Cu FCC %dx%dx%d unit cells = %d atoms over %d GPU (bricks of %dx%dx%d unit cells), eam_alloy_force (reference Cu.eam.alloy, rc %.2f, skin %.1f)" % (
+                uc[0] * rd[0], uc[1] * rd[1], uc[2] * rd[2], tot, n, uc[0], uc[1], uc[2], self.rcut, self.skin)
         return "EAM Cu FCC %d^3 unit cells x %d GPU = %d atoms, eam_alloy_force (reference Cu.eam.alloy, rc %.2f, skin %.1f)" % (uc[0], n, tot, self.rcut, self.skin)
 
     def potential(self):
