@@ -471,7 +471,7 @@ def run_xsb(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
     W = WORKLOADS[args.workload]()
-    W.inner_skin = args.inner_skin if W.xform0 is None else 0.0      # a cell matrix that changes every step re-filters every step anyway
+    W.inner_skin = args.inner_skin
     if W.strong_total and args.scaling != "strong":
         args.scaling = "strong"
     torch.cuda.set_device(local)

@@ -430,6 +430,15 @@ namespace xsb
 {
 // inner-skin accounting (SubCtl): this step moved no atom (of any rank: s2 is all-reduced) further than sqrt(*s2)
 __global__ void sub_accum_kernel(SubCtl* ctl, const unsigned long long* s2) { ctl->acc += sqrt(__longlong_as_double((long long)*s2)); }
+__global__ void sub_accum_value_kernel(SubCtl* ctl, double d) { ctl->acc += d; }
+}
+
+int xsb_internal_sub_account(xsb_ctx* ctx, double displacement)
+{
+  if( !ctx->sub_ctl.p ) return XSB_OK;
+  xsb::sub_accum_value_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, displacement);
+  XSB_LAUNCH_CHECK(ctx);
+  return XSB_OK;
 }
 
 // the fused pass; out[0] = max |r - r_backup|^2, out[1] = max |step displacement|^2 (both zeroed here)

@@ -8,7 +8,7 @@
 namespace xsb
 {
 
-static void inverse3(const double* m, double* inv)
+void inverse3(const double* m, double* inv)
 {
   const double det = m[0]*(m[4]*m[8]-m[5]*m[7]) - m[1]*(m[3]*m[8]-m[5]*m[6]) + m[2]*(m[3]*m[7]-m[4]*m[6]);
   const double id = 1.0 / det;
@@ -416,14 +416,22 @@ int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
   XSB_REQUIRE(ctx, xform != nullptr, XSB_ERR_INVALID, "null xform");
   XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
   bool ident = true;
+  double dx2 = 0.0, inv[9] = {1,0,0,0,1,0,0,0,1}, inv2 = 0.0;
+  if( !ctx->grid.xform_is_identity ) xsb::inverse3(ctx->grid.xform, inv);
   for(int i = 0; i < 9; i++)
   {
     XSB_REQUIRE(ctx, std::isfinite(xform[i]), XSB_ERR_INVALID, "xform is not finite");
+    dx2 += (xform[i] - ctx->grid.xform[i]) * (xform[i] - ctx->grid.xform[i]); inv2 += inv[i] * inv[i];
     ctx->grid.xform[i] = xform[i];
     ident = ident && xform[i] == ((i % 4 == 0) ? 1.0 : 0.0);
   }
   ctx->grid.xform_is_identity = ident ? 1 : 0;
-  ctx->pos_epoch++; ctx->foreign_epoch++;                 // physical distances changed: an in-range sub-list of the old cell is stale
+  ctx->pos_epoch++;                 // physical distances changed: the in-range sub-list of this step must be rewritten
+  // Inner-skin accounting (SubCtl): a listed pair (|X r| < nbh_dist) changes its separation by at most |dX| |X^-1| nbh_dist
+  // (Frobenius norms); that counts like both atoms moving half of it.  A barostat's per-step drift (1e-6 relative) costs
+  // 1e-5 ang of the budget; a real deformation exhausts it and the next rho phase re-filters.
+  if( ctx->sub_ctl.p && ctx->nbh_built ) { int rc = xsb_internal_sub_account(ctx, 0.5 * std::sqrt(dx2 * inv2) * ctx->nbh_dist); if( rc ) return rc; }
+  else ctx->foreign_epoch++;
   return XSB_OK;
 }
 

@@ -236,10 +236,13 @@ int  xsb_internal_assign_device(xsb_ctx* ctx, unsigned n, double* rx, double* ry
 int  xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, double* const d[7], unsigned char* types,
                           unsigned* n_new, double* e[7], unsigned char** types_new);
 void xsb_snap_release(xsb_ctx* ctx);
+// inner-skin budget (SubCtl): every atom may have moved by up to `displacement` more (xsb_assign.cu)
+int  xsb_internal_sub_account(xsb_ctx* ctx, double displacement);
 
 namespace xsb
 {
 // search range (cell layers per axis) covering every grid-space displacement of physical length < dist
 void search_range(const xsb_grid_desc& g, double dist, int R[3]);
 void search_range_unclamped(const xsb_grid_desc& g, double dist, int R[3]);
+void inverse3(const double* m, double* inv);
 }

@@ -870,8 +870,8 @@ def test_verlet_boundary_equals_the_five_separate_operators(triclinic):
         assert np.abs(u - v).max() <= 4e-16 * max(np.abs(u).max(), 1e-300)
 
 
-@pytest.mark.parametrize("two_species,mixed", [(False, False), (True, False), (False, True)])
-def test_eam_inner_skin_reuse_matches_plain_path_and_oracle(tmp_path, two_species, mixed):
+@pytest.mark.parametrize("two_species,mixed,drift", [(False, False, False), (True, False, False), (False, True, False), (True, False, True)])
+def test_eam_inner_skin_reuse_matches_plain_path_and_oracle(tmp_path, two_species, mixed, drift):
     """xsb_eam_inner_skin: the rho phase re-evaluates the sub-list of an earlier step instead of re-filtering the neighbour
     list while the device-side displacement budget holds.  An NVE run with the skin must give the plain path's forces at
     every step (same pairs; summation order differs), really reuse the list, re-filter when an atom jumps, and match the
@@ -900,7 +900,11 @@ def test_eam_inner_skin_reuse_matches_plain_path_and_oracle(tmp_path, two_specie
         return [c.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
 
     tol = 1e-5 if mixed else 1e-12
+    X0 = np.array([[1.0, 0.01, 0.005], [0.0, 1.0, 0.01], [0.0, 0.0, 1.0]])
     for step in range(7):
+        if drift:                                          # NPT-like cell matrix: changes every step, accounted in the budget
+            for c in ctxs:
+                c.grid_set_xform(X0 * (1.0 + 2e-6 * step))
         out = [forces(c) for c in ctxs]
         for a, b in zip(*out):
             assert rel_err(a, b) < tol, "step %d" % step
@@ -918,6 +922,8 @@ def test_eam_inner_skin_reuse_matches_plain_path_and_oracle(tmp_path, two_specie
     assert ctxs[0].eam_sublist_stats() == (0, 0)
     # final positions against the oracle (ghost images included: one ghost layer, rho_dEmb copied owner -> ghost)
     c = ctxs[1]
+    if drift:
+        c.grid_set_xform(np.eye(3))                        # a real deformation: exhausts the budget, the pass re-filters
     out = forces(c)
     off = c.cell_offsets()
     rx, ry, rz, tt = c.download(xsb.F_RX), c.download(xsb.F_RY), c.download(xsb.F_RZ), c.download(xsb.F_TYPE)

@@ -71,8 +71,9 @@ def traffic(path):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     acc = defaultdict(list)
     for r in rows[2:]:
-        key = "eam_force" if "EamForceTileOp" in r[kn] else "eam_rho" if "EamRhoTileOp" in r[kn] else None
-        if key:
+        key = "eam_force" if "EamForceTileOp" in r[kn] else "eam_rho_rewrite" if ("EamRhoTileOp" in r[kn] and ", 3, " in r[kn]) else "eam_rho" if "EamRhoTileOp" in r[kn] else None
+        ms = float(r[du]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[du], 1.0)
+        if key and ms > 0.05:              # the launch of a step whose mode is not current returns at once: not a measurement
             acc[key].append((float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]], float(r[du]), r[kn][:120]))
     res = {"source": path, "how": "ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum, mean per launch"}
     for k, v in acc.items():
