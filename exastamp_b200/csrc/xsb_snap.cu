@@ -32,6 +32,11 @@ constexpr int SNAP_NN_TAB = 192;     // in-range neighbours per atom the Utot ke
 
 struct SnapZ { unsigned char j1, j2, j, ma1min, ma2max, na, mb1min, mb2max, nb, pad; unsigned short jju; int cgoff; };   // 16 B
 
+// snap_y2_kernel tables (see the kernel)
+constexpr int SNAP_YPAD = 4;                       // W - 1 for the widest block
+struct SnapYTri { unsigned char j1, j2, s, P; int cgp; };         // P = j2 + 1 + 2 SNAP_YPAD = row stride of the padded table at cgp
+struct SnapYTask { unsigned char j, mb, ma0, W; unsigned short tri0, ntri; };
+
 // per-launch constants in the arithmetic type of the kernels (double, or float for XSB_FLAG_MIXED)
 template<class real>
 struct SnapConstT
@@ -74,6 +79,7 @@ struct SnapDev
   DevBuf<double> nbtab; DevBuf<unsigned> nbcnt;                                        // in-range neighbours of the chunk's atoms (Utot kernel -> force kernel)
   SnapConstT<float> K32{};                                                               // the same constants rounded to float (XSB_FLAG_MIXED)
   DevBuf<float> cglist32, betaz32, betaz_sort32;
+  DevBuf<SnapYTri> y2tri; DevBuf<SnapYTask> y2task; DevBuf<double> y2cg, y2beta; DevBuf<float> y2cg32, y2beta32; int n_y2tri = 0, n_y2task = 0;   // snap_y2_kernel
   double rcut_max = 0.0;
   bool overflowed = false;       // a call hit SNAP_NN_MAX since xsb_snap_overflow() was last read
 };
@@ -100,6 +106,28 @@ __device__ __forceinline__ int mbox_off(int m) { return m * (m + 1); }
 // that the lanes of a quarter-warp hit 8 different bank groups: with the natural stride (a multiple of 128 bytes at
 // 2J = 8) every mailbox access was an 8-way bank conflict (ncu: 590 M shared wavefronts for 149 M ideal)
 #define SNAP_MBOX_STRIDE(n) (((n) | 1))
+
+// Sum N per-lane values over the 32 lanes of a warp by recursive halving: at each step a lane keeps one half of its values
+// and receives the partner's copy of that half, so after the five steps value number `off` (if len > 0) is complete in
+// v[0] of exactly one lane.  N <= 32.
+template<class real, int N, int S> struct WarpHalving
+{
+  static __device__ __forceinline__ void run(real* v, unsigned lane, int& off, int& len)
+  {
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & unsigned(S)) != 0u;
+#   pragma unroll
+    for(int i = 0; i < H; i++)
+    {
+      const real hi = (H + i < N) ? v[H + i] : real(0.0);
+      const real keep = up ? hi : v[i], send = up ? v[i] : hi;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+    }
+    if( up ) { off += H; len = len > H ? len - H : 0; } else len = len < H ? len : H;
+    WarpHalving<real, H, S / 2>::run(v, lane, off, len);
+  }
+};
+template<class real, int N> struct WarpHalving<real, N, 0> { static __device__ __forceinline__ void run(real*, unsigned, int&, int&) { static_assert(N == 1, "at most 32 values"); } };
 
 // One sweep over the levels for the thread's (neighbour, row mb).  DERIV = false: accumulate sfac*wj*u into utot (shuffle
 // reduction over the lanes).  DERIV = true: carry du/dr_k, contract with Y -> dedr[3].
@@ -149,14 +177,14 @@ __device__ __forceinline__ void snap_sweep(const SnapConstT<real>& K, int mb, bo
     const int base = K.idxu_block[J] + (J + 1) * mb;
     if( !DERIV )
     {
+      // sum of the row over the 32 neighbours: recursive halving leaves each of the 2(J+1) totals in one lane
+      // (2(J+1) - 1 + 4 shuffles per row instead of 10(J+1))
+      real v[2 * (J + 1)];
 #     pragma unroll
-      for(int ma = 0; ma <= J; ma++)
-      {
-        real vr = sfac * ur[ma], vi = sfac * ui[ma];
-#       pragma unroll
-        for(int o = 16; o > 0; o >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o); vi += __shfl_xor_sync(0xffffffffu, vi, o); }
-        if( (threadIdx.x & 31) == 0 ) { utot[base + ma].x += vr; utot[base + ma].y += vi; }
-      }
+      for(int ma = 0; ma <= J; ma++) { v[2 * ma] = sfac * ur[ma]; v[2 * ma + 1] = sfac * ui[ma]; }
+      int off = 0, len = 2 * (J + 1);
+      WarpHalving<real, 2 * (J + 1), 16>::run(v, threadIdx.x & 31u, off, len);
+      if( len > 0 ) reinterpret_cast<real*>(utot + base)[off] += v[0];
     }
     else
     {
@@ -379,6 +407,173 @@ __device__ __forceinline__ real snap_sweep_dir(const SnapConstT<real>& K, int mb
   return dedr;
 }
 
+// Reverse-mode force sweep: dE/dr of ALL three Cartesian directions from one forward chain + one backward (adjoint) chain.
+// G(a, b) = sum_levels sum_half w Re(conj(Y) u) is a polynomial in the Cayley-Klein parameters a, b through the recursion
+// u^J[mb][ma] = qa conj(a) u^{J-1}[mb][ma] - qb conj(b) u^{J-1}[mb][ma-1]; instead of carrying du/dr_k along (one chain per
+// direction, snap_sweep_dir), the thread stores its row of every level in shared memory on the way up and walks back down
+// with the adjoint row ubar^J = w Y^J + (what level J+1 handed down): ubar^{J-1}[m] = qa a ubar^J[m] - qb b ubar^J[m+1],
+// abar += qa (ubar^J[m] . u^{J-1}[m]), bbar -= qb (ubar^J[m+1] . u^{J-1}[m]).  The birth of a row (mirror of row mb-1) is
+// real-linear, its adjoint goes back through the same mailbox.  out = { G, dG/da_r, dG/da_i, dG/db_r, dG/db_i } of this row;
+// the caller sums the rows and applies da/dr_k, db/dr_k, sfac and dsfac.  ~32 FP64 operations per element and neighbour
+// for the three directions together, against 3 x 35 of the per-direction sweeps.
+template<class real, int TJ>
+__device__ __forceinline__ void snap_sweep_rev(const SnapConstT<real>& K, int mb, real x, real y, real z, real rcut,
+                                               const real2* __restrict__ ylist, real2* __restrict__ mbox /* this neighbour's mailbox [MB] */,
+                                               real2* __restrict__ hist /* this lane's column of the level history, slot stride 32 */, int hbase,
+                                               real out[5])
+{
+  constexpr int NE = TJ + 1;
+  real ur[NE], ui[NE], br[NE], bi[NE];
+  const real rsq = x * x + y * y + z * z, r = xsqrt(rsq);
+  const real rscale0 = K.rfac0 * real(M_PI) / (rcut - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+  real sn, cs; xsincos(theta0, &sn, &cs);
+  const real z0 = r * cs / sn;
+  const real r0inv = xrsqrt(rsq + z0 * z0);
+  const real a_r = z0 * r0inv, a_i = -z * r0inv, b_r = y * r0inv, b_i = -x * r0inv;
+  real G = real(0.0), abr = real(0.0), abi = real(0.0), bbr = real(0.0), bbi = real(0.0);
+# pragma unroll
+  for(int e = 0; e < NE; e++) { ur[e] = real(0.0); ui[e] = real(0.0); br[e] = real(0.0); bi[e] = real(0.0); }
+  if( mb == 0 ) { ur[0] = real(1.0); G = real(0.5) * ylist[0].x; }      // level 0: u = 1 (middle element of its level: w = 1/2)
+
+  // row mb at level J-1 is the mirror of row mb-1 (published to the mailbox at level J-1)
+  auto birth = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;
+    const int o = mbox_off(mb - 1);
+#   pragma unroll
+    for(int ma = 0; ma < J; ma++)
+    {
+      const int mp = J - 1 - ma;
+      const real sgn = ((mb - 1 + mp) & 1) ? -real(1.0) : real(1.0);
+      const real2 v = mbox[o + mp];
+      ur[ma] = sgn * v.x; ui[ma] = -sgn * v.y;
+    }
+  };
+  // one step down: nbar = br/bi (adjoint of level J, J+1 elements), old = ur/ui (level J-1, J elements) -> br/bi = adjoint of
+  // level J-1 (J elements), or its mirror into the mailbox when the row was born at this level
+  auto down = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;
+    real nr[J + 1], ni[J + 1];
+#   pragma unroll
+    for(int ma = 0; ma <= J; ma++) { nr[ma] = br[ma]; ni[ma] = bi[ma]; }
+#   pragma unroll
+    for(int m = 0; m < J; m++)
+    {
+      const real qa = K.rootpq[J - m][J - mb], qb = K.rootpq[m + 1][J - mb];
+      const real pr = qa * nr[m], pi = qa * ni[m], sr = qb * nr[m + 1], si = qb * ni[m + 1];
+      // a * p - b * s
+      br[m] = a_r * pr - a_i * pi - (b_r * sr - b_i * si);
+      bi[m] = a_r * pi + a_i * pr - (b_r * si + b_i * sr);
+      abr += pr * ur[m] + pi * ui[m]; abi += pr * ui[m] - pi * ur[m];
+      bbr -= sr * ur[m] + si * ui[m]; bbi -= sr * ui[m] - si * ur[m];
+    }
+    if( 2 * mb == J )
+    {
+      const int o = mbox_off(mb - 1);
+#     pragma unroll
+      for(int ma = 0; ma < J; ma++)
+      {
+        const int mp = J - 1 - ma;
+        const real sgn = ((mb - 1 + mp) & 1) ? -real(1.0) : real(1.0);
+        mbox[o + mp] = mk2<real>(sgn * br[ma], -sgn * bi[ma]);
+      }
+    }
+  };
+  auto seed_w = [&](int J, int ma) -> real { return 2 * mb == J ? (ma < mb ? real(1.0) : (ma == mb ? real(0.5) : real(0.0))) : real(1.0); };
+
+  auto up = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;        // advance from level J-1 to level J < TJ, remember level J-1
+    if( 2 * mb <= J )
+    {
+      if( 2 * mb == J ) birth(jc);
+      const int hs = hbase + J * (J - 1) / 2;
+#     pragma unroll
+      for(int ma = 0; ma < J; ma++) hist[(hs + ma) * 32] = mk2<real>(ur[ma], ui[ma]);
+#     pragma unroll
+      for(int ma = J; ma >= 0; ma--)
+      {
+        real n_r = real(0.0), n_i = real(0.0);
+        if( ma < J ) { const real q = K.rootpq[J - ma][J - mb]; n_r = q * (a_r * ur[ma] + a_i * ui[ma]); n_i = q * (a_r * ui[ma] - a_i * ur[ma]); }
+        if( ma > 0 ) { const real q = K.rootpq[ma][J - mb]; n_r -= q * (b_r * ur[ma - 1] + b_i * ui[ma - 1]); n_i -= q * (b_r * ui[ma - 1] - b_i * ur[ma - 1]); }
+        ur[ma] = n_r; ui[ma] = n_i;
+      }
+      const int base = K.idxu_block[J] + (J + 1) * mb;
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++) { const real2 Y = ylist[base + ma]; G += seed_w(J, ma) * (ur[ma] * Y.x + ui[ma] * Y.y); }
+      if( J == 2 * mb + 1 )
+      {
+        const int o = mbox_off(mb);
+#       pragma unroll
+        for(int ma = 0; ma <= J; ma++) mbox[o + ma] = mk2<real>(ur[ma], ui[ma]);
+      }
+    }
+    __syncthreads();
+  };
+  if constexpr ( TJ >= 2 ) up(std::integral_constant<int, 1>{});
+  if constexpr ( TJ >= 3 ) up(std::integral_constant<int, 2>{});
+  if constexpr ( TJ >= 4 ) up(std::integral_constant<int, 3>{});
+  if constexpr ( TJ >= 5 ) up(std::integral_constant<int, 4>{});
+  if constexpr ( TJ >= 6 ) up(std::integral_constant<int, 5>{});
+  if constexpr ( TJ >= 7 ) up(std::integral_constant<int, 6>{});
+  if constexpr ( TJ >= 8 ) up(std::integral_constant<int, 7>{});
+
+  // top level: the level TJ row is only needed for G, so level TJ-1 stays in the registers and the way down starts here
+  {
+    constexpr int J = TJ;
+    if( 2 * mb <= J )
+    {
+      if( 2 * mb == J ) birth(std::integral_constant<int, J>{});
+      const int base = K.idxu_block[J] + (J + 1) * mb;
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++)
+      {
+        real n_r = real(0.0), n_i = real(0.0);
+        if( ma < J ) { const real q = K.rootpq[J - ma][J - mb]; n_r = q * (a_r * ur[ma] + a_i * ui[ma]); n_i = q * (a_r * ui[ma] - a_i * ur[ma]); }
+        if( ma > 0 ) { const real q = K.rootpq[ma][J - mb]; n_r -= q * (b_r * ur[ma - 1] + b_i * ui[ma - 1]); n_i -= q * (b_r * ui[ma - 1] - b_i * ur[ma - 1]); }
+        const real2 Y = ylist[base + ma];
+        const real w = seed_w(J, ma);
+        G += w * (n_r * Y.x + n_i * Y.y);
+        br[ma] = w * Y.x; bi[ma] = w * Y.y;
+      }
+      down(std::integral_constant<int, J>{});
+    }
+    __syncthreads();
+  }
+  auto dn = [&](auto jc)
+  {
+    constexpr int J = decltype(jc)::value;        // adjoint of level J -> level J-1
+    if( 2 * mb <= J )
+    {
+      const int base = K.idxu_block[J] + (J + 1) * mb;
+      const bool mail = J == 2 * mb + 1;          // row mb+1 was born from this level: its adjoint comes back mirrored
+      const int o = mbox_off(mb);
+#     pragma unroll
+      for(int ma = 0; ma <= J; ma++)
+      {
+        const real2 Y = ylist[base + ma];
+        const real w = seed_w(J, ma);
+        br[ma] += w * Y.x; bi[ma] += w * Y.y;
+        if( mail ) { const real2 m = mbox[o + ma]; br[ma] += m.x; bi[ma] += m.y; }
+      }
+      const int hs = hbase + J * (J - 1) / 2;
+#     pragma unroll
+      for(int ma = 0; ma < J; ma++) { const real2 v = hist[(hs + ma) * 32]; ur[ma] = v.x; ui[ma] = v.y; }
+      down(jc);
+    }
+    __syncthreads();
+  };
+  if constexpr ( TJ >= 8 ) dn(std::integral_constant<int, 7>{});
+  if constexpr ( TJ >= 7 ) dn(std::integral_constant<int, 6>{});
+  if constexpr ( TJ >= 6 ) dn(std::integral_constant<int, 5>{});
+  if constexpr ( TJ >= 5 ) dn(std::integral_constant<int, 4>{});
+  if constexpr ( TJ >= 4 ) dn(std::integral_constant<int, 3>{});
+  if constexpr ( TJ >= 3 ) dn(std::integral_constant<int, 2>{});
+  if constexpr ( TJ >= 2 ) dn(std::integral_constant<int, 1>{});
+  out[0] = G; out[1] = abr; out[2] = abi; out[3] = bbr; out[4] = bbi;
+}
+
 template<class real>
 struct SnapArgsT
 {
@@ -394,6 +589,8 @@ struct SnapArgsT
   // in-range neighbours found by the Utot kernel, per chunk slot: 6 rows of SNAP_NN_MAX doubles (dx, dy, dz, wj, rc, index bits)
   double* nbtab; unsigned* nbcnt;
   const SnapZ* __restrict__ zsort; const real* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
+  // snap_y2_kernel: triples sorted by j, padded Clebsch-Gordan rows, beta per (element, triple), work items
+  const SnapYTri* __restrict__ y2tri; const real* __restrict__ y2cg; const real* __restrict__ y2beta; const SnapYTask* __restrict__ y2task; int n_y2tri, n_y2task;
 };
 
 // PHASE 0: fused (everything in one CTA, kept for reference / small runs); PHASE 1: Utot only -> A.ubuf; PHASE 3: reads Utot
@@ -858,6 +1055,156 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) 
   }
 }
 
+// ---- force kernel, reverse mode: one CTA per atom, J/2+1 warps = rows, lane = neighbour --------------------------------
+// Forward chain with the level history in shared memory ([slot][lane], conflict-free 16-byte columns), adjoint chain back
+// down (snap_sweep_rev), then warp 0 turns { G, dG/da, dG/db } of each neighbour into the three force components.
+template<int TJ> struct SnapHist
+{
+  // history slots of row mb: levels max(1, 2mb) .. TJ-1, level J holds J elements
+  static constexpr int S(int J) { return J * (J - 1) / 2; }
+  static constexpr int j0(int mb) { return 2 * mb > 1 ? 2 * mb : 1; }
+  static constexpr int rowsize(int mb) { return j0(mb) < TJ ? S(TJ) - S(j0(mb)) : 0; }
+  static constexpr int total() { int t = 0; for(int m = 0; 2 * m <= TJ; m++) t += rowsize(m); return t; }
+};
+
+template<class real, int TJ, bool XFORM>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 5 : 3) snap_fr_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
+{
+  constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = MB ? MB : 1;
+  constexpr int HN = SnapHist<TJ>::total() ? SnapHist<TJ>::total() : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real2* ylist = reinterpret_cast<real2*>(smem_raw);                // [idxu_max]
+  real2* hist = ylist + K.idxu_max;                                   // [HN][32]
+  real2* mbox = hist + HN * 32;                                       // [32][MBS] (odd stride)
+  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(MBS));        // [SNAP_NN_MAX] x 5
+  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
+  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
+  real* red = reinterpret_cast<real*>(nb_g + SNAP_NN_MAX);          // [NR][5][32]
+  __shared__ unsigned s_nn;
+  const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
+  const unsigned at = blockIdx.x;
+  const unsigned slot = A.base + at;
+  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
+  const size_t soa = (size_t(at >> 5) * K.idxu_max) * 32 + (at & 31u);
+  const int ei = A.type ? A.type[ai] : 0;
+  int hbase = 0;
+  for(int m = 0; m < mb; m++) hbase += SnapHist<TJ>::rowsize(m);
+  hbase -= SnapHist<TJ>::S(SnapHist<TJ>::j0(mb));
+  // the Utot kernel of this chunk left the in-range neighbours of every slot (at most SNAP_NN_TAB), SNAP_NN_MAX at a time
+  const unsigned ntot = A.nbcnt[at];
+  const double* t = A.nbtab + size_t(at) * 6 * SNAP_NN_TAB;
+  auto load_batch = [&](unsigned base)
+  {
+    const unsigned nn = min(unsigned(SNAP_NN_MAX), ntot - base);
+    for(unsigned i = lane; i < nn; i += 32)
+    {
+      const unsigned o = base + i;
+      nb_x[i] = real(t[o]); nb_y[i] = real(t[SNAP_NN_TAB + o]); nb_z[i] = real(t[2 * SNAP_NN_TAB + o]); nb_w[i] = real(t[3 * SNAP_NN_TAB + o]); nb_rc[i] = real(t[4 * SNAP_NN_TAB + o]);
+      nb_g[i] = unsigned(__double_as_longlong(t[5 * SNAP_NN_TAB + o]));
+    }
+    if( lane == 0 ) s_nn = nn;
+  };
+  if( mb == 0 ) load_batch(0u);
+  if( NR == 1 || mb != 0 )
+  {
+    // the other rows fetch Y while row 0 reads the neighbour table
+    const int first = NR == 1 ? int(tid) : int(tid) - 32, step = NR == 1 ? NT : NT - 32;
+    for(int k = first; k < K.idxu_max; k += step) ylist[k] = A.ybuf[soa + size_t(k) * 32];
+  }
+  __syncthreads();
+  // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero ; Utot straight from global
+  if( A.ep )
+  {
+    real sE = real(0.0);
+    for(int j = 0; j <= TJ; j++)
+    {
+      const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
+      for(int k = int(tid); k < cnt; k += NT)
+      {
+        const real w = (j % 2 == 0 && k == cnt - 1) ? real(0.5) : real(1.0);
+        const real2 u = A.ubuf[soa + size_t(jb + k) * 32];
+        sE += w * (u.x * ylist[jb + k].x + u.y * ylist[jb + k].y);
+      }
+    }
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
+    if( lane == 0 ) red[mb] = sE;
+    __syncthreads();
+    if( tid == 0 ) { real s = real(0.0); for(int w = 0; w < NR; w++) s += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * double(s) - K.bzero_e[ei]; }
+    __syncthreads();
+  }
+  real fix = real(0.0), fiy = real(0.0), fiz = real(0.0), v[9];
+# pragma unroll
+  for(int k = 0; k < 9; k++) v[k] = real(0.0);
+  for(unsigned base = 0; base < ntot; base += SNAP_NN_MAX)
+  {
+  if( base ) { if( mb == 0 ) load_batch(base); __syncthreads(); }
+  const unsigned nn = s_nn;
+  for(unsigned b0 = 0; b0 < nn; b0 += 32)
+  {
+    const unsigned n = b0 + lane; const bool valid = n < nn;
+    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+    real o5[5];
+    snap_sweep_rev<real, TJ>(K, mb, x, y, z, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(MBS), hist + lane, hbase, o5);
+#   pragma unroll
+    for(int k = 0; k < 5; k++) red[(mb * 5 + k) * 32 + lane] = o5[k];
+    __syncthreads();
+    if( mb == 0 && valid )
+    {
+      real s5[5] = { real(0.0), real(0.0), real(0.0), real(0.0), real(0.0) };
+      for(int w2 = 0; w2 < NR; w2++) for(int k = 0; k < 5; k++) s5[k] += red[(w2 * 5 + k) * 32 + lane];
+      // chain rule a, b -> r (same expressions as the forward-mode sweeps)
+      const real wj = nb_w[n];
+      const real rsq = x * x + y * y + z * z, r = xsqrt(rsq);
+      const real rscale0 = K.rfac0 * real(M_PI) / (rc - K.rmin0), theta0 = (r - K.rmin0) * rscale0;
+      real sn, cs; xsincos(theta0, &sn, &cs);
+      const real z0 = r * cs / sn;
+      const real r0inv = xrsqrt(rsq + z0 * z0);
+      const real rinv = real(1.0) / r;
+      const real dz0dr = z0 * rinv - (r * rscale0) * (rsq + z0 * z0) / rsq;
+      const real dr0invdr = -r0inv * r0inv * r0inv * (r + z0 * dz0dr);
+      const real sfac = snap_sfac(K, r, rc) * wj, dsfac = snap_dsfac(K, r, rc) * wj;
+      const real uvec[3] = { x * rinv, y * rinv, z * rinv };
+      real f[3];
+#     pragma unroll
+      for(int k = 0; k < 3; k++)
+      {
+        const real dr0inv = dr0invdr * uvec[k], dz0 = dz0dr * uvec[k];
+        const real da_r = dz0 * r0inv + z0 * dr0inv, da_i = -z * dr0inv + (k == 2 ? -r0inv : real(0.0));
+        const real db_r = y * dr0inv + (k == 1 ? r0inv : real(0.0)), db_i = -x * dr0inv + (k == 0 ? -r0inv : real(0.0));
+        f[k] = real(2.0) * (dsfac * uvec[k] * s5[0] + sfac * (s5[1] * da_r + s5[2] * da_i + s5[3] * db_r + s5[4] * db_i));
+      }
+      fix += f[0]; fiy += f[1]; fiz += f[2];
+      const unsigned g = nb_g[n];
+      atomicAdd(A.fx + g, -double(f[0])); atomicAdd(A.fy + g, -double(f[1])); atomicAdd(A.fz + g, -double(f[2]));
+      if( A.vir )
+      {
+        v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
+        v[3] -= f[1] * x; v[4] -= f[1] * y; v[5] -= f[1] * z;
+        v[6] -= f[2] * x; v[7] -= f[2] * y; v[8] -= f[2] * z;
+      }
+    }
+    __syncthreads();
+  }
+  }
+  if( mb == 0 )
+  {
+#   pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { fix += __shfl_xor_sync(0xffffffffu, fix, o); fiy += __shfl_xor_sync(0xffffffffu, fiy, o); fiz += __shfl_xor_sync(0xffffffffu, fiz, o); }
+    if( A.vir )
+    {
+#     pragma unroll
+      for(int k = 0; k < 9; k++) { for(int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o); }
+    }
+    if( lane == 0 )
+    {
+      atomicAdd(A.fx + ai, double(fix)); atomicAdd(A.fy + ai, double(fiy)); atomicAdd(A.fz + ai, double(fiz));
+      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += double(v[k]); }
+    }
+  }
+}
+
 // ---- compute_yi for 32 atoms at a time: lane = atom -------------------------------------------------------------------
 // One CTA owns one AoSoA block of 32 central atoms: their Utot (idxu_max x 32 complex doubles, 146 KB at 2J = 8) arrives
 // in shared memory with ONE TMA bulk copy, every warp-wide U access is then 32 consecutive 16-byte words (conflict-free),
@@ -924,6 +1271,123 @@ __global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgsT<real> A,
       yr += bj * zr; yi += bj * zi;
     }
     A.ybuf[blk + size_t(task.x) * 32 + lane] = mk2<real>(yr, yi);
+  }
+}
+
+// ---- compute_yi, register-blocked (snap_y2_kernel) ------------------------------------------------------------------------
+// Same CTA shape as snap_y_kernel (32 atoms, Utot block in shared memory, lane = atom), different work item: a block of W <= 5
+// consecutive ma of ONE row (j, mb) of Y.  For a triple (j1, j2, j) and a row pair (mb1, mb2 = mb + s - mb1) the ma sum is a
+// correlation  z[ma] = sum_ma1 c[ma1][ma2] u1[ma1] u2[ma2],  ma2 = ma + s - ma1,  s = (j1 + j2 - j) / 2,  so the W outputs of a
+// block share every u1 element and a sliding window of W elements of u2 that moves by one per step: 2 shared-memory loads per W
+// complex multiply-adds instead of 2 per 1 (the first version ran at 85 % of the shared-memory pipe and 26 % of the FP64 pipe).
+// The Clebsch-Gordan rows are padded with SNAP_YPAD zeros on both sides, so a window position that sticks out of the u2 row
+// needs no test (its u2 index is clamped, its coefficient is zero).  The window registers rotate by unrolling the loop W times.
+
+template<class real, int W>
+__device__ __forceinline__ void snap_y_block(const SnapConstT<real>& K, const SnapYTask task, const SnapYTri* __restrict__ tri, const real* __restrict__ cgpad,
+                                             const real* __restrict__ betat, const real2* __restrict__ U, unsigned lane, real2* __restrict__ yout)
+{
+  real yr[W], yi[W];
+# pragma unroll
+  for(int d = 0; d < W; d++) { yr[d] = real(0.0); yi[d] = real(0.0); }
+  const int mb = task.mb, ma0 = task.ma0;
+  for(int it = 0; it < int(task.ntri); it++)
+  {
+    const SnapYTri q = tri[task.tri0 + it];
+    const int j1 = q.j1, j2 = q.j2, s = q.s, P = q.P;
+    const real* cg = cgpad + q.cgp;
+    const int mb1min = max(0, mb + s - j2), nb = min(j1, mb + s) - mb1min + 1;
+    const int L = max(0, ma0 + s - j2), n_it = min(j1, ma0 + W - 1 + s) - L + 1;
+    const real bj = __ldg(betat + task.tri0 + it);
+    for(int ib = 0; ib < nb; ib++)
+    {
+      const int r1 = mb1min + ib, r2 = mb + s - r1;
+      const real cb = bj * __ldg(cg + r1 * P + SNAP_YPAD + r2);
+      const real2* u1p = U + size_t(K.idxu_block[j1] + r1 * (j1 + 1) + L) * 32 + lane;
+      const real2* u2row = U + size_t(K.idxu_block[j2] + r2 * (j2 + 1)) * 32 + lane;
+      int t = ma0 + s - L;                                     // ma2 of output 0 at ma1 = L  (<= j2)
+      const real* cp = cg + L * P + SNAP_YPAD + t;             // coefficient of output 0; output d: cp[d]; next ma1: cp += P - 1
+      real2 w[W];
+#     pragma unroll
+      for(int d = 0; d < W; d++) w[d] = u2row[size_t(min(t + d, j2)) * 32];
+      real sr[W], si[W];
+#     pragma unroll
+      for(int d = 0; d < W; d++) { sr[d] = real(0.0); si[d] = real(0.0); }
+      for(int k = 0; k < n_it; k += W)
+      {
+#       pragma unroll
+        for(int p = 0; p < W; p++)
+        {
+          if( k + p < n_it )
+          {
+            const real2 u1 = *u1p; u1p += 32;
+#           pragma unroll
+            for(int d = 0; d < W; d++)
+            {
+              const real c = __ldg(cp + d);
+              const real2 u2 = w[(d - p + W) % W];
+              sr[d] += c * (u1.x * u2.x - u1.y * u2.y);
+              si[d] += c * (u1.x * u2.y + u1.y * u2.x);
+            }
+            cp += P - 1; t -= 1;
+            w[(W - 1 - p) % W] = u2row[size_t(max(t, 0)) * 32];
+          }
+        }
+      }
+#     pragma unroll
+      for(int d = 0; d < W; d++) { yr[d] += cb * sr[d]; yi[d] += cb * si[d]; }
+    }
+  }
+  const int jju = K.idxu_block[task.j] + (task.j + 1) * mb + ma0;
+# pragma unroll
+  for(int d = 0; d < W; d++) yout[size_t(jju + d) * 32] = mk2<real>(yr[d], yi[d]);
+}
+
+template<class real>
+__global__ void __launch_bounds__(512, 1) snap_y2_kernel(const SnapArgsT<real> A, const SnapConstT<real> K)
+{
+  extern __shared__ __align__(128) unsigned char ysm[];
+  real2* U = reinterpret_cast<real2*>(ysm);                  // [idxu_max][32]
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int next_task;
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const size_t blk = size_t(blockIdx.x) * K.idxu_max * 32;
+  if( tid == 0 ) { mbar_init(&bar, 1); mbar_fence_init(); next_task = 0; }
+  __syncthreads();
+  if( tid == 0 )
+  {
+    const unsigned bytes = unsigned(K.idxu_max) * 32u * unsigned(sizeof(real2));
+    mbar_arrive_expect_tx(&bar, bytes);
+    bulk_g2s(U, A.ubuf + blk, bytes, &bar);
+  }
+  // the second half of a middle row (2 mb = j, ma > mb) is never used with a non-zero weight, but the force sweep multiplies
+  // it by that zero: it must be finite
+  for(int j = 2; j <= K.twojmax; j += 2)
+    for(int k = int(tid); k < (j / 2) * 32; k += 512)
+      A.ybuf[blk + size_t(K.idxu_block[j] + (j + 1) * (j / 2) + j / 2 + 1 + (k >> 5)) * 32 + (k & 31)] = mk2<real>(real(0.0), real(0.0));
+  // element of this lane's atom (selects the beta row); lanes past the end of the atom list compute on stale data and
+  // write into the padding of ybuf
+  const unsigned slot = A.base + blockIdx.x * 32u + lane;
+  int ei = 0;
+  if( A.type && slot < A.n_atoms ) ei = A.type[A.atoms ? A.atoms[slot] : slot];
+  const real* betat = A.y2beta + size_t(ei) * A.n_y2tri;
+  real2* yout = A.ybuf + blk + lane;
+  mbar_wait(&bar, 0);
+  for(;;)
+  {
+    int t = 0;
+    if( lane == 0 ) t = atomicAdd(&next_task, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if( t >= A.n_y2task ) break;
+    const SnapYTask task = A.y2task[t];
+    switch( task.W )
+    {
+      case 1: snap_y_block<real, 1>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+      case 2: snap_y_block<real, 2>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+      case 3: snap_y_block<real, 3>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+      case 4: snap_y_block<real, 4>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+      default: snap_y_block<real, 5>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+    }
   }
 }
 
@@ -996,6 +1460,7 @@ void xsb_snap_release(xsb_ctx* ctx)
   if( !sd ) return;
   struct { SnapDev* second; } itv{ sd }; auto* it = &itv;
   it->second->cglist32.release(); it->second->betaz32.release(); it->second->betaz_sort32.release(); it->second->idxz.release(); it->second->cglist.release(); it->second->betaz.release(); it->second->err.release();
+  it->second->y2tri.release(); it->second->y2task.release(); it->second->y2cg.release(); it->second->y2beta.release(); it->second->y2cg32.release(); it->second->y2beta32.release();
   it->second->zsort.release(); it->second->betaz_sort.release(); it->second->ytask.release(); it->second->ubuf.release(); it->second->ybuf.release(); it->second->nbtab.release(); it->second->nbcnt.release(); it->second->clk.release();
   delete it->second; ctx->snap = nullptr;
 }
@@ -1032,13 +1497,23 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
   // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
   // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)
   constexpr bool DIRSPLIT = TJ >= 7;
-  const bool dircta = DIRSPLIT && getenv("XSB_SNAP_FKERNEL") == nullptr;      // A/B switch: XSB_SNAP_FKERNEL=1 -> the 15-warp CTA per atom
+  // force kernel: reverse mode (snap_fr_kernel) unless XSB_SNAP_FKERNEL selects one of the forward-mode kernels for A/B:
+  // 2 -> one CTA per (atom, direction) at 2J >= 7 / one thread per row with all three directions below; 1 -> the 15-warp CTA
+  const char* fk = getenv("XSB_SNAP_FKERNEL");
+  const bool reverse = fk == nullptr || fk[0] == '0';
+  const bool dircta = !reverse && DIRSPLIT && fk[0] != '1';
+  const size_t frsmem = size_t(S->K.idxu_max + 32 * (SnapHist<TJ>::total() ? SnapHist<TJ>::total() : 1)) * sizeof(typename R2<real>::type)
+                      + size_t(32) * SNAP_MBOX_STRIDE(MB ? MB : 1) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
+                      + size_t(NR) * 5 * 32 * sizeof(real) + 64;
+  if( reverse ) { if( xf ) { if( (rc = setattr(snap_fr_kernel<real, TJ, true>, frsmem)) ) return rc; } else { if( (rc = setattr(snap_fr_kernel<real, TJ, false>, frsmem)) ) return rc; } }
   const size_t fdsmem = size_t(S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
                       + size_t(NR) * 32 * sizeof(real) + 64;
   if( dircta ) { if( xf ) { if( (rc = setattr(snap_fd_kernel<real, TJ, true>, fdsmem)) ) return rc; } else { if( (rc = setattr(snap_fd_kernel<real, TJ, false>, fdsmem)) ) return rc; } }
   if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, true, 3>, smem)) ) return rc; }
   else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, false, 3>, smem)) ) return rc; }
   if( (rc = setattr(snap_y_kernel<real, TJ>, ysmem)) ) return rc;
+  if( (rc = setattr(snap_y2_kernel<real>, ysmem)) ) return rc;
+  const bool yold = getenv("XSB_SNAP_YKERNEL") != nullptr;        // A/B switch: the one-element-per-work-item kernel
   for(unsigned base = 0; base < A.n_atoms; base += chunk)
   {
     const unsigned cnt = std::min(chunk, A.n_atoms - base);
@@ -1046,9 +1521,15 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
     if( xf ) snap_force_kernel<real, TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
     else     snap_force_kernel<real, TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
     XSB_LAUNCH_CHECK(ctx);
-    snap_y_kernel<real, TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
+    if( yold ) snap_y_kernel<real, TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
+    else       snap_y2_kernel<real><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
     XSB_LAUNCH_CHECK(ctx);
-    if( dircta )
+    if( reverse )
+    {
+      if( xf ) snap_fr_kernel<real, TJ, true><<<cnt, NT, frsmem, ctx->stream>>>(A, X, KK);
+      else     snap_fr_kernel<real, TJ, false><<<cnt, NT, frsmem, ctx->stream>>>(A, X, KK);
+    }
+    else if( dircta )
     {
       if( xf ) snap_fd_kernel<real, TJ, true><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
       else     snap_fd_kernel<real, TJ, false><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
@@ -1133,6 +1614,68 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
       for(int e = 0; e < p->nelements; e++) bsort[size_t(e) * order.size() + i] = betaz[size_t(e) * order.size() + order[i]];
     }
   }
+  // snap_y2_kernel tables: triples grouped by j, zero-padded Clebsch-Gordan rows, beta per (element, triple), work items =
+  // blocks of <= 5 consecutive ma of one row (j, mb), most expensive first
+  std::vector<SnapYTri> y2tri; std::vector<SnapYTask> y2task; std::vector<double> y2cg, y2beta;
+  {
+    struct TJ3 { int j1, j2, j; };
+    std::vector<TJ3> tl;
+    std::vector<int> first(p->twojmax + 2, 0);
+    for(int j = 0; j <= p->twojmax; j++)
+    {
+      first[j] = int(tl.size());
+      for(int j1 = 0; j1 <= p->twojmax; j1++) for(int j2 = 0; j2 <= j1; j2++)
+        if( j >= j1 - j2 && j <= std::min(p->twojmax, j1 + j2) && ((j1 + j2 - j) & 1) == 0 ) tl.push_back({ j1, j2, j });
+    }
+    first[p->twojmax + 1] = int(tl.size());
+    y2beta.assign(size_t(p->nelements) * tl.size(), 0.0);
+    for(size_t t = 0; t < tl.size(); t++)
+    {
+      const TJ3 q = tl[t];
+      const int P = q.j2 + 1 + 2 * SNAP_YPAD, src = T.cg_block[T.b3(q.j1, q.j2, q.j)];
+      SnapYTri y{ (unsigned char)q.j1, (unsigned char)q.j2, (unsigned char)((q.j1 + q.j2 - q.j) / 2), (unsigned char)P, int(y2cg.size()) };
+      y2tri.push_back(y);
+      for(int m1 = 0; m1 <= q.j1; m1++) for(int c = 0; c < P; c++)
+      {
+        const int m2 = c - SNAP_YPAD;
+        y2cg.push_back(m2 >= 0 && m2 <= q.j2 ? T.cglist[size_t(src) + m1 * (q.j2 + 1) + m2] : 0.0);
+      }
+      SnapZ z{}; z.j1 = (unsigned char)q.j1; z.j2 = (unsigned char)q.j2; z.j = (unsigned char)q.j;
+      for(int e = 0; e < p->nelements; e++) y2beta[size_t(e) * tl.size() + t] = T.betaj(z, p->beta + size_t(e) * (T.ncoeff + 1) + 1);
+    }
+    std::vector<std::pair<long, SnapYTask>> tmp;
+    for(int j = 0; j <= p->twojmax; j++) for(int mb = 0; 2 * mb <= j; mb++)
+    {
+      const int n = 2 * mb == j ? mb + 1 : j + 1;          // the second half of a middle row is never used (weight 0)
+      int widths[3] = { n, 0, 0 };
+      if( n == 6 ) { widths[0] = 3; widths[1] = 3; } else if( n == 7 ) { widths[0] = 4; widths[1] = 3; } else if( n == 8 ) { widths[0] = 4; widths[1] = 4; } else if( n == 9 ) { widths[0] = 5; widths[1] = 4; }
+      for(int b = 0, ma0 = 0; b < 3 && widths[b]; ma0 += widths[b], b++)
+      {
+        const int W = widths[b];
+        long cost = 0;
+        for(int t = first[j]; t < first[j + 1]; t++)
+        {
+          const int j1 = tl[t].j1, j2 = tl[t].j2, s = (j1 + j2 - j) / 2;
+          const int nb = std::min(j1, mb + s) - std::max(0, mb + s - j2) + 1, nit = std::min(j1, ma0 + W - 1 + s) - std::max(0, ma0 + s - j2) + 1;
+          cost += long(nb) * (long(nit) * (6 * W + 6) + 4 * W + 12) + 10;
+        }
+        tmp.push_back({ cost, SnapYTask{ (unsigned char)j, (unsigned char)mb, (unsigned char)ma0, (unsigned char)W, (unsigned short)first[j], (unsigned short)(first[j + 1] - first[j]) } });
+      }
+    }
+    std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<long, SnapYTask>& a, const std::pair<long, SnapYTask>& b) { return a.first > b.first; });
+    for(auto& t : tmp) y2task.push_back(t.second);
+  }
+  S->n_y2tri = int(y2tri.size()); S->n_y2task = int(y2task.size());
+  std::vector<float> y2cg32(y2cg.begin(), y2cg.end()), y2beta32(y2beta.begin(), y2beta.end());
+  XSB_CUDA(ctx, S->y2tri.reserve(y2tri.size())); XSB_CUDA(ctx, S->y2task.reserve(y2task.size())); XSB_CUDA(ctx, S->y2cg.reserve(y2cg.size())); XSB_CUDA(ctx, S->y2beta.reserve(y2beta.size()));
+  XSB_CUDA(ctx, S->y2cg32.reserve(y2cg32.size())); XSB_CUDA(ctx, S->y2beta32.reserve(y2beta32.size()));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2tri.p, y2tri.data(), y2tri.size() * sizeof(SnapYTri), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2task.p, y2task.data(), y2task.size() * sizeof(SnapYTask), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2cg.p, y2cg.data(), y2cg.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2beta.p, y2beta.data(), y2beta.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2cg32.p, y2cg32.data(), y2cg32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaMemcpyAsync(S->y2beta32.p, y2beta32.data(), y2beta32.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging vectors of this block die at the end of the function; keep it simple
   S->n_ytask = int(tasks.size());
   XSB_CUDA(ctx, S->zsort.reserve(zsort.size())); XSB_CUDA(ctx, S->betaz_sort.reserve(bsort.size())); XSB_CUDA(ctx, S->ytask.reserve(tasks.size()));
   XSB_CUDA(ctx, cudaMemcpyAsync(S->zsort.p, zsort.data(), zsort.size() * sizeof(SnapZ), cudaMemcpyHostToDevice, ctx->stream));
@@ -1195,14 +1738,14 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   {
     SnapArgsT<float> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
                         S->idxz.p, S->cglist32.p, S->betaz32.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
-                        S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort32.p, S->ytask.p, S->n_ytask };
+                        S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort32.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg32.p, S->y2beta32.p, S->y2task.p, S->n_y2tri, S->n_y2task };
     rc = go(A, S->K32);
   }
   else
   {
     SnapArgsT<double> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
                          S->idxz.p, S->cglist.p, S->betaz.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
-                         S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask };
+                         S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg.p, S->y2beta.p, S->y2task.p, S->n_y2tri, S->n_y2task };
     rc = go(A, S->K);
   }
   ctx->prof_end(XSB_PROF_SNAP);
