@@ -514,11 +514,41 @@ def run_xsb(args):
         ctx.backup_r()
         ctx.sync()
         state["rebuilds"] += 1; state["since"] = 0
+        graph["flags"] = None                          # a recorded step belongs to one list generation
         state["move_s"] += t1 - t0; state["rebuild_s"] += time.perf_counter() - t0
 
     mode = {"flags": 0}                               # xsb.FLAG_MIXED during the extra mixed-precision measurement
 
+    graph = {"id": None, "flags": None}
+    use_graph = args.graph and world == 1 and W.xform0 is None and not (args.separate_integrator or args.sync_displ)
+
+    def record():
+        # the regular step (integrator pass, ghost update, zero + force operators) as ONE launch: xsb_step_capture_*
+        if graph["id"] is not None:
+            ctx.step_release(graph["id"])
+        ctx.step_capture_begin()
+        ctx.verlet_boundary_async(masses, DT); ctx.ghost_update(POS); W.forces(ctx, xsb, mode["flags"])
+        graph["id"] = ctx.step_capture_end(); graph["flags"] = mode["flags"]
+
+    def step_recorded():
+        # same decisions as step(), on results one step older (the host must not wait for the step it is about to follow):
+        # xsb_displ_poll(1) = the maxima of two steps ago, three step displacements of margin
+        over = False
+        if state["since"] >= 2:
+            d, s1 = ctx.displ_poll(1)
+            over = d + 3.0 * s1 > 0.5 * W.skin
+        state["since"] += 1; state["step"] += 1
+        if over or state["since"] >= args.rebuild_every:
+            ctx.verlet_boundary_async(masses, DT); rebuild(); W.forces(ctx, xsb, mode["flags"])
+        else:
+            if graph["flags"] != mode["flags"]:
+                record()
+            ctx.step_replay(graph["id"])
+
     def step():
+        nonlocal use_graph
+        if use_graph:
+            return step_recorded()
         # one velocity-Verlet step, cut at the displacement check: force_to_accel + push_f_v close the previous step,
         # push_f_v_r + push_f_v + particle_displ_over open this one (xsb_verlet_boundary = those five operators in one pass)
         if args.separate_integrator:
@@ -591,6 +621,19 @@ def run_xsb(args):
     launches = ctx.launches - l0
     rebuilds_timed = state["rebuilds"] - rb0; rebuild_s_timed = state["rebuild_s"]; move_s_timed = state["move_s"]
     prof = ctx.profile_read()
+    prof_note = None
+    if use_graph:
+        # a recorded step has no per-operator events: the kernel times behind `roofline` come from direct-call steps
+        # right after the timed region (same list, same L2 treatment), the step time itself from the recorded steps above
+        use_graph = False
+        ctx.profile_enable(True)
+        for _ in range(min(10, args.steps)):
+            if flush is not None:
+                flush.fill_(1); torch.cuda.synchronize()
+            step()
+        prof = ctx.profile_read()
+        use_graph = True
+        prof_note = "step = one CUDA-graph launch (xsb_step_replay); per-kernel times from %d direct-call steps after the timed region" % min(10, args.steps)
     ctx.profile_enable(False)
     clk = clocks.stop() if clocks else None
     ms_ranks = allranks(max(ms_dev, 0.0))
@@ -732,7 +775,7 @@ def run_xsb(args):
                        "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
                        "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown, "ranks": per_rank,
                        "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport(),
-                       "force_checksum_sum_abs": fsum, "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
+                       "recorded_step": prof_note, "force_checksum_sum_abs": fsum, "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
@@ -755,11 +798,13 @@ def main():
     ap.add_argument("--sync-displ", action="store_true", help="blocking particle_displ_over read-back every step (xsb_verlet_boundary) instead of the one-step-late check")
     ap.add_argument("--separate-integrator", action="store_true", help="five integrator operators as separate kernels instead of xsb_verlet_boundary")
     ap.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"], help="rewrite a 160 MiB buffer between timed steps; auto: on for c1, whose working set fits the 126 MB L2")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="regular steps as one CUDA-graph launch (xsb_step_capture_*); auto: on for c1 (launch-bound), one GPU only")
     ap.add_argument("--no-mixed", action="store_true", help="skip the extra mixed-precision measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.flush_l2 = args.flush_l2 == "on" or (args.flush_l2 == "auto" and args.workload == "c1")
+    args.graph = args.graph == "on" or (args.graph == "auto" and args.workload == "c1")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
     "xsb_verlet_boundary_async", "xsb_displ_poll", "xsb_ghost_transport", "xsb_eam_inner_skin", "xsb_eam_sublist_stats",
     "xsb_fields_upload_async", "xsb_fields_download_async", "xsb_copy_wait", "xsb_out_of_domain_count",
+    "xsb_step_capture_begin", "xsb_step_capture_end", "xsb_step_replay", "xsb_step_release",
 ]
 
 
@@ -103,6 +104,8 @@ def load_library():
     L.xsb_grid_set_xform.argtypes = [vp, C.POINTER(dbl)]
     L.xsb_measure_peaks.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
     L.xsb_profile_enable.argtypes = [vp, i32]
+    L.xsb_step_capture_begin.argtypes = [vp]; L.xsb_step_capture_end.argtypes = [vp, C.POINTER(C.c_int)]
+    L.xsb_step_replay.argtypes = [vp, i32]; L.xsb_step_release.argtypes = [vp, i32]
     L.xsb_profile_read.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(u64)]
     L.xsb_grid_set.argtypes = [vp, C.POINTER(GridDesc)]
     L.xsb_particles_set_cells.argtypes = [vp, vp]
@@ -345,6 +348,21 @@ class Context:
         f = C.c_int()
         self._ck(self.L.xsb_snap_overflow(self.h, C.byref(f)), "xsb_snap_overflow")
         return bool(f.value)
+
+    # ---- recorded steps (one CUDA graph launch per step)
+    def step_capture_begin(self):
+        self._ck(self.L.xsb_step_capture_begin(self.h), "xsb_step_capture_begin")
+
+    def step_capture_end(self):
+        sid = C.c_int(-1)
+        self._ck(self.L.xsb_step_capture_end(self.h, C.byref(sid)), "xsb_step_capture_end")
+        return sid.value
+
+    def step_replay(self, sid):
+        self._ck(self.L.xsb_step_replay(self.h, int(sid)), "xsb_step_replay")
+
+    def step_release(self, sid):
+        self._ck(self.L.xsb_step_release(self.h, int(sid)), "xsb_step_release")
 
     # ---- profiling (CUDA events on the context's stream)
     PROF_TAGS = ["nbr_build", "pair", "eam_rho", "eam_rho2emb", "eam_force", "ghost", "integrate", "snap", "move"]

@@ -465,6 +465,15 @@ static int verlet_boundary_launch(xsb_ctx* ctx, int n_types, const double* mass,
 
 int xsb_internal_allreduce_max(xsb_ctx* ctx, double* dev_inout, int count);      // xsb_ghost.cu
 
+int xsb_internal_displ_ring_init(xsb_ctx* ctx)
+{
+  if( ctx->displ_host ) return XSB_OK;
+  XSB_CUDA(ctx, cudaMallocHost((void**)&ctx->displ_host, sizeof(double) * 2 * XSB_DISPL_RING));
+  XSB_CUDA(ctx, ctx->displ_dev.reserve(2 * (XSB_DISPL_RING + 1)));
+  for(int i = 0; i < XSB_DISPL_RING; i++) XSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->displ_ev[i], cudaEventDisableTiming));
+  return XSB_OK;
+}
+
 extern "C" {
 
 // Same pass without a host read-back: the two maxima are all-reduced (MAX) over the ranks on the stream and land in a ring
@@ -474,17 +483,14 @@ extern "C" {
 int xsb_verlet_boundary_async(xsb_ctx* ctx, int n_types, const double* mass, double dt)
 {
   XSB_ENTER(ctx);
-  if( !ctx->displ_host )
-  {
-    XSB_CUDA(ctx, cudaMallocHost((void**)&ctx->displ_host, sizeof(double) * 2 * XSB_DISPL_RING));
-    XSB_CUDA(ctx, ctx->displ_dev.reserve(2 * XSB_DISPL_RING));
-    for(int i = 0; i < XSB_DISPL_RING; i++) XSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->displ_ev[i], cudaEventDisableTiming));
-  }
-  const int slot = int(ctx->displ_seq % XSB_DISPL_RING);
+  int rc = xsb_internal_displ_ring_init(ctx); if( rc ) return rc;
+  // while a step is being recorded the result goes to a fixed extra slot; xsb_step_replay copies it into the ring
+  const int slot = ctx->capturing ? XSB_DISPL_RING : int(ctx->displ_seq % XSB_DISPL_RING);
   unsigned long long* out = ctx->displ_dev.p + 2 * slot;
-  int rc = verlet_boundary_launch(ctx, n_types, mass, dt, out); if( rc ) return rc;
+  rc = verlet_boundary_launch(ctx, n_types, mass, dt, out); if( rc ) return rc;
   rc = xsb_internal_allreduce_max(ctx, reinterpret_cast<double*>(out), 2); if( rc ) return rc;      // squares are non-negative: MAX on the doubles
   if( ctx->sub_ctl.p ) { xsb::sub_accum_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, out + 1); XSB_LAUNCH_CHECK(ctx); }
+  if( ctx->capturing ) { ctx->cap_verlet = true; return XSB_OK; }
   XSB_CUDA(ctx, cudaMemcpyAsync(ctx->displ_host + 2 * slot, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XSB_CUDA(ctx, cudaEventRecord(ctx->displ_ev[slot], ctx->stream));
   ctx->displ_seq++;

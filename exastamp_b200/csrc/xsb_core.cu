@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) cell_tables_kernel(unsigned ncells, const
 // done on the host (ncells entries), everything per particle on the device
 int xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* off)
 {
+  ctx->graph_gen++;
   const uint64_t nc = ctx->ncells, n = off[nc];
   ctx->h_cell_off.assign(off, off + nc + 1);
   std::vector<unsigned> tab(2 * (nc + 1));            // [0, nc] cell start ; [nc+1, 2nc+1] own-particle prefix
@@ -296,6 +297,7 @@ void xsb_destroy(xsb_ctx* ctx)
   if( ctx->copy_down ) { cudaStreamSynchronize(ctx->copy_down); cudaStreamDestroy(ctx->copy_down); }
   for(cudaEvent_t e : { ctx->ev_up_done, ctx->ev_up_free, ctx->ev_down_ready, ctx->ev_down_done }) if( e ) cudaEventDestroy(e);
   for(auto& v : ctx->prof_ev) for(cudaEvent_t e : v) cudaEventDestroy(e);
+  for(auto& sg : ctx->step_graphs) if( sg.exec ) cudaGraphExecDestroy(sg.exec);
   if( ctx->stream ) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -385,6 +387,83 @@ int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms)
   return XSB_OK;
 }
 
+// ---- recorded steps -----------------------------------------------------------------------------------------------------
+// A small system (C1: 131 k atoms, 0.1 ms of kernels per step) is bound by the launch path, not by the kernels: the operator
+// calls of a regular step (integrator pass, ghost update, zero, force operators) are recorded once per neighbour-list
+// generation as a CUDA graph and re-issued with one launch.  Everything an entry point passes to a kernel by value is frozen
+// at recording time, so a recorded step is valid until the particle layout, the list or the cell matrix change (graph_gen).
+int xsb_step_capture_begin(xsb_ctx* ctx)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, !ctx->capturing, XSB_ERR_STATE, "a step is already being recorded");
+  XSB_REQUIRE(ctx, ctx->nranks == 1, XSB_ERR_UNSUPPORTED, "recorded steps are limited to one rank (the peer-memory ghost exchange passes its epoch by value)");
+  XSB_REQUIRE(ctx, ctx->inner_skin == 0.0, XSB_ERR_UNSUPPORTED, "recorded steps and the EAM inner skin (host-side epochs choose the pass) exclude each other");
+  int rc = xsb_internal_displ_ring_init(ctx); if( rc ) return rc;      // nothing may be allocated while the stream is capturing
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cap_launch0 = ctx->launches; ctx->cap_verlet = false;
+  XSB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  return XSB_OK;
+}
+
+int xsb_step_capture_end(xsb_ctx* ctx, int* step_id)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, ctx->capturing, XSB_ERR_STATE, "xsb_step_capture_begin must be called first");
+  ctx->capturing = false;
+  const uint64_t nodes = ctx->launches - ctx->cap_launch0;
+  ctx->launches = ctx->cap_launch0;                        // recorded, not executed
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  if( e != cudaSuccess || g == nullptr )
+  {
+    cudaGetLastError();
+    return ctx->fail(XSB_ERR_CUDA, "recording failed (%s): an entry point that waits for the device, reads a result back or allocates was called while recording",
+                     cudaGetErrorString(e));
+  }
+  xsb_ctx::StepGraph sg; sg.nodes = nodes; sg.gen = ctx->graph_gen; sg.verlet = ctx->cap_verlet;
+  e = cudaGraphInstantiate(&sg.exec, g, 0);
+  cudaGraphDestroy(g);
+  if( e != cudaSuccess ) return ctx->fail(XSB_ERR_CUDA, "cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+  int id = -1;
+  for(size_t i = 0; i < ctx->step_graphs.size(); i++) if( !ctx->step_graphs[i].exec ) { id = int(i); break; }
+  if( id < 0 ) { id = int(ctx->step_graphs.size()); ctx->step_graphs.push_back(sg); } else ctx->step_graphs[size_t(id)] = sg;
+  if( step_id ) *step_id = id;
+  return XSB_OK;
+}
+
+int xsb_step_replay(xsb_ctx* ctx, int step_id)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, !ctx->capturing, XSB_ERR_STATE, "a step is being recorded");
+  XSB_REQUIRE(ctx, step_id >= 0 && size_t(step_id) < ctx->step_graphs.size() && ctx->step_graphs[size_t(step_id)].exec, XSB_ERR_INVALID, "unknown recorded step");
+  const xsb_ctx::StepGraph& sg = ctx->step_graphs[size_t(step_id)];
+  XSB_REQUIRE(ctx, sg.gen == ctx->graph_gen, XSB_ERR_STATE, "the particle layout, the neighbour list or the cell matrix changed since this step was recorded");
+  XSB_CUDA(ctx, cudaGraphLaunch(sg.exec, ctx->stream));
+  ctx->launches += sg.nodes;
+  // host-side bookkeeping the recorded calls would have done: positions moved (any cached sub-list is stale for later
+  // direct calls), and the integrator pass's maxima go into the result ring
+  ctx->pos_epoch += 2; ctx->foreign_epoch++;
+  if( sg.verlet )
+  {
+    const int slot = int(ctx->displ_seq % XSB_DISPL_RING);
+    XSB_CUDA(ctx, cudaMemcpyAsync(ctx->displ_host + 2 * slot, ctx->displ_dev.p + 2 * XSB_DISPL_RING, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    XSB_CUDA(ctx, cudaEventRecord(ctx->displ_ev[slot], ctx->stream));
+    ctx->displ_seq++;
+  }
+  return XSB_OK;
+}
+
+int xsb_step_release(xsb_ctx* ctx, int step_id)
+{
+  XSB_ENTER(ctx);
+  XSB_REQUIRE(ctx, step_id >= 0 && size_t(step_id) < ctx->step_graphs.size() && ctx->step_graphs[size_t(step_id)].exec, XSB_ERR_INVALID, "unknown recorded step");
+  XSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaGraphExecDestroy(ctx->step_graphs[size_t(step_id)].exec);
+  ctx->step_graphs[size_t(step_id)] = xsb_ctx::StepGraph{};
+  return XSB_OK;
+}
+
 int xsb_sync(xsb_ctx* ctx)
 {
   XSB_ENTER(ctx);
@@ -396,6 +475,7 @@ int xsb_grid_set(xsb_ctx* ctx, const xsb_grid_desc* g)
 {
   XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, g != nullptr, XSB_ERR_INVALID, "null grid");
+  ctx->graph_gen++;
   XSB_REQUIRE(ctx, g->dims[0] > 0 && g->dims[1] > 0 && g->dims[2] > 0, XSB_ERR_INVALID, "grid dims must be positive");
   XSB_REQUIRE(ctx, g->ghost_layers >= 0 && 2 * g->ghost_layers < g->dims[0] && 2 * g->ghost_layers < g->dims[1] && 2 * g->ghost_layers < g->dims[2],
               XSB_ERR_INVALID, "ghost_layers inconsistent with dims");
@@ -415,6 +495,7 @@ int xsb_grid_set_xform(xsb_ctx* ctx, const double xform[9])
   XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, xform != nullptr, XSB_ERR_INVALID, "null xform");
   XSB_REQUIRE(ctx, ctx->grid_set, XSB_ERR_STATE, "xsb_grid_set must be called first");
+  ctx->graph_gen++;
   bool ident = true;
   double dx2 = 0.0, inv[9] = {1,0,0,0,1,0,0,0,1}, inv2 = 0.0;
   if( !ctx->grid.xform_is_identity ) xsb::inverse3(ctx->grid.xform, inv);

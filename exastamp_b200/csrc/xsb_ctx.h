@@ -185,6 +185,14 @@ struct xsb_ctx
   bool up_pending = false, down_pending = false;
   xsb::DevBuf<double> stage_up, stage_down;
 
+  // recorded steps (xsb_step_capture_begin / _end / xsb_step_replay, xsb_core.cu): the kernels a sequence of operator calls
+  // enqueues, kept as an instantiated CUDA graph and re-issued with one launch
+  struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t nodes = 0, gen = 0; bool verlet = false; };
+  std::vector<StepGraph> step_graphs;
+  bool capturing = false, cap_verlet = false;
+  uint64_t cap_launch0 = 0;
+  uint64_t graph_gen = 1;                     // bumped by everything that changes what a recorded step baked in (layout, list, cell matrix)
+
   // per-operator device timing (CUDA events on this context's stream), see xsb_profile_*
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev[XSB_PROF_COUNT_];   // begin/end pairs
@@ -192,13 +200,13 @@ struct xsb_ctx
   cudaEvent_t timer_ev[2] = { nullptr, nullptr };
   void prof_begin(int tag)
   {
-    if( !prof_on ) return;
+    if( !prof_on || capturing ) return;
     if( prof_used[tag] + 2 > prof_ev[tag].size() ) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_ev[tag].push_back(a); prof_ev[tag].push_back(b); }
     cudaEventRecord(prof_ev[tag][prof_used[tag]], stream);
   }
   void prof_end(int tag)
   {
-    if( !prof_on ) return;
+    if( !prof_on || capturing ) return;
     cudaEventRecord(prof_ev[tag][prof_used[tag] + 1], stream);
     prof_used[tag] += 2;
   }
@@ -238,6 +246,8 @@ int  xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, 
 void xsb_snap_release(xsb_ctx* ctx);
 // inner-skin budget (SubCtl): every atom may have moved by up to `displacement` more (xsb_assign.cu)
 int  xsb_internal_sub_account(xsb_ctx* ctx, double displacement);
+// pinned result ring of xsb_verlet_boundary_async (xsb_assign.cu); idempotent
+int  xsb_internal_displ_ring_init(xsb_ctx* ctx);
 
 namespace xsb
 {

@@ -551,6 +551,7 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
   XSB_ENTER(ctx);
   XSB_REQUIRE(ctx, ctx->h_cell_off.size() == ctx->ncells + 1, XSB_ERR_STATE, "grid/particles not set");
   XSB_REQUIRE(ctx, nbh_dist_lab > 0.0, XSB_ERR_INVALID, "nbh_dist_lab must be > 0");
+  ctx->graph_gen++;
   if( cfg )
   {
     int cs = cfg->chunk_size;

@@ -33,8 +33,7 @@ constexpr int SNAP_NN_TAB = 192;     // in-range neighbours per atom the Utot ke
 struct SnapZ { unsigned char j1, j2, j, ma1min, ma2max, na, mb1min, mb2max, nb, pad; unsigned short jju; int cgoff; };   // 16 B
 
 // snap_y2_kernel tables (see the kernel)
-constexpr int SNAP_YPAD = 4;                       // W - 1 for the widest block
-struct SnapYTri { unsigned char j1, j2, s, P; int cgp; };         // P = j2 + 1 + 2 SNAP_YPAD = row stride of the padded table at cgp
+struct SnapYTri { unsigned char j1, j2, s, P; int cgp; };         // table of the triple at cgp: D[ma2][m], row stride P = j + 1 rounded up to even
 struct SnapYTask { unsigned char j, mb, ma0, W; unsigned short tri0, ntri; };
 
 // per-launch constants in the arithmetic type of the kernels (double, or float for XSB_FLAG_MIXED)
@@ -79,7 +78,7 @@ struct SnapDev
   DevBuf<double> nbtab; DevBuf<unsigned> nbcnt;                                        // in-range neighbours of the chunk's atoms (Utot kernel -> force kernel)
   SnapConstT<float> K32{};                                                               // the same constants rounded to float (XSB_FLAG_MIXED)
   DevBuf<float> cglist32, betaz32, betaz_sort32;
-  DevBuf<SnapYTri> y2tri; DevBuf<SnapYTask> y2task; DevBuf<double> y2cg, y2beta; DevBuf<float> y2cg32, y2beta32; int n_y2tri = 0, n_y2task = 0;   // snap_y2_kernel
+  DevBuf<SnapYTri> y2tri; DevBuf<SnapYTask> y2task; DevBuf<double> y2cg, y2beta; DevBuf<float> y2cg32, y2beta32; int n_y2tri = 0, n_y2task = 0, n_y2cg = 0;   // snap_y2_kernel
   double rcut_max = 0.0;
   bool overflowed = false;       // a call hit SNAP_NN_MAX since xsb_snap_overflow() was last read
 };
@@ -590,7 +589,7 @@ struct SnapArgsT
   double* nbtab; unsigned* nbcnt;
   const SnapZ* __restrict__ zsort; const real* __restrict__ betaz_sort; const int4* __restrict__ ytask; int n_ytask;
   // snap_y2_kernel: triples sorted by j, padded Clebsch-Gordan rows, beta per (element, triple), work items
-  const SnapYTri* __restrict__ y2tri; const real* __restrict__ y2cg; const real* __restrict__ y2beta; const SnapYTask* __restrict__ y2task; int n_y2tri, n_y2task;
+  const SnapYTri* __restrict__ y2tri; const real* __restrict__ y2cg; const real* __restrict__ y2beta; const SnapYTask* __restrict__ y2task; int n_y2tri, n_y2task, n_y2cg;
 };
 
 // PHASE 0: fused (everything in one CTA, kept for reference / small runs); PHASE 1: Utot only -> A.ubuf; PHASE 3: reads Utot
@@ -830,6 +829,109 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
     }
   }
   mark(5);
+}
+
+// ---- Utot kernel of the split pipeline: CTA per atom, J/2+1 warps = rows, lane = neighbour -------------------------------
+// The same steps as PHASE 1 of snap_force_kernel (filter, Utot sweep, mirror, AoSoA store, neighbour table for the force
+// kernel) without the fused kernel's Y / derivative state: a fifth of its shared memory and under 80 registers, so five and
+// more CTAs share an SM and hide each other's serial prologue (list walk: four dependent global loads) and level barriers.
+template<class real, int TJ, bool XFORM>
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 8 : 4) snap_u_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
+{
+  constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
+  constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = MB ? MB : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real2* utot = reinterpret_cast<real2*>(smem_raw);                 // [idxu_max]
+  real2* mbox = utot + K.idxu_max;                                    // [32][MBS] (odd stride)
+  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(MBS));        // [SNAP_NN_MAX] x 5
+  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
+  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
+  __shared__ unsigned s_nn;
+  __shared__ unsigned long long s_e;
+  const unsigned tid = threadIdx.x, lane = tid & 31u; const int mb = int(tid >> 5);
+  const unsigned slot = A.base + blockIdx.x;
+  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
+  const size_t soa = (size_t(blockIdx.x >> 5) * K.idxu_max) * 32 + (blockIdx.x & 31u);    // + jju * 32
+  const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
+  const int ei = A.type ? A.type[ai] : 0;
+  for(int k = tid; k < K.idxu_max; k += NT) utot[k] = mk2<real>(real(0.0), real(0.0));
+  __syncthreads();
+  for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
+  const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
+  double* const tab = A.nbtab + size_t(blockIdx.x) * 6 * SNAP_NN_TAB;
+  unsigned tot = 0;
+  for(unsigned long long from = e0; ; )
+  {
+    // neighbour filter (warp 0, ballot compaction keeps the list order): rsq < cutsq_ij && rsq > 1e-20; whole 32-entry chunks
+    // of the list, at most SNAP_NN_MAX in-range neighbours per batch
+    if( mb == 0 )
+    {
+      unsigned nn = 0;
+      unsigned long long e = from;
+      for(; e < e1; e += 32)
+      {
+        const unsigned long long ee = e + lane;
+        bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
+        if( ee < e1 )
+        {
+          g = A.nbh_idx[ee];
+          dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
+          apply_xform<XFORM>(X, dx, dy, dz);
+          const int ej = A.type ? A.type[g] : 0;
+          rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
+          const double d2 = dx * dx + dy * dy + dz * dz;
+          in = d2 < rc * rc && d2 > 1e-20;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if( nn + __popc(m) > SNAP_NN_MAX ) break;                 // this chunk opens the next batch (same decision on every lane)
+        const unsigned sl = nn + __popc(m & ((1u << lane) - 1u));
+        if( in )
+        {
+          nb_x[sl] = real(dx); nb_y[sl] = real(dy); nb_z[sl] = real(dz); nb_w[sl] = real(wj); nb_rc[sl] = real(rc); nb_g[sl] = g;
+          const unsigned o = tot + sl;
+          if( o < SNAP_NN_TAB )
+          {
+            tab[o] = double(real(dx)); tab[SNAP_NN_TAB + o] = double(real(dy)); tab[2 * SNAP_NN_TAB + o] = double(real(dz));
+            tab[3 * SNAP_NN_TAB + o] = double(real(wj)); tab[4 * SNAP_NN_TAB + o] = double(real(rc)); tab[5 * SNAP_NN_TAB + o] = __longlong_as_double((long long)g);
+          }
+        }
+        nn += __popc(m);
+      }
+      if( lane == 0 ) { s_nn = nn; s_e = e; }
+    }
+    __syncthreads();
+    const unsigned nn = s_nn; const unsigned long long nxt = s_e;
+    real dummy[3];
+    for(unsigned b0 = 0; b0 < nn; b0 += 32)
+    {
+      const unsigned n = b0 + lane; const bool valid = n < nn;
+      const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
+      snap_sweep<real, TJ, false>(K, mb, valid, x, y, z, w, rc, utot, nullptr, mbox + lane * SNAP_MBOX_STRIDE(MBS), dummy);
+    }
+    __syncthreads();                      // the next filter call overwrites the neighbour arrays
+    tot += nn;
+    if( nxt >= e1 ) break;
+    from = nxt;
+  }
+  if( tid == 0 )
+  {
+    if( tot > SNAP_NN_TAB ) { atomicExch(A.err, 1); tot = SNAP_NN_TAB; }
+    A.nbcnt[blockIdx.x] = tot;
+  }
+  // right half by inversion symmetry u[j-mb][j-ma] = (-1)^(mb+ma) conj(u[mb][ma]); middle row: second half from the first
+  for(int j = 1; j <= TJ; j++)
+  {
+    const int jb = K.idxu_block[j], half = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 : 0);   // elements strictly before the mirror centre
+    for(int k = int(tid); k < half; k += NT)
+    {
+      const int mbb = k / (j + 1), ma = k % (j + 1);
+      const real sgn = ((mbb + ma) & 1) ? -real(1.0) : real(1.0);
+      const real2 v = utot[jb + k];
+      utot[jb + (j + 1) * (j - mbb) + (j - ma)] = mk2<real>(sgn * v.x, -sgn * v.y);
+    }
+  }
+  __syncthreads();
+  for(int k = tid; k < K.idxu_max; k += NT) A.ubuf[soa + size_t(k) * 32] = utot[k];
 }
 
 // ---- force kernel of the split pipeline: CTA per atom, 3 x (J/2+1) warps = (direction, row), lane = neighbour ----------
@@ -1276,15 +1378,18 @@ __global__ void __launch_bounds__(512, 1) snap_y_kernel(const SnapArgsT<real> A,
 
 // ---- compute_yi, register-blocked (snap_y2_kernel) ------------------------------------------------------------------------
 // Same CTA shape as snap_y_kernel (32 atoms, Utot block in shared memory, lane = atom), different work item: a block of W <= 5
-// consecutive ma of ONE row (j, mb) of Y.  For a triple (j1, j2, j) and a row pair (mb1, mb2 = mb + s - mb1) the ma sum is a
-// correlation  z[ma] = sum_ma1 c[ma1][ma2] u1[ma1] u2[ma2],  ma2 = ma + s - ma1,  s = (j1 + j2 - j) / 2,  so the W outputs of a
-// block share every u1 element and a sliding window of W elements of u2 that moves by one per step: 2 shared-memory loads per W
-// complex multiply-adds instead of 2 per 1 (the first version ran at 85 % of the shared-memory pipe and 26 % of the FP64 pipe).
-// The Clebsch-Gordan rows are padded with SNAP_YPAD zeros on both sides, so a window position that sticks out of the u2 row
-// needs no test (its u2 index is clamped, its coefficient is zero).  The window registers rotate by unrolling the loop W times.
-
+// consecutive ma of ONE row (j, mb) of Y.  For a triple (j1, j2 <= j1, j) and a row pair (mb1, mb2 = mb + s - mb1) the ma sum is
+// a correlation  z[ma] = sum_ma2 c[ma1][ma2] u1[ma1] u2[ma2],  ma1 = ma + s - ma2,  s = (j1 + j2 - j) / 2.  The loop runs over
+// ma2 (the SHORT row: every step is useful for almost every output), one u2 element per step; the W outputs need the W
+// consecutive u1 elements ma1 = t .. t + W - 1 with t falling by one per step: a sliding window in registers, rotated by
+// unrolling the loop W times.  2 shared-memory loads per W complex multiply-adds instead of 2 per 1 (the first version ran at
+// 85 % of the shared-memory pipe and 26 % of the FP64 pipe).  The Clebsch-Gordan coefficients are re-tabulated per triple as
+// D[ma2][m] = c[m + s - ma2][ma2] (zero where ma1 falls outside 0..j1), so the W coefficients of a step are consecutive and a
+// window position that sticks out of the u1 row needs no test (index clamped, coefficient zero).  The tables of all triples
+// (27 KB at 2J = 8) sit in shared memory behind the Utot block; blocks start at even ma, so a step fetches its W coefficients
+// as W/2 broadcast 16-byte loads.  (Constant memory was measured slower: 16 warps on different triples thrash its 2 KB L1.)
 template<class real, int W>
-__device__ __forceinline__ void snap_y_block(const SnapConstT<real>& K, const SnapYTask task, const SnapYTri* __restrict__ tri, const real* __restrict__ cgpad,
+__device__ __forceinline__ void snap_y_block(const SnapConstT<real>& K, const SnapYTask task, const SnapYTri* __restrict__ tri, const real* __restrict__ cgtab /* shared memory */,
                                              const real* __restrict__ betat, const real2* __restrict__ U, unsigned lane, real2* __restrict__ yout)
 {
   real yr[W], yi[W];
@@ -1295,21 +1400,20 @@ __device__ __forceinline__ void snap_y_block(const SnapConstT<real>& K, const Sn
   {
     const SnapYTri q = tri[task.tri0 + it];
     const int j1 = q.j1, j2 = q.j2, s = q.s, P = q.P;
-    const real* cg = cgpad + q.cgp;
     const int mb1min = max(0, mb + s - j2), nb = min(j1, mb + s) - mb1min + 1;
-    const int L = max(0, ma0 + s - j2), n_it = min(j1, ma0 + W - 1 + s) - L + 1;
+    const int lo2 = max(0, ma0 + s - j1), n_it = min(j2, ma0 + W - 1 + s) - lo2 + 1;
+    const int t0 = ma0 + s - lo2;                               // ma1 of output 0 at ma2 = lo2  (<= j1)
     const real bj = __ldg(betat + task.tri0 + it);
     for(int ib = 0; ib < nb; ib++)
     {
       const int r1 = mb1min + ib, r2 = mb + s - r1;
-      const real cb = bj * __ldg(cg + r1 * P + SNAP_YPAD + r2);
-      const real2* u1p = U + size_t(K.idxu_block[j1] + r1 * (j1 + 1) + L) * 32 + lane;
-      const real2* u2row = U + size_t(K.idxu_block[j2] + r2 * (j2 + 1)) * 32 + lane;
-      int t = ma0 + s - L;                                     // ma2 of output 0 at ma1 = L  (<= j2)
-      const real* cp = cg + L * P + SNAP_YPAD + t;             // coefficient of output 0; output d: cp[d]; next ma1: cp += P - 1
+      const real cb = bj * cgtab[q.cgp + r2 * P + mb];      // c[r1][r2]
+      const real2* u1row = U + size_t(K.idxu_block[j1] + r1 * (j1 + 1)) * 32 + lane;
+      const real2* u2p = U + size_t(K.idxu_block[j2] + r2 * (j2 + 1) + lo2) * 32 + lane;
+      int t = t0, cp = q.cgp + lo2 * P + ma0;                    // coefficient of output d at this step: D[cp + d]; next ma2: cp += P
       real2 w[W];
 #     pragma unroll
-      for(int d = 0; d < W; d++) w[d] = u2row[size_t(min(t + d, j2)) * 32];
+      for(int d = 0; d < W; d++) w[d] = u1row[size_t(min(t + d, j1)) * 32];
       real sr[W], si[W];
 #     pragma unroll
       for(int d = 0; d < W; d++) { sr[d] = real(0.0); si[d] = real(0.0); }
@@ -1320,17 +1424,19 @@ __device__ __forceinline__ void snap_y_block(const SnapConstT<real>& K, const Sn
         {
           if( k + p < n_it )
           {
-            const real2 u1 = *u1p; u1p += 32;
+            const real2 u2 = *u2p; u2p += 32;
+            real c[W + 1];
+#           pragma unroll
+            for(int d = 0; d < W; d += 2) { const real2 cc = *reinterpret_cast<const real2*>(cgtab + cp + d); c[d] = cc.x; c[d + 1] = cc.y; }
 #           pragma unroll
             for(int d = 0; d < W; d++)
             {
-              const real c = __ldg(cp + d);
-              const real2 u2 = w[(d - p + W) % W];
-              sr[d] += c * (u1.x * u2.x - u1.y * u2.y);
-              si[d] += c * (u1.x * u2.y + u1.y * u2.x);
+              const real2 u1 = w[(d - p + W) % W];
+              sr[d] += c[d] * (u1.x * u2.x - u1.y * u2.y);
+              si[d] += c[d] * (u1.x * u2.y + u1.y * u2.x);
             }
-            cp += P - 1; t -= 1;
-            w[(W - 1 - p) % W] = u2row[size_t(max(t, 0)) * 32];
+            cp += P; t -= 1;
+            w[(W - 1 - p) % W] = u1row[size_t(max(t, 0)) * 32];
           }
         }
       }
@@ -1348,6 +1454,7 @@ __global__ void __launch_bounds__(512, 1) snap_y2_kernel(const SnapArgsT<real> A
 {
   extern __shared__ __align__(128) unsigned char ysm[];
   real2* U = reinterpret_cast<real2*>(ysm);                  // [idxu_max][32]
+  real* CGs = reinterpret_cast<real*>(U + size_t(K.idxu_max) * 32);     // [n_y2cg] coefficient tables of all triples
   __shared__ __align__(8) unsigned long long bar;
   __shared__ int next_task;
   const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -1356,9 +1463,10 @@ __global__ void __launch_bounds__(512, 1) snap_y2_kernel(const SnapArgsT<real> A
   __syncthreads();
   if( tid == 0 )
   {
-    const unsigned bytes = unsigned(K.idxu_max) * 32u * unsigned(sizeof(real2));
-    mbar_arrive_expect_tx(&bar, bytes);
+    const unsigned bytes = unsigned(K.idxu_max) * 32u * unsigned(sizeof(real2)), cgbytes = unsigned(A.n_y2cg) * unsigned(sizeof(real));
+    mbar_arrive_expect_tx(&bar, bytes + cgbytes);
     bulk_g2s(U, A.ubuf + blk, bytes, &bar);
+    bulk_g2s(CGs, A.y2cg, cgbytes, &bar);
   }
   // the second half of a middle row (2 mb = j, ma > mb) is never used with a non-zero weight, but the force sweep multiplies
   // it by that zero: it must be finite
@@ -1382,11 +1490,11 @@ __global__ void __launch_bounds__(512, 1) snap_y2_kernel(const SnapArgsT<real> A
     const SnapYTask task = A.y2task[t];
     switch( task.W )
     {
-      case 1: snap_y_block<real, 1>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
-      case 2: snap_y_block<real, 2>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
-      case 3: snap_y_block<real, 3>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
-      case 4: snap_y_block<real, 4>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
-      default: snap_y_block<real, 5>(K, task, A.y2tri, A.y2cg, betat, U, lane, yout); break;
+      case 1: snap_y_block<real, 1>(K, task, A.y2tri, CGs, betat, U, lane, yout); break;
+      case 2: snap_y_block<real, 2>(K, task, A.y2tri, CGs, betat, U, lane, yout); break;
+      case 3: snap_y_block<real, 3>(K, task, A.y2tri, CGs, betat, U, lane, yout); break;
+      case 4: snap_y_block<real, 4>(K, task, A.y2tri, CGs, betat, U, lane, yout); break;
+      default: snap_y_block<real, 5>(K, task, A.y2tri, CGs, betat, U, lane, yout); break;
     }
   }
 }
@@ -1512,17 +1620,27 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
   if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, true, 3>, smem)) ) return rc; }
   else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, false, 3>, smem)) ) return rc; }
   if( (rc = setattr(snap_y_kernel<real, TJ>, ysmem)) ) return rc;
-  if( (rc = setattr(snap_y2_kernel<real>, ysmem)) ) return rc;
+  const size_t y2smem = ysmem + size_t(S->n_y2cg) * sizeof(real);
+  if( (rc = setattr(snap_y2_kernel<real>, y2smem)) ) return rc;
+  const bool uold = getenv("XSB_SNAP_UKERNEL") != nullptr;        // A/B switch: PHASE 1 of the fused kernel
+  const size_t usmem = size_t(S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(MB ? MB : 1) * sizeof(typename R2<real>::type)
+                     + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned)) + 64;
+  if( xf ) { if( (rc = setattr(snap_u_kernel<real, TJ, true>, usmem)) ) return rc; } else { if( (rc = setattr(snap_u_kernel<real, TJ, false>, usmem)) ) return rc; }
   const bool yold = getenv("XSB_SNAP_YKERNEL") != nullptr;        // A/B switch: the one-element-per-work-item kernel
   for(unsigned base = 0; base < A.n_atoms; base += chunk)
   {
     const unsigned cnt = std::min(chunk, A.n_atoms - base);
     A.base = base;
-    if( xf ) snap_force_kernel<real, TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
-    else     snap_force_kernel<real, TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
+    if( uold )
+    {
+      if( xf ) snap_force_kernel<real, TJ, true, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
+      else     snap_force_kernel<real, TJ, false, 1><<<cnt, NT, smem, ctx->stream>>>(A, X, KK);
+    }
+    else if( xf ) snap_u_kernel<real, TJ, true><<<cnt, NT, usmem, ctx->stream>>>(A, X, KK);
+    else          snap_u_kernel<real, TJ, false><<<cnt, NT, usmem, ctx->stream>>>(A, X, KK);
     XSB_LAUNCH_CHECK(ctx);
     if( yold ) snap_y_kernel<real, TJ><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
-    else       snap_y2_kernel<real><<<(cnt + 31) / 32, 512, ysmem, ctx->stream>>>(A, KK);
+    else       snap_y2_kernel<real><<<(cnt + 31) / 32, 512, y2smem, ctx->stream>>>(A, KK);
     XSB_LAUNCH_CHECK(ctx);
     if( reverse )
     {
@@ -1632,13 +1750,13 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
     for(size_t t = 0; t < tl.size(); t++)
     {
       const TJ3 q = tl[t];
-      const int P = q.j2 + 1 + 2 * SNAP_YPAD, src = T.cg_block[T.b3(q.j1, q.j2, q.j)];
-      SnapYTri y{ (unsigned char)q.j1, (unsigned char)q.j2, (unsigned char)((q.j1 + q.j2 - q.j) / 2), (unsigned char)P, int(y2cg.size()) };
+      const int P = (q.j + 2) & ~1, src = T.cg_block[T.b3(q.j1, q.j2, q.j)], sh = (q.j1 + q.j2 - q.j) / 2;
+      SnapYTri y{ (unsigned char)q.j1, (unsigned char)q.j2, (unsigned char)sh, (unsigned char)P, int(y2cg.size()) };
       y2tri.push_back(y);
-      for(int m1 = 0; m1 <= q.j1; m1++) for(int c = 0; c < P; c++)
+      for(int m2 = 0; m2 <= q.j2; m2++) for(int m = 0; m < P; m++)
       {
-        const int m2 = c - SNAP_YPAD;
-        y2cg.push_back(m2 >= 0 && m2 <= q.j2 ? T.cglist[size_t(src) + m1 * (q.j2 + 1) + m2] : 0.0);
+        const int m1 = m + sh - m2;
+        y2cg.push_back(m <= q.j && m1 >= 0 && m1 <= q.j1 ? T.cglist[size_t(src) + m1 * (q.j2 + 1) + m2] : 0.0);
       }
       SnapZ z{}; z.j1 = (unsigned char)q.j1; z.j2 = (unsigned char)q.j2; z.j = (unsigned char)q.j;
       for(int e = 0; e < p->nelements; e++) y2beta[size_t(e) * tl.size() + t] = T.betaj(z, p->beta + size_t(e) * (T.ncoeff + 1) + 1);
@@ -1648,7 +1766,8 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
     {
       const int n = 2 * mb == j ? mb + 1 : j + 1;          // the second half of a middle row is never used (weight 0)
       int widths[3] = { n, 0, 0 };
-      if( n == 6 ) { widths[0] = 3; widths[1] = 3; } else if( n == 7 ) { widths[0] = 4; widths[1] = 3; } else if( n == 8 ) { widths[0] = 4; widths[1] = 4; } else if( n == 9 ) { widths[0] = 5; widths[1] = 4; }
+      // blocks start at even ma: their coefficients are fetched as aligned pairs
+      if( n == 6 ) { widths[0] = 4; widths[1] = 2; } else if( n == 7 ) { widths[0] = 4; widths[1] = 3; } else if( n == 8 ) { widths[0] = 4; widths[1] = 4; } else if( n == 9 ) { widths[0] = 4; widths[1] = 5; }
       for(int b = 0, ma0 = 0; b < 3 && widths[b]; ma0 += widths[b], b++)
       {
         const int W = widths[b];
@@ -1656,7 +1775,7 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
         for(int t = first[j]; t < first[j + 1]; t++)
         {
           const int j1 = tl[t].j1, j2 = tl[t].j2, s = (j1 + j2 - j) / 2;
-          const int nb = std::min(j1, mb + s) - std::max(0, mb + s - j2) + 1, nit = std::min(j1, ma0 + W - 1 + s) - std::max(0, ma0 + s - j2) + 1;
+          const int nb = std::min(j1, mb + s) - std::max(0, mb + s - j2) + 1, nit = std::min(j2, ma0 + W - 1 + s) - std::max(0, ma0 + s - j1) + 1;
           cost += long(nb) * (long(nit) * (6 * W + 6) + 4 * W + 12) + 10;
         }
         tmp.push_back({ cost, SnapYTask{ (unsigned char)j, (unsigned char)mb, (unsigned char)ma0, (unsigned char)W, (unsigned short)first[j], (unsigned short)(first[j + 1] - first[j]) } });
@@ -1666,6 +1785,9 @@ int xsb_snap_set(xsb_ctx* ctx, const xsb_snap_params* p)
     for(auto& t : tmp) y2task.push_back(t.second);
   }
   S->n_y2tri = int(y2tri.size()); S->n_y2task = int(y2task.size());
+  while( y2cg.size() % 4 != 2 ) y2cg.push_back(0.0);      // room for the pair load of the last odd block; bulk copies move multiples of 16 bytes (floats: 4 words)
+  y2cg.push_back(0.0); y2cg.push_back(0.0);
+  S->n_y2cg = int(y2cg.size());
   std::vector<float> y2cg32(y2cg.begin(), y2cg.end()), y2beta32(y2beta.begin(), y2beta.end());
   XSB_CUDA(ctx, S->y2tri.reserve(y2tri.size())); XSB_CUDA(ctx, S->y2task.reserve(y2task.size())); XSB_CUDA(ctx, S->y2cg.reserve(y2cg.size())); XSB_CUDA(ctx, S->y2beta.reserve(y2beta.size()));
   XSB_CUDA(ctx, S->y2cg32.reserve(y2cg32.size())); XSB_CUDA(ctx, S->y2beta32.reserve(y2beta32.size()));
@@ -1738,14 +1860,14 @@ int xsb_snap_force(xsb_ctx* ctx, int flags)
   {
     SnapArgsT<float> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
                         S->idxz.p, S->cglist32.p, S->betaz32.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
-                        S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort32.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg32.p, S->y2beta32.p, S->y2task.p, S->n_y2tri, S->n_y2task };
+                        S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort32.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg32.p, S->y2beta32.p, S->y2task.p, S->n_y2tri, S->n_y2task, S->n_y2cg };
     rc = go(A, S->K32);
   }
   else
   {
     SnapArgsT<double> A{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, types, ctx->nbh_off.p, ctx->nbh_idx.p, sel, n_atoms,
                          S->idxz.p, S->cglist.p, S->betaz.p, ctx->f64[XSB_F_FX].p, ctx->f64[XSB_F_FY].p, ctx->f64[XSB_F_FZ].p, epp, virp, S->err.p,
-                         S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg.p, S->y2beta.p, S->y2task.p, S->n_y2tri, S->n_y2task };
+                         S->clocks ? S->clk.p : nullptr, nullptr, nullptr, 0u, nullptr, nullptr, S->zsort.p, S->betaz_sort.p, S->ytask.p, S->n_ytask, S->y2tri.p, S->y2cg.p, S->y2beta.p, S->y2task.p, S->n_y2tri, S->n_y2task, S->n_y2cg };
     rc = go(A, S->K);
   }
   ctx->prof_end(XSB_PROF_SNAP);

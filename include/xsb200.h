@@ -101,6 +101,18 @@ int xsb_profile_read(xsb_ctx* ctx, int tag, double* ms_total, uint64_t* interval
 /* stopwatch on the context's stream: record slot 0 (start) and 1 (stop), then read the device time      */
 int xsb_timer_record(xsb_ctx* ctx, int slot);
 int xsb_timer_elapsed_ms(xsb_ctx* ctx, double* ms);
+/* Recorded steps.  Small systems (configs[0]: 131 k atoms, 0.1 ms of kernels per step) are bound by the launch path: the   */
+/* operator calls of a regular step between two neighbour-list rebuilds -- xsb_verlet_boundary_async, xsb_ghost_update,     */
+/* xsb_zero_force_energy, the force operators -- are recorded once (capture_begin ... calls ... capture_end) as a CUDA graph */
+/* and re-issued with ONE launch per step (xsb_step_replay; xsb_displ_poll works as after the direct call).  No reference    */
+/* counterpart: onika enqueues every operator's kernel separately (`ParallelExecutionContext`).  A recorded step freezes     */
+/* what the calls pass by value (counts, pointers, cell matrix, flags): after xsb_particles_rebin / xsb_particles_set_cells /*/
+/* xsb_chunk_neighbors_build / xsb_grid_set[_xform] a replay fails with XSB_ERR_STATE -- record again.  One rank only; entry  */
+/* points that wait for the device or read results back fail while recording (the recording is then lost).                    */
+int xsb_step_capture_begin(xsb_ctx* ctx);
+int xsb_step_capture_end(xsb_ctx* ctx, int* step_id);
+int xsb_step_replay(xsb_ctx* ctx, int step_id);
+int xsb_step_release(xsb_ctx* ctx, int step_id);
 /* roofline denominators measured on this device ("peaks must be measured on the box"):     */
 /* a DFMA loop (FP64 pipe, TFLOP/s), an FFMA loop (FP32 pipe, TFLOP/s) and a 1 GiB copy (HBM, GB/s       */
 /* read+write); best of 5 after a warm-up, CUDA events on the context's stream.  Any output may be null. */

@@ -1010,3 +1010,52 @@ def test_eam_alloy_mixed_precision_parity(tmp_path, two_species, virial):
     assert max(errs) > 1e-12, "mixed mode produced FP64-exact results: the FP32 path did not run"
     if virial:
         assert rel_err(ctx.download(xsb.F_VIRIAL).reshape(-1, 9)[own], rvir[own]) < TOLMIX
+
+
+def test_recorded_step_replays_the_direct_calls_bit_for_bit(tmp_path):
+    """xsb_step_capture_begin/_end + xsb_step_replay: the integrator pass, ghost update, zero and the force operators of a
+    regular step recorded once and re-issued with one launch leave exactly the arrays the direct calls leave (LJ and a
+    two-pass eam_alloy_force), xsb_displ_poll sees the same maxima, and a replay after a new list build is refused"""
+    pos, typ, box = lattice("FCC", 6, 5.0, 0.1, seed=3)
+    vel = np.random.default_rng(5).normal(0.0, 2.0, pos.shape)
+    masses, dt = [39.948], 2.0e-3
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    path = write_setfl(str(tmp_path / "g.eam.alloy"), [SC_CU], nrho=2000, drho=0.05, nr=2000, rc=6.0)
+    for kind in ("lj", "eam"):
+        a = assigned_ctx(pos, typ, box, 10.0, 1, vel); b = assigned_ctx(pos, typ, box, 10.0, 1, vel)
+
+        def forces(c):
+            c.zero_force_energy(ghost=True)
+            if kind == "lj":
+                c.pair_force([0.0104 * EV, 3.4], 8.0, xsb.FLAG_ENERGY)
+            else:
+                c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG, 0)
+                c.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG, 0)
+
+        for c in (a, b):
+            if kind == "eam":
+                c.eam_alloy_load(path)
+            c.chunk_neighbors(9.0); c.backup_r(); forces(c)
+        l0 = b.launches
+        b.step_capture_begin()
+        b.verlet_boundary_async(masses, dt); b.ghost_update(POS); forces(b)
+        sid = b.step_capture_end()
+        assert b.launches == l0                      # recorded, not executed
+        for step in range(4):
+            a.verlet_boundary_async(masses, dt); a.ghost_update(POS); forces(a)
+            b.step_replay(sid)
+            assert a.displ_poll(0) == b.displ_poll(0)
+        assert b.launches > l0
+        for f in (xsb.F_RX, xsb.F_RY, xsb.F_RZ, xsb.F_VX, xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP):
+            assert np.array_equal(a.download(f), b.download(f)), (kind, f)
+        # a blocking entry point must not be recorded
+        b.step_capture_begin()
+        with pytest.raises(xsb.XsbError):
+            b.verlet_boundary(masses, dt, 1.0)
+        with pytest.raises(xsb.XsbError):
+            b.step_capture_end()
+        # the stream still works, and the old recording is refused once the list was rebuilt
+        b.sync(); b.chunk_neighbors(9.0)
+        with pytest.raises(xsb.XsbError):
+            b.step_replay(sid)
+        b.step_release(sid)
