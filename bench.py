@@ -679,11 +679,21 @@ def run_xsb(args):
     e2e = None
     if not args.no_e2e:
         outf = W.e2e_fields(xsb)
-        if hasattr(ctx, "eam_inner_skin"):
-            ctx.eam_inner_skin(0.0)       # positions arrive from the host every step: no displacement budget to reuse a sub-list under
-        pin_r = [torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in range(3)]
+        # The host application integrates: what it uploads every step is its own trajectory.  With the inner skin on, the
+        # bench records rebuild_every consecutive steps of the device integrator into pinned host buffers first and replays
+        # them as the host's positions (the upload charges their displacement to the sub-list's budget, xsb_core.cu); a
+        # host that re-sent the SAME positions every step would never spend the budget and flatter the number.  Without the
+        # skin (LJ, SNAP, a drifting cell matrix) one snapshot is re-sent: those passes do the same work whatever moved.
+        use_traj = hasattr(ctx, "eam_inner_skin") and W.inner_skin > 0.0 and W.xform0 is None and W.name in ("c2", "c4")
+        if hasattr(ctx, "eam_inner_skin") and not use_traj:
+            ctx.eam_inner_skin(0.0)
+        M = args.rebuild_every if use_traj else 1
+        pin_r = [[torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in range(3)] for _ in range(M)]
         pin_f = [[torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in outf] for _ in range(2)]   # results of even / odd steps
-        ctx.fields_download_async(POS, [t.data_ptr() for t in pin_r]); ctx.copy_wait()
+        for m in range(M):
+            ctx.fields_download_async(POS, [t.data_ptr() for t in pin_r[m]]); ctx.copy_wait()
+            if m + 1 < M:
+                ctx.verlet_boundary_async(masses, DT); ctx.ghost_update(POS); W.forces(ctx, xsb, 0)
         ke = max(3, min(args.steps, args.e2e_steps))
 
         def e2e_step(i):
@@ -693,14 +703,15 @@ def run_xsb(args):
                 ctx.ghost_update(POS)                             # owner -> ghost images of the uploaded positions
             W.e2e_forces(ctx, xsb)
             ctx.fields_download_async(outf, [t.data_ptr() for t in pin_f[i & 1]])      # results of step i
-            ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r])               # inputs of step i+1 (overlaps step i)
+            ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r[(i + 1) % M]])  # inputs of step i+1 (overlaps step i)
 
-        ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r])
-        for i in range(2):
-            e2e_step(i + 1)
+        ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r[(M - 1) % M]])
+        for i in (M - 1, M):                                      # warm-up ends on the upload of snapshot 1 % M ... re-aligned below
+            e2e_step(i)
         ctx.copy_wait(); barrier()
+        sub0 = ctx.eam_sublist_stats() if use_traj else None
         t0 = time.perf_counter()
-        ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r])
+        ctx.fields_upload_async(POS, [t.data_ptr() for t in pin_r[0]])
         for i in range(ke):
             e2e_step(i)
         ctx.copy_wait(); barrier()
@@ -708,6 +719,8 @@ def run_xsb(args):
         fsum = float(sum(float(t.abs().sum()) for t in pin_f[(ke - 1) & 1][:3]))
         e2e = {"value": atoms_total * ke / te, "unit": UNIT, "h2d_bytes_per_step": int(24 * n_own), "d2h_bytes_per_step": int(8 * len(outf) * n_own),
                "steps": ke, "bytes_are": "per GPU", "result_check_sum_abs_f": fsum,
+               "host_positions": ("a recorded %d-step trajectory (the device integrator's own steps), inner skin %.2f: %d rho phases re-filtered, %d re-evaluated the sub-list" % (
+                   (M, W.inner_skin) + tuple(b - a for a, b in zip(sub0, ctx.eam_sublist_stats()))) if use_traj else "one snapshot re-sent every step (inner skin off)"),
                "what": "pinned host r of the own atoms -> xsb_fields_upload_async, ghost_update_r, chunk_neighbors every %d steps, zero + force operators%s, "
                        "xsb_fields_download_async of %d fields of the own atoms -> pinned host; copies overlap the passes of the neighbouring steps" % (
                            args.rebuild_every, " with energies" if len(outf) > 3 else "", len(outf))}

@@ -441,6 +441,15 @@ int xsb_internal_sub_account(xsb_ctx* ctx, double displacement)
   return XSB_OK;
 }
 
+int xsb_internal_sub_account_dev(xsb_ctx* ctx, unsigned long long* s2_dev)
+{
+  if( !ctx->sub_ctl.p ) return XSB_OK;
+  int rc = xsb_internal_allreduce_max(ctx, reinterpret_cast<double*>(s2_dev), 1); if( rc ) return rc;
+  xsb::sub_accum_kernel<<<1, 1, 0, ctx->stream>>>(ctx->sub_ctl.p, s2_dev);
+  XSB_LAUNCH_CHECK(ctx);
+  return XSB_OK;
+}
+
 // the fused pass; out[0] = max |r - r_backup|^2, out[1] = max |step displacement|^2 (both zeroed here)
 static int verlet_boundary_launch(xsb_ctx* ctx, int n_types, const double* mass, double dt, unsigned long long* out)
 {
@@ -469,7 +478,7 @@ int xsb_internal_displ_ring_init(xsb_ctx* ctx)
 {
   if( ctx->displ_host ) return XSB_OK;
   XSB_CUDA(ctx, cudaMallocHost((void**)&ctx->displ_host, sizeof(double) * 2 * XSB_DISPL_RING));
-  XSB_CUDA(ctx, ctx->displ_dev.reserve(2 * (XSB_DISPL_RING + 1)));
+  XSB_CUDA(ctx, ctx->displ_dev.reserve(2 * (XSB_DISPL_RING + 2)));      // + the recording slot + the upload slot
   for(int i = 0; i < XSB_DISPL_RING; i++) XSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->displ_ev[i], cudaEventDisableTiming));
   return XSB_OK;
 }

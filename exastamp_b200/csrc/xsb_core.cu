@@ -58,6 +58,36 @@ __global__ void xfer_scatter_kernel(unsigned n, const unsigned* __restrict__ ato
   const unsigned a = atoms[t];
   for(int f = 0; f < F.nf; f++) F.p[f][a] = stage[size_t(f) * pitch + t];
 }
+// the same scatter for an upload that brings all three position fields while an inner-skin sub-list is alive: the largest
+// physical displacement |X (r_new - r_old)|^2 of the own atoms goes to *s2 (atomicMax on the bits of a non-negative double)
+__global__ void xfer_scatter_displ_kernel(unsigned n, const unsigned* __restrict__ atoms, XferFields F, const double* __restrict__ stage, size_t pitch,
+                                          int ix, int iy, int iz, XFormInv Xf, unsigned long long* __restrict__ s2)
+{
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if( t < n )
+  {
+    const unsigned a = atoms[t];
+    double ex = stage[size_t(ix) * pitch + t] - F.p[ix][a], ey = stage[size_t(iy) * pitch + t] - F.p[iy][a], ez = stage[size_t(iz) * pitch + t] - F.p[iz][a];
+    if( !Xf.identity )
+    {
+      const double x = Xf.m[0]*ex + Xf.m[1]*ey + Xf.m[2]*ez, y = Xf.m[3]*ex + Xf.m[4]*ey + Xf.m[5]*ez, z = Xf.m[6]*ex + Xf.m[7]*ey + Xf.m[8]*ez;
+      ex = x; ey = y; ez = z;
+    }
+    d2 = ex*ex + ey*ey + ez*ez;
+    for(int f = 0; f < F.nf; f++) F.p[f][a] = stage[size_t(f) * pitch + t];
+  }
+  for(int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  __shared__ double s[8];
+  if( (threadIdx.x & 31) == 0 ) s[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if( threadIdx.x == 0 )
+  {
+    double m = s[0];
+    for(unsigned w = 1; w < (blockDim.x >> 5); w++) m = fmax(m, s[w]);
+    if( !(m <= 0.0) ) atomicMax(s2, m == m ? (unsigned long long)__double_as_longlong(m) : 0x7ff0000000000000ull);      // NaN input: infinite displacement
+  }
+}
 __global__ void xfer_gather_kernel(unsigned n, const unsigned* __restrict__ atoms, XferFields F, double* __restrict__ stage, size_t pitch)
 {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,7 +646,24 @@ int xsb_fields_upload_async(xsb_ctx* ctx, int nfields, const int* fields, const 
   }
   XSB_CUDA(ctx, cudaEventRecord(ctx->ev_up_done, ctx->copy_up));
   XSB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up_done, 0));
-  if( own_only )
+  // positions of the own atoms arriving while an inner-skin sub-list is alive (a host application that integrates and
+  // hands the new positions over every step): their largest displacement is charged to the device-side budget, exactly
+  // as the integrator pass does, instead of forcing the next rho phase to re-filter the neighbour list
+  int ip[3] = { -1, -1, -1 };
+  bool any_pos = false;
+  for(int k = 0; k < nfields; k++) for(int c = 0; c < 3; c++) if( fields[k] == XSB_F_RX + c ) { ip[c] = k; any_pos = true; }
+  const bool account = own_only && ip[0] >= 0 && ip[1] >= 0 && ip[2] >= 0 && ctx->sub_ctl.p != nullptr && ctx->inner_skin > 0.0;
+  if( account )
+  {
+    if( (rc = xsb_internal_displ_ring_init(ctx)) ) return rc;
+    unsigned long long* s2 = ctx->displ_dev.p + 2 * (XSB_DISPL_RING + 1);
+    XSB_CUDA(ctx, cudaMemsetAsync(s2, 0, sizeof(unsigned long long), ctx->stream));
+    xsb::XFormInv Xf; Xf.identity = ctx->grid.xform_is_identity; for(int i = 0; i < 9; i++) Xf.m[i] = ctx->grid.xform[i];
+    xsb::xfer_scatter_displ_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(unsigned(n), ctx->own_atoms.p, F, ctx->stage_up.p, pitch, ip[0], ip[1], ip[2], Xf, s2);
+    XSB_LAUNCH_CHECK(ctx);
+    if( (rc = xsb_internal_sub_account_dev(ctx, s2)) ) return rc;
+  }
+  else if( own_only )
   {
     xsb::xfer_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(unsigned(n), ctx->own_atoms.p, F, ctx->stage_up.p, pitch);
     XSB_LAUNCH_CHECK(ctx);
@@ -625,7 +672,7 @@ int xsb_fields_upload_async(xsb_ctx* ctx, int nfields, const int* fields, const 
     for(int k = 0; k < nfields; k++) XSB_CUDA(ctx, cudaMemcpyAsync(F.p[k], ctx->stage_up.p + size_t(k) * pitch, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   XSB_CUDA(ctx, cudaEventRecord(ctx->ev_up_free, ctx->stream));
   ctx->up_pending = true;
-  for(int k = 0; k < nfields; k++) if( fields[k] == XSB_F_RX || fields[k] == XSB_F_RY || fields[k] == XSB_F_RZ ) { ctx->pos_epoch++; ctx->foreign_epoch++; break; }
+  if( any_pos ) { ctx->pos_epoch++; if( !account ) ctx->foreign_epoch++; }
   return XSB_OK;
 }
 

@@ -246,6 +246,9 @@ int  xsb_internal_migrate(xsb_ctx* ctx, const xsb_domain_desc* dom, unsigned n, 
 void xsb_snap_release(xsb_ctx* ctx);
 // inner-skin budget (SubCtl): every atom may have moved by up to `displacement` more (xsb_assign.cu)
 int  xsb_internal_sub_account(xsb_ctx* ctx, double displacement);
+// the same with the squared displacement read from device memory (all-reduced over the ranks first)
+int  xsb_internal_sub_account_dev(xsb_ctx* ctx, unsigned long long* s2_dev);
+int  xsb_internal_allreduce_max(xsb_ctx* ctx, double* dev_inout, int count);      // xsb_ghost.cu
 // pinned result ring of xsb_verlet_boundary_async (xsb_assign.cu); idempotent
 int  xsb_internal_displ_ring_init(xsb_ctx* ctx);
 

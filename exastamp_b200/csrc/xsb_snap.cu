@@ -461,11 +461,11 @@ __device__ __forceinline__ void snap_sweep_rev(const SnapConstT<real>& K, int mb
     {
       const real qa = K.rootpq[J - m][J - mb], qb = K.rootpq[m + 1][J - mb];
       const real pr = qa * nr[m], pi = qa * ni[m], sr = qb * nr[m + 1], si = qb * ni[m + 1];
-      // a * p - b * s
-      br[m] = a_r * pr - a_i * pi - (b_r * sr - b_i * si);
-      bi[m] = a_r * pi + a_i * pr - (b_r * si + b_i * sr);
-      abr += pr * ur[m] + pi * ui[m]; abi += pr * ui[m] - pi * ur[m];
-      bbr -= sr * ur[m] + si * ui[m]; bbi -= sr * ui[m] - si * ur[m];
+      // a * p - b * s, every term a fused multiply-add on the running value
+      br[m] = fma(b_i, si, fma(-b_r, sr, fma(-a_i, pi, a_r * pr)));
+      bi[m] = fma(-b_i, sr, fma(-b_r, si, fma(a_i, pr, a_r * pi)));
+      abr = fma(pi, ui[m], fma(pr, ur[m], abr)); abi = fma(-pi, ur[m], fma(pr, ui[m], abi));
+      bbr = fma(-si, ui[m], fma(-sr, ur[m], bbr)); bbi = fma(si, ur[m], fma(-sr, ui[m], bbi));
     }
     if( 2 * mb == J )
     {
@@ -500,7 +500,12 @@ __device__ __forceinline__ void snap_sweep_rev(const SnapConstT<real>& K, int mb
       }
       const int base = K.idxu_block[J] + (J + 1) * mb;
 #     pragma unroll
-      for(int ma = 0; ma <= J; ma++) { const real2 Y = ylist[base + ma]; G += seed_w(J, ma) * (ur[ma] * Y.x + ui[ma] * Y.y); }
+      for(int ma = 0; ma <= J; ma++)
+      {
+        const real2 Y = ylist[base + ma];
+        if( 2 * mb == J ) G = fma(seed_w(J, ma), fma(ui[ma], Y.y, ur[ma] * Y.x), G);
+        else G = fma(ui[ma], Y.y, fma(ur[ma], Y.x, G));
+      }
       if( J == 2 * mb + 1 )
       {
         const int o = mbox_off(mb);
@@ -552,8 +557,8 @@ __device__ __forceinline__ void snap_sweep_rev(const SnapConstT<real>& K, int mb
       for(int ma = 0; ma <= J; ma++)
       {
         const real2 Y = ylist[base + ma];
-        const real w = seed_w(J, ma);
-        br[ma] += w * Y.x; bi[ma] += w * Y.y;
+        if( 2 * mb == J ) { const real w = seed_w(J, ma); br[ma] = fma(w, Y.x, br[ma]); bi[ma] = fma(w, Y.y, bi[ma]); }
+        else { br[ma] += Y.x; bi[ma] += Y.y; }
         if( mail ) { const real2 m = mbox[o + ma]; br[ma] += m.x; bi[ma] += m.y; }
       }
       const int hs = hbase + J * (J - 1) / 2;

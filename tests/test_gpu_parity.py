@@ -1059,3 +1059,50 @@ def test_recorded_step_replays_the_direct_calls_bit_for_bit(tmp_path):
         with pytest.raises(xsb.XsbError):
             b.step_replay(sid)
         b.step_release(sid)
+
+
+def test_eam_inner_skin_with_host_driven_positions(tmp_path):
+    """positions of the own atoms uploaded every step (the plugin use case: the host integrates) are charged to the inner
+    skin's displacement budget by xsb_fields_upload_async itself: small moves let the rho phase reuse its sub-list, a jump
+    forces a re-filter, and the forces equal those of the plain path at every step"""
+    import torch
+    path = str(tmp_path / "h.eam.alloy")
+    write_setfl(path, [SC_CU], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    pos, typ, box = lattice("FCC", 6, 3.615, 0.05, seed=23)
+    rcut, nbh = 6.0, 7.0
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    ctxs = []
+    for skin in (0.0, 0.2):
+        c = assigned_ctx(pos, typ, box, 3.615 * 2, 1)
+        c.eam_alloy_load(path); c.eam_inner_skin(skin); c.chunk_neighbors(nbh)
+        ctxs.append(c)
+    n_own = ctxs[0].n_own
+    pin = [torch.empty(n_own, dtype=torch.float64).pin_memory() for _ in range(3)]
+    ctxs[0].fields_download_async(POS, [t.data_ptr() for t in pin]); ctxs[0].copy_wait()
+    rng = np.random.default_rng(9)
+
+    def forces(c):
+        c.ghost_update(POS)
+        c.zero_force_energy()
+        c.eam_alloy_force(rcut, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_EFLAG, 0)
+        c.ghost_update([xsb.F_RHO_DEMB])
+        c.eam_alloy_force(rcut, xsb.EAM_FORCE | xsb.EAM_EFLAG, 0)
+        return [c.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)]
+
+    stats = []
+    for step in range(8):
+        for c in ctxs:
+            c.fields_upload_async(POS, [t.data_ptr() for t in pin])
+        out = [forces(c) for c in ctxs]
+        for a, b in zip(*out):
+            assert rel_err(a, b) < 1e-12, "step %d" % step
+        stats.append(ctxs[1].eam_sublist_stats())
+        for c in ctxs:
+            c.copy_wait()
+        for t in pin:                                   # the host's integrator: 0.004 ang of noise per step, one 0.3 ang jump
+            t += torch.from_numpy(rng.normal(0.0, 0.004, n_own)) + (0.3 if step == 4 else 0.0)
+    built, reused = stats[-1]
+    print("host-driven inner skin: per step (re-filtered, reused) =", stats)
+    assert reused >= 4 and built >= 2
+    assert stats[5][0] == stats[4][0] + 1             # the jump after step 4 made step 5 re-filter
+    assert ctxs[0].eam_sublist_stats() == (0, 0)
