@@ -198,8 +198,13 @@ class SnapW(Workload):
         return ["snap"]
 
     def model(self, n_l, n_c):
-        # FP-pipe bound: ~1.5 Mflop per atom at 2J = 8 with ~26 neighbours, < 3 kB of HBM
-        return {"snap": dict(bytes=24 + 2 * (1 + 2 * 27 + n_l) + 32 + 2 * 285 * 16 * 2, flops=1.5e6 * max(n_c, 1.0) / 26.0, kernel="snap Utot / Y / force pipeline (snap_force)")}
+        # FP-pipe bound: ~1.5 Mflop per atom at 2J = 8 with ~26 neighbours, < 3 kB of HBM.  That figure is the
+        # reference algorithm's (three derivative chains per neighbour); the pipeline here EXECUTES about 0.8 Mflop per atom
+        # (Utot 3.1 kflop and reverse-mode force 9.9 kflop per neighbour, compute_yi 0.46 Mflop per atom incl. the zero-padded
+        # window slots): `executed_flops_per_atom` in the fp64 block, so the pipe fraction of the work actually issued is
+        # achieved x executed / algorithmic
+        return {"snap": dict(bytes=24 + 2 * (1 + 2 * 27 + n_l) + 32 + 2 * 285 * 16 * 2, flops=1.5e6 * max(n_c, 1.0) / 26.0,
+                             executed_flops=4.6e5 + 1.3e4 * max(n_c, 1.0), kernel="snap Utot / Y / force pipeline (snap_force)")}
 
     def cpu_forces(self, O, g, gs, nb, arr, img):
         fx, fy, fz, ep, emb = arr
@@ -759,7 +764,9 @@ def run_xsb(args):
             kern.append({"kernel": m["kernel"], "avg_launch_ms": dur * 1e3, "share_of_step": t_ms / ms, "algorithmic_bytes_per_atom": m["bytes"],
                          "achieved": ach, "frac": ach / peak,
                          "traffic": (traffic.get(W.name + ":" + tag) or (traffic.get(tag) if W.name in ("c2", "c4") else None) or {}).get("dram_bytes_per_launch"),
-                         "fp64": {"achieved": tf, "peak": live_fp64, "unit": "TFLOP/s", "frac": tf / live_fp64 if live_fp64 else None, "algorithmic_flops_per_atom": m["flops"]}})
+                         "fp64": dict({"achieved": tf, "peak": live_fp64, "unit": "TFLOP/s", "frac": tf / live_fp64 if live_fp64 else None, "algorithmic_flops_per_atom": m["flops"]},
+                                      **({"executed_flops_per_atom": m["executed_flops"], "executed_frac": (m["executed_flops"] * n_own / dur / 1e12) / live_fp64 if live_fp64 else None}
+                                         if "executed_flops" in m else {}))})
     kern.sort(key=lambda k: -k["avg_launch_ms"])
     roof = None
     if kern:
