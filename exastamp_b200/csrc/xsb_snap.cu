@@ -15,6 +15,8 @@
 // sweep recomputes the chains together with their three derivatives and contracts them with Y on the fly, so neither
 // U_ij nor dU_ij is ever stored.  The energy comes from Euler's theorem for the trilinear B: sum_k beta_k B_k =
 // (1/3) 2 sum_half Re(conj(Utot) Y) -- no separate Z/B pass.
+// The production path is the split pipeline snap_u_kernel -> snap_y2_kernel -> snap_fr_kernel (reverse-mode force sweep,
+// register-blocked compute_yi); the fused kernel below remains for XSB_SNAP_FUSED / A-B runs.
 #include "xsb_ctx.h"
 #include "xsb_traverse.cuh"
 #include "xsb_tile.cuh"
@@ -296,8 +298,8 @@ __device__ __forceinline__ void snap_sweep(const SnapConstT<real>& K, int mb, bo
 }
 
 // Force sweep for ONE Cartesian direction kd: the thread's (neighbour, row mb) chain of u and du/dr_kd through all levels,
-// contracted with Y on the fly.  The three directions of a neighbour run in three different warps (snap_f_kernel), which
-// cuts the per-thread state from 4 rows to 2 (fits ~128 registers) and triples the warps an SM can hold; the price is
+// contracted with Y on the fly (forward mode, kept for A/B against snap_sweep_rev).  The three directions of a neighbour run in
+// three different CTAs (snap_fd_kernel), which cuts the per-thread state from 4 rows to 2 (fits ~128 registers) and triples the warps an SM can hold; the price is
 // that the u chain itself is carried three times.
 template<class real, int TJ>
 __device__ __forceinline__ real snap_sweep_dir(const SnapConstT<real>& K, int mb, int kd, bool valid, real x, real y, real z, real wj, real rcut,
@@ -939,121 +941,8 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 8 : 4) 
   for(int k = tid; k < K.idxu_max; k += NT) A.ubuf[soa + size_t(k) * 32] = utot[k];
 }
 
-// ---- force kernel of the split pipeline: CTA per atom, 3 x (J/2+1) warps = (direction, row), lane = neighbour ----------
-template<class real, int TJ, bool XFORM>
-__global__ void __launch_bounds__(96 * (TJ / 2 + 1), 1) snap_f_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
-{
-  constexpr int NR = TJ / 2 + 1, NW = 3 * NR, NT = 32 * NW;
-  constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = 2 * (MB ? MB : 1);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  real2* utot = reinterpret_cast<real2*>(smem_raw);                 // [idxu_max]
-  real2* ylist = utot + K.idxu_max;                                   // [idxu_max]
-  real2* mbox = ylist + K.idxu_max;                                   // [32][3][MBS]
-  real* nb_x = reinterpret_cast<real*>(mbox + 32 * SNAP_MBOX_STRIDE(3 * MBS));        // [SNAP_NN_MAX] x 5
-  real* nb_y = nb_x + SNAP_NN_MAX; real* nb_z = nb_y + SNAP_NN_MAX; real* nb_w = nb_z + SNAP_NN_MAX; real* nb_rc = nb_w + SNAP_NN_MAX;
-  unsigned* nb_g = reinterpret_cast<unsigned*>(nb_rc + SNAP_NN_MAX);    // [SNAP_NN_MAX]
-  real* red = reinterpret_cast<real*>(nb_g + SNAP_NN_MAX);          // [NW][32]
-  __shared__ unsigned s_nn;
-  const unsigned tid = threadIdx.x, lane = tid & 31u; const int wrp = int(tid >> 5), mb = wrp % NR, kd = wrp / NR;
-  const unsigned slot = A.base + blockIdx.x;
-  const unsigned ai = A.atoms ? A.atoms[slot] : slot;
-  const size_t soa = (size_t(blockIdx.x >> 5) * K.idxu_max) * 32 + (blockIdx.x & 31u);
-  const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
-  const int ei = A.type ? A.type[ai] : 0;
-  for(int k = tid; k < K.idxu_max; k += NT) { utot[k] = A.ubuf[soa + size_t(k) * 32]; ylist[k] = A.ybuf[soa + size_t(k) * 32]; }
-  if( wrp == 0 )
-  {
-    unsigned nn = 0;
-    const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
-    for(unsigned long long e = e0; e < e1; e += 32)
-    {
-      const unsigned long long ee = e + lane;
-      bool in = false; double dx = 0, dy = 0, dz = 0, rc = 0, wj = 0; unsigned g = 0;
-      if( ee < e1 )
-      {
-        g = A.nbh_idx[ee];
-        dx = A.rx[g] - xa; dy = A.ry[g] - ya; dz = A.rz[g] - za;
-        apply_xform<XFORM>(X, dx, dy, dz);
-        const int ej = A.type ? A.type[g] : 0;
-        rc = (double(K.radelem[ei]) + double(K.radelem[ej])) * double(K.rcutfac); wj = K.wjelem[ej];
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        in = d2 < rc * rc && d2 > 1e-20;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, in);
-      const unsigned sl = nn + __popc(m & ((1u << lane) - 1u));
-      if( in && sl < SNAP_NN_MAX ) { nb_x[sl] = real(dx); nb_y[sl] = real(dy); nb_z[sl] = real(dz); nb_w[sl] = real(wj); nb_rc[sl] = real(rc); nb_g[sl] = g; }
-      nn += __popc(m);
-    }
-    if( lane == 0 ) { if( nn > SNAP_NN_MAX ) { atomicExch(A.err, 1); nn = SNAP_NN_MAX; } s_nn = nn; }
-  }
-  __syncthreads();
-  const unsigned nn = s_nn;
-  // ---- energy: e0 + (1/3) 2 sum_half Re(conj(Utot) Y) - sum_k beta_k bzero
-  if( A.ep )
-  {
-    real sE = real(0.0);
-    for(int j = 0; j <= TJ; j++)
-    {
-      const int jb = K.idxu_block[j], cnt = (j + 1) * ((j + 1) / 2) + ((j % 2 == 0) ? j / 2 + 1 : 0);
-      for(int k = int(tid); k < cnt; k += NT)
-      {
-        const real w = (j % 2 == 0 && k == cnt - 1) ? real(0.5) : real(1.0);
-        sE += w * (utot[jb + k].x * ylist[jb + k].x + utot[jb + k].y * ylist[jb + k].y);
-      }
-    }
-#   pragma unroll
-    for(int o = 16; o > 0; o >>= 1) sE += __shfl_xor_sync(0xffffffffu, sE, o);
-    if( lane == 0 ) red[wrp] = sE;
-    __syncthreads();
-    if( tid == 0 ) { real t = real(0.0); for(int w = 0; w < NW; w++) t += red[w]; A.ep[ai] += K.beta0[ei] + (2.0 / 3.0) * double(t) - K.bzero_e[ei]; }
-    __syncthreads();
-  }
-  real fix = real(0.0), fiy = real(0.0), fiz = real(0.0), v[9];
-# pragma unroll
-  for(int k = 0; k < 9; k++) v[k] = real(0.0);
-  for(unsigned b0 = 0; b0 < nn; b0 += 32)
-  {
-    const unsigned n = b0 + lane; const bool valid = n < nn;
-    const real x = valid ? nb_x[n] : real(1.0), y = valid ? nb_y[n] : real(0.0), z = valid ? nb_z[n] : real(0.0), w = valid ? nb_w[n] : real(0.0), rc = valid ? nb_rc[n] : real(4.0);
-    const real d = snap_sweep_dir<real, TJ>(K, mb, kd, valid, x, y, z, w, rc, ylist, mbox + lane * SNAP_MBOX_STRIDE(3 * MBS) + kd * MBS);
-    red[wrp * 32 + lane] = d;
-    __syncthreads();
-    if( wrp == 0 && valid )
-    {
-      real f[3] = { real(0.0), real(0.0), real(0.0) };
-      for(int k = 0; k < 3; k++) for(int w2 = 0; w2 < NR; w2++) f[k] += red[(k * NR + w2) * 32 + lane];
-      for(int k = 0; k < 3; k++) f[k] *= real(2.0);
-      fix += f[0]; fiy += f[1]; fiz += f[2];
-      const unsigned g = nb_g[n];
-      atomicAdd(A.fx + g, -double(f[0])); atomicAdd(A.fy + g, -double(f[1])); atomicAdd(A.fz + g, -double(f[2]));
-      if( A.vir )
-      {
-        v[0] -= f[0] * x; v[1] -= f[0] * y; v[2] -= f[0] * z;
-        v[3] -= f[1] * x; v[4] -= f[1] * y; v[5] -= f[1] * z;
-        v[6] -= f[2] * x; v[7] -= f[2] * y; v[8] -= f[2] * z;
-      }
-    }
-    __syncthreads();
-  }
-  if( wrp == 0 )
-  {
-#   pragma unroll
-    for(int o = 16; o > 0; o >>= 1) { fix += __shfl_xor_sync(0xffffffffu, fix, o); fiy += __shfl_xor_sync(0xffffffffu, fiy, o); fiz += __shfl_xor_sync(0xffffffffu, fiz, o); }
-    if( A.vir )
-    {
-#     pragma unroll
-      for(int k = 0; k < 9; k++) { for(int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o); }
-    }
-    if( lane == 0 )
-    {
-      atomicAdd(A.fx + ai, double(fix)); atomicAdd(A.fy + ai, double(fiy)); atomicAdd(A.fz + ai, double(fiz));
-      if( A.vir ) { double* p = A.vir + 9ull * ai; for(int k = 0; k < 9; k++) p[k] += double(v[k]); }
-    }
-  }
-}
-
 // ---- force kernel, one CTA per (atom, Cartesian direction): J/2+1 warps = rows, lane = neighbour ------------------------
-// Same sweep as snap_f_kernel, but the three directions of an atom are three independent CTAs of 160 threads (2J = 8):
+// Forward-mode sweep (snap_sweep_dir); the three directions of an atom are three independent CTAs of 160 threads (2J = 8):
 // three of them fit the register file of an SM, so the serial prologue of one (neighbour filter: four dependent global
 // loads; Y fetch) overlaps the sweeps of the others, and a barrier only joins 5 warps instead of real(15.)  The neighbour
 // filter and the Y fetch are repeated per direction (cheap against the sweep); the energy is computed by direction real(0.)
@@ -1605,16 +1494,14 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
   A.ubuf = reinterpret_cast<typename R2<real>::type*>(S->ubuf.p); A.ybuf = reinterpret_cast<typename R2<real>::type*>(S->ybuf.p);      // sized for double2, float2 uses half
   XSB_CUDA(ctx, S->nbtab.reserve(size_t(chunk) * 6 * SNAP_NN_TAB)); XSB_CUDA(ctx, S->nbcnt.reserve(chunk));
   A.nbtab = S->nbtab.p; A.nbcnt = S->nbcnt.p;
-  const size_t fsmem = size_t(2 * S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(3 * 2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
-                     + size_t(3 * NR) * 32 * sizeof(real) + 64;
-  // force kernel: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
+  // forward mode: (direction, row) warps pay off once the per-thread state of the 3-direction sweep no longer fits the
   // register file (measured: 2J = 8 faster, 2J <= 6 slower than the one-thread-per-row sweep)
   constexpr bool DIRSPLIT = TJ >= 7;
-  // force kernel: reverse mode (snap_fr_kernel) unless XSB_SNAP_FKERNEL selects one of the forward-mode kernels for A/B:
-  // 2 -> one CTA per (atom, direction) at 2J >= 7 / one thread per row with all three directions below; 1 -> the 15-warp CTA
+  // force kernel: reverse mode (snap_fr_kernel) unless XSB_SNAP_FKERNEL=1 selects the forward-mode kernels for A/B: one CTA
+  // per (atom, direction) at 2J >= 7, one thread per row carrying all three directions below
   const char* fk = getenv("XSB_SNAP_FKERNEL");
   const bool reverse = fk == nullptr || fk[0] == '0';
-  const bool dircta = !reverse && DIRSPLIT && fk[0] != '1';
+  const bool dircta = !reverse && DIRSPLIT;
   const size_t frsmem = size_t(S->K.idxu_max + 32 * (SnapHist<TJ>::total() ? SnapHist<TJ>::total() : 1)) * sizeof(typename R2<real>::type)
                       + size_t(32) * SNAP_MBOX_STRIDE(MB ? MB : 1) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
                       + size_t(NR) * 5 * 32 * sizeof(real) + 64;
@@ -1622,8 +1509,8 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
   const size_t fdsmem = size_t(S->K.idxu_max) * sizeof(typename R2<real>::type) + size_t(32) * SNAP_MBOX_STRIDE(2 * (MB ? MB : 1)) * sizeof(typename R2<real>::type) + SNAP_NN_MAX * (5 * sizeof(real) + sizeof(unsigned))
                       + size_t(NR) * 32 * sizeof(real) + 64;
   if( dircta ) { if( xf ) { if( (rc = setattr(snap_fd_kernel<real, TJ, true>, fdsmem)) ) return rc; } else { if( (rc = setattr(snap_fd_kernel<real, TJ, false>, fdsmem)) ) return rc; } }
-  if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, true>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, true, 3>, smem)) ) return rc; }
-  else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_f_kernel<real, TJ, false>, fsmem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, false, 3>, smem)) ) return rc; }
+  if( xf ) { if( (rc = setattr(snap_force_kernel<real, TJ, true, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, true, 3>, smem)) ) return rc; }
+  else     { if( (rc = setattr(snap_force_kernel<real, TJ, false, 1>, smem)) ) return rc; if( (rc = setattr(snap_force_kernel<real, TJ, false, 3>, smem)) ) return rc; }
   if( (rc = setattr(snap_y_kernel<real, TJ>, ysmem)) ) return rc;
   const size_t y2smem = ysmem + size_t(S->n_y2cg) * sizeof(real);
   if( (rc = setattr(snap_y2_kernel<real>, y2smem)) ) return rc;
@@ -1656,11 +1543,6 @@ static int snap_launch(xsb_ctx* ctx, SnapDev* S, SnapArgsT<real> A, const SnapCo
     {
       if( xf ) snap_fd_kernel<real, TJ, true><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
       else     snap_fd_kernel<real, TJ, false><<<3 * cnt, NT, fdsmem, ctx->stream>>>(A, X, KK);
-    }
-    else if( DIRSPLIT )
-    {
-      if( xf ) snap_f_kernel<real, TJ, true><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, KK);
-      else     snap_f_kernel<real, TJ, false><<<cnt, 3 * NT, fsmem, ctx->stream>>>(A, X, KK);
     }
     else
     {
