@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1)) snap_force_kernel(const Sna
 // kernel) without the fused kernel's Y / derivative state: a fifth of its shared memory and under 80 registers, so five and
 // more CTAs share an SM and hide each other's serial prologue (list walk: four dependent global loads) and level barriers.
 template<class real, int TJ, bool XFORM>
-__global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 8 : 4) snap_u_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
+__global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 8 : 5) snap_u_kernel(const SnapArgsT<real> A, const XForm X, const SnapConstT<real> K)
 {
   constexpr int NR = TJ / 2 + 1, NT = 32 * NR;
   constexpr int MB = (TJ / 2) * (TJ / 2 + 1), MBS = MB ? MB : 1;
@@ -861,9 +861,14 @@ __global__ void __launch_bounds__(32 * (TJ / 2 + 1), sizeof(real) == 4 ? 8 : 4) 
   const size_t soa = (size_t(blockIdx.x >> 5) * K.idxu_max) * 32 + (blockIdx.x & 31u);    // + jju * 32
   const double xa = A.rx[ai], ya = A.ry[ai], za = A.rz[ai];
   const int ei = A.type ? A.type[ai] : 0;
-  for(int k = tid; k < K.idxu_max; k += NT) utot[k] = mk2<real>(real(0.0), real(0.0));
-  __syncthreads();
-  for(int j = int(tid); j <= TJ; j += NT) for(int ma = 0; ma <= j; ma++) utot[K.idxu_block[j] + (j + 1) * ma + ma].x = K.wself;
+  // Utot = wself on the diagonals, zero elsewhere (one pass, no barrier of its own: the filter's barrier below orders it)
+  for(int k = tid; k < K.idxu_max; k += NT)
+  {
+    int j = 0;
+    while( j < TJ && k >= K.idxu_block[j + 1] ) ++j;
+    const int r = k - K.idxu_block[j];
+    utot[k] = mk2<real>(r % (j + 2) == 0 ? K.wself : real(0.0), real(0.0));      // r = (j+1) ma + ma
+  }
   const unsigned long long e0 = A.nbh_off[ai], e1 = A.nbh_off[ai + 1];
   double* const tab = A.nbtab + size_t(blockIdx.x) * 6 * SNAP_NN_TAB;
   unsigned tot = 0;
