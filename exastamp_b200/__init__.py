@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "libxsb200.so")
 F_RX, F_RY, F_RZ, F_FX, F_FY, F_FZ, F_EP, F_VX, F_VY, F_VZ, F_VIRIAL, F_RHO_DEMB, F_TYPE, F_ID = range(14)
 FLAG_GHOST, FLAG_ENERGY, FLAG_VIRIAL, FLAG_MIXED = 1, 2, 4, 8
 EAM_RHO, EAM_RHO2EMB, EAM_GHOST, EAM_FORCE, EAM_EFLAG = 1, 2, 4, 8, 16
-POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM = 0, 1, 2, 3
+POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM, POT_YUKAWA, POT_RELAX, POT_ZERO = 0, 1, 2, 3, 4, 5, 6
+EAM_JOHNSON, EAM_SUTTON_CHEN, EAM_VNIITF = 0, 1, 2
 _FIELD_DTYPE = {F_TYPE: np.uint8, F_ID: np.uint64}
 
 # every symbol include/xsb200.h declares (tests check the library exports all of them)
@@ -27,7 +28,7 @@ ABI_SYMBOLS = [
     "xsb_field_download", "xsb_field_device_ptr", "xsb_zero_force_energy",
     "xsb_chunk_neighbors_build", "xsb_chunk_neighbors_stats", "xsb_chunk_neighbors_export_size",
     "xsb_chunk_neighbors_export", "xsb_chunk_neighbors_download_flat",
-    "xsb_pair_force", "xsb_pair_multi_force", "xsb_eam_johnson_force",
+    "xsb_pair_force", "xsb_pair_multi_force", "xsb_eam_johnson_force", "xsb_eam_analytic_force",
     "xsb_snap_ncoeff", "xsb_snap_set", "xsb_snap_rcut_max", "xsb_snap_force", "xsb_snap_overflow",
     "xsb_eam_alloy_read", "xsb_eam_alloy_free", "xsb_eam_alloy_set", "xsb_eam_alloy_force",
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
@@ -126,6 +127,7 @@ def load_library():
     L.xsb_pair_force.argtypes = [vp, i32, vp, i32, dbl, i32]
     L.xsb_pair_multi_force.argtypes = [vp, i32, i32, vp, i32, dbl, i32]
     L.xsb_eam_johnson_force.argtypes = [vp, vp, dbl, i32, i32]
+    L.xsb_eam_analytic_force.argtypes = [vp, i32, vp, i32, dbl, i32, i32]
     L.xsb_eam_alloy_read.argtypes = [C.c_char_p, C.POINTER(EamAlloyTables), C.c_char_p, C.c_size_t]
     L.xsb_eam_alloy_free.argtypes = [C.POINTER(EamAlloyTables)]
     L.xsb_eam_alloy_set.argtypes = [vp, C.POINTER(EamAlloyTables)]
@@ -303,6 +305,11 @@ class Context:
         p = np.ascontiguousarray(params19, dtype=np.float64)
         assert p.size == 19
         self._ck(self.L.xsb_eam_johnson_force(self.h, _ptr(p), float(rcut), int(phases), int(flags)), "xsb_eam_johnson_force")
+
+    def eam_analytic_force(self, model, params, rcut, phases=7, flags=0):
+        """single-species analytic EAM of eam_potential_template: EAM_JOHNSON (19 scalars), EAM_SUTTON_CHEN (5), EAM_VNIITF (13)"""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.xsb_eam_analytic_force(self.h, int(model), _ptr(p), p.size, float(rcut), int(phases), int(flags)), "xsb_eam_analytic_force")
 
     def eam_alloy_load(self, path):
         t = EamAlloyTables()

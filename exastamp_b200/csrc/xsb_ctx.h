@@ -133,7 +133,7 @@ struct xsb_ctx
   xsb::DevBuf<unsigned> sub_cnt;              // [n]
   xsb::DevBuf<double> pair_w;                 // [total] per-pair value cached by the pass that wrote the sub-list
   int sub_pw_kind = 0;                        // what pair_w holds for the current sub-list: 0 nothing, 1 eam_alloy rho'(r), 2 johnson rho'(r), 3 eam_alloy multi-element (rhojp, rhoip)
-  double sub_pw_johnson[19] = {};             // parameter set behind a kind-2 cache
+  double sub_pw_johnson[20] = {};             // parameter set (+ model id) behind a kind-2 cache
   int subcell_bits = 0;                       // particles of a cell sorted along a Morton curve of 2^bits sub-cells per axis when binning (env XSB_SUBCELL_SORT)
   int exp_tpa = 0;                            // A/B switch (env XSB_TPA=8): lanes per central atom of the non-virial FP64 force passes
   bool pair_cache_off = false;                // env XSB_NO_PAIR_CACHE=1: second pass re-evaluates instead (A/B profiling)

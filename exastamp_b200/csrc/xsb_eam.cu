@@ -18,9 +18,14 @@ namespace xsb
 // ------------------------------------------------------------------------------------------------
 // Johnson analytic EAM
 // ------------------------------------------------------------------------------------------------
+// The same struct carries the parameters of the other analytic single-species models of eam_potential_template in its first
+// slots (reference struct order): model 1 sutton_chen {c, epsilon, a0, n, m}, model 2 vniitf {rmax, rmin, rt0, Ecoh, E0, beta, A,
+// Z, n, alpha, D, eta, mu}; the operators only differ in the three functions rho(r), phi(r), F(rho).
 struct JohnsonP
 {
   double re, fe, rhoe, alpha, beta, A, B, kappa, lambda, Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, Fo, eta;
+  int model, pad_;
+  __host__ __device__ __forceinline__ double v(int i) const { return (&re)[i]; }
 };
 
 // c^20 and c^19 by squaring (johnson.h uses pow(c2,20) and 20*c3/c2)
@@ -79,6 +84,68 @@ __device__ __forceinline__ void johnson_fEmbed(const JohnsonP& p, double rho, do
   }
 }
 
+// sutton_chen.h:33-62
+__device__ __forceinline__ void sutton_chen_rho(const JohnsonP& p, double r, double& rho, double& drho)
+{
+  rho = pow(p.v(2) / r, p.v(4));
+  drho = -1 * p.v(4) * rho / r;
+}
+__device__ __forceinline__ void sutton_chen_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+{
+  phi = p.v(1) * pow(p.v(2) / r, p.v(3));
+  dphi = -1 * p.v(3) * phi / r;
+}
+__device__ __forceinline__ void sutton_chen_fEmbed(const JohnsonP& p, double rho, double& f, double& df)
+{
+  f = -1. * p.v(0) * p.v(1) * sqrt(rho);
+  df = 0.5 * f / (rho > 0 ? rho : 0);
+}
+
+// vniitf.h:48-125 ; v(0..12) = rmax rmin rt0 Ecoh E0 beta A Z n alpha D eta mu
+__device__ __forceinline__ void vniitf_switch(const JohnsonP& p, double r, double& S, double& dS)
+{
+  const double x = (p.v(0) - r) / (p.v(0) - p.v(1));
+  const double x2 = x * x, x3 = x2 * x;
+  S = x2 * x2 * ( -20 * x2 * x + 70 * x2 - 84 * x + 35 );
+  dS = (140 * x3 * ( -1 * x3 + 3 * x2 - 3 * x + 1 )) / (p.v(1) - p.v(0));
+  if( x < 0 ) { S = 0.; dS = 0.; }
+  else if( x > 1 ) { S = 1.; dS = 0.; }
+}
+__device__ __forceinline__ void vniitf_rho(const JohnsonP& p, double r, double& rho, double& drho)
+{
+  const double irt0 = 1 / p.v(2);
+  const double F = exp(-p.v(5) * (r * irt0 - 1.0)) / p.v(7), dF = -p.v(5) * F * irt0;
+  double S, dS; vniitf_switch(p, r, S, dS);
+  rho = F * S; drho = F * dS + S * dF;
+}
+__device__ __forceinline__ void vniitf_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+{
+  const double ir = 1 / r, irt0 = 1 / p.v(2), dr = r * irt0 - 1.0, dr2 = dr * dr;
+  const double alpha = p.v(9), eta = p.v(11), mu = p.v(12);
+  const double a = -2 * p.v(3) / p.v(7), b = alpha * alpha * alpha * p.v(10) * p.v(2);
+  const double f1  = a * ( 1 + alpha * dr + eta * dr2 + (mu + b * ir) * dr2 * dr );
+  const double df1 = a * ( alpha * irt0 + 2 * eta * irt0 * dr + 3 * mu * irt0 * dr2 + b * (3 * irt0 - dr * ir) * dr2 * ir );
+  const double f2 = exp(-alpha * dr), df2 = -alpha * irt0 * f2;
+  double S, dS; vniitf_switch(p, r, S, dS);
+  phi = (p.v(4) + f1 * f2) * S;
+  dphi = (p.v(4) + f1 * f2) * dS + (f1 * df2 + f2 * df1) * S;
+}
+__device__ __forceinline__ void vniitf_fEmbed(const JohnsonP& p, double rho, double& f, double& df)
+{
+  if( rho <= 0. ) { f = 0.; df = 0.; return; }
+  const double a = pow(rho, p.v(8)), b = p.v(6) * p.v(3) * a, c = log(a);
+  f = b * (c - 1);
+  df = p.v(8) * b * c / rho;
+}
+
+// the model switch is uniform over the launch
+__device__ __forceinline__ void eam1_rho(const JohnsonP& p, double r, double& f, double& df)
+{ if( p.model == 0 ) johnson_rho(p, r, f, df); else if( p.model == 1 ) sutton_chen_rho(p, r, f, df); else vniitf_rho(p, r, f, df); }
+__device__ __forceinline__ void eam1_phi(const JohnsonP& p, double r, double& f, double& df)
+{ if( p.model == 0 ) johnson_phi(p, r, f, df); else if( p.model == 1 ) sutton_chen_phi(p, r, f, df); else vniitf_phi(p, r, f, df); }
+__device__ __forceinline__ void eam1_fEmbed(const JohnsonP& p, double x, double& f, double& df)
+{ if( p.model == 0 ) johnson_fEmbed(p, x, f, df); else if( p.model == 1 ) sutton_chen_fEmbed(p, x, f, df); else vniitf_fEmbed(p, x, f, df); }
+
 // pass 1 (EmbOp): rho_i = sum rho(r_ij) ; ep_i += F(rho_i) ; rho_dEmb_i = F'(rho_i)
 template<int TPA, bool XFORM>
 __global__ void __launch_bounds__(256) johnson_emb_kernel(ParticleView P, XForm X, JohnsonP p, double rcut2,
@@ -98,7 +165,7 @@ __global__ void __launch_bounds__(256) johnson_emb_kernel(ParticleView P, XForm 
     const double d2 = dx * dx + dy * dy + dz * dz;
     if( d2 <= rcut2 )
     {
-      double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
+      double rho, drho; eam1_rho(p, sqrt(d2), rho, drho);
       srho += rho; ++cnt;
     }
   }
@@ -107,7 +174,7 @@ __global__ void __launch_bounds__(256) johnson_emb_kernel(ParticleView P, XForm 
   for(int o = TPA / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if( valid && sub == 0 && cnt > 0 )   // the functor only runs for non-empty pair buffers
   {
-    double f, df; johnson_fEmbed(p, srho, f, df);
+    double f, df; eam1_fEmbed(p, srho, f, df);
     ep[a] += f; rho_dEmb[a] = df;
   }
 }
@@ -135,8 +202,8 @@ __global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XFor
     {
       const double r = sqrt(d2);
       double rho, drho, phi, dphi;
-      johnson_rho(p, r, rho, drho);
-      johnson_phi(p, r, phi, dphi);
+      eam1_rho(p, r, rho, drho);
+      eam1_phi(p, r, phi, dphi);
       const double de = (drho * (fpi + rho_dEmb[b]) + dphi) / r;
       const double fex = de * dx, fey = de * dy, fez = de * dz;
       sfx += fex; sfy += fey; sfz += fez; sep += 0.5 * phi;
@@ -180,7 +247,7 @@ struct JohnsonEmbTileOp
   // returns rho'(r): kept per pair for the force pass of the step (PW_OUT), which then skips one exp + one power
   __device__ __forceinline__ double pair_d2(Acc& A, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
   {
-    double rho, drho; johnson_rho(p, sqrt(d2), rho, drho);
+    double rho, drho; eam1_rho(p, sqrt(d2), rho, drho);
     A.rho += rho; ++A.cnt;
     return drho;
   }
@@ -190,7 +257,7 @@ struct JohnsonEmbTileOp
     A.rho = group_sum<TPA>(A.rho);
 #   pragma unroll
     for(int o = TPA / 2; o > 0; o >>= 1) A.cnt += __shfl_xor_sync(0xffffffffu, A.cnt, o);
-    if( valid && sub == 0 && A.cnt > 0 ) { double f, df; johnson_fEmbed(p, A.rho, f, df); ep[a] += f; rho_dEmb[a] = df; }
+    if( valid && sub == 0 && A.cnt > 0 ) { double f, df; eam1_fEmbed(p, A.rho, f, df); ep[a] += f; rho_dEmb[a] = df; }
   }
 };
 
@@ -209,8 +276,8 @@ struct JohnsonForceTileOp
   {
     const double r = sqrt(d2);
     double rho, drho = drho_in, phi, dphi;
-    if( !HAVE ) johnson_rho(p, r, rho, drho);
-    johnson_phi(p, r, phi, dphi);
+    if( !HAVE ) eam1_rho(p, r, rho, drho);
+    eam1_phi(p, r, phi, dphi);
     const double de = (drho * (A.fpi + B.w[j]) + dphi) / r;
     const double fex = de * dx, fey = de * dy, fez = de * dz;
     A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * phi;
@@ -703,12 +770,21 @@ extern "C" {
 
 int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int phases, int flags)
 {
+  return xsb_eam_analytic_force(ctx, XSB_EAM_JOHNSON, params19, 19, rcut, phases, flags);
+}
+
+int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int nparams, double rcut, int phases, int flags)
+{
   XSB_ENTER(ctx);
-  XSB_REQUIRE(ctx, params19 != nullptr && rcut > 0.0, XSB_ERR_INVALID, "johnson: null parameters or rcut <= 0");
+  const int want = model == XSB_EAM_JOHNSON ? 19 : (model == XSB_EAM_SUTTON_CHEN ? 5 : (model == XSB_EAM_VNIITF ? 13 : -1));
+  XSB_REQUIRE(ctx, want > 0, XSB_ERR_UNSUPPORTED, "single-species EAM model not implemented (johnson, sutton_chen, vniitf)");
+  XSB_REQUIRE(ctx, params != nullptr && nparams == want && rcut > 0.0, XSB_ERR_INVALID, "eam: null parameters, wrong parameter count (johnson 19, sutton_chen 5, vniitf 13) or rcut <= 0");
   XSB_REQUIRE(ctx, ctx->nbh_built, XSB_ERR_STATE, "chunk_neighbors must be built before a force operator");
   XSB_REQUIRE(ctx, rcut <= ctx->nbh_dist, XSB_ERR_INVALID, "rcut exceeds the neighbour-list distance nbh_dist_lab");
   XSB_CUDA(ctx, cudaSetDevice(ctx->device));
-  JohnsonP p; std::memcpy(&p, params19, sizeof(p));
+  double params19[20] = {};                  // the per-pair cache key: parameters zero-padded + model
+  std::memcpy(params19, params, size_t(want) * sizeof(double)); params19[19] = double(model);
+  JohnsonP p; std::memcpy(&p, params19, 19 * sizeof(double)); p.model = model; p.pad_ = 0;
   const bool virial = flags & XSB_FLAG_VIRIAL;
   if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
   const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;

@@ -12,6 +12,7 @@ namespace xsb
 //   zbl        k = { d1a, d2a, d3a, d4a, zze, sw1, sw2, sw3, sw4, sw5, r1, - }   (zbl/potential.h:180-303)
 //   exp6       k = { A, B, C, D }                                               (exp6.h:66-84)
 //   buckingham k = { A, Rho, C }                                                (buckingham.h:41-52)
+//   yukawa k = { A, kappa } (yukawa.h:39-48); relax k = { r1, rc } (relax/potential.h:43-51); zero: no parameters
 struct LJPair { double k[12]; double ecut, rcut2, rc2_pot; int pot, pad_; };   // ecut = e(rcut) ; rc2_pot: zbl's own rc^2
 
 struct LJMulti { LJPair pp[16]; };   // indexed by unique_pair_id (MAX_TYPE_PAIR_IDS = 16, multiparam.h:68)
@@ -73,13 +74,29 @@ __host__ __device__ __forceinline__ void lj_eval(const LJPair& p, real d2, real&
     ee = Ae - Cr6 + D12;
     de = -real(p.k[1]) * Ae + (real(6) * Cr6 - real(12) * D12) / r;
   }
-  else
+  else if( p.pot == XSB_POT_BUCKINGHAM )
   {
     const real x6 = d2 * d2 * d2, x7 = x6 * r;
     const real Ae = real(p.k[0]) * xexp(-r / real(p.k[1]));
     ee = Ae - (real(p.k[2]) / x6);
     de = (real(6) * real(p.k[2]) / x7) - (Ae / real(p.k[1]));
   }
+  else if( p.pot == XSB_POT_YUKAWA )
+  {
+    // yukawa.h:39-48, `de` as the reference writes it: e (1/r - kappa)
+    ee = (real(p.k[0]) * rinv) * xexp(-real(p.k[1]) * r);
+    de = ee * (rinv - real(p.k[1]));
+  }
+  else if( p.pot == XSB_POT_RELAX )
+  {
+    // relax/potential.h:43-51: r clamped to [r1, rc], e = rc / r - 1, de = -e
+    real rr = r;
+    if( rr < real(p.k[0]) ) rr = real(p.k[0]);
+    if( rr > real(p.k[1]) ) rr = real(p.k[1]);
+    ee = (real(p.k[1]) / rr) - real(1);
+    de = -ee;
+  }
+  // XSB_POT_ZERO (zero/potential.h:49-54): e = de = 0
   e = ee - real(p.ecut);
   de_r = de * rinv;
 }
@@ -184,7 +201,17 @@ struct LJTileOp
   }
 };
 
-static int pair_nparams(int pot) { return pot == XSB_POT_LJ ? 2 : (pot == XSB_POT_BUCKINGHAM ? 3 : (pot == XSB_POT_ZBL || pot == XSB_POT_EXP6 ? 4 : -1)); }
+static int pair_nparams(int pot)
+{
+  switch( pot )
+  {
+    case XSB_POT_LJ: case XSB_POT_YUKAWA: case XSB_POT_RELAX: return 2;
+    case XSB_POT_BUCKINGHAM: return 3;
+    case XSB_POT_ZBL: case XSB_POT_EXP6: return 4;
+    case XSB_POT_ZERO: return 0;
+    default: return -1;
+  }
+}
 
 // host-side zbl helpers: the r-independent part of zbl_compute_energy (zbl/potential.h:180-246)
 static double zbl_e_h(double r, const double* d, double zze) { return zze * (0.02817 * exp(-d[0] * r) + 0.28022 * exp(-d[1] * r) + 0.50986 * exp(-d[2] * r) + 0.18175 * exp(-d[3] * r)) / r; }
@@ -282,8 +309,9 @@ extern "C" {
 int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags)
 {
   XSB_ENTER(ctx);
-  XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
-  XSB_REQUIRE(ctx, params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "wrong parameter count: lj {epsilon, sigma}, zbl {r1, rc, z_a, z_b}, exp6 {A, B, C, D}, buckingham {A, Rho, C}");
+  XSB_REQUIRE(ctx, pair_nparams(pot) >= 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham, yukawa, relax, zero)");
+  XSB_REQUIRE(ctx, (params != nullptr || pair_nparams(pot) == 0) && nparams == pair_nparams(pot), XSB_ERR_INVALID,
+              "wrong parameter count: lj {epsilon, sigma}, zbl {r1, rc, z_a, z_b}, exp6 {A, B, C, D}, buckingham {A, Rho, C}, yukawa {A, kappa}, relax {r1, rc}, zero {}");
   XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
   LJMulti prm; prm.pp[0] = make_pair(pot, params, rcut);
   return launch_pair<false>(ctx, prm, rcut, flags);
@@ -292,7 +320,7 @@ int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, dou
 int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, double rcut_max, int flags)
 {
   XSB_ENTER(ctx);
-  XSB_REQUIRE(ctx, pair_nparams(pot) > 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham)");
+  XSB_REQUIRE(ctx, pair_nparams(pot) >= 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham, yukawa, relax, zero)");
   XSB_REQUIRE(ctx, pair_params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "rows of {params..., rcut} expected");
   const int npairs = n_types * (n_types + 1) / 2;
   XSB_REQUIRE(ctx, n_types >= 1 && npairs <= 16, XSB_ERR_INVALID, "too many type pairs (MAX_TYPE_PAIR_IDS = 16)");

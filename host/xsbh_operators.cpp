@@ -578,8 +578,10 @@ static OperatorRegistrar reg_pfv("push_f_v", []() { return std::unique_ptr<Opera
 // exp6.h:44-57 {A, B, C, D}, buckingham.h:60-70 {A, Rho, C}.
 struct PairPotDesc { int pot; std::vector<const char*> names; bool needs_z; };
 static const PairPotDesc& pot_desc(int pot) {
-  static const PairPotDesc d[4] = {{XSB_POT_LJ, {"epsilon", "sigma"}, false}, {XSB_POT_ZBL, {"r1", "rc"}, true},
-                                   {XSB_POT_EXP6, {"A", "B", "C", "D"}, false}, {XSB_POT_BUCKINGHAM, {"A", "Rho", "C"}, false}};
+  // yukawa.h:56-70 {A, kappa}; relax/potential.h:56-72 {r1, rc}; zero/potential.h:37-45 (no parameters)
+  static const PairPotDesc d[7] = {{XSB_POT_LJ, {"epsilon", "sigma"}, false}, {XSB_POT_ZBL, {"r1", "rc"}, true},
+                                   {XSB_POT_EXP6, {"A", "B", "C", "D"}, false}, {XSB_POT_BUCKINGHAM, {"A", "Rho", "C"}, false},
+                                   {XSB_POT_YUKAWA, {"A", "kappa"}, false}, {XSB_POT_RELAX, {"r1", "rc"}, false}, {XSB_POT_ZERO, {}, false}};
   return d[pot];
 }
 // raw parameter vector in C-ABI order; absent entries of `common_parameters` default to 0 like the reference's structs
@@ -675,6 +677,9 @@ XSBH_PAIR_OPS(lj, XSB_POT_LJ)
 XSBH_PAIR_OPS(zbl, XSB_POT_ZBL)
 XSBH_PAIR_OPS(exp6, XSB_POT_EXP6)
 XSBH_PAIR_OPS(buckingham, XSB_POT_BUCKINGHAM)
+XSBH_PAIR_OPS(yukawa, XSB_POT_YUKAWA)
+XSBH_PAIR_OPS(relax, XSB_POT_RELAX)
+XSBH_PAIR_OPS(zero, XSB_POT_ZERO)
 // lj_compute_force_symetric (pair_potential_singlemat_symetric.cpp:335-346): the reference walks half lists and
 // scatters -f to the neighbour under particle locks, then folds ghost forces back (config_update_symmetric_forces.msp).
 // Here the same totals come from the full-list kernel (one writer per atom, nothing lands on ghosts), so the
@@ -683,18 +688,25 @@ static OperatorRegistrar reg_lj_sym("lj_compute_force_symetric", []() { return s
 static OperatorRegistrar reg_zbl_sym("zbl_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(XSB_POT_ZBL)); });
 
 // johnson_force / johnson_emb / johnson_force_reuse_emb / johnson_init (eam_potential.cu:92-100,178-193; johnson.h:176-204)
+// The same operator class serves the other analytic single-species models of eam_potential_template: sutton_chen
+// (sutton_chen.h:71-83 {c, epsilon, a0, n, m}) and vniitf (vniitf.h:139-157, 13 scalars); only the parameter names differ.
 class JohnsonForce : public Operator {
 public:
   int phases;     // bit0 emb, bit1 emb over ghosts, bit2 force
-  explicit JohnsonForce(int ph) : phases(ph) {}
+  int model;      // xsb_eam_model
+  explicit JohnsonForce(int ph, int m = XSB_EAM_JOHNSON) : phases(ph), model(m) {}
   void execute(Simulation& sim) override {
     TRACE(sim);
     check_slots({"parameters", "rcut", "rcut_max", "ghost_dist_max", "chunk_neighbors", "grid", "domain", "eam_extra_fields"});
     const double rcut = quantity(required("rcut"));
     const Node& p = required("parameters");
-    static const char* names[19] = {"re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lambda", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta"};
+    static const std::vector<const char*> all_names[3] = {
+      {"re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lambda", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta"},
+      {"c", "epsilon", "a0", "n", "m"},
+      {"rmax", "rmin", "rt0", "Ecoh", "E0", "beta", "A", "Z", "n", "alpha", "D", "eta", "mu"}};
+    const std::vector<const char*>& names = all_names[model];
     double prm[19];
-    for (int i = 0; i < 19; ++i) {
+    for (size_t i = 0; i < names.size(); ++i) {
       const Node* v = p.find(names[i]);
       if (!v) throw OperatorError(name + ": parameter '" + names[i] + "' is missing");
       prm[i] = quantity(*v);
@@ -704,13 +716,20 @@ public:
     if (sim.preinit || phases == 0) return;
     need_gpu(sim, name);
     int fl = sim.compute_virial && sim.trigger_thermo_state ? XSB_FLAG_VIRIAL : 0;
-    sim.check(xsb_eam_johnson_force(sim.ctx, prm, rcut, phases, fl), "xsb_eam_johnson_force");
+    sim.check(xsb_eam_analytic_force(sim.ctx, model, prm, int(names.size()), rcut, phases, fl), "xsb_eam_analytic_force");
   }
 };
 static OperatorRegistrar reg_jf("johnson_force", []() { return std::unique_ptr<Operator>(new JohnsonForce(7)); });
 static OperatorRegistrar reg_je("johnson_emb", []() { return std::unique_ptr<Operator>(new JohnsonForce(3)); });
 static OperatorRegistrar reg_jr("johnson_force_reuse_emb", []() { return std::unique_ptr<Operator>(new JohnsonForce(4)); });
 static OperatorRegistrar reg_ji("johnson_init", []() { return std::unique_ptr<Operator>(new JohnsonForce(0)); });
+#define XSBH_EAM1_OPS(nm, MODEL) \
+  static OperatorRegistrar reg_##nm##_f(#nm "_force", []() { return std::unique_ptr<Operator>(new JohnsonForce(7, MODEL)); }); \
+  static OperatorRegistrar reg_##nm##_e(#nm "_emb", []() { return std::unique_ptr<Operator>(new JohnsonForce(3, MODEL)); }); \
+  static OperatorRegistrar reg_##nm##_r(#nm "_force_reuse_emb", []() { return std::unique_ptr<Operator>(new JohnsonForce(4, MODEL)); }); \
+  static OperatorRegistrar reg_##nm##_i(#nm "_init", []() { return std::unique_ptr<Operator>(new JohnsonForce(0, MODEL)); });
+XSBH_EAM1_OPS(sutton_chen, XSB_EAM_SUTTON_CHEN)
+XSBH_EAM1_OPS(vniitf, XSB_EAM_VNIITF)
 
 // eam_alloy_force / eam_alloy_init (eam_potential_multimat.cu:88-109 slots; eam_alloy.cpp:66-84 parameters)
 class EamAlloyForce : public Operator {

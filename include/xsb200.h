@@ -78,7 +78,10 @@ typedef enum xsb_pair_pot {
   XSB_POT_LJ = 0,          /* params: epsilon, sigma                  (lennard_jones/.../lennard_jones.h:40-50)     */
   XSB_POT_ZBL = 1,         /* params: r1, rc, z_a, z_b                (zbl/potential.h:36-57,180-303; z from species) */
   XSB_POT_EXP6 = 2,        /* params: A, B, C, D                      (exp6/.../exp6.h:66-84)                        */
-  XSB_POT_BUCKINGHAM = 3   /* params: A, Rho, C                       (buckingham/buckingham.h:41-52)                */
+  XSB_POT_BUCKINGHAM = 3,  /* params: A, Rho, C                       (buckingham/buckingham.h:41-52)                */
+  XSB_POT_YUKAWA = 4,      /* params: A, kappa                        (yukawa/.../yukawa.h:39-48)                    */
+  XSB_POT_RELAX = 5,       /* params: r1, rc  (overlap relaxation ramp, relax/potential.h:43-51)                    */
+  XSB_POT_ZERO = 6         /* no parameters: e = de = 0               (zero/potential.h:49-54)                       */
 } xsb_pair_pot;
 
 /* ---------------------------------------------------------------------------------------------------- */
@@ -197,6 +200,14 @@ int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_
 /*     params19: re fe rhoe alpha beta A B kappa lambda Fn0..Fn3 F0..F3 Fo eta.                          */
 /*     phases: bit0 emb pass, bit1 emb pass covers ghost cells (ComputeGhostEmb), bit2 force pass.        */
 int xsb_eam_johnson_force(xsb_ctx* ctx, const double* params19, double rcut, int phases, int flags);
+/* The other analytic single-species models of the same operator template (eam_potential_template, one plugin per model:   */
+/* `<name>_force`, `<name>_emb`, `<name>_force_reuse_emb`, `<name>_init`): parameters in the reference struct's order.       */
+typedef enum xsb_eam_model {
+  XSB_EAM_JOHNSON = 0,      /* 19 scalars (eam_potentials/johnson/johnson.h:29-50)                                            */
+  XSB_EAM_SUTTON_CHEN = 1,  /* c, epsilon, a0, n, m (eam_potentials/sutton_chen/sutton_chen.h:24-62)                          */
+  XSB_EAM_VNIITF = 2        /* rmax, rmin, rt0, Ecoh, E0, beta, A, Z, n, alpha, D, eta, mu (eam_potentials/vniitf/vniitf.h:31-125) */
+} xsb_eam_model;
+int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int nparams, double rcut, int phases, int flags);
 
 /* a8  eam_alloy_force (eam_potential_multimat.cu:65-259, eam_alloy.h:37-313).                           */
 typedef struct xsb_eam_alloy_tables {

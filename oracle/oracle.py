@@ -67,6 +67,7 @@ def lib():
         L.orc_pair_multi_force.argtypes = [gp, _u64p, _dp, _dp, _dp, _u8p, vp, C.c_int, C.c_int, _dp, C.c_double, C.c_int,
                                            _dp, _dp, _dp, vp, vp]
         L.orc_eam_johnson.argtypes = [gp, _u64p, _dp, _dp, _dp, vp, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
+        L.orc_eam_analytic.argtypes = [gp, _u64p, _dp, _dp, _dp, vp, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, vp, _dp]
         L.orc_eam_alloy_load.restype = vp
         L.orc_eam_alloy_load.argtypes = [C.c_char_p]
         L.orc_eam_alloy_free.argtypes = [vp]
@@ -88,6 +89,7 @@ def lib():
         L.orc_num_threads.restype = C.c_int
         L.orc_lj_eval.argtypes = [C.c_double, C.c_double, C.c_double, dpp, dpp]
         L.orc_johnson_eval.argtypes = [_dp, C.c_int, C.c_double, dpp, dpp]
+        L.orc_eam_analytic_eval.argtypes = [C.c_int, _dp, C.c_int, C.c_double, dpp, dpp]
         L.orc_ev_internal.restype = C.c_double
         L.orc_pair_eval.argtypes = [C.c_int, _dp, C.c_double, dpp, dpp]
         L.orc_pair_ecut.restype = C.c_double
@@ -158,6 +160,8 @@ def ref():
         R.xsref_ev_internal.restype = C.c_double
         if hasattr(R, "xsref_pair"):
             R.xsref_pair.argtypes = [C.c_int, _dp, C.c_double, dpp, dpp]
+        if hasattr(R, "xsref_eam_analytic"):
+            R.xsref_eam_analytic.argtypes = [C.c_int, _dp, C.c_int, C.c_double, dpp, dpp]
         _ref = R
     return _ref
 
@@ -223,7 +227,8 @@ def _opt(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM = 0, 1, 2, 3
+POT_LJ, POT_ZBL, POT_EXP6, POT_BUCKINGHAM, POT_YUKAWA, POT_RELAX, POT_ZERO = 0, 1, 2, 3, 4, 5, 6
+EAM_JOHNSON, EAM_SUTTON_CHEN, EAM_VNIITF = 0, 1, 2
 
 
 def pair_eval(pot, params, r):
@@ -251,6 +256,19 @@ def pair_multi_force(grid, cell_off, rx, ry, rz, typ, nbh, pair_params, rcut_max
 def eam_johnson(grid, cell_off, rx, ry, rz, nbh, params19, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb):
     lib().orc_eam_johnson(C.byref(grid), cell_off, rx, ry, rz, nbh.h, np.ascontiguousarray(params19, dtype=np.float64), float(rcut),
                           int(flags), fx, fy, fz, ep, _opt(vir), rho_dEmb)
+
+
+def eam_analytic(grid, cell_off, rx, ry, rz, nbh, model, params, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb):
+    """single-species analytic EAM (eam_potential_template): model 0 johnson, 1 sutton_chen, 2 vniitf; flags as eam_johnson"""
+    lib().orc_eam_analytic(C.byref(grid), cell_off, rx, ry, rz, nbh.h, int(model), np.ascontiguousarray(params, dtype=np.float64), float(rcut),
+                           int(flags), fx, fy, fz, ep, _opt(vir), rho_dEmb)
+
+
+def eam_analytic_eval(model, params, what, x):
+    """(f, df) of phi (what 0), rho (1) or fEmbed (2) of the restated model"""
+    f, df = C.c_double(), C.c_double()
+    lib().orc_eam_analytic_eval(int(model), np.ascontiguousarray(params, dtype=np.float64), int(what), float(x), C.byref(f), C.byref(df))
+    return f.value, df.value
 
 
 class EamAlloy:

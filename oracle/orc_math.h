@@ -6,6 +6,7 @@
 // against oracle/_ref/libxsref.so, which compiles the reference's own unmodified headers.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -140,18 +141,39 @@ static inline void buckingham_energy(const double* p /* A Rho C */, double x, do
   de = (6 * p[2] / x7) - (p[0] * exp(-x / p[1]) / p[1]);
 }
 
+// src/potential/pair_potentials/yukawa/include/exaStamp/potential/pair_potentials/yukawa/yukawa.h:39-48 (the derivative is
+// restated as the reference writes it: de = e (1/r - kappa))
+static inline void yukawa_compute_energy(const double* p /* A kappa */, double r, double& e, double& de)
+{
+  double ratio = p[0] / r;
+  double rinv = 1. / r;
+  e  = ratio * exp( - p[1] * r );
+  de = e * ( rinv - p[1] );
+}
+
+// src/potential/pair_potentials/relax/potential.h:43-51 (overlap-relaxation ramp: r clamped to [r1, rc], de = -e)
+static inline void relax_compute_energy(const double* p /* r1 rc */, double rij, double& e, double& de)
+{
+  double r = rij;
+  if( r < p[0] ) r = p[0];
+  if( r > p[1] ) r = p[1];
+  e = ( p[1] / r ) - 1.0;
+  de = - e;
+}
+
 // one pair evaluation of potential `pot` with its raw parameter vector (what USTAMP_POTENTIAL_COMPUTE expands to)
+// 4 yukawa {A, kappa}; 5 relax {r1, rc}; 6 zero {} (src/potential/pair_potentials/zero/potential.h:49-54: e = de = 0)
 struct PairPot
 {
   int pot = 0; double prm[4] = {0, 0, 0, 0}; ZBLPair zbl{};
   PairPot() = default;
   PairPot(int pot_, const double* params) : pot(pot_)
   {
-    const int n = pot == 0 ? 2 : (pot == 3 ? 3 : 4);
+    const int n = nparams(pot);
     for(int i = 0; i < n; i++) prm[i] = params[i];
     if( pot == 1 ) zbl = zbl_pair(ZBLParams{ params[0], params[1] }, params[2], params[3]);
   }
-  static int nparams(int pot) { return pot == 0 ? 2 : (pot == 3 ? 3 : 4); }
+  static int nparams(int pot) { return pot == 6 ? 0 : (pot == 0 || pot == 4 || pot == 5 ? 2 : (pot == 3 ? 3 : 4)); }
   inline void compute(double r, double& e, double& de) const
   {
     switch( pot )
@@ -159,7 +181,10 @@ struct PairPot
       case 0: lj_compute_energy(LJParams{ prm[0], prm[1] }, r, e, de); break;
       case 1: zbl_compute_energy(zbl, r, e, de); break;
       case 2: exp6_compute_energy(prm, r, e, de); break;
-      default: buckingham_energy(prm, r, e, de); break;
+      case 3: buckingham_energy(prm, r, e, de); break;
+      case 4: yukawa_compute_energy(prm, r, e, de); break;
+      case 5: relax_compute_energy(prm, r, e, de); break;
+      default: e = 0.0; de = 0.0; break;
     }
   }
   // pair_potential_impl.hxx:488-498 (energy_cutoff)
@@ -236,6 +261,92 @@ static inline void johnson_fEmbed(const JohnsonParams& p, double rho, double& f,
     df *= p.Fo * irhoe / raprho;
   }
 }
+
+// src/potential/eam_potentials/sutton_chen/sutton_chen.h:33-62 (5 scalars: c, epsilon, a0, n, m)
+struct SuttonChenParams { double c, epsilon, a0, n, m; };
+static inline void sutton_chen_phi(const SuttonChenParams& p, double r, double& phiValue, double& dphi)
+{
+  double ratio = p.a0 / r;
+  phiValue = p.epsilon * std::pow(ratio, p.n);
+  dphi = -1 * p.n * phiValue / r;
+}
+static inline void sutton_chen_rho(const SuttonChenParams& p, double r, double& rhoValue, double& drho)
+{
+  double ratio = p.a0 / r;
+  rhoValue = std::pow(ratio, p.m);
+  drho = -1 * p.m * rhoValue / r;
+}
+static inline void sutton_chen_fEmbed(const SuttonChenParams& p, double rhoValue, double& f, double& df)
+{
+  double sqrtRho = std::sqrt(rhoValue);
+  f  = -1. * p.c * p.epsilon * sqrtRho;
+  df = 0.5 * f / (rhoValue > 0 ? rhoValue : 0);
+}
+
+// src/potential/eam_potentials/vniitf/vniitf.h:31-125 (13 scalars, same order)
+struct VniitfParams { double rmax, rmin, rt0, Ecoh, E0, beta, A, Z, n, alpha, D, eta, mu; };
+static inline double vniitf_dS3(double x) { double x2 = x * x; double x3 = x2 * x; return 140 * x3 * ( -1 * x3 + 3 * x2 - 3 * x + 1 ); }
+static inline double vniitf_S3(double x) { double x2 = x * x; return x2 * x2 * ( -20 * x2 * x + 70 * x2 - 84 * x + 35 ); }
+static inline void vniitf_switch(const VniitfParams& p, double r, double& S, double& dS)
+{
+  double drS = (p.rmax - r) / (p.rmax - p.rmin);
+  S  = vniitf_S3(drS);
+  dS = vniitf_dS3(drS) / (p.rmin - p.rmax);
+  if( drS < 0 ) { S = 0.; dS = 0.; }
+  else if( drS > 1 ) { S = 1.; dS = 0.; }
+}
+static inline void vniitf_phi(const VniitfParams& p, double r, double& phi, double& dphi)
+{
+  double ir = 1 / r;
+  double irt0 = 1 / p.rt0;
+  double dr = r * irt0 - 1.0;
+  double dr2 = dr * dr;
+  double a = -2 * p.Ecoh / p.Z;
+  double b = p.alpha * p.alpha * p.alpha * p.D * p.rt0;
+  double f1  = a * ( 1 + p.alpha * dr + p.eta * dr2 + (p.mu + b * ir) * dr2 * dr );
+  double df1 = a * ( p.alpha * irt0 + 2 * p.eta * irt0 * dr + 3 * p.mu * irt0 * dr2 + b * (3 * irt0 - dr * ir) * dr2 * ir );
+  double f2  = std::exp(-p.alpha * dr);
+  double df2 = -p.alpha * irt0 * f2;
+  double S, dS; vniitf_switch(p, r, S, dS);
+  phi  = (p.E0 + f1 * f2) * S;
+  dphi = (p.E0 + f1 * f2) * dS + (f1 * df2 + f2 * df1) * S;
+}
+static inline void vniitf_rho(const VniitfParams& p, double r, double& rho, double& drho)
+{
+  double irt0 = 1 / p.rt0;
+  double F  = exp(-p.beta * (r * irt0 - 1.0)) / p.Z;
+  double dF = -p.beta * F * irt0;
+  double S, dS; vniitf_switch(p, r, S, dS);
+  rho  = F * S;
+  drho = F * dS + S * dF;
+}
+static inline void vniitf_fEmbed(const VniitfParams& p, double rho, double& f, double& df)
+{
+  if( rho <= 0. ) { f = 0.; df = 0.; }
+  else
+  {
+    double a = pow(rho, p.n);
+    double b = p.A * p.Ecoh * a;
+    double c = log(a);
+    f  = b * (c - 1);
+    df = p.n * b * c / rho;
+  }
+}
+
+// the analytic single-species models behind eam_potential_template (USTAMP_POTENTIAL_EAM_RHO / _PHI / _EMB):
+// model ids as include/xsb200.h xsb_eam_model: 0 johnson (19 scalars), 1 sutton_chen (5), 2 vniitf (13)
+struct EamAnalytic
+{
+  int model = 0; JohnsonParams j{}; SuttonChenParams sc{}; VniitfParams vn{};
+  static int nparams(int model) { return model == 0 ? 19 : (model == 1 ? 5 : (model == 2 ? 13 : -1)); }
+  EamAnalytic(int m, const double* prm) : model(m)
+  {
+    if( m == 0 ) std::memcpy(&j, prm, sizeof(j)); else if( m == 1 ) std::memcpy(&sc, prm, sizeof(sc)); else std::memcpy(&vn, prm, sizeof(vn));
+  }
+  inline void rho(double r, double& f, double& df) const { if( model == 0 ) johnson_rho(j, r, f, df); else if( model == 1 ) sutton_chen_rho(sc, r, f, df); else vniitf_rho(vn, r, f, df); }
+  inline void phi(double r, double& f, double& df) const { if( model == 0 ) johnson_phi(j, r, f, df); else if( model == 1 ) sutton_chen_phi(sc, r, f, df); else vniitf_phi(vn, r, f, df); }
+  inline void fEmbed(double x, double& f, double& df) const { if( model == 0 ) johnson_fEmbed(j, x, f, df); else if( model == 1 ) sutton_chen_fEmbed(sc, x, f, df); else vniitf_fEmbed(vn, x, f, df); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // eam/alloy (setfl) tables, LAMMPS pair_eam 7-coefficient splines.

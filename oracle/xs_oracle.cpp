@@ -416,12 +416,21 @@ void orc_pair_multi_force(const orc_grid_t* g, const uint64_t* cell_off, const d
 // operator: src/potential/eam_potential_template/eam_potential.cu:105-174 ; functors
 // eam_force_op_singlemat.h:39-84 (EmbOp) and :86-171 (ForceOp).  flags: bit0 = compute emb pass,
 // bit1 = emb pass over ghost cells too (ComputeGhostEmb), bit2 = force pass.
+// model: 0 johnson, 1 sutton_chen, 2 vniitf -- the operator template is the same, only the three functions differ
+// (<name>/potential.h: USTAMP_POTENTIAL_EAM_RHO / _PHI / _EMB)
+void orc_eam_analytic(const orc_grid_t* g, const uint64_t* cell_off, const double* rx, const double* ry, const double* rz,
+                      void* nbh, int model, const double* params, double rcut, int flags,
+                      double* fx, double* fy, double* fz, double* ep, double* vir, double* rho_dEmb);
 void orc_eam_johnson(const orc_grid_t* g, const uint64_t* cell_off, const double* rx, const double* ry, const double* rz,
                      void* nbh, const double* params19, double rcut, int flags,
                      double* fx, double* fy, double* fz, double* ep, double* vir, double* rho_dEmb)
+{ orc_eam_analytic(g, cell_off, rx, ry, rz, nbh, 0, params19, rcut, flags, fx, fy, fz, ep, vir, rho_dEmb); }
+void orc_eam_analytic(const orc_grid_t* g, const uint64_t* cell_off, const double* rx, const double* ry, const double* rz,
+                      void* nbh, int model, const double* params, double rcut, int flags,
+                      double* fx, double* fy, double* fz, double* ep, double* vir, double* rho_dEmb)
 {
   const Particles P{ cell_off, rx, ry, rz, nullptr };
-  JohnsonParams p; std::memcpy(&p, params19, sizeof(p));
+  const EamAnalytic p(model, params);
   const Nbh& nb = *static_cast<Nbh*>(nbh);
   if( flags & 1 )
   {
@@ -435,11 +444,11 @@ void orc_eam_johnson(const orc_grid_t* g, const uint64_t* cell_off, const double
       {
         const double r = std::sqrt(tab.d2[i]);
         double Rho = 0., dRho = 0.;
-        johnson_rho(p, r, Rho, dRho);
+        p.rho(r, Rho, dRho);
         particle_rho += Rho;
       }
       double Emb = 0., dEmb = 0.;
-      johnson_fEmbed(p, particle_rho, Emb, dEmb);
+      p.fEmbed(particle_rho, Emb, dEmb);
       ep[ga] += Emb;
       rho_dEmb[ga] = dEmb;
     });
@@ -455,8 +464,8 @@ void orc_eam_johnson(const orc_grid_t* g, const uint64_t* cell_off, const double
       {
         const double r = std::sqrt(tab.d2[i]);
         double Rho = 0., dRho = 0., Phi = 0., dPhi = 0.;
-        johnson_rho(p, r, Rho, dRho);
-        johnson_phi(p, r, Phi, dPhi);
+        p.rho(r, Rho, dRho);
+        p.phi(r, Phi, dPhi);
         const double de = ( dRho * ( dEmb + rho_dEmb[tab.gb[i]] ) + dPhi ) / r;
         const double fe_x = de * tab.drx[i], fe_y = de * tab.dry[i], fe_z = de * tab.drz[i];
         _fx += fe_x; _fy += fe_y; _fz += fe_z;
@@ -625,6 +634,12 @@ void orc_johnson_eval(const double* params19, int what, double x, double* f, dou
   if( what == 0 ) johnson_phi(p, x, *f, *df);
   else if( what == 1 ) johnson_rho(p, x, *f, *df);
   else johnson_fEmbed(p, x, *f, *df);
+}
+
+void orc_eam_analytic_eval(int model, const double* params, int what, double x, double* f, double* df)
+{
+  const EamAnalytic p(model, params);
+  if( what == 0 ) p.phi(x, *f, *df); else if( what == 1 ) p.rho(x, *f, *df); else p.fEmbed(x, *f, *df);
 }
 
 int orc_num_threads() { return omp_get_max_threads(); }

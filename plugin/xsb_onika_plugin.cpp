@@ -190,7 +190,7 @@ namespace xsbplugin
   // ------------------------------------------------------------------------------------------------------------------
   // <pot>_compute_force (pair_potential_impl.hxx:39-500; slots :104-122) and <pot>_multi_force
   // ------------------------------------------------------------------------------------------------------------------
-  static int pair_param_count(int pot) { return pot == XSB_POT_LJ ? 2 : pot == XSB_POT_BUCKINGHAM ? 3 : 4; }
+  static int pair_param_count(int pot) { return pot == XSB_POT_ZERO ? 0 : (pot == XSB_POT_LJ || pot == XSB_POT_YUKAWA || pot == XSB_POT_RELAX) ? 2 : pot == XSB_POT_BUCKINGHAM ? 3 : 4; }
 
   // parameters of one pair in the library's order; quantities arrive converted to internal units by onika's YAML layer
   static std::vector<double> pair_params(int pot, const YAML::Node& p, unsigned za, unsigned zb)
@@ -200,7 +200,10 @@ namespace xsbplugin
       case XSB_POT_LJ:         return { p["epsilon"].as<double>(), p["sigma"].as<double>() };                      // lennard_jones.h:60-71
       case XSB_POT_ZBL:        return { p["r1"].as<double>(), p["rc"].as<double>(), double(za), double(zb) };      // zbl/potential.h:36-57 (z from species)
       case XSB_POT_EXP6:       return { p["A"].as<double>(), p["B"].as<double>(), p["C"].as<double>(), p["D"].as<double>() };
-      default:                 return { p["A"].as<double>(), p["Rho"].as<double>(), p["C"].as<double>() };
+      case XSB_POT_BUCKINGHAM: return { p["A"].as<double>(), p["Rho"].as<double>(), p["C"].as<double>() };
+      case XSB_POT_YUKAWA:     return { p["A"].as<double>(), p["kappa"].as<double>() };                            // yukawa.h:56-70
+      case XSB_POT_RELAX:      return { p["r1"].as<double>(), p["rc"].as<double>() };                              // relax/potential.h:56-72
+      default:                 return {};                                                                          // zero
     }
   }
 
@@ -270,11 +273,15 @@ namespace xsbplugin
   template<class GridT> using XsbZblMultiForce    = XsbPairForce<GridT, XSB_POT_ZBL, true>;
   template<class GridT> using XsbExp6ComputeForce = XsbPairForce<GridT, XSB_POT_EXP6, false>;
   template<class GridT> using XsbBuckComputeForce = XsbPairForce<GridT, XSB_POT_BUCKINGHAM, false>;
+  template<class GridT> using XsbYukawaComputeForce = XsbPairForce<GridT, XSB_POT_YUKAWA, false>;
+  template<class GridT> using XsbRelaxComputeForce  = XsbPairForce<GridT, XSB_POT_RELAX, false>;
+  template<class GridT> using XsbZeroComputeForce   = XsbPairForce<GridT, XSB_POT_ZERO, false>;
 
   // ------------------------------------------------------------------------------------------------------------------
   // johnson_force / johnson_emb / johnson_force_reuse_emb (eam_potential.cu:69-176; 19 scalars johnson.h:176-204)
   // ------------------------------------------------------------------------------------------------------------------
-  template<class GridT, int PHASES>
+  // MODEL = xsb_eam_model: the same operator template serves sutton_chen (sutton_chen.h:71-83) and vniitf (vniitf.h:139-157)
+  template<class GridT, int PHASES, int MODEL = XSB_EAM_JOHNSON>
   class XsbJohnson : public OperatorNode
   {
     ADD_SLOT( YAML::Node , parameters     , INPUT , REQUIRED );
@@ -290,19 +297,29 @@ namespace xsbplugin
       *rcut_max = std::max(*rcut_max, *rcut);
       *ghost_dist_max = std::max(*ghost_dist_max, 2.0 * (*rcut));      // single-pass EAM needs F'(rho) of ghosts: 2 rcut of ghost atoms
       if( grid->number_of_cells() == 0 ) return;
-      static const char* names[19] = { "re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lambda", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta" };
-      double p[19]; for(int i = 0; i < 19; i++) p[i] = (*parameters)[names[i]].template as<double>();
+      static const std::vector<const char*> all_names[3] = {
+        { "re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lambda", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta" },
+        { "c", "epsilon", "a0", "n", "m" },
+        { "rmax", "rmin", "rt0", "Ecoh", "E0", "beta", "A", "Z", "n", "alpha", "D", "eta", "mu" } };
+      const std::vector<const char*>& names = all_names[MODEL];
+      double p[19]; for(size_t i = 0; i < names.size(); i++) p[i] = (*parameters)[names[i]].template as<double>();
       xsb_ctx* c = context(this);
       bind_grid(c, *grid, *domain, true);
       const bool vir = grid->has_allocated_field(field::virial);
       XSB_CK(xsb_zero_force_energy(c, 1));
-      XSB_CK(xsb_eam_johnson_force(c, p, *rcut, PHASES, vir ? XSB_FLAG_VIRIAL : 0));
+      XSB_CK(xsb_eam_analytic_force(c, MODEL, p, int(names.size()), *rcut, PHASES, vir ? XSB_FLAG_VIRIAL : 0));
       add_forces_to_grid(c, *grid, vir);
     }
   };
   template<class GridT> using XsbJohnsonForce   = XsbJohnson<GridT, 1 | 2 | 4>;
   template<class GridT> using XsbJohnsonEmb     = XsbJohnson<GridT, 1 | 2>;
   template<class GridT> using XsbJohnsonReuse   = XsbJohnson<GridT, 4>;
+  template<class GridT> using XsbSuttonChenForce = XsbJohnson<GridT, 1 | 2 | 4, XSB_EAM_SUTTON_CHEN>;
+  template<class GridT> using XsbSuttonChenEmb   = XsbJohnson<GridT, 1 | 2, XSB_EAM_SUTTON_CHEN>;
+  template<class GridT> using XsbSuttonChenReuse = XsbJohnson<GridT, 4, XSB_EAM_SUTTON_CHEN>;
+  template<class GridT> using XsbVniitfForce     = XsbJohnson<GridT, 1 | 2 | 4, XSB_EAM_VNIITF>;
+  template<class GridT> using XsbVniitfEmb       = XsbJohnson<GridT, 1 | 2, XSB_EAM_VNIITF>;
+  template<class GridT> using XsbVniitfReuse     = XsbJohnson<GridT, 4, XSB_EAM_VNIITF>;
 
   // ------------------------------------------------------------------------------------------------------------------
   // eam_alloy_init / eam_alloy_force (eam_potential_multimat.cu:58-259; slots :88-109)
@@ -462,6 +479,15 @@ namespace xsbplugin
     F->register_factory( XSB_OPNAME("zbl_multi_force")           , make_grid_variant_operator< XsbZblMultiForce > );
     F->register_factory( XSB_OPNAME("exp6_compute_force")        , make_grid_variant_operator< XsbExp6ComputeForce > );
     F->register_factory( XSB_OPNAME("buckingham_compute_force")  , make_grid_variant_operator< XsbBuckComputeForce > );
+    F->register_factory( XSB_OPNAME("yukawa_compute_force")      , make_grid_variant_operator< XsbYukawaComputeForce > );
+    F->register_factory( XSB_OPNAME("relax_compute_force")       , make_grid_variant_operator< XsbRelaxComputeForce > );
+    F->register_factory( XSB_OPNAME("zero_compute_force")        , make_grid_variant_operator< XsbZeroComputeForce > );
+    F->register_factory( XSB_OPNAME("sutton_chen_force")         , make_grid_variant_operator< XsbSuttonChenForce > );
+    F->register_factory( XSB_OPNAME("sutton_chen_emb")           , make_grid_variant_operator< XsbSuttonChenEmb > );
+    F->register_factory( XSB_OPNAME("sutton_chen_force_reuse_emb"), make_grid_variant_operator< XsbSuttonChenReuse > );
+    F->register_factory( XSB_OPNAME("vniitf_force")              , make_grid_variant_operator< XsbVniitfForce > );
+    F->register_factory( XSB_OPNAME("vniitf_emb")                , make_grid_variant_operator< XsbVniitfEmb > );
+    F->register_factory( XSB_OPNAME("vniitf_force_reuse_emb")    , make_grid_variant_operator< XsbVniitfReuse > );
     F->register_factory( XSB_OPNAME("johnson_force")             , make_grid_variant_operator< XsbJohnsonForce > );
     F->register_factory( XSB_OPNAME("johnson_emb")               , make_grid_variant_operator< XsbJohnsonEmb > );
     F->register_factory( XSB_OPNAME("johnson_force_reuse_emb")   , make_grid_variant_operator< XsbJohnsonReuse > );

@@ -218,6 +218,48 @@ def test_johnson_force_parity(virial):
         assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
 
 
+# sutton_chen / vniitf: the other analytic single-species models of eam_potential_template (xsb_eam_analytic_force)
+JOULE = 1.0 / 1.602176634e-19 * EV
+EAM1_CASES = {
+    # parameter sets of the reference's regression decks potentials/eam/eam_sutton_chen/single_specy.msp, eam_vniitf/single_specy.msp
+    "sutton_chen": (xsb.EAM_SUTTON_CHEN, [3.317e1, 3.605e-21 * JOULE, 3.27, 9.05, 5.005], 5.5, 6.5),
+    "vniitf": (xsb.EAM_VNIITF, [5.599, 1.0, 3.437, 2.956031e-19 * JOULE, 5.15003855e-20 * JOULE, 6.0, 1.401, 7.618, 0.724, 3.072, 0.145, 2.72, -1.87], 5.599, 6.5),
+    "vniitf_narrow_switch": (xsb.EAM_VNIITF, [5.5, 4.9, 3.44, 3.1 * EV, 0.02 * EV, 5.1, 1.05, 10.0, 0.62, 3.7, 0.08, 6.0, 2.5], 5.5, 6.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EAM1_CASES))
+@pytest.mark.parametrize("virial,two_step", [(False, False), (True, True)])
+def test_eam_analytic_models_parity(name, virial, two_step):
+    """<name>_force, and <name>_emb followed by <name>_force_reuse_emb (the force pass then consumes the cached rho'(r))"""
+    model, p, rcut, nbh = EAM1_CASES[name]
+    O = oracle()
+    gs = system(ncells=5, a=3.615, sigma=0.05, cell=3.615, gl=4)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    fx, fy, fz, ep, emb = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    O.eam_analytic(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, model, p, rcut, 7, fx, fy, fz, ep, vir, emb)
+    assert np.abs(fx).max() > 0 and np.all(np.isfinite(emb))
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(nbh)
+    ctx.zero_force_energy(ghost=True)
+    fl = xsb.FLAG_VIRIAL if virial else 0
+    if two_step:
+        ctx.eam_analytic_force(model, p, rcut, 3, fl)
+        ctx.eam_analytic_force(model, p, rcut, 4, fl)
+    else:
+        ctx.eam_analytic_force(model, p, rcut, 7, fl)
+    assert rel_err(ctx.download(xsb.F_RHO_DEMB), emb) < TOL64
+    for f, ref in ((xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep)):
+        assert rel_err(ctx.download(f), ref) < TOL64, (name, f)
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+    # a johnson call with other parameters must not reuse this model's cached pair values
+    with pytest.raises(xsb.XsbError):
+        ctx.eam_analytic_force(model, p[:-1], rcut, 7, 0)
+
+
 # ------------------------------------------------------------------------------------------------ a8
 def eam_alloy_case(tmp_path, elements, types, eflag, virial, two_step):
     O = oracle()
@@ -504,6 +546,9 @@ PAIR_CASES = {
     "zbl_rcut_beyond_rc": (1, [1.0, 3.6, 29, 29], 4.4, 5.4),         # pairs between rc and rcut contribute -ecut = 0 and no force
     "exp6": (2, [3.0e5 * EV, 3.6, 60.0 * EV, 1.0e-6 * EV], 5.5, 6.5),
     "buckingham": (3, [1.2e3 * EV, 0.32, 25.0 * EV], 5.5, 6.5),
+    "yukawa": (4, [2.43 * EV, 4.1], 5.5, 6.5),                        # potentials/pair/yukawa/single_specy_nosym.msp:6 (`de` as the reference writes it)
+    "yukawa_soft": (4, [25.0 * EV, 1.3], 5.5, 6.5),
+    "relax": (5, [2.2, 3.9], 4.4, 5.4),                               # relax/potential.h:43-51: pairs below r1 and beyond rc are clamped
 }
 
 
@@ -527,6 +572,17 @@ def test_pair_potentials_parity(name, virial):
         assert rel_err(ctx.download(f), ref) < TOL64, (name, f)
     if virial:
         assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOL64
+
+
+def test_zero_potential_adds_nothing():
+    """zero_compute_force (zero/potential.h:49-54): e = de = 0 for every pair"""
+    gs = system(ncells=6, a=3.3, sigma=0.08, cell=3.3, gl=2)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(5.0)
+    ctx.zero_force_energy(ghost=True)
+    ctx.pair_force([], 4.0, xsb.FLAG_ENERGY, pot=xsb.POT_ZERO)
+    for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP):
+        assert not ctx.download(f).any()
 
 
 @pytest.mark.parametrize("twoj", [8, 4])

@@ -102,7 +102,9 @@ def test_operator_factory_lists_the_reference_names():
     for n in ["lj_compute_force", "lj_multi_force", "lj_compute_force_symetric", "johnson_force", "johnson_emb", "johnson_force_reuse_emb", "johnson_init",
               "eam_alloy_force", "eam_alloy_init", "snap_force", "chunk_neighbors", "ghost_update_r", "ghost_update_opt", "ghost_update_all_no_fv",
               "update_force_energy_from_ghost", "update_opt_from_ghost", "ghost_comm_scheme", "zero_force_energy", "force_to_accel", "push_f_v_r", "push_f_v",
-              "particle_displ_over", "backup_r", "move_particles", "simulation_thermodynamic_state", "domain", "lattice"]:
+              "particle_displ_over", "backup_r", "move_particles", "simulation_thermodynamic_state", "domain", "lattice",
+              "yukawa_compute_force", "yukawa_multi_force", "relax_compute_force", "zero_compute_force", "sutton_chen_force", "sutton_chen_emb",
+              "sutton_chen_force_reuse_emb", "sutton_chen_init", "vniitf_force", "vniitf_emb", "vniitf_force_reuse_emb", "vniitf_init"]:
         assert n in names, n
 
 
@@ -170,7 +172,9 @@ def test_no_cpu_fallback_in_the_host_layer():
     ("pair/lj/single_specy_nosym.msp", 8.0), ("pair/lj/multi_species_nosym.msp", 8.0), ("pair/lj/single_specy_sym.msp", 8.0),
     ("eam/eam_alloy/single_specy_nosym_cs1.msp", 5.3), ("eam/eam_alloy/multi_species_nosym_cs4.msp", 6.6825),
     ("eam/eam_alloy/multi_species_singlepass_cs1.msp", 6.6825), ("eam/eam_alloy/multi_species_sym_cs1.msp", 6.6825),
-    ("eam/eam_alloy/benchmark_Al_Cu.msp", 6.6825), ("eam/eam_johnson/single_specy.msp", 6.1), ("snap/multi_WBe.msp", 4.8123)])
+    ("eam/eam_alloy/benchmark_Al_Cu.msp", 6.6825), ("eam/eam_johnson/single_specy.msp", 6.1), ("snap/multi_WBe.msp", 4.8123),
+    ("eam/eam_sutton_chen/single_specy.msp", 7.29), ("eam/eam_vniitf/single_specy.msp", 5.599), ("pair/yukawa/single_specy_nosym.msp", 10.0),
+    ("pair/yukawa/multi_species_nosym.msp", 8.0), ("pair/zero/single_specy_nosym.msp", 8.0)])
 def test_unmodified_reference_decks_resolve(deck, rcut_max):
     """the reference's own regression decks build a graph here: same names, same slots, same layering"""
     g, v = graph_of(os.path.join("/root/reference/data/regression_new/potentials", deck), "--data-dir", "/root/reference/data/config")
@@ -321,6 +325,24 @@ def test_johnson_deck_matches_oracle(tmp_path):
     nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 7.0, 1, True)
     fx, fy, fz, ep, emb = [gs.zeros() for _ in range(5)]
     O.eam_johnson(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, johnson_params(JOHNSON_CU), 6.0, 7, fx, fy, fz, ep, None, emb)
+    compare(d, gs, [63.546], fx, fy, fz, ep)
+
+
+@pytest.mark.gpu
+def test_sutton_chen_deck_matches_oracle(tmp_path):
+    """the parameters of the reference's own regression deck (eam_sutton_chen/single_specy.msp) through the deck layer:
+    unit conversion (J, m), sutton_chen_force on the GPU, oracle restatement of the same three functions"""
+    run(os.path.join(DECKS, "sutton_chen_single_specy.msp"), cwd=tmp_path)
+    d = read_dump(tmp_path / "sutton_chen.xsbdump")
+    from oracle import oracle as O
+    box = d["bounds_max"] - d["bounds_min"]
+    pos = np.mod(np.stack([d["rx"], d["ry"], d["rz"]], axis=1) - d["bounds_min"], box)
+    gs = GridSystem(pos, d["type"], box, d["cell_size"], 5)          # ghosts out to 2 rcut + skin (ComputeGhostEmb)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, 8.29, 1, True)
+    fx, fy, fz, ep, emb = [gs.zeros() for _ in range(5)]
+    prm = [3.317e1, 3.605e-21 / 1.602176634e-19 * EV, 3.27, 9.05, 5.005]
+    O.eam_analytic(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, O.EAM_SUTTON_CHEN, prm, 7.29, 7, fx, fy, fz, ep, None, emb)
     compare(d, gs, [63.546], fx, fy, fz, ep)
 
 
