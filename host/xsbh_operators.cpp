@@ -670,8 +670,13 @@ public:
               "xsb_pair_multi_force");
   }
 };
+// <pot>_compute_force_symetric (pair_potential_singlemat_symetric.cpp:335-346): the reference walks half lists and scatters -f
+// to the neighbour under particle locks, then folds ghost forces back (config_update_symmetric_forces.msp).  Here the same
+// totals come from the full-list kernel (one writer per atom, nothing lands on ghosts), so the surrounding zero-ghost /
+// update_force_energy_from_ghost nodes of those decks add zeros.
 #define XSBH_PAIR_OPS(potname, POT) \
   static OperatorRegistrar reg_##potname##_cf(#potname "_compute_force", []() { return std::unique_ptr<Operator>(new PairComputeForce(POT)); }); \
+  static OperatorRegistrar reg_##potname##_sy(#potname "_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(POT)); }); \
   static OperatorRegistrar reg_##potname##_mf(#potname "_multi_force", []() { return std::unique_ptr<Operator>(new PairMultiForce(POT)); });
 XSBH_PAIR_OPS(lj, XSB_POT_LJ)
 XSBH_PAIR_OPS(zbl, XSB_POT_ZBL)
@@ -680,12 +685,6 @@ XSBH_PAIR_OPS(buckingham, XSB_POT_BUCKINGHAM)
 XSBH_PAIR_OPS(yukawa, XSB_POT_YUKAWA)
 XSBH_PAIR_OPS(relax, XSB_POT_RELAX)
 XSBH_PAIR_OPS(zero, XSB_POT_ZERO)
-// lj_compute_force_symetric (pair_potential_singlemat_symetric.cpp:335-346): the reference walks half lists and
-// scatters -f to the neighbour under particle locks, then folds ghost forces back (config_update_symmetric_forces.msp).
-// Here the same totals come from the full-list kernel (one writer per atom, nothing lands on ghosts), so the
-// surrounding zero-ghost / update_force_energy_from_ghost nodes of those decks add zeros.
-static OperatorRegistrar reg_lj_sym("lj_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(XSB_POT_LJ)); });
-static OperatorRegistrar reg_zbl_sym("zbl_compute_force_symetric", []() { return std::unique_ptr<Operator>(new PairComputeForce(XSB_POT_ZBL)); });
 
 // johnson_force / johnson_emb / johnson_force_reuse_emb / johnson_init (eam_potential.cu:92-100,178-193; johnson.h:176-204)
 // The same operator class serves the other analytic single-species models of eam_potential_template: sutton_chen
@@ -784,6 +783,8 @@ class SnapForce : public Operator {
 public:
   bool configured = false;
   double rcut = 0.0;
+  bool fp32 = false;          // snap_force_fp32: the reference's SNAP_FP32_MATH plugin (snap/snap_force.cu:25-29) = XSB_FLAG_MIXED
+  explicit SnapForce(bool f32 = false) : fp32(f32) {}
   void execute(Simulation& sim) override {
     TRACE(sim);
     check_slots({"parameters", "rcut_max", "chunk_neighbors", "ghost", "grid", "domain", "bispectrumchkfile", "conv_coef_units", "trigger_thermo_state", "species", "particle_locks"});
@@ -820,7 +821,7 @@ public:
     sim.rcut_max = std::max(sim.rcut_max, rcut);
     if (sim.preinit) return;
     need_gpu(sim, name);
-    sim.check(xsb_snap_force(sim.ctx, force_flags(sim, bool_slot("ghost", false))), "xsb_snap_force");
+    sim.check(xsb_snap_force(sim.ctx, force_flags(sim, bool_slot("ghost", false)) | ((fp32 || sim.mixed_precision) ? XSB_FLAG_MIXED : 0)), "xsb_snap_force");
     int ovf = 0;
     sim.check(xsb_snap_overflow(sim.ctx, &ovf), "xsb_snap_overflow");
     if (ovf) throw OperatorError(name + ": an atom has more in-range neighbours than the kernel's capacity");
@@ -829,6 +830,8 @@ public:
 XSBH_REGISTER_OPERATOR("snap_force", SnapForce);
 // snaplmp_force (snaplmp.cpp:59-360) is the same operator computed through LAMMPS' sna.cpp upstream: same slots, same files
 static OperatorRegistrar reg_snaplmp("snaplmp_force", []() { return std::unique_ptr<Operator>(new SnapForce()); });
+// snap_force_fp32 (potentials/snap/multi_WBe_fp32.msp:31,60): the FP32-arithmetic build of the same operator
+static OperatorRegistrar reg_snapf32("snap_force_fp32", []() { return std::unique_ptr<Operator>(new SnapForce(true)); });
 
 // ================================================================================================ thermodynamic state, loop control
 class TriggerThermoState : public Operator {     // config_thermostate.msp: screen frequency trigger

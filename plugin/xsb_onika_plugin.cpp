@@ -386,8 +386,9 @@ namespace xsbplugin
   struct SnapFiles { int twojmax = 0, switchflag = 1, bzeroflag = 1; double rcutfac = 0, rfac0 = 0.99363, rmin0 = 0; std::vector<double> radelem, wjelem, beta; };
   SnapFiles read_snap_files(const std::string& param, const std::string& coef);      // same grammar as host/xsbh_readers.cpp
 
-  template<class GridT>
-  class XsbSnapForce : public OperatorNode
+  // FP32 = true: snap_force_fp32, the reference's SNAP_FP32_MATH plugin (snap/snap_force.cu:25-29, multi_WBe_fp32.msp:31,60)
+  template<class GridT, bool FP32 = false>
+  class XsbSnapForceT : public OperatorNode
   {
     ADD_SLOT( YAML::Node , parameters           , INPUT , REQUIRED , DocString{"{nt, param, coef}"} );
     ADD_SLOT( double     , rcut_max             , INPUT_OUTPUT , 0.0 );
@@ -420,10 +421,12 @@ namespace xsbplugin
       XSB_CK(xsb_zero_force_energy(c, 1));
       // f_i += f_ij, f_j -= f_ij: contributions to ghost neighbours land on the ghost copies, the deck's
       // update_force_energy_from_ghost folds them back (config_update_symmetric_forces.msp)
-      XSB_CK(xsb_snap_force(c, (*ghost ? XSB_FLAG_GHOST : 0) | (eflag ? XSB_FLAG_ENERGY : 0) | (vir ? XSB_FLAG_VIRIAL : 0)));
+      XSB_CK(xsb_snap_force(c, (*ghost ? XSB_FLAG_GHOST : 0) | (eflag ? XSB_FLAG_ENERGY : 0) | (vir ? XSB_FLAG_VIRIAL : 0) | (FP32 ? XSB_FLAG_MIXED : 0)));
       add_forces_to_grid(c, *grid, vir);
     }
   };
+  template<class GridT> using XsbSnapForce     = XsbSnapForceT<GridT, false>;
+  template<class GridT> using XsbSnapForceFp32 = XsbSnapForceT<GridT, true>;
 
   // ------------------------------------------------------------------------------------------------------------------
   // ghost operators (src/mpi/update_ghosts.cu:30-47, update_from_ghosts.cu:29-48) on the library's own exchange
@@ -479,6 +482,12 @@ namespace xsbplugin
     F->register_factory( XSB_OPNAME("zbl_multi_force")           , make_grid_variant_operator< XsbZblMultiForce > );
     F->register_factory( XSB_OPNAME("exp6_compute_force")        , make_grid_variant_operator< XsbExp6ComputeForce > );
     F->register_factory( XSB_OPNAME("buckingham_compute_force")  , make_grid_variant_operator< XsbBuckComputeForce > );
+    F->register_factory( XSB_OPNAME("zbl_compute_force_symetric")        , make_grid_variant_operator< XsbZblComputeForce > );
+    F->register_factory( XSB_OPNAME("exp6_compute_force_symetric")       , make_grid_variant_operator< XsbExp6ComputeForce > );
+    F->register_factory( XSB_OPNAME("buckingham_compute_force_symetric") , make_grid_variant_operator< XsbBuckComputeForce > );
+    F->register_factory( XSB_OPNAME("yukawa_compute_force_symetric")     , make_grid_variant_operator< XsbYukawaComputeForce > );
+    F->register_factory( XSB_OPNAME("relax_compute_force_symetric")      , make_grid_variant_operator< XsbRelaxComputeForce > );
+    F->register_factory( XSB_OPNAME("zero_compute_force_symetric")       , make_grid_variant_operator< XsbZeroComputeForce > );
     F->register_factory( XSB_OPNAME("yukawa_compute_force")      , make_grid_variant_operator< XsbYukawaComputeForce > );
     F->register_factory( XSB_OPNAME("relax_compute_force")       , make_grid_variant_operator< XsbRelaxComputeForce > );
     F->register_factory( XSB_OPNAME("zero_compute_force")        , make_grid_variant_operator< XsbZeroComputeForce > );
@@ -494,6 +503,7 @@ namespace xsbplugin
     F->register_factory( XSB_OPNAME("eam_alloy_init")            , make_simple_operator< XsbEamAlloyInit > );
     F->register_factory( XSB_OPNAME("eam_alloy_force")           , make_grid_variant_operator< XsbEamAlloyForce > );
     F->register_factory( XSB_OPNAME("snap_force")                , make_grid_variant_operator< XsbSnapForce > );
+    F->register_factory( XSB_OPNAME("snap_force_fp32")           , make_grid_variant_operator< XsbSnapForceFp32 > );
     F->register_factory( XSB_OPNAME("ghost_update_r")            , make_simple_operator< XsbGhostUpdateR > );
     F->register_factory( XSB_OPNAME("ghost_update_all_no_fv")    , make_simple_operator< XsbGhostUpdateAllNoFV > );
     F->register_factory( XSB_OPNAME("ghost_update_opt")          , make_simple_operator< XsbGhostUpdateOpt > );

@@ -174,13 +174,18 @@ def test_no_cpu_fallback_in_the_host_layer():
     ("eam/eam_alloy/multi_species_singlepass_cs1.msp", 6.6825), ("eam/eam_alloy/multi_species_sym_cs1.msp", 6.6825),
     ("eam/eam_alloy/benchmark_Al_Cu.msp", 6.6825), ("eam/eam_johnson/single_specy.msp", 6.1), ("snap/multi_WBe.msp", 4.8123),
     ("eam/eam_sutton_chen/single_specy.msp", 7.29), ("eam/eam_vniitf/single_specy.msp", 5.599), ("pair/yukawa/single_specy_nosym.msp", 10.0),
-    ("pair/yukawa/multi_species_nosym.msp", 8.0), ("pair/zero/single_specy_nosym.msp", 8.0)])
+    ("pair/yukawa/multi_species_nosym.msp", 8.0), ("pair/zero/single_specy_nosym.msp", 8.0), ("pair/yukawa/single_specy_sym.msp", 8.0),
+    ("pair/buckingham/single_specy_sym.msp", None), ("pair/exp6/single_specy_sym.msp", None), ("pair/relax/single_specy_sym.msp", None),
+    ("snap/multi_WBe_fp32.msp", 4.8123)])
 def test_unmodified_reference_decks_resolve(deck, rcut_max):
     """the reference's own regression decks build a graph here: same names, same slots, same layering"""
     g, v = graph_of(os.path.join("/root/reference/data/regression_new/potentials", deck), "--data-dir", "/root/reference/data/config")
-    assert v["rcut_max"] == pytest.approx(rcut_max, rel=1e-15)
+    if rcut_max is not None:
+        assert v["rcut_max"] == pytest.approx(rcut_max, rel=1e-15)
     assert "chunk_neighbors" in g and "force_to_accel" in g
-    if "multi_WBe" in deck:   # zbl_multi_force + snap_force with the reference's own WBe_Wood_PRB2019 files, symmetric-force epilog
+    if "multi_WBe_fp32" in deck:   # the reference's SNAP_FP32_MATH variant: same graph with snap_force_fp32 (-> XSB_FLAG_MIXED)
+        assert " ".join(g).count("zero_force_energy zbl_multi_force snap_force_fp32 update_force_energy_from_ghost force_to_accel") >= 2
+    elif "multi_WBe" in deck:   # zbl_multi_force + snap_force with the reference's own WBe_Wood_PRB2019 files, symmetric-force epilog
         assert " ".join(g).count("zero_force_energy zbl_multi_force snap_force update_force_energy_from_ghost force_to_accel") >= 2
 
 

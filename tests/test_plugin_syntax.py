@@ -26,7 +26,8 @@ def test_plugin_registers_every_operator_of_the_hot_path():
             "eam_alloy_force", "snap_force", "ghost_update_r", "ghost_update_all_no_fv", "ghost_update_opt", "update_force_energy_from_ghost",
             "update_virial_force_energy_from_ghost", "update_opt_from_ghost", "zero_force_energy",
             "yukawa_compute_force", "relax_compute_force", "zero_compute_force", "sutton_chen_force", "sutton_chen_emb",
-            "sutton_chen_force_reuse_emb", "vniitf_force", "vniitf_emb", "vniitf_force_reuse_emb"}
+            "sutton_chen_force_reuse_emb", "vniitf_force", "vniitf_emb", "vniitf_force_reuse_emb", "snap_force_fp32",
+            "yukawa_compute_force_symetric", "buckingham_compute_force_symetric", "exp6_compute_force_symetric"}
     assert want <= names, sorted(want - names)
     # every C entry point the shim calls is declared by the public header
     hdr = open(os.path.join(ROOT, "include", "xsb200.h")).read()
