@@ -298,6 +298,7 @@ int xsb_create(int device, xsb_ctx** out)
   ctx->sm_count = prop.multiProcessorCount;
   ctx->tile_deal = getenv("XSB_TILE_DEAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
   ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
+  ctx->pair_sub_off = getenv("XSB_PAIR_NO_SUBLIST") != nullptr;
   ctx->exp_tpa = getenv("XSB_TPA") ? atoi(getenv("XSB_TPA")) : 0;
   ctx->inner_skin = getenv("XSB_INNER_SKIN") ? std::max(0.0, atof(getenv("XSB_INNER_SKIN"))) : 0.0;
   ctx->subcell_bits = getenv("XSB_SUBCELL_SORT") ? std::min(3, std::max(0, atoi(getenv("XSB_SUBCELL_SORT")))) : 0;

@@ -149,6 +149,11 @@ struct xsb_ctx
   bool type_external = false;                 // same for the type bytes (the per-pair cache of a multi-element pass depends on them)
   bool sub_valid(double rcut, bool need_ghost) const
   { return !pos_external && sub_epoch == pos_epoch && sub_rcut == rcut && (sub_ghost || !need_ghost); }
+  // a later operator of the same step with a SHORTER cut-off (a pair potential chained behind an EAM operator) may walk the
+  // sub-list instead of the full neighbour list: it holds every pair within sub_rcut on the current positions
+  bool sub_covers(double rcut, bool need_ghost) const
+  { return !pos_external && !pair_sub_off && sub_epoch == pos_epoch && rcut <= sub_rcut && (sub_ghost || !need_ghost); }
+  bool pair_sub_off = false;                  // env XSB_PAIR_NO_SUBLIST=1 (A/B)
   xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.
   xsb::DevBuf<unsigned long long> scratch64;  // misc u64 scratch
 

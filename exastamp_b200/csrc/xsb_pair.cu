@@ -274,7 +274,11 @@ static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int fl
     double *tep = (flags & XSB_FLAG_ENERGY) ? ctx->f64[XSB_F_EP].p : nullptr, *tvir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
     int rc;
     ctx->prof_begin(XSB_PROF_PAIR);
-#   define XSB_LJ_TILE(VIR, REAL, TPA_, NT_) { LJTileOp<MULTI, VIR, REAL> op{ rcut_max * rcut_max, prm, tfx, tfy, tfz, tep, tvir }; rc = launch_tile_pass<TPA_, NT_>(ctx, ghost, op, nullptr); }
+    // behind an EAM operator of the same step (compute_force: [eam_alloy_force, lj_multi_force], configs[4]) the in-range sub-list
+    // that operator left is a superset of this potential's pairs when its cut-off is the larger one: walk it instead of the
+    // full list (the distance test against this operator's own cut-off stays)
+    const int lmode = ctx->sub_covers(rcut_max, ghost) ? LIST_SUB : LIST_FULL;
+#   define XSB_LJ_TILE(VIR, REAL, TPA_, NT_) { LJTileOp<MULTI, VIR, REAL> op{ rcut_max * rcut_max, prm, tfx, tfy, tfz, tep, tvir }; rc = launch_tile_pass<TPA_, NT_>(ctx, ghost, op, nullptr, lmode); }
     if( mixed ) { if( virial ) XSB_LJ_TILE(true, float, 8, 512) else XSB_LJ_TILE(false, float, 16, 1024) }
     else        { if( virial ) XSB_LJ_TILE(true, double, 8, 512) else if( ctx->exp_tpa == 8 ) XSB_LJ_TILE(false, double, 8, 1024) else XSB_LJ_TILE(false, double, 16, 1024) }
 #   undef XSB_LJ_TILE

@@ -1162,3 +1162,40 @@ def test_eam_inner_skin_with_host_driven_positions(tmp_path):
     assert reused >= 4 and built >= 2
     assert stats[5][0] == stats[4][0] + 1             # the jump after step 4 made step 5 re-filter
     assert ctxs[0].eam_sublist_stats() == (0, 0)
+
+
+def test_pair_operator_behind_eam_walks_the_sublist(tmp_path, monkeypatch):
+    """compute_force: [eam_alloy_force, lj_multi_force] (configs[4]): the pair operator reuses the in-range sub-list the EAM
+    operator left when its own cut-off is not larger; XSB_PAIR_NO_SUBLIST=1 keeps the full list.  Same forces either way (only
+    the summation order differs), with a shorter pair cut-off, the inner skin on, and after the atoms moved (re-evaluated list)"""
+    path = write_setfl(str(tmp_path / "ab.eam.alloy"), [SC_CU, SC_XX], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    rng = np.random.default_rng(5)
+    pos, typ, box = lattice("FCC", 6, 3.615, 0.06, seed=9)
+    typ = (rng.random(len(pos)) < 0.5).astype(np.uint8)
+    vel = rng.normal(0.0, 3.0, pos.shape)
+    rows = np.array([[0.0104 * EV, 2.3, 5.6], [0.0150 * EV, 2.2, 5.0], [0.0200 * EV, 2.1, 4.4]])
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    ctxs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("XSB_PAIR_NO_SUBLIST", "1")
+        c = assigned_ctx(pos, typ, box, 3.615 * 2, 1, vel)
+        c.eam_alloy_load(path); c.eam_inner_skin(0.2); c.chunk_neighbors(7.0); c.backup_r()
+        ctxs.append(c)
+    monkeypatch.delenv("XSB_PAIR_NO_SUBLIST")
+    for step in range(3):
+        outs = []
+        for c in ctxs:
+            c.zero_force_energy()
+            c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_EFLAG, 0)
+            c.ghost_update([xsb.F_RHO_DEMB])
+            c.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG, 0)
+            eam_only = c.download(xsb.F_FX).copy()
+            c.pair_multi_force(2, rows, 5.6, xsb.FLAG_ENERGY)
+            outs.append([c.download(f) for f in (xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)])
+            assert np.abs(outs[-1][0] - eam_only).max() > 0            # the pair operator did add something
+        for a, b in zip(*outs):
+            assert rel_err(a, b) < 1e-12, step
+        for c in ctxs:
+            c.verlet_boundary_async([63.5, 27.0], 1.0e-3); c.ghost_update(POS)
+    assert ctxs[0].eam_sublist_stats()[1] >= 1                         # a re-evaluated (not re-filtered) sub-list was walked too
