@@ -11,6 +11,7 @@ Workloads = BASELINE.json configs, all NVE velocity Verlet, dt 1 
   c3  configs[2]  SNAP BCC a=3.316, 63^3 unit cells = 500 094 atoms, snap_force 2J=8 with the W block of the reference's
                   WBe_Wood_PRB2019.snap{param,coeff} (rcutfac 4.8123; no Ta 2J=8 file ships), skin 1.0
   c4  configs[3]  the c2 potential on 160^3 unit cells = 16 384 000 atoms split over the GPUs (strong scaling)
+  c2j configs[1]  the analytic variant: johnson_force (Zhou-Johnson-Wadley Cu parameters, rc 6.0) on the c2 lattice
   c5  configs[4]  two-species random FCC alloy a=3.8, 126^3 unit cells = 8 001 504 atoms, eam_alloy_force with the reference's
                   AlCu.eam.alloy (rc 6.6825) + lj_multi_force (potentials/pair/lj/multi_species_nosym.msp parameters),
                   triclinic cell matrix drifting every step as under NPT, rebuild on the displacement trigger
@@ -166,6 +167,46 @@ class EamCu(Workload):
         O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, self._cpu_eam, self.rcut, 8, fx, fy, fz, ep, None, emb)
 
 
+class EamCuJohnson(EamCu):
+    """configs[1], analytic variant: johnson_force on the same lattice.  No Cu set of the Johnson form ships
+    with the reference (its only one is Ta, potentials/eam/eam_johnson/single_specy.msp); the Zhou / Johnson / Wadley 2004 Cu
+    values (tests/helpers.JOHNSON_CU) are used with rc 6.0: ~80 neighbours in range, 4 exp + 4 pow(., 20) per pair and pass."""
+    name = "c2j"; rcut = 6.0
+    baseline = "configs[1] EAM Cu (Johnson/Mishin-type) FCC 2M atoms NVE on 1xB200 -- analytic johnson_force variant"
+    J = dict(re=2.556162, fe=1.554485, rhoe=21.175871, alpha=8.127620, beta=4.334731, A=0.396620, B=0.548085, kappa=0.308782, lam=0.756515,
+             Fn0=-2.170269, Fn1=-0.263788, Fn2=1.088878, Fn3=-0.817603, F0=-2.19, F1=0.0, F2=0.561830, F3=-2.100595, Fo=-2.186568, eta=0.310490)
+
+    def params(self):
+        e = {"A", "B", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo"}
+        order = ["re", "fe", "rhoe", "alpha", "beta", "A", "B", "kappa", "lam", "Fn0", "Fn1", "Fn2", "Fn3", "F0", "F1", "F2", "F3", "Fo", "eta"]
+        return np.array([self.J[k] * (EV if k in e else 1.0) for k in order])
+
+    def label(self, n, uc, scaling):
+        return "EAM Cu FCC %d^3 unit cells x %d GPU = %d atoms, johnson_force (analytic, Zhou-Johnson-Wadley Cu parameters, rc %.2f, skin %.1f)" % (
+            uc[0], n, 4 * uc[0] * uc[1] * uc[2] * n, self.rcut, self.skin)
+
+    def setup(self, ctx, xsb):
+        self.p19 = self.params()
+
+    def forces(self, ctx, xsb, flags=0, ef=0):
+        ctx.zero_force_energy()
+        ctx.eam_johnson_force(self.p19, self.rcut, 1, flags)                 # johnson_emb
+        ctx.ghost_update([xsb.F_RHO_DEMB])
+        ctx.eam_johnson_force(self.p19, self.rcut, 4, flags)                 # johnson_force_reuse_emb
+
+    def model(self, n_l, n_c):
+        b_list = 2 * (1 + 2 * 27 + n_l)
+        return {"eam_rho": dict(bytes=24 + 1 + b_list + 8 + 8, flops=8 * n_l + 60 * n_c, kernel="tile_pass_kernel<32,1024,LIST_FULL_WRITE_SUB,JohnsonEmbTileOp> (johnson_emb)"),
+                "eam_force": dict(bytes=24 + 1 + 8 + b_list + 32, flops=8 * n_l + 90 * n_c, kernel="tile_pass_kernel<16,1024,LIST_SUB,JohnsonForceTileOp> (johnson_force_reuse_emb)")}
+
+    def cpu_forces(self, O, g, gs, nb, arr, img):
+        fx, fy, fz, ep, emb = arr
+        p = self.params()
+        O.eam_johnson(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, p, self.rcut, 1, fx, fy, fz, ep, None, emb)
+        emb[:] = emb[img]
+        O.eam_johnson(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, p, self.rcut, 4, fx, fy, fz, ep, None, emb)
+
+
 class EamCuStrong(EamCu):
     name = "c4"; strong_total = 160
     baseline = "configs[3] EAM Cu 16M atoms weak/strong scaling over 1/2/4/8 B200 with ghost exchange"
@@ -233,7 +274,8 @@ class AlloyNPT(EamCu):
 
     def forces(self, ctx, xsb, flags=0, ef=0):
         EamCu.forces(self, ctx, xsb, flags, ef)
-        ctx.pair_multi_force(2, self.lj_rows, 6.10, flags)
+        # same energy switch for both operators of the chain (the reference's trigger_thermo_state reaches every force operator)
+        ctx.pair_multi_force(2, self.lj_rows, 6.10, flags | (xsb.FLAG_ENERGY if ef else 0))
 
     def kernels(self):
         return ["eam_rho", "eam_force", "pair"]
@@ -245,7 +287,7 @@ class AlloyNPT(EamCu):
         O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, rows, 6.10, 0, fx, fy, fz, None, None)
 
 
-WORKLOADS = {"c1": LJ, "c2": EamCu, "c3": SnapW, "c4": EamCuStrong, "c5": AlloyNPT}
+WORKLOADS = {"c1": LJ, "c2": EamCu, "c2j": EamCuJohnson, "c3": SnapW, "c4": EamCuStrong, "c5": AlloyNPT}
 
 
 def brick_cells(W, args, n):
@@ -795,7 +837,7 @@ def run_xsb(args):
                        "rebuilds_in_timed_region": rebuilds_timed, "rebuild_wall_s_total": rebuild_s_timed,
                        "move_particles_wall_s_total": move_s_timed, "host_wall_s": wall, "breakdown": breakdown, "ranks": per_rank,
                        "clamped_at_assign": ctx.out_of_domain_count(), "ghost_transport": ctx.ghost_transport(),
-                       "recorded_step": prof_note, "force_checksum_sum_abs": fsum, "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
+                       "recorded_step": prof_note, "force_checksum_sum_abs": fsum, "pair_operators_fused_into_eam_force_pass": ctx.chain_stats(), "eam_sublist": dict(zip(("inner_skin", "refiltered", "reused"), (W.inner_skin,) + tuple(ctx.eam_sublist_stats())))}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

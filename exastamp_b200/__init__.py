@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "xsb_particles_assign", "xsb_particles_rebin", "xsb_push_f_v_r", "xsb_push_f_v", "xsb_force_to_accel", "xsb_backup_r",
     "xsb_particle_displ_over", "xsb_verlet_boundary", "xsb_comm_unique_id", "xsb_comm_init", "xsb_comm_allreduce_max", "xsb_num_own_particles", "xsb_cell_offsets_download", "xsb_ghost_comm_scheme", "xsb_ghost_update", "xsb_ghost_reduce_add",
     "xsb_thermo_state", "xsb_ghost_plan", "xsb_migration_stats",
-    "xsb_verlet_boundary_async", "xsb_displ_poll", "xsb_ghost_transport", "xsb_eam_inner_skin", "xsb_eam_sublist_stats",
+    "xsb_verlet_boundary_async", "xsb_displ_poll", "xsb_ghost_transport", "xsb_eam_inner_skin", "xsb_eam_sublist_stats", "xsb_chain_stats",
     "xsb_fields_upload_async", "xsb_fields_download_async", "xsb_copy_wait", "xsb_out_of_domain_count",
     "xsb_step_capture_begin", "xsb_step_capture_end", "xsb_step_replay", "xsb_step_release",
 ]
@@ -159,6 +159,7 @@ def load_library():
     L.xsb_ghost_update.argtypes = [vp, C.c_uint32]
     L.xsb_eam_inner_skin.argtypes = [vp, dbl]
     L.xsb_eam_sublist_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.xsb_chain_stats.argtypes = [vp, C.POINTER(u64)]
     L.xsb_ghost_transport.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.xsb_verlet_boundary_async.argtypes = [vp, i32, vp, dbl]
     L.xsb_displ_poll.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
@@ -332,6 +333,12 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self.L.xsb_eam_sublist_stats(self.h, C.byref(a), C.byref(b)), "xsb_eam_sublist_stats")
         return a.value, b.value
+
+    def chain_stats(self):
+        """pair operators evaluated inside the force pass of the eam_alloy_force operator in front of them"""
+        a = C.c_uint64()
+        self._ck(self.L.xsb_chain_stats(self.h, C.byref(a)), "xsb_chain_stats")
+        return a.value
 
     def eam_alloy_force(self, rcut, phases=EAM_RHO | EAM_RHO2EMB | EAM_GHOST | EAM_FORCE, flags=0):
         self._ck(self.L.xsb_eam_alloy_force(self.h, float(rcut), int(phases), int(flags)), "xsb_eam_alloy_force")

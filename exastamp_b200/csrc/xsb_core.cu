@@ -299,6 +299,7 @@ int xsb_create(int device, xsb_ctx** out)
   ctx->tile_deal = getenv("XSB_TILE_DEAL") != nullptr;   // A/B switches for profiling, not a fallback: same kernels
   ctx->pair_cache_off = getenv("XSB_NO_PAIR_CACHE") != nullptr;
   ctx->pair_sub_off = getenv("XSB_PAIR_NO_SUBLIST") != nullptr;
+  ctx->chain_fusion = getenv("XSB_NO_CHAIN_FUSION") == nullptr;
   ctx->exp_tpa = getenv("XSB_TPA") ? atoi(getenv("XSB_TPA")) : 0;
   ctx->inner_skin = getenv("XSB_INNER_SKIN") ? std::max(0.0, atof(getenv("XSB_INNER_SKIN"))) : 0.0;
   ctx->subcell_bits = getenv("XSB_SUBCELL_SORT") ? std::min(3, std::max(0, atoi(getenv("XSB_SUBCELL_SORT")))) : 0;
@@ -334,7 +335,13 @@ void xsb_destroy(xsb_ctx* ctx)
 }
 
 const char* xsb_last_error(const xsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t xsb_kernel_launch_count(const xsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t xsb_kernel_launch_count(const xsb_ctx* ctx)
+{
+  if( !ctx ) return 0;
+  // a deferred EAM force phase (xsb_ctx::pending_eam) counts as launched by the call that requested it
+  if( ctx->pending_eam.active && ctx->stream && cudaSetDevice(ctx->device) == cudaSuccess ) xsb_internal_flush_pending(const_cast<xsb_ctx*>(ctx));
+  return ctx->launches;
+}
 
 int xsb_profile_enable(xsb_ctx* ctx, int on)
 {
@@ -726,6 +733,7 @@ int xsb_copy_wait(xsb_ctx* ctx)
 void* xsb_field_device_ptr(xsb_ctx* ctx, int field)
 {
   if( !ctx || !ctx->stream || cudaSetDevice(ctx->device) != cudaSuccess ) return nullptr;
+  if( ctx->pending_eam.active && xsb_internal_flush_pending(ctx) ) return nullptr;
   void* p = nullptr; size_t bytes = 0;
   if( field_ptr(ctx, field, &p, &bytes) ) return nullptr;
   if( field == XSB_F_RX || field == XSB_F_RY || field == XSB_F_RZ ) ctx->pos_external = true;   // caller may move particles behind our back

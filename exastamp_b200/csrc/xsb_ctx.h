@@ -154,6 +154,14 @@ struct xsb_ctx
   bool sub_covers(double rcut, bool need_ghost) const
   { return !pos_external && !pair_sub_off && sub_epoch == pos_epoch && rcut <= sub_rcut && (sub_ghost || !need_ghost); }
   bool pair_sub_off = false;                  // env XSB_PAIR_NO_SUBLIST=1 (A/B)
+  // Operator chain `compute_force: [eam_alloy_force, <pot>_multi_force]` (configs[4]): the force phase of eam_alloy_force is
+  // not launched by its own call but by the NEXT entry point on this context -- on its own (any entry: XSB_ENTER), or, when
+  // that entry is a pair operator with a cut-off <= the EAM one and the same flags, as ONE pass that evaluates both
+  // potentials on the pairs it visits (positions gathered once instead of twice).  Calls were asynchronous already, so the
+  // deferral is invisible; env XSB_NO_CHAIN_FUSION=1 launches at once (A/B).
+  struct PendingEamForce { bool active = false; double rcut = 0.0; int phases = 0, flags = 0; } pending_eam;
+  bool chain_fusion = true;
+  uint64_t fused_chains = 0;                  // how many pair operators went into an EAM force pass (xsb_chain_stats)
   xsb::DevBuf<unsigned char> scratch;         // cub temp storage etc.
   xsb::DevBuf<unsigned long long> scratch64;  // misc u64 scratch
 
@@ -233,12 +241,16 @@ struct xsb_ctx
   return (ctx)->fail(XSB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } while(0)
 // first statement of every extern "C" entry that touches the stream or allocates: one context per GPU, several contexts
 // (devices) may live in one process, so the calling thread's current device must follow the context
-#define XSB_ENTER(ctx) do { if( !(ctx) || !(ctx)->stream ) return XSB_ERR_STATE; XSB_CUDA(ctx, cudaSetDevice((ctx)->device)); } while(0)
+// XSB_ENTER also launches a deferred EAM force phase (xsb_ctx::pending_eam); the pair operators, which may absorb it, use
+// XSB_ENTER_KEEP and decide themselves
+#define XSB_ENTER_KEEP(ctx) do { if( !(ctx) || !(ctx)->stream ) return XSB_ERR_STATE; XSB_CUDA(ctx, cudaSetDevice((ctx)->device)); } while(0)
+#define XSB_ENTER(ctx) do { XSB_ENTER_KEEP(ctx); if( (ctx)->pending_eam.active ) { int rc__ = xsb_internal_flush_pending(ctx); if( rc__ ) return rc__; } } while(0)
 #define XSB_LAUNCH_CHECK(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if( e__ != cudaSuccess ) \
   return (ctx)->fail(XSB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } while(0)
 #define XSB_REQUIRE(ctx, cond, code, msg) do { if( !(cond) ) return (ctx)->fail(code, "%s", msg); } while(0)
 
 // internal helpers shared across translation units (C++ linkage, not exported by the header)
+int  xsb_internal_flush_pending(xsb_ctx* ctx);                       // xsb_eam.cu: launch the deferred EAM force phase on its own
 int  xsb_internal_ensure_virial(xsb_ctx* ctx);
 int  xsb_internal_install_cells(xsb_ctx* ctx, const uint64_t* cell_off);
 int  xsb_internal_relayout(xsb_ctx* ctx, const uint64_t* new_cell_off);

@@ -6,6 +6,7 @@
 //      operator eam_potential_multimat.cu:65-259, functors eam_force_op_multimat.h:107-343,
 //      tables + evaluation src/potential/eam_potentials/eam_alloy/eam_alloy.h:37-313, reader eam_alloy.cpp:66-278.
 #include "xsb_tilepass.cuh"
+#include "xsb_pairpot.cuh"
 #include <climits>
 #include <cmath>
 #include <fstream>
@@ -511,7 +512,30 @@ struct EamRhoTileOp
   }
 };
 
-template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_>
+// A pair operator chained behind the EAM operator (compute_force: [eam_alloy_force, lj_multi_force], xsb_ctx::pending_eam)
+// rides along in the force pass: CHAIN adds its table and one lj_eval per visited pair inside its own cut-off.
+struct NoChain {};
+template<bool MULTI, bool CHAIN, class real>
+__device__ __forceinline__ void chain_eval(const std::conditional_t<CHAIN, LJMulti, NoChain>& prm, unsigned ta, unsigned tb, double d2, double& fpair, double& e_half)
+{
+  if constexpr ( CHAIN )
+  {
+    const LJPair& pp = MULTI ? prm.pp[unique_pair_id(ta, tb)] : prm.pp[0];
+    if( d2 <= pp.rcut2 )
+    {
+      // lennard_jones.h:40-50 as in lj_eval (only Lennard-Jones operators are taken along: the other potentials' exp / sqrt
+      // branches do not fit the 64 registers of the 1024-thread passes)
+      const real rinv2 = real(1) / real(d2);
+      const real s2 = real(pp.k[2]) * rinv2;
+      const real s6 = s2 * s2 * s2;
+      const real s12 = s6 * s6;
+      fpair += double(-real(pp.k[1]) * (real(2) * s12 - s6) * rinv2);
+      e_half += 0.5 * double(real(pp.k[0]) * (s12 - s6) - real(pp.ecut));
+    }
+  }
+}
+
+template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_, bool CHAIN = false>
 struct EamForceTileOp
 {
   static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false, PW_IN = PWI_;
@@ -519,6 +543,7 @@ struct EamForceTileOp
   static constexpr int PW_N = MULTI ? 2 : 1;
   double rcut2; EamFcView T; int nel; double conv_z2r;
   double *fx, *fy, *fz, *ep, *vir;
+  std::conditional_t<CHAIN, LJMulti, NoChain> chain;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
   __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
   struct Acc { double fx, fy, fz, ep, fpi; int ta; Vir9 v; };
@@ -552,10 +577,12 @@ struct EamForceTileOp
     double phi = z2 * recip;
     const double phip = (z2p * recip - phi * recip) * conv_z2r;
     phi *= conv_z2r;
-    const double fpair = (A.fpi * rhojp + B.w[j] * rhoip + phip) * recip;
+    double fpair = (A.fpi * rhojp + B.w[j] * rhoip + phip) * recip;
+    double eh = 0.5 * phi;
+    chain_eval<MULTI, CHAIN, double>(chain, A.ta, tb, d2, fpair, eh);
     const double fex = dx * fpair, fey = dy * fpair, fez = dz * fpair;
     A.fx += fex; A.fy += fey; A.fz += fez;
-    if( EFLAG ) A.ep += 0.5 * phi;
+    if( EFLAG ) A.ep += eh;
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
   __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
@@ -642,13 +669,14 @@ struct EamRhoTileOp32
   }
 };
 
-template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_>
+template<bool MULTI, bool EFLAG, bool VIRIAL, bool PWI_, bool CHAIN = false>
 struct EamForceTileOp32
 {
   static constexpr bool HAS_W = true, TYPES = MULTI, D2_ONLY = false, PW_IN = PWI_;
   static constexpr int PW_N = MULTI ? 2 : 1;
   double rcut2; EamFcView32 T; int nel; float conv_z2r;
   double *fx, *fy, *fz, *ep, *vir;
+  std::conditional_t<CHAIN, LJMulti, NoChain> chain;
   __host__ __device__ size_t table_bytes() const { return T.table_bytes(); }
   __device__ __forceinline__ void load_tables(unsigned char* smem, int nt) const { T.load(smem, nt); }
   struct Acc { double fx, fy, fz, ep, fpi; int ta; Vir9 v; };
@@ -676,10 +704,12 @@ struct EamForceTileOp32
     float phi = z2 * recip;
     const float phip = (z2p * recip - phi * recip) * conv_z2r;
     phi *= conv_z2r;
-    const double fpair = double((float(A.fpi) * rhojp + float(B.w[j]) * rhoip + phip) * recip);
+    double fpair = double((float(A.fpi) * rhojp + float(B.w[j]) * rhoip + phip) * recip);
+    double eh = 0.5 * double(phi);
+    chain_eval<MULTI, CHAIN, float>(chain, A.ta, tb, d2, fpair, eh);
     const double fex = dx * fpair, fey = dy * fpair, fez = dz * fpair;
     A.fx += fex; A.fy += fey; A.fz += fez;
-    if( EFLAG ) A.ep += 0.5 * double(phi);
+    if( EFLAG ) A.ep += eh;
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
   __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<HAS_W, TYPES>& B, const unsigned char* tab) const
@@ -967,6 +997,79 @@ int xsb_eam_sublist_stats(xsb_ctx* ctx, uint64_t* refiltered, uint64_t* reused)
   return XSB_OK;
 }
 
+} // extern "C"
+
+// third phase of eam_alloy_force (eam_force_op_multimat.h:243-343), optionally with the pair operator chained behind it
+int xsb_internal_eam_force_phase(xsb_ctx* ctx, double rcut, int phases, int flags, const xsb::LJMulti* chain)
+{
+  const EamAlloyDev& E = ctx->eam;
+  EamAlloyView T{ E.frho.p, E.rtab.p, E.rtab.p + size_t(E.nelements) * (E.nr + 1) * 8, E.nr, E.nrho, E.rdr, E.rdrho, E.rhomax, E.conv_z2r, E.conv_frho };
+  const bool eflag = phases & XSB_EAM_EFLAG;
+  const bool virial = eflag && (flags & XSB_FLAG_VIRIAL);
+  const bool mixed = (flags & XSB_FLAG_MIXED) && ctx->tile_ok;
+  const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;
+  constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
+  ParticleView P{ ctx->f64[XSB_F_RX].p, ctx->f64[XSB_F_RY].p, ctx->f64[XSB_F_RZ].p, ctx->type.p, ctx->nbh_off.p, ctx->nbh_idx.p, nullptr, 0 };
+  double* emb = ctx->f64[XSB_F_RHO_DEMB].p;
+  const bool tile = ctx->tile_ok, multi = E.nelements > 1;
+  if( tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
+  {
+    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+    const int ntab = E.nelements + E.nelements * (E.nelements + 1) / 2;
+    int rc;
+    ctx->prof_begin(XSB_PROF_EAM_FORCE);
+    const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
+    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == ((multi ? 3 : 1) | (mixed ? 16 : 0)) && !(multi && ctx->type_external);
+    const int npair = E.nelements * (E.nelements + 1) / 2;
+    XSB_REQUIRE(ctx, pwi || !chain, XSB_ERR_STATE, "chained pair operator without the per-pair cache of the rho pass");
+#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { \
+      if( pwi && chain ) { EamForceTileOp<MU, EF, VIR, true, true> op{ rc2, make_fc_view<true, MU>(ctx, E.nelements, npair, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir, *chain }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, E.nelements, npair, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, 0, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
+#   define XSB_EAM_TILE32(MU, EF, VIR, TPA_, NT_) { \
+      if( pwi && chain ) { EamForceTileOp32<MU, EF, VIR, true, true> op{ rc2, make_fc_view32<true, MU>(ctx, E.nelements, npair, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir, *chain }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else if( pwi ) { EamForceTileOp32<MU, EF, VIR, true>  op{ rc2, make_fc_view32<true, MU>(ctx, E.nelements, npair, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
+      else      { EamForceTileOp32<MU, EF, VIR, false> op{ rc2, make_fc_view32<true, MU>(ctx, 0, ntab, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
+    if( mixed )
+    {
+      if( multi ) { if( virial ) XSB_EAM_TILE32(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(true, true, false, 16, 1024) else XSB_EAM_TILE32(true, false, false, 16, 1024) }
+      else        { if( virial ) XSB_EAM_TILE32(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(false, true, false, 16, 1024) else XSB_EAM_TILE32(false, false, false, 16, 1024) }
+    }
+    else
+    if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
+    else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else if( ctx->exp_tpa == 8 ) XSB_EAM_TILE(false, false, false, 8, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
+#   undef XSB_EAM_TILE32
+#   undef XSB_EAM_TILE
+    ctx->prof_end(XSB_PROF_EAM_FORCE);
+    if( rc ) return rc;
+  }
+  if( !tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
+  {
+    P.atoms = ctx->own_atoms.p; P.n_atoms = unsigned(ctx->n_own);
+    const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
+    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
+    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
+#   define XSB_EAM_GO(XF, EF, VIR) eam_alloy_force_kernel<TPA, XF, EF, VIR><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb, fx, fy, fz, ep, vir)
+    ctx->prof_begin(XSB_PROF_EAM_FORCE);
+    if( xf ) { if( virial ) XSB_EAM_GO(true, true, true); else if( eflag ) XSB_EAM_GO(true, true, false); else XSB_EAM_GO(true, false, false); }
+    else     { if( virial ) XSB_EAM_GO(false, true, true); else if( eflag ) XSB_EAM_GO(false, true, false); else XSB_EAM_GO(false, false, false); }
+    ctx->prof_end(XSB_PROF_EAM_FORCE);
+#   undef XSB_EAM_GO
+    XSB_LAUNCH_CHECK(ctx);
+  }
+  return XSB_OK;
+}
+
+int xsb_internal_flush_pending(xsb_ctx* ctx)
+{
+  const xsb_ctx::PendingEamForce pe = ctx->pending_eam;
+  ctx->pending_eam.active = false;
+  return xsb_internal_eam_force_phase(ctx, pe.rcut, pe.phases, pe.flags, nullptr);
+}
+
+extern "C" {
+
 int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
 {
   XSB_ENTER(ctx);
@@ -1057,48 +1160,12 @@ int xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags)
     ctx->prof_end(XSB_PROF_EAM_RHO2EMB);
     XSB_LAUNCH_CHECK(ctx);
   }
-  if( tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
+  if( (phases & XSB_EAM_FORCE) && ctx->n_own )
   {
-    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
-    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
-    const int ntab = E.nelements + E.nelements * (E.nelements + 1) / 2;
-    int rc;
-    ctx->prof_begin(XSB_PROF_EAM_FORCE);
-    const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
-    const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == ((multi ? 3 : 1) | (mixed ? 16 : 0)) && !(multi && ctx->type_external);
-    const int npair = E.nelements * (E.nelements + 1) / 2;
-#   define XSB_EAM_TILE(MU, EF, VIR, TPA_, NT_) { \
-      if( pwi ) { EamForceTileOp<MU, EF, VIR, true>  op{ rc2, make_fc_view<true, MU>(ctx, E.nelements, npair, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
-      else      { EamForceTileOp<MU, EF, VIR, false> op{ rc2, make_fc_view<true, MU>(ctx, 0, ntab, 0), E.nelements, E.conv_z2r, fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
-#   define XSB_EAM_TILE32(MU, EF, VIR, TPA_, NT_) { \
-      if( pwi ) { EamForceTileOp32<MU, EF, VIR, true>  op{ rc2, make_fc_view32<true, MU>(ctx, E.nelements, npair, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } \
-      else      { EamForceTileOp32<MU, EF, VIR, false> op{ rc2, make_fc_view32<true, MU>(ctx, 0, ntab, 0), E.nelements, float(E.conv_z2r), fx, fy, fz, ep, vir }; rc = launch_tile_pass<TPA_, NT_>(ctx, false, op, emb, lmode); } }
-    if( mixed )
-    {
-      if( multi ) { if( virial ) XSB_EAM_TILE32(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(true, true, false, 16, 1024) else XSB_EAM_TILE32(true, false, false, 16, 1024) }
-      else        { if( virial ) XSB_EAM_TILE32(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE32(false, true, false, 16, 1024) else XSB_EAM_TILE32(false, false, false, 16, 1024) }
-    }
-    else
-    if( multi ) { if( virial ) XSB_EAM_TILE(true, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(true, true, false, 16, 1024) else XSB_EAM_TILE(true, false, false, 16, 1024) }
-    else        { if( virial ) XSB_EAM_TILE(false, true, true, 8, 512) else if( eflag ) XSB_EAM_TILE(false, true, false, 16, 1024) else if( ctx->exp_tpa == 8 ) XSB_EAM_TILE(false, false, false, 8, 1024) else XSB_EAM_TILE(false, false, false, 16, 1024) }
-#   undef XSB_EAM_TILE32
-#   undef XSB_EAM_TILE
-    ctx->prof_end(XSB_PROF_EAM_FORCE);
-    if( rc ) return rc;
-  }
-  if( !tile && (phases & XSB_EAM_FORCE) && ctx->n_own )
-  {
-    P.atoms = ctx->own_atoms.p; P.n_atoms = unsigned(ctx->n_own);
-    const unsigned grid = groups_grid<TPA>(P.n_atoms, block);
-    double *fx = ctx->f64[XSB_F_FX].p, *fy = ctx->f64[XSB_F_FY].p, *fz = ctx->f64[XSB_F_FZ].p, *ep = ctx->f64[XSB_F_EP].p;
-    double* vir = virial ? ctx->f64[XSB_F_VIRIAL].p : nullptr;
-#   define XSB_EAM_GO(XF, EF, VIR) eam_alloy_force_kernel<TPA, XF, EF, VIR><<<grid, block, 0, ctx->stream>>>(P, X, T, rc2, emb, fx, fy, fz, ep, vir)
-    ctx->prof_begin(XSB_PROF_EAM_FORCE);
-    if( xf ) { if( virial ) XSB_EAM_GO(true, true, true); else if( eflag ) XSB_EAM_GO(true, true, false); else XSB_EAM_GO(true, false, false); }
-    else     { if( virial ) XSB_EAM_GO(false, true, true); else if( eflag ) XSB_EAM_GO(false, true, false); else XSB_EAM_GO(false, false, false); }
-    ctx->prof_end(XSB_PROF_EAM_FORCE);
-#   undef XSB_EAM_GO
-    XSB_LAUNCH_CHECK(ctx);
+    // the force phase waits for the next entry point: a pair operator chained behind this one joins its pass (xsb_ctx::pending_eam)
+    const bool pwi_now = tile && ctx->sub_valid(rcut, false) && ctx->sub_pw_kind == ((multi ? 3 : 1) | (mixed ? 16 : 0)) && !(multi && ctx->type_external);
+    if( ctx->chain_fusion && pwi_now ) { ctx->pending_eam.active = true; ctx->pending_eam.rcut = rcut; ctx->pending_eam.phases = phases; ctx->pending_eam.flags = flags; }
+    else return xsb_internal_eam_force_phase(ctx, rcut, phases, flags, nullptr);
   }
   return XSB_OK;
 }

@@ -164,6 +164,28 @@ static LJPair make_pair(int pot, const double* prm, double rcut)
   return p;
 }
 
+// A deferred EAM force phase (xsb_ctx::pending_eam) takes this operator along when its pairs are a subset of the ones that
+// pass visits and both accumulate the same fields; otherwise the EAM phase is launched first and the operator runs on its own.
+template<bool MULTI>
+static int join_pending_eam(xsb_ctx* ctx, const LJMulti& prm, int n_types, double rcut_max, int flags, bool* absorbed)
+{
+  *absorbed = false;
+  if( !ctx->pending_eam.active ) return XSB_OK;
+  const xsb_ctx::PendingEamForce pe = ctx->pending_eam;
+  const bool eflag = pe.phases & XSB_EAM_EFLAG, virial = eflag && (pe.flags & XSB_FLAG_VIRIAL);
+  const bool fits = prm.pp[0].pot == XSB_POT_LJ && !(flags & XSB_FLAG_GHOST) && bool(flags & XSB_FLAG_ENERGY) == eflag && bool(flags & XSB_FLAG_VIRIAL) == virial &&
+                    bool(flags & XSB_FLAG_MIXED) == bool(pe.flags & XSB_FLAG_MIXED) && rcut_max <= pe.rcut &&
+                    !(MULTI && n_types > 1 && ctx->eam.nelements < 2);      // a single-element pass stages no type bytes
+  if( !fits ) return xsb_internal_flush_pending(ctx);
+  ctx->pending_eam.active = false;
+  LJMulti all = prm;
+  if( !MULTI ) for(int i = 1; i < 16; i++) all.pp[i] = prm.pp[0];          // one parameter set for every type pair
+  const int rc = xsb_internal_eam_force_phase(ctx, pe.rcut, pe.phases, pe.flags, &all);
+  if( rc ) return rc;
+  ctx->fused_chains++; *absorbed = true;
+  return XSB_OK;
+}
+
 template<bool MULTI>
 static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int flags)
 {
@@ -211,22 +233,6 @@ static int launch_pair(xsb_ctx* ctx, const LJMulti& prm, double rcut_max, int fl
   return XSB_OK;
 }
 
-int xsb_internal_pair_table(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, LJMulti* out, double* rmax)
-{
-  XSB_REQUIRE(ctx, pair_nparams(pot) >= 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham, yukawa, relax, zero)");
-  XSB_REQUIRE(ctx, pair_params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "rows of {params..., rcut} expected");
-  const int npairs = n_types * (n_types + 1) / 2;
-  XSB_REQUIRE(ctx, n_types >= 1 && npairs <= 16, XSB_ERR_INVALID, "too many type pairs (MAX_TYPE_PAIR_IDS = 16)");
-  *rmax = 0.0;
-  for(int i = 0; i < npairs; i++)
-  {
-    const double* row = pair_params + size_t(nparams + 1) * i;
-    out->pp[i] = make_pair(pot, row, row[nparams]);
-    if( row[nparams] > *rmax ) *rmax = row[nparams];
-  }
-  return XSB_OK;
-}
-
 } // namespace xsb
 
 using namespace xsb;
@@ -235,18 +241,20 @@ extern "C" {
 
 int xsb_pair_force(xsb_ctx* ctx, int pot, const double* params, int nparams, double rcut, int flags)
 {
-  XSB_ENTER(ctx);
+  XSB_ENTER_KEEP(ctx);
   XSB_REQUIRE(ctx, pair_nparams(pot) >= 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham, yukawa, relax, zero)");
   XSB_REQUIRE(ctx, (params != nullptr || pair_nparams(pot) == 0) && nparams == pair_nparams(pot), XSB_ERR_INVALID,
               "wrong parameter count: lj {epsilon, sigma}, zbl {r1, rc, z_a, z_b}, exp6 {A, B, C, D}, buckingham {A, Rho, C}, yukawa {A, kappa}, relax {r1, rc}, zero {}");
   XSB_REQUIRE(ctx, rcut > 0.0, XSB_ERR_INVALID, "rcut must be > 0");
   LJMulti prm; prm.pp[0] = make_pair(pot, params, rcut);
+  bool absorbed; const int jrc = join_pending_eam<false>(ctx, prm, 1, rcut, flags, &absorbed);
+  if( jrc || absorbed ) return jrc;
   return launch_pair<false>(ctx, prm, rcut, flags);
 }
 
 int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, double rcut_max, int flags)
 {
-  XSB_ENTER(ctx);
+  XSB_ENTER_KEEP(ctx);
   XSB_REQUIRE(ctx, pair_nparams(pot) >= 0, XSB_ERR_UNSUPPORTED, "pair potential not implemented (lj, zbl, exp6, buckingham, yukawa, relax, zero)");
   XSB_REQUIRE(ctx, pair_params != nullptr && nparams == pair_nparams(pot), XSB_ERR_INVALID, "rows of {params..., rcut} expected");
   const int npairs = n_types * (n_types + 1) / 2;
@@ -259,7 +267,17 @@ int xsb_pair_multi_force(xsb_ctx* ctx, int pot, int n_types, const double* pair_
     if( row[nparams] > rmax ) rmax = row[nparams];
   }
   XSB_REQUIRE(ctx, rcut_max >= rmax, XSB_ERR_INVALID, "rcut_max is smaller than a pair rcut");
+  bool absorbed; const int jrc = join_pending_eam<true>(ctx, prm, n_types, rcut_max, flags, &absorbed);
+  if( jrc || absorbed ) return jrc;
   return launch_pair<true>(ctx, prm, rcut_max, flags);
+}
+
+// how many pair operators were evaluated inside the force pass of the eam_alloy_force operator in front of them
+int xsb_chain_stats(xsb_ctx* ctx, uint64_t* fused_pair_operators)
+{
+  XSB_ENTER(ctx);
+  if( fused_pair_operators ) *fused_pair_operators = ctx->fused_chains;
+  return XSB_OK;
 }
 
 } // extern "C"

@@ -1,6 +1,6 @@
 // xsb_pairpot.cuh -- per type-pair coefficient records and the evaluation of the pair potentials behind <pot>_compute_force /
 // <pot>_multi_force (xsb_pair.cu); shared with xsb_eam.cu, whose force pass can evaluate a chained pair operator on the pairs it
-// visits anyway (xsb_eam_alloy_force_with_pair).
+// visits anyway (xsb_ctx::pending_eam).
 #pragma once
 #include "xsb_ctx.h"
 
@@ -101,7 +101,7 @@ __host__ __device__ __forceinline__ void lj_eval(const LJPair& p, real d2, real&
   de_r = de * rinv;
 }
 
-// host (xsb_pair.cu): the table of a <pot>_multi_force call from its rows {params..., rcut}; rmax = largest pair rcut
-int xsb_internal_pair_table(xsb_ctx* ctx, int pot, int n_types, const double* pair_params, int nparams, LJMulti* out, double* rmax);
-
 } // namespace xsb
+
+// xsb_eam.cu: the force phase of eam_alloy_force with `chain` (nullable) evaluated on the same pairs
+int xsb_internal_eam_force_phase(xsb_ctx* ctx, double rcut, int phases, int flags, const xsb::LJMulti* chain);

@@ -230,6 +230,15 @@ int  xsb_eam_alloy_force(xsb_ctx* ctx, double rcut, int phases, int flags);
 /* other way of moving particles (uploads, xsb_push_f_v_r, re-binning, a new xform) makes the next rho phase re-filter.   */
 /* Results are those of the plain path (same pairs, same arithmetic per pair; summation order differs).                   */
 int  xsb_eam_inner_skin(xsb_ctx* ctx, double skin);
+/* Operator chains `compute_force: [eam_alloy_force, lj_multi_force]` (data/regression decks of configs[4]; onika runs the    */
+/* operators of a batch one after the other, eam_potential_multimat.cu:196-230 then pair_potential_impl.hxx:476-484): the      */
+/* force phase of xsb_eam_alloy_force is enqueued by the NEXT entry point called on the context.  When that entry is           */
+/* xsb_pair_force / xsb_pair_multi_force with a Lennard-Jones potential, a cut-off <= the EAM one, no ghost flag and the same  */
+/* energy / virial / mixed flags, both potentials are evaluated in ONE pass over the in-range pairs (same pairs, the pair      */
+/* force is added to the EAM pair force before the multiplication with dr); in every other case the EAM phase is enqueued      */
+/* first and the next operator runs as usual.  Every entry point (xsb_sync and xsb_field_device_ptr included) does this,       */
+/* so the deferral cannot be observed.  XSB_NO_CHAIN_FUSION=1 (environment, read by xsb_create) turns it off.                  */
+int  xsb_chain_stats(xsb_ctx* ctx, uint64_t* fused_pair_operators);
 int  xsb_eam_sublist_stats(xsb_ctx* ctx, uint64_t* refiltered, uint64_t* reused);
 
 /* ---------------------------------------------------------------------------------------------------- */

@@ -34,7 +34,7 @@ def test_bricks_are_whole_cells_of_one_size(wl, n):
         assert gcells[ax] == ncb3[ax] * rd[ax]                                 # the bricks tile the global grid
     per_cell = 2 if W.structure == "BCC" else 4
     atoms = per_cell * uc[0] * uc[1] * uc[2] * n
-    want = {"c1": 131072 * n, "c2": 1972156 * n, "c3": 500094 * n, "c4": 16384000, "c5": 8001504 * n}[wl]
+    want = {"c1": 131072 * n, "c2": 1972156 * n, "c2j": 1972156 * n, "c3": 500094 * n, "c4": 16384000, "c5": 8001504 * n}[wl]
     assert atoms == want
     assert str(atoms) in bench.workload_config(W, a, n)["workload"]
 

@@ -1077,7 +1077,7 @@ def test_recorded_step_replays_the_direct_calls_bit_for_bit(tmp_path):
     masses, dt = [39.948], 2.0e-3
     POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
     path = write_setfl(str(tmp_path / "g.eam.alloy"), [SC_CU], nrho=2000, drho=0.05, nr=2000, rc=6.0)
-    for kind in ("lj", "eam"):
+    for kind in ("lj", "eam", "chain"):         # chain: an LJ operator behind the EAM one joins its (deferred) force pass
         a = assigned_ctx(pos, typ, box, 10.0, 1, vel); b = assigned_ctx(pos, typ, box, 10.0, 1, vel)
 
         def forces(c):
@@ -1087,9 +1087,11 @@ def test_recorded_step_replays_the_direct_calls_bit_for_bit(tmp_path):
             else:
                 c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | xsb.EAM_GHOST | xsb.EAM_EFLAG, 0)
                 c.eam_alloy_force(6.0, xsb.EAM_FORCE | xsb.EAM_EFLAG, 0)
+                if kind == "chain":
+                    c.pair_force([0.0104 * EV, 3.4], 5.5, xsb.FLAG_ENERGY)
 
         for c in (a, b):
-            if kind == "eam":
+            if kind != "lj":
                 c.eam_alloy_load(path)
             c.chunk_neighbors(9.0); c.backup_r(); forces(c)
         l0 = b.launches
@@ -1199,3 +1201,86 @@ def test_pair_operator_behind_eam_walks_the_sublist(tmp_path, monkeypatch):
         for c in ctxs:
             c.verlet_boundary_async([63.5, 27.0], 1.0e-3); c.ghost_update(POS)
     assert ctxs[0].eam_sublist_stats()[1] >= 1                         # a re-evaluated (not re-filtered) sub-list was walked too
+
+
+@pytest.mark.parametrize("two_species,eflag,virial,mixed,triclinic", [(True, False, False, False, True), (True, True, False, False, False),
+                                                                     (True, True, True, False, True), (False, True, False, False, False),
+                                                                     (True, True, True, True, False), (False, False, False, True, True)])
+def test_lj_operator_chained_behind_eam_joins_its_force_pass(tmp_path, monkeypatch, two_species, eflag, virial, mixed, triclinic):
+    """compute_force: [eam_alloy_force, lj_multi_force] (configs[4]): the EAM force phase waits for the next entry point and
+    takes a Lennard-Jones operator along (one pass over the in-range pairs).  Same forces / energies / virial as with
+    XSB_NO_CHAIN_FUSION=1 (two passes) over several steps incl. re-evaluated sub-lists; anything that is not such an operator
+    (another potential, a larger cut-off, a ghost flag, different flags, any other entry point) is served unfused"""
+    els = [SC_CU, SC_XX] if two_species else [SC_CU]
+    path = write_setfl(str(tmp_path / "ab.eam.alloy"), els, nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    rng = np.random.default_rng(15)
+    pos, typ, box = lattice("FCC", 6, 3.615, 0.06, seed=19)
+    if two_species:
+        typ = (rng.random(len(pos)) < 0.5).astype(np.uint8)
+    vel = rng.normal(0.0, 3.0, pos.shape)
+    rows = np.array([[0.0104 * EV, 2.3, 5.6], [0.0150 * EV, 2.2, 5.0], [0.0200 * EV, 2.1, 4.4]])
+    masses = [63.5, 27.0] if two_species else [63.5]
+    POS = [xsb.F_RX, xsb.F_RY, xsb.F_RZ]
+    X = np.array([[1.015, 0.02, -0.01], [0.0, 0.99, 0.015], [0.0, 0.0, 1.005]]) if triclinic else None
+    ef = xsb.EAM_EFLAG if eflag else 0
+    fl = (xsb.FLAG_VIRIAL if virial else 0) | (xsb.FLAG_MIXED if mixed else 0)
+    pfl = fl | (xsb.FLAG_ENERGY if eflag else 0)
+    ctxs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("XSB_NO_CHAIN_FUSION", "1")
+        c = assigned_ctx(pos, typ, box, 3.615 * 2, 1, vel)
+        if X is not None:
+            c.grid_set_xform(X)
+        c.eam_alloy_load(path); c.eam_inner_skin(0.2); c.chunk_neighbors(7.0); c.backup_r()
+        ctxs.append(c)
+    monkeypatch.delenv("XSB_NO_CHAIN_FUSION")
+
+    def lj(c):
+        if two_species:
+            c.pair_multi_force(2, rows, 5.6, pfl)
+        else:
+            c.pair_force([0.0104 * EV, 2.3], 5.6, pfl)
+
+    fields = [xsb.F_FX, xsb.F_FY, xsb.F_FZ] + ([xsb.F_EP] if eflag else []) + ([xsb.F_VIRIAL] if virial else [])
+    tol = 2e-6 if mixed else 1e-12
+    for step in range(3):
+        outs = []
+        for c in ctxs:
+            c.zero_force_energy()
+            c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | ef, fl)
+            c.ghost_update([xsb.F_RHO_DEMB])
+            c.eam_alloy_force(6.0, xsb.EAM_FORCE | ef, fl)
+            lj(c)
+            outs.append([c.download(f) for f in fields])
+        for a, b in zip(*outs):
+            assert rel_err(a, b) < tol, step
+        for c in ctxs:
+            c.verlet_boundary_async(masses, 1.0e-3); c.ghost_update(POS)
+    assert ctxs[0].chain_stats() == 3 and ctxs[1].chain_stats() == 0
+    assert ctxs[0].eam_sublist_stats()[1] >= 1
+    # not absorbed: the results must still be those of the unfused context
+    a, b = ctxs
+    cases = [lambda c: c.pair_force([3.0e-3 * EV, 2.0, 1.0e-4 * EV], 5.0, pfl, pot=xsb.POT_BUCKINGHAM),
+             lambda c: (c.pair_multi_force(2, rows + np.array([0, 0, 1.0]), 6.6, pfl) if two_species else c.pair_force([0.0104 * EV, 2.3], 6.6, pfl)),
+             lambda c: (c.pair_multi_force(2, rows, 5.6, pfl ^ xsb.FLAG_VIRIAL) if eflag else c.pair_force([0.0104 * EV, 2.3], 5.6, pfl | xsb.FLAG_ENERGY))]
+    n0 = a.chain_stats()
+    for case in cases:
+        outs = []
+        for c in (a, b):
+            c.zero_force_energy()
+            c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | ef, fl)
+            c.ghost_update([xsb.F_RHO_DEMB])
+            c.eam_alloy_force(6.0, xsb.EAM_FORCE | ef, fl)
+            case(c)
+            outs.append([c.download(f) for f in fields])
+        for u, v in zip(*outs):
+            assert rel_err(u, v) < tol
+    assert a.chain_stats() == n0
+    # the deferred phase alone: any other entry point launches it
+    for c in (a, b):
+        c.zero_force_energy()
+        c.eam_alloy_force(6.0, xsb.EAM_RHO | xsb.EAM_RHO2EMB | ef, fl)
+        c.ghost_update([xsb.F_RHO_DEMB])
+        c.eam_alloy_force(6.0, xsb.EAM_FORCE | ef, fl)
+    assert rel_err(a.download(xsb.F_FX), b.download(xsb.F_FX)) < tol
