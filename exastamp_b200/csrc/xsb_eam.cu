@@ -22,40 +22,54 @@ namespace xsb
 // The same struct carries the parameters of the other analytic single-species models of eam_potential_template in its first
 // slots (reference struct order): model 1 sutton_chen {c, epsilon, a0, n, m}, model 2 vniitf {rmax, rmin, rt0, Ecoh, E0, beta, A,
 // Z, n, alpha, D, eta, mu}; the operators only differ in the three functions rho(r), phi(r), F(rho).
-struct JohnsonP
+template<class real>
+struct JohnsonPT
 {
-  double re, fe, rhoe, alpha, beta, A, B, kappa, lambda, Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, Fo, eta;
+  real re, fe, rhoe, alpha, beta, A, B, kappa, lambda, Fn0, Fn1, Fn2, Fn3, F0, F1, F2, F3, Fo, eta;
   int model, pad_;
-  __host__ __device__ __forceinline__ double v(int i) const { return (&re)[i]; }
+  __host__ __device__ __forceinline__ real v(int i) const { return (&re)[i]; }
 };
+typedef JohnsonPT<double> JohnsonP;
+// XSB_FLAG_MIXED: the pair functions rho(r), phi(r) in FP32 (parameters rounded once on the host); F(rho), distances and sums FP64
+static JohnsonPT<float> johnson_f32(const JohnsonP& p)
+{
+  JohnsonPT<float> q; for(int i = 0; i < 19; i++) (&q.re)[i] = float(p.v(i));
+  q.model = p.model; q.pad_ = 0; return q;
+}
+__device__ __forceinline__ float  xpow(float x, float y)   { return powf(x, y); }
+__device__ __forceinline__ double xpow(double x, double y) { return pow(x, y); }
 
 // c^20 and c^19 by squaring (johnson.h uses pow(c2,20) and 20*c3/c2)
-__device__ __forceinline__ void pow20_19(double c, double& c20, double& c19)
+template<class real>
+__device__ __forceinline__ void pow20_19(real c, real& c20, real& c19)
 {
-  const double c2 = c * c, c4 = c2 * c2, c8 = c4 * c4, c16 = c8 * c8;
+  const real c2 = c * c, c4 = c2 * c2, c8 = c4 * c4, c16 = c8 * c8;
   c20 = c16 * c4; c19 = c16 * c2 * c;
 }
 
 // one term  s*exp(-k(x-1)) / (1+(x-l)^20)  and its derivative wrt r (ire = 1/re)
-__device__ __forceinline__ void johnson_term(double s, double k, double l, double x, double ire, double& f, double& df)
+template<class real>
+__device__ __forceinline__ void johnson_term(real s, real k, real l, real x, real ire, real& f, real& df)
 {
-  const double num = s * exp(-k * (x - 1.0));
-  double c20, c19; pow20_19(x - l, c20, c19);
-  const double den = 1.0 + c20, iden = 1.0 / den;
+  const real num = s * xexp(-k * (x - real(1.0)));
+  real c20, c19; pow20_19(x - l, c20, c19);
+  const real den = real(1.0) + c20, iden = real(1.0) / den;
   f = num * iden;
-  df = ire * ((-k * num) * den - num * (20.0 * c19)) * iden * iden;
+  df = ire * ((-k * num) * den - num * (real(20.0) * c19)) * iden * iden;
 }
 
-__device__ __forceinline__ void johnson_rho(const JohnsonP& p, double r, double& rho, double& drho)
+template<class real>
+__device__ __forceinline__ void johnson_rho(const JohnsonPT<real>& p, real r, real& rho, real& drho)
 {
-  const double ire = 1.0 / p.re;
+  const real ire = real(1.0) / p.re;
   johnson_term(p.fe, p.beta, p.lambda, r * ire, ire, rho, drho);
 }
 
-__device__ __forceinline__ void johnson_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+template<class real>
+__device__ __forceinline__ void johnson_phi(const JohnsonPT<real>& p, real r, real& phi, real& dphi)
 {
-  const double ire = 1.0 / p.re, x = r * ire;
-  double f1, d1, f2, d2;
+  const real ire = real(1.0) / p.re, x = r * ire;
+  real f1, d1, f2, d2;
   johnson_term(p.A, p.alpha, p.kappa, x, ire, f1, d1);
   johnson_term(-p.B, p.beta, p.lambda, x, ire, f2, d2);
   phi = f1 + f2; dphi = d1 + d2;
@@ -86,14 +100,16 @@ __device__ __forceinline__ void johnson_fEmbed(const JohnsonP& p, double rho, do
 }
 
 // sutton_chen.h:33-62
-__device__ __forceinline__ void sutton_chen_rho(const JohnsonP& p, double r, double& rho, double& drho)
+template<class real>
+__device__ __forceinline__ void sutton_chen_rho(const JohnsonPT<real>& p, real r, real& rho, real& drho)
 {
-  rho = pow(p.v(2) / r, p.v(4));
+  rho = xpow(p.v(2) / r, p.v(4));
   drho = -1 * p.v(4) * rho / r;
 }
-__device__ __forceinline__ void sutton_chen_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+template<class real>
+__device__ __forceinline__ void sutton_chen_phi(const JohnsonPT<real>& p, real r, real& phi, real& dphi)
 {
-  phi = p.v(1) * pow(p.v(2) / r, p.v(3));
+  phi = p.v(1) * xpow(p.v(2) / r, p.v(3));
   dphi = -1 * p.v(3) * phi / r;
 }
 __device__ __forceinline__ void sutton_chen_fEmbed(const JohnsonP& p, double rho, double& f, double& df)
@@ -103,31 +119,34 @@ __device__ __forceinline__ void sutton_chen_fEmbed(const JohnsonP& p, double rho
 }
 
 // vniitf.h:48-125 ; v(0..12) = rmax rmin rt0 Ecoh E0 beta A Z n alpha D eta mu
-__device__ __forceinline__ void vniitf_switch(const JohnsonP& p, double r, double& S, double& dS)
+template<class real>
+__device__ __forceinline__ void vniitf_switch(const JohnsonPT<real>& p, real r, real& S, real& dS)
 {
-  const double x = (p.v(0) - r) / (p.v(0) - p.v(1));
-  const double x2 = x * x, x3 = x2 * x;
+  const real x = (p.v(0) - r) / (p.v(0) - p.v(1));
+  const real x2 = x * x, x3 = x2 * x;
   S = x2 * x2 * ( -20 * x2 * x + 70 * x2 - 84 * x + 35 );
   dS = (140 * x3 * ( -1 * x3 + 3 * x2 - 3 * x + 1 )) / (p.v(1) - p.v(0));
-  if( x < 0 ) { S = 0.; dS = 0.; }
-  else if( x > 1 ) { S = 1.; dS = 0.; }
+  if( x < 0 ) { S = real(0.); dS = real(0.); }
+  else if( x > 1 ) { S = real(1.); dS = real(0.); }
 }
-__device__ __forceinline__ void vniitf_rho(const JohnsonP& p, double r, double& rho, double& drho)
+template<class real>
+__device__ __forceinline__ void vniitf_rho(const JohnsonPT<real>& p, real r, real& rho, real& drho)
 {
-  const double irt0 = 1 / p.v(2);
-  const double F = exp(-p.v(5) * (r * irt0 - 1.0)) / p.v(7), dF = -p.v(5) * F * irt0;
-  double S, dS; vniitf_switch(p, r, S, dS);
+  const real irt0 = 1 / p.v(2);
+  const real F = xexp(-p.v(5) * (r * irt0 - real(1.0))) / p.v(7), dF = -p.v(5) * F * irt0;
+  real S, dS; vniitf_switch(p, r, S, dS);
   rho = F * S; drho = F * dS + S * dF;
 }
-__device__ __forceinline__ void vniitf_phi(const JohnsonP& p, double r, double& phi, double& dphi)
+template<class real>
+__device__ __forceinline__ void vniitf_phi(const JohnsonPT<real>& p, real r, real& phi, real& dphi)
 {
-  const double ir = 1 / r, irt0 = 1 / p.v(2), dr = r * irt0 - 1.0, dr2 = dr * dr;
-  const double alpha = p.v(9), eta = p.v(11), mu = p.v(12);
-  const double a = -2 * p.v(3) / p.v(7), b = alpha * alpha * alpha * p.v(10) * p.v(2);
-  const double f1  = a * ( 1 + alpha * dr + eta * dr2 + (mu + b * ir) * dr2 * dr );
-  const double df1 = a * ( alpha * irt0 + 2 * eta * irt0 * dr + 3 * mu * irt0 * dr2 + b * (3 * irt0 - dr * ir) * dr2 * ir );
-  const double f2 = exp(-alpha * dr), df2 = -alpha * irt0 * f2;
-  double S, dS; vniitf_switch(p, r, S, dS);
+  const real ir = 1 / r, irt0 = 1 / p.v(2), dr = r * irt0 - real(1.0), dr2 = dr * dr;
+  const real alpha = p.v(9), eta = p.v(11), mu = p.v(12);
+  const real a = -2 * p.v(3) / p.v(7), b = alpha * alpha * alpha * p.v(10) * p.v(2);
+  const real f1  = a * ( 1 + alpha * dr + eta * dr2 + (mu + b * ir) * dr2 * dr );
+  const real df1 = a * ( alpha * irt0 + 2 * eta * irt0 * dr + 3 * mu * irt0 * dr2 + b * (3 * irt0 - dr * ir) * dr2 * ir );
+  const real f2 = xexp(-alpha * dr), df2 = -alpha * irt0 * f2;
+  real S, dS; vniitf_switch(p, r, S, dS);
   phi = (p.v(4) + f1 * f2) * S;
   dphi = (p.v(4) + f1 * f2) * dS + (f1 * df2 + f2 * df1) * S;
 }
@@ -140,9 +159,11 @@ __device__ __forceinline__ void vniitf_fEmbed(const JohnsonP& p, double rho, dou
 }
 
 // the model switch is uniform over the launch
-__device__ __forceinline__ void eam1_rho(const JohnsonP& p, double r, double& f, double& df)
+template<class real>
+__device__ __forceinline__ void eam1_rho(const JohnsonPT<real>& p, real r, real& f, real& df)
 { if( p.model == 0 ) johnson_rho(p, r, f, df); else if( p.model == 1 ) sutton_chen_rho(p, r, f, df); else vniitf_rho(p, r, f, df); }
-__device__ __forceinline__ void eam1_phi(const JohnsonP& p, double r, double& f, double& df)
+template<class real>
+__device__ __forceinline__ void eam1_phi(const JohnsonPT<real>& p, real r, real& f, real& df)
 { if( p.model == 0 ) johnson_phi(p, r, f, df); else if( p.model == 1 ) sutton_chen_phi(p, r, f, df); else vniitf_phi(p, r, f, df); }
 __device__ __forceinline__ void eam1_fEmbed(const JohnsonP& p, double x, double& f, double& df)
 { if( p.model == 0 ) johnson_fEmbed(p, x, f, df); else if( p.model == 1 ) sutton_chen_fEmbed(p, x, f, df); else vniitf_fEmbed(p, x, f, df); }
@@ -235,11 +256,11 @@ __global__ void __launch_bounds__(256) johnson_force_kernel(ParticleView P, XFor
 }
 
 // ---- the same two passes as functors for the persistent tile kernel (xsb_tilepass.cuh) ----------------------------
-template<bool PWO_>
+template<bool PWO_, class real = double>
 struct JohnsonEmbTileOp
 {
   static constexpr bool HAS_W = false, TYPES = false, D2_ONLY = true, PW_OUT = PWO_;
-  double rcut2; JohnsonP p; double *ep, *rho_dEmb;
+  double rcut2; JohnsonP p; double *ep, *rho_dEmb; JohnsonPT<real> q;      // q: the pair functions' copy of p in `real`
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
   struct Acc { double rho; unsigned cnt; };
@@ -248,9 +269,9 @@ struct JohnsonEmbTileOp
   // returns rho'(r): kept per pair for the force pass of the step (PW_OUT), which then skips one exp + one power
   __device__ __forceinline__ double pair_d2(Acc& A, double d2, unsigned, const StageBuf<false, false>&, const unsigned char*) const
   {
-    double rho, drho; eam1_rho(p, sqrt(d2), rho, drho);
-    A.rho += rho; ++A.cnt;
-    return drho;
+    real rho, drho; eam1_rho<real>(q, xsqrt(real(d2)), rho, drho);
+    A.rho += double(rho); ++A.cnt;
+    return double(drho);
   }
   __device__ __forceinline__ void pair(Acc& A, double, double, double, double d2, unsigned j, const StageBuf<false, false>& B, const unsigned char* t) const { pair_d2(A, d2, j, B, t); }
   template<int TPA> __device__ __forceinline__ void finish(Acc& A, unsigned a, bool valid, unsigned sub) const
@@ -262,11 +283,11 @@ struct JohnsonEmbTileOp
   }
 };
 
-template<bool VIRIAL, bool PWI_>
+template<bool VIRIAL, bool PWI_, class real = double>
 struct JohnsonForceTileOp
 {
   static constexpr bool HAS_W = true, TYPES = false, D2_ONLY = false, PW_IN = PWI_;
-  double rcut2; JohnsonP p; double *fx, *fy, *fz, *ep, *vir;
+  double rcut2; JohnsonPT<real> p; double *fx, *fy, *fz, *ep, *vir;
   __host__ __device__ size_t table_bytes() const { return 0; }
   __device__ __forceinline__ void load_tables(unsigned char*, int) const {}
   struct Acc { double fx, fy, fz, ep, fpi; Vir9 v; };
@@ -275,13 +296,13 @@ struct JohnsonForceTileOp
   template<bool HAVE>
   __device__ __forceinline__ void eval(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, double drho_in) const
   {
-    const double r = sqrt(d2);
-    double rho, drho = drho_in, phi, dphi;
-    if( !HAVE ) eam1_rho(p, r, rho, drho);
-    eam1_phi(p, r, phi, dphi);
-    const double de = (drho * (A.fpi + B.w[j]) + dphi) / r;
+    const real r = xsqrt(real(d2));
+    real rho, drho = real(drho_in), phi, dphi;
+    if( !HAVE ) eam1_rho<real>(p, r, rho, drho);
+    eam1_phi<real>(p, r, phi, dphi);
+    const double de = double((drho * (real(A.fpi) + real(B.w[j])) + dphi) / r);
     const double fex = de * dx, fey = de * dy, fez = de * dz;
-    A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * phi;
+    A.fx += fex; A.fy += fey; A.fz += fez; A.ep += 0.5 * double(phi);
     if( VIRIAL ) A.v.add(fex, fey, fez, dx, dy, dz);
   }
   __device__ __forceinline__ void pair(Acc& A, double dx, double dy, double dz, double d2, unsigned j, const StageBuf<true, false>& B, const unsigned char*) const
@@ -816,6 +837,8 @@ int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int np
   std::memcpy(params19, params, size_t(want) * sizeof(double)); params19[19] = double(model);
   JohnsonP p; std::memcpy(&p, params19, 19 * sizeof(double)); p.model = model; p.pad_ = 0;
   const bool virial = flags & XSB_FLAG_VIRIAL;
+  const bool mixed = (flags & XSB_FLAG_MIXED) && ctx->tile_ok;       // FP32 rho(r), phi(r) on the tile path (tolerance 1e-5)
+  const int pw_kind = mixed ? (2 | 16) : 2;                          // a cached rho'(r) computed in FP32 serves FP32 force passes only
   if( virial ) { int rc = xsb_internal_ensure_virial(ctx); if( rc ) return rc; }
   const XForm X = make_xform(ctx->grid); const bool xf = !ctx->grid.xform_is_identity;
   constexpr int TPA = 8; const int block = 256; const double rc2 = rcut * rcut;
@@ -830,12 +853,13 @@ int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int np
       ctx->sub_pw_kind = 0;
       ctx->prof_begin(XSB_PROF_EAM_RHO);
       int rc;
-      if( pwo ) { JohnsonEmbTileOp<true>  op{ rc2, p, ctx->f64[XSB_F_EP].p, emb }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
-      else      { JohnsonEmbTileOp<false> op{ rc2, p, ctx->f64[XSB_F_EP].p, emb }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
+      if( mixed )    { JohnsonEmbTileOp<true, float> op{ rc2, p, ctx->f64[XSB_F_EP].p, emb, johnson_f32(p) }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
+      else if( pwo ) { JohnsonEmbTileOp<true>  op{ rc2, p, ctx->f64[XSB_F_EP].p, emb, p }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
+      else           { JohnsonEmbTileOp<false> op{ rc2, p, ctx->f64[XSB_F_EP].p, emb, p }; rc = launch_tile_pass<32, 1024>(ctx, (phases & 2) != 0, op, nullptr, LIST_FULL_WRITE_SUB); }
       ctx->prof_end(XSB_PROF_EAM_RHO);
       if( rc ) return rc;
       ctx->sub_epoch = ctx->pos_epoch; ctx->sub_rcut = rcut; ctx->sub_ghost = (phases & 2) != 0;
-      if( pwo ) { ctx->sub_pw_kind = 2; std::memcpy(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)); }
+      if( pwo || mixed ) { ctx->sub_pw_kind = pw_kind; std::memcpy(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)); }
     }
     if( (phases & 4) && ctx->n_own )
     {
@@ -843,8 +867,17 @@ int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int np
       int rc;
       const int lmode = ctx->sub_valid(rcut, false) ? LIST_SUB : LIST_FULL;
       // the cached rho'(r) is only good for the parameter set that produced it
-      const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == 2 && std::memcmp(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)) == 0;
+      const bool pwi = lmode == LIST_SUB && ctx->sub_pw_kind == pw_kind && std::memcmp(ctx->sub_pw_johnson, params19, sizeof(ctx->sub_pw_johnson)) == 0;
       ctx->prof_begin(XSB_PROF_EAM_FORCE);
+      if( mixed )
+      {
+        const JohnsonPT<float> q = johnson_f32(p);
+        if( virial ) { if( pwi ) { JohnsonForceTileOp<true, true, float>   op{ rc2, q, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); }
+                       else      { JohnsonForceTileOp<true, false, float>  op{ rc2, q, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); } }
+        else         { if( pwi ) { JohnsonForceTileOp<false, true, float>  op{ rc2, q, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); }
+                       else      { JohnsonForceTileOp<false, false, float> op{ rc2, q, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); } }
+      }
+      else
       if( virial ) { if( pwi ) { JohnsonForceTileOp<true, true>   op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); }
                      else      { JohnsonForceTileOp<true, false>  op{ rc2, p, fx, fy, fz, ep, ctx->f64[XSB_F_VIRIAL].p }; rc = launch_tile_pass<8, 512>(ctx, false, op, emb, lmode); } }
       else         { if( pwi ) { JohnsonForceTileOp<false, true>  op{ rc2, p, fx, fy, fz, ep, nullptr }; rc = launch_tile_pass<16, 1024>(ctx, false, op, emb, lmode); }

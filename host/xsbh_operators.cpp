@@ -715,6 +715,7 @@ public:
     if (sim.preinit || phases == 0) return;
     need_gpu(sim, name);
     int fl = sim.compute_virial && sim.trigger_thermo_state ? XSB_FLAG_VIRIAL : 0;
+    if (sim.mixed_precision) fl |= XSB_FLAG_MIXED;      // xsb extension (global `enable_mixed_precision`): FP32 rho(r), phi(r), tolerance 1e-5
     sim.check(xsb_eam_analytic_force(sim.ctx, model, prm, int(names.size()), rcut, phases, fl), "xsb_eam_analytic_force");
   }
 };

@@ -207,6 +207,7 @@ typedef enum xsb_eam_model {
   XSB_EAM_SUTTON_CHEN = 1,  /* c, epsilon, a0, n, m (eam_potentials/sutton_chen/sutton_chen.h:24-62)                          */
   XSB_EAM_VNIITF = 2        /* rmax, rmin, rt0, Ecoh, E0, beta, A, Z, n, alpha, D, eta, mu (eam_potentials/vniitf/vniitf.h:31-125) */
 } xsb_eam_model;
+/* flags: XSB_FLAG_VIRIAL, XSB_FLAG_MIXED (FP32 rho(r) / phi(r), FP64 embedding function, distances and sums; 1e-5).      */
 int xsb_eam_analytic_force(xsb_ctx* ctx, int model, const double* params, int nparams, double rcut, int phases, int flags);
 
 /* a8  eam_alloy_force (eam_potential_multimat.cu:65-259, eam_alloy.h:37-313).                           */

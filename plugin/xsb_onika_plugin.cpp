@@ -291,6 +291,7 @@ namespace xsbplugin
     ADD_SLOT( exanb::GridChunkNeighbors , chunk_neighbors , INPUT , OPTIONAL );
     ADD_SLOT( GridT      , grid           , INPUT_OUTPUT );
     ADD_SLOT( Domain     , domain         , INPUT , REQUIRED );
+    ADD_SLOT( bool       , mixed_precision, INPUT , false );
   public:
     void execute() override final
     {
@@ -307,7 +308,7 @@ namespace xsbplugin
       bind_grid(c, *grid, *domain, true);
       const bool vir = grid->has_allocated_field(field::virial);
       XSB_CK(xsb_zero_force_energy(c, 1));
-      XSB_CK(xsb_eam_analytic_force(c, MODEL, p, int(names.size()), *rcut, PHASES, vir ? XSB_FLAG_VIRIAL : 0));
+      XSB_CK(xsb_eam_analytic_force(c, MODEL, p, int(names.size()), *rcut, PHASES, (vir ? XSB_FLAG_VIRIAL : 0) | (*mixed_precision ? XSB_FLAG_MIXED : 0)));
       add_forces_to_grid(c, *grid, vir);
     }
   };

@@ -1284,3 +1284,42 @@ def test_lj_operator_chained_behind_eam_joins_its_force_pass(tmp_path, monkeypat
         c.ghost_update([xsb.F_RHO_DEMB])
         c.eam_alloy_force(6.0, xsb.EAM_FORCE | ef, fl)
     assert rel_err(a.download(xsb.F_FX), b.download(xsb.F_FX)) < tol
+
+
+@pytest.mark.parametrize("name", ["johnson"] + sorted(EAM1_CASES))
+@pytest.mark.parametrize("virial,two_step", [(False, True), (True, False)])
+def test_eam_analytic_models_mixed_precision(name, virial, two_step):
+    """XSB_FLAG_MIXED on johnson / sutton_chen / vniitf (FP32 rho(r), phi(r); FP64 F(rho), distances, sums): 1e-5 against the
+    FP64 oracle, really computed in FP32 (differs from the FP64 pass), and an FP64 force pass never consumes the rho'(r) an
+    FP32 emb pass cached"""
+    model, p, rcut, nbh = (xsb.EAM_JOHNSON, johnson_params(), 5.5, 6.5) if name == "johnson" else EAM1_CASES[name]
+    O = oracle()
+    gs = system(ncells=5, a=3.615, sigma=0.05, cell=3.615, gl=4)
+    g = gs.oracle_grid()
+    nb = O.Neighbors.build(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nbh, 1, True)
+    fx, fy, fz, ep, emb = gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros(), gs.zeros()
+    vir = np.zeros((gs.n, 9)) if virial else None
+    O.eam_analytic(g, gs.cell_off, gs.rx, gs.ry, gs.rz, nb, model, p, rcut, 7, fx, fy, fz, ep, vir, emb)
+    ctx = make_ctx(gs)
+    ctx.chunk_neighbors(nbh)
+    fl = (xsb.FLAG_VIRIAL if virial else 0) | xsb.FLAG_MIXED
+    ctx.zero_force_energy(ghost=True)
+    if two_step:
+        ctx.eam_analytic_force(model, p, rcut, 3, fl)
+        ctx.eam_analytic_force(model, p, rcut, 4, fl)
+    else:
+        ctx.eam_analytic_force(model, p, rcut, 7, fl)
+    got = {f: ctx.download(f).copy() for f in (xsb.F_RHO_DEMB, xsb.F_FX, xsb.F_FY, xsb.F_FZ, xsb.F_EP)}
+    errs = [rel_err(got[f], ref) for f, ref in ((xsb.F_RHO_DEMB, emb), (xsb.F_FX, fx), (xsb.F_FY, fy), (xsb.F_FZ, fz), (xsb.F_EP, ep))]
+    print("%s mixed: max rel err rho_dEmb,fx,fy,fz,ep = %s" % (name, ["%.2e" % e for e in errs]))
+    assert max(errs) < TOLMIX
+    assert max(errs) > 1e-9                                            # FP32 arithmetic really ran
+    if virial:
+        assert rel_err(ctx.download(xsb.F_VIRIAL), vir) < TOLMIX
+    # FP32 emb pass, then an FP64 force pass on the oracle's F'(rho): the pass must re-evaluate rho'(r) itself instead of
+    # taking the FP32 values the emb pass cached -- then its forces are the oracle's to 1e-10
+    ctx.zero_force_energy(ghost=True)
+    ctx.eam_analytic_force(model, p, rcut, 3, xsb.FLAG_MIXED)
+    ctx.upload(xsb.F_RHO_DEMB, emb)
+    ctx.eam_analytic_force(model, p, rcut, 4, 0)
+    assert rel_err(ctx.download(xsb.F_FX), fx) < TOL64
