@@ -178,6 +178,87 @@ __device__ __forceinline__ double lds_f64_16(unsigned addr) { double v; asm vola
 // farther away is classified correctly by a wide margin.  The resulting list is bit-identical to the all-FP64 sweep.
 struct NbrF32 { float m[9]; float d2max, band; int xform; };
 
+// count sweep of NA (1 or 2) consecutive atoms of ONE cell: the word descriptor and the candidate's coordinates are loaded once
+// per word and tested against both central atoms (issue-bound loop: 39 -> ~31 instructions per atom and word)
+template<int NA, bool XFORM>
+__device__ __forceinline__ void nbr_count_atoms(const NbrWords& W, const unsigned a0, const unsigned sbase, const unsigned lane12, const unsigned c_off, const unsigned lane,
+                                                const float lo_sure, const float hi_sure, const float hi_out, const NbrF32& F, const GridView& gv, const double d2max,
+                                                const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                                unsigned* __restrict__ counts, unsigned* __restrict__ masks, const unsigned mask_stride, float& dmin_f)
+{
+  const unsigned nw = W.n;
+  unsigned ada[NA], cnt[NA]; float xa[NA], ya[NA], za[NA]; unsigned* mrow[NA];
+# pragma unroll
+  for(int i = 0; i < NA; i++)
+  {
+    ada[i] = sbase + 12u * (a0 + unsigned(i) + c_off);
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xa[i]) : "r"(ada[i]));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(ya[i]) : "r"(ada[i]));
+    asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(za[i]) : "r"(ada[i]));
+    cnt[i] = 0;
+    mrow[i] = masks + size_t(a0 + unsigned(i)) * mask_stride;
+  }
+  const unsigned wsc = smem_u32(&W.sc[0]);
+  for(unsigned q0 = 0; q0 < nw; q0 += 32u)
+  {
+    const unsigned qe = min(32u, nw - q0);
+    unsigned held[NA];
+#   pragma unroll
+    for(int i = 0; i < NA; i++) held[i] = 0;
+    for(unsigned tq = 0; tq < qe; tq++)
+    {
+      unsigned ws, wc;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ws), "=r"(wc) : "r"(wsc + 8u * (q0 + tq)));
+      // branch-free body: lanes past the end of the word read a valid slot and are masked out
+      const unsigned ad = lane12 + 12u * ws;
+      float cx, cy, cz;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cx) : "r"(ad));
+      asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(cy) : "r"(ad));
+      asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(cz) : "r"(ad));
+      float d2f[NA]; bool keep[NA], maybe[NA]; bool any_maybe = false;
+#     pragma unroll
+      for(int i = 0; i < NA; i++)
+      {
+        float dx = cx - xa[i], dy = cy - ya[i], dz = cz - za[i];
+        if( XFORM )
+        {
+          const float x = F.m[0] * dx + F.m[1] * dy + F.m[2] * dz, y = F.m[3] * dx + F.m[4] * dy + F.m[5] * dz, z = F.m[6] * dx + F.m[7] * dy + F.m[8] * dz;
+          dx = x; dy = y; dz = z;
+        }
+        d2f[i] = dx * dx + dy * dy + dz * dz;
+        const bool valid = (lane < wc) & (ad != ada[i]);
+        keep[i] = valid & (d2f[i] >= lo_sure) & (d2f[i] < hi_sure);
+        maybe[i] = valid & !keep[i] & (d2f[i] <= hi_out);
+        any_maybe |= maybe[i];
+      }
+      if( __any_sync(0xffffffffu, any_maybe) )
+      {
+        // guard band (rare): the exact FP64 test in the reference's operation order decides
+#       pragma unroll
+        for(int i = 0; i < NA; i++)
+          if( maybe[i] )
+          {
+            const unsigned b = W.g[q0 + tq] + lane, a = a0 + unsigned(i);
+            const double d2 = nbh_d2<XFORM>(gv, rx[b] - rx[a], ry[b] - ry[a], rz[b] - rz[a]);
+            keep[i] = d2 > 0.0 && d2 < d2max;
+          }
+      }
+#     pragma unroll
+      for(int i = 0; i < NA; i++)
+      {
+        dmin_f = fminf(dmin_f, keep[i] ? d2f[i] : 3.0e38f);
+        const unsigned m = __ballot_sync(0xffffffffu, keep[i]);
+        cnt[i] += __popc(m);
+        held[i] = tq == lane ? m : held[i];
+      }
+    }
+#   pragma unroll
+    for(int i = 0; i < NA; i++) if( lane < qe ) mrow[i][q0 + lane] = held[i];          // up to 32 words -> one coalesced store
+  }
+# pragma unroll
+  for(int i = 0; i < NA; i++) if( lane == 0 ) counts[a0 + unsigned(i)] = cnt[i];
+}
+
 template<bool XFORM>
 __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv, double d2max, NbrF32 F, const unsigned* __restrict__ cell_start,
                                                          const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
@@ -213,62 +294,23 @@ __global__ void __launch_bounds__(256) nbr_count_kernel(TileGeom G, GridView gv,
   asm volatile("" : "+r"(sbase), "+f"(lo_sure), "+f"(hi_sure), "+f"(hi_out));
   const unsigned lane12 = sbase + 12u * lane;
   float dmin_f = 3.0e38f;            // smallest FP32 d2 among the kept pairs (sizes the EAM table window: a bound within 1e-3 is enough)
-  for(unsigned a = M.a_begin + warp; a < a_end; a += nwarps)
+  // a warp takes two consecutive atoms at a time; a pair that straddles two cells of the tile (different word tables) is
+  // swept one atom after the other
+  for(unsigned a = M.a_begin + 2u * warp; a < a_end; a += 2u * nwarps)
   {
     unsigned t = 0;                                    // cell of the tile that holds atom a (warp-uniform)
     while( t + 1 < ncell && a >= Wc[t].a_end ) ++t;
-    const NbrWords& W = Wc[t];
-    const unsigned nw = W.n;
-    const unsigned ada = sbase + 12u * (a + c_off);
-    float xa, ya, za;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xa) : "r"(ada));
-    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(ya) : "r"(ada));
-    asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(za) : "r"(ada));
-    unsigned cnt = 0;
-    unsigned* mrow = masks + size_t(a) * mask_stride;
-    const unsigned wsc = smem_u32(&W.sc[0]);
-    for(unsigned q0 = 0; q0 < nw; q0 += 32u)
+    if( a + 1u < Wc[t].a_end )
+      nbr_count_atoms<2, XFORM>(Wc[t], a, sbase, lane12, c_off, lane, lo_sure, hi_sure, hi_out, F, gv, d2max, rx, ry, rz, counts, masks, mask_stride, dmin_f);
+    else
     {
-      const unsigned qe = min(32u, nw - q0);
-      unsigned held = 0;
-      for(unsigned tq = 0; tq < qe; tq++)
+      nbr_count_atoms<1, XFORM>(Wc[t], a, sbase, lane12, c_off, lane, lo_sure, hi_sure, hi_out, F, gv, d2max, rx, ry, rz, counts, masks, mask_stride, dmin_f);
+      if( a + 1u < a_end )
       {
-        unsigned ws, wc;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ws), "=r"(wc) : "r"(wsc + 8u * (q0 + tq)));
-        // branch-free body: lanes past the end of the word read a valid slot and are masked out
-        const unsigned ad = lane12 + 12u * ws;
-        float dx, dy, dz;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dx) : "r"(ad));
-        asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(dy) : "r"(ad));
-        asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(dz) : "r"(ad));
-        dx -= xa; dy -= ya; dz -= za;
-        if( XFORM )
-        {
-          const float x = F.m[0] * dx + F.m[1] * dy + F.m[2] * dz, y = F.m[3] * dx + F.m[4] * dy + F.m[5] * dz, z = F.m[6] * dx + F.m[7] * dy + F.m[8] * dz;
-          dx = x; dy = y; dz = z;
-        }
-        const float d2f = dx * dx + dy * dy + dz * dz;
-        const bool valid = (lane < wc) & (ad != ada);
-        bool keep = valid & (d2f >= lo_sure) & (d2f < hi_sure);
-        const bool maybe = valid & !keep & (d2f <= hi_out);
-        if( __any_sync(0xffffffffu, maybe) )
-        {
-          // guard band (rare): the exact FP64 test in the reference's operation order decides
-          if( maybe )
-          {
-            const unsigned b = W.g[q0 + tq] + lane;
-            const double d2 = nbh_d2<XFORM>(gv, rx[b] - rx[a], ry[b] - ry[a], rz[b] - rz[a]);
-            keep = d2 > 0.0 && d2 < d2max;
-          }
-        }
-        dmin_f = fminf(dmin_f, keep ? d2f : 3.0e38f);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        cnt += __popc(m);
-        held = tq == lane ? m : held;
+        while( t + 1 < ncell && a + 1u >= Wc[t].a_end ) ++t;
+        nbr_count_atoms<1, XFORM>(Wc[t], a + 1u, sbase, lane12, c_off, lane, lo_sure, hi_sure, hi_out, F, gv, d2max, rx, ry, rz, counts, masks, mask_stride, dmin_f);
       }
-      if( lane < qe ) mrow[q0 + lane] = held;          // up to 32 words -> one coalesced store
     }
-    if( lane == 0 ) counts[a] = cnt;
   }
 # pragma unroll
   for(int o = 16; o > 0; o >>= 1) dmin_f = fminf(dmin_f, __shfl_xor_sync(0xffffffffu, dmin_f, o));

@@ -1,0 +1,12 @@
+#!/bin/bash
+TAG=${1:-r02y3}
+O=gpurun_out; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_tests.log 2>&1; echo "tests rc=$?" >> $O/${TAG}_tests.log
+timeout 900 python bench.py --steps 40 --warmup 5 --no-cpu --no-e2e --no-mixed > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
+timeout 900 python bench.py --workload c1 --steps 100 --warmup 10 --no-cpu --no-e2e --no-mixed > $O/${TAG}_bench_c1.json 2> $O/${TAG}_bench_c1.err
+timeout 900 python bench.py --workload c5 --steps 20 --warmup 5 --no-cpu --no-e2e --no-mixed > $O/${TAG}_bench_c5.json 2> $O/${TAG}_bench_c5.err
+tail -4 $O/${TAG}_tests.log
+for f in $O/${TAG}_bench.json $O/${TAG}_bench_c1.json $O/${TAG}_bench_c5.json; do [ -f $f ] && (echo "== $f"; python -c "
+import json; d=json.loads(open('$f').read()); print(d['value'], d['ms_per_step'], {k: round(v['ms_total']/v['intervals'],3) for k,v in d['detail']['breakdown'].items()}, d['detail']['force_checksum_sum_abs'])"); done
+tail -n 3 $O/${TAG}_bench.err
+exit 0
