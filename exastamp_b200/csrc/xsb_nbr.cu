@@ -205,6 +205,7 @@ __device__ __forceinline__ void nbr_count_atoms(const NbrWords& W, const unsigne
     unsigned held[NA];
 #   pragma unroll
     for(int i = 0; i < NA; i++) held[i] = 0;
+#   pragma unroll 2
     for(unsigned tq = 0; tq < qe; tq++)
     {
       unsigned ws, wc;
@@ -231,25 +232,35 @@ __device__ __forceinline__ void nbr_count_atoms(const NbrWords& W, const unsigne
         maybe[i] = valid & !keep[i] & (d2f[i] <= hi_out);
         any_maybe |= maybe[i];
       }
+      unsigned m[NA];
+#     pragma unroll
+      for(int i = 0; i < NA; i++)
+      {
+        if( keep[i] ) dmin_f = fminf(dmin_f, d2f[i]);
+        m[i] = __ballot_sync(0xffffffffu, keep[i]);
+      }
       if( __any_sync(0xffffffffu, any_maybe) )
       {
-        // guard band (rare): the exact FP64 test in the reference's operation order decides
+        // guard band (rare): the exact FP64 test in the reference's operation order decides; its survivors join the mask
 #       pragma unroll
         for(int i = 0; i < NA; i++)
+        {
+          bool ex = false;
           if( maybe[i] )
           {
             const unsigned b = W.g[q0 + tq] + lane, a = a0 + unsigned(i);
             const double d2 = nbh_d2<XFORM>(gv, rx[b] - rx[a], ry[b] - ry[a], rz[b] - rz[a]);
-            keep[i] = d2 > 0.0 && d2 < d2max;
+            ex = d2 > 0.0 && d2 < d2max;
+            if( ex ) dmin_f = fminf(dmin_f, d2f[i]);
           }
+          m[i] |= __ballot_sync(0xffffffffu, ex);
+        }
       }
 #     pragma unroll
       for(int i = 0; i < NA; i++)
       {
-        dmin_f = fminf(dmin_f, keep[i] ? d2f[i] : 3.0e38f);
-        const unsigned m = __ballot_sync(0xffffffffu, keep[i]);
-        cnt[i] += __popc(m);
-        held[i] = tq == lane ? m : held[i];
+        cnt[i] += __popc(m[i]);
+        held[i] = tq == lane ? m[i] : held[i];
       }
     }
 #   pragma unroll
