@@ -64,6 +64,11 @@ static int run(const std::string& deck_path, const std::vector<std::pair<std::st
   graph->execute(sim);
   if (trace && sim.rank == 0) { std::printf("trace:"); for (auto& o : sim.trace) std::printf(" %s", o.c_str()); std::printf("\n"); }
   if (sim.ctx) sim.check(xsb_sync(sim.ctx), "xsb_sync");
+  if (trace && sim.ctx && sim.rank == 0) {
+    // operator chains served in one pass (a Lennard-Jones operator behind eam_alloy_force, xsb200.h: xsb_chain_stats)
+    uint64_t fused = 0; sim.check(xsb_chain_stats(sim.ctx, &fused), "xsb_chain_stats");
+    std::printf("fused_pair_operators: %llu\n", (unsigned long long)fused);
+  }
   return 0;
 }
 

@@ -63,6 +63,7 @@ struct Simulation {
   bool trigger_thermo_state = true;     // energy step: force operators accumulate ep (and virial)
   bool compute_virial = false;          // grid flavor carries field::virial
   bool mixed_precision = false;         // xsb extension: XSB_FLAG_MIXED for the pair operators and eam_alloy_force
+  std::string eam_alloy_loaded;         // setfl file whose tables the context holds (xsb_eam_alloy_set)
   std::map<std::string, bool> flags;    // trigger_move_particles, md_loop_continue, ...
   std::map<std::string, Node> shared_slots;   // graph-level named values connected to slots by `rebind`
   ThermoState thermo;

@@ -735,7 +735,6 @@ XSBH_EAM1_OPS(vniitf, XSB_EAM_VNIITF)
 class EamAlloyForce : public Operator {
 public:
   bool init_only;
-  std::string loaded;
   explicit EamAlloyForce(bool i) : init_only(i) {}
   void execute(Simulation& sim) override {
     TRACE(sim);
@@ -752,7 +751,9 @@ public:
     if (sim.preinit) return;
     need_gpu(sim, name);
     std::string path = sim.data_path(file);
-    if (loaded != path) {
+    // the tables live in the context: the instances of one graph (eam_alloy_init, eam_rho, eam_rho2emb, eam_force) share them;
+    // uploading the same file again would also drop the per-pair cache the rho phase left for the force phase
+    if (sim.eam_alloy_loaded != path) {
       xsb_eam_alloy_tables t{};
       char names[512];
       int rc = xsb_eam_alloy_read(path.c_str(), &t, names, sizeof(names));
@@ -765,7 +766,7 @@ public:
       rc = xsb_eam_alloy_set(sim.ctx, &t);
       xsb_eam_alloy_free(&t);
       sim.check(rc, "xsb_eam_alloy_set");
-      loaded = path;
+      sim.eam_alloy_loaded = path;
     }
     if (init_only) return;
     int phases = (rho ? XSB_EAM_RHO : 0) | (r2e ? XSB_EAM_RHO2EMB : 0) | (ghost ? XSB_EAM_GHOST : 0) | (force ? XSB_EAM_FORCE : 0);

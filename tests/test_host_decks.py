@@ -317,6 +317,37 @@ def test_eam_alloy_deck_matches_oracle_and_conserves_energy(tmp_path):
 
 
 @pytest.mark.gpu
+def test_eam_alloy_lj_chain_deck_is_fused_and_matches_oracle(tmp_path):
+    """compute_force: [eam_rho, eam_rho2emb, ghost_update_opt, eam_force, lj_multi_force] (configs[4]): the deck runs the
+    operators one by one, the library evaluates lj_multi_force inside the EAM force pass -- forces and energies are the
+    oracle's sum of both operators, with and without XSB_NO_CHAIN_FUSION"""
+    setfl = write_setfl(str(tmp_path / "synthetic_CuXx.eam.alloy"), [SC_CU, SC_XX], nrho=2000, drho=0.1, nr=2000, rc=6.0)
+    deck = os.path.join(DECKS, "eam_alloy_lj_chain.msp")
+    p = run(deck, "--data-dir", tmp_path, "--trace", cwd=tmp_path)
+    assert int(re.search(r"^fused_pair_operators: (\d+)$", p.stdout, re.M).group(1)) >= 1
+    d = read_dump(tmp_path / "eam_alloy_lj.xsbdump")
+    O, gs, g, nb = oracle_system(d, 7.0)
+    eam = O.EamAlloy(setfl)
+    fx, fy, fz, ep, emb = [gs.zeros() for _ in range(5)]
+    own = ~gs.is_ghost
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, 6.0, 1 | 2 | 16, fx, fy, fz, ep, None, emb)
+    owner_of = np.zeros(len(d["id"]), dtype=np.int64); owner_of[gs.src_index[own]] = np.nonzero(own)[0]
+    emb[:] = emb[owner_of[gs.src_index]]
+    O.eam_alloy(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, eam, 6.0, 8 | 16, fx, fy, fz, ep, None, emb)
+    J = 1.0 / 1.602176634e-19 * EV
+    rows = []                                        # unique_pair_id order (0,0), (0,1), (1,1); Cu = 0, Xx = 1; (0,0) <- common_parameters
+    for e, s, rc in ((0.0, 0.0, 5.9), (4.853e-20 * J, 2.36, 5.50), (2.522e-20 * J, 2.44, 5.90)):
+        q6 = (s / rc) ** 6
+        rows.append([e, s, rc, 4 * e * (q6 * q6 - q6)])
+    O.pair_multi_force(g, gs.cell_off, gs.rx, gs.ry, gs.rz, gs.type, nb, np.array(rows), 5.9, 0, fx, fy, fz, ep, None)
+    compare(d, gs, [63.546, 26.982], fx, fy, fz, ep)
+    env = dict(os.environ, XSB_NO_CHAIN_FUSION="1")
+    q = subprocess.run([RUN, deck, "--data-dir", str(tmp_path), "--trace"], capture_output=True, text=True, cwd=tmp_path, timeout=600, env=env)
+    assert q.returncode == 0 and re.search(r"^fused_pair_operators: 0$", q.stdout, re.M)
+    compare(read_dump(tmp_path / "eam_alloy_lj.xsbdump"), gs, [63.546, 26.982], fx, fy, fz, ep)
+
+
+@pytest.mark.gpu
 def test_johnson_deck_matches_oracle(tmp_path):
     run(os.path.join(DECKS, "johnson_single_specy.msp"), cwd=tmp_path)
     d = read_dump(tmp_path / "johnson.xsbdump")
