@@ -518,7 +518,8 @@ def run_xsb(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
     W = WORKLOADS[args.workload]()
-    W.inner_skin = args.inner_skin
+    # measured optima (profiles/r02k_skin_*: c2 0.12; profiles/r02y8_*: c5 0.28 -- light Al atoms spend the budget faster)
+    W.inner_skin = args.inner_skin if args.inner_skin >= 0.0 else {"c5": 0.28}.get(W.name, 0.12)
     if W.strong_total and args.scaling != "strong":
         args.scaling = "strong"
     torch.cuda.set_device(local)
@@ -856,7 +857,7 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-cells", type=int, default=0, help="unit cells per axis of the CPU arm's system (default: the full configuration for --impl reference)")
-    ap.add_argument("--inner-skin", type=float, default=0.12, help="inner skin (angstrom) of eam_alloy_force's in-range sub-list: 0 re-filters the neighbour list every step (xsb_eam_inner_skin)")
+    ap.add_argument("--inner-skin", type=float, default=-1.0, help="inner skin (angstrom) of eam_alloy_force's in-range sub-list: 0 re-filters the neighbour list every step (xsb_eam_inner_skin); default: 0.12, c5 0.28")
     ap.add_argument("--sync-displ", action="store_true", help="blocking particle_displ_over read-back every step (xsb_verlet_boundary) instead of the one-step-late check")
     ap.add_argument("--separate-integrator", action="store_true", help="five integrator operators as separate kernels instead of xsb_verlet_boundary")
     ap.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"], help="rewrite a 160 MiB buffer between timed steps; auto: on for c1, whose working set fits the 126 MB L2")
