@@ -280,6 +280,15 @@ class AlloyNPT(EamCu):
     def kernels(self):
         return ["eam_rho", "eam_force", "pair"]
 
+    def model(self, n_l, n_c):
+        m = EamCu.model(self, n_l, n_c)
+        # the force pass also evaluates the chained lj_multi_force (one reciprocal + ~12 FP64 operations per pair inside its cut-off)
+        m["eam_force"] = dict(m["eam_force"], flops=m["eam_force"]["flops"] + 14 * n_c * (6.10 / self.rcut) ** 3,
+                              kernel="tile_pass_kernel<16,1024,LIST_SUB,EamForceTileOp<MULTI,CHAIN>> (eam_alloy_force force phase + the lj_multi_force chained behind it; "
+                                     "without the fusion: XSB_NO_CHAIN_FUSION=1, separate LJTileOp pass under the `pair` tag)")
+        m["pair"] = dict(bytes=24 + 1 + 32 + 2 * (1 + 2 * 27 + n_l), flops=8 * n_l + 30 * n_c * (6.10 / self.rcut) ** 3, kernel="tile_pass_kernel<16,1024,LIST_SUB,LJTileOp<MULTI>> (lj_multi_force on its own)")
+        return m
+
     def cpu_forces(self, O, g, gs, nb, arr, img):
         EamCu.cpu_forces(self, O, g, gs, nb, arr, img)
         fx, fy, fz, ep, emb = arr
