@@ -666,13 +666,9 @@ int xsb_chunk_neighbors_build(xsb_ctx* ctx, double nbh_dist_lab, const xsb_chunk
     TG.ntiles = unsigned(TG.ti_n) * unsigned(TG.j_n) * unsigned(TG.k_n); TG.nbuf = 1;
     tile_smem = (size_t(s_cap) + 32) * 12;      // + 32 slots: lanes past the end of the last word read (and discard) them
     const NbrF32 F32 = nbr_fp32_band(ctx->grid, TG.TX, R, nbh_dist_lab);
-    static bool attr_done = false;
-    if( !attr_done )
-    {
-      cudaFuncSetAttribute(nbr_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(nbr_count_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_done = true;
-    }
+    // per device and cheap: set on every build rather than behind a process-global flag (several contexts / GPUs per process)
+    cudaFuncSetAttribute(nbr_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(nbr_count_kernel<true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     // survivor masks of the count sweep (one word per 32-candidate step), replayed by nbr_expand_kernel
     mask_stride = ((s_cap + 31u) / 32u + unsigned((2 * R[1] + 1) * (2 * R[2] + 1)) + 31u) & ~31u;
     XSB_CUDA(ctx, ctx->nbh_masks.reserve(size_t(n) * mask_stride + 32, XSB_GROW));
