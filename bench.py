@@ -483,6 +483,22 @@ def _cpu_reference_run(O, L, flags, nthr, W, ucells, steps, warmup, rebuild_ever
                                     "cpu_model": model, "compiler": cc, "flags": flags}
 
 
+def cpu_arm_sample_cells(W, full, steps, warmup, threads, forced=0):
+    """0 = time the full configuration `full` (unit cells per axis of the whole N-GPU system), else the edge (unit cells) of
+    the cube timed instead.  The full configuration is timed whenever warmup + steps force steps of it fit ~4 minutes on
+    this host (per-thread rates of the restatement measured on the round's boxes, profiles/r02zz_*); otherwise -- SNAP at
+    2J = 8 always (~0.2 s per 1000 atoms and core), a 16 M-atom system with a long step count -- a cube of the same lattice /
+    potential / cutoffs sized to that budget, which the caller names in config.workload."""
+    per_cell = 2 if W.structure == "BCC" else 4
+    atoms_full = per_cell * full[0] * full[1] * full[2]
+    rate = {"c1": 6.0e5, "c2": 1.8e5, "c4": 1.8e5, "c2j": 1.1e5, "c5": 1.4e5, "c3": 2.8e2}.get(W.name, 1.0e5) * threads
+    est_s = atoms_full * (steps + warmup + 2) / rate
+    if not (forced or W.name == "c3" or est_s > 240.0):
+        return 0
+    sc = forced or (24 if W.name == "c3" else max(16, int((240.0 * rate / (steps + warmup + 2) / per_cell) ** (1.0 / 3.0))))
+    return min(sc, min(full))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -498,17 +514,8 @@ def run_reference(args):
     sample_note = None
     ucells = full
     cell, _, _ = domain_cells(W, args.scaling, np.asarray(uc, dtype=np.float64) * W.a, rd)      # the GPU arm's cell size
-    # The full configuration is timed whenever warmup + steps force steps of it fit ~4 minutes on this host (per-thread rates of
-    # the restatement measured on the round's boxes, profiles/r02zz_*); otherwise -- SNAP at 2J = 8 always (~0.2 s per 1000 atoms
-    # and core), a 16 M-atom system with a long step count -- a cube of the same lattice / potential / cutoffs sized to that
-    # budget is timed instead and named in config.workload.
-    per_cell = 2 if W.structure == "BCC" else 4
-    atoms_full = per_cell * full[0] * full[1] * full[2]
-    rate = {"c1": 6.0e5, "c2": 1.8e5, "c4": 1.8e5, "c2j": 1.1e5, "c5": 1.4e5, "c3": 2.8e2}.get(W.name, 1.0e5) * (os.cpu_count() or 1)
-    est_s = atoms_full * (args.steps + args.warmup + 2) / rate
-    if args.cpu_sample_cells or W.name == "c3" or est_s > 240.0:
-        sc = args.cpu_sample_cells or (24 if W.name == "c3" else max(16, int((240.0 * rate / (args.steps + args.warmup + 2) / per_cell) ** (1.0 / 3.0))))
-        sc = min(sc, min(full))
+    sc = cpu_arm_sample_cells(W, full, args.steps, args.warmup, os.cpu_count() or 1, args.cpu_sample_cells)
+    if sc:
         ucells, cell = [sc] * 3, None
         sample_note = "bounded sample: %d^3 unit cells of the same lattice / potential / cutoffs" % sc
     value, info = cpu_reference_run(W, ucells, args.steps, args.warmup, args.rebuild_every, cell)

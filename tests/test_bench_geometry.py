@@ -44,3 +44,17 @@ def test_cpu_arm_runs_every_workload_on_a_small_sample(wl, cells):
     W = bench.WORKLOADS[wl]()
     v, info = bench.cpu_reference_run(W, cells, 1, 0, 20)
     assert v > 0 and info["atoms"] == (2 if W.structure == "BCC" else 4) * cells ** 3 and info["threads"] >= 1
+
+
+def test_cpu_arm_times_the_full_configuration_unless_it_cannot_fit_its_budget():
+    """--impl reference: the stated configuration at the driver's step counts (N = 1 and N = 8), SNAP and over-long runs on a
+    labelled cube that is smaller than the configuration"""
+    c2 = bench.WORKLOADS["c2"]()
+    assert bench.cpu_arm_sample_cells(c2, [79, 79, 79], 20, 5, 16) == 0
+    assert bench.cpu_arm_sample_cells(c2, [158, 158, 158], 20, 5, 32) == 0            # 15.8 M atoms, 27 steps: ~75 s on 32 cores
+    sc = bench.cpu_arm_sample_cells(c2, [158, 158, 158], 100, 10, 16)
+    assert 16 <= sc < 158
+    assert 4 * sc ** 3 * 112 / (1.8e5 * 16) <= 240.0 * 1.01
+    assert bench.cpu_arm_sample_cells(bench.WORKLOADS["c3"](), [63, 63, 63], 3, 1, 64) == 24
+    assert bench.cpu_arm_sample_cells(c2, [79, 79, 79], 20, 5, 16, forced=40) == 40
+    assert bench.cpu_arm_sample_cells(c2, [12, 12, 12], 20, 5, 16, forced=40) == 12
